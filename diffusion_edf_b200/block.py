@@ -1,0 +1,98 @@
+"""Equiformer blocks of the key encoder (UNet) and of the tensor field.
+
+Mirrors /root/reference/diffusion_edf/block.py:64-174 (``EquiformerBlock`` used by the
+UNet; note the reference computes ``norm_1_src`` / ``norm_1_dst`` and discards the
+result, :149-153 -- the linears see un-normalised inputs; preserved here) and
+/root/reference/diffusion_edf/gnn_block.py:65-218 (``EquiformerBlock`` of the score
+head's ``MultiscaleTensorField``).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from .irreps import Irreps
+from .layers import (EquivariantLayerNormV2, FeedForwardNetwork, GaussianRadialBasisLayerFiniteCutoff, GraphAttention,
+                     LinearRS, ProjectIfMismatch)
+
+
+def mlp_mid(irreps_emb: Irreps, mult) -> Irreps:
+    if isinstance(mult, int):
+        return irreps_emb * mult
+    return Irreps(mult)
+
+
+class UnetEquiformerBlock(nn.Module):
+    def __init__(self, irreps_src, irreps_dst, irreps_edge_attr, irreps_head, num_heads: int, fc_neurons: Sequence[int],
+                 irreps_mlp_mid=3, src_bias: bool = False, dst_bias: bool = True, **_ignored):
+        super().__init__()
+        self.irreps_src, self.irreps_dst = Irreps(irreps_src), Irreps(irreps_dst)
+        self.irreps_emb = self.irreps_dst
+        if Irreps(irreps_edge_attr).m != (1, 1, 1):
+            raise NotImplementedError("edge attributes must be the l<=2 spherical harmonics 1x0e+1x1e+1x2e")
+        self.norm_1_src = EquivariantLayerNormV2(self.irreps_src)      # parameters exist, output discarded (reference quirk)
+        self.linear_src = LinearRS(self.irreps_src, self.irreps_emb, bias=src_bias)
+        self.norm_1_dst = EquivariantLayerNormV2(self.irreps_dst)
+        self.linear_dst = LinearRS(self.irreps_dst, self.irreps_emb, bias=dst_bias)
+        self.ga = GraphAttention(self.irreps_emb, self.irreps_dst, fc_neurons, num_heads)
+        self.norm_2 = EquivariantLayerNormV2(self.irreps_dst)
+        self.ffn = FeedForwardNetwork(self.irreps_dst, self.irreps_dst, mlp_mid(self.irreps_emb, irreps_mlp_mid))
+
+    def forward(self, f_src: torch.Tensor, f_dst: torch.Tensor, g: ops.Csr, sh: torch.Tensor, length: torch.Tensor,
+                radial: GaussianRadialBasisLayerFiniteCutoff) -> torch.Tensor:
+        msg_src = self.linear_src(f_src)
+        msg_dst = self.linear_dst(f_dst)
+        # per-edge TP weights: RadialProfile(GaussianRadialBasisLayerFiniteCutoff(length))
+        rad = self.ga.sep_act.dtp_rad
+        E = max(1, g.n_edges)
+        w = torch.empty(E, self.ga.sep_act.numel, dtype=torch.float32, device=f_src.device)
+        d = L.MlpDesc()
+        d.mode = L.MLP_IN_RBF
+        d.n_edges_dev = L.ptr(g.n_edges_dev, torch.int32)
+        d.length = L.ptr(length)
+        mean, std, wl = radial.mean.detach().reshape(-1), radial.std_logit.detach().reshape(-1), radial.weight_logit.detach().reshape(-1)
+        d.rbf_mean, d.rbf_std_logit, d.rbf_weight_logit = L.ptr(mean), L.ptr(std), L.ptr(wl)
+        d.rbf_cutoff, d.rbf_offset = radial.cutoff, radial.offset
+        rad.fill_desc(d, 0)
+        d.out = L.ptr(w)
+        ops.edge_mlp(d, g.n_edges)
+        attn = self.ga.attend(msg_src, msg_dst, g, sh, w, None)
+        out = self.ga.proj(attn, res=f_dst)                          # node_output = node_input_dst + ga(...)
+        return self.ffn(out, ln=self.norm_2, res=out)                # + ffn(norm_2(node_output))
+
+
+class EquiformerBlock(nn.Module):
+    """The tensor-field block (no destination features: ``use_dst_feature=False`` in every shipped config)."""
+
+    def __init__(self, irreps_src, irreps_dst, irreps_edge_attr, num_heads: int, fc_neurons: Sequence[int], irreps_emb=None,
+                 irreps_output=None, irreps_mlp_mid=3, use_dst_feature: bool = True, skip_connection: bool = True,
+                 bias: bool = True, use_src_point_attn: bool = False, use_dst_point_attn: bool = False,
+                 use_edge_weights: bool = True, **_ignored):
+        super().__init__()
+        if use_dst_feature or use_src_point_attn or use_dst_point_attn or not use_edge_weights or not skip_connection:
+            raise NotImplementedError("only the edge-time-encoding tensor field (no dst features / point attention) is "
+                                      "implemented on the CUDA path")
+        self.irreps_src = Irreps(irreps_src)
+        self.irreps_emb = Irreps(irreps_emb) if irreps_emb is not None else Irreps(irreps_dst)
+        self.irreps_output = Irreps(irreps_output) if irreps_output is not None else Irreps(irreps_dst)
+        self.prenorm_src = EquivariantLayerNormV2(self.irreps_src)
+        self.linear_src = LinearRS(self.irreps_src, self.irreps_emb, bias=True)
+        self.skip_2 = ProjectIfMismatch(self.irreps_emb, self.irreps_output, bias=True, layernorm=False)
+        self.ga = GraphAttention(self.irreps_emb, self.irreps_emb, fc_neurons, num_heads)
+        self.post_norm = EquivariantLayerNormV2(self.irreps_emb)
+        self.ffn = FeedForwardNetwork(self.irreps_emb, self.irreps_output, mlp_mid(self.irreps_emb, irreps_mlp_mid))
+
+    def source_messages(self, f_src: torch.Tensor) -> torch.Tensor:
+        """linear_src(prenorm_src(f)): pose-independent, so callers may cache it per scene (gnn_block.py:170-171)."""
+        return self.linear_src(f_src, ln=self.prenorm_src)
+
+    def forward(self, msg_src: torch.Tensor, g: ops.Csr, sh: torch.Tensor, w: torch.Tensor,
+                edge_logit: torch.Tensor) -> torch.Tensor:
+        attn = self.ga.attend(msg_src, None, g, sh, w, edge_logit)
+        emb = self.ga.proj(attn)
+        skip = emb if self.skip_2.is_identity else self.skip_2(emb)
+        return self.ffn(emb, ln=self.post_norm, res=skip)

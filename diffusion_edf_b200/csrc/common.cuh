@@ -1,0 +1,85 @@
+// Shared device helpers for the Diffusion-EDF score-network kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dedf {
+
+// e3nn.math.normalize2mom constants (Monte-Carlo values of e3nn==0.4.4's recipe:
+// manual_seed(0), randn(1_000_000, float64)); used by fast_activation.py:69 in the
+// reference.  tests/test_constants.py checks them against the oracle's recomputation.
+constexpr float kCSilu = 1.6791767923989418f;
+constexpr float kCSigmoid = 1.8467055342154763f;
+constexpr float kCSlrelu = 1.531320475574866f;
+
+constexpr int kNumSMs = 148;  // B200
+
+enum : int {
+    DEDF_OK = 0,
+    DEDF_ERR_ARG = -1,       // bad argument (null pointer, unsupported irreps, ...)
+    DEDF_ERR_LAUNCH = -2,    // cudaGetLastError() after a launch
+    DEDF_ERR_UNSUPPORTED = -3,
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
+// SmoothLeakyReLU(0.2): 0.6 x + 0.4 x (2 sigmoid(x) - 1)   (fast_activation.py:14-23)
+__device__ __forceinline__ float slreluf_(float x) { return 0.6f * x + 0.4f * x * (2.0f * sigmoidf_(x) - 1.0f); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// soft_step(x, n=3) = 4x^3 - 3x^4 on (0,1), 0 below, 1 above   (radial_func.py:16-17)
+__device__ __forceinline__ float soft_step3(float x) {
+    if (x <= 0.0f) return 0.0f;
+    if (x >= 1.0f) return 1.0f;
+    float x3 = x * x * x;
+    return 4.0f * x3 - 3.0f * x3 * x;
+}
+
+// real spherical harmonics l<=2 of a UNIT vector, e3nn 'component' normalisation
+// (o3.SphericalHarmonics(normalize=True)).  sh[0..8].
+__device__ __forceinline__ void sph_harm_l2(float x, float y, float z, float* sh) {
+    const float s3 = 1.7320508075688772f, s5 = 2.23606797749979f, s15 = 3.872983346207417f;
+    sh[0] = 1.0f;
+    sh[1] = s3 * x;
+    sh[2] = s3 * y;
+    sh[3] = s3 * z;
+    sh[4] = s15 * x * z;
+    sh[5] = s15 * x * y;
+    sh[6] = s5 * (y * y - 0.5f * (x * x + z * z));
+    sh[7] = s15 * y * z;
+    sh[8] = 0.5f * s15 * (z * z - x * x);
+}
+
+// Feature layout of an irreps triple (m0 x0e + m1 x1e + m2 x2e), e3nn mul_ir order.
+struct Irr {
+    int m0, m1, m2;
+    __host__ __device__ int dim() const { return m0 + 3 * m1 + 5 * m2; }
+    __host__ __device__ int off1() const { return m0; }
+    __host__ __device__ int off2() const { return m0 + 3 * m1; }
+    __host__ __device__ int nirr() const { return m0 + m1 + m2; }
+};
+
+inline int grid_for(long long work_items, int per_block, int max_blocks) {
+    long long b = (work_items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+#define DEDF_CHECK_LAUNCH()                                         \
+    do {                                                            \
+        cudaError_t e__ = cudaGetLastError();                       \
+        if (e__ != cudaSuccess) return DEDF_ERR_LAUNCH;             \
+    } while (0)
+
+}  // namespace dedf

@@ -1,0 +1,860 @@
+// Per-edge kernels of the equivariant graph attention
+// (GraphAttentionMLP / GraphAttentionMLP2, /root/reference/diffusion_edf/graph_attention.py:84-122, :218-273):
+//
+//   edge_geom       vec / length / spherical harmonics / soft cut-offs          (graph_parser.py:146-224,
+//                                                                                unet_feature_extractor.py:284-288)
+//   edge_mlp        length (+time) embedding -> RadialProfile MLP -> per-edge TP weights
+//                                                                               (equiformer/radial_func.py:56-59,
+//                                                                                multiscale_tensor_field.py:225-234)
+//   edge_tp_lin     gather -> depthwise CG tensor product -> block-diagonal linear -> (alpha logits + gate | bias)
+//                   with the (E,1568) tensor-product output kept in shared memory  (graph_attention.py:231-246)
+//   segment_softmax_reduce   per-destination softmax over incoming edges + weighted sum (graph_attention.py:254-265)
+//   edge_tp_reduce  "K1": gather -> depthwise CG TP with per-edge weights -> x alpha_h -> segment reduce
+#include "common.cuh"
+#include "cg_slots.cuh"
+#include "gemm_tile.cuh"
+#include "../../include/dedf.h"
+
+namespace dedf {
+
+// ===========================================================================
+// edge geometry
+// ===========================================================================
+struct GeomArgs {
+    const float* x_src; const float* x_dst;
+    const int* edge_src; const int* edge_dst;
+    const int* n_edges;                 // device scalar
+    float* length; float* sh; float* logit;   // logit may be null
+    float ns_lo, ns_hi;                 // non-scalar SH min-cut range; ns_hi <= 0: none
+    int n_scales;
+    int src_off[DEDF_MAX_SCALES + 1];
+    float r[DEDF_MAX_SCALES];           // < 0: infinite scale (logit 0)
+};
+
+__global__ void __launch_bounds__(256) edge_geom_kernel(GeomArgs a) {
+    const int E = *a.n_edges;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const int s = a.edge_src[e], d = a.edge_dst[e];
+        const float vx = a.x_src[3 * s] - a.x_dst[3 * d];
+        const float vy = a.x_src[3 * s + 1] - a.x_dst[3 * d + 1];
+        const float vz = a.x_src[3 * s + 2] - a.x_dst[3 * d + 2];
+        const float len = sqrtf(vx * vx + vy * vy + vz * vz);
+        const float inv = 1.0f / fmaxf(len, 1e-12f);          // F.normalize
+        float sh[9];
+        sph_harm_l2(vx * inv, vy * inv, vz * inv, sh);
+        if (a.ns_hi > 0.f) {                                   // graph_parser.py:174-177, 199-204
+            const float c = soft_step3((len - a.ns_lo) / (a.ns_hi - a.ns_lo));
+#pragma unroll
+            for (int j = 1; j < 9; ++j) sh[j] *= c;
+        }
+        a.length[e] = len;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) a.sh[(size_t)e * 9 + j] = sh[j];
+        if (a.logit) {
+            int sc = 0;
+            while (sc + 1 < a.n_scales && s >= a.src_off[sc + 1]) ++sc;
+            const float r = a.r[sc];
+            float lg = 0.f;
+            if (r >= 0.f) {                                    // graph_parser.py:170-173, 206-215
+                const float cut = 1.0f - soft_step3((len - 0.8f * r) / (r - 0.8f * r));
+                lg = logf(fmaxf(cut, 1e-12f));
+            }
+            a.logit[e] = lg;
+        }
+    }
+}
+
+// ===========================================================================
+// edge MLP
+// ===========================================================================
+constexpr int kMlpTE = 64;          // edges per tile
+constexpr int kMlpThreads = 256;
+constexpr int kMlpMaxW = 128;       // widest hidden layer kept in shared memory
+
+struct MlpArgs {
+    int mode;                       // DEDF_MLP_IN_ROWS / _RBF / _FIELD
+    const int* n_edges;             // device scalar
+    // input
+    const float* x_in;              // ROWS: (E, K[0])
+    const float* length;            // RBF / FIELD
+    // RBF (GaussianRadialBasisLayerFiniteCutoff, radial_func.py:231-278)
+    const float* rbf_mean; const float* rbf_std_logit; const float* rbf_weight_logit;
+    float rbf_cutoff, rbf_offset;
+    // FIELD (graph_parser length encoders + edge_scalars_pre_linears, per scale)
+    int n_scales; int n_dst;        // edges of (scale s, dst d) = [row_ptr[s*n_dst+d], row_ptr[s*n_dst+d+1])
+    const int* row_ptr;
+    const int* edge_dst;
+    const float* enc_mean[DEDF_MAX_SCALES]; const float* enc_std_logit[DEDF_MAX_SCALES];
+    const float* enc_weight_logit[DEDF_MAX_SCALES];
+    float enc_r[DEDF_MAX_SCALES];   // < 0: sinusoidal encoder with max_val = enc_max_r, n = enc_n
+    float enc_max_r, enc_n;
+    const float* enc_freq;          // (K0/2) sinusoidal frequency table
+    const float* pre_w[DEDF_MAX_SCALES];   // (len_dim, K1) = W_s[:, :len_dim]^T
+    const float* row_bias;          // (n_scales, n_rb, K1): W_s[:, len_dim:] t_emb + b_s
+    int n_rb; int rb_div;           // row of row_bias = edge_dst / rb_div  (clamped to n_rb - 1)
+    // layers
+    int n_layers;
+    int K[DEDF_MLP_MAX_LAYERS + 1];
+    const float* W[DEDF_MLP_MAX_LAYERS];   // (K[i], K[i+1])
+    const float* b[DEDF_MLP_MAX_LAYERS];   // may be null
+    const float* ln_g[DEDF_MLP_MAX_LAYERS]; const float* ln_b[DEDF_MLP_MAX_LAYERS];
+    int flags[DEDF_MLP_MAX_LAYERS];        // 1: LayerNorm, 2: SiLU
+    const float* out_offset;        // added to the last layer (RadialProfile.offset), may be null
+    float* out;                     // (E, K[n_layers])
+};
+
+__device__ __forceinline__ float softplusf_(float x) { return (x > 20.f) ? x : log1pf(expf(x)); }
+
+__global__ void __launch_bounds__(kMlpThreads) edge_mlp_kernel(MlpArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int lda = pad_lda(kMlpMaxW);
+    float* buf0 = smem;
+    float* buf1 = smem + kMlpTE * lda;
+    const int tid = threadIdx.x;
+    const int E = *a.n_edges;
+
+    // tiles: FIELD mode keeps tiles inside one scale (first layer weights differ per scale)
+    int n_tiles = 0;
+    int tile_base[DEDF_MAX_SCALES + 1];
+    if (a.mode == DEDF_MLP_IN_FIELD) {
+        tile_base[0] = 0;
+        for (int s = 0; s < a.n_scales; ++s) {
+            const int es = a.row_ptr[(size_t)(s + 1) * a.n_dst] - a.row_ptr[(size_t)s * a.n_dst];
+            tile_base[s + 1] = tile_base[s] + (es + kMlpTE - 1) / kMlpTE;
+        }
+        n_tiles = tile_base[a.n_scales];
+    } else {
+        n_tiles = (E + kMlpTE - 1) / kMlpTE;
+    }
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int e0, e1, scale = 0;
+        if (a.mode == DEDF_MLP_IN_FIELD) {
+            while (tile >= tile_base[scale + 1]) ++scale;
+            const int sbeg = a.row_ptr[(size_t)scale * a.n_dst], send = a.row_ptr[(size_t)(scale + 1) * a.n_dst];
+            e0 = sbeg + (tile - tile_base[scale]) * kMlpTE;
+            e1 = min(e0 + kMlpTE, send);
+        } else {
+            e0 = tile * kMlpTE;
+            e1 = min(e0 + kMlpTE, E);
+        }
+        const int rows = e1 - e0;
+        const int K0 = a.K[0];
+        __syncthreads();   // previous tile's readers are done with buf0/buf1
+        // ---- stage the input tile into buf0 ---------------------------------
+        if (a.mode == DEDF_MLP_IN_ROWS) {
+            for (int i = tid; i < kMlpTE * K0; i += kMlpThreads) {
+                const int r = i / K0, k = i % K0;
+                buf0[r * lda + k] = (r < rows) ? a.x_in[(size_t)(e0 + r) * K0 + k] : 0.f;
+            }
+        } else if (a.mode == DEDF_MLP_IN_RBF) {
+            const float inv_span = 1.0f / (a.rbf_cutoff - a.rbf_offset);
+            const float normalizer = sqrtf((float)K0);
+            for (int i = tid; i < kMlpTE * K0; i += kMlpThreads) {
+                const int r = i / K0, k = i % K0;
+                float v = 0.f;
+                if (r < rows) {
+                    const float d = (a.length[e0 + r] - a.rbf_offset) * inv_span;
+                    const float std = softplusf_(a.rbf_std_logit[k]) + 1e-5f;
+                    const float z = (d - a.rbf_mean[k]) / std;
+                    v = expf(-0.5f * z * z) * (sigmoidf_(a.rbf_weight_logit[k]) * 4.0f);
+                    // soft_square_cutoff(d, thr=0.8, infinite=False): only the inner (d -> 0) edge is cut
+                    const float cut = (d > 0.5f) ? 1.0f : (1.0f - soft_step3(((1.0f - d) - 0.8f) / (1.0f - 0.8f)));
+                    v = v * cut * normalizer;
+                }
+                buf0[r * lda + k] = v;
+            }
+        } else {   // FIELD: length embedding of this scale
+            const float r_s = a.enc_r[scale];
+            for (int i = tid; i < kMlpTE * K0; i += kMlpThreads) {
+                const int r = i / K0, k = i % K0;
+                float v = 0.f;
+                if (r < rows) {
+                    const float len = a.length[e0 + r];
+                    if (r_s >= 0.f) {   // GaussianRadialBasis (radial_func.py:208-227)
+                        const float d = len / r_s;
+                        const float std = softplusf_(a.enc_std_logit[scale][k]) + 1e-5f;
+                        const float z = (d - a.enc_mean[scale][k]) / std;
+                        v = expf(-0.5f * z * z) * (sigmoidf_(a.enc_weight_logit[scale][k]) * (4.0f * sqrtf((float)K0)));
+                    } else {            // SinusoidalPositionEmbeddings (radial_func.py:291-316)
+                        const int half = K0 / 2;
+                        const int kk = (k < half) ? k : k - half;
+                        const float x = len / a.enc_max_r * a.enc_n;
+                        const float arg = __fmul_rn(x, a.enc_freq[kk]);
+                        v = (k < half) ? sinf(arg) : cosf(arg);
+                    }
+                }
+                buf0[r * lda + k] = v;
+            }
+        }
+        __syncthreads();
+
+        float* in = buf0;
+        float* outb = buf1;
+        for (int L = 0; L < a.n_layers; ++L) {
+            const int K = a.K[L], N = a.K[L + 1];
+            const bool last = (L == a.n_layers - 1);
+            const float* W = (a.mode == DEDF_MLP_IN_FIELD && L == 0) ? a.pre_w[scale] : a.W[L];
+            const int n_rg = kMlpTE / 4, n_cg = N / 4;
+            for (int item = tid; item < n_rg * n_cg; item += kMlpThreads) {
+                const int cg = item % n_cg, rg = item / n_cg;
+                float acc[4][4] = {};
+                gemm_item_4x4<true>(in, lda, n_rg, rg, W, N, 4 * cg, K, acc);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = rg + i * n_rg;
+                    if (r >= rows && last) continue;
+                    float v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = 4 * cg + j;
+                        float t = acc[i][j];
+                        if (a.b[L]) t += a.b[L][c];
+                        if (a.mode == DEDF_MLP_IN_FIELD && L == 0 && r < rows) {
+                            const int rb = min(a.edge_dst[e0 + r] / a.rb_div, a.n_rb - 1);
+                            t += a.row_bias[((size_t)scale * a.n_rb + rb) * N + c];
+                        }
+                        if (!(a.flags[L] & 1) && (a.flags[L] & 2)) t = siluf_(t);
+                        if (last && a.out_offset) t += a.out_offset[c];
+                        v[j] = t;
+                    }
+                    if (last) {
+                        *reinterpret_cast<float4*>(a.out + (size_t)(e0 + r) * N + 4 * cg) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+                        *reinterpret_cast<float4*>(outb + r * lda + 4 * cg) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                }
+            }
+            __syncthreads();
+            if (!last && (a.flags[L] & 1)) {   // LayerNorm (+SiLU) in place, 4 threads per row
+                const int r = tid >> 2, q = tid & 3;
+                float s = 0.f, ss = 0.f;
+                for (int c = q; c < N; c += 4) { const float t = outb[r * lda + c]; s += t; }
+                s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2);
+                const float mean = s / (float)N;
+                for (int c = q; c < N; c += 4) { const float t = outb[r * lda + c] - mean; ss += t * t; }
+                ss += __shfl_xor_sync(0xffffffffu, ss, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+                const float rstd = rsqrtf(ss / (float)N + 1e-5f);
+                for (int c = q; c < N; c += 4) {
+                    float t = (outb[r * lda + c] - mean) * rstd * a.ln_g[L][c] + a.ln_b[L][c];
+                    if (a.flags[L] & 2) t = siluf_(t);
+                    outb[r * lda + c] = t;
+                }
+                __syncthreads();
+            }
+            float* t = in; in = outb; outb = t;
+        }
+    }
+}
+
+// ===========================================================================
+// edge_tp_lin: gather -> depthwise TP -> block-diagonal linear -> epilogue
+// ===========================================================================
+struct TpLinArgs {
+    const float* x_src;      // (N_src, F) messages of the source nodes
+    const float* x_dst;      // (N_dst, F) or null: added to the gathered source message
+    const int* edge_src; const int* edge_dst;
+    const int* n_edges;      // device scalar
+    const float* sh;         // (E, 9)
+    const float* w; long long w_stride;   // per-edge TP weights (E, NUMEL), or shared (NUMEL,) with stride 0
+    const float* W0; const float* W1; const float* W2;   // (D0,N0) (D1,N1) (D2,N2)
+    const float* bias0;      // (N0) added to the 0e outputs (may be null)
+    // EPI_ACT
+    const float* alpha_dot;  // (H * Ma/H)
+    const float* edge_logit; // (E) or null
+    float* logits;           // (E, 4)
+    float* out;              // (E, F_out)
+    int per_edge_x;          // 1: x_src is (E, F) indexed by the edge itself (no gather)
+};
+
+enum { EPI_ACT = 0, EPI_LIN = 1 };
+
+template <int G, int EPI>
+struct TpLinCfg {
+    using D = Dtp<G>;
+    static constexpr int TE = 512 / G;                       // edges per tile (16 / 32)
+    static constexpr int MA = (EPI == EPI_ACT) ? D::M0 : 0;  // alpha channels (= mul of 0e in the heads irreps)
+    static constexpr int N0 = (EPI == EPI_ACT) ? (MA + D::M0 + D::M1 + D::M2) : D::M0;
+    static constexpr int N1 = D::M1, N2 = D::M2;
+    static constexpr int FO = D::M0 + 3 * D::M1 + 5 * D::M2;  // output feature dim (= F)
+    static constexpr int NITEMS = (TE / 4) * (N0 / 4) + (3 * TE / 4) * (N1 / 4) + (5 * TE / 4) * (N2 / 4);
+    static constexpr int THREADS = ((NITEMS + 31) / 32) * 32;
+};
+
+template <int G, int EPI>
+__global__ void __launch_bounds__(TpLinCfg<G, EPI>::THREADS)
+edge_tp_lin_kernel(TpLinArgs a, int lda0, int lda1, int lda2) {
+    using C = TpLinCfg<G, EPI>;
+    using D = Dtp<G>;
+    constexpr int TE = C::TE, P = D::P;
+    extern __shared__ __align__(16) float smem[];
+    float* A0 = smem;                            // [TE][lda0]
+    float* A1 = A0 + TE * lda0;                  // [3 TE][lda1]   row = k * TE + e
+    float* A2 = A1 + 3 * TE * lda1;              // [5 TE][lda2]
+    float* s_sh = A2 + 5 * TE * lda2;            // [TE][9]
+    int* s_src = reinterpret_cast<int*>(s_sh + TE * 9);
+    int* s_dst = s_src + TE;
+    float* O0 = smem;                            // outputs alias the A region after the GEMM
+    float* O1 = O0 + TE * C::N0;
+    float* O2 = O1 + 3 * TE * C::N1;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARPS = C::THREADS / 32;
+    const int E = *a.n_edges;
+    const int n_tiles = (E + TE - 1) / TE;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int e0 = tile * TE;
+        const int rows = min(TE, E - e0);
+        __syncthreads();
+        for (int i = tid; i < TE; i += C::THREADS) {
+            const bool ok = i < rows;
+            s_src[i] = ok ? (a.per_edge_x ? (e0 + i) : a.edge_src[e0 + i]) : 0;
+            s_dst[i] = ok ? a.edge_dst[e0 + i] : 0;
+        }
+        for (int i = tid; i < TE * 9; i += C::THREADS) s_sh[i] = (i / 9 < rows) ? a.sh[(size_t)e0 * 9 + i] : 0.f;
+        __syncthreads();
+
+        // ---------------- CG phase: one pack of P edges per warp iteration ----------------
+        for (int pack = warp; pack < TE / P; pack += NWARPS) {
+            const int pe0 = pack * P;
+            // l = 0 slots
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                int ei, ch; D::slot0(lane, s, ei, ch);
+                const int e = pe0 + ei;
+                const bool ok = e < rows;
+                float o[9];
+                float x = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f;
+                if (ok) {
+                    x = a.x_src[(size_t)s_src[e] * D::F + ch];
+                    if (a.x_dst) x += a.x_dst[(size_t)s_dst[e] * D::F + ch];
+                    const float* w = a.w + (size_t)(e0 + e) * a.w_stride;
+                    w0 = w[D::W_K0 + ch]; w1 = w[D::W_K1 + ch]; w2 = w[D::W_K2 + ch];
+                }
+                dtp_l0(x, w0, w1, w2, s_sh + e * 9, o);
+                A0[e * lda0 + D::C0_K0 + ch] = o[0];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) A1[(k * TE + e) * lda1 + D::C1_K1 + ch] = o[1 + k];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) A2[(k * TE + e) * lda2 + D::C2_K2 + ch] = o[4 + k];
+            }
+            // l = 1 slots
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                int ei, ch; D::slot1(lane, s, ei, ch);
+                const int e = pe0 + ei;
+                const bool ok = e < rows;
+                float x[3] = {0.f, 0.f, 0.f}, w[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o[20];
+                if (ok) {
+                    const float* xs = a.x_src + (size_t)s_src[e] * D::F + D::M0 + 3 * ch;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) x[i] = xs[i];
+                    if (a.x_dst) {
+                        const float* xd = a.x_dst + (size_t)s_dst[e] * D::F + D::M0 + 3 * ch;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) x[i] += xd[i];
+                    }
+                    const float* wp = a.w + (size_t)(e0 + e) * a.w_stride + D::W_K3 + ch;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) w[i] = wp[i * D::M1];
+                }
+                dtp_l1(x, w, s_sh + e * 9, o);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float* row = A1 + (k * TE + e) * lda1 + ch;
+                    row[D::C1_K3] = o[k]; row[D::C1_K5] = o[4 + k]; row[D::C1_K7] = o[12 + k];
+                }
+                A0[e * lda0 + D::C0_K4 + ch] = o[3];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    float* row = A2 + (k * TE + e) * lda2 + ch;
+                    row[D::C2_K6] = o[7 + k]; row[D::C2_K8] = o[15 + k];
+                }
+            }
+            // l = 2 slot
+            {
+                int ei, ch; D::slot2(lane, ei, ch);
+                const int e = pe0 + ei;
+                const bool ok = e < rows;
+                float x[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, w[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o[22];
+                if (ok) {
+                    const float* xs = a.x_src + (size_t)s_src[e] * D::F + D::M0 + 3 * D::M1 + 5 * ch;
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) x[i] = xs[i];
+                    if (a.x_dst) {
+                        const float* xd = a.x_dst + (size_t)s_dst[e] * D::F + D::M0 + 3 * D::M1 + 5 * ch;
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) x[i] += xd[i];
+                    }
+                    const float* wp = a.w + (size_t)(e0 + e) * a.w_stride + D::W_K9 + ch;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) w[i] = wp[i * D::M2];
+                }
+                dtp_l2(x, w, s_sh + e * 9, o);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    float* row = A2 + (k * TE + e) * lda2 + ch;
+                    row[D::C2_K9] = o[k]; row[D::C2_K11] = o[8 + k]; row[D::C2_K14] = o[17 + k];
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float* row = A1 + (k * TE + e) * lda1 + ch;
+                    row[D::C1_K10] = o[5 + k]; row[D::C1_K13] = o[14 + k];
+                }
+                A0[e * lda0 + D::C0_K12 + ch] = o[13];
+            }
+        }
+        __syncthreads();
+
+        // ---------------- GEMM phase: one 4x4 item per thread ----------------
+        constexpr int I0 = (TE / 4) * (C::N0 / 4), I1 = (3 * TE / 4) * (C::N1 / 4), I2 = (5 * TE / 4) * (C::N2 / 4);
+        float acc[4][4] = {};
+        int which = -1, rg = 0, cg = 0;
+        if (tid < I0) { which = 0; cg = tid % (C::N0 / 4); rg = tid / (C::N0 / 4); }
+        else if (tid < I0 + I1) { which = 1; const int t = tid - I0; cg = t % (C::N1 / 4); rg = t / (C::N1 / 4); }
+        else if (tid < I0 + I1 + I2) { which = 2; const int t = tid - I0 - I1; cg = t % (C::N2 / 4); rg = t / (C::N2 / 4); }
+        if (which == 0) gemm_item_4x4<true>(A0, lda0, TE / 4, rg, a.W0, C::N0, 4 * cg, D::D0, acc);
+        else if (which == 1) gemm_item_4x4<true>(A1, lda1, 3 * TE / 4, rg, a.W1, C::N1, 4 * cg, D::D1, acc);
+        else if (which == 2) gemm_item_4x4<true>(A2, lda2, 5 * TE / 4, rg, a.W2, C::N2, 4 * cg, D::D2, acc);
+        __syncthreads();   // all A reads done -> the region may be overwritten with the outputs
+        if (which == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(O0 + (rg + i * (TE / 4)) * C::N0 + 4 * cg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        } else if (which == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(O1 + (rg + i * (3 * TE / 4)) * C::N1 + 4 * cg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        } else if (which == 2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(O2 + (rg + i * (5 * TE / 4)) * C::N2 + 4 * cg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        __syncthreads();
+
+        // ---------------- epilogue: one warp per edge ----------------
+        for (int e = warp; e < rows; e += NWARPS) {
+            const size_t eg = (size_t)(e0 + e);
+            if constexpr (EPI == EPI_ACT) {
+                // attention logits: sum_k c * SLReLU(pre[h, k]) * alpha_dot[h, k] (+ edge logit)   (graph_attention.py:241-246)
+                constexpr int MA = C::MA, HD = MA / 4;          // channels per head
+                float part[MA / 32];
+#pragma unroll
+                for (int j = 0; j < MA / 32; ++j) {
+                    const int c = lane + 32 * j;
+                    const float pre = O0[e * C::N0 + c] + (a.bias0 ? a.bias0[c] : 0.f);
+                    part[j] = kCSlrelu * slreluf_(pre) * a.alpha_dot[c];
+                }
+#pragma unroll
+                for (int j = 0; j < MA / 32; ++j) {
+#pragma unroll
+                    for (int o = HD / 2; o > 0; o >>= 1) part[j] += __shfl_xor_sync(0xffffffffu, part[j], o);
+                }
+                const float el = a.edge_logit ? a.edge_logit[eg] : 0.f;
+#pragma unroll
+                for (int j = 0; j < MA / 32; ++j) {
+                    if ((lane % HD) == 0) a.logits[eg * 4 + (lane + 32 * j) / HD] = part[j] + el;
+                }
+                // gate (fast_activation.py:210-224): scalars | gates | gated
+                const float* b = a.bias0 ? a.bias0 + MA : nullptr;
+                for (int c = lane; c < C::FO; c += 32) {
+                    float v;
+                    if (c < D::M0) {
+                        v = kCSilu * siluf_(O0[e * C::N0 + MA + c] + (b ? b[c] : 0.f));
+                    } else if (c < D::M0 + 3 * D::M1) {
+                        const int u = (c - D::M0) / 3, k = (c - D::M0) % 3;
+                        const float g = kCSigmoid * sigmoidf_(O0[e * C::N0 + MA + D::M0 + u] + (b ? b[D::M0 + u] : 0.f));
+                        v = O1[(k * TE + e) * C::N1 + u] * g;
+                    } else {
+                        const int u = (c - D::M0 - 3 * D::M1) / 5, k = (c - D::M0 - 3 * D::M1) % 5;
+                        const float g = kCSigmoid * sigmoidf_(O0[e * C::N0 + MA + D::M0 + D::M1 + u] + (b ? b[D::M0 + D::M1 + u] : 0.f));
+                        v = O2[(k * TE + e) * C::N2 + u] * g;
+                    }
+                    a.out[eg * C::FO + c] = v;
+                }
+            } else {
+                for (int c = lane; c < C::FO; c += 32) {
+                    float v;
+                    if (c < C::N0) v = O0[e * C::N0 + c] + (a.bias0 ? a.bias0[c] : 0.f);
+                    else if (c < C::N0 + 3 * C::N1) { const int u = (c - C::N0) / 3, k = (c - C::N0) % 3; v = O1[(k * TE + e) * C::N1 + u]; }
+                    else { const int u = (c - C::N0 - 3 * C::N1) / 5, k = (c - C::N0 - 3 * C::N1) % 5; v = O2[(k * TE + e) * C::N2 + u]; }
+                    a.out[eg * C::FO + c] = v;
+                }
+            }
+        }
+    }
+}
+
+// ===========================================================================
+// per-destination softmax over incoming edges + weighted sum of the values
+// ===========================================================================
+struct SoftmaxArgs {
+    const int* row_ptr; int n_dst; int n_seg;   // edges of dst d in segment s: [row_ptr[s*n_dst+d], row_ptr[s*n_dst+d+1])
+    const float* logits;   // (E, 4)
+    const float* val;      // (E, F)
+    float* out;            // (n_dst, F)
+    int m0, m1, m2;        // value irreps; heads split every mul in 4
+};
+
+__global__ void __launch_bounds__(256) segment_softmax_reduce_kernel(SoftmaxArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int F = a.m0 + 3 * a.m1 + 5 * a.m2;
+    constexpr int MAXC = 8;   // channels per lane (F <= 256)
+    for (int d = blockIdx.x * wpb + (threadIdx.x >> 5); d < a.n_dst; d += gridDim.x * wpb) {
+        // pass 1: per-head max
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int deg = 0;
+        for (int s = 0; s < a.n_seg; ++s) {
+            const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
+            deg += e - b;
+            for (int i = b + lane; i < e; i += 32) {
+                const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
+                mx[0] = fmaxf(mx[0], l.x); mx[1] = fmaxf(mx[1], l.y); mx[2] = fmaxf(mx[2], l.z); mx[3] = fmaxf(mx[3], l.w);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) mx[h] = warp_max(mx[h]);
+        // pass 2: sum of exp
+        float sm[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int s = 0; s < a.n_seg; ++s) {
+            const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
+            for (int i = b + lane; i < e; i += 32) {
+                const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
+                sm[0] += __expf(l.x - mx[0]); sm[1] += __expf(l.y - mx[1]); sm[2] += __expf(l.z - mx[2]); sm[3] += __expf(l.w - mx[3]);
+            }
+        }
+        float logZ[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { sm[h] = warp_sum(sm[h]); logZ[h] = (deg > 0) ? (logf(sm[h] + 1e-12f) + mx[h]) : 0.f; }
+        // head of each of this lane's channels
+        int hd[MAXC];
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+            const int c = lane + 32 * j;
+            int h = 0;
+            if (c < a.m0) h = c / (a.m0 / 4);
+            else if (c < a.m0 + 3 * a.m1) h = ((c - a.m0) / 3) / (a.m1 / 4);
+            else if (c < F) h = ((c - a.m0 - 3 * a.m1) / 5) / (a.m2 / 4);
+            hd[j] = h;
+        }
+        // pass 3: weighted sum
+        float acc[MAXC];
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) acc[j] = 0.f;
+        for (int s = 0; s < a.n_seg; ++s) {
+            const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
+            for (int i = b; i < e; ++i) {
+                const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
+                const float al0 = __expf(l.x - logZ[0]), al1 = __expf(l.y - logZ[1]), al2 = __expf(l.z - logZ[2]), al3 = __expf(l.w - logZ[3]);
+                const float* v = a.val + (size_t)i * F;
+#pragma unroll
+                for (int j = 0; j < MAXC; ++j) {
+                    const int c = lane + 32 * j;
+                    const float al = (hd[j] == 0) ? al0 : (hd[j] == 1) ? al1 : (hd[j] == 2) ? al2 : al3;
+                    if (c < F) acc[j] = fmaf(al, v[c], acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+            const int c = lane + 32 * j;
+            if (c < F) a.out[(size_t)d * F + c] = acc[j];
+        }
+    }
+}
+
+// ===========================================================================
+// K1: gather -> depthwise CG TP (per-edge weights) -> x alpha_h -> segment reduce
+// ===========================================================================
+struct TpReduceArgs {
+    const float* x;        // (N_src, F)
+    const int* row_ptr;    // (N_dst + 1) CSR by destination
+    const int* edge_src;   // (E)
+    const float* sh;       // (E, 9)
+    const float* w;        // (E, NUMEL)
+    const float* alpha;    // (E, 4)
+    float* out;            // (N_dst, FOUT)
+    int n_dst;
+};
+
+template <int G>
+__global__ void __launch_bounds__(256) edge_tp_reduce_kernel(TpReduceArgs a) {
+    using D = Dtp<G>;
+    constexpr int P = D::P;
+    constexpr int S0 = 4 / P;   // distinct l0 channels per lane (2 / 1)
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float* stage = smem + (size_t)warp * D::FOUT;
+    for (int d = blockIdx.x * wpb + warp; d < a.n_dst; d += gridDim.x * wpb) {
+        const int eb = a.row_ptr[d], ee = a.row_ptr[d + 1];
+        // accumulators, indexed by slot: slots that map to the same channel (different edge of
+        // the pack) are summed when written out.
+        float acc0[4][9], acc1[2][20], acc2[22];
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc0[s][k] = 0.f;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int k = 0; k < 20; ++k) acc1[s][k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 22; ++k) acc2[k] = 0.f;
+
+        for (int pe = eb; pe < ee; pe += P) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                int ei, ch; D::slot0(lane, s, ei, ch);
+                const int e = pe + ei;
+                if (e < ee) {
+                    const float al = a.alpha[(size_t)e * 4 + ch / (D::M0 / 4)];
+                    const float x = a.x[(size_t)a.edge_src[e] * D::F + ch];
+                    const float* w = a.w + (size_t)e * D::NUMEL;
+                    float o[9];
+                    dtp_l0(x * al, w[D::W_K0 + ch], w[D::W_K1 + ch], w[D::W_K2 + ch], a.sh + (size_t)e * 9, o);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) acc0[s][k] += o[k];
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                int ei, ch; D::slot1(lane, s, ei, ch);
+                const int e = pe + ei;
+                if (e < ee) {
+                    const float al = a.alpha[(size_t)e * 4 + ch / (D::M1 / 4)];
+                    const float* xs = a.x + (size_t)a.edge_src[e] * D::F + D::M0 + 3 * ch;
+                    float x[3] = {xs[0] * al, xs[1] * al, xs[2] * al}, w[6], o[20];
+                    const float* wp = a.w + (size_t)e * D::NUMEL + D::W_K3 + ch;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) w[i] = wp[i * D::M1];
+                    dtp_l1(x, w, a.sh + (size_t)e * 9, o);
+#pragma unroll
+                    for (int k = 0; k < 20; ++k) acc1[s][k] += o[k];
+                }
+            }
+            {
+                int ei, ch; D::slot2(lane, ei, ch);
+                const int e = pe + ei;
+                if (e < ee) {
+                    const float al = a.alpha[(size_t)e * 4 + ch / (D::M2 / 4)];
+                    const float* xs = a.x + (size_t)a.edge_src[e] * D::F + D::M0 + 3 * D::M1 + 5 * ch;
+                    float x[5], w[6], o[22];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) x[i] = xs[i] * al;
+                    const float* wp = a.w + (size_t)e * D::NUMEL + D::W_K9 + ch;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) w[i] = wp[i * D::M2];
+                    dtp_l2(x, w, a.sh + (size_t)e * 9, o);
+#pragma unroll
+                    for (int k = 0; k < 22; ++k) acc2[k] += o[k];
+                }
+            }
+        }
+        // ---- fold the pack dimension ------------------------------------------------
+        // l0: slots s and s' with the same channel: G=32: (0,2),(1,3); G=16: all four slots -> channel = lane
+        // l1: G=32: slots (0,1) same channel; G=16: slot s, lane>>4 selects the edge -> fold across lane^16 too
+        // l2: fold across the P lane groups of width M2
+        if (G == 32) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { acc0[0][k] += acc0[2][k]; acc0[1][k] += acc0[3][k]; }
+#pragma unroll
+            for (int k = 0; k < 20; ++k) acc1[0][k] += acc1[1][k];
+#pragma unroll
+            for (int k = 0; k < 22; ++k) acc2[k] += __shfl_xor_sync(0xffffffffu, acc2[k], 16);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc0[0][k] += acc0[1][k] + acc0[2][k] + acc0[3][k];
+#pragma unroll
+            for (int k = 0; k < 20; ++k) { acc1[0][k] += acc1[1][k]; acc1[0][k] += __shfl_xor_sync(0xffffffffu, acc1[0][k], 16); }
+#pragma unroll
+            for (int k = 0; k < 22; ++k) { acc2[k] += __shfl_xor_sync(0xffffffffu, acc2[k], 8); acc2[k] += __shfl_xor_sync(0xffffffffu, acc2[k], 16); }
+        }
+        // ---- stage the output row in shared memory in the sorted-irreps layout ---------
+        constexpr int B1 = D::D0, B2 = D::D0 + 3 * D::D1;      // block offsets of lo=1 / lo=2
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < S0; ++s) {
+            const int ch = lane + 32 * s;                       // G=32: channels lane, lane+32 ; G=16: lane
+            stage[D::C0_K0 + ch] = acc0[s][0];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) stage[B1 + (D::C1_K1 + ch) * 3 + k] = acc0[s][1 + k];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) stage[B2 + (D::C2_K2 + ch) * 5 + k] = acc0[s][4 + k];
+        }
+        if (lane < D::M1) {
+            const int ch = lane;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                stage[B1 + (D::C1_K3 + ch) * 3 + k] = acc1[0][k];
+                stage[B1 + (D::C1_K5 + ch) * 3 + k] = acc1[0][4 + k];
+                stage[B1 + (D::C1_K7 + ch) * 3 + k] = acc1[0][12 + k];
+            }
+            stage[D::C0_K4 + ch] = acc1[0][3];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                stage[B2 + (D::C2_K6 + ch) * 5 + k] = acc1[0][7 + k];
+                stage[B2 + (D::C2_K8 + ch) * 5 + k] = acc1[0][15 + k];
+            }
+        }
+        if (lane < D::M2) {
+            const int ch = lane;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                stage[B2 + (D::C2_K9 + ch) * 5 + k] = acc2[k];
+                stage[B2 + (D::C2_K11 + ch) * 5 + k] = acc2[8 + k];
+                stage[B2 + (D::C2_K14 + ch) * 5 + k] = acc2[17 + k];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                stage[B1 + (D::C1_K10 + ch) * 3 + k] = acc2[5 + k];
+                stage[B1 + (D::C1_K13 + ch) * 3 + k] = acc2[14 + k];
+            }
+            stage[D::C0_K12 + ch] = acc2[13];
+        }
+        __syncwarp();
+        float4* dst = reinterpret_cast<float4*>(a.out + (size_t)d * D::FOUT);
+        const float4* srcv = reinterpret_cast<const float4*>(stage);
+        for (int i = lane; i < D::FOUT / 4; i += 32) dst[i] = srcv[i];
+    }
+}
+
+}  // namespace dedf
+
+using namespace dedf;
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" int dedf_edge_geom(const float* x_src, const float* x_dst, const int* edge_src, const int* edge_dst,
+                              const int* n_edges_dev, int max_edges, int n_scales, const int* src_off, const float* r,
+                              float ns_lo, float ns_hi, float* length, float* sh, float* logit, cudaStream_t stream) {
+    if (max_edges <= 0) return DEDF_OK;
+    if (!x_src || !x_dst || !edge_src || !edge_dst || !n_edges_dev || !length || !sh) return DEDF_ERR_ARG;
+    if (n_scales < 1 || n_scales > DEDF_MAX_SCALES) return DEDF_ERR_ARG;
+    if (logit && (!src_off || !r)) return DEDF_ERR_ARG;
+    if (max_edges <= 0) return DEDF_OK;
+    GeomArgs a{};
+    a.x_src = x_src; a.x_dst = x_dst; a.edge_src = edge_src; a.edge_dst = edge_dst; a.n_edges = n_edges_dev;
+    a.length = length; a.sh = sh; a.logit = logit; a.ns_lo = ns_lo; a.ns_hi = ns_hi; a.n_scales = n_scales;
+    for (int s = 0; s < n_scales; ++s) { a.src_off[s] = src_off ? src_off[s] : 0; a.r[s] = r ? r[s] : -1.f; }
+    a.src_off[n_scales] = src_off ? src_off[n_scales] : 0x7fffffff;
+    edge_geom_kernel<<<grid_for(max_edges, 256, kNumSMs * 8), 256, 0, stream>>>(a);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_edge_mlp(const dedf_mlp_desc* d, int max_edges, cudaStream_t stream) {
+    if (max_edges <= 0) return DEDF_OK;
+    if (!d || !d->n_edges_dev || !d->out) return DEDF_ERR_ARG;
+    if (d->n_layers < 1 || d->n_layers > DEDF_MLP_MAX_LAYERS) return DEDF_ERR_ARG;
+    for (int i = 0; i <= d->n_layers; ++i) {
+        if (d->dims[i] < 4 || d->dims[i] % 4) return DEDF_ERR_ARG;
+        if (i < d->n_layers && d->dims[i] > kMlpMaxW) return DEDF_ERR_ARG;      // hidden widths staged in smem
+    }
+    if (max_edges <= 0) return DEDF_OK;
+    MlpArgs a{};
+    a.mode = d->mode; a.n_edges = d->n_edges_dev; a.x_in = d->x_in; a.length = d->length;
+    a.rbf_mean = d->rbf_mean; a.rbf_std_logit = d->rbf_std_logit; a.rbf_weight_logit = d->rbf_weight_logit;
+    a.rbf_cutoff = d->rbf_cutoff; a.rbf_offset = d->rbf_offset;
+    a.n_scales = d->n_scales; a.n_dst = d->n_dst; a.row_ptr = d->row_ptr; a.edge_dst = d->edge_dst;
+    a.enc_max_r = d->enc_max_r; a.enc_n = d->enc_n; a.enc_freq = d->enc_freq; a.row_bias = d->row_bias; a.n_rb = d->n_rb; a.rb_div = d->rb_div;
+    if (a.mode == DEDF_MLP_IN_ROWS) { if (!a.x_in) return DEDF_ERR_ARG; }
+    else if (a.mode == DEDF_MLP_IN_RBF) { if (!a.length || !a.rbf_mean || !a.rbf_std_logit || !a.rbf_weight_logit) return DEDF_ERR_ARG; }
+    else if (a.mode == DEDF_MLP_IN_FIELD) {
+        if (!a.length || !a.row_ptr || !a.edge_dst || !a.row_bias || a.n_scales < 1 || a.n_scales > DEDF_MAX_SCALES || a.rb_div < 1 || a.n_rb < 1)
+            return DEDF_ERR_ARG;
+        for (int s = 0; s < a.n_scales; ++s) {
+            a.enc_mean[s] = d->enc_mean[s]; a.enc_std_logit[s] = d->enc_std_logit[s]; a.enc_weight_logit[s] = d->enc_weight_logit[s];
+            a.enc_r[s] = d->enc_r[s]; a.pre_w[s] = d->pre_w[s];
+            if (!a.pre_w[s]) return DEDF_ERR_ARG;
+            if (a.enc_r[s] >= 0.f && (!a.enc_mean[s] || !a.enc_std_logit[s] || !a.enc_weight_logit[s])) return DEDF_ERR_ARG;
+            if (a.enc_r[s] < 0.f && !a.enc_freq) return DEDF_ERR_ARG;
+        }
+    } else return DEDF_ERR_ARG;
+    for (int i = 0; i <= d->n_layers; ++i) a.K[i] = d->dims[i];
+    a.n_layers = d->n_layers;
+    for (int i = 0; i < d->n_layers; ++i) {
+        a.W[i] = d->W[i]; a.b[i] = d->b[i]; a.ln_g[i] = d->ln_g[i]; a.ln_b[i] = d->ln_b[i]; a.flags[i] = d->flags[i];
+        if (!(a.mode == DEDF_MLP_IN_FIELD && i == 0) && !a.W[i]) return DEDF_ERR_ARG;
+        if ((a.flags[i] & 1) && (!a.ln_g[i] || !a.ln_b[i])) return DEDF_ERR_ARG;
+    }
+    a.out_offset = d->out_offset; a.out = d->out;
+    const size_t smem = (size_t)2 * kMlpTE * pad_lda(kMlpMaxW) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) { cudaFuncSetAttribute(edge_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
+    const int n_tiles = (max_edges + kMlpTE - 1) / kMlpTE + DEDF_MAX_SCALES;
+    edge_mlp_kernel<<<grid_for(n_tiles, 1, kNumSMs * 3), kMlpThreads, smem, stream>>>(a);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+template <int G, int EPI>
+static int launch_tp_lin(const TpLinArgs& a, int max_edges, cudaStream_t stream) {
+    using C = TpLinCfg<G, EPI>;
+    using D = Dtp<G>;
+    const int lda0 = pad_lda(D::D0), lda1 = pad_lda(D::D1), lda2 = pad_lda(D::D2);
+    const size_t smem = ((size_t)C::TE * lda0 + 3 * C::TE * lda1 + 5 * C::TE * lda2 + C::TE * 9 + 2 * C::TE) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(edge_tp_lin_kernel<G, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
+    const int n_tiles = (max_edges + C::TE - 1) / C::TE;
+    edge_tp_lin_kernel<G, EPI><<<grid_for(n_tiles, 1, kNumSMs * 2), C::THREADS, smem, stream>>>(a, lda0, lda1, lda2);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_edge_tp_lin(int mul1, int epilogue, const float* x_src, const float* x_dst, int per_edge_x,
+                                const int* edge_src, const int* edge_dst, const int* n_edges_dev, int max_edges,
+                                const float* sh, const float* w, long long w_stride, const float* W0, const float* W1,
+                                const float* W2, const float* bias0, const float* alpha_dot, const float* edge_logit,
+                                float* logits, float* out, cudaStream_t stream) {
+    if (max_edges <= 0) return DEDF_OK;
+    if (!x_src || !edge_dst || !n_edges_dev || !sh || !w || !W0 || !W1 || !W2 || !out) return DEDF_ERR_ARG;
+    if (!per_edge_x && !edge_src) return DEDF_ERR_ARG;
+    if (epilogue == DEDF_EPI_ACT && (!alpha_dot || !logits)) return DEDF_ERR_ARG;
+    if (max_edges <= 0) return DEDF_OK;
+    TpLinArgs a{};
+    a.x_src = x_src; a.x_dst = x_dst; a.edge_src = edge_src; a.edge_dst = edge_dst; a.n_edges = n_edges_dev; a.sh = sh;
+    a.w = w; a.w_stride = w_stride; a.W0 = W0; a.W1 = W1; a.W2 = W2; a.bias0 = bias0; a.alpha_dot = alpha_dot;
+    a.edge_logit = edge_logit; a.logits = logits; a.out = out; a.per_edge_x = per_edge_x;
+    if (mul1 == 32 && epilogue == DEDF_EPI_ACT) return launch_tp_lin<32, EPI_ACT>(a, max_edges, stream);
+    if (mul1 == 32 && epilogue == DEDF_EPI_LIN) return launch_tp_lin<32, EPI_LIN>(a, max_edges, stream);
+    if (mul1 == 16 && epilogue == DEDF_EPI_ACT) return launch_tp_lin<16, EPI_ACT>(a, max_edges, stream);
+    if (mul1 == 16 && epilogue == DEDF_EPI_LIN) return launch_tp_lin<16, EPI_LIN>(a, max_edges, stream);
+    return DEDF_ERR_UNSUPPORTED;
+}
+
+extern "C" int dedf_segment_softmax_reduce(const int* row_ptr, int n_dst, int n_seg, const float* logits,
+                                           const float* val, int m0, int m1, int m2, float* out, cudaStream_t stream) {
+    if (!row_ptr || !logits || !val || !out || n_seg < 1) return DEDF_ERR_ARG;
+    if (m0 % 4 || m1 % 4 || m2 % 4 || m0 + 3 * m1 + 5 * m2 > 256) return DEDF_ERR_UNSUPPORTED;
+    if (n_dst <= 0) return DEDF_OK;
+    SoftmaxArgs a{row_ptr, n_dst, n_seg, logits, val, out, m0, m1, m2};
+    segment_softmax_reduce_kernel<<<grid_for(n_dst, 8, kNumSMs * 8), 256, 0, stream>>>(a);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_edge_tp_reduce(int mul1, const float* x, const int* row_ptr, const int* edge_src, const float* sh,
+                                   const float* w, const float* alpha, int n_dst, float* out, cudaStream_t stream) {
+    if (!x || !row_ptr || !edge_src || !sh || !w || !alpha || !out) return DEDF_ERR_ARG;
+    if (n_dst <= 0) return DEDF_OK;
+    TpReduceArgs a{x, row_ptr, edge_src, sh, w, alpha, out, n_dst};
+    if (mul1 == 32) {
+        const size_t smem = (size_t)8 * Dtp<32>::FOUT * sizeof(float);
+        static bool done = false;
+        if (!done) { cudaFuncSetAttribute(edge_tp_reduce_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
+        edge_tp_reduce_kernel<32><<<grid_for(n_dst, 8, kNumSMs * 4), 256, smem, stream>>>(a);
+    } else if (mul1 == 16) {
+        const size_t smem = (size_t)8 * Dtp<16>::FOUT * sizeof(float);
+        static bool done = false;
+        if (!done) { cudaFuncSetAttribute(edge_tp_reduce_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
+        edge_tp_reduce_kernel<16><<<grid_for(n_dst, 8, kNumSMs * 4), 256, smem, stream>>>(a);
+    } else return DEDF_ERR_UNSUPPORTED;
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}

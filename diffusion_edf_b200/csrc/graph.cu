@@ -1,0 +1,274 @@
+// Graph construction kernels: farthest-point sampling, radius search (CSR by
+// destination, sources ascending -- the order torch_cluster.radius returns), scan.
+//
+// Replaces, for the reference's hot path:
+//   torch_cluster.fps            (connectivity.py:62)
+//   torch_cluster.radius         (graph_parser.py:339, connectivity.py:42)
+//   torch_cluster.radius_graph   (connectivity.py:22)
+//   the all-pairs meshgrid of InfiniteBipartite (graph_parser.py:272-286)
+// Index results are bit-exact against oracle/graph.py: squared distances are
+// evaluated as (dx*dx + dy*dy) + dz*dz with no FMA contraction.
+#include "common.cuh"
+#include "../../include/dedf.h"
+
+namespace dedf {
+
+__device__ __forceinline__ float sqdist_exact(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// ---------------------------------------------------------------------------
+// FPS: one persistent CTA per call; points and running min-distances live in
+// registers (PT per thread), one barrier per iteration (double-buffered slots).
+// ---------------------------------------------------------------------------
+constexpr int kFpsThreads = 1024;
+
+__device__ __forceinline__ void argmax_pair(float& v, int& i, float ov, int oi) {
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+
+template <int PT>
+__global__ void __launch_bounds__(kFpsThreads, 1)
+fps_kernel(const float* __restrict__ x, int n, int m, int start, int idx_base, long long* __restrict__ out_idx) {
+    __shared__ float s_val[2][32];
+    __shared__ int s_idx[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float px[PT], py[PT], pz[PT], dist[PT];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+        int i = tid + j * kFpsThreads;
+        if (i < n) { px[j] = x[3 * i]; py[j] = x[3 * i + 1]; pz[j] = x[3 * i + 2]; dist[j] = __int_as_float(0x7f800000); }
+        else       { px[j] = py[j] = pz[j] = 0.f; dist[j] = -1.0f; }   // never selected
+    }
+    int cur = start;
+    for (int it = 0; it < m; ++it) {
+        if (tid == 0) out_idx[it] = (long long)(cur + idx_base);
+        const float cx = __ldg(x + 3 * cur), cy = __ldg(x + 3 * cur + 1), cz = __ldg(x + 3 * cur + 2);
+        float bv = -2.0f; int bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            int i = tid + j * kFpsThreads;
+            if (i < n) {
+                float d = sqdist_exact(px[j], py[j], pz[j], cx, cy, cz);
+                dist[j] = fminf(dist[j], d);
+                argmax_pair(bv, bi, dist[j], i);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            argmax_pair(bv, bi, ov, oi);
+        }
+        const int buf = it & 1;
+        if (lane == 0) { s_val[buf][warp] = bv; s_idx[buf][warp] = bi; }
+        __syncthreads();
+        bv = s_val[buf][lane]; bi = s_idx[buf][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            argmax_pair(bv, bi, ov, oi);
+        }
+        cur = bi;
+    }
+}
+
+// fallback for very large clouds: running distances in global scratch
+__global__ void __launch_bounds__(kFpsThreads, 1)
+fps_kernel_large(const float* __restrict__ x, int n, int m, int start, int idx_base, long long* __restrict__ out_idx,
+                 float* __restrict__ dist) {
+    __shared__ float s_val[2][32];
+    __shared__ int s_idx[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += kFpsThreads) dist[i] = __int_as_float(0x7f800000);
+    __syncthreads();
+    int cur = start;
+    for (int it = 0; it < m; ++it) {
+        if (tid == 0) out_idx[it] = (long long)(cur + idx_base);
+        const float cx = __ldg(x + 3 * cur), cy = __ldg(x + 3 * cur + 1), cz = __ldg(x + 3 * cur + 2);
+        float bv = -2.0f; int bi = 0x7fffffff;
+        for (int i = tid; i < n; i += kFpsThreads) {
+            float d = sqdist_exact(x[3 * i], x[3 * i + 1], x[3 * i + 2], cx, cy, cz);
+            float nd = fminf(dist[i], d);
+            dist[i] = nd;
+            argmax_pair(bv, bi, nd, i);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            argmax_pair(bv, bi, ov, oi);
+        }
+        const int buf = it & 1;
+        if (lane == 0) { s_val[buf][warp] = bv; s_idx[buf][warp] = bi; }
+        __syncthreads();
+        bv = s_val[buf][lane]; bi = s_idx[buf][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            argmax_pair(bv, bi, ov, oi);
+        }
+        cur = bi;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Radius search, brute force, one warp per (destination, scale): the warp walks
+// the sources 32 at a time in index order and compacts hits with a ballot, so
+// every destination's neighbour list comes out ascending and the
+// ``max_num_neighbors`` truncation keeps the first ones, like torch_cluster.
+// ---------------------------------------------------------------------------
+struct RadiusArgs {
+    const float* x_src;            // (sum n_src, 3)
+    const float* x_dst;            // (n_dst, 3)
+    const long long* b_src;        // optional batch ids
+    const long long* b_dst;
+    const long long* excl;         // exclusion table (mode 1: per dst, mode 3: per src)
+    int n_dst, n_scales, max_nb, excl_mode;
+    int src_off[DEDF_MAX_SCALES + 1];
+    float r[DEDF_MAX_SCALES];      // < 0: all pairs
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+radius_kernel(RadiusArgs a, int* __restrict__ counts, const int* __restrict__ row_ptr,
+              int* __restrict__ edge_src, int* __restrict__ edge_dst) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long n_items = (long long)a.n_dst * a.n_scales;
+    for (long long item = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < n_items;
+         item += (long long)gridDim.x * warps_per_block) {
+        const int s = (int)(item / a.n_dst), d = (int)(item % a.n_dst);
+        const int s0 = a.src_off[s], s1 = a.src_off[s + 1];
+        const float r = a.r[s];
+        const bool all = r < 0.f;
+        const float r2 = r * r;
+        const float qx = a.x_dst[3 * d], qy = a.x_dst[3 * d + 1], qz = a.x_dst[3 * d + 2];
+        const long long qb = a.b_dst ? a.b_dst[d] : 0;
+        const long long ex = (a.excl_mode == 1) ? a.excl[d] : -1;
+        // ``max_nb`` caps the hits INCLUDING excluded ones (torch_cluster truncates first, the
+        // reference filters self pairs afterwards: connectivity.py:68-70, radius_graph's +1).
+        int cnt_all = 0, cnt_keep = 0;
+        int base = 0;
+        if (FILL) base = row_ptr[item];
+        for (int c = s0; c < s1 && cnt_all < a.max_nb; c += 32) {
+            const int i = c + lane;
+            bool hit = false, excluded = false;
+            if (i < s1) {
+                hit = all || sqdist_exact(a.x_src[3 * i], a.x_src[3 * i + 1], a.x_src[3 * i + 2], qx, qy, qz) < r2;
+                if (a.b_src && !all) hit = hit && (a.b_src[i] == qb);   // the all-pairs scale ignores batches (graph_parser.py:276-278)
+                const int li = i - s0;   // index local to this scale's cloud
+                if (a.excl_mode == 1) excluded = ((long long)li == ex);
+                else if (a.excl_mode == 2) excluded = (li == d);
+                else if (a.excl_mode == 3) excluded = (a.excl[li] == (long long)d);
+            }
+            const unsigned lt = (1u << lane) - 1u;
+            const unsigned bal_all = __ballot_sync(0xffffffffu, hit);
+            const bool keep = hit && !excluded && (cnt_all + __popc(bal_all & lt) < a.max_nb);
+            const unsigned bal_keep = __ballot_sync(0xffffffffu, keep);
+            if (FILL && keep) {
+                const int pos = base + cnt_keep + __popc(bal_keep & lt);
+                edge_src[pos] = i;                  // flat index into the concatenated clouds
+                edge_dst[pos] = d;
+            }
+            cnt_all += __popc(bal_all);
+            cnt_keep += __popc(bal_keep);
+        }
+        if (!FILL && lane == 0) counts[item] = cnt_keep;
+    }
+}
+
+// single-CTA exclusive scan: row_ptr[0..n] from counts[0..n-1]
+__global__ void __launch_bounds__(1024, 1)
+exclusive_scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ row_ptr) {
+    __shared__ int s_part[1024];
+    const int tid = threadIdx.x;
+    const int chunk = (n + 1023) / 1024;
+    const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += counts[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = (tid >= o) ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int run = s_part[tid] - sum;
+    for (int i = lo; i < hi; ++i) { row_ptr[i] = run; run += counts[i]; }
+    if (tid == 1023) row_ptr[n] = s_part[1023];
+}
+
+}  // namespace dedf
+
+using namespace dedf;
+
+extern "C" int dedf_fps(const float* x, int n, int m, int start, int idx_base, long long* out_idx,
+                        float* scratch_dist, cudaStream_t stream) {
+    if (!x || !out_idx || n <= 0 || m <= 0 || m > n || start < 0 || start >= n) return DEDF_ERR_ARG;
+    const int pt = (n + kFpsThreads - 1) / kFpsThreads;
+    if (pt <= 1) fps_kernel<1><<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx);
+    else if (pt <= 2) fps_kernel<2><<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx);
+    else if (pt <= 4) fps_kernel<4><<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx);
+    else if (pt <= 8) fps_kernel<8><<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx);
+    else if (pt <= 12) fps_kernel<12><<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx);
+    else if (pt <= 16) fps_kernel<16><<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx);
+    else {
+        if (!scratch_dist) return DEDF_ERR_ARG;
+        fps_kernel_large<<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx, scratch_dist);
+    }
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+static int fill_radius_args(RadiusArgs& a, const float* x_src, const float* x_dst, int n_dst, int n_scales,
+                            const int* src_off, const float* r, const long long* b_src, const long long* b_dst,
+                            int excl_mode, const long long* excl, int max_nb) {
+    if (!x_src || !x_dst || !src_off || !r || n_dst < 0 || n_scales < 1 || n_scales > DEDF_MAX_SCALES || max_nb < 1)
+        return DEDF_ERR_ARG;
+    if ((excl_mode == 1 || excl_mode == 3) && !excl) return DEDF_ERR_ARG;
+    if (excl_mode < 0 || excl_mode > 3) return DEDF_ERR_ARG;
+    if ((b_src == nullptr) != (b_dst == nullptr)) return DEDF_ERR_ARG;
+    a.x_src = x_src; a.x_dst = x_dst; a.b_src = b_src; a.b_dst = b_dst; a.excl = excl;
+    a.n_dst = n_dst; a.n_scales = n_scales; a.max_nb = max_nb; a.excl_mode = excl_mode;
+    for (int s = 0; s <= n_scales; ++s) a.src_off[s] = src_off[s];
+    for (int s = 0; s < n_scales; ++s) a.r[s] = r[s];
+    return DEDF_OK;
+}
+
+extern "C" int dedf_radius_count(const float* x_src, const float* x_dst, int n_dst, int n_scales, const int* src_off,
+                                 const float* r, const long long* b_src, const long long* b_dst, int excl_mode,
+                                 const long long* excl, int max_nb, int* counts, int* row_ptr, cudaStream_t stream) {
+    RadiusArgs a;
+    int rc = fill_radius_args(a, x_src, x_dst, n_dst, n_scales, src_off, r, b_src, b_dst, excl_mode, excl, max_nb);
+    if (rc) return rc;
+    if (!counts || !row_ptr) return DEDF_ERR_ARG;
+    const long long items = (long long)n_dst * n_scales;
+    if (items > 0) {
+        radius_kernel<false><<<grid_for(items, 8, kNumSMs * 8), 256, 0, stream>>>(a, counts, nullptr, nullptr, nullptr);
+        DEDF_CHECK_LAUNCH();
+    }
+    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(counts, (int)items, row_ptr);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_radius_fill(const float* x_src, const float* x_dst, int n_dst, int n_scales, const int* src_off,
+                                const float* r, const long long* b_src, const long long* b_dst, int excl_mode,
+                                const long long* excl, int max_nb, const int* row_ptr, int* edge_src, int* edge_dst,
+                                cudaStream_t stream) {
+    RadiusArgs a;
+    int rc = fill_radius_args(a, x_src, x_dst, n_dst, n_scales, src_off, r, b_src, b_dst, excl_mode, excl, max_nb);
+    if (rc) return rc;
+    if (!row_ptr || !edge_src || !edge_dst) return DEDF_ERR_ARG;
+    const long long items = (long long)n_dst * n_scales;
+    if (items == 0) return DEDF_OK;
+    radius_kernel<true><<<grid_for(items, 8, kNumSMs * 8), 256, 0, stream>>>(a, nullptr, row_ptr, edge_src, edge_dst);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}

@@ -1,0 +1,438 @@
+// Score-head kernels that run once per (pose, diffusion step)
+// (/root/reference/diffusion_edf/score_head.py:142-211, score_model_base.py:146-199):
+//
+//   time_embed        sinusoidal time encoding -> per-scale MLP -> time half of the edge pre-linear
+//                     (score_head.py:53-63,160-164 ; multiscale_tensor_field.py:225-234, reassociated:
+//                      W [len_emb | t_emb] + b = W_len len_emb + (W_t t_emb + b))
+//   query_transform   x' = R(q) x + t,  f' = D(q) f with D^1 = R and D^2 built from R directly
+//                     (gnn_data.py:88-100, wigner.py:257-283; no Euler angles / J matrices)
+//   score_tp          the two 240 x 240 'uvu' tensor products (lin / ang), linear, gate, mean over the 32
+//                     vectors, rotate back by q^-1, orbital term, weighted sum over the query points
+//   pose_update       one annealed-Langevin step on SE(3) in float64 (score_model_base.py:178-193)
+#include "common.cuh"
+#include "cg_paths.cuh"
+#include <curand_kernel.h>
+#include "../../include/dedf.h"
+
+namespace dedf {
+
+// ---------------------------------------------------------------------------
+// time embedding
+// ---------------------------------------------------------------------------
+struct TimeArgs {
+    const float* time; int n_t;
+    float max_time, enc_n; int enc_dim;        // SinusoidalPositionEmbeddings(dim, max_val, n)
+    const float* enc_freq;                     // (enc_dim/2) frequency table
+    int h_dim, e_dim, out_dim;                 // MLP enc_dim -> h_dim -> e_dim ; pre-linear e_dim -> out_dim
+    int n_scales;
+    const float* W1[DEDF_MAX_SCALES]; const float* b1[DEDF_MAX_SCALES];   // (enc_dim, h_dim) transposed
+    const float* W2[DEDF_MAX_SCALES]; const float* b2[DEDF_MAX_SCALES];   // (h_dim, e_dim)
+    const float* Wp[DEDF_MAX_SCALES]; const float* bp[DEDF_MAX_SCALES];   // (e_dim, out_dim) = W_s[:, len_dim:]^T, b_s
+    float* out;                                // (n_scales, n_t, out_dim)
+};
+
+__global__ void __launch_bounds__(128) time_embed_kernel(TimeArgs a) {
+    extern __shared__ float sm[];
+    float* enc = sm;                 // enc_dim
+    float* h = enc + a.enc_dim;      // h_dim
+    float* e = h + a.h_dim;          // e_dim
+    const int t = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+    const float x = a.time[t] / a.max_time * a.enc_n;
+    const int half = a.enc_dim / 2;
+    for (int i = tid; i < a.enc_dim; i += blockDim.x) {
+        const int k = (i < half) ? i : i - half;
+        const float arg = __fmul_rn(x, a.enc_freq[k]);
+        enc[i] = (i < half) ? sinf(arg) : cosf(arg);
+    }
+    __syncthreads();
+    for (int o = tid; o < a.h_dim; o += blockDim.x) {
+        float acc = a.b1[s][o];
+        for (int i = 0; i < a.enc_dim; ++i) acc = fmaf(enc[i], a.W1[s][(size_t)i * a.h_dim + o], acc);
+        h[o] = siluf_(acc);
+    }
+    __syncthreads();
+    for (int o = tid; o < a.e_dim; o += blockDim.x) {
+        float acc = a.b2[s][o];
+        for (int i = 0; i < a.h_dim; ++i) acc = fmaf(h[i], a.W2[s][(size_t)i * a.e_dim + o], acc);
+        e[o] = acc;
+    }
+    __syncthreads();
+    for (int o = tid; o < a.out_dim; o += blockDim.x) {
+        float acc = a.bp[s][o];
+        for (int i = 0; i < a.e_dim; ++i) acc = fmaf(e[i], a.Wp[s][(size_t)i * a.out_dim + o], acc);
+        a.out[((size_t)s * a.n_t + t) * a.out_dim + o] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// quaternion helpers (transforms.py:83-110, :113-163)
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void quat_to_matrix(const T* q, T* R) {   // R row-major 3x3
+    const T r = q[0], i = q[1], j = q[2], k = q[3];
+    const T two_s = T(2) / (r * r + i * i + j * j + k * k);
+    R[0] = T(1) - two_s * (j * j + k * k); R[1] = two_s * (i * j - k * r); R[2] = two_s * (i * k + j * r);
+    R[3] = two_s * (i * j + k * r); R[4] = T(1) - two_s * (i * i + k * k); R[5] = two_s * (j * k - i * r);
+    R[6] = two_s * (i * k - j * r); R[7] = two_s * (j * k + i * r); R[8] = T(1) - two_s * (i * i + j * j);
+}
+
+// quaternion_apply(q, p) = vec(q * (0,p) * conj(q))   -- not normalised, like the reference
+template <typename T>
+__device__ __forceinline__ void quat_apply(const T* q, const T* p, T* o) {
+    const T aw = q[0], ax = q[1], ay = q[2], az = q[3];
+    // t = q * (0, p)
+    const T tw = -ax * p[0] - ay * p[1] - az * p[2];
+    const T tx = aw * p[0] + ay * p[2] - az * p[1];
+    const T ty = aw * p[1] - ax * p[2] + az * p[0];
+    const T tz = aw * p[2] + ax * p[1] - ay * p[0];
+    // o = t * conj(q)
+    o[0] = -tw * ax + tx * aw - ty * az + tz * ay;
+    o[1] = -tw * ay + tx * az + ty * aw - tz * ax;
+    o[2] = -tw * az - tx * ay + ty * ax + tz * aw;
+}
+
+// D^2(R): Y2_a(R x) = sum_b D_ab Y2_b(x), via the symmetric traceless matrices M_a of the l=2 harmonics
+// (|M_a|_F^2 = 7.5 for every a):  D_ab = <R^T M_a R, M_b>_F / 7.5
+__device__ __forceinline__ void wigner_d2_from_R(const float* R, float* D) {
+    const float s15 = 3.872983346207417f, s5 = 2.23606797749979f;
+    // M_a as (xx, yy, zz, xy, xz, yz)
+    const float M[5][6] = {
+        {0.f, 0.f, 0.f, 0.f, 0.5f * s15, 0.f},          // sqrt15 x z
+        {0.f, 0.f, 0.f, 0.5f * s15, 0.f, 0.f},          // sqrt15 x y
+        {-0.5f * s5, s5, -0.5f * s5, 0.f, 0.f, 0.f},    // sqrt5 (y^2 - (x^2+z^2)/2)
+        {0.f, 0.f, 0.f, 0.f, 0.f, 0.5f * s15},          // sqrt15 y z
+        {-0.5f * s15, 0.f, 0.5f * s15, 0.f, 0.f, 0.f},  // sqrt15/2 (z^2 - x^2)
+    };
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        // full symmetric M
+        const float m[3][3] = {{M[a][0], M[a][3], M[a][4]}, {M[a][3], M[a][1], M[a][5]}, {M[a][4], M[a][5], M[a][2]}};
+        float t[3][3], n[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) t[i][j] = m[i][0] * R[0 * 3 + j] + m[i][1] * R[1 * 3 + j] + m[i][2] * R[2 * 3 + j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) n[i][j] = R[0 * 3 + i] * t[0][j] + R[1 * 3 + i] * t[1][j] + R[2 * 3 + i] * t[2][j];
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            const float ip = M[b][0] * n[0][0] + M[b][1] * n[1][1] + M[b][2] * n[2][2] +
+                             2.f * (M[b][3] * n[0][1] + M[b][4] * n[0][2] + M[b][5] * n[1][2]);
+            D[a * 5 + b] = ip * (1.0f / 7.5f);
+        }
+    }
+}
+
+struct QueryArgs {
+    const float* Ts; int n_t;       // (n_t, 7)
+    const float* qx; const float* qf; int n_q;   // (n_q,3), (n_q,F)
+    Irr irr;
+    float* x_out; float* f_out;     // (n_t*n_q, 3), (n_t*n_q, F)
+};
+
+__global__ void __launch_bounds__(128) query_transform_kernel(QueryArgs a) {
+    __shared__ float sR[9], sD2[25], sq[4], st[3];
+    const int t = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        const float* T = a.Ts + (size_t)t * 7;
+        // features: q / |q|, standardised (the sign does not change R); points: raw q like transform_points
+        const float nrm = sqrtf(T[0] * T[0] + T[1] * T[1] + T[2] * T[2] + T[3] * T[3]);
+        float qn[4] = {T[0] / nrm, T[1] / nrm, T[2] / nrm, T[3] / nrm};
+        float R[9]; quat_to_matrix<float>(qn, R);
+        for (int i = 0; i < 9; ++i) sR[i] = R[i];
+        float D[25]; wigner_d2_from_R(R, D);
+        for (int i = 0; i < 25; ++i) sD2[i] = D[i];
+        for (int i = 0; i < 4; ++i) sq[i] = T[i];
+        for (int i = 0; i < 3; ++i) st[i] = T[4 + i];
+    }
+    __syncthreads();
+    const int F = a.irr.dim();
+    for (int q = tid; q < a.n_q; q += blockDim.x) {
+        float p[3] = {a.qx[3 * q], a.qx[3 * q + 1], a.qx[3 * q + 2]}, o[3];
+        quat_apply<float>(sq, p, o);
+        float* xo = a.x_out + ((size_t)t * a.n_q + q) * 3;
+        xo[0] = o[0] + st[0]; xo[1] = o[1] + st[1]; xo[2] = o[2] + st[2];
+    }
+    for (int i = tid; i < a.n_q * F; i += blockDim.x) {
+        const int q = i / F, c = i % F;
+        const float* f = a.qf + (size_t)q * F;
+        float v;
+        if (c < a.irr.m0) v = f[c];
+        else if (c < a.irr.off2()) {
+            const int u = (c - a.irr.m0) / 3, m = (c - a.irr.m0) % 3;
+            const float* fu = f + a.irr.m0 + 3 * u;
+            v = sR[m * 3] * fu[0] + sR[m * 3 + 1] * fu[1] + sR[m * 3 + 2] * fu[2];
+        } else {
+            const int u = (c - a.irr.off2()) / 5, m = (c - a.irr.off2()) % 5;
+            const float* fu = f + a.irr.off2() + 5 * u;
+            v = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) v = fmaf(sD2[m * 5 + j], fu[j], v);
+        }
+        a.f_out[((size_t)t * a.n_q) * F + i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// score tensor products + final reduction
+// ---------------------------------------------------------------------------
+// uvu tensor product of two (M0,M1,M2) irreps with shared weights, outputs l<=1 only
+// (score_head.py:123-139; path/weight layout SURVEY.md App. E.2):
+//   k : l1 x l2 -> lo   weight block (mul1 x mul2)
+//   0 : 0 x 0 -> 0 | 1 : 0 x 1 -> 1 | 2 : 1 x 0 -> 1 | 3 : 1 x 1 -> 0 | 4 : 1 x 1 -> 1
+//   5 : 1 x 2 -> 1 | 6 : 2 x 1 -> 1 | 7 : 2 x 2 -> 0 | 8 : 2 x 2 -> 1
+struct ScoreArgs {
+    const float* Ts; int n_t;          // (n_t,7)
+    const float* qf_rot;               // (n_t*n_q, F): D(q) psi  (first TP operand, 'node_input')
+    const float* key_f;                // (n_t*n_q, F): field output (second operand, 'edge_attr')
+    const float* qx; const float* qw; int n_q;   // query coords (n_q,3), weights (n_q)
+    Irr irr;
+    const float* Wd[2];                // dtp weights (lin, ang), flat in path order
+    const float* Wl0[2]; const float* Wl1[2]; const float* bl[2];   // lin: (D0, 1+NV), (D1, NV), bias (1+NV)
+    int n_vec;                         // NV = 32
+    float lin_mult;
+    float* ang_out; float* lin_out;    // (n_t,3)
+};
+
+__global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
+    extern __shared__ float sm[];
+    const int M0 = a.irr.m0, M1 = a.irr.m1, M2 = a.irr.m2, F = a.irr.dim();
+    const int D0 = M0 + M1 + M2, D1 = M0 + 3 * M1 + 2 * M2;   // 112, 192 channels
+    const int NV = a.n_vec;
+    // t buffers: T[p][u][j]
+    const int tsz[9] = {M0, M0 * 3, M1, M1 * 3, M1 * 3, M1 * 5, M2 * 3, M2 * 5, M2 * 5};
+    int toff[10]; toff[0] = 0;
+    for (int p = 0; p < 9; ++p) toff[p + 1] = toff[p] + tsz[p];
+    float* sa = sm;                 // F
+    float* sb = sa + F;             // F
+    float* st = sb + F;             // toff[9]
+    float* sd0 = st + toff[9];      // D0
+    float* sd1 = sd0 + D0;          // D1*3
+    float* sy = sd1 + 3 * D1;       // 1 + NV + 3 NV
+    float* sres = sy + (1 + 4 * NV);   // [n_q][2][3]
+    const int t = blockIdx.x, tid = threadIdx.x;
+    // weight offsets (mul1 x mul2 row-major per path)
+    const int m1s[9] = {M0, M0, M1, M1, M1, M1, M2, M2, M2};
+    const int m2s[9] = {M0, M1, M0, M1, M1, M2, M1, M2, M2};
+    const int l2s[9] = {0, 1, 0, 1, 1, 2, 1, 2, 2};
+    int woff[10]; woff[0] = 0;
+    for (int p = 0; p < 9; ++p) woff[p + 1] = woff[p] + m1s[p] * m2s[p];
+    const int boff[3] = {0, M0, M0 + 3 * M1};   // offsets of l blocks in a feature vector
+
+    for (int q = 0; q < a.n_q; ++q) {
+        const size_t node = (size_t)t * a.n_q + q;
+        __syncthreads();
+        for (int i = tid; i < F; i += blockDim.x) { sa[i] = a.qf_rot[node * F + i]; sb[i] = a.key_f[node * F + i]; }
+        for (int which = 0; which < 2; ++which) {
+            __syncthreads();
+            // step 1: t_p[u][j] = sum_v W_p[u][v] b_{l2}[v][j]
+            for (int i = tid; i < toff[9]; i += blockDim.x) {
+                int p = 0;
+                while (i >= toff[p + 1]) ++p;
+                const int d2 = 2 * l2s[p] + 1;
+                const int u = (i - toff[p]) / d2, j = (i - toff[p]) % d2;
+                const float* w = a.Wd[which] + woff[p] + (size_t)u * m2s[p];
+                const float* b = sb + boff[l2s[p]] + j;
+                float acc = 0.f;
+                for (int v = 0; v < m2s[p]; ++v) acc = fmaf(__ldg(w + v), b[v * d2], acc);
+                st[i] = acc;
+            }
+            __syncthreads();
+            // step 2: d[p][u][:] = cg(a[u], t_p[u])  ->  sd0 [112] , sd1 [192][3] in i_out order
+            //   lo=0 block: [p0 (M0) | p3 (M1) | p7 (M2)] ; lo=1 block: [p1 (M0) | p2 (M1) | p4 (M1) | p5 (M1) | p6 (M2) | p8 (M2)]
+            const int ntask = 2 * M0 + 4 * M1 + 3 * M2;
+            for (int i = tid; i < ntask; i += blockDim.x) {
+                int p, u;
+                if (i < M0) { p = 0; u = i; }
+                else if (i < 2 * M0) { p = 1; u = i - M0; }
+                else if (i < 2 * M0 + 4 * M1) { p = 2 + (i - 2 * M0) / M1; u = (i - 2 * M0) % M1; }
+                else { p = 6 + (i - 2 * M0 - 4 * M1) / M2; u = (i - 2 * M0 - 4 * M1) % M2; }
+                float o[3];
+                switch (p) {
+                    case 0: sd0[u] = sa[u] * st[toff[0] + u]; break;
+                    case 1: { const float x = sa[u]; const float* y = st + toff[1] + 3 * u;
+                              sd1[(u) * 3 + 0] = x * y[0]; sd1[(u) * 3 + 1] = x * y[1]; sd1[(u) * 3 + 2] = x * y[2]; } break;
+                    case 2: { const float* x = sa + boff[1] + 3 * u; const float y = st[toff[2] + u];
+                              float* d = sd1 + (M0 + u) * 3; d[0] = x[0] * y; d[1] = x[1] * y; d[2] = x[2] * y; } break;
+                    case 3: cg_110(sa + boff[1] + 3 * u, st + toff[3] + 3 * u, o); sd0[M0 + u] = o[0]; break;
+                    case 4: { cg_111(sa + boff[1] + 3 * u, st + toff[4] + 3 * u, o);
+                              float* d = sd1 + (M0 + M1 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+                    case 5: { cg_121(sa + boff[1] + 3 * u, st + toff[5] + 5 * u, o);
+                              float* d = sd1 + (M0 + 2 * M1 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+                    case 6: { cg_211(sa + boff[2] + 5 * u, st + toff[6] + 3 * u, o);
+                              float* d = sd1 + (M0 + 3 * M1 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+                    case 7: cg_220(sa + boff[2] + 5 * u, st + toff[7] + 5 * u, o); sd0[M0 + M1 + u] = o[0]; break;
+                    default: { cg_221(sa + boff[2] + 5 * u, st + toff[8] + 5 * u, o);
+                               float* d = sd1 + (M0 + 3 * M1 + M2 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+                }
+            }
+            __syncthreads();
+            // step 3: linear  (D0 -> 1+NV scalars with bias ; D1 -> NV vectors)
+            for (int i = tid; i < (1 + NV) + 3 * NV; i += blockDim.x) {
+                float acc;
+                if (i < 1 + NV) {
+                    acc = a.bl[which][i];
+                    for (int r = 0; r < D0; ++r) acc = fmaf(sd0[r], __ldg(a.Wl0[which] + (size_t)r * (1 + NV) + i), acc);
+                } else {
+                    const int c = (i - 1 - NV) / 3, k = (i - 1 - NV) % 3;
+                    acc = 0.f;
+                    for (int r = 0; r < D1; ++r) acc = fmaf(sd1[r * 3 + k], __ldg(a.Wl1[which] + (size_t)r * NV + c), acc);
+                }
+                sy[i] = acc;
+            }
+            __syncthreads();
+            // step 4: gate, mean over the NV vectors (drop the scalar), rotate by q^-1
+            if (tid < 3) {
+                float s = 0.f;
+                for (int c = 0; c < NV; ++c) s += sy[1 + NV + 3 * c + tid] * (kCSigmoid * sigmoidf_(sy[1 + c]));
+                sres[(q * 2 + which) * 3 + tid] = s / (float)NV;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const float* T = a.Ts + (size_t)t * 7;
+        const float qinv[4] = {T[0], -T[1], -T[2], -T[3]};
+        float lin[3] = {0.f, 0.f, 0.f}, ang[3] = {0.f, 0.f, 0.f};
+        for (int q = 0; q < a.n_q; ++q) {
+            float l[3], s[3];
+            quat_apply<float>(qinv, sres + (q * 2 + 0) * 3, l);
+            quat_apply<float>(qinv, sres + (q * 2 + 1) * 3, s);
+            const float px = a.qx[3 * q] / a.lin_mult, py = a.qx[3 * q + 1] / a.lin_mult, pz = a.qx[3 * q + 2] / a.lin_mult;
+            const float ox = py * l[2] - pz * l[1], oy = pz * l[0] - px * l[2], oz = px * l[1] - py * l[0];
+            const float w = a.qw[q];
+            lin[0] += w * l[0]; lin[1] += w * l[1]; lin[2] += w * l[2];
+            ang[0] += w * (ox + s[0]); ang[1] += w * (oy + s[1]); ang[2] += w * (oz + s[2]);
+        }
+        for (int i = 0; i < 3; ++i) { a.lin_out[(size_t)t * 3 + i] = lin[i]; a.ang_out[(size_t)t * 3 + i] = ang[i]; }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pose update (float64)
+// ---------------------------------------------------------------------------
+struct PoseArgs {
+    double* T; int n_t;                 // (n_t,7) in place
+    const float* ang; const float* lin; // dimensionless scores (n_t,3)
+    const double* noise;                // (n_t,6) standard normals (ang, lin) or null -> Philox
+    unsigned long long seed, offset;
+    double t, ang_mult, lin_mult, alpha_ang, alpha_lin, temperature;
+    double* traj_out;                   // optional (n_t,7) copy of the new pose
+};
+
+__global__ void pose_update_kernel(PoseArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_t) return;
+    double z[6];
+    if (a.noise) {
+        for (int k = 0; k < 6; ++k) z[k] = a.noise[(size_t)i * 6 + k];
+    } else {
+        curandStatePhilox4_32_10_t st;
+        curand_init(a.seed, (unsigned long long)i, a.offset, &st);
+        for (int k = 0; k < 6; k += 2) { double2 n = curand_normal2_double(&st); z[k] = n.x; z[k + 1] = n.y; }
+    }
+    double* T = a.T + (size_t)i * 7;
+    const double sq_t = sqrt(a.t);
+    double ang_disp[3], lin_disp[3];
+    for (int k = 0; k < 3; ++k) {
+        const double as = (double)a.ang[(size_t)i * 3 + k] / (a.ang_mult * sq_t);
+        const double ls = (double)a.lin[(size_t)i * 3 + k] / (a.lin_mult * sq_t);
+        ang_disp[k] = (a.alpha_ang / 2) * as + sqrt(a.temperature * a.alpha_ang) * z[k];
+        lin_disp[k] = (a.alpha_lin / 2) * ls + sqrt(a.temperature * a.alpha_lin) * z[3 + k];
+    }
+    const double q[4] = {T[0], T[1], T[2], T[3]};
+    // L = T[q_indices] * q_factor   (score_model_base.py:31-32,188)
+    const int qi[4][3] = {{1, 2, 3}, {0, 3, 2}, {3, 0, 1}, {2, 1, 0}};
+    const double qf[4][3] = {{-0.5, -0.5, -0.5}, {0.5, -0.5, 0.5}, {0.5, 0.5, -0.5}, {-0.5, 0.5, 0.5}};
+    double qn[4], nrm = 0;
+    for (int r = 0; r < 4; ++r) {
+        double dq = 0;
+        for (int c = 0; c < 3; ++c) dq += q[qi[r][c]] * qf[r][c] * ang_disp[c];
+        qn[r] = q[r] + dq;
+        nrm += qn[r] * qn[r];
+    }
+    nrm = sqrt(nrm);
+    double dx[3];
+    quat_apply<double>(q, lin_disp, dx);
+    for (int r = 0; r < 4; ++r) T[r] = qn[r] / nrm;
+    for (int k = 0; k < 3; ++k) T[4 + k] += dx[k];
+    if (a.traj_out) for (int k = 0; k < 7; ++k) a.traj_out[(size_t)i * 7 + k] = T[k];
+}
+
+__global__ void cast_pose_kernel(const double* __restrict__ T, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)T[i];
+}
+
+}  // namespace dedf
+
+using namespace dedf;
+
+extern "C" int dedf_time_embed(const dedf_time_desc* d, const float* time, int n_t, float* out, cudaStream_t stream) {
+    if (!d || !time || !out || d->n_scales < 1 || d->n_scales > DEDF_MAX_SCALES) return DEDF_ERR_ARG;
+    if (n_t <= 0) return DEDF_OK;
+    TimeArgs a{};
+    a.time = time; a.n_t = n_t; a.max_time = d->max_time; a.enc_n = d->enc_n; a.enc_dim = d->enc_dim; a.enc_freq = d->enc_freq;
+    if (!a.enc_freq) return DEDF_ERR_ARG;
+    a.h_dim = d->h_dim; a.e_dim = d->e_dim; a.out_dim = d->out_dim; a.n_scales = d->n_scales; a.out = out;
+    for (int s = 0; s < d->n_scales; ++s) {
+        a.W1[s] = d->W1[s]; a.b1[s] = d->b1[s]; a.W2[s] = d->W2[s]; a.b2[s] = d->b2[s]; a.Wp[s] = d->Wp[s]; a.bp[s] = d->bp[s];
+        if (!a.W1[s] || !a.b1[s] || !a.W2[s] || !a.b2[s] || !a.Wp[s] || !a.bp[s]) return DEDF_ERR_ARG;
+    }
+    const size_t smem = (size_t)(a.enc_dim + a.h_dim + a.e_dim) * sizeof(float);
+    time_embed_kernel<<<dim3(n_t, d->n_scales), 128, smem, stream>>>(a);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_query_transform(const float* Ts, int n_t, const float* qx, const float* qf, int n_q,
+                                    const int* irr, float* x_out, float* f_out, cudaStream_t stream) {
+    if (!Ts || !qx || !qf || !irr || !x_out || !f_out) return DEDF_ERR_ARG;
+    if (n_t <= 0 || n_q <= 0) return DEDF_OK;
+    QueryArgs a{Ts, n_t, qx, qf, n_q, Irr{irr[0], irr[1], irr[2]}, x_out, f_out};
+    query_transform_kernel<<<n_t, 128, 0, stream>>>(a);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, const float* key_f, const float* qx,
+                             const float* qw, int n_q, const int* irr, const float* const* Wd, const float* const* Wl0,
+                             const float* const* Wl1, const float* const* bl, int n_vec, float lin_mult,
+                             float* ang_out, float* lin_out, cudaStream_t stream) {
+    if (!Ts || !qf_rot || !key_f || !qx || !qw || !irr || !Wd || !Wl0 || !Wl1 || !bl || !ang_out || !lin_out) return DEDF_ERR_ARG;
+    if (n_t <= 0) return DEDF_OK;
+    ScoreArgs a{};
+    a.Ts = Ts; a.n_t = n_t; a.qf_rot = qf_rot; a.key_f = key_f; a.qx = qx; a.qw = qw; a.n_q = n_q;
+    a.irr = Irr{irr[0], irr[1], irr[2]};
+    for (int i = 0; i < 2; ++i) { a.Wd[i] = Wd[i]; a.Wl0[i] = Wl0[i]; a.Wl1[i] = Wl1[i]; a.bl[i] = bl[i];
+                                  if (!Wd[i] || !Wl0[i] || !Wl1[i] || !bl[i]) return DEDF_ERR_ARG; }
+    a.n_vec = n_vec; a.lin_mult = lin_mult; a.ang_out = ang_out; a.lin_out = lin_out;
+    const int M0 = a.irr.m0, M1 = a.irr.m1, M2 = a.irr.m2, F = a.irr.dim();
+    const int tt = M0 + 3 * M0 + M1 + 3 * M1 + 3 * M1 + 5 * M1 + 3 * M2 + 5 * M2 + 5 * M2;
+    const int D0 = M0 + M1 + M2, D1 = M0 + 3 * M1 + 2 * M2;
+    const size_t smem = (size_t)(2 * F + tt + D0 + 3 * D1 + 1 + 4 * n_vec + 6 * n_q) * sizeof(float);
+    if (smem > 96 * 1024) return DEDF_ERR_UNSUPPORTED;
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(score_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); done = true; }
+    score_tp_kernel<<<n_t, 256, smem, stream>>>(a);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_pose_update(double* T, int n_t, const float* ang, const float* lin, const double* noise,
+                                unsigned long long seed, unsigned long long offset, double t, double ang_mult,
+                                double lin_mult, double alpha_ang, double alpha_lin, double temperature,
+                                double* traj_out, float* T_f32_out, cudaStream_t stream) {
+    if (!T || !ang || !lin) return DEDF_ERR_ARG;
+    if (n_t <= 0) return DEDF_OK;
+    PoseArgs a{T, n_t, ang, lin, noise, seed, offset, t, ang_mult, lin_mult, alpha_ang, alpha_lin, temperature, traj_out};
+    pose_update_kernel<<<(n_t + 127) / 128, 128, 0, stream>>>(a);
+    DEDF_CHECK_LAUNCH();
+    if (T_f32_out) {
+        cast_pose_kernel<<<(n_t * 7 + 255) / 256, 256, 0, stream>>>(T, n_t * 7, T_f32_out);
+        DEDF_CHECK_LAUNCH();
+    }
+    return DEDF_OK;
+}

@@ -1,0 +1,230 @@
+// Per-node kernels: equivariant layer norm -> block-diagonal linear (LinearRS /
+// FullyConnectedTensorProductRescale with a 1x0e second operand) -> gate / residual.
+//
+// Replaces, on the reference's hot path (/root/reference/diffusion_edf):
+//   equiformer/layer_norm.py:91-156        EquivariantLayerNormV2 ('component', affine)
+//   equiformer/tensor_product_rescale.py:176-185, :155-173, :241-268   LinearRS / FCTP (+SwishGate)
+//   equiformer/fast_activation.py:210-224  Gate
+//   skip.py:13-35                          ProjectIfMismatch
+//   gnn_block.py:51-57, block.py:51-57     FeedForwardNetwork
+// LinearRS semantics: per l,  y[w, m] = sum_u W_l[u, w] x[u, m];
+// bias only on the 0e block; nothing is rescaled at run time.
+#include "common.cuh"
+#include "gemm_tile.cuh"
+#include "../../include/dedf.h"
+
+namespace dedf {
+
+constexpr int kNodeTN = 16;        // nodes per tile
+constexpr int kNodeThreads = 256;
+
+struct NodeLinArgs {
+    const float* x; int n;                 // (n, Fin)
+    Irr in, out;                           // irreps of x and of the linear output (pre-gate)
+    const float* W0; const float* W1; const float* W2;   // (in.m_l, out.m_l) row-major; null if either mul is 0
+    const float* bias0;                    // (out.m0) or null
+    // optional layer-norm prologue
+    const float* ln_w; const float* ln_b; float ln_eps; int ln;
+    // epilogue
+    int gate;                              // 1: out.m0 = scalars + gates, gates = out.m1 + out.m2
+    const float* res; float res_scale;     // y = (y + res) * res_scale   (res may be null)
+    float* y;                              // (n, Fy)
+};
+
+__global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a, int lda0, int lda1, int lda2, int ldo) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int TN = kNodeTN;
+    const int Fin = a.in.dim(), Fout = a.out.dim();
+    float* A0 = smem;                       // [TN][lda0]
+    float* A1 = A0 + TN * lda0;             // [3 TN][lda1]  row = k * TN + n
+    float* A2 = A1 + 3 * TN * lda1;         // [5 TN][lda2]
+    float* O = A2 + 5 * TN * lda2;          // [TN][ldo]  linear output in e3nn layout
+    float* s_scale = O + TN * ldo;          // [TN][3]    layer-norm scale per l
+    float* s_mean = s_scale + TN * 3;       // [TN]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_tiles = (a.n + TN - 1) / TN;
+    const int Fy = a.gate ? (Fout - a.out.m1 - a.out.m2) : Fout;
+    const int m0s = a.gate ? (a.out.m0 - a.out.m1 - a.out.m2) : a.out.m0;   // scalars that survive the gate
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int n0 = tile * TN;
+        const int rows = min(TN, a.n - n0);
+        __syncthreads();
+        // ---- layer-norm statistics: one warp per node --------------------------------
+        if (a.ln) {
+            for (int r = warp; r < TN; r += kNodeThreads / 32) {
+                float mean = 0.f, sc0 = 0.f, sc1 = 0.f, sc2 = 0.f;
+                if (r < rows) {
+                    const float* xr = a.x + (size_t)(n0 + r) * Fin;
+                    float s = 0.f;
+                    for (int c = lane; c < a.in.m0; c += 32) s += xr[c];
+                    s = warp_sum(s);
+                    mean = (a.in.m0 > 0) ? s / (float)a.in.m0 : 0.f;
+                    float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+                    for (int c = lane; c < a.in.m0; c += 32) { const float t = xr[c] - mean; q0 += t * t; }
+                    for (int c = lane; c < 3 * a.in.m1; c += 32) { const float t = xr[a.in.off1() + c]; q1 += t * t; }
+                    for (int c = lane; c < 5 * a.in.m2; c += 32) { const float t = xr[a.in.off2() + c]; q2 += t * t; }
+                    q0 = warp_sum(q0); q1 = warp_sum(q1); q2 = warp_sum(q2);
+                    // field.pow(2).mean(-1) then mean over mul  == sum / (mul * d)
+                    sc0 = (a.in.m0 > 0) ? rsqrtf(q0 / (float)a.in.m0 + a.ln_eps) : 0.f;
+                    sc1 = (a.in.m1 > 0) ? rsqrtf(q1 / (float)(3 * a.in.m1) + a.ln_eps) : 0.f;
+                    sc2 = (a.in.m2 > 0) ? rsqrtf(q2 / (float)(5 * a.in.m2) + a.ln_eps) : 0.f;
+                }
+                if (lane == 0) { s_mean[r] = mean; s_scale[r * 3] = sc0; s_scale[r * 3 + 1] = sc1; s_scale[r * 3 + 2] = sc2; }
+            }
+            __syncthreads();
+        }
+        // ---- stage A tiles (normalised on the fly) -----------------------------------
+        for (int i = tid; i < TN * Fin; i += kNodeThreads) {
+            const int r = i / Fin, c = i % Fin;
+            float v = (r < rows) ? a.x[(size_t)(n0 + r) * Fin + c] : 0.f;
+            if (c < a.in.m0) {
+                if (a.ln) v = (v - s_mean[r]) * s_scale[r * 3] * a.ln_w[c] + a.ln_b[c];
+                A0[r * lda0 + c] = v;
+            } else if (c < a.in.off2()) {
+                const int u = (c - a.in.m0) / 3, k = (c - a.in.m0) % 3;
+                if (a.ln) v = v * s_scale[r * 3 + 1] * a.ln_w[a.in.m0 + u];
+                A1[(k * TN + r) * lda1 + u] = v;
+            } else {
+                const int u = (c - a.in.off2()) / 5, k = (c - a.in.off2()) % 5;
+                if (a.ln) v = v * s_scale[r * 3 + 2] * a.ln_w[a.in.m0 + a.in.m1 + u];
+                A2[(k * TN + r) * lda2 + u] = v;
+            }
+        }
+        __syncthreads();
+        // ---- block-diagonal GEMM -----------------------------------------------------
+        const int cg0 = (a.out.m0 + 3) / 4, cg1 = (a.out.m1 + 3) / 4, cg2 = (a.out.m2 + 3) / 4;
+        const int I0 = (a.W0 ? (TN / 4) * cg0 : 0), I1 = (a.W1 ? (3 * TN / 4) * cg1 : 0), I2 = (a.W2 ? (5 * TN / 4) * cg2 : 0);
+        // outputs without a path are zero (e.g. l>0 of the 3x0e input embedding)
+        for (int i = tid; i < TN * Fout; i += kNodeThreads) {
+            const int c = i % Fout;
+            const bool has = (c < a.out.m0) ? (a.W0 != nullptr) : (c < a.out.off2()) ? (a.W1 != nullptr) : (a.W2 != nullptr);
+            if (!has) O[(i / Fout) * ldo + c] = 0.f;
+        }
+        for (int item = tid; item < I0 + I1 + I2; item += kNodeThreads) {
+            float acc[4][4] = {};
+            if (item < I0) {
+                const int cg = item % cg0, rg = item / cg0;
+                gemm_item_4x4<false>(A0, lda0, TN / 4, rg, a.W0, a.out.m0, 4 * cg, a.in.m0, acc);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = 4 * cg + j, r = rg + i * (TN / 4);
+                        if (c < a.out.m0) O[r * ldo + c] = acc[i][j] + (a.bias0 ? a.bias0[c] : 0.f);
+                    }
+            } else if (item < I0 + I1) {
+                const int t = item - I0, cg = t % cg1, rg = t / cg1;
+                gemm_item_4x4<false>(A1, lda1, 3 * TN / 4, rg, a.W1, a.out.m1, 4 * cg, a.in.m1, acc);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = 4 * cg + j, row = rg + i * (3 * TN / 4), k = row / TN, r = row % TN;
+                        if (c < a.out.m1) O[r * ldo + a.out.off1() + c * 3 + k] = acc[i][j];
+                    }
+            } else {
+                const int t = item - I0 - I1, cg = t % cg2, rg = t / cg2;
+                gemm_item_4x4<false>(A2, lda2, 5 * TN / 4, rg, a.W2, a.out.m2, 4 * cg, a.in.m2, acc);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = 4 * cg + j, row = rg + i * (5 * TN / 4), k = row / TN, r = row % TN;
+                        if (c < a.out.m2) O[r * ldo + a.out.off2() + c * 5 + k] = acc[i][j];
+                    }
+            }
+        }
+        __syncthreads();
+        // ---- epilogue: gate / residual, coalesced store --------------------------------
+        for (int i = tid; i < rows * Fy; i += kNodeThreads) {
+            const int r = i / Fy, c = i % Fy;
+            const float* o = O + r * ldo;
+            float v;
+            if (!a.gate) {
+                v = o[c];
+            } else if (c < m0s) {
+                v = kCSilu * siluf_(o[c]);
+            } else if (c < m0s + 3 * a.out.m1) {
+                const int u = (c - m0s) / 3;
+                v = o[a.out.off1() + (c - m0s)] * (kCSigmoid * sigmoidf_(o[m0s + u]));
+            } else {
+                const int u = (c - m0s - 3 * a.out.m1) / 5;
+                v = o[a.out.off2() + (c - m0s - 3 * a.out.m1)] * (kCSigmoid * sigmoidf_(o[m0s + a.out.m1 + u]));
+            }
+            if (a.res) v = (v + a.res[(size_t)(n0 + r) * Fy + c]) * a.res_scale;
+            a.y[(size_t)(n0 + r) * Fy + c] = v;
+        }
+    }
+}
+
+// y[i, :] = x[idx[i], :]
+__global__ void gather_rows_kernel(const float* __restrict__ x, const long long* __restrict__ idx, int n, int F,
+                                   float* __restrict__ y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n * F; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / F), c = (int)(i % F);
+        y[i] = x[(size_t)idx[r] * F + c];
+    }
+}
+
+// y = (a + b) * s
+__global__ void add_scale_kernel(const float* __restrict__ a, const float* __restrict__ b, float s, long long n,
+                                 float* __restrict__ y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = (a[i] + b[i]) * s;
+}
+
+}  // namespace dedf
+
+using namespace dedf;
+
+extern "C" int dedf_node_linear(const float* x, int n, const int* irr_in, const int* irr_out, const float* W0,
+                                const float* W1, const float* W2, const float* bias0, const float* ln_w,
+                                const float* ln_b, float ln_eps, int gate, const float* res, float res_scale,
+                                float* y, cudaStream_t stream) {
+    if (!x || !irr_in || !irr_out || !y) return DEDF_ERR_ARG;
+    NodeLinArgs a{};
+    a.x = x; a.n = n;
+    a.in = Irr{irr_in[0], irr_in[1], irr_in[2]};
+    a.out = Irr{irr_out[0], irr_out[1], irr_out[2]};
+    // a block needs weights iff both sides have that l; a missing path leaves zeros
+    a.W0 = (a.in.m0 && a.out.m0) ? W0 : nullptr;
+    a.W1 = (a.in.m1 && a.out.m1) ? W1 : nullptr;
+    a.W2 = (a.in.m2 && a.out.m2) ? W2 : nullptr;
+    if ((a.in.m0 && a.out.m0 && !W0) || (a.in.m1 && a.out.m1 && !W1) || (a.in.m2 && a.out.m2 && !W2)) return DEDF_ERR_ARG;
+    a.bias0 = bias0;
+    a.ln = (ln_w != nullptr); a.ln_w = ln_w; a.ln_b = ln_b; a.ln_eps = ln_eps;
+    if (a.ln && a.in.m0 && !ln_b) return DEDF_ERR_ARG;
+    a.gate = gate; a.res = res; a.res_scale = res_scale; a.y = y;
+    if (gate && a.out.m0 < a.out.m1 + a.out.m2) return DEDF_ERR_ARG;
+    if (n <= 0) return DEDF_OK;
+    const int lda0 = pad_lda(a.in.m0), lda1 = pad_lda(a.in.m1), lda2 = pad_lda(a.in.m2);
+    const int ldo = a.out.dim() + 1;
+    const size_t smem = ((size_t)kNodeTN * lda0 + 3 * kNodeTN * lda1 + 5 * kNodeTN * lda2 + (size_t)kNodeTN * ldo + kNodeTN * 4) * sizeof(float);
+    if (smem > 200 * 1024) return DEDF_ERR_UNSUPPORTED;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaFuncSetAttribute(node_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        attr_smem = 200 * 1024;
+    }
+    const int n_tiles = (n + kNodeTN - 1) / kNodeTN;
+    node_linear_kernel<<<grid_for(n_tiles, 1, kNumSMs * 4), kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_gather_rows(const float* x, const long long* idx, int n, int F, float* y, cudaStream_t stream) {
+    if (!x || !idx || !y || F <= 0) return DEDF_ERR_ARG;
+    if (n <= 0) return DEDF_OK;
+    gather_rows_kernel<<<grid_for((long long)n * F, 256, kNumSMs * 8), 256, 0, stream>>>(x, idx, n, F, y);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_add_scale(const float* a, const float* b, float s, long long n, float* y, cudaStream_t stream) {
+    if (!a || !b || !y) return DEDF_ERR_ARG;
+    if (n <= 0) return DEDF_OK;
+    add_scale_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, stream>>>(a, b, s, n, y);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}

@@ -1,0 +1,302 @@
+"""Parameter containers that mirror the reference's module tree (so that
+``state_dict`` keys agree with checkpoints trained by the reference, SURVEY.md
+App. C) and run their arithmetic through the CUDA kernels in libdedf.so.
+
+Reference classes mirrored (under /root/reference/diffusion_edf):
+  equiformer/tensor_product_rescale.py:176-185 LinearRS, :155-173 / :241-268 FCTP (+SwishGate)
+  equiformer/layer_norm.py:64-156 EquivariantLayerNormV2
+  equiformer/radial_func.py:11-59 RadialProfile
+  equiformer/graph_attention_transformer.py:60-135 SeparableFCTP
+  graph_attention.py:16-122 GraphAttentionMLP, :138-273 GraphAttentionMLP2
+  gnn_block.py:21-57 / block.py:21-57 FeedForwardNetwork
+  skip.py:13-35 ProjectIfMismatch
+  radial_func.py:168-227 GaussianRadialBasis, :231-278 GaussianRadialBasisLayerFiniteCutoff
+None of the ``forward`` methods falls back to PyTorch arithmetic.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from .irreps import Irreps, dtp_numel, dtp_out, gate_pre
+
+
+def _versions(mod: nn.Module):
+    return tuple((p.data_ptr(), p._version) for p in mod.parameters())
+
+
+class _Packed:
+    """Cache of kernel-layout copies of a module's parameters, rebuilt when they change."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, mod: nn.Module, build):
+        key = _versions(mod)
+        if key != self._key:
+            with torch.no_grad():
+                self._val = build()
+            self._key = key
+        return self._val
+
+
+class _TP(nn.Module):
+    """Stands in for e3nn's o3.TensorProduct: only owns ``weight`` (key ``tp.weight``)."""
+
+    def __init__(self, numel: int, internal: bool):
+        super().__init__()
+        if internal and numel > 0:
+            self.weight = nn.Parameter(torch.randn(numel))
+        else:
+            self.register_parameter("weight", None)
+
+
+class LinearRS(nn.Module):
+    """Block-diagonal (per-l) linear map; also FullyConnectedTensorProductRescale with a 1x0e second operand."""
+
+    def __init__(self, irreps_in, irreps_out, bias: bool = True, rescale: bool = True):
+        super().__init__()
+        self.irreps_in, self.irreps_out = Irreps(irreps_in), Irreps(irreps_out)
+        shapes = [(a, b) for a, b in zip(self.irreps_in.m, self.irreps_out.m)]
+        self._shapes = [(a, b) if (a and b) else None for a, b in shapes]
+        numel = sum(a * b for s in self._shapes if s for a, b in [s])
+        self.tp = _TP(numel, True)
+        self.bias = nn.ParameterList([nn.Parameter(torch.zeros(self.irreps_out.m[0]))] if (bias and self.irreps_out.m[0]) else [])
+        if rescale and numel:
+            with torch.no_grad():      # tensor_product_rescale.py:97-120: weights ~ N(0,1) / sqrt(fan_in)
+                off = 0
+                for s in self._shapes:
+                    if s:
+                        self.tp.weight[off:off + s[0] * s[1]].mul_(1.0 / math.sqrt(s[0]))
+                        off += s[0] * s[1]
+        self._packed = _Packed()
+
+    def packed(self):
+        def build():
+            w, off, out = self.tp.weight, 0, []
+            for s in self._shapes:
+                if s:
+                    out.append(w[off:off + s[0] * s[1]].detach().clone().contiguous())
+                    off += s[0] * s[1]
+                else:
+                    out.append(None)
+            b = self.bias[0].detach().contiguous() if len(self.bias) else None
+            return out, b
+        return self._packed.get(self, build)
+
+    def forward(self, x: torch.Tensor, ln: Optional["EquivariantLayerNormV2"] = None, gate: bool = False,
+                res: Optional[torch.Tensor] = None, res_scale: float = 1.0) -> torch.Tensor:
+        W, b = self.packed()
+        lnp = None
+        if ln is not None:
+            lnp = (ln.affine_weight.detach(), ln.affine_bias.detach())
+        return ops.node_linear(x.contiguous(), self.irreps_in.m, self.irreps_out.m, W, b, ln=lnp,
+                               ln_eps=ln.eps if ln is not None else 1e-5, gate=gate, res=res, res_scale=res_scale)
+
+
+class EquivariantLayerNormV2(nn.Module):
+    """Parameters only; the normalisation runs as the prologue of the following LinearRS kernel."""
+
+    def __init__(self, irreps, eps: float = 1e-5, affine: bool = True):
+        super().__init__()
+        self.irreps, self.eps = Irreps(irreps), eps
+        assert affine
+        self.affine_weight = nn.Parameter(torch.ones(self.irreps.num_irreps))
+        self.affine_bias = nn.Parameter(torch.zeros(self.irreps.m[0]))
+
+
+class ProjectIfMismatch(nn.Module):
+    def __init__(self, irreps_in, irreps_out, bias: bool = True, layernorm: bool = True):
+        super().__init__()
+        self.irreps_in, self.irreps_out = Irreps(irreps_in), Irreps(irreps_out)
+        if self.irreps_in == self.irreps_out:
+            self.skip, self.layernorm = nn.Identity(), nn.Identity()
+        else:
+            self.layernorm = EquivariantLayerNormV2(self.irreps_in) if layernorm else nn.Identity()
+            self.skip = LinearRS(self.irreps_in, self.irreps_out, bias=bias, rescale=True)
+
+    @property
+    def is_identity(self) -> bool:
+        return isinstance(self.skip, nn.Identity)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.is_identity:
+            return x
+        ln = self.layernorm if isinstance(self.layernorm, EquivariantLayerNormV2) else None
+        return self.skip(x, ln=ln)
+
+
+class FeedForwardNetwork(nn.Module):
+    def __init__(self, irreps_in, irreps_out, irreps_mid):
+        super().__init__()
+        self.irreps_mid = Irreps(irreps_mid)
+        self.fctp_1 = LinearRS(irreps_in, gate_pre(self.irreps_mid))     # ...SwishGate: linear to the pre-gate irreps
+        self.fctp_2 = LinearRS(self.irreps_mid, irreps_out)
+
+    def forward(self, x: torch.Tensor, ln: EquivariantLayerNormV2, res: torch.Tensor) -> torch.Tensor:
+        """res + fctp_2(Gate(fctp_1(LN(x))))"""
+        h = self.fctp_1(x, ln=ln, gate=True)
+        return self.fctp_2(h, res=res, res_scale=1.0)
+
+
+class RadialProfile(nn.Module):
+    def __init__(self, ch_list: Sequence[int]):
+        super().__init__()
+        mods, cin = [], ch_list[0]
+        for i in range(1, len(ch_list)):
+            last = i == len(ch_list) - 1
+            mods.append(nn.Linear(cin, ch_list[i], bias=not last))
+            cin = ch_list[i]
+            if last:
+                break
+            mods.append(nn.LayerNorm(ch_list[i]))
+            mods.append(nn.SiLU())
+        self.net = nn.Sequential(*mods)
+        self.offset = nn.Parameter(torch.zeros(ch_list[-1]))
+        bound = 1 / math.sqrt(ch_list[-2])
+        nn.init.uniform_(self.offset, -bound, bound)
+        self.ch_list = list(ch_list)
+        self._packed = _Packed()
+
+    def packed(self):
+        def build():
+            lin = [m for m in self.net if isinstance(m, nn.Linear)]
+            lns = [m for m in self.net if isinstance(m, nn.LayerNorm)]
+            W = [m.weight.detach().t().contiguous() for m in lin]
+            b = [m.bias.detach().contiguous() if m.bias is not None else None for m in lin]
+            g = [m.weight.detach().contiguous() for m in lns]
+            bb = [m.bias.detach().contiguous() for m in lns]
+            return W, b, g, bb, self.offset.detach().contiguous()
+        return self._packed.get(self, build)
+
+    def fill_desc(self, d: L.MlpDesc, first_layer: int = 0) -> None:
+        """Describe the MLP layers starting at slot ``first_layer`` of ``d`` (dims[first_layer] must be ch_list[0])."""
+        W, b, g, bb, off = self.packed()
+        n = len(W)
+        assert first_layer + n <= L.MLP_MAX_LAYERS
+        for i in range(n):
+            s = first_layer + i
+            d.dims[s] = self.ch_list[i]
+            d.dims[s + 1] = self.ch_list[i + 1]
+            d.W[s] = L.ptr(W[i])
+            d.b[s] = L.ptr(b[i])
+            last = i == n - 1
+            d.ln_g[s] = None if last else L.ptr(g[i])
+            d.ln_b[s] = None if last else L.ptr(bb[i])
+            d.flags[s] = 0 if last else 3
+        d.n_layers = first_layer + n
+        d.out_offset = L.ptr(off)
+        # keep the packed tensors alive for as long as the descriptor is
+        d._keep = (W, b, g, bb, off)
+
+
+class GaussianRadialBasisLayerFiniteCutoff(nn.Module):
+    """Parameters of the UNet's edge-length encoder; evaluated inside dedf_edge_mlp (RBF input mode)."""
+
+    def __init__(self, num_basis: int, cutoff: float):
+        super().__init__()
+        self.num_basis, self.cutoff = num_basis, float(cutoff)
+        self.offset = 0.01 * self.cutoff
+        self.mean = nn.Parameter(torch.linspace(0, 1.0, num_basis + 2)[1:-1].unsqueeze(0))
+        self.std_logit = nn.Parameter(torch.full((1, num_basis), math.log(math.exp(2.0 / num_basis) - 1)))
+        self.weight_logit = nn.Parameter(torch.full((1, num_basis), -math.log(4.0 / 1.0 - 1)))
+
+
+class _GaussianParamModule(nn.Module):
+    def __init__(self, dim: int, max_weight: float = 4.0):
+        super().__init__()
+        self.std_logit = nn.Parameter(torch.full((1, dim), math.log(math.exp(2.0 / dim) - 1), dtype=torch.float32))
+        self.weight_logit = nn.Parameter(torch.full((1, dim), -math.log(max_weight / 1.0 - 1), dtype=torch.float32))
+        self.mean = nn.Parameter(torch.linspace(0.0, 1.0, dim + 2, dtype=torch.float32)[1:-1].unsqueeze(0))
+
+
+class GaussianRadialBasis(nn.Module):
+    def __init__(self, dim: int, max_val: float):
+        super().__init__()
+        self.dim, self.max_val = int(dim), float(max_val)
+        self.param_module = _GaussianParamModule(dim)
+
+
+class _DTP(nn.Module):
+    """DepthwiseTensorProduct container: ``tp.weight`` exists only for shared (internal) weights."""
+
+    def __init__(self, numel: int, internal: bool, fan_in_scales: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.tp = _TP(numel, internal)
+        if internal and fan_in_scales is not None:
+            with torch.no_grad():
+                self.tp.weight.mul_(fan_in_scales)
+
+
+class SeparableFCTP(nn.Module):
+    """dtp (+ dtp_rad) + lin (+ gate) for node irreps ``m0=2G, m1=G, m2=G/2`` and the l<=2 spherical harmonics."""
+
+    def __init__(self, irreps_node: Irreps, irreps_out: Irreps, fc_neurons: Optional[Sequence[int]], use_activation: bool,
+                 internal_weights: bool):
+        super().__init__()
+        self.irreps_node, self.irreps_out = Irreps(irreps_node), Irreps(irreps_out)
+        m0, m1, m2 = self.irreps_node.m
+        if not (m0 == 2 * m1 and m1 == 2 * m2 and m1 in (16, 32)):
+            raise NotImplementedError(f"the fused edge kernels are specialised for 2G x0e + G x1e + G/2 x2e with G in (16, 32); got {self.irreps_node}")
+        self.numel = dtp_numel(self.irreps_node)
+        self.dtp = _DTP(self.numel, internal_weights)
+        self.dtp_rad = RadialProfile(list(fc_neurons) + [self.numel]) if fc_neurons is not None else None
+        self.use_activation = use_activation
+        lin_out = gate_pre(self.irreps_out) if use_activation else self.irreps_out
+        self.lin = LinearRS(dtp_out(self.irreps_node), lin_out)
+
+
+class GraphAttention(nn.Module):
+    """GraphAttentionMLP / GraphAttentionMLP2 (same parameters; the latter adds the edge logits)."""
+
+    def __init__(self, irreps_emb, irreps_out, fc_neurons: Sequence[int], num_heads: int):
+        super().__init__()
+        self.irreps_emb, self.irreps_out = Irreps(irreps_emb), Irreps(irreps_out)
+        if num_heads != 4:
+            raise NotImplementedError("the attention kernels are specialised for 4 heads (all shipped configs)")
+        self.num_heads = num_heads
+        self.irreps_head = self.irreps_emb.div(num_heads)
+        mul_alpha = self.irreps_emb.m[0]
+        self.sep_act = SeparableFCTP(self.irreps_emb, self.irreps_emb, fc_neurons, use_activation=True, internal_weights=False)
+        self.sep_alpha = LinearRS(Irreps((dtp_out(self.irreps_emb).m[0], 0, 0)), Irreps((mul_alpha, 0, 0)))
+        self.sep_value = SeparableFCTP(self.irreps_emb, self.irreps_emb, None, use_activation=False, internal_weights=True)
+        self.alpha_dot = nn.Parameter(torch.randn(1, num_heads, mul_alpha // num_heads))
+        nn.init.xavier_uniform_(self.alpha_dot)
+        self.proj = LinearRS(self.irreps_emb, self.irreps_out)
+        self._packed = _Packed()
+
+    def packed(self):
+        def build():
+            (a0, _, _), ab = self.sep_alpha.packed()
+            (l0, l1, l2), lb = self.sep_act.lin.packed()
+            d0 = dtp_out(self.irreps_emb).m[0]
+            ma = self.irreps_emb.m[0]
+            n_lin0 = self.sep_act.lin.irreps_out.m[0]
+            W0 = torch.cat([a0.view(d0, ma), l0.view(d0, n_lin0)], dim=1).contiguous()
+            b0 = torch.cat([ab, lb]).contiguous()
+            (v0, v1, v2), vb = self.sep_value.lin.packed()
+            return dict(W0=W0, W1=l1, W2=l2, b0=b0, alpha_dot=self.alpha_dot.detach().reshape(-1).contiguous(),
+                        wv=self.sep_value.dtp.tp.weight.detach().contiguous(), V0=v0, V1=v1, V2=v2, vb=vb)
+        return self._packed.get(self, build)
+
+    def attend(self, msg_src: torch.Tensor, msg_dst: Optional[torch.Tensor], g: ops.Csr, sh: torch.Tensor,
+               w: torch.Tensor, edge_logit: Optional[torch.Tensor]) -> torch.Tensor:
+        """-> sum_e softmax(logit)_e * value_e per destination, (n_dst, F) (before ``proj``)."""
+        p = self.packed()
+        G = self.irreps_emb.m[1]
+        F = self.irreps_emb.dim
+        E = max(1, g.n_edges)
+        dev = msg_src.device
+        logits = torch.empty(E, 4, dtype=torch.float32, device=dev)
+        v = torch.empty(E, F, dtype=torch.float32, device=dev)
+        ops.edge_tp_lin(G, L.EPI_ACT, msg_src, msg_dst, False, g, sh, w, self.sep_act.numel, p["W0"], p["W1"], p["W2"], p["b0"],
+                        alpha_dot=p["alpha_dot"], edge_logit=edge_logit, logits=logits, out=v)
+        val = torch.empty(E, F, dtype=torch.float32, device=dev)
+        ops.edge_tp_lin(G, L.EPI_LIN, v, None, True, g, sh, p["wv"], 0, p["V0"], p["V1"], p["V2"], p["vb"], out=val)
+        return ops.segment_softmax_reduce(g, logits, val, self.irreps_emb.m)

@@ -1,0 +1,222 @@
+"""Thin Python wrappers over the C ABI (include/dedf.h).  PyTorch is used only to
+own device memory and streams; every arithmetic op below is a hand-written
+sm_100a kernel in libdedf.so.  All tensors must be CUDA / contiguous.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, NamedTuple, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import check, ptr, stream
+
+
+class Csr(NamedTuple):
+    """Graph in CSR-by-destination form.  ``row_ptr`` has n_seg * n_dst + 1 entries."""
+    row_ptr: torch.Tensor      # int32
+    edge_src: torch.Tensor     # int32 (E)  flat source index
+    edge_dst: torch.Tensor     # int32 (E)
+    n_edges_dev: torch.Tensor  # int32 (1)  == row_ptr[-1:]
+    n_edges: int
+    n_dst: int
+    n_seg: int
+
+
+# ----------------------------------------------------------------------------
+# graph construction
+# ----------------------------------------------------------------------------
+def fps(x: torch.Tensor, batch: Optional[torch.Tensor], ratio: float, random_start: bool = False) -> torch.Tensor:
+    """torch_cluster.fps: LongTensor of selected indices, per batch segment, in selection order."""
+    lib = L.load()
+    n_total = x.shape[0]
+    x = x.contiguous()
+    if batch is None or n_total == 0:
+        segs = [(0, n_total)]
+    else:
+        counts = torch.bincount(batch).tolist()        # batch ids are sorted/contiguous (as torch_cluster requires)
+        segs, o = [], 0
+        for c in counts:
+            if c:
+                segs.append((o, c))
+            o += c
+    ms = [int(math.ceil(ratio * n)) for _, n in segs]
+    out = torch.empty(sum(ms), dtype=torch.long, device=x.device)
+    off = 0
+    for (o, n), m in zip(segs, ms):
+        start = int(torch.randint(n, (1,)).item()) if random_start else 0
+        scratch = torch.empty(n, dtype=torch.float32, device=x.device) if n > 16384 else None
+        check(lib.dedf_fps(ptr(x) + o * 12, n, m, start, o, out.data_ptr() + off * 8, ptr(scratch), stream()), "dedf_fps")
+        off += m
+    return out
+
+
+def radius_csr(x_src: torch.Tensor, x_dst: torch.Tensor, radii: Sequence[Optional[float]],
+               src_off: Optional[Sequence[int]] = None, b_src: Optional[torch.Tensor] = None,
+               b_dst: Optional[torch.Tensor] = None, excl_mode: int = 0, excl: Optional[torch.Tensor] = None,
+               max_num_neighbors: int = 1000) -> Csr:
+    """Radius search of ``x_dst`` against ``len(radii)`` concatenated source clouds (None radius = all pairs)."""
+    lib = L.load()
+    n_scales = len(radii)
+    if src_off is None:
+        assert n_scales == 1
+        src_off = [0, x_src.shape[0]]
+    n_dst = x_dst.shape[0]
+    x_src, x_dst = x_src.contiguous(), x_dst.contiguous()
+    so = L.int_array(src_off)
+    rr = L.float_array([-1.0 if r is None else float(r) for r in radii])
+    dev = x_src.device
+    counts = torch.empty(max(1, n_scales * n_dst), dtype=torch.int32, device=dev)
+    row_ptr = torch.empty(n_scales * n_dst + 1, dtype=torch.int32, device=dev)
+    pb_s = ptr(b_src, torch.long) if b_src is not None else None
+    pb_d = ptr(b_dst, torch.long) if b_dst is not None else None
+    pex = ptr(excl, torch.long) if excl is not None else None
+    check(lib.dedf_radius_count(ptr(x_src), ptr(x_dst), n_dst, n_scales, so, rr, pb_s, pb_d, excl_mode, pex,
+                                max_num_neighbors, ptr(counts, torch.int32), ptr(row_ptr, torch.int32), stream()),
+          "dedf_radius_count")
+    n_edges_dev = row_ptr[-1:]
+    n_edges = int(n_edges_dev.item())          # the one host sync of a graph build (sizes the edge buffers)
+    edge_src = torch.empty(max(1, n_edges), dtype=torch.int32, device=dev)
+    edge_dst = torch.empty(max(1, n_edges), dtype=torch.int32, device=dev)
+    check(lib.dedf_radius_fill(ptr(x_src), ptr(x_dst), n_dst, n_scales, so, rr, pb_s, pb_d, excl_mode, pex,
+                               max_num_neighbors, ptr(row_ptr, torch.int32), ptr(edge_src, torch.int32),
+                               ptr(edge_dst, torch.int32), stream()), "dedf_radius_fill")
+    return Csr(row_ptr, edge_src[:n_edges], edge_dst[:n_edges], n_edges_dev, n_edges, n_dst, n_scales)
+
+
+def radius(x: torch.Tensor, y: torch.Tensor, r: float, batch_x: Optional[torch.Tensor] = None,
+           batch_y: Optional[torch.Tensor] = None, max_num_neighbors: int = 32) -> torch.Tensor:
+    """Drop-in for torch_cluster.radius: LongTensor[2, E] = (y index, x index), sorted by y then x."""
+    g = radius_csr(x, y, [r], b_src=batch_x, b_dst=batch_y, max_num_neighbors=max_num_neighbors)
+    return torch.stack([g.edge_dst.long(), g.edge_src.long()], dim=0)
+
+
+def radius_graph(x: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None, loop: bool = False,
+                 max_num_neighbors: int = 32) -> torch.Tensor:
+    """Drop-in for torch_cluster.radius_graph (row 0 = centre / destination, row 1 = neighbour / source)."""
+    g = radius_csr(x, x, [r], b_src=batch, b_dst=batch, excl_mode=0 if loop else 2,
+                   max_num_neighbors=max_num_neighbors if loop else max_num_neighbors + 1)
+    return torch.stack([g.edge_dst.long(), g.edge_src.long()], dim=0)
+
+
+# ----------------------------------------------------------------------------
+# per-edge
+# ----------------------------------------------------------------------------
+def edge_geom(x_src: torch.Tensor, x_dst: torch.Tensor, g: Csr, radii: Optional[Sequence[Optional[float]]] = None,
+              src_off: Optional[Sequence[int]] = None, ns_cut: Optional[Tuple[float, float]] = None,
+              want_logit: bool = False):
+    """-> (length (E), sh (E,9), logit (E) or None)."""
+    lib = L.load()
+    dev = x_src.device
+    E = max(1, g.n_edges)
+    length = torch.empty(E, dtype=torch.float32, device=dev)
+    sh = torch.empty(E, 9, dtype=torch.float32, device=dev)
+    logit = torch.empty(E, dtype=torch.float32, device=dev) if want_logit else None
+    n_scales = len(radii) if radii is not None else 1
+    so = L.int_array(src_off if src_off is not None else [0, x_src.shape[0]])
+    rr = L.float_array([-1.0 if r is None else float(r) for r in (radii if radii is not None else [None])])
+    lo, hi = ns_cut if ns_cut is not None else (0.0, -1.0)
+    check(lib.dedf_edge_geom(ptr(x_src.contiguous()), ptr(x_dst.contiguous()), ptr(g.edge_src, torch.int32),
+                             ptr(g.edge_dst, torch.int32), ptr(g.n_edges_dev, torch.int32), g.n_edges, n_scales, so, rr,
+                             lo, hi, ptr(length), ptr(sh), ptr(logit), stream()), "dedf_edge_geom")
+    return length, sh, logit
+
+
+def edge_mlp(desc: L.MlpDesc, max_edges: int) -> None:
+    check(L.load().dedf_edge_mlp(C.byref(desc), max_edges, stream()), "dedf_edge_mlp")
+
+
+def edge_tp_lin(mul1: int, epilogue: int, x_src: torch.Tensor, x_dst: Optional[torch.Tensor], per_edge_x: bool, g: Csr,
+                sh: torch.Tensor, w: torch.Tensor, w_stride: int, W0, W1, W2, bias0, alpha_dot=None, edge_logit=None,
+                logits=None, out=None) -> None:
+    check(L.load().dedf_edge_tp_lin(mul1, epilogue, ptr(x_src), ptr(x_dst), 1 if per_edge_x else 0,
+                                    ptr(g.edge_src, torch.int32), ptr(g.edge_dst, torch.int32),
+                                    ptr(g.n_edges_dev, torch.int32), g.n_edges, ptr(sh), ptr(w), w_stride, ptr(W0), ptr(W1),
+                                    ptr(W2), ptr(bias0), ptr(alpha_dot), ptr(edge_logit), ptr(logits), ptr(out), stream()),
+          "dedf_edge_tp_lin")
+
+
+def segment_softmax_reduce(g: Csr, logits: torch.Tensor, val: torch.Tensor, irr: Tuple[int, int, int]) -> torch.Tensor:
+    out = torch.empty(g.n_dst, irr[0] + 3 * irr[1] + 5 * irr[2], dtype=torch.float32, device=val.device)
+    check(L.load().dedf_segment_softmax_reduce(ptr(g.row_ptr, torch.int32), g.n_dst, g.n_seg, ptr(logits), ptr(val),
+                                               irr[0], irr[1], irr[2], ptr(out), stream()), "dedf_segment_softmax_reduce")
+    return out
+
+
+def edge_tp_reduce(mul1: int, x: torch.Tensor, row_ptr: torch.Tensor, edge_src: torch.Tensor, sh: torch.Tensor,
+                   w: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
+    """K1: out[d] = sum_{e->d} alpha[e, head(u)] * DTP(x[src_e], sh_e, w_e)  -> (N_dst, 49 * mul1)."""
+    n_dst = row_ptr.numel() - 1
+    out = torch.empty(n_dst, 49 * mul1, dtype=torch.float32, device=x.device)
+    check(L.load().dedf_edge_tp_reduce(mul1, ptr(x), ptr(row_ptr, torch.int32), ptr(edge_src, torch.int32), ptr(sh), ptr(w),
+                                       ptr(alpha), n_dst, ptr(out), stream()), "dedf_edge_tp_reduce")
+    return out
+
+
+# ----------------------------------------------------------------------------
+# per-node
+# ----------------------------------------------------------------------------
+def node_linear(x: torch.Tensor, irr_in, irr_out, W: Sequence[Optional[torch.Tensor]], bias0: Optional[torch.Tensor],
+                ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, ln_eps: float = 1e-5, gate: bool = False,
+                res: Optional[torch.Tensor] = None, res_scale: float = 1.0) -> torch.Tensor:
+    n = x.shape[0]
+    fy = irr_out[0] + 3 * irr_out[1] + 5 * irr_out[2]
+    if gate:
+        fy -= irr_out[1] + irr_out[2]
+    y = torch.empty(n, fy, dtype=torch.float32, device=x.device)
+    ln_w, ln_b = (ln if ln is not None else (None, None))
+    check(L.load().dedf_node_linear(ptr(x), n, L.int_array(irr_in), L.int_array(irr_out), ptr(W[0]), ptr(W[1]), ptr(W[2]),
+                                    ptr(bias0), ptr(ln_w), ptr(ln_b), ln_eps, 1 if gate else 0, ptr(res), res_scale, ptr(y),
+                                    stream()), "dedf_node_linear")
+    return y
+
+
+def gather_rows(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    y = torch.empty(idx.shape[0], x.shape[1], dtype=torch.float32, device=x.device)
+    check(L.load().dedf_gather_rows(ptr(x), ptr(idx, torch.long), idx.shape[0], x.shape[1], ptr(y), stream()), "dedf_gather_rows")
+    return y
+
+
+def add_scale(a: torch.Tensor, b: torch.Tensor, s: float) -> torch.Tensor:
+    y = torch.empty_like(a)
+    check(L.load().dedf_add_scale(ptr(a), ptr(b), s, a.numel(), ptr(y), stream()), "dedf_add_scale")
+    return y
+
+
+# ----------------------------------------------------------------------------
+# score head
+# ----------------------------------------------------------------------------
+def time_embed(desc: L.TimeDesc, time: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(desc.n_scales, time.shape[0], desc.out_dim, dtype=torch.float32, device=time.device)
+    check(L.load().dedf_time_embed(C.byref(desc), ptr(time), time.shape[0], ptr(out), stream()), "dedf_time_embed")
+    return out
+
+
+def query_transform(Ts: torch.Tensor, qx: torch.Tensor, qf: torch.Tensor, irr) -> Tuple[torch.Tensor, torch.Tensor]:
+    n_t, n_q = Ts.shape[0], qx.shape[0]
+    x_out = torch.empty(n_t * n_q, 3, dtype=torch.float32, device=Ts.device)
+    f_out = torch.empty(n_t * n_q, qf.shape[1], dtype=torch.float32, device=Ts.device)
+    check(L.load().dedf_query_transform(ptr(Ts), n_t, ptr(qx), ptr(qf), n_q, L.int_array(irr), ptr(x_out), ptr(f_out), stream()),
+          "dedf_query_transform")
+    return x_out, f_out
+
+
+def score_tp(Ts, qf_rot, key_f, qx, qw, irr, Wd: List[torch.Tensor], Wl0, Wl1, bl, n_vec: int, lin_mult: float):
+    n_t = Ts.shape[0]
+    ang = torch.empty(n_t, 3, dtype=torch.float32, device=Ts.device)
+    lin = torch.empty(n_t, 3, dtype=torch.float32, device=Ts.device)
+    arr = lambda ts: (L.c_fp * 2)(ptr(ts[0]), ptr(ts[1]))
+    check(L.load().dedf_score_tp(ptr(Ts), n_t, ptr(qf_rot), ptr(key_f), ptr(qx), ptr(qw), qx.shape[0], L.int_array(irr),
+                                 arr(Wd), arr(Wl0), arr(Wl1), arr(bl), n_vec, lin_mult, ptr(ang), ptr(lin), stream()),
+          "dedf_score_tp")
+    return ang, lin
+
+
+def pose_update(T: torch.Tensor, ang: torch.Tensor, lin: torch.Tensor, noise: Optional[torch.Tensor], seed: int, offset: int,
+                t: float, ang_mult: float, lin_mult: float, alpha_ang: float, alpha_lin: float, temperature: float,
+                traj_out: Optional[torch.Tensor], T_f32_out: Optional[torch.Tensor]) -> None:
+    check(L.load().dedf_pose_update(ptr(T, torch.float64), T.shape[0], ptr(ang), ptr(lin), ptr(noise, torch.float64), seed, offset,
+                                    t, ang_mult, lin_mult, alpha_ang, alpha_lin, temperature, ptr(traj_out, torch.float64),
+                                    ptr(T_f32_out), stream()), "dedf_pose_update")

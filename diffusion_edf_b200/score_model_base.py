@@ -1,0 +1,111 @@
+"""ScoreModelBase on the CUDA path: ``forward`` / ``sample`` / ``get_train_loss`` with the reference's
+signatures (/root/reference/diffusion_edf/score_model_base.py:22-225)."""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import ops
+from .gnn_data import FeaturedPoints, detach_featured_points
+
+
+class ScoreModelBase(nn.Module):
+    lin_mult: float
+    ang_mult: float
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        self.register_buffer("q_indices", torch.tensor([[1, 2, 3], [0, 3, 2], [3, 0, 1], [2, 1, 0]], dtype=torch.long), persistent=False)
+        self.register_buffer("q_factor", torch.tensor([[-0.5, -0.5, -0.5], [0.5, -0.5, 0.5], [0.5, 0.5, -0.5], [-0.5, 0.5, 0.5]]), persistent=False)
+        self.sample_seed = 0
+
+    def get_key_pcd_multiscale(self, pcd: FeaturedPoints) -> List[FeaturedPoints]:
+        raise NotImplementedError
+
+    def get_query_pcd(self, pcd: FeaturedPoints) -> FeaturedPoints:
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ training loss (forward value)
+    def get_train_loss(self, Ts, time, key_pcd, query_pcd, target_ang_score, target_lin_score):
+        """Forward value of the reference's loss and its statistics (score_model_base.py:41-107).  The CUDA path
+        has no backward kernels yet: calling it with parameters that require grad raises."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("diffusion_edf_b200 has forward kernels only (no autograd through the CUDA path yet); "
+                                      "call under torch.no_grad() or with requires_grad_(False)")
+        assert target_ang_score.ndim == 2 and target_ang_score.shape[-1] == 3
+        assert target_lin_score.ndim == 2 and target_lin_score.shape[-1] == 3
+        assert len(time) == len(target_ang_score) == len(target_lin_score)
+        key_ms = self.get_key_pcd_multiscale(key_pcd)
+        q = self.get_query_pcd(query_pcd)
+        ang, lin = self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)
+        t_ang = target_ang_score * torch.sqrt(time[..., None]) * self.ang_mult
+        t_lin = target_lin_score * torch.sqrt(time[..., None]) * self.lin_mult
+        ang_loss = torch.sum(torch.square(t_ang - ang), dim=-1).mean(dim=-1)
+        lin_loss = torch.sum(torch.square(t_lin - lin), dim=-1).mean(dim=-1)
+        loss = ang_loss + lin_loss
+        tn_a, tn_l = torch.norm(t_ang, dim=-1), torch.norm(t_lin, dim=-1)
+        sn_a, sn_l = torch.norm(ang, dim=-1), torch.norm(lin, dim=-1)
+        dp_a, dp_l = (ang * t_ang).sum(-1), (lin * t_lin).sum(-1)
+        stats = torch.stack([loss, ang_loss, lin_loss, tn_a.mean(), tn_l.mean(), sn_a.mean(), sn_l.mean(), dp_a.mean(),
+                             dp_l.mean(), (dp_a / tn_a / sn_a).mean(), (dp_l / tn_l / sn_l).mean()]).tolist()   # one D2H
+        names = ["Loss/train", "Loss/angular", "Loss/linear", "norm/target_ang", "norm/target_lin", "norm/inferred_ang",
+                 "norm/inferred_lin", "alignment/unnormalized/ang", "alignment/unnormalized/lin",
+                 "alignment/normalized/ang", "alignment/normalized/lin"]
+        statistics = dict(zip(names, stats))
+        fp_info = {"key_fp": None, "query_fp": detach_featured_points(q)}
+        tensor_info = {"ang_score": ang.detach(), "lin_score": lin.detach()}
+        return loss, fp_info, tensor_info, statistics
+
+    # ------------------------------------------------------------------ sampling
+    @torch.no_grad()
+    def sample(self, T_seed: torch.Tensor, scene_pcd_multiscale: List[FeaturedPoints], grasp_pcd: FeaturedPoints,
+               diffusion_schedules: List[Union[List[float], Tuple[float, float]]], N_steps: List[int], timesteps: List[float],
+               temperatures: Union[Union[int, float], Sequence[Union[int, float]]] = 1.0, log_t_schedule: bool = True,
+               time_exponent_temp: float = 0.5, time_exponent_alpha: float = 0.5,
+               noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Annealed Langevin dynamics on SE(3) (score_model_base.py:110-204): returns (sum(N_steps)+2, nT, 7) float64.
+
+        The pose integrator runs on the device in float64 (dedf_pose_update); the noise comes from Philox
+        (seed = ``self.sample_seed``) unless ``noise`` (sum(N_steps), nT, 6) standard normals is given."""
+        if isinstance(temperatures, (int, float)):
+            temperatures = [float(temperatures)] * len(diffusion_schedules)
+        dev = T_seed.device
+        nT = T_seed.shape[0]
+        T = T_seed.detach().to(torch.float64).contiguous().clone()
+        total = int(sum(N_steps))
+        traj = torch.empty(total + 2, nT, 7, dtype=torch.float64, device=dev)
+        traj[0].copy_(T)
+        T32 = T.to(torch.float32)
+        sources = self.score_head.key_tensor_field.encode_sources(scene_pcd_multiscale)   # pose-independent, once per scene
+        step = 0
+        for n, sch in enumerate(diffusion_schedules):
+            s0, s1 = float(sch[0]), float(sch[1])
+            if log_t_schedule:
+                ts = torch.logspace(math.log(s0), math.log(s1), N_steps[n], base=math.e, dtype=torch.float64).tolist()
+            else:
+                ts = torch.linspace(s0, s1, N_steps[n], dtype=torch.float64).tolist()
+            for t in ts:
+                temperature = float(temperatures[n]) * (t ** time_exponent_temp)
+                a_ang = (self.ang_mult ** 2) * (t ** time_exponent_alpha) * timesteps[n]
+                a_lin = (self.lin_mult ** 2) * (t ** time_exponent_alpha) * timesteps[n]
+                time = torch.full((1,), t, dtype=torch.float32, device=dev)
+                ang, lin = self.score_head(Ts=T32, key_pcd_multiscale=scene_pcd_multiscale, query_pcd=grasp_pcd, time=time,
+                                           sources=sources, shared_time=True)
+                nz = noise[step].contiguous() if noise is not None else None
+                ops.pose_update(T, ang, lin, nz, int(self.sample_seed), step, t, self.ang_mult, self.lin_mult, a_ang, a_lin,
+                                temperature, traj[step + 1], T32)
+                step += 1
+        traj[total + 1].copy_(T)
+        return traj
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, Ts: torch.Tensor, time: torch.Tensor, key_pcd: FeaturedPoints, query_pcd: FeaturedPoints,
+                debug: bool = False):
+        key_ms = self.get_key_pcd_multiscale(key_pcd)
+        q = self.get_query_pcd(query_pcd)
+        score = self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)
+        dbg = ([detach_featured_points(k) for k in key_ms], detach_featured_points(q)) if debug else None
+        return score, dbg

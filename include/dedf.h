@@ -1,0 +1,181 @@
+/*
+ * dedf.h -- C ABI of libdedf.so: hand-written sm_100a CUDA kernels for the Diffusion-EDF
+ * score-network hot path (MultiscaleScoreModel.forward / ScoreModelBase.sample).
+ *
+ * The reference (tomato1mule/diffusion_edf) is pure Python: it has no FFI / plugin boundary of
+ * its own.  Its de-facto operator boundary is the set of third-party ops the hot path calls
+ * (SURVEY.md section 8b); every entry point below names the reference call site (file:line under
+ * /root/reference/diffusion_edf unless noted) whose arithmetic it replaces.  INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host (plain int/float arrays that are
+ *     copied into the launch parameters); all buffers are allocated and owned by the caller
+ *   - returns 0 on success, a negative DEDF_ERR_* code otherwise; never throws, never allocates, never
+ *     synchronises; work is enqueued on `stream`
+ *   - features are fp32, row-major (N, F), e3nn "mul_ir" layout of an irreps triple
+ *     (m0 x0e + m1 x1e + m2 x2e): [m0 scalars | m1 x 3 | m2 x 5]; `irr` arguments are int[3] = {m0,m1,m2}
+ *   - graphs are CSR by destination: row_ptr[(n_seg * n_dst) + 1], edge_src[E], edge_dst[E] (int32);
+ *     edges of destination d in segment s are [row_ptr[s*n_dst+d], row_ptr[s*n_dst+d+1]); sources ascend
+ *   - the number of edges of a data-dependent graph lives on the device (`n_edges_dev`); `max_edges` only
+ *     sizes the launch
+ */
+#ifndef DEDF_H
+#define DEDF_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEDF_MAX_SCALES 8
+#define DEDF_MLP_MAX_LAYERS 4
+
+#define DEDF_MLP_IN_ROWS 0   /* input rows given explicitly */
+#define DEDF_MLP_IN_RBF 1    /* GaussianRadialBasisLayerFiniteCutoff(length)            (radial_func.py:231-278) */
+#define DEDF_MLP_IN_FIELD 2  /* per-scale length encoder + edge_scalars_pre_linears     (graph_parser.py:180-183,
+                                                                                         multiscale_tensor_field.py:225-234) */
+#define DEDF_EPI_ACT 0       /* alpha logits + Gate                                     (graph_attention.py:233-246) */
+#define DEDF_EPI_LIN 1       /* bias only                                               (graph_attention.py:237-239) */
+
+/* ---- graph construction ------------------------------------------------------------------------------ */
+
+/* torch_cluster.fps(src, ratio, random_start) for ONE batch segment (connectivity.py:62).
+ * Selects m points greedily (arg-max of the running min squared distance, ties -> lowest index) starting from
+ * `start`; writes idx_base + index in selection order.  scratch_dist (n floats) is needed only for n > 16384. */
+int dedf_fps(const float* x, int n, int m, int start, int idx_base, long long* out_idx, float* scratch_dist,
+             cudaStream_t stream);
+
+/* torch_cluster.radius / radius_graph / the all-pairs meshgrid (graph_parser.py:339, :276-278;
+ * connectivity.py:22, :42, :68-70), for n_scales source clouds at once (sources concatenated, cloud s =
+ * [src_off_host[s], src_off_host[s+1]), radius r_host[s], r < 0 = all pairs).  Pass 1 writes counts
+ * (n_scales * n_dst) and their exclusive scan row_ptr (+1 entry = E); pass 2 fills edge_src (flat source index)
+ * and edge_dst.  excl_mode: 0 none; 1 drop src == excl[dst]; 2 drop src == dst; 3 drop excl[src] == dst.
+ * max_nb caps the hits per (scale, dst) BEFORE the exclusion, like torch_cluster + the reference's filter. */
+int dedf_radius_count(const float* x_src, const float* x_dst, int n_dst, int n_scales, const int* src_off_host,
+                      const float* r_host, const long long* b_src, const long long* b_dst, int excl_mode,
+                      const long long* excl, int max_nb, int* counts, int* row_ptr, cudaStream_t stream);
+int dedf_radius_fill(const float* x_src, const float* x_dst, int n_dst, int n_scales, const int* src_off_host,
+                     const float* r_host, const long long* b_src, const long long* b_dst, int excl_mode,
+                     const long long* excl, int max_nb, const int* row_ptr, int* edge_src, int* edge_dst,
+                     cudaStream_t stream);
+
+/* ---- per-edge ---------------------------------------------------------------------------------------- */
+
+/* Edge vector, length, o3.SphericalHarmonics(lmax=2, normalize=True, 'component'), non-scalar SH min-cut and
+ * log soft cut-off (graph_parser.py:146-224; unet_feature_extractor.py:284-288).  logit may be NULL (UNet);
+ * ns_hi <= 0 disables the min-cut; r_host[s] < 0 marks the infinite scale (logit 0). */
+int dedf_edge_geom(const float* x_src, const float* x_dst, const int* edge_src, const int* edge_dst,
+                   const int* n_edges_dev, int max_edges, int n_scales, const int* src_off_host, const float* r_host,
+                   float ns_lo, float ns_hi, float* length, float* sh, float* logit, cudaStream_t stream);
+
+typedef struct dedf_mlp_desc {
+    int mode;                      /* DEDF_MLP_IN_* */
+    const int* n_edges_dev;
+    const float* x_in;             /* ROWS: (E, dims[0]) */
+    const float* length;           /* RBF / FIELD: (E) */
+    const float* rbf_mean; const float* rbf_std_logit; const float* rbf_weight_logit;   /* RBF: (dims[0]) each */
+    float rbf_cutoff, rbf_offset;
+    int n_scales, n_dst;           /* FIELD */
+    const int* row_ptr; const int* edge_dst;
+    const float* enc_mean[DEDF_MAX_SCALES]; const float* enc_std_logit[DEDF_MAX_SCALES];
+    const float* enc_weight_logit[DEDF_MAX_SCALES];
+    float enc_r[DEDF_MAX_SCALES];  /* >= 0: GaussianRadialBasis(max_val = r); < 0: sinusoidal(max_val = enc_max_r, n = enc_n) */
+    float enc_max_r, enc_n;
+    const float* enc_freq;         /* (dims[0]/2) sinusoidal frequencies exp(-k ln(n)/(half-1)), tabulated by the host in fp32 */
+    const float* pre_w[DEDF_MAX_SCALES];   /* (dims[0], dims[1]): transposed length half of the pre-linear */
+    const float* row_bias;         /* (n_scales, n_rb, dims[1]) from dedf_time_embed */
+    int n_rb, rb_div;              /* row = min(edge_dst / rb_div, n_rb - 1) */
+    int n_layers;
+    int dims[DEDF_MLP_MAX_LAYERS + 1];
+    const float* W[DEDF_MLP_MAX_LAYERS];      /* (dims[i], dims[i+1]) = torch Linear.weight^T */
+    const float* b[DEDF_MLP_MAX_LAYERS];
+    const float* ln_g[DEDF_MLP_MAX_LAYERS]; const float* ln_b[DEDF_MLP_MAX_LAYERS];
+    int flags[DEDF_MLP_MAX_LAYERS];           /* bit0 LayerNorm, bit1 SiLU */
+    const float* out_offset;       /* RadialProfile.offset (dims[n_layers]) or NULL */
+    float* out;                    /* (E, dims[n_layers]) */
+} dedf_mlp_desc;
+
+/* RadialProfile MLP on the edge scalars (equiformer/radial_func.py:56-59) fused with the computation of its
+ * input embedding. */
+int dedf_edge_mlp(const dedf_mlp_desc* desc_host, int max_edges, cudaStream_t stream);
+
+/* gather message[src] (+ message_dst[dst]) -> DepthwiseTensorProduct 'uvu' with the 9 spherical harmonics
+ * (equiformer/tensor_product_rescale.py:352-382 -> o3.TensorProduct) -> LinearRS block-diagonal linear ->
+ * epilogue, the (E, 1568) tensor-product output never leaving shared memory (graph_attention.py:231-239).
+ * mul1 = multiplicity of 1e (32: 64x0e+32x1e+16x2e, 16: 32x0e+16x1e+8x2e).
+ * w: per-edge TP weights (E, numel) with w_stride = numel, or shared weights (numel) with w_stride = 0.
+ * EPI_ACT: W0 = [sep_alpha | sep_act.lin 0e] (D0, MA + m0 + m1 + m2), bias0 likewise; writes logits (E,4)
+ *          (SmoothLeakyReLU . alpha_dot + edge_logit) and out = Gate(...) (E, F).
+ * EPI_LIN: W0 (D0, m0), bias0 (m0); writes out (E, F). */
+int dedf_edge_tp_lin(int mul1, int epilogue, const float* x_src, const float* x_dst, int per_edge_x,
+                     const int* edge_src, const int* edge_dst, const int* n_edges_dev, int max_edges,
+                     const float* sh, const float* w, long long w_stride, const float* W0, const float* W1,
+                     const float* W2, const float* bias0, const float* alpha_dot, const float* edge_logit,
+                     float* logits, float* out, cudaStream_t stream);
+
+/* torch_scatter.scatter_logsumexp + exp + scatter(sum) (graph_attention.py:254-265): per destination and head
+ * softmax of the logits over the incoming edges (all n_seg segments), out[d] = sum_e alpha[e, head(c)] val[e, c]. */
+int dedf_segment_softmax_reduce(const int* row_ptr, int n_dst, int n_seg, const float* logits, const float* val,
+                                int m0, int m1, int m2, float* out, cudaStream_t stream);
+
+/* "K1": out[d] = sum_{e -> d} alpha[e, head(u)] * DTP(x[src_e], sh_e, w_e)   (N_dst, 1568 | 784), op-equivalent to
+ * scatter(alpha * o3.TensorProduct(x[edge_src], sh, weight), edge_dst) of graph_attention.py:231-232,264-265. */
+int dedf_edge_tp_reduce(int mul1, const float* x, const int* row_ptr, const int* edge_src, const float* sh,
+                        const float* w, const float* alpha, int n_dst, float* out, cudaStream_t stream);
+
+/* ---- per-node ---------------------------------------------------------------------------------------- */
+
+/* y = epilogue( LinearRS( [EquivariantLayerNormV2](x) ) ): equiformer/layer_norm.py:91-156,
+ * equiformer/tensor_product_rescale.py:176-185 / :155-173 / :241-268, equiformer/fast_activation.py:210-224,
+ * skip.py:13-35.  W_l (in.m_l, out.m_l) row-major; ln_w NULL = no norm; gate = 1 applies the SiLU/sigmoid Gate
+ * (out.m0 = scalars + gates); y = (y + res) * res_scale when res != NULL. */
+int dedf_node_linear(const float* x, int n, const int* irr_in_host, const int* irr_out_host, const float* W0,
+                     const float* W1, const float* W2, const float* bias0, const float* ln_w, const float* ln_b,
+                     float ln_eps, int gate, const float* res, float res_scale, float* y, cudaStream_t stream);
+
+int dedf_gather_rows(const float* x, const long long* idx, int n, int F, float* y, cudaStream_t stream);
+int dedf_add_scale(const float* a, const float* b, float s, long long n, float* y, cudaStream_t stream);
+
+/* ---- score head -------------------------------------------------------------------------------------- */
+
+typedef struct dedf_time_desc {
+    float max_time, enc_n;
+    const float* enc_freq;         /* (enc_dim/2) frequencies exp(-k ln(n)/(half-1)), tabulated by the host in fp32 */
+    int enc_dim, h_dim, e_dim, out_dim, n_scales;
+    const float* W1[DEDF_MAX_SCALES]; const float* b1[DEDF_MAX_SCALES];   /* (enc_dim, h_dim) */
+    const float* W2[DEDF_MAX_SCALES]; const float* b2[DEDF_MAX_SCALES];   /* (h_dim, e_dim) */
+    const float* Wp[DEDF_MAX_SCALES]; const float* bp[DEDF_MAX_SCALES];   /* (e_dim, out_dim) */
+} dedf_time_desc;
+
+/* SinusoidalPositionEmbeddings + time MLPs (score_head.py:53-63,160-164) + the time half of
+ * edge_scalars_pre_linears (multiscale_tensor_field.py:225-234): out (n_scales, n_t, out_dim). */
+int dedf_time_embed(const dedf_time_desc* desc_host, const float* time, int n_t, float* out, cudaStream_t stream);
+
+/* TransformPcd.forward (gnn_data.py:88-100): x' = q x q^-1 + t, f' = D(q) f  (wigner.py:257-283). */
+int dedf_query_transform(const float* Ts, int n_t, const float* qx, const float* qf, int n_q, const int* irr_host,
+                         float* x_out, float* f_out, cudaStream_t stream);
+
+/* lin_vel_tp / ang_vel_tp (SeparableFCTP with shared weights), Gate, mean over the vectors, rotation by q^-1,
+ * orbital term and weighted sum over the query points (score_head.py:192-209).  Arrays of 2 = (lin, ang). */
+int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, const float* key_f, const float* qx, const float* qw,
+                  int n_q, const int* irr_host, const float* const* Wd_host2, const float* const* Wl0_host2,
+                  const float* const* Wl1_host2, const float* const* bl_host2, int n_vec, float lin_mult,
+                  float* ang_out, float* lin_out, cudaStream_t stream);
+
+/* One annealed-Langevin step on SE(3) in float64 (score_model_base.py:178-193).  noise (n_t, 6) standard normals
+ * or NULL (Philox4x32-10 with (seed, pose, offset)).  Optionally copies the new poses to traj_out (f64) and
+ * T_f32_out (f32, the network input of the next step). */
+int dedf_pose_update(double* T, int n_t, const float* ang, const float* lin, const double* noise,
+                     unsigned long long seed, unsigned long long offset, double t, double ang_mult, double lin_mult,
+                     double alpha_ang, double alpha_lin, double temperature, double* traj_out, float* T_f32_out,
+                     cudaStream_t stream);
+
+/* library self-description: returns the compute capability the kernels were built for (100) */
+int dedf_build_arch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEDF_H */

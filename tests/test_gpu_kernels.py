@@ -1,0 +1,382 @@
+"""Per-kernel parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Tolerance: 1e-4 relative (max |a-b| / max |b|), the bound BASELINE.json's north_star states for fp32."""
+import math
+
+import pytest
+import torch
+
+from oracle import encoders as enc
+from oracle import graph as OG
+from oracle import model as OM
+from oracle import nn as ON
+from oracle import so3
+from oracle.irreps import Irreps as OIrreps
+from tests.util import assert_close, random_graph, rel_err
+
+pytestmark = pytest.mark.gpu
+
+IRR = {32: "64x0e+32x1e+16x2e", 16: "32x0e+16x1e+8x2e"}
+SH = "1x0e+1x1e+1x2e"
+TOL = 1e-4
+
+
+def _csr(cuda, row_ptr, edge_src, edge_dst, n_dst):
+    from diffusion_edf_b200 import ops
+    rp = row_ptr.to(cuda)
+    return ops.Csr(rp, edge_src.to(cuda), edge_dst.to(cuda), rp[-1:], int(row_ptr[-1]), n_dst, 1)
+
+
+def _random_sh(E, gen):
+    v = torch.randn(E, 3, generator=gen)
+    return so3.spherical_harmonics(2, v), v
+
+
+# --------------------------------------------------------------------------- geometry
+def test_edge_geom(cuda):
+    from diffusion_edf_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    clouds = [torch.rand(n, 3, generator=g) * 30 for n in (500, 120, 30, 8)]
+    y = torch.rand(40, 3, generator=g) * 30
+    y[0] = clouds[0][3]                              # zero-length edge
+    radii = [5.0, 10.0, 20.0, None]
+    off = [0, 500, 620, 650, 658]
+    xs = torch.cat(clouds)
+    csr = ops.radius_csr(xs.to(cuda), y.to(cuda), radii, src_off=off)
+    length, sh, logit = ops.edge_geom(xs.to(cuda), y.to(cuda), csr, radii=radii, src_off=off, ns_cut=(0.06, 0.3), want_logit=True)
+    es, ed = csr.edge_src.cpu().long(), csr.edge_dst.cpu().long()
+    rp = csr.row_ptr.cpu().long()
+    for s, r in enumerate(radii):
+        lo, hi = int(rp[s * 40]), int(rp[(s + 1) * 40])
+        par = (OM.InfiniteBipartite(SH, 0.3, 64, 100.0, fill_edge_weights=True) if r is None
+               else OM.RadiusBipartite(r, SH, 64, 0.3))
+        ge = par._encode_edges(xs, y, es[lo:hi], ed[lo:hi], par.fill_edge_weights if r is None else None)
+        assert_close(length[lo:hi], ge.edge_length, 1e-6, f"length s{s}")
+        assert_close(sh[lo:hi], ge.edge_attr, 1e-5, f"sh s{s}")
+        assert (logit[lo:hi].cpu() - ge.edge_logits).abs().max() < 2e-4, f"logit s{s}"
+    # plain variant (UNet): no cut-off, no logits
+    length2, sh2, lg2 = ops.edge_geom(xs.to(cuda), y.to(cuda), csr)
+    assert lg2 is None
+    vec = xs[es] - y[ed]
+    assert_close(sh2, so3.spherical_harmonics(2, vec), 1e-5, "plain sh")
+
+
+# --------------------------------------------------------------------------- edge MLPs
+@pytest.mark.parametrize("fc,numel,r", [([32, 16, 16], 240, 3.0), ([64, 32, 32], 480, 15.0), ([64, 32, 32], 240, 15.0)])
+def test_edge_mlp_rbf(cuda, fc, numel, r):
+    from diffusion_edf_b200 import _lib as L, layers, ops
+    torch.manual_seed(1)
+    E = 777
+    length = torch.rand(E) * r
+    length[:5] = torch.tensor([0.0, 0.001 * r, 0.01 * r, 0.1 * r, r])
+    o_rbf = enc.GaussianRadialBasisLayerFiniteCutoff(fc[0], 0.99 * r)
+    o_rad = ON.RadialProfile(fc + [numel])
+    with torch.no_grad():
+        ref = o_rad(o_rbf(length))
+    p_rbf = layers.GaussianRadialBasisLayerFiniteCutoff(fc[0], 0.99 * r)
+    p_rbf.load_state_dict(o_rbf.state_dict())
+    p_rad = layers.RadialProfile(fc + [numel])
+    p_rad.load_state_dict(o_rad.state_dict())
+    p_rbf, p_rad = p_rbf.to(cuda), p_rad.to(cuda)
+    n_dev = torch.tensor([E], dtype=torch.int32, device=cuda)
+    out = torch.empty(E, numel, device=cuda)
+    d = L.MlpDesc()
+    d.mode = L.MLP_IN_RBF
+    d.n_edges_dev = L.ptr(n_dev, torch.int32)
+    ld = length.to(cuda)
+    d.length = L.ptr(ld)
+    m, s, w = (p_rbf.mean.detach().reshape(-1), p_rbf.std_logit.detach().reshape(-1), p_rbf.weight_logit.detach().reshape(-1))
+    d.rbf_mean, d.rbf_std_logit, d.rbf_weight_logit = L.ptr(m), L.ptr(s), L.ptr(w)
+    d.rbf_cutoff, d.rbf_offset = p_rbf.cutoff, p_rbf.offset
+    p_rad.fill_desc(d, 0)
+    d.out = L.ptr(out)
+    ops.edge_mlp(d, E)
+    assert_close(out, ref, TOL, "RadialProfile(RBF)")
+
+
+def test_edge_mlp_rows(cuda):
+    from diffusion_edf_b200 import _lib as L, layers, ops
+    torch.manual_seed(2)
+    E = 301
+    x = torch.randn(E, 128)
+    o_rad = ON.RadialProfile([128, 128, 64, 480])
+    with torch.no_grad():
+        ref = o_rad(x)
+    p_rad = layers.RadialProfile([128, 128, 64, 480])
+    p_rad.load_state_dict(o_rad.state_dict())
+    p_rad = p_rad.to(cuda)
+    n_dev = torch.tensor([E], dtype=torch.int32, device=cuda)
+    out = torch.empty(E, 480, device=cuda)
+    xd = x.to(cuda)
+    d = L.MlpDesc()
+    d.mode = L.MLP_IN_ROWS
+    d.n_edges_dev = L.ptr(n_dev, torch.int32)
+    d.x_in = L.ptr(xd)
+    p_rad.fill_desc(d, 0)
+    d.out = L.ptr(out)
+    ops.edge_mlp(d, E)
+    assert_close(out, ref, TOL, "RadialProfile(rows)")
+
+
+# --------------------------------------------------------------------------- fused TP + linear
+@pytest.mark.parametrize("G", [32, 16])
+def test_graph_attention_pieces(cuda, G):
+    """edge_tp_lin (both epilogues) + segment_softmax_reduce against GraphAttentionMLP2's arithmetic."""
+    from diffusion_edf_b200 import _lib as L, layers, ops
+    gen = torch.Generator().manual_seed(10 + G)
+    torch.manual_seed(10 + G)
+    irr = OIrreps(IRR[G])
+    F, numel = irr.dim, 15 * G
+    n_src, n_dst = 90, 37
+    row_ptr, es, ed = random_graph(n_src, n_dst, 9, gen)
+    E = int(row_ptr[-1])
+    sh, _ = _random_sh(E, gen)
+    msg_src = torch.randn(n_src, F, generator=gen)
+    msg_dst = torch.randn(n_dst, F, generator=gen)
+    w = torch.randn(E, numel, generator=gen) / math.sqrt(3.0)
+    edge_logit = -torch.rand(E, generator=gen) * 3
+    oga = OM.GraphAttentionMLP2(irr, SH, irr, [32, 16, 16], 4)
+    # give the zero-initialised biases values so that they are exercised
+    with torch.no_grad():
+        for p in oga.parameters():
+            if p.abs().sum() == 0:
+                p.uniform_(-0.5, 0.5)
+    pga = layers.GraphAttention(IRR[G], IRR[G], [32, 16, 16], 4)
+    pga.load_state_dict(oga.state_dict())
+    pga = pga.to(cuda)
+    with torch.no_grad():
+        message = msg_src[es.long()] + msg_dst[ed.long()]
+        d1 = oga.sep_act.dtp(message, sh, w)
+        la = oga.sep_alpha(d1).reshape(E, 4, -1)
+        v_ref = oga.sep_act.gate(oga.sep_act.lin(d1))
+        la = oga.c_slrelu * ON.smooth_leaky_relu(la)
+        logit_ref = torch.einsum("ehk,hk->eh", la, oga.alpha_dot.squeeze(0)) + edge_logit[:, None]
+        val_ref = oga.sep_value(v_ref, edge_attr=sh, edge_scalars=None)
+        logZ = OG.scatter_logsumexp(logit_ref, ed.long(), n_dst)
+        alpha = torch.exp(logit_ref - logZ[ed.long()])
+        attn_ref = ON.heads2vec(OG.scatter_sum(ON.vec2heads(val_ref, oga.irreps_head, 4) * alpha[..., None], ed.long(), n_dst), oga.irreps_head)
+    csr = _csr(cuda, row_ptr, es, ed, n_dst)
+    p = pga.packed()
+    logits = torch.empty(E, 4, device=cuda)
+    v = torch.empty(E, F, device=cuda)
+    ops.edge_tp_lin(G, L.EPI_ACT, msg_src.to(cuda), msg_dst.to(cuda), False, csr, sh.to(cuda), w.to(cuda), numel, p["W0"], p["W1"],
+                    p["W2"], p["b0"], alpha_dot=p["alpha_dot"], edge_logit=edge_logit.to(cuda), logits=logits, out=v)
+    assert_close(logits, logit_ref, TOL, "attention logits")
+    assert_close(v, v_ref, TOL, "gated value")
+    val = torch.empty(E, F, device=cuda)
+    ops.edge_tp_lin(G, L.EPI_LIN, v_ref.to(cuda), None, True, csr, sh.to(cuda), p["wv"], 0, p["V0"], p["V1"], p["V2"], p["vb"], out=val)
+    assert_close(val, val_ref, TOL, "sep_value")
+    attn = ops.segment_softmax_reduce(csr, logit_ref.to(cuda), val_ref.to(cuda), pga.irreps_emb.m)
+    assert_close(attn, attn_ref, TOL, "softmax-reduce")
+    assert float(attn[0].abs().max()) == 0.0, "isolated destination must give zeros"
+    # whole attend() path
+    attn2 = pga.attend(msg_src.to(cuda), msg_dst.to(cuda), csr, sh.to(cuda), w.to(cuda), edge_logit.to(cuda))
+    assert_close(attn2, attn_ref, TOL, "attend")
+
+
+@pytest.mark.parametrize("G", [32, 16])
+def test_edge_tp_reduce_k1(cuda, G):
+    """K1 == scatter(alpha_head(u) * o3.TensorProduct(x[src], sh, w), dst)."""
+    from diffusion_edf_b200 import ops
+    gen = torch.Generator().manual_seed(100 + G)
+    irr = OIrreps(IRR[G])
+    F, numel = irr.dim, 15 * G
+    n = 200
+    row_ptr, es, ed = random_graph(n, n, 13, gen)
+    E = int(row_ptr[-1])
+    sh, _ = _random_sh(E, gen)
+    x = torch.randn(n, F, generator=gen)
+    w = torch.randn(E, numel, generator=gen)
+    alpha = torch.rand(E, 4, generator=gen)
+    dtp = ON.DepthwiseTensorProduct(irr, OIrreps(SH), irr, internal_weights=False, bias=False)
+    d = dtp(x[es.long()], sh, w)                                   # (E, 49 G)
+    # alpha of the head the INPUT channel u belongs to, per output entry (depthwise: output channel == input channel)
+    cols = []
+    for (i1, i2, io, mode) in dtp.tp.instructions:
+        pass
+    head_cols = torch.empty(dtp.irreps_out.dim, dtype=torch.long)
+    sl = dtp.irreps_out.slices()
+    for (i1, i2, io, mode) in dtp.tp.instructions:
+        m1 = irr[i1][0]
+        dd = 2 * dtp.irreps_out[io][1] + 1
+        hc = (torch.arange(m1) // (m1 // 4)).repeat_interleave(dd)
+        head_cols[sl[io]] = hc
+    ref = OG.scatter_sum(d * alpha[:, head_cols], ed.long(), n)
+    out = ops.edge_tp_reduce(G, x.to(cuda), row_ptr.to(cuda), es.to(cuda), sh.to(cuda), w.to(cuda), alpha.to(cuda))
+    assert_close(out, ref, TOL, "K1")
+    assert float(out[0].abs().max()) == 0.0
+
+
+# --------------------------------------------------------------------------- node kernels
+@pytest.mark.parametrize("irr_in,irr_out,bias", [("3x0e", IRR[16], True), (IRR[16], IRR[32], True), (IRR[32], IRR[16], False),
+                                                 ("112x0e+192x1e", "33x0e+32x1e", True), (IRR[32], IRR[32], True)])
+def test_linear_rs(cuda, irr_in, irr_out, bias):
+    from diffusion_edf_b200 import layers
+    torch.manual_seed(3)
+    o = ON.LinearRS(OIrreps(irr_in), OIrreps(irr_out), bias=bias)
+    with torch.no_grad():
+        for b in o.bias:
+            b.uniform_(-1, 1)
+    p = layers.LinearRS(irr_in, irr_out, bias=bias)
+    p.load_state_dict(o.state_dict())
+    p = p.to(cuda)
+    x = torch.randn(53, OIrreps(irr_in).dim)
+    with torch.no_grad():
+        ref = o(x)
+    assert_close(p(x.to(cuda)), ref, TOL, f"LinearRS {irr_in}->{irr_out}")
+
+
+@pytest.mark.parametrize("G", [32, 16])
+def test_ln_linear_gate_residual(cuda, G):
+    from diffusion_edf_b200 import layers
+    torch.manual_seed(4)
+    irr = OIrreps(IRR[G])
+    mid = ON.sort_even_first(irr * 3)[0].simplify()
+    o_ln = ON.EquivariantLayerNormV2(irr)
+    o_ffn = OM.FeedForwardNetwork(irr, irr, mid)
+    with torch.no_grad():
+        o_ln.affine_weight.uniform_(0.5, 1.5); o_ln.affine_bias.uniform_(-0.5, 0.5)
+        for b in list(o_ffn.fctp_1.bias) + list(o_ffn.fctp_2.bias):
+            b.uniform_(-0.5, 0.5)
+    p_ln = layers.EquivariantLayerNormV2(IRR[G])
+    p_ln.load_state_dict(o_ln.state_dict())
+    p_ffn = layers.FeedForwardNetwork(IRR[G], IRR[G], str(mid))
+    p_ffn.load_state_dict(o_ffn.state_dict())
+    p_ln, p_ffn = p_ln.to(cuda), p_ffn.to(cuda)
+    x = torch.randn(41, irr.dim) * torch.rand(41, 1) * 3
+    with torch.no_grad():
+        ref = x + o_ffn(o_ln(x))
+    assert_close(p_ffn(x.to(cuda), ln=p_ln, res=x.to(cuda)), ref, TOL, "x + FFN(LN(x))")
+    # LN + linear alone (ProjectIfMismatch)
+    o_proj = ON.ProjectIfMismatch(OIrreps(IRR[16]), OIrreps(IRR[32]))
+    p_proj = layers.ProjectIfMismatch(IRR[16], IRR[32])
+    p_proj.load_state_dict(o_proj.state_dict())
+    xx = torch.randn(30, 120)
+    with torch.no_grad():
+        ref = o_proj(xx)
+    assert_close(p_proj.to(cuda)(xx.to(cuda)), ref, TOL, "ProjectIfMismatch")
+
+
+def test_misc_node_ops(cuda):
+    from diffusion_edf_b200 import ops
+    torch.manual_seed(5)
+    x = torch.randn(100, 120)
+    idx = torch.randint(100, (33,))
+    assert torch.equal(ops.gather_rows(x.to(cuda), idx.to(cuda)).cpu(), x[idx])
+    a, b = torch.randn(77, 240), torch.randn(77, 240)
+    assert_close(ops.add_scale(a.to(cuda), b.to(cuda), 1 / math.sqrt(3)), (a + b) / math.sqrt(3), 1e-6, "add_scale")
+
+
+# --------------------------------------------------------------------------- head kernels
+def test_query_transform(cuda):
+    from diffusion_edf_b200 import ops
+    torch.manual_seed(6)
+    irr = OIrreps(IRR[32])
+    nT, nQ = 33, 5
+    q = torch.randn(nT, 4)
+    q[0] = torch.tensor([1.0, 0, 0, 0])                  # identity (the Euler route of the reference is singular here)
+    q[1] = torch.tensor([-0.3, 0.1, 0.9, 0.2])           # w < 0, un-normalised
+    q[2:] = torch.nn.functional.normalize(q[2:], dim=-1)
+    Ts = torch.cat([q, torch.randn(nT, 3) * 10], -1)
+    pcd = OM.FeaturedPoints(torch.randn(nQ, 3), torch.randn(nQ, irr.dim), torch.zeros(nQ, dtype=torch.long), torch.rand(nQ))
+    tp = OM.TransformPcd(irr)
+    # fp64 oracle: the reference's Euler-angle route loses digits in fp32 near beta -> 0 (SURVEY.md hard parts)
+    ref = tp(OM.FeaturedPoints(pcd.x.double(), pcd.f.double(), pcd.b, pcd.w.double()), Ts.double())
+    x, f = ops.query_transform(Ts.to(cuda), pcd.x.to(cuda), pcd.f.to(cuda), (64, 32, 16))
+    assert_close(x.view(nT, nQ, 3)[1:], ref.x[1:], 1e-5, "transformed points")
+    assert_close(f.view(nT, nQ, -1)[1:], ref.f[1:], 2e-5, "transformed features")
+    # identity pose: D = 1 exactly in the kernel; the reference's fp64 route is accurate to ~1e-8 there
+    assert_close(f.view(nT, nQ, -1)[0], pcd.f, 1e-6, "identity pose")
+
+
+def test_time_embed(cuda):
+    from diffusion_edf_b200 import ScoreModelHead, ops
+    from diffusion_edf_b200.synthetic import model_kwargs
+    torch.manual_seed(7)
+    kw = model_kwargs()["score_head_kwargs"]
+    tf = kw["key_tensor_field_kwargs"]
+    tf.update(irreps_input="64x0e+32x1e+16x2e", use_src_point_attn=False, use_dst_point_attn=False)
+    okw = dict(tf)
+    ohead = OM.ScoreModelHead(1.0, [256, 128, 64], okw, "64x0e+32x1e+16x2e", 15.0, 2.5, edge_time_encoding=True, query_time_encoding=False)
+    head = ScoreModelHead(1.0, [256, 128, 64], dict(tf), "64x0e+32x1e+16x2e", 15.0, 2.5, edge_time_encoding=True, query_time_encoding=False)
+    head.load_state_dict(ohead.state_dict())
+    head = head.to(cuda)
+    t = torch.cat([torch.tensor([1e-4, 0.01, 1.0]), torch.rand(20)])
+    rows = ops.time_embed(head._time_desc(), t.to(cuda))
+    with torch.no_grad():
+        te = ohead.time_enc(t.double()).float()          # fp64 range reduction of sin/cos(t * 1e4 * f)
+        for s in range(4):
+            emb = ohead.time_mlps_multiscale[s](te)
+            lin = ohead.key_tensor_field.edge_scalars_pre_linears[s][0]
+            ref = emb @ lin.weight[:, 64:].T + lin.bias
+            assert_close(rows[s], ref, TOL, f"time rows scale {s}")
+
+
+def test_score_tp(cuda):
+    from diffusion_edf_b200 import ops
+    from diffusion_edf_b200.score_head import _ScoreTP
+    from diffusion_edf_b200.irreps import Irreps
+    torch.manual_seed(8)
+    irr = OIrreps(IRR[32])
+    nT, nQ = 9, 3
+    pres = OIrreps("1x0e") + OIrreps("32x1e")
+    o_lin = ON.SeparableFCTP(irr, irr, pres, None, use_activation=True, internal_weights=True)
+    o_ang = ON.SeparableFCTP(irr, irr, pres, None, use_activation=True, internal_weights=True)
+    with torch.no_grad():
+        for m in (o_lin, o_ang):
+            m.lin.bias[0].uniform_(-1, 1)
+    p_lin, p_ang = _ScoreTP(Irreps(IRR[32]), 32), _ScoreTP(Irreps(IRR[32]), 32)
+    p_lin.load_state_dict(o_lin.state_dict()); p_ang.load_state_dict(o_ang.state_dict())
+    p_lin, p_ang = p_lin.to(cuda), p_ang.to(cuda)
+    a, b = torch.randn(nT * nQ, 240), torch.randn(nT * nQ, 240)
+    q = torch.nn.functional.normalize(torch.randn(nT, 4), dim=-1)
+    Ts = torch.cat([q, torch.randn(nT, 3)], -1)
+    qx, qw = torch.randn(nQ, 3) * 5, torch.rand(nQ)
+    with torch.no_grad():
+        lin = o_lin(a, b, edge_scalars=None)[..., 1:].view(nT, nQ, 32, 3).mean(-2)
+        ang = o_ang(a, b, edge_scalars=None)[..., 1:].view(nT, nQ, 32, 3).mean(-2)
+        qinv = enc.quaternion_invert(q.unsqueeze(-2))
+        lin, ang = enc.quaternion_apply(qinv, lin), enc.quaternion_apply(qinv, ang)
+        orb = torch.cross(qx.unsqueeze(0) / 15.0, lin, dim=-1)
+        lin_ref = torch.einsum("q,tqi->ti", qw, lin)
+        ang_ref = torch.einsum("q,tqi->ti", qw, orb) + torch.einsum("q,tqi->ti", qw, ang)
+    Wd = [p_lin.dtp.tp.weight.detach().contiguous(), p_ang.dtp.tp.weight.detach().contiguous()]
+    (l0, l1, _), lb = p_lin.lin.packed()
+    (a0, a1, _), ab = p_ang.lin.packed()
+    ang_g, lin_g = ops.score_tp(Ts.to(cuda), a.to(cuda), b.to(cuda), qx.to(cuda), qw.to(cuda), (64, 32, 16), Wd, [l0, a0], [l1, a1], [lb, ab], 32, 15.0)
+    assert_close(lin_g, lin_ref, TOL, "lin score")
+    assert_close(ang_g, ang_ref, TOL, "ang score")
+
+
+def test_pose_update(cuda):
+    from diffusion_edf_b200 import ops
+    torch.manual_seed(9)
+    n = 50
+    q = torch.nn.functional.normalize(torch.randn(n, 4, dtype=torch.float64), dim=-1)
+    T = torch.cat([q, torch.randn(n, 3, dtype=torch.float64)], -1)
+    ang, lin = torch.randn(n, 3), torch.randn(n, 3)
+    z = torch.randn(n, 6, dtype=torch.float64)
+    t, am, lm, temp = 0.37, 2.5, 15.0, 0.8
+    a_ang, a_lin = am ** 2 * t ** 0.5 * 0.04, lm ** 2 * t ** 0.5 * 0.04
+    # reference arithmetic (score_model_base.py:178-193)
+    s_a = ang.double() / (am * math.sqrt(t)); s_l = lin.double() / (lm * math.sqrt(t))
+    ad = (a_ang / 2) * s_a + math.sqrt(temp * a_ang) * z[:, :3]
+    ld = (a_lin / 2) * s_l + math.sqrt(temp * a_lin) * z[:, 3:]
+    qi = torch.tensor([[1, 2, 3], [0, 3, 2], [3, 0, 1], [2, 1, 0]])
+    qf = torch.tensor([[-0.5, -0.5, -0.5], [0.5, -0.5, 0.5], [0.5, 0.5, -0.5], [-0.5, 0.5, 0.5]], dtype=torch.float64)
+    Lm = T[..., qi] * qf
+    dq = torch.einsum("...ij,...j->...i", Lm, ad)
+    dx = enc.quaternion_apply(T[:, :4], ld)
+    ref = torch.cat([enc.normalize_quaternion(T[:, :4] + dq), T[:, 4:] + dx], -1)
+    Td = T.to(cuda).clone()
+    traj = torch.empty(n, 7, dtype=torch.float64, device=cuda)
+    T32 = torch.empty(n, 7, dtype=torch.float32, device=cuda)
+    ops.pose_update(Td, ang.to(cuda), lin.to(cuda), z.to(cuda), 0, 0, t, am, lm, a_ang, a_lin, temp, traj, T32)
+    assert (Td.cpu() - ref).abs().max() < 1e-12
+    assert torch.equal(traj, Td) and torch.equal(T32, Td.float())
+    # Philox path: unit quaternions, finite, different poses get different noise, deterministic in (seed, offset)
+    T1, T2 = T.to(cuda).clone(), T.to(cuda).clone()
+    ops.pose_update(T1, ang.to(cuda), lin.to(cuda), None, 123, 5, t, am, lm, a_ang, a_lin, temp, None, None)
+    ops.pose_update(T2, ang.to(cuda), lin.to(cuda), None, 123, 5, t, am, lm, a_ang, a_lin, temp, None, None)
+    assert torch.equal(T1, T2) and torch.isfinite(T1).all()
+    assert (T1[:, :4].norm(dim=-1) - 1).abs().max() < 1e-12
+    assert (T1 - Td).abs().max() > 1e-3
