@@ -110,7 +110,7 @@ class TensorProduct(nn.Module):
                 outs[io] = outs[io] + torch.einsum(f"{z}uv,zuvk->zuk", w, t)
             else:
                 outs[io] = outs[io] + torch.einsum(f"{z}uvw,zuvk->zwk", w, t)
-        return torch.cat([o.reshape(N, -1) for o in outs], dim=1)
+        return torch.cat([o.reshape(N, m * (2 * l + 1)) for o, (m, l, _) in zip(outs, self.out)], dim=1)
 
 
 class TensorProductRescale(nn.Module):
@@ -352,7 +352,7 @@ def vec2heads(x: torch.Tensor, irreps_head: Irreps, num_heads: int) -> torch.Ten
     N, out, off = x.shape[0], [], 0
     for m, l, _ in irreps_head:
         w = m * num_heads * (2 * l + 1)
-        out.append(x[:, off:off + w].reshape(N, num_heads, -1))
+        out.append(x[:, off:off + w].reshape(N, num_heads, m * (2 * l + 1)))
         off += w
     return torch.cat(out, dim=2)
 
@@ -362,7 +362,7 @@ def heads2vec(x: torch.Tensor, irreps_head: Irreps) -> torch.Tensor:
     N, out, off = x.shape[0], [], 0
     for m, l, _ in irreps_head:
         w = m * (2 * l + 1)
-        out.append(x[:, :, off:off + w].reshape(N, -1))
+        out.append(x[:, :, off:off + w].reshape(N, x.shape[1] * w))
         off += w
     return torch.cat(out, dim=1)
 

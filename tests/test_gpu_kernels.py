@@ -52,7 +52,9 @@ def test_edge_geom(cuda):
         ge = par._encode_edges(xs, y, es[lo:hi], ed[lo:hi], par.fill_edge_weights if r is None else None)
         assert_close(length[lo:hi], ge.edge_length, 1e-6, f"length s{s}")
         assert_close(sh[lo:hi], ge.edge_attr, 1e-5, f"sh s{s}")
-        assert (logit[lo:hi].cpu() - ge.edge_logits).abs().max() < 2e-4, f"logit s{s}"
+        # log(1 - soft_step(u)) cancels catastrophically as u -> 1: compare the weights, and the logits loosely
+        assert (logit[lo:hi].cpu().exp() - ge.edge_logits.exp()).abs().max() < 1e-6, f"edge weight s{s}"
+        assert (logit[lo:hi].cpu() - ge.edge_logits).abs().max() < 5e-3, f"logit s{s}"
     # plain variant (UNet): no cut-off, no logits
     length2, sh2, lg2 = ops.edge_geom(xs.to(cuda), y.to(cuda), csr)
     assert lg2 is None
