@@ -1,0 +1,330 @@
+#!/usr/bin/env python3
+"""Benchmark of the Diffusion-EDF score-network hot path (BASELINE.json metric: pose-scores/sec of
+MultiscaleScoreModel.forward).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host CPU cores (oracle port)
+
+Workload (config C2, BASELINE.json configs[1]): MultiscaleScoreModel of configs/panda_mug/pick_lowres, random-init
+weights (seed 0), 10 000-point synthetic surface-like scene (cm), 128 poses per GPU, per-pose time ~ U(0.01, 1].
+One step = one full forward: UNet scene encode + query model + score head.  With N GPUs every rank scores its own
+128 poses (weak scaling); rank 0 encodes the scene and broadcasts the packed field (one NCCL broadcast per step).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_POINTS, N_POSES = 10_000, 128
+METRIC = "pose-scores/sec (nPoses x steps) MultiscaleScoreModel fwd"
+UNIT = "pose-scores/s"
+WORKLOAD = "C2: MultiscaleScoreModel.forward, panda_mug pick_lowres, 10k-pt synthetic scene, 128 T_seed per GPU"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _inputs(seed_rank: int):
+    from diffusion_edf_b200.synthetic import make_poses, make_scene
+    x, rgb = make_scene(N_POINTS, seed=0)
+    Ts, t = make_poses(N_POSES, x, seed=seed_rank)
+    b = torch.zeros(N_POINTS, dtype=torch.long)
+    gx, gf, gb = torch.zeros(512, 3), torch.zeros(512, 3), torch.zeros(512, dtype=torch.long)
+    return x, rgb, b, Ts, t, gx, gf, gb
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own algorithm for this path on the host CPU.  e3nn / torch_scatter / torch_cluster cannot be
+    installed in this image (no wheels, no network), so the reference itself cannot run; this arm times the oracle
+    port (oracle/, plain torch on all host cores), which restates the reference line by line."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from diffusion_edf_b200.synthetic import model_kwargs
+    from oracle import model as OM
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = OM.MultiscaleScoreModel(**model_kwargs(), deterministic=True).eval()
+    x, rgb, b, Ts, t, gx, gf, gb = _inputs(0)
+    key, grasp = OM.FeaturedPoints(x, rgb, b), OM.FeaturedPoints(gx, gf, gb)
+    budget_s = 170.0
+    times = []
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        model(Ts, t, key, grasp)
+        first = time.perf_counter() - t0
+        warm = max(0, min(args.warmup - 1, int(0.25 * budget_s / first)))
+        for _ in range(warm):
+            model(Ts, t, key, grasp)
+        steps = max(1, min(args.steps, int((budget_s - (1 + warm) * first) / first)))
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            model(Ts, t, key, grasp)
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = N_POSES / (ms / 1e3)
+    sample = (f"{steps} full forwards of the C2 workload (10k-pt scene, {N_POSES} poses) on {cores} host threads"
+              + ("" if steps == args.steps else f"; {args.steps} steps requested, bounded to {steps} by the {budget_s:.0f}s budget"))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "steps_requested": args.steps, "warmup": 1 + warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "poses_per_step": N_POSES, "scene_points": N_POINTS, "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ CUDA arm
+def _k1_roofline(dev, peak_gbs, peak_src):
+    """K1 (fused gather -> depthwise CG TP -> x alpha -> segment reduce) on config C4 at N = 100k, degree 32:
+    algorithmic bytes / CUDA-event time."""
+    from diffusion_edf_b200 import ops
+    N, deg, F, W, FOUT = 100_000, 32, 240, 480, 1568
+    E = N * deg
+    g = torch.Generator(device="cpu").manual_seed(0)
+    row_ptr = (torch.arange(N + 1, dtype=torch.int64) * deg).to(torch.int32).to(dev)
+    edge_src = torch.randint(0, N, (E,), generator=g, dtype=torch.int32).to(dev)
+    x = torch.randn(N, F, device=dev)
+    v = torch.nn.functional.normalize(torch.randn(E, 3, device=dev), dim=-1)
+    s3, s5, s15 = 3 ** 0.5, 5 ** 0.5, 15 ** 0.5
+    sh = torch.stack([torch.ones(E, device=dev), s3 * v[:, 0], s3 * v[:, 1], s3 * v[:, 2], s15 * v[:, 0] * v[:, 2], s15 * v[:, 0] * v[:, 1],
+                      s5 * (v[:, 1] ** 2 - 0.5 * (v[:, 0] ** 2 + v[:, 2] ** 2)), s15 * v[:, 1] * v[:, 2],
+                      0.5 * s15 * (v[:, 2] ** 2 - v[:, 0] ** 2)], dim=1).contiguous()
+    w = torch.randn(E, W, device=dev) * 0.1
+    alpha = torch.rand(E, 4, device=dev)
+    flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)          # > 126 MB L2
+    times = []
+    for it in range(3 + 10):
+        flush.fill_(float(it))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = ops.edge_tp_reduce(32, x, row_ptr, edge_src, sh, w, alpha)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    alg_bytes = E * 4 * (W + 9 + 4 + 1) + N * 4 * F + N * 4 * FOUT + 4 * (N + 1)
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    del flush, w
+    return {"kernel": "dedf_edge_tp_reduce (K1: gather + depthwise CG TP + alpha + segment reduce)",
+            "workload": "C4: N=100k nodes, degree 32, 64x0e+32x1e+16x2e, per-edge weights (E,480)",
+            "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+            "peak_source": peak_src, "ms_per_launch": ms, "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": len(times),
+            "traffic": None, "l2": "flushed between launches (512 MB fill)"}
+
+
+def run_cuda(args):
+    import torch.distributed as dist
+    from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel, ops, parallel
+    from diffusion_edf_b200.synthetic import model_kwargs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N bench.py --gpus N ...")
+    assert torch.cuda.is_available(), "bench.py (CUDA arm) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = MultiscaleScoreModel(**model_kwargs(), deterministic=True).eval().to(dev)
+    model.requires_grad_(False)
+    x, rgb, b, Ts, t, gx, gf, gb = _inputs(rank)
+    host = [v.pin_memory() for v in (x, rgb, b, Ts, t, gx, gf, gb)]
+    d = [v.to(dev) for v in host]
+    sizes = [4, 240, 2, 2000, 400, 80, 16]
+
+    def step(dv):
+        key = FeaturedPoints(dv[0], dv[1], dv[2])
+        grasp = FeaturedPoints(dv[5], dv[6], dv[7])
+        with torch.no_grad():
+            if world == 1:
+                (ang, lin), _ = model(dv[3], dv[4], key, grasp)
+            else:
+                ang, lin = parallel.sharded_forward(model, dv[3], dv[4], key if rank == 0 else None, grasp, src=0, sizes=sizes)
+        return ang, lin
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)            # 256 MB > 126 MB L2
+    for _ in range(max(3, args.warmup)):
+        step(d)
+    barrier()
+    # ---------------- timed region: device-resident inputs, CUDA events per step, L2 flushed between steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCHES
+    ev = []
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(d)
+        e1.record()
+        ev.append((e0, e1))
+    barrier()
+    launches = ops.LAUNCHES - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_local = sum(a.elapsed_time(bb) for a, bb in ev) / args.steps
+    # ---------------- e2e: host (pinned) inputs -> H2D -> forward -> D2H of the scores, wall clock
+    out_host = [torch.empty(N_POSES, 3).pin_memory(), torch.empty(N_POSES, 3).pin_memory()]
+    h2d = sum(v.numel() * v.element_size() for i, v in enumerate(host) if (rank == 0 or i >= 3))
+    d2h = sum(v.numel() * v.element_size() for v in out_host)
+
+    def e2e_step():
+        dv = [v.to(dev, non_blocking=True) for v in host]
+        ang, lin = step(dv)
+        out_host[0].copy_(ang, non_blocking=True)
+        out_host[1].copy_(lin, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_ms_local = 1e3 * (time.perf_counter() - t0) / args.steps
+    # max over ranks
+    tms = torch.tensor([ms_local, e2e_ms_local], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = tms.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    # ---------------- rank 0 only: per-entry-point breakdown of one more set of steps, K1 roofline, CPU baseline
+    ops.PROFILE = {}
+    for _ in range(min(5, args.steps)):
+        step(d)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    n_prof = min(5, args.steps)
+    breakdown = {k: {"ms_per_step": sum(a.elapsed_time(bb) for a, bb in v) / n_prof, "calls_per_step": len(v) / n_prof} for k, v in prof.items()}
+    total_k = sum(v["ms_per_step"] for v in breakdown.values())
+    for v in breakdown.values():
+        v["share"] = v["ms_per_step"] / total_k if total_k else 0.0
+    del flush
+    peak, peak_src = _peaks()
+    roof = _k1_roofline(dev, peak, peak_src)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import model as OM
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        torch.manual_seed(0)
+        omodel = OM.MultiscaleScoreModel(**model_kwargs(), deterministic=True).eval()
+        key, grasp = OM.FeaturedPoints(x, rgb, b), OM.FeaturedPoints(gx, gf, gb)
+        ts = []
+        with torch.no_grad():
+            for i in range(3):
+                t0 = time.perf_counter()
+                omodel(Ts, t, key, grasp)
+                ts.append(time.perf_counter() - t0)
+        cpu_s = statistics.median(ts[1:])
+        cpu = {"value": N_POSES / cpu_s, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"2 full forwards of the same C2 workload (after 1 warm-up) through oracle/ on {cores} host threads, median"}
+    print(json.dumps({
+        "metric": METRIC, "value": world * N_POSES / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "poses_per_gpu": N_POSES, "scene_points": N_POINTS, "weights": "random init, seed 0",
+                   "parallelism": f"pose-sharded x{world}; rank 0 encodes the scene, 1 NCCL broadcast of the packed field per step" if world > 1 else "single GPU",
+                   "l2": "flushed between timed steps (256 MB fill)", "timing": "CUDA events per step, max over ranks"},
+        "e2e": {"value": world * N_POSES / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "timing": "wall clock incl. pinned H2D of scene+poses and D2H of the scores"},
+        "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
+        "clocks": clocks, "roofline": roof, "step_breakdown": breakdown, "cpu_baseline": cpu,
+    }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

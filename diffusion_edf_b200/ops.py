@@ -26,6 +26,32 @@ class Csr(NamedTuple):
 
 
 # ----------------------------------------------------------------------------
+# call accounting: kernels launched (bench.py's ``gpu_launches``) and optional per-entry-point CUDA-event timing
+# ----------------------------------------------------------------------------
+LAUNCHES = 0
+PROFILE = None      # set to {} to collect {entry point: [(start_event, end_event), ...]}
+_KERNELS = {"dedf_fps": 1, "dedf_radius_count": 2, "dedf_radius_fill": 1, "dedf_edge_geom": 1, "dedf_edge_mlp": 1,
+            "dedf_edge_tp_lin": 1, "dedf_segment_softmax_reduce": 1, "dedf_edge_tp_reduce": 1, "dedf_node_linear": 1,
+            "dedf_gather_rows": 1, "dedf_add_scale": 1, "dedf_time_embed": 1, "dedf_query_transform": 1, "dedf_score_tp": 1,
+            "dedf_pose_update": 2}
+
+
+def _call(name: str, *args) -> None:
+    global LAUNCHES
+    fn = getattr(L.load(), name)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROFILE.setdefault(name, []).append((e0, e1))
+    else:
+        rc = fn(*args)
+    check(rc, name)
+    LAUNCHES += _KERNELS[name]
+
+
+# ----------------------------------------------------------------------------
 # graph construction
 # ----------------------------------------------------------------------------
 def fps(x: torch.Tensor, batch: Optional[torch.Tensor], ratio: float, random_start: bool = False) -> torch.Tensor:
@@ -48,7 +74,7 @@ def fps(x: torch.Tensor, batch: Optional[torch.Tensor], ratio: float, random_sta
     for (o, n), m in zip(segs, ms):
         start = int(torch.randint(n, (1,)).item()) if random_start else 0
         scratch = torch.empty(n, dtype=torch.float32, device=x.device) if n > 16384 else None
-        check(lib.dedf_fps(ptr(x) + o * 12, n, m, start, o, out.data_ptr() + off * 8, ptr(scratch), stream()), "dedf_fps")
+        _call("dedf_fps", ptr(x) + o * 12, n, m, start, o, out.data_ptr() + off * 8, ptr(scratch), stream())
         off += m
     return out
 
@@ -73,16 +99,15 @@ def radius_csr(x_src: torch.Tensor, x_dst: torch.Tensor, radii: Sequence[Optiona
     pb_s = ptr(b_src, torch.long) if b_src is not None else None
     pb_d = ptr(b_dst, torch.long) if b_dst is not None else None
     pex = ptr(excl, torch.long) if excl is not None else None
-    check(lib.dedf_radius_count(ptr(x_src), ptr(x_dst), n_dst, n_scales, so, rr, pb_s, pb_d, excl_mode, pex,
-                                max_num_neighbors, ptr(counts, torch.int32), ptr(row_ptr, torch.int32), stream()),
-          "dedf_radius_count")
+    _call("dedf_radius_count", ptr(x_src), ptr(x_dst), n_dst, n_scales, so, rr, pb_s, pb_d, excl_mode, pex,
+                                max_num_neighbors, ptr(counts, torch.int32), ptr(row_ptr, torch.int32), stream())
     n_edges_dev = row_ptr[-1:]
     n_edges = int(n_edges_dev.item())          # the one host sync of a graph build (sizes the edge buffers)
     edge_src = torch.empty(max(1, n_edges), dtype=torch.int32, device=dev)
     edge_dst = torch.empty(max(1, n_edges), dtype=torch.int32, device=dev)
-    check(lib.dedf_radius_fill(ptr(x_src), ptr(x_dst), n_dst, n_scales, so, rr, pb_s, pb_d, excl_mode, pex,
+    _call("dedf_radius_fill", ptr(x_src), ptr(x_dst), n_dst, n_scales, so, rr, pb_s, pb_d, excl_mode, pex,
                                max_num_neighbors, ptr(row_ptr, torch.int32), ptr(edge_src, torch.int32),
-                               ptr(edge_dst, torch.int32), stream()), "dedf_radius_fill")
+                               ptr(edge_dst, torch.int32), stream())
     return Csr(row_ptr, edge_src[:n_edges], edge_dst[:n_edges], n_edges_dev, n_edges, n_dst, n_scales)
 
 
@@ -118,30 +143,29 @@ def edge_geom(x_src: torch.Tensor, x_dst: torch.Tensor, g: Csr, radii: Optional[
     so = L.int_array(src_off if src_off is not None else [0, x_src.shape[0]])
     rr = L.float_array([-1.0 if r is None else float(r) for r in (radii if radii is not None else [None])])
     lo, hi = ns_cut if ns_cut is not None else (0.0, -1.0)
-    check(lib.dedf_edge_geom(ptr(x_src.contiguous()), ptr(x_dst.contiguous()), ptr(g.edge_src, torch.int32),
+    _call("dedf_edge_geom", ptr(x_src.contiguous()), ptr(x_dst.contiguous()), ptr(g.edge_src, torch.int32),
                              ptr(g.edge_dst, torch.int32), ptr(g.n_edges_dev, torch.int32), g.n_edges, n_scales, so, rr,
-                             lo, hi, ptr(length), ptr(sh), ptr(logit), stream()), "dedf_edge_geom")
+                             lo, hi, ptr(length), ptr(sh), ptr(logit), stream())
     return length, sh, logit
 
 
 def edge_mlp(desc: L.MlpDesc, max_edges: int) -> None:
-    check(L.load().dedf_edge_mlp(C.byref(desc), max_edges, stream()), "dedf_edge_mlp")
+    _call("dedf_edge_mlp", C.byref(desc), max_edges, stream())
 
 
 def edge_tp_lin(mul1: int, epilogue: int, x_src: torch.Tensor, x_dst: Optional[torch.Tensor], per_edge_x: bool, g: Csr,
                 sh: torch.Tensor, w: torch.Tensor, w_stride: int, W0, W1, W2, bias0, alpha_dot=None, edge_logit=None,
                 logits=None, out=None) -> None:
-    check(L.load().dedf_edge_tp_lin(mul1, epilogue, ptr(x_src), ptr(x_dst), 1 if per_edge_x else 0,
+    _call("dedf_edge_tp_lin", mul1, epilogue, ptr(x_src), ptr(x_dst), 1 if per_edge_x else 0,
                                     ptr(g.edge_src, torch.int32), ptr(g.edge_dst, torch.int32),
                                     ptr(g.n_edges_dev, torch.int32), g.n_edges, ptr(sh), ptr(w), w_stride, ptr(W0), ptr(W1),
-                                    ptr(W2), ptr(bias0), ptr(alpha_dot), ptr(edge_logit), ptr(logits), ptr(out), stream()),
-          "dedf_edge_tp_lin")
+                                    ptr(W2), ptr(bias0), ptr(alpha_dot), ptr(edge_logit), ptr(logits), ptr(out), stream())
 
 
 def segment_softmax_reduce(g: Csr, logits: torch.Tensor, val: torch.Tensor, irr: Tuple[int, int, int]) -> torch.Tensor:
     out = torch.empty(g.n_dst, irr[0] + 3 * irr[1] + 5 * irr[2], dtype=torch.float32, device=val.device)
-    check(L.load().dedf_segment_softmax_reduce(ptr(g.row_ptr, torch.int32), g.n_dst, g.n_seg, ptr(logits), ptr(val),
-                                               irr[0], irr[1], irr[2], ptr(out), stream()), "dedf_segment_softmax_reduce")
+    _call("dedf_segment_softmax_reduce", ptr(g.row_ptr, torch.int32), g.n_dst, g.n_seg, ptr(logits), ptr(val),
+                                               irr[0], irr[1], irr[2], ptr(out), stream())
     return out
 
 
@@ -150,8 +174,8 @@ def edge_tp_reduce(mul1: int, x: torch.Tensor, row_ptr: torch.Tensor, edge_src: 
     """K1: out[d] = sum_{e->d} alpha[e, head(u)] * DTP(x[src_e], sh_e, w_e)  -> (N_dst, 49 * mul1)."""
     n_dst = row_ptr.numel() - 1
     out = torch.empty(n_dst, 49 * mul1, dtype=torch.float32, device=x.device)
-    check(L.load().dedf_edge_tp_reduce(mul1, ptr(x), ptr(row_ptr, torch.int32), ptr(edge_src, torch.int32), ptr(sh), ptr(w),
-                                       ptr(alpha), n_dst, ptr(out), stream()), "dedf_edge_tp_reduce")
+    _call("dedf_edge_tp_reduce", mul1, ptr(x), ptr(row_ptr, torch.int32), ptr(edge_src, torch.int32), ptr(sh), ptr(w),
+                                       ptr(alpha), n_dst, ptr(out), stream())
     return out
 
 
@@ -167,21 +191,21 @@ def node_linear(x: torch.Tensor, irr_in, irr_out, W: Sequence[Optional[torch.Ten
         fy -= irr_out[1] + irr_out[2]
     y = torch.empty(n, fy, dtype=torch.float32, device=x.device)
     ln_w, ln_b = (ln if ln is not None else (None, None))
-    check(L.load().dedf_node_linear(ptr(x), n, L.int_array(irr_in), L.int_array(irr_out), ptr(W[0]), ptr(W[1]), ptr(W[2]),
+    _call("dedf_node_linear", ptr(x), n, L.int_array(irr_in), L.int_array(irr_out), ptr(W[0]), ptr(W[1]), ptr(W[2]),
                                     ptr(bias0), ptr(ln_w), ptr(ln_b), ln_eps, 1 if gate else 0, ptr(res), res_scale, ptr(y),
-                                    stream()), "dedf_node_linear")
+                                    stream())
     return y
 
 
 def gather_rows(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     y = torch.empty(idx.shape[0], x.shape[1], dtype=torch.float32, device=x.device)
-    check(L.load().dedf_gather_rows(ptr(x), ptr(idx, torch.long), idx.shape[0], x.shape[1], ptr(y), stream()), "dedf_gather_rows")
+    _call("dedf_gather_rows", ptr(x), ptr(idx, torch.long), idx.shape[0], x.shape[1], ptr(y), stream())
     return y
 
 
 def add_scale(a: torch.Tensor, b: torch.Tensor, s: float) -> torch.Tensor:
     y = torch.empty_like(a)
-    check(L.load().dedf_add_scale(ptr(a), ptr(b), s, a.numel(), ptr(y), stream()), "dedf_add_scale")
+    _call("dedf_add_scale", ptr(a), ptr(b), s, a.numel(), ptr(y), stream())
     return y
 
 
@@ -190,7 +214,7 @@ def add_scale(a: torch.Tensor, b: torch.Tensor, s: float) -> torch.Tensor:
 # ----------------------------------------------------------------------------
 def time_embed(desc: L.TimeDesc, time: torch.Tensor) -> torch.Tensor:
     out = torch.empty(desc.n_scales, time.shape[0], desc.out_dim, dtype=torch.float32, device=time.device)
-    check(L.load().dedf_time_embed(C.byref(desc), ptr(time), time.shape[0], ptr(out), stream()), "dedf_time_embed")
+    _call("dedf_time_embed", C.byref(desc), ptr(time), time.shape[0], ptr(out), stream())
     return out
 
 
@@ -198,8 +222,7 @@ def query_transform(Ts: torch.Tensor, qx: torch.Tensor, qf: torch.Tensor, irr) -
     n_t, n_q = Ts.shape[0], qx.shape[0]
     x_out = torch.empty(n_t * n_q, 3, dtype=torch.float32, device=Ts.device)
     f_out = torch.empty(n_t * n_q, qf.shape[1], dtype=torch.float32, device=Ts.device)
-    check(L.load().dedf_query_transform(ptr(Ts), n_t, ptr(qx), ptr(qf), n_q, L.int_array(irr), ptr(x_out), ptr(f_out), stream()),
-          "dedf_query_transform")
+    _call("dedf_query_transform", ptr(Ts), n_t, ptr(qx), ptr(qf), n_q, L.int_array(irr), ptr(x_out), ptr(f_out), stream())
     return x_out, f_out
 
 
@@ -208,15 +231,14 @@ def score_tp(Ts, qf_rot, key_f, qx, qw, irr, Wd: List[torch.Tensor], Wl0, Wl1, b
     ang = torch.empty(n_t, 3, dtype=torch.float32, device=Ts.device)
     lin = torch.empty(n_t, 3, dtype=torch.float32, device=Ts.device)
     arr = lambda ts: (L.c_fp * 2)(ptr(ts[0]), ptr(ts[1]))
-    check(L.load().dedf_score_tp(ptr(Ts), n_t, ptr(qf_rot), ptr(key_f), ptr(qx), ptr(qw), qx.shape[0], L.int_array(irr),
-                                 arr(Wd), arr(Wl0), arr(Wl1), arr(bl), n_vec, lin_mult, ptr(ang), ptr(lin), stream()),
-          "dedf_score_tp")
+    _call("dedf_score_tp", ptr(Ts), n_t, ptr(qf_rot), ptr(key_f), ptr(qx), ptr(qw), qx.shape[0], L.int_array(irr),
+                                 arr(Wd), arr(Wl0), arr(Wl1), arr(bl), n_vec, lin_mult, ptr(ang), ptr(lin), stream())
     return ang, lin
 
 
 def pose_update(T: torch.Tensor, ang: torch.Tensor, lin: torch.Tensor, noise: Optional[torch.Tensor], seed: int, offset: int,
                 t: float, ang_mult: float, lin_mult: float, alpha_ang: float, alpha_lin: float, temperature: float,
                 traj_out: Optional[torch.Tensor], T_f32_out: Optional[torch.Tensor]) -> None:
-    check(L.load().dedf_pose_update(ptr(T, torch.float64), T.shape[0], ptr(ang), ptr(lin), ptr(noise, torch.float64), seed, offset,
+    _call("dedf_pose_update", ptr(T, torch.float64), T.shape[0], ptr(ang), ptr(lin), ptr(noise, torch.float64), seed, offset,
                                     t, ang_mult, lin_mult, alpha_ang, alpha_lin, temperature, ptr(traj_out, torch.float64),
-                                    ptr(T_f32_out), stream()), "dedf_pose_update")
+                                    ptr(T_f32_out), stream())

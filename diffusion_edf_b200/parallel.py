@@ -86,3 +86,23 @@ def all_gather_rows(mine: torch.Tensor, n_total: int) -> torch.Tensor:
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return torch.cat(out, dim=0)[:n_total]
+
+
+def sharded_forward(model, Ts_local: torch.Tensor, time_local: torch.Tensor, key_pcd: Optional[FeaturedPoints],
+                    query_pcd: FeaturedPoints, src: int = 0, sizes: Optional[Sequence[int]] = None):
+    """``MultiscaleScoreModel.forward`` with the pose batch sharded over the ranks: rank ``src`` encodes the scene
+    (UNet) and the query points once, the packed field is broadcast, every rank scores its own poses.
+    Returns this rank's (ang (nT_local,3), lin (nT_local,3))."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if world == 1:
+        (ang, lin), _ = model(Ts_local, time_local, key_pcd, query_pcd)
+        return ang, lin
+    if rank == src:
+        keys = model.get_key_pcd_multiscale(key_pcd)
+        query = model.get_query_pcd(query_pcd)
+        query = FeaturedPoints(query.x.detach(), query.f.detach(), query.b, query.w.detach())
+    else:
+        keys, query = None, None
+    keys, query = broadcast_scene_field(keys, query, src=src, device=Ts_local.device, sizes=sizes)
+    return model.score_head(Ts=Ts_local, key_pcd_multiscale=keys, query_pcd=query, time=time_local)
