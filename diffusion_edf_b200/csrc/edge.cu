@@ -497,7 +497,7 @@ struct SoftmaxArgs {
     int m0, m1, m2;        // value irreps; heads split every mul in 4
 };
 
-__global__ void __launch_bounds__(256) segment_softmax_reduce_kernel(SoftmaxArgs a) {
+__global__ void __launch_bounds__(128) segment_softmax_reduce_kernel(SoftmaxArgs a) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int F = a.m0 + 3 * a.m1 + 5 * a.m2;
@@ -539,21 +539,33 @@ __global__ void __launch_bounds__(256) segment_softmax_reduce_kernel(SoftmaxArgs
             else if (c < F) h = ((c - a.m0 - 3 * a.m1) / 5) / (a.m2 / 4);
             hd[j] = h;
         }
-        // pass 3: weighted sum
+        // pass 3: weighted sum, 4 edges in flight per iteration (independent loads)
         float acc[MAXC];
 #pragma unroll
         for (int j = 0; j < MAXC; ++j) acc[j] = 0.f;
         for (int s = 0; s < a.n_seg; ++s) {
             const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
-            for (int i = b; i < e; ++i) {
-                const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
-                const float al0 = __expf(l.x - logZ[0]), al1 = __expf(l.y - logZ[1]), al2 = __expf(l.z - logZ[2]), al3 = __expf(l.w - logZ[3]);
-                const float* v = a.val + (size_t)i * F;
+            for (int i0 = b; i0 < e; i0 += 4) {
+                float4 l[4];
+                float v[4][MAXC];
 #pragma unroll
-                for (int j = 0; j < MAXC; ++j) {
-                    const int c = lane + 32 * j;
-                    const float al = (hd[j] == 0) ? al0 : (hd[j] == 1) ? al1 : (hd[j] == 2) ? al2 : al3;
-                    if (c < F) acc[j] = fmaf(al, v[c], acc[j]);
+                for (int u = 0; u < 4; ++u) {
+                    const int i = min(i0 + u, e - 1);
+                    l[u] = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
+                    const float* vp = a.val + (size_t)i * F;
+#pragma unroll
+                    for (int j = 0; j < MAXC; ++j) { const int c = lane + 32 * j; v[u][j] = (c < F) ? vp[c] : 0.f; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool on = (i0 + u) < e;
+                    const float al0 = on ? __expf(l[u].x - logZ[0]) : 0.f, al1 = on ? __expf(l[u].y - logZ[1]) : 0.f;
+                    const float al2 = on ? __expf(l[u].z - logZ[2]) : 0.f, al3 = on ? __expf(l[u].w - logZ[3]) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < MAXC; ++j) {
+                        const float al = (hd[j] == 0) ? al0 : (hd[j] == 1) ? al1 : (hd[j] == 2) ? al2 : al3;
+                        acc[j] = fmaf(al, v[u][j], acc[j]);
+                    }
                 }
             }
         }
@@ -720,6 +732,263 @@ __global__ void __launch_bounds__(256) edge_tp_reduce_kernel(TpReduceArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// K1, TMA variant: every warp owns a private multi-stage ring in shared memory that is filled by 1-D bulk
+// async copies (cp.async.bulk global -> shared, SASS UBLKCP) signalled through mbarriers: one stage = one pack
+// of P edges = [P weight rows | P gathered source-feature rows | P spherical harmonics (padded to 12) | P alphas].
+// The CG math reads only shared memory; the output row is staged and written with coalesced float4 stores.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+constexpr int kK1Warps = 8;
+constexpr int kK1Stages = 3;
+constexpr int kK1TaskD = 16;      // destinations per warp task (row pointers live in lanes 0..16)
+
+template <int G>
+struct K1Stage {
+    using D = Dtp<G>;
+    static constexpr int P = D::P;
+    static constexpr int W_OFF = 0, X_OFF = P * D::NUMEL, SH_OFF = X_OFF + P * D::F, AL_OFF = SH_OFF + P * 12;
+    static constexpr int FLOATS = AL_OFF + P * 4;
+    static constexpr int EDGE_BYTES = (D::NUMEL + D::F + 12 + 4) * 4;
+    static constexpr int WARP_FLOATS = kK1Stages * FLOATS + D::FOUT;
+};
+
+template <int G>
+__global__ void __launch_bounds__(kK1Warps * 32, 1) edge_tp_reduce_tma_kernel(TpReduceArgs a) {
+    using D = Dtp<G>;
+    using ST = K1Stage<G>;
+    constexpr int P = D::P, S = kK1Stages;
+    constexpr int S0 = 4 / P;
+    extern __shared__ __align__(128) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * S;                 // [warps][S]
+    float* base = smem + (kK1Warps * S * 2 + 31) / 32 * 32 + (size_t)warp * ST::WARP_FLOATS;
+    float* outst = base + S * ST::FLOATS;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phase = 0;                         // bit s = parity to wait for on stage s
+    const int n_tasks = (a.n_dst + kK1TaskD - 1) / kK1TaskD;
+    const int gw = blockIdx.x * kK1Warps + warp, nw = gridDim.x * kK1Warps;
+
+    for (int task = gw; task < n_tasks; task += nw) {
+        const int d0 = task * kK1TaskD;
+        const int nd = min(kK1TaskD, a.n_dst - d0);
+        const int rp_l = a.row_ptr[d0 + min(lane, nd)];
+        const int e_end = __shfl_sync(0xffffffffu, rp_l, nd);
+        // source-index windows (current / next 32 edges of this task's contiguous edge range)
+        int wbase = __shfl_sync(0xffffffffu, rp_l, 0);
+        int srcw = (wbase + lane < e_end) ? a.edge_src[wbase + lane] : 0;
+        int srcn = (wbase + 32 + lane < e_end) ? a.edge_src[wbase + 32 + lane] : 0;
+        // producer iterator over the task's packs
+        int pd = 0, ppe = 0, pee = 0;
+        while (pd < nd) {
+            ppe = __shfl_sync(0xffffffffu, rp_l, pd); pee = __shfl_sync(0xffffffffu, rp_l, pd + 1);
+            if (ppe < pee) break;
+            ++pd;
+        }
+        int pstage = 0;
+        auto issue = [&](int stage) {
+            if (pd >= nd) return;
+            while (ppe >= wbase + 32) {
+                srcw = srcn; wbase += 32;
+                srcn = (wbase + 32 + lane < e_end) ? a.edge_src[wbase + 32 + lane] : 0;
+            }
+            const int nv = min(P, pee - ppe);
+            int srcs[P];
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                const int idx = ppe + i - wbase;
+                const int v0 = __shfl_sync(0xffffffffu, srcw, idx & 31), v1 = __shfl_sync(0xffffffffu, srcn, idx & 31);
+                srcs[i] = (idx < 32) ? v0 : v1;
+            }
+            if (lane == 0) {
+                float* st = base + stage * ST::FLOATS;
+                uint64_t* bar = bars + stage;
+                mbar_expect_tx(bar, (uint32_t)(nv * ST::EDGE_BYTES));
+                bulk_g2s(st + ST::W_OFF, a.w + (size_t)ppe * D::NUMEL, (uint32_t)(nv * D::NUMEL * 4), bar);
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+                    if (i < nv) bulk_g2s(st + ST::X_OFF + i * D::F, a.x + (size_t)srcs[i] * D::F, (uint32_t)(D::F * 4), bar);
+                bulk_g2s(st + ST::SH_OFF, a.sh + (size_t)ppe * 12, (uint32_t)(nv * 48), bar);
+                bulk_g2s(st + ST::AL_OFF, a.alpha + (size_t)ppe * 4, (uint32_t)(nv * 16), bar);
+            }
+            ppe += P;
+            if (ppe >= pee) {
+                ++pd;
+                while (pd < nd) {
+                    ppe = __shfl_sync(0xffffffffu, rp_l, pd); pee = __shfl_sync(0xffffffffu, rp_l, pd + 1);
+                    if (ppe < pee) break;
+                    ++pd;
+                }
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < S; ++s) { issue(pstage); pstage = (pstage + 1) % S; }
+
+        int cstage = 0;
+        for (int cd = 0; cd < nd; ++cd) {
+            const int ceb = __shfl_sync(0xffffffffu, rp_l, cd), cee = __shfl_sync(0xffffffffu, rp_l, cd + 1);
+            float acc0[4][9], acc1[2][20], acc2[22];
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc0[s][k] = 0.f;
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int k = 0; k < 20; ++k) acc1[s][k] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 22; ++k) acc2[k] = 0.f;
+
+            for (int pe = ceb; pe < cee; pe += P) {
+                const int nv = min(P, cee - pe);
+                mbar_wait(bars + cstage, (phase >> cstage) & 1u);
+                phase ^= (1u << cstage);
+                const float* st = base + cstage * ST::FLOATS;
+                const float* sw = st + ST::W_OFF;
+                const float* sx = st + ST::X_OFF;
+                const float* ssh = st + ST::SH_OFF;
+                const float* sal = st + ST::AL_OFF;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    int ei, ch; D::slot0(lane, s, ei, ch);
+                    if (ei < nv) {
+                        const float al = sal[ei * 4 + ch / (D::M0 / 4)];
+                        const float* w = sw + ei * D::NUMEL;
+                        float o[9];
+                        dtp_l0(sx[ei * D::F + ch] * al, w[D::W_K0 + ch], w[D::W_K1 + ch], w[D::W_K2 + ch], ssh + ei * 12, o);
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) acc0[s][k] += o[k];
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    int ei, ch; D::slot1(lane, s, ei, ch);
+                    if (ei < nv) {
+                        const float al = sal[ei * 4 + ch / (D::M1 / 4)];
+                        const float* xs = sx + ei * D::F + D::M0 + 3 * ch;
+                        float x[3] = {xs[0] * al, xs[1] * al, xs[2] * al}, w[6], o[20];
+                        const float* wp = sw + ei * D::NUMEL + D::W_K3 + ch;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) w[i] = wp[i * D::M1];
+                        dtp_l1(x, w, ssh + ei * 12, o);
+#pragma unroll
+                        for (int k = 0; k < 20; ++k) acc1[s][k] += o[k];
+                    }
+                }
+                {
+                    int ei, ch; D::slot2(lane, ei, ch);
+                    if (ei < nv) {
+                        const float al = sal[ei * 4 + ch / (D::M2 / 4)];
+                        const float* xs = sx + ei * D::F + D::M0 + 3 * D::M1 + 5 * ch;
+                        float x[5], w[6], o[22];
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) x[i] = xs[i] * al;
+                        const float* wp = sw + ei * D::NUMEL + D::W_K9 + ch;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) w[i] = wp[i * D::M2];
+                        dtp_l2(x, w, ssh + ei * 12, o);
+#pragma unroll
+                        for (int k = 0; k < 22; ++k) acc2[k] += o[k];
+                    }
+                }
+                __syncwarp();                    // every lane is done reading this stage -> refill it
+                issue(cstage);
+                cstage = (cstage + 1) % S;
+            }
+            // ---- fold the pack dimension, stage the row, coalesced store (same layout as the LDG variant) ----
+            if (G == 32) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { acc0[0][k] += acc0[2][k]; acc0[1][k] += acc0[3][k]; }
+#pragma unroll
+                for (int k = 0; k < 20; ++k) acc1[0][k] += acc1[1][k];
+#pragma unroll
+                for (int k = 0; k < 22; ++k) acc2[k] += __shfl_xor_sync(0xffffffffu, acc2[k], 16);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc0[0][k] += acc0[1][k] + acc0[2][k] + acc0[3][k];
+#pragma unroll
+                for (int k = 0; k < 20; ++k) { acc1[0][k] += acc1[1][k]; acc1[0][k] += __shfl_xor_sync(0xffffffffu, acc1[0][k], 16); }
+#pragma unroll
+                for (int k = 0; k < 22; ++k) { acc2[k] += __shfl_xor_sync(0xffffffffu, acc2[k], 8); acc2[k] += __shfl_xor_sync(0xffffffffu, acc2[k], 16); }
+            }
+            constexpr int B1 = D::D0, B2 = D::D0 + 3 * D::D1;
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < S0; ++s) {
+                const int ch = lane + 32 * s;
+                outst[D::C0_K0 + ch] = acc0[s][0];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) outst[B1 + (D::C1_K1 + ch) * 3 + k] = acc0[s][1 + k];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) outst[B2 + (D::C2_K2 + ch) * 5 + k] = acc0[s][4 + k];
+            }
+            if (lane < D::M1) {
+                const int ch = lane;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    outst[B1 + (D::C1_K3 + ch) * 3 + k] = acc1[0][k];
+                    outst[B1 + (D::C1_K5 + ch) * 3 + k] = acc1[0][4 + k];
+                    outst[B1 + (D::C1_K7 + ch) * 3 + k] = acc1[0][12 + k];
+                }
+                outst[D::C0_K4 + ch] = acc1[0][3];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    outst[B2 + (D::C2_K6 + ch) * 5 + k] = acc1[0][7 + k];
+                    outst[B2 + (D::C2_K8 + ch) * 5 + k] = acc1[0][15 + k];
+                }
+            }
+            if (lane < D::M2) {
+                const int ch = lane;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    outst[B2 + (D::C2_K9 + ch) * 5 + k] = acc2[k];
+                    outst[B2 + (D::C2_K11 + ch) * 5 + k] = acc2[8 + k];
+                    outst[B2 + (D::C2_K14 + ch) * 5 + k] = acc2[17 + k];
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    outst[B1 + (D::C1_K10 + ch) * 3 + k] = acc2[5 + k];
+                    outst[B1 + (D::C1_K13 + ch) * 3 + k] = acc2[14 + k];
+                }
+                outst[D::C0_K12 + ch] = acc2[13];
+            }
+            __syncwarp();
+            float4* dst = reinterpret_cast<float4*>(a.out + (size_t)(d0 + cd) * D::FOUT);
+            const float4* srcv = reinterpret_cast<const float4*>(outst);
+            for (int i = lane; i < D::FOUT / 4; i += 32) dst[i] = srcv[i];
+        }
+    }
+}
+
 }  // namespace dedf
 
 using namespace dedf;
@@ -834,16 +1103,35 @@ extern "C" int dedf_segment_softmax_reduce(const int* row_ptr, int n_dst, int n_
     if (m0 % 4 || m1 % 4 || m2 % 4 || m0 + 3 * m1 + 5 * m2 > 256) return DEDF_ERR_UNSUPPORTED;
     if (n_dst <= 0) return DEDF_OK;
     SoftmaxArgs a{row_ptr, n_dst, n_seg, logits, val, out, m0, m1, m2};
-    segment_softmax_reduce_kernel<<<grid_for(n_dst, 8, kNumSMs * 8), 256, 0, stream>>>(a);
+    segment_softmax_reduce_kernel<<<grid_for(n_dst, 4, kNumSMs * 16), 128, 0, stream>>>(a);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+template <int G>
+static int launch_k1_tma(const TpReduceArgs& a, cudaStream_t stream) {
+    using ST = K1Stage<G>;
+    const size_t smem = ((size_t)(kK1Warps * kK1Stages * 2 + 31) / 32 * 32 + (size_t)kK1Warps * ST::WARP_FLOATS) * sizeof(float);
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(edge_tp_reduce_tma_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
+    const int n_tasks = (a.n_dst + kK1TaskD - 1) / kK1TaskD;
+    edge_tp_reduce_tma_kernel<G><<<grid_for(n_tasks, kK1Warps, kNumSMs), kK1Warps * 32, smem, stream>>>(a);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
 
 extern "C" int dedf_edge_tp_reduce(int mul1, const float* x, const int* row_ptr, const int* edge_src, const float* sh,
-                                   const float* w, const float* alpha, int n_dst, float* out, cudaStream_t stream) {
+                                   int sh_stride, const float* w, const float* alpha, int n_dst, float* out,
+                                   cudaStream_t stream) {
     if (!x || !row_ptr || !edge_src || !sh || !w || !alpha || !out) return DEDF_ERR_ARG;
+    if (sh_stride != 9 && sh_stride != 12) return DEDF_ERR_ARG;
     if (n_dst <= 0) return DEDF_OK;
     TpReduceArgs a{x, row_ptr, edge_src, sh, w, alpha, out, n_dst};
+    if (sh_stride == 12) {      // bulk-copy (TMA) pipeline: needs 16-byte rows everywhere
+        if (mul1 == 32) return launch_k1_tma<32>(a, stream);
+        if (mul1 == 16) return launch_k1_tma<16>(a, stream);
+        return DEDF_ERR_UNSUPPORTED;
+    }
     if (mul1 == 32) {
         const size_t smem = (size_t)8 * Dtp<32>::FOUT * sizeof(float);
         static bool done = false;

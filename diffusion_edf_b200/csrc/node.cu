@@ -31,6 +31,7 @@ struct NodeLinArgs {
     float* y;                              // (n, Fy)
 };
 
+template <bool kVecW>
 __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a, int lda0, int lda1, int lda2, int ldo) {
     extern __shared__ __align__(16) float smem[];
     constexpr int TN = kNodeTN;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a
             float acc[4][4] = {};
             if (item < I0) {
                 const int cg = item % cg0, rg = item / cg0;
-                gemm_item_4x4<false>(A0, lda0, TN / 4, rg, a.W0, a.out.m0, 4 * cg, a.in.m0, acc);
+                gemm_item_4x4<kVecW>(A0, lda0, TN / 4, rg, a.W0, a.out.m0, 4 * cg, a.in.m0, acc);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a
                     }
             } else if (item < I0 + I1) {
                 const int t = item - I0, cg = t % cg1, rg = t / cg1;
-                gemm_item_4x4<false>(A1, lda1, 3 * TN / 4, rg, a.W1, a.out.m1, 4 * cg, a.in.m1, acc);
+                gemm_item_4x4<kVecW>(A1, lda1, 3 * TN / 4, rg, a.W1, a.out.m1, 4 * cg, a.in.m1, acc);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a
                     }
             } else {
                 const int t = item - I0 - I1, cg = t % cg2, rg = t / cg2;
-                gemm_item_4x4<false>(A2, lda2, 5 * TN / 4, rg, a.W2, a.out.m2, 4 * cg, a.in.m2, acc);
+                gemm_item_4x4<kVecW>(A2, lda2, 5 * TN / 4, rg, a.W2, a.out.m2, 4 * cg, a.in.m2, acc);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -202,13 +203,17 @@ extern "C" int dedf_node_linear(const float* x, int n, const int* irr_in, const 
     const int ldo = a.out.dim() + 1;
     const size_t smem = ((size_t)kNodeTN * lda0 + 3 * kNodeTN * lda1 + 5 * kNodeTN * lda2 + (size_t)kNodeTN * ldo + kNodeTN * 4) * sizeof(float);
     if (smem > 200 * 1024) return DEDF_ERR_UNSUPPORTED;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        cudaFuncSetAttribute(node_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-        attr_smem = 200 * 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(node_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        cudaFuncSetAttribute(node_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        attr_done = true;
     }
     const int n_tiles = (n + kNodeTN - 1) / kNodeTN;
-    node_linear_kernel<<<grid_for(n_tiles, 1, kNumSMs * 4), kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
+    // float4 weight loads need every output multiplicity to be a multiple of 4 (true for all feature irreps)
+    const bool vec = (a.out.m0 % 4 == 0) && (a.out.m1 % 4 == 0) && (a.out.m2 % 4 == 0);
+    if (vec) node_linear_kernel<true><<<grid_for(n_tiles, 1, kNumSMs * 4), kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
+    else node_linear_kernel<false><<<grid_for(n_tiles, 1, kNumSMs * 4), kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

@@ -171,10 +171,12 @@ def segment_softmax_reduce(g: Csr, logits: torch.Tensor, val: torch.Tensor, irr:
 
 def edge_tp_reduce(mul1: int, x: torch.Tensor, row_ptr: torch.Tensor, edge_src: torch.Tensor, sh: torch.Tensor,
                    w: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
-    """K1: out[d] = sum_{e->d} alpha[e, head(u)] * DTP(x[src_e], sh_e, w_e)  -> (N_dst, 49 * mul1)."""
+    """K1: out[d] = sum_{e->d} alpha[e, head(u)] * DTP(x[src_e], sh_e, w_e)  -> (N_dst, 49 * mul1).
+    ``sh`` is (E, 9) (plain-load kernel) or (E, 12) zero-padded rows (TMA bulk-copy pipeline, the fast path)."""
     n_dst = row_ptr.numel() - 1
+    assert sh.shape[1] in (9, 12)
     out = torch.empty(n_dst, 49 * mul1, dtype=torch.float32, device=x.device)
-    _call("dedf_edge_tp_reduce", mul1, ptr(x), ptr(row_ptr, torch.int32), ptr(edge_src, torch.int32), ptr(sh), ptr(w),
+    _call("dedf_edge_tp_reduce", mul1, ptr(x), ptr(row_ptr, torch.int32), ptr(edge_src, torch.int32), ptr(sh), sh.shape[1], ptr(w),
                                        ptr(alpha), n_dst, ptr(out), stream())
     return out
 

@@ -121,9 +121,12 @@ int dedf_segment_softmax_reduce(const int* row_ptr, int n_dst, int n_seg, const 
                                 int m0, int m1, int m2, float* out, cudaStream_t stream);
 
 /* "K1": out[d] = sum_{e -> d} alpha[e, head(u)] * DTP(x[src_e], sh_e, w_e)   (N_dst, 1568 | 784), op-equivalent to
- * scatter(alpha * o3.TensorProduct(x[edge_src], sh, weight), edge_dst) of graph_attention.py:231-232,264-265. */
+ * scatter(alpha * o3.TensorProduct(x[edge_src], sh, weight), edge_dst) of graph_attention.py:231-232,264-265.
+ * sh_stride = 9: packed harmonics, plain loads.  sh_stride = 12: rows padded to 48 bytes, which lets every operand
+ * (weight rows, gathered feature rows, harmonics, alphas) be staged by 1-D TMA bulk copies into a per-warp
+ * shared-memory ring (the fast path). */
 int dedf_edge_tp_reduce(int mul1, const float* x, const int* row_ptr, const int* edge_src, const float* sh,
-                        const float* w, const float* alpha, int n_dst, float* out, cudaStream_t stream);
+                        int sh_stride, const float* w, const float* alpha, int n_dst, float* out, cudaStream_t stream);
 
 /* ---- per-node ---------------------------------------------------------------------------------------- */
 

@@ -158,6 +158,7 @@ def test_graph_attention_pieces(cuda, G):
         attn_ref = ON.heads2vec(OG.scatter_sum(ON.vec2heads(val_ref, oga.irreps_head, 4) * alpha[..., None], ed.long(), n_dst), oga.irreps_head)
     csr = _csr(cuda, row_ptr, es, ed, n_dst)
     p = pga.packed()
+    logit_ref, v_ref, val_ref = logit_ref.contiguous(), v_ref.contiguous(), val_ref.contiguous()
     logits = torch.empty(E, 4, device=cuda)
     v = torch.empty(E, F, device=cuda)
     ops.edge_tp_lin(G, L.EPI_ACT, msg_src.to(cuda), msg_dst.to(cuda), False, csr, sh.to(cuda), w.to(cuda), numel, p["W0"], p["W1"],
@@ -204,8 +205,37 @@ def test_edge_tp_reduce_k1(cuda, G):
         head_cols[sl[io]] = hc
     ref = OG.scatter_sum(d * alpha[:, head_cols], ed.long(), n)
     out = ops.edge_tp_reduce(G, x.to(cuda), row_ptr.to(cuda), es.to(cuda), sh.to(cuda), w.to(cuda), alpha.to(cuda))
-    assert_close(out, ref, TOL, "K1")
+    assert_close(out, ref, TOL, "K1 (plain loads)")
     assert float(out[0].abs().max()) == 0.0
+    # TMA bulk-copy pipeline: harmonics rows padded to 12 floats
+    sh12 = torch.zeros(E, 12)
+    sh12[:, :9] = sh
+    out2 = ops.edge_tp_reduce(G, x.to(cuda), row_ptr.to(cuda), es.to(cuda), sh12.to(cuda), w.to(cuda), alpha.to(cuda))
+    assert_close(out2, ref, TOL, "K1 (TMA pipeline)")
+    assert float(out2[0].abs().max()) == 0.0
+
+
+def test_edge_tp_reduce_k1_large_regular(cuda):
+    """C4-shaped instance (degree 32, 20k nodes): the two K1 variants agree, and a linearity property holds
+    (out(w1 + w2) = out(w1) + out(w2)) -- size-independent checks where the oracle would be slow."""
+    from diffusion_edf_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    N, deg = 20_000, 32
+    E = N * deg
+    row_ptr = (torch.arange(N + 1) * deg).int().to(cuda)
+    es = torch.randint(0, N, (E,), generator=g, dtype=torch.int32).to(cuda)
+    x = torch.randn(N, 240, generator=g).to(cuda)
+    sh12 = torch.zeros(E, 12)
+    sh12[:, :9] = so3.spherical_harmonics(2, torch.randn(E, 3, generator=g))
+    sh12 = sh12.to(cuda)
+    w1, w2 = torch.randn(E, 480, generator=g).to(cuda), torch.randn(E, 480, generator=g).to(cuda)
+    alpha = torch.rand(E, 4, generator=g).to(cuda)
+    a = ops.edge_tp_reduce(32, x, row_ptr, es, sh12, w1, alpha)
+    b = ops.edge_tp_reduce(32, x, row_ptr, es, sh12[:, :9].contiguous(), w1, alpha)
+    assert_close(a, b, 1e-5, "TMA vs plain")
+    c = ops.edge_tp_reduce(32, x, row_ptr, es, sh12, w2, alpha)
+    d = ops.edge_tp_reduce(32, x, row_ptr, es, sh12, w1 + w2, alpha)
+    assert_close(d, a + c, 1e-5, "linearity in the weights")
 
 
 # --------------------------------------------------------------------------- node kernels
