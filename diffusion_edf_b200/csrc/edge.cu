@@ -750,6 +750,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -762,7 +772,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-constexpr int kK1Warps = 8;
+constexpr int kK1Warps = 10;
 constexpr int kK1Stages = 3;
 constexpr int kK1TaskD = 16;      // destinations per warp task (row pointers live in lanes 0..16)
 
@@ -773,7 +783,7 @@ struct K1Stage {
     static constexpr int W_OFF = 0, X_OFF = P * D::NUMEL, SH_OFF = X_OFF + P * D::F, AL_OFF = SH_OFF + P * 12;
     static constexpr int FLOATS = AL_OFF + P * 4;
     static constexpr int EDGE_BYTES = (D::NUMEL + D::F + 12 + 4) * 4;
-    static constexpr int WARP_FLOATS = kK1Stages * FLOATS + D::FOUT;
+    static constexpr int WARP_FLOATS = kK1Stages * FLOATS;
 };
 
 template <int G>
@@ -786,7 +796,9 @@ __global__ void __launch_bounds__(kK1Warps * 32, 1) edge_tp_reduce_tma_kernel(Tp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * S;                 // [warps][S]
     float* base = smem + (kK1Warps * S * 2 + 31) / 32 * 32 + (size_t)warp * ST::WARP_FLOATS;
-    float* outst = base + S * ST::FLOATS;
+    // streamed operands (weights / harmonics / alphas) are read once: evict-first, so that the gathered feature
+    // table (evict-last) stays resident in the 126 MB L2 across the launch
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < S; ++s) mbar_init(bars + s, 1);
@@ -833,12 +845,12 @@ __global__ void __launch_bounds__(kK1Warps * 32, 1) edge_tp_reduce_tma_kernel(Tp
                 float* st = base + stage * ST::FLOATS;
                 uint64_t* bar = bars + stage;
                 mbar_expect_tx(bar, (uint32_t)(nv * ST::EDGE_BYTES));
-                bulk_g2s(st + ST::W_OFF, a.w + (size_t)ppe * D::NUMEL, (uint32_t)(nv * D::NUMEL * 4), bar);
+                bulk_g2s_hint(st + ST::W_OFF, a.w + (size_t)ppe * D::NUMEL, (uint32_t)(nv * D::NUMEL * 4), bar, pol_stream);
 #pragma unroll
                 for (int i = 0; i < P; ++i)
-                    if (i < nv) bulk_g2s(st + ST::X_OFF + i * D::F, a.x + (size_t)srcs[i] * D::F, (uint32_t)(D::F * 4), bar);
-                bulk_g2s(st + ST::SH_OFF, a.sh + (size_t)ppe * 12, (uint32_t)(nv * 48), bar);
-                bulk_g2s(st + ST::AL_OFF, a.alpha + (size_t)ppe * 4, (uint32_t)(nv * 16), bar);
+                    if (i < nv) bulk_g2s_hint(st + ST::X_OFF + i * D::F, a.x + (size_t)srcs[i] * D::F, (uint32_t)(D::F * 4), bar, pol_keep);
+                bulk_g2s_hint(st + ST::SH_OFF, a.sh + (size_t)ppe * 12, (uint32_t)(nv * 48), bar, pol_stream);
+                bulk_g2s_hint(st + ST::AL_OFF, a.alpha + (size_t)ppe * 4, (uint32_t)(nv * 16), bar, pol_stream);
             }
             ppe += P;
             if (ppe >= pee) {
@@ -941,50 +953,49 @@ __global__ void __launch_bounds__(kK1Warps * 32, 1) edge_tp_reduce_tma_kernel(Tp
                 for (int k = 0; k < 22; ++k) { acc2[k] += __shfl_xor_sync(0xffffffffu, acc2[k], 8); acc2[k] += __shfl_xor_sync(0xffffffffu, acc2[k], 16); }
             }
             constexpr int B1 = D::D0, B2 = D::D0 + 3 * D::D1;
-            __syncwarp();
+            // every lane owns whole (channel, m) groups of the row: 4-byte streaming stores, merged into full sectors in L2
+            float* outst = a.out + (size_t)(d0 + cd) * D::FOUT;
+#define OUTST(i, v) __stcs(outst + (i), (v))
 #pragma unroll
             for (int s = 0; s < S0; ++s) {
                 const int ch = lane + 32 * s;
-                outst[D::C0_K0 + ch] = acc0[s][0];
+                OUTST(D::C0_K0 + ch, acc0[s][0]);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) outst[B1 + (D::C1_K1 + ch) * 3 + k] = acc0[s][1 + k];
+                for (int k = 0; k < 3; ++k) OUTST(B1 + (D::C1_K1 + ch) * 3 + k, acc0[s][1 + k]);
 #pragma unroll
-                for (int k = 0; k < 5; ++k) outst[B2 + (D::C2_K2 + ch) * 5 + k] = acc0[s][4 + k];
+                for (int k = 0; k < 5; ++k) OUTST(B2 + (D::C2_K2 + ch) * 5 + k, acc0[s][4 + k]);
             }
             if (lane < D::M1) {
                 const int ch = lane;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    outst[B1 + (D::C1_K3 + ch) * 3 + k] = acc1[0][k];
-                    outst[B1 + (D::C1_K5 + ch) * 3 + k] = acc1[0][4 + k];
-                    outst[B1 + (D::C1_K7 + ch) * 3 + k] = acc1[0][12 + k];
+                    OUTST(B1 + (D::C1_K3 + ch) * 3 + k, acc1[0][k]);
+                    OUTST(B1 + (D::C1_K5 + ch) * 3 + k, acc1[0][4 + k]);
+                    OUTST(B1 + (D::C1_K7 + ch) * 3 + k, acc1[0][12 + k]);
                 }
-                outst[D::C0_K4 + ch] = acc1[0][3];
+                OUTST(D::C0_K4 + ch, acc1[0][3]);
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
-                    outst[B2 + (D::C2_K6 + ch) * 5 + k] = acc1[0][7 + k];
-                    outst[B2 + (D::C2_K8 + ch) * 5 + k] = acc1[0][15 + k];
+                    OUTST(B2 + (D::C2_K6 + ch) * 5 + k, acc1[0][7 + k]);
+                    OUTST(B2 + (D::C2_K8 + ch) * 5 + k, acc1[0][15 + k]);
                 }
             }
             if (lane < D::M2) {
                 const int ch = lane;
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
-                    outst[B2 + (D::C2_K9 + ch) * 5 + k] = acc2[k];
-                    outst[B2 + (D::C2_K11 + ch) * 5 + k] = acc2[8 + k];
-                    outst[B2 + (D::C2_K14 + ch) * 5 + k] = acc2[17 + k];
+                    OUTST(B2 + (D::C2_K9 + ch) * 5 + k, acc2[k]);
+                    OUTST(B2 + (D::C2_K11 + ch) * 5 + k, acc2[8 + k]);
+                    OUTST(B2 + (D::C2_K14 + ch) * 5 + k, acc2[17 + k]);
                 }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    outst[B1 + (D::C1_K10 + ch) * 3 + k] = acc2[5 + k];
-                    outst[B1 + (D::C1_K13 + ch) * 3 + k] = acc2[14 + k];
+                    OUTST(B1 + (D::C1_K10 + ch) * 3 + k, acc2[5 + k]);
+                    OUTST(B1 + (D::C1_K13 + ch) * 3 + k, acc2[14 + k]);
                 }
-                outst[D::C0_K12 + ch] = acc2[13];
+                OUTST(D::C0_K12 + ch, acc2[13]);
             }
-            __syncwarp();
-            float4* dst = reinterpret_cast<float4*>(a.out + (size_t)(d0 + cd) * D::FOUT);
-            const float4* srcv = reinterpret_cast<const float4*>(outst);
-            for (int i = lane; i < D::FOUT / 4; i += 32) dst[i] = srcv[i];
+#undef OUTST
         }
     }
 }

@@ -3,7 +3,8 @@
 // A lives in shared memory, row-major [rows][lda] (K contiguous, lda % 4 == 0 and
 // lda % 32 == 4 or 20 so that consecutive row-groups hit distinct banks); W lives
 // in global memory, row-major [K][N] ("in x out"), read through L1 (every CTA
-// reads the same few weight matrices).  One work item = 4 rows x 4 columns; the 4
+// reads the same few weight matrices), or in shared memory (kWShared) when the
+// caller staged the whole matrix there to take L2 latency off the K loop.  One work item = 4 rows x 4 columns; the 4
 // rows of item (rg, cg) are rg, rg+n_rg, rg+2 n_rg, rg+3 n_rg.
 //
 // fp32 FMA is used on purpose: the reference is an fp32 network checked to 1e-4
@@ -15,7 +16,7 @@
 namespace dedf {
 
 // acc[i][j] += sum_k A[row_i][k] * W[k][col0 + j]     (K % 4 == 0, N % 4 == 0)
-template <bool kVecW>
+template <bool kVecW, bool kWShared = false>
 __device__ __forceinline__ void gemm_item_4x4(const float* __restrict__ A, int lda, int n_rg, int rg,
                                               const float* __restrict__ W, int N, int col0, int K,
                                               float acc[4][4]) {
@@ -34,11 +35,12 @@ __device__ __forceinline__ void gemm_item_4x4(const float* __restrict__ A, int l
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             if (kVecW) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(W + (size_t)(k + kk) * N + col0));
+                const float4 t = kWShared ? *reinterpret_cast<const float4*>(W + (size_t)(k + kk) * N + col0)
+                                          : __ldg(reinterpret_cast<const float4*>(W + (size_t)(k + kk) * N + col0));
                 w[kk][0] = t.x; w[kk][1] = t.y; w[kk][2] = t.z; w[kk][3] = t.w;
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) w[kk][j] = (col0 + j < N) ? __ldg(W + (size_t)(k + kk) * N + col0 + j) : 0.f;
+                for (int j = 0; j < 4; ++j) w[kk][j] = (col0 + j < N) ? (kWShared ? W[(size_t)(k + kk) * N + col0 + j] : __ldg(W + (size_t)(k + kk) * N + col0 + j)) : 0.f;
             }
         }
         const float xa[4][4] = {{x0.x, x0.y, x0.z, x0.w}, {x1.x, x1.y, x1.z, x1.w}, {x2.x, x2.y, x2.z, x2.w}, {x3.x, x3.y, x3.z, x3.w}};
@@ -53,7 +55,7 @@ __device__ __forceinline__ void gemm_item_4x4(const float* __restrict__ A, int l
         const float xa[4] = {a0[k], a1[k], a2[k], a3[k]};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float wv = (col0 + j < N) ? __ldg(W + (size_t)k * N + col0 + j) : 0.f;
+            const float wv = (col0 + j < N) ? (kWShared ? W[(size_t)k * N + col0 + j] : __ldg(W + (size_t)k * N + col0 + j)) : 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[i][j] = fmaf(xa[i], wv, acc[i][j]);
         }

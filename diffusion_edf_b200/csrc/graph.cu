@@ -28,50 +28,54 @@ __device__ __forceinline__ void argmax_pair(float& v, int& i, float ov, int oi) 
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
 }
 
+// Per iteration: every thread updates its PT points (10 FP instructions each: the exact, unfused squared distance, a min and
+// a max), the block arg-max is two REDUX pairs (max of the distance bits, then min index among the holders of the max) around
+// ONE barrier, and the winner's coordinates are read back from a shared-memory copy of the cloud (no global load, no second
+// barrier on the critical path).
 template <int PT>
 __global__ void __launch_bounds__(kFpsThreads, 1)
 fps_kernel(const float* __restrict__ x, int n, int m, int start, int idx_base, long long* __restrict__ out_idx) {
-    __shared__ float s_val[2][32];
+    extern __shared__ float s_pts[];            // [3 n] copy of the cloud for the winner broadcast
+    __shared__ unsigned s_val[2][32];
     __shared__ int s_idx[2][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 3 * n; i += kFpsThreads) s_pts[i] = x[i];
     float px[PT], py[PT], pz[PT], dist[PT];
 #pragma unroll
     for (int j = 0; j < PT; ++j) {
-        int i = tid + j * kFpsThreads;
+        const int i = tid + j * kFpsThreads;
         if (i < n) { px[j] = x[3 * i]; py[j] = x[3 * i + 1]; pz[j] = x[3 * i + 2]; dist[j] = __int_as_float(0x7f800000); }
-        else       { px[j] = py[j] = pz[j] = 0.f; dist[j] = -1.0f; }   // never selected
+        else       { px[j] = py[j] = pz[j] = 0.f; dist[j] = 0.f; }      // padding: never beats a real point (ties -> lowest index)
     }
+    __syncthreads();
     int cur = start;
     for (int it = 0; it < m; ++it) {
         if (tid == 0) out_idx[it] = (long long)(cur + idx_base);
-        const float cx = __ldg(x + 3 * cur), cy = __ldg(x + 3 * cur + 1), cz = __ldg(x + 3 * cur + 2);
-        float bv = -2.0f; int bi = 0x7fffffff;
+        const float cx = s_pts[3 * cur], cy = s_pts[3 * cur + 1], cz = s_pts[3 * cur + 2];
+        float bv = 0.f;
 #pragma unroll
         for (int j = 0; j < PT; ++j) {
-            int i = tid + j * kFpsThreads;
-            if (i < n) {
-                float d = sqdist_exact(px[j], py[j], pz[j], cx, cy, cz);
+            if (tid + j * kFpsThreads < n) {
+                const float d = sqdist_exact(px[j], py[j], pz[j], cx, cy, cz);
                 dist[j] = fminf(dist[j], d);
-                argmax_pair(bv, bi, dist[j], i);
             }
+            bv = fmaxf(bv, dist[j]);
         }
+        // distances are >= 0, so their bit patterns order like unsigned integers
+        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(bv));
+        int cand = 0x7fffffff;
+        if (__float_as_uint(bv) == wm) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            argmax_pair(bv, bi, ov, oi);
+            for (int j = PT - 1; j >= 0; --j)
+                if (__float_as_uint(dist[j]) == wm) cand = tid + j * kFpsThreads;   // lowest index among this thread's ties
         }
+        const int wi = __reduce_min_sync(0xffffffffu, cand);
         const int buf = it & 1;
-        if (lane == 0) { s_val[buf][warp] = bv; s_idx[buf][warp] = bi; }
+        if (lane == 0) { s_val[buf][warp] = wm; s_idx[buf][warp] = wi; }
         __syncthreads();
-        bv = s_val[buf][lane]; bi = s_idx[buf][lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            argmax_pair(bv, bi, ov, oi);
-        }
-        cur = bi;
+        const unsigned v = s_val[buf][lane];
+        const unsigned gm = __reduce_max_sync(0xffffffffu, v);
+        cur = __reduce_min_sync(0xffffffffu, (v == gm) ? s_idx[buf][lane] : 0x7fffffff);
     }
 }
 
@@ -212,12 +216,22 @@ extern "C" int dedf_fps(const float* x, int n, int m, int start, int idx_base, l
                         float* scratch_dist, cudaStream_t stream) {
     if (!x || !out_idx || n <= 0 || m <= 0 || m > n || start < 0 || start >= n) return DEDF_ERR_ARG;
     const int pt = (n + kFpsThreads - 1) / kFpsThreads;
-    if (pt <= 1) fps_kernel<1><<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx);
-    else if (pt <= 2) fps_kernel<2><<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx);
-    else if (pt <= 4) fps_kernel<4><<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx);
-    else if (pt <= 8) fps_kernel<8><<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx);
-    else if (pt <= 12) fps_kernel<12><<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx);
-    else if (pt <= 16) fps_kernel<16><<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx);
+    const size_t smem = (size_t)3 * n * sizeof(float);
+#define DEDF_FPS_CASE(PT)                                                                                          \
+    {                                                                                                              \
+        static bool done = false;                                                                                  \
+        if (!done) { cudaFuncSetAttribute(fps_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done = true; } \
+        fps_kernel<PT><<<1, kFpsThreads, smem, stream>>>(x, n, m, start, idx_base, out_idx);                       \
+    }
+    if (pt <= 1) DEDF_FPS_CASE(1)
+    else if (pt <= 2) DEDF_FPS_CASE(2)
+    else if (pt <= 4) DEDF_FPS_CASE(4)
+    else if (pt <= 6) DEDF_FPS_CASE(6)
+    else if (pt <= 8) DEDF_FPS_CASE(8)
+    else if (pt <= 10) DEDF_FPS_CASE(10)
+    else if (pt <= 12) DEDF_FPS_CASE(12)
+    else if (pt <= 16) DEDF_FPS_CASE(16)
+#undef DEDF_FPS_CASE
     else {
         if (!scratch_dist) return DEDF_ERR_ARG;
         fps_kernel_large<<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx, scratch_dist);

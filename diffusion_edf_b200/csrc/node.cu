@@ -31,7 +31,7 @@ struct NodeLinArgs {
     float* y;                              // (n, Fy)
 };
 
-template <bool kVecW>
+template <bool kVecW, bool kWShared>
 __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a, int lda0, int lda1, int lda2, int ldo) {
     extern __shared__ __align__(16) float smem[];
     constexpr int TN = kNodeTN;
@@ -43,6 +43,20 @@ __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a
     float* s_scale = O + TN * ldo;          // [TN][3]    layer-norm scale per l
     float* s_mean = s_scale + TN * 3;       // [TN]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Stage the weight matrices in shared memory once per CTA (they are reused by every tile): the K loop then runs at
+    // shared-memory latency instead of L2 latency, which is what bounds the small (few-tile) launches of the coarse scales.
+    const float* W0 = a.W0; const float* W1 = a.W1; const float* W2 = a.W2;
+    if (kWShared) {
+        float* sW = s_mean + ((TN + 3) & ~3);
+        const int n0w = a.W0 ? a.in.m0 * a.out.m0 : 0, n1w = a.W1 ? a.in.m1 * a.out.m1 : 0, n2w = a.W2 ? a.in.m2 * a.out.m2 : 0;
+        const int o1 = (n0w + 3) & ~3, o2 = o1 + ((n1w + 3) & ~3);
+        for (int i = tid; i < n0w; i += kNodeThreads) sW[i] = __ldg(a.W0 + i);
+        for (int i = tid; i < n1w; i += kNodeThreads) sW[o1 + i] = __ldg(a.W1 + i);
+        for (int i = tid; i < n2w; i += kNodeThreads) sW[o2 + i] = __ldg(a.W2 + i);
+        if (a.W0) W0 = sW;
+        if (a.W1) W1 = sW + o1;
+        if (a.W2) W2 = sW + o2;
+    }
     const int n_tiles = (a.n + TN - 1) / TN;
     const int Fy = a.gate ? (Fout - a.out.m1 - a.out.m2) : Fout;
     const int m0s = a.gate ? (a.out.m0 - a.out.m1 - a.out.m2) : a.out.m0;   // scalars that survive the gate
@@ -106,7 +120,7 @@ __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a
             float acc[4][4] = {};
             if (item < I0) {
                 const int cg = item % cg0, rg = item / cg0;
-                gemm_item_4x4<kVecW>(A0, lda0, TN / 4, rg, a.W0, a.out.m0, 4 * cg, a.in.m0, acc);
+                gemm_item_4x4<kVecW, kWShared>(A0, lda0, TN / 4, rg, W0, a.out.m0, 4 * cg, a.in.m0, acc);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -116,7 +130,7 @@ __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a
                     }
             } else if (item < I0 + I1) {
                 const int t = item - I0, cg = t % cg1, rg = t / cg1;
-                gemm_item_4x4<kVecW>(A1, lda1, 3 * TN / 4, rg, a.W1, a.out.m1, 4 * cg, a.in.m1, acc);
+                gemm_item_4x4<kVecW, kWShared>(A1, lda1, 3 * TN / 4, rg, W1, a.out.m1, 4 * cg, a.in.m1, acc);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -126,7 +140,7 @@ __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a
                     }
             } else {
                 const int t = item - I0 - I1, cg = t % cg2, rg = t / cg2;
-                gemm_item_4x4<kVecW>(A2, lda2, 5 * TN / 4, rg, a.W2, a.out.m2, 4 * cg, a.in.m2, acc);
+                gemm_item_4x4<kVecW, kWShared>(A2, lda2, 5 * TN / 4, rg, W2, a.out.m2, 4 * cg, a.in.m2, acc);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -201,19 +215,29 @@ extern "C" int dedf_node_linear(const float* x, int n, const int* irr_in, const 
     if (n <= 0) return DEDF_OK;
     const int lda0 = pad_lda(a.in.m0), lda1 = pad_lda(a.in.m1), lda2 = pad_lda(a.in.m2);
     const int ldo = a.out.dim() + 1;
-    const size_t smem = ((size_t)kNodeTN * lda0 + 3 * kNodeTN * lda1 + 5 * kNodeTN * lda2 + (size_t)kNodeTN * ldo + kNodeTN * 4) * sizeof(float);
-    if (smem > 200 * 1024) return DEDF_ERR_UNSUPPORTED;
+    const size_t base_floats = (size_t)kNodeTN * lda0 + 3 * kNodeTN * lda1 + 5 * kNodeTN * lda2 + (size_t)kNodeTN * ldo + kNodeTN * 3 + ((kNodeTN + 3) & ~3);
+    const size_t w_floats = (size_t)((a.W0 ? a.in.m0 * a.out.m0 : 0) + 3) / 4 * 4 + (size_t)((a.W1 ? a.in.m1 * a.out.m1 : 0) + 3) / 4 * 4 +
+                            (size_t)((a.W2 ? a.in.m2 * a.out.m2 : 0) + 3) / 4 * 4;
+    constexpr size_t kMaxSmem = 220 * 1024;
+    const bool wshared = (base_floats + w_floats) * sizeof(float) <= kMaxSmem;
+    const size_t smem = (base_floats + (wshared ? w_floats : 0)) * sizeof(float);
+    if (smem > kMaxSmem) return DEDF_ERR_UNSUPPORTED;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(node_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-        cudaFuncSetAttribute(node_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        cudaFuncSetAttribute(node_linear_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        cudaFuncSetAttribute(node_linear_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        cudaFuncSetAttribute(node_linear_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        cudaFuncSetAttribute(node_linear_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
         attr_done = true;
     }
     const int n_tiles = (n + kNodeTN - 1) / kNodeTN;
     // float4 weight loads need every output multiplicity to be a multiple of 4 (true for all feature irreps)
     const bool vec = (a.out.m0 % 4 == 0) && (a.out.m1 % 4 == 0) && (a.out.m2 % 4 == 0);
-    if (vec) node_linear_kernel<true><<<grid_for(n_tiles, 1, kNumSMs * 4), kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
-    else node_linear_kernel<false><<<grid_for(n_tiles, 1, kNumSMs * 4), kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
+    const int grid = grid_for(n_tiles, 1, kNumSMs * 2);
+    if (vec && wshared) node_linear_kernel<true, true><<<grid, kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
+    else if (vec) node_linear_kernel<true, false><<<grid, kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
+    else if (wshared) node_linear_kernel<false, true><<<grid, kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
+    else node_linear_kernel<false, false><<<grid, kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
