@@ -261,18 +261,22 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms, e2e_ms = tms.tolist()
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-    # ---------------- rank 0 only: per-entry-point breakdown of one more set of steps, K1 roofline, CPU baseline
+    # ---------------- per-entry-point breakdown of a few more steps (all ranks take part: the step holds a collective)
+    model.use_cuda_graph = False                      # the breakdown needs the individual launches
+    step(d)
     ops.PROFILE = {}
-    for _ in range(min(5, args.steps)):
+    n_prof = min(5, args.steps)
+    for _ in range(n_prof):
         step(d)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
-    n_prof = min(5, args.steps)
+    model.use_cuda_graph = True
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    # ---------------- rank 0 only from here: K1 roofline, CPU baseline
     breakdown = {k: {"ms_per_step": sum(a.elapsed_time(bb) for a, bb in v) / n_prof, "calls_per_step": len(v) / n_prof} for k, v in prof.items()}
     total_k = sum(v["ms_per_step"] for v in breakdown.values())
     for v in breakdown.values():
@@ -303,15 +307,13 @@ def run_cuda(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "poses_per_gpu": N_POSES, "scene_points": N_POINTS, "weights": "random init, seed 0",
                    "parallelism": f"pose-sharded x{world}; rank 0 encodes the scene, 1 NCCL broadcast of the packed field per step" if world > 1 else "single GPU",
-                   "l2": "flushed between timed steps (256 MB fill)", "timing": "CUDA events per step, max over ranks"},
+                   "l2": "flushed between timed steps (256 MB fill)", "timing": "CUDA events per step, max over ranks",
+                   "execution": "whole forward replayed as one CUDA graph (graphs.py); step_breakdown measured eagerly"},
         "e2e": {"value": world * N_POSES / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "timing": "wall clock incl. pinned H2D of scene+poses and D2H of the scores"},
         "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
         "clocks": clocks, "roofline": roof, "step_breakdown": breakdown, "cpu_baseline": cpu,
     }))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 def main():

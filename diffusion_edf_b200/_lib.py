@@ -53,8 +53,8 @@ class TimeDesc(C.Structure):
 
 
 _PROTOS = {
-    "dedf_fps": [c_fp, c_int, c_int, c_int, c_int, c_fp, c_fp, c_fp],
-    "dedf_radius_count": [c_fp, c_fp, c_int, c_int, C.POINTER(c_int), C.POINTER(c_f), c_fp, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_fp],
+    "dedf_fps": [c_fp, c_int, c_int, c_int, c_fp, c_int, c_fp, c_fp, c_fp],
+    "dedf_radius_count": [c_fp, c_fp, c_int, c_int, C.POINTER(c_int), C.POINTER(c_f), c_fp, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_int, c_fp, c_fp, c_fp],
     "dedf_radius_fill": [c_fp, c_fp, c_int, c_int, C.POINTER(c_int), C.POINTER(c_f), c_fp, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_fp, c_fp],
     "dedf_edge_geom": [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, C.POINTER(c_int), C.POINTER(c_f), c_f, c_f, c_fp, c_fp, c_fp, c_fp],
     "dedf_edge_mlp": [C.POINTER(MlpDesc), c_int, c_fp],
@@ -68,7 +68,8 @@ _PROTOS = {
     "dedf_query_transform": [c_fp, c_int, c_fp, c_fp, c_int, C.POINTER(c_int), c_fp, c_fp, c_fp],
     "dedf_score_tp": [c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_int, C.POINTER(c_int), C.POINTER(c_fp), C.POINTER(c_fp),
                       C.POINTER(c_fp), C.POINTER(c_fp), c_int, c_f, c_fp, c_fp, c_fp],
-    "dedf_pose_update": [c_fp, c_int, c_fp, c_fp, c_fp, c_ull, c_ull, c_d, c_d, c_d, c_d, c_d, c_d, c_fp, c_fp, c_fp],
+    "dedf_pose_update": [c_fp, c_int, c_fp, c_fp, c_fp, c_ull, c_ull, c_d, c_d, c_d, c_d, c_d, c_d, c_fp, c_fp, c_fp, c_fp, c_fp],
+    "dedf_sample_advance": [c_fp, c_int, c_fp, c_fp, c_fp, c_fp],
     "dedf_build_arch": [],
 }
 

@@ -34,7 +34,8 @@ __device__ __forceinline__ void argmax_pair(float& v, int& i, float ov, int oi) 
 // barrier on the critical path).
 template <int PT>
 __global__ void __launch_bounds__(kFpsThreads, 1)
-fps_kernel(const float* __restrict__ x, int n, int m, int start, int idx_base, long long* __restrict__ out_idx) {
+fps_kernel(const float* __restrict__ x, int n, int m, int start, const long long* __restrict__ start_dev, int idx_base,
+           long long* __restrict__ out_idx) {
     extern __shared__ float s_pts[];            // [3 n] copy of the cloud for the winner broadcast
     __shared__ unsigned s_val[2][32];
     __shared__ int s_idx[2][32];
@@ -48,7 +49,7 @@ fps_kernel(const float* __restrict__ x, int n, int m, int start, int idx_base, l
         else       { px[j] = py[j] = pz[j] = 0.f; dist[j] = 0.f; }      // padding: never beats a real point (ties -> lowest index)
     }
     __syncthreads();
-    int cur = start;
+    int cur = start_dev ? (int)min(max(start_dev[0], 0ll), (long long)(n - 1)) : start;
     for (int it = 0; it < m; ++it) {
         if (tid == 0) out_idx[it] = (long long)(cur + idx_base);
         const float cx = s_pts[3 * cur], cy = s_pts[3 * cur + 1], cz = s_pts[3 * cur + 2];
@@ -81,14 +82,14 @@ fps_kernel(const float* __restrict__ x, int n, int m, int start, int idx_base, l
 
 // fallback for very large clouds: running distances in global scratch
 __global__ void __launch_bounds__(kFpsThreads, 1)
-fps_kernel_large(const float* __restrict__ x, int n, int m, int start, int idx_base, long long* __restrict__ out_idx,
-                 float* __restrict__ dist) {
+fps_kernel_large(const float* __restrict__ x, int n, int m, int start, const long long* __restrict__ start_dev, int idx_base,
+                 long long* __restrict__ out_idx, float* __restrict__ dist) {
     __shared__ float s_val[2][32];
     __shared__ int s_idx[2][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < n; i += kFpsThreads) dist[i] = __int_as_float(0x7f800000);
     __syncthreads();
-    int cur = start;
+    int cur = start_dev ? (int)min(max(start_dev[0], 0ll), (long long)(n - 1)) : start;
     for (int it = 0; it < m; ++it) {
         if (tid == 0) out_idx[it] = (long long)(cur + idx_base);
         const float cx = __ldg(x + 3 * cur), cy = __ldg(x + 3 * cur + 1), cz = __ldg(x + 3 * cur + 2);
@@ -156,8 +157,8 @@ radius_kernel(RadiusArgs a, int* __restrict__ counts, const int* __restrict__ ro
         // ``max_nb`` caps the hits INCLUDING excluded ones (torch_cluster truncates first, the
         // reference filters self pairs afterwards: connectivity.py:68-70, radius_graph's +1).
         int cnt_all = 0, cnt_keep = 0;
-        int base = 0;
-        if (FILL) base = row_ptr[item];
+        int base = 0, seg_end = 0x7fffffff;
+        if (FILL) { base = row_ptr[item]; seg_end = row_ptr[item + 1]; }
         for (int c = s0; c < s1 && cnt_all < a.max_nb; c += 32) {
             const int i = c + lane;
             bool hit = false, excluded = false;
@@ -175,8 +176,10 @@ radius_kernel(RadiusArgs a, int* __restrict__ counts, const int* __restrict__ ro
             const unsigned bal_keep = __ballot_sync(0xffffffffu, keep);
             if (FILL && keep) {
                 const int pos = base + cnt_keep + __popc(bal_keep & lt);
-                edge_src[pos] = i;                  // flat index into the concatenated clouds
-                edge_dst[pos] = d;
+                if (pos < seg_end) {
+                    edge_src[pos] = i;              // flat index into the concatenated clouds
+                    edge_dst[pos] = d;
+                }
             }
             cnt_all += __popc(bal_all);
             cnt_keep += __popc(bal_keep);
@@ -187,7 +190,8 @@ radius_kernel(RadiusArgs a, int* __restrict__ counts, const int* __restrict__ ro
 
 // single-CTA exclusive scan: row_ptr[0..n] from counts[0..n-1]
 __global__ void __launch_bounds__(1024, 1)
-exclusive_scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ row_ptr) {
+exclusive_scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ row_ptr, int capacity,
+                      int* __restrict__ n_edges_out, int* __restrict__ overflow) {
     __shared__ int s_part[1024];
     const int tid = threadIdx.x;
     const int chunk = (n + 1023) / 1024;
@@ -203,16 +207,24 @@ exclusive_scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ r
         s_part[tid] += v;
         __syncthreads();
     }
+    // capacity > 0: the edge buffers were sized ahead of time (CUDA-graph replay); clamp the CSR so that no consumer can
+    // index past them and raise the overflow flag -- the host then re-plans with larger buffers.
+    const int cap = capacity > 0 ? capacity : 0x7fffffff;
     int run = s_part[tid] - sum;
-    for (int i = lo; i < hi; ++i) { row_ptr[i] = run; run += counts[i]; }
-    if (tid == 1023) row_ptr[n] = s_part[1023];
+    for (int i = lo; i < hi; ++i) { row_ptr[i] = min(run, cap); run += counts[i]; }
+    if (tid == 1023) {
+        const int total = s_part[1023];
+        row_ptr[n] = min(total, cap);
+        if (n_edges_out) *n_edges_out = min(total, cap);
+        if (overflow && total > cap) atomicOr(overflow, 1);
+    }
 }
 
 }  // namespace dedf
 
 using namespace dedf;
 
-extern "C" int dedf_fps(const float* x, int n, int m, int start, int idx_base, long long* out_idx,
+extern "C" int dedf_fps(const float* x, int n, int m, int start, const long long* start_dev, int idx_base, long long* out_idx,
                         float* scratch_dist, cudaStream_t stream) {
     if (!x || !out_idx || n <= 0 || m <= 0 || m > n || start < 0 || start >= n) return DEDF_ERR_ARG;
     const int pt = (n + kFpsThreads - 1) / kFpsThreads;
@@ -221,7 +233,7 @@ extern "C" int dedf_fps(const float* x, int n, int m, int start, int idx_base, l
     {                                                                                                              \
         static bool done = false;                                                                                  \
         if (!done) { cudaFuncSetAttribute(fps_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done = true; } \
-        fps_kernel<PT><<<1, kFpsThreads, smem, stream>>>(x, n, m, start, idx_base, out_idx);                       \
+        fps_kernel<PT><<<1, kFpsThreads, smem, stream>>>(x, n, m, start, start_dev, idx_base, out_idx);                       \
     }
     if (pt <= 1) DEDF_FPS_CASE(1)
     else if (pt <= 2) DEDF_FPS_CASE(2)
@@ -234,7 +246,7 @@ extern "C" int dedf_fps(const float* x, int n, int m, int start, int idx_base, l
 #undef DEDF_FPS_CASE
     else {
         if (!scratch_dist) return DEDF_ERR_ARG;
-        fps_kernel_large<<<1, kFpsThreads, 0, stream>>>(x, n, m, start, idx_base, out_idx, scratch_dist);
+        fps_kernel_large<<<1, kFpsThreads, 0, stream>>>(x, n, m, start, start_dev, idx_base, out_idx, scratch_dist);
     }
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
@@ -257,7 +269,8 @@ static int fill_radius_args(RadiusArgs& a, const float* x_src, const float* x_ds
 
 extern "C" int dedf_radius_count(const float* x_src, const float* x_dst, int n_dst, int n_scales, const int* src_off,
                                  const float* r, const long long* b_src, const long long* b_dst, int excl_mode,
-                                 const long long* excl, int max_nb, int* counts, int* row_ptr, cudaStream_t stream) {
+                                 const long long* excl, int max_nb, int* counts, int* row_ptr, int capacity, int* n_edges_out,
+                                 int* overflow, cudaStream_t stream) {
     RadiusArgs a;
     int rc = fill_radius_args(a, x_src, x_dst, n_dst, n_scales, src_off, r, b_src, b_dst, excl_mode, excl, max_nb);
     if (rc) return rc;
@@ -267,7 +280,7 @@ extern "C" int dedf_radius_count(const float* x_src, const float* x_dst, int n_d
         radius_kernel<false><<<grid_for(items, 8, kNumSMs * 8), 256, 0, stream>>>(a, counts, nullptr, nullptr, nullptr);
         DEDF_CHECK_LAUNCH();
     }
-    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(counts, (int)items, row_ptr);
+    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(counts, (int)items, row_ptr, capacity, n_edges_out, overflow);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

@@ -313,6 +313,24 @@ __global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
 // ---------------------------------------------------------------------------
 // pose update (float64)
 // ---------------------------------------------------------------------------
+// Device-resident schedule of a denoise loop: one row per step, advanced by sample_advance_kernel so that a whole step
+// (score head + pose update) can be replayed as a CUDA graph without host-side parameters.
+//   row = [t, alpha_ang, alpha_lin, temperature]
+struct SampleState {
+    const double* sched; int n_steps;   // (n_steps, 4)
+    int* counter;                       // current step (device)
+    float* time_out;                    // (1) fp32 time of the current step, read by time_embed
+    double* cur;                        // (4) current row, read by pose_update
+};
+
+__global__ void sample_advance_kernel(SampleState s) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int i = min(*s.counter, s.n_steps - 1);
+        for (int k = 0; k < 4; ++k) s.cur[k] = s.sched[(size_t)i * 4 + k];
+        s.time_out[0] = (float)s.sched[(size_t)i * 4];
+    }
+}
+
 struct PoseArgs {
     double* T; int n_t;                 // (n_t,7) in place
     const float* ang; const float* lin; // dimensionless scores (n_t,3)
@@ -320,11 +338,20 @@ struct PoseArgs {
     unsigned long long seed, offset;
     double t, ang_mult, lin_mult, alpha_ang, alpha_lin, temperature;
     double* traj_out;                   // optional (n_t,7) copy of the new pose
+    const double* dev_row;              // optional device row [t, alpha_ang, alpha_lin, temperature] overriding the host values
+    int* dev_counter;                   // optional device step counter: Philox offset, trajectory row (counter+1), incremented here
 };
 
 __global__ void pose_update_kernel(PoseArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_t) return;
+    if (a.dev_row) { a.t = a.dev_row[0]; a.alpha_ang = a.dev_row[1]; a.alpha_lin = a.dev_row[2]; a.temperature = a.dev_row[3]; }
+    if (a.dev_counter) {
+        const int step = *a.dev_counter;
+        a.offset = (unsigned long long)step;
+        if (a.noise) a.noise += (size_t)step * a.n_t * 6;
+        if (a.traj_out) a.traj_out += (size_t)(step + 1) * a.n_t * 7;
+    }
     double z[6];
     if (a.noise) {
         for (int k = 0; k < 6; ++k) z[k] = a.noise[(size_t)i * 6 + k];
@@ -361,9 +388,10 @@ __global__ void pose_update_kernel(PoseArgs a) {
     if (a.traj_out) for (int k = 0; k < 7; ++k) a.traj_out[(size_t)i * 7 + k] = T[k];
 }
 
-__global__ void cast_pose_kernel(const double* __restrict__ T, int n, float* __restrict__ out) {
+__global__ void cast_pose_kernel(const double* __restrict__ T, int n, float* __restrict__ out, int* counter) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (float)T[i];
+    if (counter && i == 0) *counter += 1;      // runs after pose_update_kernel on the same stream
 }
 
 }  // namespace dedf
@@ -424,15 +452,27 @@ extern "C" int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, cons
 extern "C" int dedf_pose_update(double* T, int n_t, const float* ang, const float* lin, const double* noise,
                                 unsigned long long seed, unsigned long long offset, double t, double ang_mult,
                                 double lin_mult, double alpha_ang, double alpha_lin, double temperature,
-                                double* traj_out, float* T_f32_out, cudaStream_t stream) {
+                                double* traj_out, float* T_f32_out, const double* dev_row, int* dev_counter,
+                                cudaStream_t stream) {
     if (!T || !ang || !lin) return DEDF_ERR_ARG;
+    if (dev_counter && !T_f32_out) return DEDF_ERR_ARG;     // the counter is advanced by the cast kernel
     if (n_t <= 0) return DEDF_OK;
-    PoseArgs a{T, n_t, ang, lin, noise, seed, offset, t, ang_mult, lin_mult, alpha_ang, alpha_lin, temperature, traj_out};
+    PoseArgs a{T, n_t, ang, lin, noise, seed, offset, t, ang_mult, lin_mult, alpha_ang, alpha_lin, temperature, traj_out,
+               dev_row, dev_counter};
     pose_update_kernel<<<(n_t + 127) / 128, 128, 0, stream>>>(a);
     DEDF_CHECK_LAUNCH();
     if (T_f32_out) {
-        cast_pose_kernel<<<(n_t * 7 + 255) / 256, 256, 0, stream>>>(T, n_t * 7, T_f32_out);
+        cast_pose_kernel<<<(n_t * 7 + 255) / 256, 256, 0, stream>>>(T, n_t * 7, T_f32_out, dev_counter);
         DEDF_CHECK_LAUNCH();
     }
+    return DEDF_OK;
+}
+
+extern "C" int dedf_sample_advance(const double* sched, int n_steps, int* counter, float* time_out, double* cur_row,
+                                   cudaStream_t stream) {
+    if (!sched || !counter || !time_out || !cur_row || n_steps <= 0) return DEDF_ERR_ARG;
+    SampleState s{sched, n_steps, counter, time_out, cur_row};
+    sample_advance_kernel<<<1, 32, 0, stream>>>(s);
+    DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

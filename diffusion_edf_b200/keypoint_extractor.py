@@ -6,6 +6,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from . import ops
 from .gnn_data import FeaturedPoints
 from .irreps import Irreps
 
@@ -23,7 +24,7 @@ class StaticKeypointModel(nn.Module):
     def forward(self, input_points: FeaturedPoints) -> FeaturedPoints:
         b = input_points.b
         assert b.ndim == 1
-        bu = torch.unique(b)
+        bu = ops.plan_value(lambda: torch.unique(b))      # device->host sync: recorded once under a CUDA-graph plan
         n = len(bu)
         return FeaturedPoints(x=self.keypoint_coords.repeat(n, 1), f=self.keypoint_features.repeat(n, 1),
                               b=bu.repeat(len(self.keypoint_coords)), w=torch.sigmoid(self.keypoint_weights).repeat(n))

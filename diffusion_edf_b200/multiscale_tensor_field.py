@@ -118,7 +118,7 @@ class MultiscaleTensorField(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, query_points: FeaturedPoints, input_points_multiscale: List[FeaturedPoints],
                 context_emb=None, max_neighbors: int = 1000, *, time_rows: Optional[torch.Tensor] = None,
-                rows_per_time: int = 1, sources=None) -> FeaturedPoints:
+                rows_per_time: int = 1, sources=None, edge_capacity: Optional[int] = None) -> FeaturedPoints:
         """``time_rows`` (n_scales, n_rb, K): time half of the pre-linear from dedf_time_embed; the row used by an
         edge is ``edge_dst // rows_per_time`` (clamped), i.e. nQ consecutive query nodes share a pose's time."""
         if context_emb is not None:
@@ -128,7 +128,7 @@ class MultiscaleTensorField(nn.Module):
         xq = query_points.x.contiguous()
         radii = self.r_cluster_multiscale
         g = ops.radius_csr(x_src, xq, radii, src_off=src_off, b_src=b_src, b_dst=query_points.b.contiguous(),
-                           max_num_neighbors=max_neighbors)
+                           max_num_neighbors=max_neighbors, capacity=edge_capacity)
         ns = self.r_mincut_nonscalar_sh
         length, sh, logit = ops.edge_geom(x_src, xq, g, radii=radii, src_off=src_off, ns_cut=(0.2 * ns, 1.0 * ns),
                                           want_logit=True)

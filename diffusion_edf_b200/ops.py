@@ -33,7 +33,7 @@ PROFILE = None      # set to {} to collect {entry point: [(start_event, end_even
 _KERNELS = {"dedf_fps": 1, "dedf_radius_count": 2, "dedf_radius_fill": 1, "dedf_edge_geom": 1, "dedf_edge_mlp": 1,
             "dedf_edge_tp_lin": 1, "dedf_segment_softmax_reduce": 1, "dedf_edge_tp_reduce": 1, "dedf_node_linear": 1,
             "dedf_gather_rows": 1, "dedf_add_scale": 1, "dedf_time_embed": 1, "dedf_query_transform": 1, "dedf_score_tp": 1,
-            "dedf_pose_update": 2}
+            "dedf_pose_update": 2, "dedf_sample_advance": 1}
 
 
 def _call(name: str, *args) -> None:
@@ -52,29 +52,97 @@ def _call(name: str, *args) -> None:
 
 
 # ----------------------------------------------------------------------------
+# static plans: make a data-dependent forward replayable as a CUDA graph
+# ----------------------------------------------------------------------------
+class Plan:
+    """Host-side values a forward pass normally has to read back from the device (edge counts, batch layout), recorded
+    once in an eager pass and then replayed, so that the same Python code runs without any host synchronisation and with
+    buffer sizes fixed ahead of time (edge counts become capacities; ``overflow`` is raised on the device if one is exceeded)."""
+
+    def __init__(self, margin: float = 1.5, pad: int = 1024):
+        self.items: list = []
+        self.pos = 0
+        self.mode = "record"
+        self.margin, self.pad = margin, pad
+        self.overflow: Optional[torch.Tensor] = None
+
+    def start(self, mode: str, overflow: Optional[torch.Tensor] = None):
+        self.mode, self.pos, self.overflow = mode, 0, overflow
+        if mode == "record":
+            self.items = []
+
+    def value(self, fn):
+        """Record ``fn()`` (eager pass) or return the recorded value (replay pass)."""
+        if self.mode == "record":
+            v = fn()
+            self.items.append(v)
+            return v
+        v = self.items[self.pos]
+        self.pos += 1
+        return v
+
+    def capacity(self, n_edges: int) -> int:
+        return int(n_edges * self.margin) + self.pad
+
+
+_PLAN: Optional[Plan] = None
+
+
+class use_plan:
+    def __init__(self, plan: Optional[Plan], mode: str = "record", overflow: Optional[torch.Tensor] = None):
+        self.plan, self.mode, self.overflow = plan, mode, overflow
+
+    def __enter__(self):
+        global _PLAN
+        self.prev = _PLAN
+        _PLAN = self.plan
+        if self.plan is not None:
+            self.plan.start(self.mode, self.overflow)
+        return self.plan
+
+    def __exit__(self, *exc):
+        global _PLAN
+        _PLAN = self.prev
+        return False
+
+
+def plan_value(fn):
+    """``fn()`` normally; under a plan the value is recorded / replayed (use for anything that syncs with the device)."""
+    return fn() if _PLAN is None else _PLAN.value(fn)
+
+
+def replaying() -> bool:
+    return _PLAN is not None and _PLAN.mode == "replay"
+
+
+# ----------------------------------------------------------------------------
 # graph construction
 # ----------------------------------------------------------------------------
 def fps(x: torch.Tensor, batch: Optional[torch.Tensor], ratio: float, random_start: bool = False) -> torch.Tensor:
     """torch_cluster.fps: LongTensor of selected indices, per batch segment, in selection order."""
-    lib = L.load()
     n_total = x.shape[0]
     x = x.contiguous()
-    if batch is None or n_total == 0:
-        segs = [(0, n_total)]
-    else:
+
+    def _segments():
+        if batch is None or n_total == 0:
+            return [(0, n_total)]
         counts = torch.bincount(batch).tolist()        # batch ids are sorted/contiguous (as torch_cluster requires)
         segs, o = [], 0
         for c in counts:
             if c:
                 segs.append((o, c))
             o += c
+        return segs
+
+    segs = plan_value(_segments)
     ms = [int(math.ceil(ratio * n)) for _, n in segs]
     out = torch.empty(sum(ms), dtype=torch.long, device=x.device)
     off = 0
     for (o, n), m in zip(segs, ms):
-        start = int(torch.randint(n, (1,)).item()) if random_start else 0
+        # random start: drawn on the device and read by the kernel, so the call never synchronises
+        start_dev = torch.randint(n, (1,), device=x.device, dtype=torch.long) if random_start else None
         scratch = torch.empty(n, dtype=torch.float32, device=x.device) if n > 16384 else None
-        _call("dedf_fps", ptr(x) + o * 12, n, m, start, o, out.data_ptr() + off * 8, ptr(scratch), stream())
+        _call("dedf_fps", ptr(x) + o * 12, n, m, 0, ptr(start_dev, torch.long), o, out.data_ptr() + off * 8, ptr(scratch), stream())
         off += m
     return out
 
@@ -82,9 +150,13 @@ def fps(x: torch.Tensor, batch: Optional[torch.Tensor], ratio: float, random_sta
 def radius_csr(x_src: torch.Tensor, x_dst: torch.Tensor, radii: Sequence[Optional[float]],
                src_off: Optional[Sequence[int]] = None, b_src: Optional[torch.Tensor] = None,
                b_dst: Optional[torch.Tensor] = None, excl_mode: int = 0, excl: Optional[torch.Tensor] = None,
-               max_num_neighbors: int = 1000) -> Csr:
-    """Radius search of ``x_dst`` against ``len(radii)`` concatenated source clouds (None radius = all pairs)."""
-    lib = L.load()
+               max_num_neighbors: int = 1000, capacity: Optional[int] = None,
+               overflow: Optional[torch.Tensor] = None) -> Csr:
+    """Radius search of ``x_dst`` against ``len(radii)`` concatenated source clouds (None radius = all pairs).
+
+    Default: exact CSR, one host sync to size the edge buffers.  With ``capacity`` (or under a replaying ``Plan``) the edge
+    buffers are pre-sized, nothing synchronises, the CSR is clamped on the device and ``overflow`` (int32[1]) is raised
+    if the capacity was exceeded; ``Csr.n_edges`` is then the capacity and the true count lives in ``n_edges_dev``."""
     n_scales = len(radii)
     if src_off is None:
         assert n_scales == 1
@@ -99,10 +171,23 @@ def radius_csr(x_src: torch.Tensor, x_dst: torch.Tensor, radii: Sequence[Optiona
     pb_s = ptr(b_src, torch.long) if b_src is not None else None
     pb_d = ptr(b_dst, torch.long) if b_dst is not None else None
     pex = ptr(excl, torch.long) if excl is not None else None
+    if capacity is None and replaying():
+        capacity = _PLAN.capacity(_PLAN.value(None))
+        overflow = _PLAN.overflow
+    if capacity is not None:
+        capacity = max(1, int(capacity))
+        _call("dedf_radius_count", ptr(x_src), ptr(x_dst), n_dst, n_scales, so, rr, pb_s, pb_d, excl_mode, pex,
+              max_num_neighbors, ptr(counts, torch.int32), ptr(row_ptr, torch.int32), capacity, None,
+              ptr(overflow, torch.int32), stream())
+        edge_src = torch.empty(capacity, dtype=torch.int32, device=dev)
+        edge_dst = torch.empty(capacity, dtype=torch.int32, device=dev)
+        _call("dedf_radius_fill", ptr(x_src), ptr(x_dst), n_dst, n_scales, so, rr, pb_s, pb_d, excl_mode, pex,
+              max_num_neighbors, ptr(row_ptr, torch.int32), ptr(edge_src, torch.int32), ptr(edge_dst, torch.int32), stream())
+        return Csr(row_ptr, edge_src, edge_dst, row_ptr[-1:], capacity, n_dst, n_scales)
     _call("dedf_radius_count", ptr(x_src), ptr(x_dst), n_dst, n_scales, so, rr, pb_s, pb_d, excl_mode, pex,
-                                max_num_neighbors, ptr(counts, torch.int32), ptr(row_ptr, torch.int32), stream())
+                                max_num_neighbors, ptr(counts, torch.int32), ptr(row_ptr, torch.int32), 0, None, None, stream())
     n_edges_dev = row_ptr[-1:]
-    n_edges = int(n_edges_dev.item())          # the one host sync of a graph build (sizes the edge buffers)
+    n_edges = plan_value(lambda: int(n_edges_dev.item()))   # the one host sync of a graph build (sizes the edge buffers)
     edge_src = torch.empty(max(1, n_edges), dtype=torch.int32, device=dev)
     edge_dst = torch.empty(max(1, n_edges), dtype=torch.int32, device=dev)
     _call("dedf_radius_fill", ptr(x_src), ptr(x_dst), n_dst, n_scales, so, rr, pb_s, pb_d, excl_mode, pex,
@@ -133,7 +218,6 @@ def edge_geom(x_src: torch.Tensor, x_dst: torch.Tensor, g: Csr, radii: Optional[
               src_off: Optional[Sequence[int]] = None, ns_cut: Optional[Tuple[float, float]] = None,
               want_logit: bool = False):
     """-> (length (E), sh (E,9), logit (E) or None)."""
-    lib = L.load()
     dev = x_src.device
     E = max(1, g.n_edges)
     length = torch.empty(E, dtype=torch.float32, device=dev)
@@ -240,7 +324,13 @@ def score_tp(Ts, qf_rot, key_f, qx, qw, irr, Wd: List[torch.Tensor], Wl0, Wl1, b
 
 def pose_update(T: torch.Tensor, ang: torch.Tensor, lin: torch.Tensor, noise: Optional[torch.Tensor], seed: int, offset: int,
                 t: float, ang_mult: float, lin_mult: float, alpha_ang: float, alpha_lin: float, temperature: float,
-                traj_out: Optional[torch.Tensor], T_f32_out: Optional[torch.Tensor]) -> None:
+                traj_out: Optional[torch.Tensor], T_f32_out: Optional[torch.Tensor], dev_row: Optional[torch.Tensor] = None,
+                dev_counter: Optional[torch.Tensor] = None) -> None:
     _call("dedf_pose_update", ptr(T, torch.float64), T.shape[0], ptr(ang), ptr(lin), ptr(noise, torch.float64), seed, offset,
-                                    t, ang_mult, lin_mult, alpha_ang, alpha_lin, temperature, ptr(traj_out, torch.float64),
-                                    ptr(T_f32_out), stream())
+          t, ang_mult, lin_mult, alpha_ang, alpha_lin, temperature, ptr(traj_out, torch.float64), ptr(T_f32_out),
+          ptr(dev_row, torch.float64), ptr(dev_counter, torch.int32), stream())
+
+
+def sample_advance(sched: torch.Tensor, counter: torch.Tensor, time_out: torch.Tensor, cur_row: torch.Tensor) -> None:
+    _call("dedf_sample_advance", ptr(sched, torch.float64), sched.shape[0], ptr(counter, torch.int32), ptr(time_out),
+          ptr(cur_row, torch.float64), stream())

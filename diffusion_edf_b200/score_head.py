@@ -109,7 +109,8 @@ class ScoreModelHead(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, Ts: torch.Tensor, key_pcd_multiscale: List[FeaturedPoints], query_pcd: FeaturedPoints,
-                time: torch.Tensor, *, sources=None, shared_time: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+                time: torch.Tensor, *, sources=None, shared_time: bool = False,
+                edge_capacity: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         assert Ts.ndim == 2 and Ts.shape[-1] == 7, f"{Ts.shape}"
         assert time.ndim == 1 and (len(time) == len(Ts) or shared_time), f"{time.shape}"
         assert query_pcd.f.ndim == 2 and query_pcd.f.shape[-1] == self.query_edf_dim, f"{query_pcd.f.shape}"
@@ -124,7 +125,7 @@ class ScoreModelHead(nn.Module):
         bq = query_pcd.b.unsqueeze(0).expand(nT, -1).reshape(-1).contiguous()
         flat = FeaturedPoints(x=xq, f=fq, b=bq, w=None)
         field = self.key_tensor_field(query_points=flat, input_points_multiscale=key_pcd_multiscale,
-                                      time_rows=time_rows, rows_per_time=nQ, sources=sources)
+                                      time_rows=time_rows, rows_per_time=nQ, sources=sources, edge_capacity=edge_capacity)
         Wd, Wl0, Wl1, bl = self._tp_packed()
         ang, lin = ops.score_tp(Ts, fq, field.f, qx, query_pcd.w.contiguous(), self.irreps_key_edf.m, Wd, Wl0, Wl1, bl,
                                 self.n_irreps_prescore, self.lin_mult)

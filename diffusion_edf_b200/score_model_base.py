@@ -10,6 +10,7 @@ from torch import nn
 
 from . import ops
 from .gnn_data import FeaturedPoints, detach_featured_points
+from .graphs import GraphedCallable
 
 
 class ScoreModelBase(nn.Module):
@@ -21,6 +22,9 @@ class ScoreModelBase(nn.Module):
         self.register_buffer("q_indices", torch.tensor([[1, 2, 3], [0, 3, 2], [3, 0, 1], [2, 1, 0]], dtype=torch.long), persistent=False)
         self.register_buffer("q_factor", torch.tensor([[-0.5, -0.5, -0.5], [0.5, -0.5, 0.5], [0.5, 0.5, -0.5], [-0.5, 0.5, 0.5]]), persistent=False)
         self.sample_seed = 0
+        # CUDA-graph replay of forward() / the denoise step when no gradients are needed (see graphs.py)
+        self.use_cuda_graph = True
+        self._graphs = {}
 
     def get_key_pcd_multiscale(self, pcd: FeaturedPoints) -> List[FeaturedPoints]:
         raise NotImplementedError
@@ -80,7 +84,8 @@ class ScoreModelBase(nn.Module):
         traj[0].copy_(T)
         T32 = T.to(torch.float32)
         sources = self.score_head.key_tensor_field.encode_sources(scene_pcd_multiscale)   # pose-independent, once per scene
-        step = 0
+        # schedule rows [t, alpha_ang, alpha_lin, temperature] in float64 (score_model_base.py:146-171)
+        rows = []
         for n, sch in enumerate(diffusion_schedules):
             s0, s1 = float(sch[0]), float(sch[1])
             if log_t_schedule:
@@ -88,22 +93,82 @@ class ScoreModelBase(nn.Module):
             else:
                 ts = torch.linspace(s0, s1, N_steps[n], dtype=torch.float64).tolist()
             for t in ts:
-                temperature = float(temperatures[n]) * (t ** time_exponent_temp)
-                a_ang = (self.ang_mult ** 2) * (t ** time_exponent_alpha) * timesteps[n]
-                a_lin = (self.lin_mult ** 2) * (t ** time_exponent_alpha) * timesteps[n]
+                rows.append([t, (self.ang_mult ** 2) * (t ** time_exponent_alpha) * timesteps[n],
+                             (self.lin_mult ** 2) * (t ** time_exponent_alpha) * timesteps[n],
+                             float(temperatures[n]) * (t ** time_exponent_temp)])
+        if noise is not None:
+            noise = noise.to(torch.float64).contiguous()
+        if not self.use_cuda_graph:
+            for step, (t, a_ang, a_lin, temperature) in enumerate(rows):
                 time = torch.full((1,), t, dtype=torch.float32, device=dev)
                 ang, lin = self.score_head(Ts=T32, key_pcd_multiscale=scene_pcd_multiscale, query_pcd=grasp_pcd, time=time,
                                            sources=sources, shared_time=True)
-                nz = noise[step].contiguous() if noise is not None else None
+                nz = noise[step] if noise is not None else None
                 ops.pose_update(T, ang, lin, nz, int(self.sample_seed), step, t, self.ang_mult, self.lin_mult, a_ang, a_lin,
                                 temperature, traj[step + 1], T32)
-                step += 1
+            traj[total + 1].copy_(T)
+            return traj
+        # ---- one CUDA graph per denoise step: schedule, step counter, poses, trajectory and noise all live on the device;
+        # edge buffers are sized for the worst case (every key point within reach of every query point), so there is no
+        # overflow to check and no host synchronisation in the loop.
+        sched = torch.tensor(rows, dtype=torch.float64, device=dev)
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        time_cur = torch.zeros(1, dtype=torch.float32, device=dev)
+        cur_row = torch.zeros(4, dtype=torch.float64, device=dev)
+        n_q = grasp_pcd.x.shape[0]
+        cap = nT * n_q * sum(min(p.x.shape[0], 1000) for p in scene_pcd_multiscale)
+
+        def one_step():
+            ops.sample_advance(sched, counter, time_cur, cur_row)
+            ang, lin = self.score_head(Ts=T32, key_pcd_multiscale=scene_pcd_multiscale, query_pcd=grasp_pcd, time=time_cur,
+                                       sources=sources, shared_time=True, edge_capacity=cap)
+            ops.pose_update(T, ang, lin, noise, int(self.sample_seed), 0, 0.0, self.ang_mult, self.lin_mult, 0.0, 0.0, 0.0,
+                            traj, T32, dev_row=cur_row, dev_counter=counter)
+
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            one_step()                                        # warm-up (then restore the state it advanced)
+        cur.wait_stream(side)
+        T.copy_(traj[0]); T32.copy_(T); counter.zero_()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        k0 = ops.LAUNCHES
+        with torch.cuda.graph(graph):
+            one_step()
+        n_kernels = ops.LAUNCHES - k0
+        T.copy_(traj[0]); T32.copy_(T); counter.zero_()       # capture does not execute, but keep the state explicit
+        for _ in range(total):
+            graph.replay()
+        ops.LAUNCHES += n_kernels * total
         traj[total + 1].copy_(T)
         return traj
 
     # ------------------------------------------------------------------ forward
+    def _param_signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _forward_tensors(self, Ts, time, kx, kf, kb, qx, qf, qb):
+        key_ms = self.get_key_pcd_multiscale(FeaturedPoints(kx, kf, kb))
+        q = self.get_query_pcd(FeaturedPoints(qx, qf, qb))
+        return self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)
+
     def forward(self, Ts: torch.Tensor, time: torch.Tensor, key_pcd: FeaturedPoints, query_pcd: FeaturedPoints,
                 debug: bool = False):
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if self.use_cuda_graph and Ts.is_cuda and not debug and not needs_grad and not self.training:
+            ins = [Ts.contiguous(), time.contiguous(), key_pcd.x.contiguous(), key_pcd.f.contiguous(), key_pcd.b.contiguous(),
+                   query_pcd.x.contiguous(), query_pcd.f.contiguous(), query_pcd.b.contiguous()]
+            key = (tuple(tuple(t.shape) for t in ins), str(Ts.device), self._param_signature())
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) >= 4:
+                    self._graphs.clear()
+                g = GraphedCallable(self._forward_tensors, ins)
+                self._graphs[key] = g
+                return tuple(o.clone() for o in g.eager_out), None
+            return g(*ins), None
         key_ms = self.get_key_pcd_multiscale(key_pcd)
         q = self.get_query_pcd(query_pcd)
         score = self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)

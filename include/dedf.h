@@ -43,19 +43,23 @@ extern "C" {
 
 /* torch_cluster.fps(src, ratio, random_start) for ONE batch segment (connectivity.py:62).
  * Selects m points greedily (arg-max of the running min squared distance, ties -> lowest index) starting from
- * `start`; writes idx_base + index in selection order.  scratch_dist (n floats) is needed only for n > 16384. */
-int dedf_fps(const float* x, int n, int m, int start, int idx_base, long long* out_idx, float* scratch_dist,
-             cudaStream_t stream);
+ * `start` (or `*start_dev` when non-NULL: a device-side random start, so that the call stays capturable in a CUDA
+ * graph); writes idx_base + index in selection order.  scratch_dist (n floats) is needed only for n > 16384. */
+int dedf_fps(const float* x, int n, int m, int start, const long long* start_dev, int idx_base, long long* out_idx,
+             float* scratch_dist, cudaStream_t stream);
 
 /* torch_cluster.radius / radius_graph / the all-pairs meshgrid (graph_parser.py:339, :276-278;
  * connectivity.py:22, :42, :68-70), for n_scales source clouds at once (sources concatenated, cloud s =
  * [src_off_host[s], src_off_host[s+1]), radius r_host[s], r < 0 = all pairs).  Pass 1 writes counts
  * (n_scales * n_dst) and their exclusive scan row_ptr (+1 entry = E); pass 2 fills edge_src (flat source index)
  * and edge_dst.  excl_mode: 0 none; 1 drop src == excl[dst]; 2 drop src == dst; 3 drop excl[src] == dst.
- * max_nb caps the hits per (scale, dst) BEFORE the exclusion, like torch_cluster + the reference's filter. */
+ * max_nb caps the hits per (scale, dst) BEFORE the exclusion, like torch_cluster + the reference's filter.
+ * capacity > 0 (edge buffers sized ahead of time, e.g. for CUDA-graph replay): row_ptr is clamped to `capacity`,
+ * *n_edges_out = min(E, capacity) and *overflow |= 1 if E > capacity; capacity <= 0: exact CSR. */
 int dedf_radius_count(const float* x_src, const float* x_dst, int n_dst, int n_scales, const int* src_off_host,
                       const float* r_host, const long long* b_src, const long long* b_dst, int excl_mode,
-                      const long long* excl, int max_nb, int* counts, int* row_ptr, cudaStream_t stream);
+                      const long long* excl, int max_nb, int* counts, int* row_ptr, int capacity, int* n_edges_out,
+                      int* overflow, cudaStream_t stream);
 int dedf_radius_fill(const float* x_src, const float* x_dst, int n_dst, int n_scales, const int* src_off_host,
                      const float* r_host, const long long* b_src, const long long* b_dst, int excl_mode,
                      const long long* excl, int max_nb, const int* row_ptr, int* edge_src, int* edge_dst,
@@ -169,11 +173,20 @@ int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, const float* ke
 
 /* One annealed-Langevin step on SE(3) in float64 (score_model_base.py:178-193).  noise (n_t, 6) standard normals
  * or NULL (Philox4x32-10 with (seed, pose, offset)).  Optionally copies the new poses to traj_out (f64) and
- * T_f32_out (f32, the network input of the next step). */
+ * T_f32_out (f32, the network input of the next step).
+ * Graph-replay mode: dev_row (4 doubles [t, alpha_ang, alpha_lin, temperature], see dedf_sample_advance) overrides the
+ * host scalars and dev_counter (device step index) selects the Philox offset, the noise rows (noise + step*n_t*6) and
+ * the trajectory row (traj_out + (step+1)*n_t*7); the counter is incremented at the end of the call. */
 int dedf_pose_update(double* T, int n_t, const float* ang, const float* lin, const double* noise,
                      unsigned long long seed, unsigned long long offset, double t, double ang_mult, double lin_mult,
                      double alpha_ang, double alpha_lin, double temperature, double* traj_out, float* T_f32_out,
-                     cudaStream_t stream);
+                     const double* dev_row, int* dev_counter, cudaStream_t stream);
+
+/* Loads row `*counter` of the device-resident schedule (n_steps, 4) = [t, alpha_ang, alpha_lin, temperature] into
+ * cur_row and writes the fp32 time of the step to time_out[0] (the `time` input of dedf_time_embed), so that one denoise
+ * step (score_model_base.py:146-199) is a parameter-free, replayable sequence of launches. */
+int dedf_sample_advance(const double* sched, int n_steps, int* counter, float* time_out, double* cur_row,
+                        cudaStream_t stream);
 
 /* library self-description: returns the compute capability the kernels were built for (100) */
 int dedf_build_arch(void);

@@ -215,3 +215,52 @@ def test_identity_pose_deviation(cuda):
     assert (got.cpu() - f).abs().max() < 1e-6                          # the identity, to fp32 round-off
     l1 = ref[:, 64:160].view(3, 32, 3)
     assert torch.allclose(l1, f[:, 64:160].view(3, 32, 3) * torch.tensor([-1.0, 1.0, -1.0]), atol=1e-6)   # the reference's artefact
+
+
+def test_cuda_graph_forward_matches_eager_and_replans_on_overflow(cuda):
+    """graphs.py: replayed forward == eager forward (same kernels, same inputs); when an edge list outgrows its planned
+    capacity the device flag triggers a re-plan and the result is still the eager one."""
+    from diffusion_edf_b200 import FeaturedPoints
+    from diffusion_edf_b200.synthetic import make_poses, make_scene
+    _, model = _models(cuda, seed=8)
+    x, rgb = make_scene(2000, seed=8, half_extent=14.0)
+    b = torch.zeros(len(x), dtype=torch.long)
+    key = FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda))
+    grasp = FeaturedPoints(torch.zeros(4, 3, device=cuda), torch.zeros(4, 3, device=cuda), torch.zeros(4, dtype=torch.long, device=cuda))
+    far, t = make_poses(16, x + 500.0, seed=1, spread=3.0)          # nothing within reach: only the all-pairs scale
+    near, _ = make_poses(16, x, seed=2, spread=4.0)                 # many more edges than planned
+    near[:, 6] -= 8.0
+    with torch.no_grad():
+        model.use_cuda_graph = False
+        ref = {k: model(T.to(cuda), t.to(cuda), key, grasp)[0] for k, T in (("far", far), ("near", near))}
+        model.use_cuda_graph = True
+        (a0, l0), _ = model(far.to(cuda), t.to(cuda), key, grasp)          # builds the plan + graph
+        (a1, l1), _ = model(far.to(cuda), t.to(cuda), key, grasp)          # replay
+        g = next(iter(model._graphs.values()))
+        assert g.replays == 1 and g.n_kernels > 100
+        for a, l in ((a0, l0), (a1, l1)):
+            assert_close(a, ref["far"][0], 1e-6, "graph vs eager (ang)")
+            assert_close(l, ref["far"][1], 1e-6, "graph vs eager (lin)")
+        (a2, l2), _ = model(near.to(cuda), t.to(cuda), key, grasp)         # overflows the planned capacity -> re-plan
+        assert_close(a2, ref["near"][0], 1e-6, "re-planned (ang)")
+        assert_close(l2, ref["near"][1], 1e-6, "re-planned (lin)")
+        (a3, l3), _ = model(near.to(cuda), t.to(cuda), key, grasp)         # replay of the new plan
+        assert_close(a3, ref["near"][0], 1e-6, "replay after re-plan")
+
+
+def test_sample_graph_replay_equals_eager_loop(cuda):
+    from diffusion_edf_b200 import FeaturedPoints
+    from diffusion_edf_b200.synthetic import make_poses, make_scene
+    _, model = _models(cuda, seed=9)
+    x, rgb = make_scene(1200, seed=9, half_extent=10.0)
+    T0, _ = make_poses(8, x, seed=9, spread=4.0)
+    b = torch.zeros(len(x), dtype=torch.long)
+    kw = dict(diffusion_schedules=[[1.0, 0.3]], N_steps=[9], timesteps=[0.04], temperatures=[1.0], time_exponent_temp=1.0)
+    with torch.no_grad():
+        model.use_cuda_graph = False
+        keys = model.get_key_pcd_multiscale(FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)))
+        q = model.get_query_pcd(FeaturedPoints(torch.zeros(3, 3, device=cuda), torch.zeros(3, 3, device=cuda), torch.zeros(3, dtype=torch.long, device=cuda)))
+        eager = model.sample(T0.to(cuda), keys, q, **kw)                 # Philox noise, (seed, pose, step) keyed
+        model.use_cuda_graph = True
+        graphed = model.sample(T0.to(cuda), keys, q, **kw)
+    assert (eager - graphed).abs().max() < 1e-9
