@@ -56,6 +56,9 @@ _PROTOS = {
     "dedf_fps": [c_fp, c_int, c_int, c_int, c_fp, c_int, c_fp, c_fp, c_fp],
     "dedf_radius_count": [c_fp, c_fp, c_int, c_int, C.POINTER(c_int), C.POINTER(c_f), c_fp, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_int, c_fp, c_fp, c_fp],
     "dedf_radius_fill": [c_fp, c_fp, c_int, c_int, C.POINTER(c_int), C.POINTER(c_f), c_fp, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_fp, c_fp],
+    "dedf_grid_build": [c_fp, c_int, c_f, c_int, c_fp, c_fp, c_fp, c_fp, c_fp],
+    "dedf_radius_grid_count": [c_fp, c_int, c_fp, c_int, c_f, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_int, c_fp, c_fp, c_fp],
+    "dedf_radius_grid_fill": [c_fp, c_int, c_fp, c_int, c_f, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_fp, c_fp],
     "dedf_edge_geom": [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, C.POINTER(c_int), C.POINTER(c_f), c_f, c_f, c_fp, c_fp, c_fp, c_fp],
     "dedf_edge_mlp": [C.POINTER(MlpDesc), c_int, c_fp],
     "dedf_edge_tp_lin": [c_int, c_int, c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp],

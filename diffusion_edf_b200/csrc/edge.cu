@@ -772,9 +772,60 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-constexpr int kK1Warps = 10;
+constexpr int kK1Warps = 12;
 constexpr int kK1Stages = 3;
 constexpr int kK1TaskD = 16;      // destinations per warp task (row pointers live in lanes 0..16)
+
+// CG math of one pack read from a shared-memory stage.  FULL = all P edges valid: no per-slot predicates.
+template <int G, bool FULL>
+__device__ __forceinline__ void k1_pack_math(int lane, int nv, const float* __restrict__ sw, const float* __restrict__ sx,
+                                             const float* __restrict__ ssh, const float* __restrict__ sal,
+                                             float (&acc0)[4][9], float (&acc1)[2][20], float (&acc2)[22]) {
+    using D = Dtp<G>;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        int ei, ch; D::slot0(lane, s, ei, ch);
+        if (FULL || ei < nv) {
+            const float al = sal[ei * 4 + ch / (D::M0 / 4)];
+            const float* w = sw + ei * D::NUMEL;
+            float o[9];
+            dtp_l0(sx[ei * D::F + ch] * al, w[D::W_K0 + ch], w[D::W_K1 + ch], w[D::W_K2 + ch], ssh + ei * 12, o);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc0[s][k] += o[k];
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        int ei, ch; D::slot1(lane, s, ei, ch);
+        if (FULL || ei < nv) {
+            const float al = sal[ei * 4 + ch / (D::M1 / 4)];
+            const float* xs = sx + ei * D::F + D::M0 + 3 * ch;
+            float x[3] = {xs[0] * al, xs[1] * al, xs[2] * al}, w[6], o[20];
+            const float* wp = sw + ei * D::NUMEL + D::W_K3 + ch;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) w[i] = wp[i * D::M1];
+            dtp_l1(x, w, ssh + ei * 12, o);
+#pragma unroll
+            for (int k = 0; k < 20; ++k) acc1[s][k] += o[k];
+        }
+    }
+    {
+        int ei, ch; D::slot2(lane, ei, ch);
+        if (FULL || ei < nv) {
+            const float al = sal[ei * 4 + ch / (D::M2 / 4)];
+            const float* xs = sx + ei * D::F + D::M0 + 3 * D::M1 + 5 * ch;
+            float x[5], w[6], o[22];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) x[i] = xs[i] * al;
+            const float* wp = sw + ei * D::NUMEL + D::W_K9 + ch;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) w[i] = wp[i * D::M2];
+            dtp_l2(x, w, ssh + ei * 12, o);
+#pragma unroll
+            for (int k = 0; k < 22; ++k) acc2[k] += o[k];
+        }
+    }
+}
 
 template <int G>
 struct K1Stage {
@@ -889,49 +940,8 @@ __global__ void __launch_bounds__(kK1Warps * 32, 1) edge_tp_reduce_tma_kernel(Tp
                 const float* sx = st + ST::X_OFF;
                 const float* ssh = st + ST::SH_OFF;
                 const float* sal = st + ST::AL_OFF;
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    int ei, ch; D::slot0(lane, s, ei, ch);
-                    if (ei < nv) {
-                        const float al = sal[ei * 4 + ch / (D::M0 / 4)];
-                        const float* w = sw + ei * D::NUMEL;
-                        float o[9];
-                        dtp_l0(sx[ei * D::F + ch] * al, w[D::W_K0 + ch], w[D::W_K1 + ch], w[D::W_K2 + ch], ssh + ei * 12, o);
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) acc0[s][k] += o[k];
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    int ei, ch; D::slot1(lane, s, ei, ch);
-                    if (ei < nv) {
-                        const float al = sal[ei * 4 + ch / (D::M1 / 4)];
-                        const float* xs = sx + ei * D::F + D::M0 + 3 * ch;
-                        float x[3] = {xs[0] * al, xs[1] * al, xs[2] * al}, w[6], o[20];
-                        const float* wp = sw + ei * D::NUMEL + D::W_K3 + ch;
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) w[i] = wp[i * D::M1];
-                        dtp_l1(x, w, ssh + ei * 12, o);
-#pragma unroll
-                        for (int k = 0; k < 20; ++k) acc1[s][k] += o[k];
-                    }
-                }
-                {
-                    int ei, ch; D::slot2(lane, ei, ch);
-                    if (ei < nv) {
-                        const float al = sal[ei * 4 + ch / (D::M2 / 4)];
-                        const float* xs = sx + ei * D::F + D::M0 + 3 * D::M1 + 5 * ch;
-                        float x[5], w[6], o[22];
-#pragma unroll
-                        for (int i = 0; i < 5; ++i) x[i] = xs[i] * al;
-                        const float* wp = sw + ei * D::NUMEL + D::W_K9 + ch;
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) w[i] = wp[i * D::M2];
-                        dtp_l2(x, w, ssh + ei * 12, o);
-#pragma unroll
-                        for (int k = 0; k < 22; ++k) acc2[k] += o[k];
-                    }
-                }
+                if (nv == P) k1_pack_math<G, true>(lane, nv, sw, sx, ssh, sal, acc0, acc1, acc2);
+                else k1_pack_math<G, false>(lane, nv, sw, sx, ssh, sal, acc0, acc1, acc2);
                 __syncwarp();                    // every lane is done reading this stage -> refill it
                 issue(cstage);
                 cstage = (cstage + 1) % S;

@@ -220,6 +220,176 @@ exclusive_scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ r
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Grid-hash radius search (one source cloud, finite radius): sources are counting-sorted into the buckets of a hashed
+// uniform grid with cell edge slightly larger than r (so every neighbour lies in the 27 surrounding cells); a warp per
+// destination scans those cells, collects the hits in shared memory, sorts them ascending (bitonic) and applies
+// torch_cluster's truncation + the reference's exclusion filter on the ordered list.  Results are identical, element for
+// element, to the brute-force kernel above (same exact squared distance); destinations with more hits than the shared
+// buffer holds fall back to the ordered brute-force scan.
+// ---------------------------------------------------------------------------
+constexpr int kGridMaxHits = 1024;          // per-warp hit buffer (ints)
+constexpr int kGridWarps = 8;
+
+__device__ __forceinline__ int3 grid_cell(float x, float y, float z, float inv_cell) {
+    return make_int3((int)floorf(x * inv_cell), (int)floorf(y * inv_cell), (int)floorf(z * inv_cell));
+}
+__device__ __forceinline__ unsigned grid_hash(int3 c, unsigned mask) {
+    return ((unsigned)c.x * 73856093u ^ (unsigned)c.y * 19349663u ^ (unsigned)c.z * 83492791u) & mask;
+}
+
+__global__ void grid_count_kernel(const float* __restrict__ x, int n, float inv_cell, unsigned mask, int* __restrict__ bucket_cnt) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(bucket_cnt + grid_hash(grid_cell(x[3 * i], x[3 * i + 1], x[3 * i + 2], inv_cell), mask), 1);
+}
+
+__global__ void grid_fill_kernel(const float* __restrict__ x, int n, float inv_cell, unsigned mask, const int* __restrict__ bucket_start,
+                                 int* __restrict__ bucket_fill, int* __restrict__ sorted_idx) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned b = grid_hash(grid_cell(x[3 * i], x[3 * i + 1], x[3 * i + 2], inv_cell), mask);
+        sorted_idx[bucket_start[b] + atomicAdd(bucket_fill + b, 1)] = i;
+    }
+}
+
+// one thread per bucket: order the bucket by source index (the atomics above fill it in arbitrary order) and lay the
+// coordinates out in the same order so that the query kernel streams them
+__global__ void grid_sort_kernel(const float* __restrict__ x, int n_buckets, const int* __restrict__ bucket_start,
+                                 int* __restrict__ sorted_idx, float* __restrict__ sorted_xyz) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += gridDim.x * blockDim.x) {
+        const int s = bucket_start[b], e = bucket_start[b + 1];
+        for (int i = s + 1; i < e; ++i) {
+            const int v = sorted_idx[i];
+            int j = i - 1;
+            while (j >= s && sorted_idx[j] > v) { sorted_idx[j + 1] = sorted_idx[j]; --j; }
+            sorted_idx[j + 1] = v;
+        }
+        for (int i = s; i < e; ++i) {
+            const int v = sorted_idx[i];
+            sorted_xyz[3 * i] = x[3 * v]; sorted_xyz[3 * i + 1] = x[3 * v + 1]; sorted_xyz[3 * i + 2] = x[3 * v + 2];
+        }
+    }
+}
+
+struct GridArgs {
+    const float* x_src; const float* x_dst;      // x_src only for the brute-force fallback
+    const long long* b_src; const long long* b_dst; const long long* excl;
+    const int* bucket_start; const int* sorted_idx; const float* sorted_xyz;
+    int n_src, n_dst, max_nb, excl_mode;
+    float r, inv_cell; unsigned mask;
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(kGridWarps * 32)
+radius_grid_kernel(GridArgs a, int* __restrict__ counts, const int* __restrict__ row_ptr, int* __restrict__ edge_src,
+                   int* __restrict__ edge_dst) {
+    __shared__ int s_hits[kGridWarps][kGridMaxHits];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* hits = s_hits[warp];
+    const float r2 = a.r * a.r;
+    for (int d = blockIdx.x * kGridWarps + warp; d < a.n_dst; d += gridDim.x * kGridWarps) {
+        const float qx = a.x_dst[3 * d], qy = a.x_dst[3 * d + 1], qz = a.x_dst[3 * d + 2];
+        const long long qb = a.b_dst ? a.b_dst[d] : 0;
+        const int3 qc = grid_cell(qx, qy, qz, a.inv_cell);
+        int n_hits = 0;
+        __syncwarp();
+        for (int nb = 0; nb < 27; ++nb) {
+            const int3 c = make_int3(qc.x + nb % 3 - 1, qc.y + (nb / 3) % 3 - 1, qc.z + nb / 9 - 1);
+            const unsigned b = grid_hash(c, a.mask);
+            const int s = a.bucket_start[b], e = a.bucket_start[b + 1];
+            for (int i0 = s; i0 < e; i0 += 32) {
+                const int i = i0 + lane;
+                bool hit = false;
+                int src = 0;
+                if (i < e) {
+                    const float px = a.sorted_xyz[3 * i], py = a.sorted_xyz[3 * i + 1], pz = a.sorted_xyz[3 * i + 2];
+                    const int3 pc = grid_cell(px, py, pz, a.inv_cell);
+                    // bucket collisions: only accept points that really live in the cell being visited (also prevents
+                    // duplicates when two of the 27 cells share a bucket)
+                    hit = (pc.x == c.x && pc.y == c.y && pc.z == c.z) && (sqdist_exact(px, py, pz, qx, qy, qz) < r2);
+                    src = a.sorted_idx[i];
+                    if (hit && a.b_src) hit = (a.b_src[src] == qb);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    const int pos = n_hits + __popc(bal & ((1u << lane) - 1u));
+                    if (pos < kGridMaxHits) hits[pos] = src;
+                }
+                n_hits += __popc(bal);
+            }
+        }
+        __syncwarp();
+        int base = 0, seg_end = 0x7fffffff;
+        if (FILL) { base = row_ptr[d]; seg_end = row_ptr[d + 1]; }
+        const long long ex = (a.excl_mode == 1) ? a.excl[d] : -1;
+        int cnt_keep = 0;
+        if (n_hits > kGridMaxHits) {
+            // rare, very dense neighbourhood: ordered brute-force scan (same code path as radius_kernel)
+            int cnt_all = 0;
+            for (int c0 = 0; c0 < a.n_src && cnt_all < a.max_nb; c0 += 32) {
+                const int i = c0 + lane;
+                bool hit = false, excluded = false;
+                if (i < a.n_src) {
+                    hit = sqdist_exact(a.x_src[3 * i], a.x_src[3 * i + 1], a.x_src[3 * i + 2], qx, qy, qz) < r2;
+                    if (a.b_src) hit = hit && (a.b_src[i] == qb);
+                    if (a.excl_mode == 1) excluded = ((long long)i == ex);
+                    else if (a.excl_mode == 2) excluded = (i == d);
+                    else if (a.excl_mode == 3) excluded = (a.excl[i] == (long long)d);
+                }
+                const unsigned lt = (1u << lane) - 1u;
+                const unsigned bal_all = __ballot_sync(0xffffffffu, hit);
+                const bool keep = hit && !excluded && (cnt_all + __popc(bal_all & lt) < a.max_nb);
+                const unsigned bal_keep = __ballot_sync(0xffffffffu, keep);
+                if (FILL && keep) {
+                    const int pos = base + cnt_keep + __popc(bal_keep & lt);
+                    if (pos < seg_end) { edge_src[pos] = i; edge_dst[pos] = d; }
+                }
+                cnt_all += __popc(bal_all);
+                cnt_keep += __popc(bal_keep);
+            }
+        } else {
+            // bitonic sort of the hit list (padded to a power of two with INT_MAX), ascending source index
+            int np2 = 32;
+            while (np2 < n_hits) np2 <<= 1;
+            for (int i = n_hits + lane; i < np2; i += 32) hits[i] = 0x7fffffff;
+            __syncwarp();
+            for (int k = 2; k <= np2; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = lane; i < np2; i += 32) {
+                        const int p = i ^ j;
+                        if (p > i) {
+                            const int vi = hits[i], vp = hits[p];
+                            const bool up = ((i & k) == 0);
+                            if ((vi > vp) == up) { hits[i] = vp; hits[p] = vi; }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            const int n_all = min(n_hits, a.max_nb);             // torch_cluster keeps the first max_nb in index order
+            for (int i0 = 0; i0 < n_all; i0 += 32) {
+                const int i = i0 + lane;
+                bool keep = false;
+                int src = 0;
+                if (i < n_all) {
+                    src = hits[i];
+                    keep = true;
+                    if (a.excl_mode == 1) keep = ((long long)src != ex);
+                    else if (a.excl_mode == 2) keep = (src != d);
+                    else if (a.excl_mode == 3) keep = (a.excl[src] != (long long)d);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (FILL && keep) {
+                    const int pos = base + cnt_keep + __popc(bal & ((1u << lane) - 1u));
+                    if (pos < seg_end) { edge_src[pos] = src; edge_dst[pos] = d; }
+                }
+                cnt_keep += __popc(bal);
+            }
+        }
+        if (!FILL && lane == 0) counts[d] = cnt_keep;
+    }
+}
+
 }  // namespace dedf
 
 using namespace dedf;
@@ -296,6 +466,68 @@ extern "C" int dedf_radius_fill(const float* x_src, const float* x_dst, int n_ds
     const long long items = (long long)n_dst * n_scales;
     if (items == 0) return DEDF_OK;
     radius_kernel<true><<<grid_for(items, 8, kNumSMs * 8), 256, 0, stream>>>(a, nullptr, row_ptr, edge_src, edge_dst);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+// ---- grid-hash variant --------------------------------------------------------------------------------------------
+static int fill_grid_args(GridArgs& a, const float* x_src, int n_src, const float* x_dst, int n_dst, float r, int n_buckets,
+                          const int* bucket_start, const int* sorted_idx, const float* sorted_xyz, const long long* b_src,
+                          const long long* b_dst, int excl_mode, const long long* excl, int max_nb) {
+    if (!x_src || !x_dst || !bucket_start || !sorted_idx || !sorted_xyz || n_src < 0 || n_dst < 0 || r <= 0.f || max_nb < 1) return DEDF_ERR_ARG;
+    if (n_buckets < 32 || (n_buckets & (n_buckets - 1))) return DEDF_ERR_ARG;
+    if ((excl_mode == 1 || excl_mode == 3) && !excl) return DEDF_ERR_ARG;
+    if (excl_mode < 0 || excl_mode > 3) return DEDF_ERR_ARG;
+    if ((b_src == nullptr) != (b_dst == nullptr)) return DEDF_ERR_ARG;
+    a.x_src = x_src; a.x_dst = x_dst; a.b_src = b_src; a.b_dst = b_dst; a.excl = excl;
+    a.bucket_start = bucket_start; a.sorted_idx = sorted_idx; a.sorted_xyz = sorted_xyz;
+    a.n_src = n_src; a.n_dst = n_dst; a.max_nb = max_nb; a.excl_mode = excl_mode;
+    a.r = r; a.inv_cell = 1.0f / (r * 1.001f); a.mask = (unsigned)(n_buckets - 1);
+    return DEDF_OK;
+}
+
+extern "C" int dedf_grid_build(const float* x_src, int n_src, float r, int n_buckets, int* bucket_cnt, int* bucket_start,
+                               int* sorted_idx, float* sorted_xyz, cudaStream_t stream) {
+    if (!x_src || !bucket_cnt || !bucket_start || !sorted_idx || !sorted_xyz || n_src < 0 || r <= 0.f) return DEDF_ERR_ARG;
+    if (n_buckets < 32 || (n_buckets & (n_buckets - 1))) return DEDF_ERR_ARG;
+    const float inv_cell = 1.0f / (r * 1.001f);
+    const unsigned mask = (unsigned)(n_buckets - 1);
+    cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * n_buckets, stream);
+    if (n_src > 0) { grid_count_kernel<<<grid_for(n_src, 256, kNumSMs * 8), 256, 0, stream>>>(x_src, n_src, inv_cell, mask, bucket_cnt); DEDF_CHECK_LAUNCH(); }
+    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(bucket_cnt, n_buckets, bucket_start, 0, nullptr, nullptr);
+    DEDF_CHECK_LAUNCH();
+    cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * n_buckets, stream);
+    if (n_src > 0) { grid_fill_kernel<<<grid_for(n_src, 256, kNumSMs * 8), 256, 0, stream>>>(x_src, n_src, inv_cell, mask, bucket_start, bucket_cnt, sorted_idx); DEDF_CHECK_LAUNCH(); }
+    grid_sort_kernel<<<grid_for(n_buckets, 256, kNumSMs * 8), 256, 0, stream>>>(x_src, n_buckets, bucket_start, sorted_idx, sorted_xyz);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_radius_grid_count(const float* x_src, int n_src, const float* x_dst, int n_dst, float r, int n_buckets,
+                                      const int* bucket_start, const int* sorted_idx, const float* sorted_xyz,
+                                      const long long* b_src, const long long* b_dst, int excl_mode, const long long* excl,
+                                      int max_nb, int* counts, int* row_ptr, int capacity, int* n_edges_out, int* overflow,
+                                      cudaStream_t stream) {
+    GridArgs a;
+    int rc = fill_grid_args(a, x_src, n_src, x_dst, n_dst, r, n_buckets, bucket_start, sorted_idx, sorted_xyz, b_src, b_dst, excl_mode, excl, max_nb);
+    if (rc) return rc;
+    if (!counts || !row_ptr) return DEDF_ERR_ARG;
+    if (n_dst > 0) { radius_grid_kernel<false><<<grid_for(n_dst, kGridWarps, kNumSMs * 4), kGridWarps * 32, 0, stream>>>(a, counts, nullptr, nullptr, nullptr); DEDF_CHECK_LAUNCH(); }
+    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(counts, n_dst, row_ptr, capacity, n_edges_out, overflow);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_radius_grid_fill(const float* x_src, int n_src, const float* x_dst, int n_dst, float r, int n_buckets,
+                                     const int* bucket_start, const int* sorted_idx, const float* sorted_xyz,
+                                     const long long* b_src, const long long* b_dst, int excl_mode, const long long* excl,
+                                     int max_nb, const int* row_ptr, int* edge_src, int* edge_dst, cudaStream_t stream) {
+    GridArgs a;
+    int rc = fill_grid_args(a, x_src, n_src, x_dst, n_dst, r, n_buckets, bucket_start, sorted_idx, sorted_xyz, b_src, b_dst, excl_mode, excl, max_nb);
+    if (rc) return rc;
+    if (!row_ptr || !edge_src || !edge_dst) return DEDF_ERR_ARG;
+    if (n_dst == 0) return DEDF_OK;
+    radius_grid_kernel<true><<<grid_for(n_dst, kGridWarps, kNumSMs * 4), kGridWarps * 32, 0, stream>>>(a, nullptr, row_ptr, edge_src, edge_dst);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

@@ -65,6 +65,22 @@ int dedf_radius_fill(const float* x_src, const float* x_dst, int n_dst, int n_sc
                      const long long* excl, int max_nb, const int* row_ptr, int* edge_src, int* edge_dst,
                      cudaStream_t stream);
 
+/* Grid-hash variant of the radius search for ONE large source cloud (connectivity.py:22,42 at the fine scales; the C4
+ * sweep): dedf_grid_build counting-sorts the sources into `n_buckets` (power of two, >= 32) hash buckets of a uniform grid
+ * with cell edge 1.001 r (workspace: bucket_cnt[n_buckets], bucket_start[n_buckets+1], sorted_idx[n_src],
+ * sorted_xyz[3 n_src]); the two passes then visit only the 27 surrounding cells of each destination.  Same arguments and
+ * element-for-element the same CSR as dedf_radius_count / dedf_radius_fill with n_scales = 1. */
+int dedf_grid_build(const float* x_src, int n_src, float r, int n_buckets, int* bucket_cnt, int* bucket_start,
+                    int* sorted_idx, float* sorted_xyz, cudaStream_t stream);
+int dedf_radius_grid_count(const float* x_src, int n_src, const float* x_dst, int n_dst, float r, int n_buckets,
+                           const int* bucket_start, const int* sorted_idx, const float* sorted_xyz, const long long* b_src,
+                           const long long* b_dst, int excl_mode, const long long* excl, int max_nb, int* counts,
+                           int* row_ptr, int capacity, int* n_edges_out, int* overflow, cudaStream_t stream);
+int dedf_radius_grid_fill(const float* x_src, int n_src, const float* x_dst, int n_dst, float r, int n_buckets,
+                          const int* bucket_start, const int* sorted_idx, const float* sorted_xyz, const long long* b_src,
+                          const long long* b_dst, int excl_mode, const long long* excl, int max_nb, const int* row_ptr,
+                          int* edge_src, int* edge_dst, cudaStream_t stream);
+
 /* ---- per-edge ---------------------------------------------------------------------------------------- */
 
 /* Edge vector, length, o3.SphericalHarmonics(lmax=2, normalize=True, 'component'), non-scalar SH min-cut and

@@ -113,3 +113,31 @@ def test_pool_exclusions(cuda):
     a = set(zip(rev.edge_dst.cpu().tolist(), rev.edge_src.cpu().tolist()))
     bset = set(zip(ref_src.tolist(), ref_dst.tolist()))
     assert a == bset
+
+
+@pytest.mark.parametrize("n_src,n_dst,r,max_nb,excl_mode", [(5000, 700, 2.5, 1000, 0), (5000, 5000, 2.0, 1000, 2), (3000, 200, 30.0, 1000, 0),
+                                                           (4000, 300, 6.0, 24, 0), (2500, 500, 3.0, 1000, 1)])
+def test_grid_hash_equals_brute_force(cuda, n_src, n_dst, r, max_nb, excl_mode):
+    """The grid-hash kernels return element-for-element the CSR of the ordered brute-force kernel (negative coordinates,
+    truncation, exclusions, batches, and the > 1024-hit fallback at r = 30)."""
+    from diffusion_edf_b200 import ops
+    g = torch.Generator().manual_seed(n_src + n_dst)
+    x = (torch.rand(n_src, 3, generator=g) - 0.5) * 40
+    y = x[:n_dst].clone() if excl_mode == 2 else (torch.rand(n_dst, 3, generator=g) - 0.5) * 40
+    if excl_mode == 2:
+        x = y
+    bx = (torch.arange(len(x)) >= len(x) // 3).long()
+    by = (torch.arange(len(y)) >= len(y) // 3).long()
+    excl = torch.randint(0, len(x), (len(y),), generator=g) if excl_mode == 1 else None
+    kw = dict(b_src=bx.to(cuda), b_dst=by.to(cuda), excl_mode=excl_mode, excl=None if excl is None else excl.to(cuda), max_num_neighbors=max_nb)
+    old = ops.GRID_MIN_SOURCES
+    try:
+        ops.GRID_MIN_SOURCES = 1 << 30
+        brute = ops.radius_csr(x.to(cuda), y.to(cuda), [r], **kw)
+        ops.GRID_MIN_SOURCES = 1
+        grid = ops.radius_csr(x.to(cuda), y.to(cuda), [r], **kw)
+    finally:
+        ops.GRID_MIN_SOURCES = old
+    assert grid.n_edges == brute.n_edges and brute.n_edges > 0
+    assert torch.equal(grid.row_ptr, brute.row_ptr)
+    assert torch.equal(grid.edge_src, brute.edge_src) and torch.equal(grid.edge_dst, brute.edge_dst)
