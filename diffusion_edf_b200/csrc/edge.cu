@@ -282,7 +282,7 @@ struct TpLinCfg {
 };
 
 template <int G, int EPI>
-__global__ void __launch_bounds__(TpLinCfg<G, EPI>::THREADS)
+__global__ void __launch_bounds__(TpLinCfg<G, EPI>::THREADS, 2)
 edge_tp_lin_kernel(TpLinArgs a, int lda0, int lda1, int lda2) {
     using C = TpLinCfg<G, EPI>;
     using D = Dtp<G>;

@@ -9,6 +9,7 @@
 // Index results are bit-exact against oracle/graph.py: squared distances are
 // evaluated as (dx*dx + dy*dy) + dz*dz with no FMA contraction.
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include "../../include/dedf.h"
 
 namespace dedf {
@@ -78,6 +79,78 @@ fps_kernel(const float* __restrict__ x, int n, int m, int start, const long long
         const unsigned gm = __reduce_max_sync(0xffffffffu, v);
         cur = __reduce_min_sync(0xffffffffu, (v == gm) ? s_idx[buf][lane] : 0x7fffffff);
     }
+}
+
+// Cluster variant for the large scales: 8 CTAs (8 SMs, one thread-block cluster) split the points, so the per-iteration
+// distance update shrinks 8x; every CTA keeps a full shared-memory copy of the cloud (winner coordinates need no
+// communication) and the per-CTA candidates are exchanged through distributed shared memory: one remote store per peer and
+// ONE cluster barrier per iteration (double-buffered slots).  Same arithmetic and tie-breaking as the single-CTA kernel.
+constexpr int kFpsClusterSize = 8;
+constexpr int kFpsClusterThreads = 512;
+
+template <int PT>
+__global__ void __launch_bounds__(kFpsClusterThreads, 1)
+fps_cluster_kernel(const float* __restrict__ x, int n, int m, int start, const long long* __restrict__ start_dev, int idx_base,
+                   long long* __restrict__ out_idx) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ float s_pts[];
+    __shared__ unsigned s_val[2][kFpsClusterThreads / 32];
+    __shared__ int s_idx[2][kFpsClusterThreads / 32];
+    __shared__ unsigned c_val[2][kFpsClusterSize];
+    __shared__ int c_idx[2][kFpsClusterSize];
+    constexpr int NW = kFpsClusterThreads / 32, STRIDE = kFpsClusterSize * kFpsClusterThreads;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)cluster.block_rank();
+    const int gtid = rank * kFpsClusterThreads + tid;
+    for (int i = tid; i < 3 * n; i += kFpsClusterThreads) s_pts[i] = x[i];
+    float px[PT], py[PT], pz[PT], dist[PT];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+        const int i = gtid + j * STRIDE;
+        if (i < n) { px[j] = x[3 * i]; py[j] = x[3 * i + 1]; pz[j] = x[3 * i + 2]; dist[j] = __int_as_float(0x7f800000); }
+        else       { px[j] = py[j] = pz[j] = 0.f; dist[j] = 0.f; }
+    }
+    cluster.sync();
+    int cur = start_dev ? (int)min(max(start_dev[0], 0ll), (long long)(n - 1)) : start;
+    for (int it = 0; it < m; ++it) {
+        if (gtid == 0) out_idx[it] = (long long)(cur + idx_base);
+        const float cx = s_pts[3 * cur], cy = s_pts[3 * cur + 1], cz = s_pts[3 * cur + 2];
+        float bv = 0.f;
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            if (gtid + j * STRIDE < n) {
+                const float d = sqdist_exact(px[j], py[j], pz[j], cx, cy, cz);
+                dist[j] = fminf(dist[j], d);
+            }
+            bv = fmaxf(bv, dist[j]);
+        }
+        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(bv));
+        int cand = 0x7fffffff;
+        if (__float_as_uint(bv) == wm) {
+#pragma unroll
+            for (int j = PT - 1; j >= 0; --j)
+                if (__float_as_uint(dist[j]) == wm) cand = gtid + j * STRIDE;
+        }
+        const int wi = __reduce_min_sync(0xffffffffu, cand);
+        const int buf = it & 1;
+        if (lane == 0) { s_val[buf][warp] = wm; s_idx[buf][warp] = wi; }
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned v = (lane < NW) ? s_val[buf][lane] : 0u;
+            const unsigned cm = __reduce_max_sync(0xffffffffu, v);
+            const int ci = __reduce_min_sync(0xffffffffu, (lane < NW && v == cm) ? s_idx[buf][lane] : 0x7fffffff);
+            if (lane < kFpsClusterSize) {           // lane r publishes this CTA's candidate into CTA r's slot table
+                *cluster.map_shared_rank(&c_val[buf][rank], lane) = cm;
+                *cluster.map_shared_rank(&c_idx[buf][rank], lane) = ci;
+            }
+        }
+        cluster.sync();
+        const unsigned v = (lane < kFpsClusterSize) ? c_val[buf][lane] : 0u;
+        const unsigned gm = __reduce_max_sync(0xffffffffu, v);
+        cur = __reduce_min_sync(0xffffffffu, (lane < kFpsClusterSize && v == gm) ? c_idx[buf][lane] : 0x7fffffff);
+    }
+    cluster.sync();     // no CTA may exit while a peer could still write into its shared memory
 }
 
 // fallback for very large clouds: running distances in global scratch
@@ -397,8 +470,33 @@ using namespace dedf;
 extern "C" int dedf_fps(const float* x, int n, int m, int start, const long long* start_dev, int idx_base, long long* out_idx,
                         float* scratch_dist, cudaStream_t stream) {
     if (!x || !out_idx || n <= 0 || m <= 0 || m > n || start < 0 || start >= n) return DEDF_ERR_ARG;
-    const int pt = (n + kFpsThreads - 1) / kFpsThreads;
     const size_t smem = (size_t)3 * n * sizeof(float);
+    if (n >= 4096 && n <= 16384) {
+        // cluster launch: 8 CTAs x 512 threads
+        const int ptc = (n + kFpsClusterSize * kFpsClusterThreads - 1) / (kFpsClusterSize * kFpsClusterThreads);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(kFpsClusterSize); cfg.blockDim = dim3(kFpsClusterThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kFpsClusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t err;
+#define DEDF_FPSC_CASE(PT)                                                                                             \
+        {                                                                                                              \
+            static bool done = false;                                                                                  \
+            if (!done) { cudaFuncSetAttribute(fps_cluster_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done = true; } \
+            err = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PT>, x, n, m, start, start_dev, idx_base, out_idx);      \
+        }
+        if (ptc <= 1) DEDF_FPSC_CASE(1)
+        else if (ptc <= 2) DEDF_FPSC_CASE(2)
+        else if (ptc <= 3) DEDF_FPSC_CASE(3)
+        else DEDF_FPSC_CASE(4)
+#undef DEDF_FPSC_CASE
+        if (err != cudaSuccess) return DEDF_ERR_LAUNCH;
+        DEDF_CHECK_LAUNCH();
+        return DEDF_OK;
+    }
+    const int pt = (n + kFpsThreads - 1) / kFpsThreads;
 #define DEDF_FPS_CASE(PT)                                                                                          \
     {                                                                                                              \
         static bool done = false;                                                                                  \

@@ -106,3 +106,27 @@ def sharded_forward(model, Ts_local: torch.Tensor, time_local: torch.Tensor, key
         keys, query = None, None
     keys, query = broadcast_scene_field(keys, query, src=src, device=Ts_local.device, sizes=sizes)
     return model.score_head(Ts=Ts_local, key_pcd_multiscale=keys, query_pcd=query, time=time_local)
+
+
+def sharded_sample(model, T_seed: torch.Tensor, key_pcd: Optional[FeaturedPoints], query_pcd: Optional[FeaturedPoints],
+                   src: int = 0, gather: bool = True, **sample_kwargs) -> torch.Tensor:
+    """``ScoreModelBase.sample`` with the seeds sharded over the ranks (BASELINE config C3): rank ``src`` encodes the scene
+    and the query points, ONE broadcast ships the packed field, every rank denoises its contiguous chunk of ``T_seed`` with
+    its own Philox stream (zero collectives per diffusion step), ONE all-gather returns the trajectories (steps+2, nT, 7)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if rank == src:
+        keys = model.get_key_pcd_multiscale(key_pcd)
+        query = model.get_query_pcd(query_pcd)
+        query = FeaturedPoints(query.x.detach(), query.f.detach(), query.b, query.w.detach())
+    else:
+        keys, query = None, None
+    if world > 1:
+        keys, query = broadcast_scene_field(keys, query, src=src, device=T_seed.device)
+    lo, hi = shard_range(T_seed.shape[0], rank, world)
+    model.sample_seed = int(getattr(model, "sample_seed", 0)) * 1000003 + rank      # independent noise per rank
+    traj = model.sample(T_seed[lo:hi].contiguous(), keys, query, **sample_kwargs)    # (S, n_local, 7)
+    if world == 1 or not gather:
+        return traj
+    rows = all_gather_rows(traj.transpose(0, 1).contiguous(), T_seed.shape[0])       # (nT, S, 7)
+    return rows.transpose(0, 1).contiguous()

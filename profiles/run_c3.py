@@ -1,0 +1,61 @@
+"""BASELINE config C3: full denoise loop (panda_mug server.yaml schedule rounded to 1000 steps) on a 10k-point scene with
+nT seeds sharded over the visible ranks.  Prints one JSON line (rank 0).
+
+    python profiles/run_c3.py [n_seeds=1024] [steps_per_schedule=500]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 profiles/run_c3.py 1024 500
+"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel, ops, parallel
+from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs
+
+n_seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+n_sub = int(sys.argv[2]) if len(sys.argv) > 2 else 500
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+torch.manual_seed(0)
+model = MultiscaleScoreModel(**model_kwargs(), deterministic=True).eval().to(dev)
+model.requires_grad_(False)
+x, rgb = make_scene(10_000, seed=0)
+T_seed, _ = make_poses(n_seeds, x, seed=0)
+key = FeaturedPoints(x.to(dev), rgb.to(dev), torch.zeros(len(x), dtype=torch.long, device=dev))
+grasp = FeaturedPoints(torch.zeros(8, 3, device=dev), torch.zeros(8, 3, device=dev), torch.zeros(8, dtype=torch.long, device=dev))
+kw = dict(diffusion_schedules=[[1.0, 0.15], [0.15, 0.09]], N_steps=[n_sub, n_sub], timesteps=[0.04, 0.04], temperatures=[1.0, 1.0],
+          log_t_schedule=True, time_exponent_temp=1.0, time_exponent_alpha=0.5)
+with torch.no_grad():
+    # warm-up: a short loop (builds kernels' attributes, allocator pools)
+    parallel.sharded_sample(model, T_seed.to(dev), key if rank == 0 else None, grasp if rank == 0 else None, gather=False,
+                            **{**kw, "N_steps": [3, 3]})
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    k0 = ops.LAUNCHES
+    t0 = time.perf_counter()
+    traj = parallel.sharded_sample(model, T_seed.to(dev), key if rank == 0 else None, grasp if rank == 0 else None, **kw)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+if world > 1:
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+if rank == 0:
+    steps = 2 * n_sub
+    assert traj.shape == (steps + 2, n_seeds, 7) and torch.isfinite(traj).all()
+    print(json.dumps({"workload": "C3: full denoise loop, scene encode + 1 broadcast + %d steps + 1 all-gather" % steps,
+                      "metric": "pose-scores/sec (nPoses x steps)", "value": n_seeds * steps / float(tt), "unit": "pose-scores/s",
+                      "n_gpus": world, "n_seeds": n_seeds, "steps": steps, "wall_s": float(tt), "ms_per_step": 1e3 * float(tt) / steps,
+                      "scaling": "strong", "gpu_launches_rank0": ops.LAUNCHES - k0,
+                      "final_quat_norm_err": float((traj[-1, :, :4].norm(dim=-1) - 1).abs().max())}))
+if world > 1:
+    dist.destroy_process_group()

@@ -9,7 +9,7 @@ from oracle import graph as OG
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n,ratio", [(1, 1.0), (7, 0.5), (100, 0.2), (1500, 0.2), (10_000, 0.2), (20_000, 0.05)])
+@pytest.mark.parametrize("n,ratio", [(1, 1.0), (7, 0.5), (100, 0.2), (1500, 0.2), (4096, 0.1), (10_000, 0.2), (16_384, 0.05), (20_000, 0.05)])
 def test_fps_bitexact(cuda, n, ratio):
     from diffusion_edf_b200 import ops
     g = torch.Generator().manual_seed(n)
