@@ -589,6 +589,7 @@ struct TpReduceArgs {
     const float* alpha;    // (E, 4)
     float* out;            // (N_dst, FOUT)
     int n_dst;
+    int task_d;            // destinations per warp task (TMA kernel), 1..16
 };
 
 template <int G>
@@ -858,12 +859,13 @@ __global__ void __launch_bounds__(kK1Warps * 32, 1) edge_tp_reduce_tma_kernel(Tp
     }
     __syncwarp();
     uint32_t phase = 0;                         // bit s = parity to wait for on stage s
-    const int n_tasks = (a.n_dst + kK1TaskD - 1) / kK1TaskD;
+    const int task_d = a.task_d;
+    const int n_tasks = (a.n_dst + task_d - 1) / task_d;
     const int gw = blockIdx.x * kK1Warps + warp, nw = gridDim.x * kK1Warps;
 
     for (int task = gw; task < n_tasks; task += nw) {
-        const int d0 = task * kK1TaskD;
-        const int nd = min(kK1TaskD, a.n_dst - d0);
+        const int d0 = task * task_d;
+        const int nd = min(task_d, a.n_dst - d0);
         const int rp_l = a.row_ptr[d0 + min(lane, nd)];
         const int e_end = __shfl_sync(0xffffffffu, rp_l, nd);
         // source-index windows (current / next 32 edges of this task's contiguous edge range)
@@ -1135,8 +1137,11 @@ static int launch_k1_tma(const TpReduceArgs& a, cudaStream_t stream) {
     const size_t smem = ((size_t)(kK1Warps * kK1Stages * 2 + 31) / 32 * 32 + (size_t)kK1Warps * ST::WARP_FLOATS) * sizeof(float);
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(edge_tp_reduce_tma_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
-    const int n_tasks = (a.n_dst + kK1TaskD - 1) / kK1TaskD;
-    edge_tp_reduce_tma_kernel<G><<<grid_for(n_tasks, kK1Warps, kNumSMs), kK1Warps * 32, smem, stream>>>(a);
+    // small graphs: shrink the per-warp task so that every warp of the 148 CTAs has work (a task is sequential)
+    TpReduceArgs b = a;
+    b.task_d = max(1, min(kK1TaskD, a.n_dst / (kNumSMs * kK1Warps * 2)));
+    const int n_tasks = (a.n_dst + b.task_d - 1) / b.task_d;
+    edge_tp_reduce_tma_kernel<G><<<grid_for(n_tasks, kK1Warps, kNumSMs), kK1Warps * 32, smem, stream>>>(b);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -1147,7 +1152,7 @@ extern "C" int dedf_edge_tp_reduce(int mul1, const float* x, const int* row_ptr,
     if (!x || !row_ptr || !edge_src || !sh || !w || !alpha || !out) return DEDF_ERR_ARG;
     if (sh_stride != 9 && sh_stride != 12) return DEDF_ERR_ARG;
     if (n_dst <= 0) return DEDF_OK;
-    TpReduceArgs a{x, row_ptr, edge_src, sh, w, alpha, out, n_dst};
+    TpReduceArgs a{x, row_ptr, edge_src, sh, w, alpha, out, n_dst, kK1TaskD};
     if (sh_stride == 12) {      // bulk-copy (TMA) pipeline: needs 16-byte rows everywhere
         if (mul1 == 32) return launch_k1_tma<32>(a, stream);
         if (mul1 == 16) return launch_k1_tma<16>(a, stream);
