@@ -7,7 +7,7 @@ from .multiscale_score_model import MultiscaleScoreModel  # noqa: F401
 from .score_head import ScoreModelHead  # noqa: F401
 from .multiscale_tensor_field import MultiscaleTensorField  # noqa: F401
 from .unet_feature_extractor import UnetFeatureExtractor  # noqa: F401
-from .keypoint_extractor import StaticKeypointModel  # noqa: F401
+from .keypoint_extractor import KeypointExtractor, StaticKeypointModel  # noqa: F401
 
 __all__ = ["FeaturedPoints", "GraphEdge", "TransformPcd", "MultiscaleScoreModel", "ScoreModelHead",
-           "MultiscaleTensorField", "UnetFeatureExtractor", "StaticKeypointModel"]
+           "MultiscaleTensorField", "UnetFeatureExtractor", "StaticKeypointModel", "KeypointExtractor"]

@@ -65,6 +65,7 @@ _PROTOS = {
     "dedf_segment_softmax_reduce": [c_fp, c_int, c_int, c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp],
     "dedf_edge_tp_reduce": [c_int, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_int, c_fp, c_fp],
     "dedf_node_linear": [c_fp, c_int, C.POINTER(c_int), C.POINTER(c_int), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_f, c_int, c_fp, c_f, c_fp, c_fp],
+    "dedf_weight_post": [c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp],
     "dedf_gather_rows": [c_fp, c_fp, c_int, c_int, c_fp, c_fp],
     "dedf_add_scale": [c_fp, c_fp, c_f, c_ll, c_fp, c_fp],
     "dedf_time_embed": [C.POINTER(TimeDesc), c_fp, c_int, c_fp, c_fp],

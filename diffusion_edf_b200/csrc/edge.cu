@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kMlpThreads) edge_mlp_kernel(MlpArgs a) {
                         const int c = 4 * cg + j;
                         float t = acc[i][j];
                         if (a.b[L]) t += a.b[L][c];
-                        if (a.mode == DEDF_MLP_IN_FIELD && L == 0 && r < rows) {
+                        if (a.mode == DEDF_MLP_IN_FIELD && L == 0 && r < rows && a.row_bias) {
                             const int rb = min(a.edge_dst[e0 + r] / a.rb_div, a.n_rb - 1);
                             t += a.row_bias[((size_t)scale * a.n_rb + rb) * N + c];
                         }
@@ -1055,8 +1055,8 @@ extern "C" int dedf_edge_mlp(const dedf_mlp_desc* d, int max_edges, cudaStream_t
     if (a.mode == DEDF_MLP_IN_ROWS) { if (!a.x_in) return DEDF_ERR_ARG; }
     else if (a.mode == DEDF_MLP_IN_RBF) { if (!a.length || !a.rbf_mean || !a.rbf_std_logit || !a.rbf_weight_logit) return DEDF_ERR_ARG; }
     else if (a.mode == DEDF_MLP_IN_FIELD) {
-        if (!a.length || !a.row_ptr || !a.edge_dst || !a.row_bias || a.n_scales < 1 || a.n_scales > DEDF_MAX_SCALES || a.rb_div < 1 || a.n_rb < 1)
-            return DEDF_ERR_ARG;
+        if (!a.length || !a.row_ptr || !a.edge_dst || a.n_scales < 1 || a.n_scales > DEDF_MAX_SCALES) return DEDF_ERR_ARG;
+        if (a.row_bias && (a.rb_div < 1 || a.n_rb < 1)) return DEDF_ERR_ARG;
         for (int s = 0; s < a.n_scales; ++s) {
             a.enc_mean[s] = d->enc_mean[s]; a.enc_std_logit[s] = d->enc_std_logit[s]; a.enc_weight_logit[s] = d->enc_weight_logit[s];
             a.enc_r[s] = d->enc_r[s]; a.pre_w[s] = d->pre_w[s];

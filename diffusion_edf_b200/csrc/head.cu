@@ -189,7 +189,7 @@ struct ScoreArgs {
     const float* key_f;                // (n_t*n_q, F): field output (second operand, 'edge_attr')
     const float* qx; const float* qw; int n_q;   // query coords (n_q,3), weights (n_q)
     Irr irr;
-    const float* Wd[2];                // dtp weights (lin, ang), flat in path order
+    const float* Wd[2];                // dtp weights (lin, ang), flat in path order, each path block TRANSPOSED to [mul2][mul1]
     const float* Wl0[2]; const float* Wl1[2]; const float* bl[2];   // lin: (D0, 1+NV), (D1, NV), bias (1+NV)
     int n_vec;                         // NV = 32
     float lin_mult;
@@ -227,17 +227,18 @@ __global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
         for (int i = tid; i < F; i += blockDim.x) { sa[i] = a.qf_rot[node * F + i]; sb[i] = a.key_f[node * F + i]; }
         for (int which = 0; which < 2; ++which) {
             __syncthreads();
-            // step 1: t_p[u][j] = sum_v W_p[u][v] b_{l2}[v][j]
+            // step 1: t_p[u][j] = sum_v W_p[u][v] b_{l2}[v][j].  The host passes W_p TRANSPOSED ([mul2][mul1]) and consecutive
+            // threads take consecutive u, so every weight load is a coalesced row segment and b[v][j] is a broadcast.
             for (int i = tid; i < toff[9]; i += blockDim.x) {
                 int p = 0;
                 while (i >= toff[p + 1]) ++p;
                 const int d2 = 2 * l2s[p] + 1;
-                const int u = (i - toff[p]) / d2, j = (i - toff[p]) % d2;
-                const float* w = a.Wd[which] + woff[p] + (size_t)u * m2s[p];
+                const int j = (i - toff[p]) / m1s[p], u = (i - toff[p]) % m1s[p];
+                const float* w = a.Wd[which] + woff[p] + u;
                 const float* b = sb + boff[l2s[p]] + j;
                 float acc = 0.f;
-                for (int v = 0; v < m2s[p]; ++v) acc = fmaf(__ldg(w + v), b[v * d2], acc);
-                st[i] = acc;
+                for (int v = 0; v < m2s[p]; ++v) acc = fmaf(__ldg(w + (size_t)v * m1s[p]), b[v * d2], acc);
+                st[toff[p] + u * d2 + j] = acc;
             }
             __syncthreads();
             // step 2: d[p][u][:] = cg(a[u], t_p[u])  ->  sd0 [112] , sd1 [192][3] in i_out order

@@ -189,6 +189,29 @@ __global__ void add_scale_kernel(const float* __restrict__ a, const float* __res
         y[i] = (a[i] + b[i]) * s;
 }
 
+// KeypointExtractor.weight_post (keypoint_extractor.py:129-134): LayerNorm -> SiLU -> Linear(D, 1) -> sigmoid (optional),
+// times an optional scalar multiplier softplus(weight_mult_logit).  One warp per node.
+__global__ void weight_post_kernel(const float* __restrict__ x, int n, int D, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                   const float* __restrict__ w, const float* __restrict__ b, int use_sigmoid,
+                                   const float* __restrict__ mult_logit, float* __restrict__ y) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+        const float* xr = x + (size_t)i * D;
+        float s = 0.f;
+        for (int c = lane; c < D; c += 32) s += xr[c];
+        const float mean = warp_sum(s) / (float)D;
+        float q = 0.f;
+        for (int c = lane; c < D; c += 32) { const float t = xr[c] - mean; q += t * t; }
+        const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-5f);
+        float acc = 0.f;
+        for (int c = lane; c < D; c += 32) acc = fmaf(siluf_((xr[c] - mean) * rstd * ln_g[c] + ln_b[c]), w[c], acc);
+        acc = warp_sum(acc) + b[0];
+        if (use_sigmoid) acc = sigmoidf_(acc);
+        if (mult_logit) { const float m = mult_logit[0]; acc *= (m > 20.f) ? m : log1pf(expf(m)); }
+        if (lane == 0) y[i] = acc;
+    }
+}
+
 }  // namespace dedf
 
 using namespace dedf;
@@ -254,6 +277,15 @@ extern "C" int dedf_add_scale(const float* a, const float* b, float s, long long
     if (!a || !b || !y) return DEDF_ERR_ARG;
     if (n <= 0) return DEDF_OK;
     add_scale_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, stream>>>(a, b, s, n, y);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_weight_post(const float* x, int n, int dim, const float* ln_g, const float* ln_b, const float* w,
+                                const float* b, int use_sigmoid, const float* mult_logit, float* y, cudaStream_t stream) {
+    if (!x || !ln_g || !ln_b || !w || !b || !y || dim <= 0) return DEDF_ERR_ARG;
+    if (n <= 0) return DEDF_OK;
+    weight_post_kernel<<<grid_for(n, 8, kNumSMs * 8), 256, 0, stream>>>(x, n, dim, ln_g, ln_b, w, b, use_sigmoid, mult_logit, y);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

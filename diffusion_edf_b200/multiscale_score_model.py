@@ -7,7 +7,7 @@ from typing import Dict, List
 import torch
 
 from .gnn_data import FeaturedPoints
-from .keypoint_extractor import StaticKeypointModel
+from .keypoint_extractor import KeypointExtractor, StaticKeypointModel
 from .score_head import ScoreModelHead
 from .score_model_base import ScoreModelBase
 from .unet_feature_extractor import UnetFeatureExtractor
@@ -21,9 +21,12 @@ class MultiscaleScoreModel(ScoreModelBase):
         if name != "UnetFeatureExtractor":
             raise NotImplementedError(f"feature extractor {name!r} (only UnetFeatureExtractor is on the CUDA path)")
         self.key_model = UnetFeatureExtractor(**key_kwargs["feature_extractor_kwargs"], deterministic=deterministic)
-        if query_model != "StaticKeypointModel":
-            raise NotImplementedError(f"query model {query_model!r} (only StaticKeypointModel is on the CUDA path)")
-        self.query_model = StaticKeypointModel(**query_kwargs)
+        if query_model == "StaticKeypointModel":
+            self.query_model = StaticKeypointModel(**query_kwargs)
+        elif query_model == "KeypointExtractor":
+            self.query_model = KeypointExtractor(**query_kwargs, deterministic=deterministic)
+        else:
+            raise ValueError(f"Unknown query model: {query_model}")
         if score_head_kwargs.get("ebm", False):
             raise NotImplementedError("EbmScoreModelHead is out of scope (SURVEY.md 8f)")
         kw = score_head_kwargs["key_tensor_field_kwargs"]

@@ -56,11 +56,10 @@ class MultiscaleTensorField(nn.Module):
         self.num_heads = num_heads
         fc_neurons = list(fc_neurons)
         self.length_emb_dim, self.context_emb_dim = length_emb_dim, edge_context_emb_dim
-        if self.context_emb_dim is None:
-            raise NotImplementedError("edge_time_encoding=False is not used by the shipped configs")
+        ctx = self.context_emb_dim or 0            # None: no context embedding (KeypointExtractor's fields)
         if fc_neurons[0] == -1:
-            fc_neurons[0] = self.length_emb_dim + self.context_emb_dim
-        assert fc_neurons[0] == self.length_emb_dim + self.context_emb_dim
+            fc_neurons[0] = self.length_emb_dim + ctx
+        assert fc_neurons[0] == self.length_emb_dim + ctx
         self.fc_neurons = fc_neurons
         self.r_cluster_multiscale = list(r_cluster_multiscale)
         self.n_scales = len(self.r_cluster_multiscale)
@@ -123,7 +122,7 @@ class MultiscaleTensorField(nn.Module):
         edge is ``edge_dst // rows_per_time`` (clamped), i.e. nQ consecutive query nodes share a pose's time."""
         if context_emb is not None:
             raise NotImplementedError("pass the time rows produced by ScoreModelHead (time_rows=...), not context_emb")
-        assert time_rows is not None
+        assert (time_rows is not None) == (self.context_emb_dim is not None)
         x_src, b_src, src_off, msg_src = sources if sources is not None else self.encode_sources(input_points_multiscale)
         xq = query_points.x.contiguous()
         radii = self.r_cluster_multiscale
@@ -133,7 +132,7 @@ class MultiscaleTensorField(nn.Module):
         length, sh, logit = ops.edge_geom(x_src, xq, g, radii=radii, src_off=src_off, ns_cut=(0.2 * ns, 1.0 * ns),
                                           want_logit=True)
         # length embedding + pre-linear (+ time rows) -> h0 ; RadialProfile -> per-edge TP weights
-        wl, _, _ = self.packed_prelinear()
+        wl, _, pre_bias = self.packed_prelinear()
         K = self.fc_neurons[0]
         E = max(1, g.n_edges)
         dev = xq.device
@@ -155,6 +154,12 @@ class MultiscaleTensorField(nn.Module):
             else:
                 d.enc_r[s] = -1.0
             d.pre_w[s] = L.ptr(wl[s])
+        if time_rows is None:
+            # without a context embedding the per-scale bias rides in row_bias (one row per scale)
+            rb = torch.stack(pre_bias, dim=0).unsqueeze(1).contiguous()      # (n_scales, 1, K)
+            keep.append(rb)
+            d.row_bias = L.ptr(rb)
+            d.n_rb, d.rb_div = 1, 1
         d.enc_max_r = float(self.length_enc_max_r) if self.length_enc_max_r is not None else 1.0
         d.enc_n = 1000.0
         half = self.length_emb_dim // 2
@@ -162,8 +167,9 @@ class MultiscaleTensorField(nn.Module):
             # SinusoidalPositionEmbeddings frequency table (radial_func.py:310-312), fp32 exp on the host
             self._sin_freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(1000.0) / (half - 1))).to(dev)
         d.enc_freq = L.ptr(self._sin_freq)
-        d.row_bias = L.ptr(time_rows)
-        d.n_rb, d.rb_div = time_rows.shape[1], rows_per_time
+        if time_rows is not None:
+            d.row_bias = L.ptr(time_rows)          # W_time t_emb + b, per pose
+            d.n_rb, d.rb_div = time_rows.shape[1], rows_per_time
         d.n_layers = 1
         d.dims[0], d.dims[1] = self.length_emb_dim, K
         d.flags[0] = 2

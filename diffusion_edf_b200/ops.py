@@ -33,7 +33,7 @@ LAUNCHES = 0
 PROFILE = None      # set to {} to collect {entry point: [(start_event, end_event), ...]}
 _KERNELS = {"dedf_grid_build": 4, "dedf_radius_grid_count": 2, "dedf_radius_grid_fill": 1, "dedf_fps": 1, "dedf_radius_count": 2, "dedf_radius_fill": 1, "dedf_edge_geom": 1, "dedf_edge_mlp": 1,
             "dedf_edge_tp_lin": 1, "dedf_segment_softmax_reduce": 1, "dedf_edge_tp_reduce": 1, "dedf_node_linear": 1,
-            "dedf_gather_rows": 1, "dedf_add_scale": 1, "dedf_time_embed": 1, "dedf_query_transform": 1, "dedf_score_tp": 1,
+            "dedf_gather_rows": 1, "dedf_weight_post": 1, "dedf_add_scale": 1, "dedf_time_embed": 1, "dedf_query_transform": 1, "dedf_score_tp": 1,
             "dedf_pose_update": 2, "dedf_sample_advance": 1}
 
 
@@ -308,6 +308,13 @@ def node_linear(x: torch.Tensor, irr_in, irr_out, W: Sequence[Optional[torch.Ten
     _call("dedf_node_linear", ptr(x), n, L.int_array(irr_in), L.int_array(irr_out), ptr(W[0]), ptr(W[1]), ptr(W[2]),
                                     ptr(bias0), ptr(ln_w), ptr(ln_b), ln_eps, 1 if gate else 0, ptr(res), res_scale, ptr(y),
                                     stream())
+    return y
+
+
+def weight_post(x: torch.Tensor, ln_g, ln_b, w, b, use_sigmoid: bool, mult_logit: Optional[torch.Tensor]) -> torch.Tensor:
+    y = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    _call("dedf_weight_post", ptr(x), x.shape[0], x.shape[1], ptr(ln_g), ptr(ln_b), ptr(w), ptr(b), 1 if use_sigmoid else 0,
+          ptr(mult_logit), ptr(y), stream())
     return y
 
 

@@ -28,6 +28,15 @@ class _ScoreTP(nn.Module):
         self.dtp = _DTP(sum(a * b for a, b in shapes), True, scales)
         d0, d1 = m0 + m1 + m2, m0 + 3 * m1 + 2 * m2
         self.lin = LinearRS(Irreps((d0, d1, 0)), Irreps((1 + n_vec, n_vec, 0)))
+        self._shapes = shapes
+
+    def packed_dtp(self) -> torch.Tensor:
+        """dtp.tp.weight with every path block transposed to [mul2][mul1] (the layout dedf_score_tp reads coalesced)."""
+        w, off, out = self.dtp.tp.weight.detach(), 0, []
+        for a, b in self._shapes:
+            out.append(w[off:off + a * b].view(a, b).t().contiguous().view(-1))
+            off += a * b
+        return torch.cat(out).contiguous()
 
 
 class ScoreModelHead(nn.Module):
@@ -103,7 +112,7 @@ class ScoreModelHead(nn.Module):
                 Wd, Wl0, Wl1, bl = [], [], [], []
                 for tp in (self.lin_vel_tp, self.ang_vel_tp):
                     (w0, w1, _), b = tp.lin.packed()
-                    Wd.append(tp.dtp.tp.weight.detach().contiguous()); Wl0.append(w0); Wl1.append(w1); bl.append(b)
+                    Wd.append(tp.packed_dtp()); Wl0.append(w0); Wl1.append(w1); bl.append(b)
             self._tp_cache = (key, (Wd, Wl0, Wl1, bl))
         return self._tp_cache[1]
 

@@ -98,7 +98,11 @@ class ScoreModelBase(nn.Module):
                              float(temperatures[n]) * (t ** time_exponent_temp)])
         if noise is not None:
             noise = noise.to(torch.float64).contiguous()
-        if not self.use_cuda_graph:
+        n_q = grasp_pcd.x.shape[0]
+        cap = nT * n_q * sum(min(p.x.shape[0], 1000) for p in scene_pcd_multiscale)      # worst-case edge count
+        # the graph path pre-sizes every edge buffer for the worst case (~4.5 KB per edge, twice: warm-up + graph pool)
+        fits = 2 * cap * 4500 < 0.5 * torch.cuda.mem_get_info(dev)[0]
+        if not (self.use_cuda_graph and fits):
             for step, (t, a_ang, a_lin, temperature) in enumerate(rows):
                 time = torch.full((1,), t, dtype=torch.float32, device=dev)
                 ang, lin = self.score_head(Ts=T32, key_pcd_multiscale=scene_pcd_multiscale, query_pcd=grasp_pcd, time=time,
@@ -115,9 +119,6 @@ class ScoreModelBase(nn.Module):
         counter = torch.zeros(1, dtype=torch.int32, device=dev)
         time_cur = torch.zeros(1, dtype=torch.float32, device=dev)
         cur_row = torch.zeros(4, dtype=torch.float64, device=dev)
-        n_q = grasp_pcd.x.shape[0]
-        cap = nT * n_q * sum(min(p.x.shape[0], 1000) for p in scene_pcd_multiscale)
-
         def one_step():
             ops.sample_advance(sched, counter, time_cur, cur_row)
             ang, lin = self.score_head(Ts=T32, key_pcd_multiscale=scene_pcd_multiscale, query_pcd=grasp_pcd, time=time_cur,

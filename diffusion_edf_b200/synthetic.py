@@ -45,6 +45,25 @@ def model_kwargs() -> Dict:
     return copy.deepcopy(PANDA_MUG_PICK_LOWRES)
 
 
+def model_kwargs_place() -> Dict:
+    """model_kwargs of configs/panda_mug/place_lowres/score_model_configs.yaml: same score head and key encoder as
+    pick_lowres, query model = KeypointExtractor (own UNet with pool ratio 0.25, FPS 0.1 inside a bounding box, two
+    tensor fields with radii [5, 10, 20, 40] cm and no context embedding, sigmoid weight head)."""
+    kw = copy.deepcopy(PANDA_MUG_PICK_LOWRES)
+    fe = copy.deepcopy(PANDA_MUG_PICK_LOWRES["key_kwargs"]["feature_extractor_kwargs"])
+    fe["pool_ratio"] = [0.25, 0.25, 0.25, 0.25]
+    kw["query_model"] = "KeypointExtractor"
+    kw["query_kwargs"] = {
+        "weight_activation": "sigmoid", "weight_mult": None,
+        "keypoint_kwargs": {"pool_ratio": 0.1, "weight_pre_emb_dim": 64, "bbox": [[-30.0, 30.0], [-30.0, 30.0], [8.0, 100.0]]},
+        "feature_extractor_kwargs": fe,
+        "tensor_field_kwargs": {"irreps_output": "64x0e+32x1e+16x2e", "irreps_sh": "1x0e+1x1e+1x2e", "num_heads": 4,
+                                "fc_neurons": [-1, 32, 32], "length_emb_dim": 64, "r_cluster_multiscale": [5.0, 10.0, 20.0, 40.0],
+                                "n_layers": 1, "irreps_mlp_mid": 3, "cutoff_method": "edge_attn"},
+    }
+    return kw
+
+
 def make_scene(n_points: int = 10_000, seed: int = 0, half_extent: float = 30.0) -> Tuple[torch.Tensor, torch.Tensor]:
     """Surface-like cloud (cm): table plane z=0 over [-h,h]^2 plus spheres / cylinders / boxes of radius 3-8 cm,
     jitter sigma 0.3 cm, 1 cm voxel average, random-subsampled / padded to exactly ``n_points``.  -> (x (N,3), rgb (N,3))"""

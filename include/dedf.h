@@ -105,7 +105,7 @@ typedef struct dedf_mlp_desc {
     float enc_max_r, enc_n;
     const float* enc_freq;         /* (dims[0]/2) sinusoidal frequencies exp(-k ln(n)/(half-1)), tabulated by the host in fp32 */
     const float* pre_w[DEDF_MAX_SCALES];   /* (dims[0], dims[1]): transposed length half of the pre-linear */
-    const float* row_bias;         /* (n_scales, n_rb, dims[1]) from dedf_time_embed */
+    const float* row_bias;         /* (n_scales, n_rb, dims[1]) from dedf_time_embed, or NULL (no context embedding: use b[0]) */
     int n_rb, rb_div;              /* row = min(edge_dst / rb_div, n_rb - 1) */
     int n_layers;
     int dims[DEDF_MLP_MAX_LAYERS + 1];
@@ -158,6 +158,10 @@ int dedf_node_linear(const float* x, int n, const int* irr_in_host, const int* i
                      const float* W1, const float* W2, const float* bias0, const float* ln_w, const float* ln_b,
                      float ln_eps, int gate, const float* res, float res_scale, float* y, cudaStream_t stream);
 
+/* KeypointExtractor.weight_post (keypoint_extractor.py:129-134, :186-190): y = act(Linear(SiLU(LayerNorm(x)))) * softplus(mult). */
+int dedf_weight_post(const float* x, int n, int dim, const float* ln_g, const float* ln_b, const float* w, const float* b,
+                     int use_sigmoid, const float* mult_logit, float* y, cudaStream_t stream);
+
 int dedf_gather_rows(const float* x, const long long* idx, int n, int F, float* y, cudaStream_t stream);
 int dedf_add_scale(const float* a, const float* b, float s, long long n, float* y, cudaStream_t stream);
 
@@ -181,7 +185,8 @@ int dedf_query_transform(const float* Ts, int n_t, const float* qx, const float*
                          float* x_out, float* f_out, cudaStream_t stream);
 
 /* lin_vel_tp / ang_vel_tp (SeparableFCTP with shared weights), Gate, mean over the vectors, rotation by q^-1,
- * orbital term and weighted sum over the query points (score_head.py:192-209).  Arrays of 2 = (lin, ang). */
+ * orbital term and weighted sum over the query points (score_head.py:192-209).  Arrays of 2 = (lin, ang).
+ * Wd: the 9 path blocks of dtp.tp.weight in creation order, each transposed to [mul2][mul1]. */
 int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, const float* key_f, const float* qx, const float* qw,
                   int n_q, const int* irr_host, const float* const* Wd_host2, const float* const* Wl0_host2,
                   const float* const* Wl1_host2, const float* const* bl_host2, int n_vec, float lin_mult,

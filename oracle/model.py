@@ -463,6 +463,48 @@ class StaticKeypointModel(nn.Module):
                               b=bu.repeat(len(self.keypoint_coords)), w=torch.sigmoid(self.keypoint_weights).repeat(n))
 
 
+class KeypointExtractor(nn.Module):
+    """keypoint_extractor.py:50-197 (UnetFeatureExtractor, sigmoid / none weight activation)."""
+
+    def __init__(self, feature_extractor_kwargs, tensor_field_kwargs, keypoint_kwargs, feature_extractor_name="UnetFeatureExtractor",
+                 weight_activation="sigmoid", weight_mult=None, deterministic=False):
+        super().__init__()
+        assert feature_extractor_name == "UnetFeatureExtractor"
+        self.pool_ratio = float(keypoint_kwargs["pool_ratio"])
+        self.keypoint_bbox = keypoint_kwargs.get("bbox", None)
+        self.weight_pre_emb_dim = int(keypoint_kwargs["weight_pre_emb_dim"])
+        self.weight_mult_logit = None if weight_mult is None else nn.Parameter(torch.log(torch.exp(torch.tensor(float(weight_mult))) - 1))
+        self.feature_extractor = UnetFeatureExtractor(**feature_extractor_kwargs, deterministic=deterministic)
+        kw = dict(tensor_field_kwargs)
+        kw.update(irreps_input=feature_extractor_kwargs["irreps_output"], irreps_query=None, edge_context_emb_dim=None)
+        self.tensor_field = MultiscaleTensorField(**kw)
+        kw["irreps_output"] = f"{self.weight_pre_emb_dim}x0e"
+        self.weight_field = MultiscaleTensorField(**kw)
+        self.weight_post = nn.Sequential(nn.LayerNorm(self.weight_pre_emb_dim), nn.SiLU(), nn.Linear(self.weight_pre_emb_dim, 1),
+                                         nn.Sigmoid() if weight_activation == "sigmoid" else nn.Identity())
+        self.irreps_output = Irreps(self.tensor_field.irreps_output)
+
+    def get_query_points(self, src: FeaturedPoints) -> FeaturedPoints:
+        x, b = src.x, src.b
+        if self.keypoint_bbox is not None:
+            bb = torch.tensor(self.keypoint_bbox, dtype=x.dtype)
+            idx = ((x >= bb[:, 0]) * (x <= bb[:, 1])).all(dim=-1).nonzero().squeeze(-1)
+            x, b = x.index_select(0, idx), b.index_select(0, idx)
+        sel = G.fps(x, b, self.pool_ratio, random_start=False)
+        x, b = x.index_select(0, sel), b.index_select(0, sel)
+        return FeaturedPoints(x=x, f=torch.empty_like(x), b=b, w=None)
+
+    def forward(self, input_points: FeaturedPoints, max_neighbors: int = 1000) -> FeaturedPoints:
+        keys = self.feature_extractor(input_points)
+        q = self.get_query_points(input_points)
+        out = self.tensor_field(query_points=q, input_points_multiscale=keys, context_emb=None, max_neighbors=max_neighbors)
+        w = self.weight_field(query_points=q, input_points_multiscale=keys, context_emb=None, max_neighbors=max_neighbors).f
+        w = self.weight_post(w).squeeze(-1)
+        if self.weight_mult_logit is not None:
+            w = w * torch.nn.functional.softplus(self.weight_mult_logit)
+        return FeaturedPoints(x=out.x, f=out.f, b=out.b, w=w)
+
+
 # ==========================================================================
 # key encoder (UNet)
 # ==========================================================================
@@ -608,8 +650,11 @@ class MultiscaleScoreModel(nn.Module):
         self.register_buffer("q_factor", torch.tensor([[-0.5, -0.5, -0.5], [0.5, -0.5, 0.5], [0.5, 0.5, -0.5], [-0.5, 0.5, 0.5]]), persistent=False)
         assert key_kwargs["feature_extractor_name"] == "UnetFeatureExtractor"
         self.key_model = UnetFeatureExtractor(**key_kwargs["feature_extractor_kwargs"], deterministic=deterministic)
-        assert query_model == "StaticKeypointModel"
-        self.query_model = StaticKeypointModel(**query_kwargs)
+        if query_model == "StaticKeypointModel":
+            self.query_model = StaticKeypointModel(**query_kwargs)
+        else:
+            assert query_model == "KeypointExtractor"
+            self.query_model = KeypointExtractor(**query_kwargs, deterministic=deterministic)
         kw = dict(score_head_kwargs["key_tensor_field_kwargs"])
         kw.update(irreps_input=self.key_model.irreps_output, use_src_point_attn=False, use_dst_point_attn=False)
         self.score_head = ScoreModelHead(max_time=float(score_head_kwargs["max_time"]),

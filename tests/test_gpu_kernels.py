@@ -371,7 +371,7 @@ def test_score_tp(cuda):
         orb = torch.cross(qx.unsqueeze(0) / 15.0, lin, dim=-1)
         lin_ref = torch.einsum("q,tqi->ti", qw, lin)
         ang_ref = torch.einsum("q,tqi->ti", qw, orb) + torch.einsum("q,tqi->ti", qw, ang)
-    Wd = [p_lin.dtp.tp.weight.detach().contiguous(), p_ang.dtp.tp.weight.detach().contiguous()]
+    Wd = [p_lin.packed_dtp(), p_ang.packed_dtp()]
     (l0, l1, _), lb = p_lin.lin.packed()
     (a0, a1, _), ab = p_ang.lin.packed()
     ang_g, lin_g = ops.score_tp(Ts.to(cuda), a.to(cuda), b.to(cuda), qx.to(cuda), qw.to(cuda), (64, 32, 16), Wd, [l0, a0], [l1, a1], [lb, ab], 32, 15.0)

@@ -264,3 +264,35 @@ def test_sample_graph_replay_equals_eager_loop(cuda):
         model.use_cuda_graph = True
         graphed = model.sample(T0.to(cuda), keys, q, **kw)
     assert (eager - graphed).abs().max() < 1e-9
+
+
+def test_place_model_with_keypoint_extractor(cuda):
+    """the place configs' query model (second UNet on the grasp cloud + bbox + FPS + two tensor fields without
+    context embedding + weight head) and a score head with many query points."""
+    from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel
+    from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs_place
+    torch.manual_seed(11)
+    oracle = OM.MultiscaleScoreModel(**model_kwargs_place(), deterministic=True).eval()
+    _perturb_zero_params(oracle)
+    model = MultiscaleScoreModel(**model_kwargs_place(), deterministic=True).eval()
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda)
+    x, rgb = make_scene(1500, seed=11, half_extent=12.0)
+    gx, grgb = make_scene(900, seed=12, half_extent=8.0)
+    gx[:, 2] += 9.0                                                  # part of the grasp cloud inside the keypoint bbox (z >= 8)
+    Ts, t = make_poses(5, x, seed=11, spread=5.0)
+    b, gb = torch.zeros(len(x), dtype=torch.long), torch.zeros(len(gx), dtype=torch.long)
+    with torch.no_grad():
+        (ang_o, lin_o), dbg_o = oracle(Ts, t, OM.FeaturedPoints(x, rgb, b), OM.FeaturedPoints(gx, grgb, gb), debug=True)
+        (ang, lin), dbg = model(Ts.to(cuda), t.to(cuda), FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)),
+                                FeaturedPoints(gx.to(cuda), grgb.to(cuda), gb.to(cuda)), debug=True)
+        qo, qg = dbg_o[1], dbg[1]
+        assert torch.equal(qo.x, qg.x.cpu()) and len(qo.x) > 10
+        assert_close(qg.f, qo.f, 5e-4, "query features")
+        assert_close(qg.w, qo.w, 5e-4, "query weights")
+        assert_close(ang, ang_o, 1e-3, "ang")
+        assert_close(lin, lin_o, 1e-3, "lin")
+        # graph path (second call replays)
+        (a2, l2), _ = model(Ts.to(cuda), t.to(cuda), FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)), FeaturedPoints(gx.to(cuda), grgb.to(cuda), gb.to(cuda)))
+        (a3, l3), _ = model(Ts.to(cuda), t.to(cuda), FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)), FeaturedPoints(gx.to(cuda), grgb.to(cuda), gb.to(cuda)))
+        assert_close(a3, ang, 1e-5, "graph replay")

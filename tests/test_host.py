@@ -137,8 +137,8 @@ def test_product_state_dict_matches_oracle_and_survey_appendix_c():
 def test_unsupported_configs_fail_loudly():
     from diffusion_edf_b200 import MultiscaleScoreModel
     from diffusion_edf_b200.synthetic import model_kwargs
-    kw = model_kwargs(); kw["query_model"] = "KeypointExtractor"
-    with pytest.raises(NotImplementedError):
+    kw = model_kwargs(); kw["query_model"] = "NoSuchModel"
+    with pytest.raises(ValueError):
         MultiscaleScoreModel(**kw)
     kw = model_kwargs(); kw["score_head_kwargs"]["ebm"] = True
     with pytest.raises(NotImplementedError):
@@ -195,3 +195,15 @@ def test_pose_sharding_gloo_world2():
         assert p.exitcode == 0
     assert abs(res[0][1] - res[1][1]) < 1e-4 and res[0][2] == res[1][2] == [20, 8, 3, 1]
     assert res[0][3] == (0, 6) and res[1][3] == (6, 11) and res[0][4] and res[1][4]
+
+
+def test_place_config_state_dict_matches_oracle():
+    from diffusion_edf_b200 import MultiscaleScoreModel
+    from diffusion_edf_b200.synthetic import model_kwargs_place
+    from oracle import model as OM
+    m = MultiscaleScoreModel(**model_kwargs_place(), deterministic=True)
+    o = OM.MultiscaleScoreModel(**model_kwargs_place(), deterministic=True)
+    sm, so = m.state_dict(), o.state_dict()
+    assert set(sm) == set(so) and all(sm[k].shape == so[k].shape for k in sm)
+    assert sm["query_model.weight_field.gnn_block_init.ffn.fctp_2.tp.weight"].shape == (192 * 64,)
+    assert sm["query_model.weight_post.2.weight"].shape == (1, 64)
