@@ -72,9 +72,12 @@ class KeypointExtractor(nn.Module):
     def get_query_points(self, src_points: FeaturedPoints) -> FeaturedPoints:
         x, b = src_points.x, src_points.b
         if self.keypoint_bbox is not None:
-            bb = torch.tensor(self.keypoint_bbox, dtype=x.dtype, device=x.device)
-            # data-dependent size: one device->host sync (recorded under a CUDA-graph plan)
-            idx = ops.plan_value(lambda: ((x >= bb[:, 0]) * (x <= bb[:, 1])).all(dim=-1).nonzero().squeeze(-1))
+            def _inside():
+                # data-dependent size: one device->host sync (recorded once under a CUDA-graph plan, which therefore assumes
+                # the grasp cloud's in-box subset is unchanged between replays -- true for a fixed grasp)
+                bb = torch.tensor(self.keypoint_bbox, dtype=x.dtype, device=x.device)
+                return ((x >= bb[:, 0]) * (x <= bb[:, 1])).all(dim=-1).nonzero().squeeze(-1)
+            idx = ops.plan_value(_inside)
             x, b = x.index_select(0, idx), b.index_select(0, idx)
         sel = ops.fps(x.contiguous(), b.contiguous(), self.pool_ratio, random_start=not self.deterministic)
         x, b = ops.gather_rows(x.contiguous(), sel), b.index_select(0, sel)
