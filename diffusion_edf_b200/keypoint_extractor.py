@@ -15,6 +15,8 @@ from .irreps import Irreps
 
 
 class StaticKeypointModel(nn.Module):
+    graph_safe = True       # forward() has no data-dependent shapes beyond the batch layout
+
     def __init__(self, keypoint_coords, irreps_output):
         super().__init__()
         kc = torch.as_tensor(keypoint_coords, dtype=torch.float32)
@@ -34,6 +36,8 @@ class StaticKeypointModel(nn.Module):
 
 
 class KeypointExtractor(nn.Module):
+    graph_safe = False      # the bbox filter selects a data-dependent subset: MultiscaleScoreModel.forward stays eager
+
     def __init__(self, feature_extractor_kwargs: Dict, tensor_field_kwargs: Dict, keypoint_kwargs: Dict,
                  feature_extractor_name: str = "UnetFeatureExtractor", weight_activation: str = "sigmoid",
                  weight_mult: Optional[float] = None, deterministic: bool = False):
@@ -72,12 +76,8 @@ class KeypointExtractor(nn.Module):
     def get_query_points(self, src_points: FeaturedPoints) -> FeaturedPoints:
         x, b = src_points.x, src_points.b
         if self.keypoint_bbox is not None:
-            def _inside():
-                # data-dependent size: one device->host sync (recorded once under a CUDA-graph plan, which therefore assumes
-                # the grasp cloud's in-box subset is unchanged between replays -- true for a fixed grasp)
-                bb = torch.tensor(self.keypoint_bbox, dtype=x.dtype, device=x.device)
-                return ((x >= bb[:, 0]) * (x <= bb[:, 1])).all(dim=-1).nonzero().squeeze(-1)
-            idx = ops.plan_value(_inside)
+            bb = torch.tensor(self.keypoint_bbox, dtype=x.dtype, device=x.device)
+            idx = ((x >= bb[:, 0]) * (x <= bb[:, 1])).all(dim=-1).nonzero().squeeze(-1)     # data-dependent size: one host sync
             x, b = x.index_select(0, idx), b.index_select(0, idx)
         sel = ops.fps(x.contiguous(), b.contiguous(), self.pool_ratio, random_start=not self.deterministic)
         x, b = ops.gather_rows(x.contiguous(), sel), b.index_select(0, sel)

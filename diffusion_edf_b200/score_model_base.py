@@ -158,7 +158,8 @@ class ScoreModelBase(nn.Module):
     def forward(self, Ts: torch.Tensor, time: torch.Tensor, key_pcd: FeaturedPoints, query_pcd: FeaturedPoints,
                 debug: bool = False):
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if self.use_cuda_graph and Ts.is_cuda and not debug and not needs_grad and not self.training:
+        graph_ok = getattr(self.query_model, "graph_safe", False)      # see graphs.py: shapes must not depend on the data
+        if self.use_cuda_graph and graph_ok and Ts.is_cuda and not debug and not needs_grad and not self.training:
             ins = [Ts.contiguous(), time.contiguous(), key_pcd.x.contiguous(), key_pcd.f.contiguous(), key_pcd.b.contiguous(),
                    query_pcd.x.contiguous(), query_pcd.f.contiguous(), query_pcd.b.contiguous()]
             key = (tuple(tuple(t.shape) for t in ins), str(Ts.device), self._param_signature())
