@@ -83,10 +83,22 @@ fps_kernel(const float* __restrict__ x, int n, int m, int start, const long long
 
 // Cluster variant for the large scales: 8 CTAs (8 SMs, one thread-block cluster) split the points, so the per-iteration
 // distance update shrinks 8x; every CTA keeps a full shared-memory copy of the cloud (winner coordinates need no
-// communication) and the per-CTA candidates are exchanged through distributed shared memory: one remote store per peer and
-// ONE cluster barrier per iteration (double-buffered slots).  Same arithmetic and tie-breaking as the single-CTA kernel.
+// communication).  Candidate exchange: every WARP publishes one 64-bit key [distance bits | ~index | iteration tag] straight
+// into the slot tables of all 8 CTAs with plain distributed-shared-memory stores; every warp then polls its own CTA's 64
+// slots until all carry this iteration's tag and reduces them.  One one-way DSMEM flight per iteration: no __syncthreads,
+// no mbarrier, no cluster barrier (a cluster.sync costs ~380 cycles and flushes L1).  Slots are double-buffered by iteration
+// parity: a peer can only write the slots of iteration it+2 after it has received this CTA's keys of iteration it+1, which
+// are sent after the slots of iteration it were read.  Same arithmetic and tie-breaking (largest distance, then lowest
+// index) as the single-CTA kernel.
 constexpr int kFpsClusterSize = 8;
-constexpr int kFpsClusterThreads = 512;
+constexpr int kFpsClusterThreads = 256;
+constexpr int kFpsTagBits = 18;                 // iteration tag; 14 bits of (complemented) index; 32 bits of distance
+constexpr int kFpsClusterMaxN = 1 << 14;
+
+__device__ __forceinline__ uint32_t fps_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t fps_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
 
 template <int PT>
 __global__ void __launch_bounds__(kFpsClusterThreads, 1)
@@ -94,15 +106,16 @@ fps_cluster_kernel(const float* __restrict__ x, int n, int m, int start, const l
                    long long* __restrict__ out_idx) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ float s_pts[];
-    __shared__ unsigned s_val[2][kFpsClusterThreads / 32];
-    __shared__ int s_idx[2][kFpsClusterThreads / 32];
-    __shared__ unsigned c_val[2][kFpsClusterSize];
-    __shared__ int c_idx[2][kFpsClusterSize];
     constexpr int NW = kFpsClusterThreads / 32, STRIDE = kFpsClusterSize * kFpsClusterThreads;
+    constexpr int NSLOT = kFpsClusterSize * NW;                     // 64 keys per iteration
+    constexpr int SPL = NSLOT / 32;                                 // slots per lane
+    constexpr unsigned long long TAG_MASK = (1ull << kFpsTagBits) - 1;
+    extern __shared__ float s_pts[];
+    __shared__ __align__(8) unsigned long long c_slot[2][NSLOT];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = (int)cluster.block_rank();
     const int gtid = rank * kFpsClusterThreads + tid;
+    for (int i = tid; i < 2 * NSLOT; i += kFpsClusterThreads) (&c_slot[0][0])[i] = TAG_MASK;          // a tag no iteration uses (m < 2^18 - 1)
     for (int i = tid; i < 3 * n; i += kFpsClusterThreads) s_pts[i] = x[i];
     float px[PT], py[PT], pz[PT], dist[PT];
 #pragma unroll
@@ -111,9 +124,15 @@ fps_cluster_kernel(const float* __restrict__ x, int n, int m, int start, const l
         if (i < n) { px[j] = x[3 * i]; py[j] = x[3 * i + 1]; pz[j] = x[3 * i + 2]; dist[j] = __int_as_float(0x7f800000); }
         else       { px[j] = py[j] = pz[j] = 0.f; dist[j] = 0.f; }
     }
-    cluster.sync();
+    // remote address of this warp's slot in CTA `lane` (lanes 0..7 publish)
+    const uint32_t peer = (uint32_t)(lane & (kFpsClusterSize - 1));
+    const uint32_t r_slot0 = fps_mapa(fps_smem_u32(&c_slot[0][rank * NW + warp]), peer);
+    const uint32_t r_slot1 = fps_mapa(fps_smem_u32(&c_slot[1][rank * NW + warp]), peer);
+    const uint32_t l_slot = fps_smem_u32(&c_slot[0][lane]);
+    cluster.sync();     // slot tables initialised and clouds staged everywhere before the first remote store
     int cur = start_dev ? (int)min(max(start_dev[0], 0ll), (long long)(n - 1)) : start;
     for (int it = 0; it < m; ++it) {
+        const int buf = it & 1;
         if (gtid == 0) out_idx[it] = (long long)(cur + idx_base);
         const float cx = s_pts[3 * cur], cy = s_pts[3 * cur + 1], cz = s_pts[3 * cur + 2];
         float bv = 0.f;
@@ -125,30 +144,44 @@ fps_cluster_kernel(const float* __restrict__ x, int n, int m, int start, const l
             }
             bv = fmaxf(bv, dist[j]);
         }
+        // distances are >= 0, so their bit patterns order like unsigned integers
         const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(bv));
-        int cand = 0x7fffffff;
+        int cand = kFpsClusterMaxN - 1;
         if (__float_as_uint(bv) == wm) {
 #pragma unroll
             for (int j = PT - 1; j >= 0; --j)
                 if (__float_as_uint(dist[j]) == wm) cand = gtid + j * STRIDE;
         }
         const int wi = __reduce_min_sync(0xffffffffu, cand);
-        const int buf = it & 1;
-        if (lane == 0) { s_val[buf][warp] = wm; s_idx[buf][warp] = wi; }
-        __syncthreads();
-        if (warp == 0) {
-            const unsigned v = (lane < NW) ? s_val[buf][lane] : 0u;
-            const unsigned cm = __reduce_max_sync(0xffffffffu, v);
-            const int ci = __reduce_min_sync(0xffffffffu, (lane < NW && v == cm) ? s_idx[buf][lane] : 0x7fffffff);
-            if (lane < kFpsClusterSize) {           // lane r publishes this CTA's candidate into CTA r's slot table
-                *cluster.map_shared_rank(&c_val[buf][rank], lane) = cm;
-                *cluster.map_shared_rank(&c_idx[buf][rank], lane) = ci;
-            }
+        // key: larger distance first, then LOWER index (stored complemented so that one max picks both), then the tag
+        const unsigned long long tag = (unsigned long long)it & TAG_MASK;
+        const unsigned long long key = ((unsigned long long)wm << 32) |
+                                       ((unsigned long long)((kFpsClusterMaxN - 1) - wi) << kFpsTagBits) | tag;
+        if (lane < kFpsClusterSize)
+            asm volatile("st.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(buf ? r_slot1 : r_slot0), "l"(key) : "memory");
+        // poll this CTA's slots (SPL per lane) for the keys of this iteration (bounded: a lost store traps, not hangs)
+        unsigned long long kmax;
+        {
+            const uint32_t a0 = l_slot + (uint32_t)buf * NSLOT * 8;
+            int spins = 0;
+            bool ok;
+            do {
+                ok = true; kmax = 0;
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) {
+                    unsigned long long k;
+                    asm volatile("ld.relaxed.cluster.shared::cta.b64 %0, [%1];" : "=l"(k) : "r"(a0 + q * 32 * 8) : "memory");
+                    ok = ok && ((k & TAG_MASK) == tag);
+                    kmax = k > kmax ? k : kmax;
+                }
+                if (++spins > (1 << 24)) __trap();
+            } while (!__all_sync(0xffffffffu, ok));
         }
-        cluster.sync();
-        const unsigned v = (lane < kFpsClusterSize) ? c_val[buf][lane] : 0u;
-        const unsigned gm = __reduce_max_sync(0xffffffffu, v);
-        cur = __reduce_min_sync(0xffffffffu, (lane < kFpsClusterSize && v == gm) ? c_idx[buf][lane] : 0x7fffffff);
+        const unsigned long long kk = kmax >> kFpsTagBits;     // [distance | ~index], 46 bits
+        const unsigned hi = (unsigned)(kk >> 14);
+        const unsigned gm = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned gl = __reduce_max_sync(0xffffffffu, (hi == gm) ? (unsigned)(kk & (kFpsClusterMaxN - 1)) : 0u);
+        cur = (kFpsClusterMaxN - 1) - (int)gl;
     }
     cluster.sync();     // no CTA may exit while a peer could still write into its shared memory
 }
@@ -472,7 +505,7 @@ extern "C" int dedf_fps(const float* x, int n, int m, int start, const long long
     if (!x || !out_idx || n <= 0 || m <= 0 || m > n || start < 0 || start >= n) return DEDF_ERR_ARG;
     const size_t smem = (size_t)3 * n * sizeof(float);
     if (n >= 4096 && n <= 16384) {
-        // cluster launch: 8 CTAs x 512 threads
+        // cluster launch: 8 CTAs x 256 threads
         const int ptc = (n + kFpsClusterSize * kFpsClusterThreads - 1) / (kFpsClusterSize * kFpsClusterThreads);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(kFpsClusterSize); cfg.blockDim = dim3(kFpsClusterThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -487,10 +520,12 @@ extern "C" int dedf_fps(const float* x, int n, int m, int start, const long long
             if (!done) { cudaFuncSetAttribute(fps_cluster_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done = true; } \
             err = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PT>, x, n, m, start, start_dev, idx_base, out_idx);      \
         }
-        if (ptc <= 1) DEDF_FPSC_CASE(1)
-        else if (ptc <= 2) DEDF_FPSC_CASE(2)
+        if (ptc <= 2) DEDF_FPSC_CASE(2)
         else if (ptc <= 3) DEDF_FPSC_CASE(3)
-        else DEDF_FPSC_CASE(4)
+        else if (ptc <= 4) DEDF_FPSC_CASE(4)
+        else if (ptc <= 5) DEDF_FPSC_CASE(5)
+        else if (ptc <= 6) DEDF_FPSC_CASE(6)
+        else DEDF_FPSC_CASE(8)
 #undef DEDF_FPSC_CASE
         if (err != cudaSuccess) return DEDF_ERR_LAUNCH;
         DEDF_CHECK_LAUNCH();
