@@ -74,6 +74,8 @@ _PROTOS = {
                       C.POINTER(c_fp), C.POINTER(c_fp), c_int, c_f, c_fp, c_fp, c_fp],
     "dedf_pose_update": [c_fp, c_int, c_fp, c_fp, c_fp, c_ull, c_ull, c_d, c_d, c_d, c_d, c_d, c_d, c_fp, c_fp, c_fp, c_fp, c_fp],
     "dedf_sample_advance": [c_fp, c_int, c_fp, c_fp, c_fp, c_fp],
+    "dedf_prefetch_l2": [c_fp, c_fp, c_int, c_fp],
+    "dedf_tc_selftest": [c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp],
     "dedf_build_arch": [],
 }
 

@@ -101,6 +101,7 @@ struct MlpArgs {
     int flags[DEDF_MLP_MAX_LAYERS];        // 1: LayerNorm, 2: SiLU
     const float* out_offset;        // added to the last layer (RadialProfile.offset), may be null
     float* out;                     // (E, K[n_layers])
+    int w_smem;                     // 1: all weight matrices are staged in shared memory by TMA bulk copies at kernel start
 };
 
 __device__ __forceinline__ float softplusf_(float x) { return (x > 20.f) ? x : log1pf(expf(x)); }
@@ -111,6 +112,26 @@ __global__ void __launch_bounds__(kMlpThreads) edge_mlp_kernel(MlpArgs a) {
     float* buf0 = smem;
     float* buf1 = smem + kMlpTE * lda;
     const int tid = threadIdx.x;
+    // ---- weights -> shared memory (TMA bulk copies, issued before anything else; waited for before the first GEMM) ----
+    __shared__ __align__(8) uint64_t wbar;
+    float* sW = buf1 + kMlpTE * lda;
+    int w_off[DEDF_MLP_MAX_LAYERS + 1];
+    bool w_pending = false;
+    if (a.w_smem) {
+        const int n_first = (a.mode == DEDF_MLP_IN_FIELD) ? a.n_scales : 1;      // FIELD: one first-layer matrix per scale
+        w_off[0] = 0;
+        w_off[1] = n_first * a.K[0] * a.K[1];
+        for (int L = 1; L < a.n_layers; ++L) w_off[L + 1] = w_off[L] + a.K[L] * a.K[L + 1];
+        if (tid == 0) {
+            mbar_init(&wbar, 1);
+            mbar_init_fence();
+            mbar_expect_tx(&wbar, (uint32_t)w_off[a.n_layers] * 4u);
+            for (int s = 0; s < n_first; ++s)
+                bulk_g2s_chunked(sW + s * a.K[0] * a.K[1], (a.mode == DEDF_MLP_IN_FIELD) ? a.pre_w[s] : a.W[0], (uint32_t)(a.K[0] * a.K[1]) * 4u, &wbar);
+            for (int L = 1; L < a.n_layers; ++L) bulk_g2s_chunked(sW + w_off[L], a.W[L], (uint32_t)(a.K[L] * a.K[L + 1]) * 4u, &wbar);
+        }
+        w_pending = true;
+    }
     const int E = *a.n_edges;
 
     // tiles: FIELD mode keeps tiles inside one scale (first layer weights differ per scale)
@@ -188,6 +209,7 @@ __global__ void __launch_bounds__(kMlpThreads) edge_mlp_kernel(MlpArgs a) {
             }
         }
         __syncthreads();
+        if (w_pending) { mbar_wait(&wbar, 0); w_pending = false; }
 
         float* in = buf0;
         float* outb = buf1;
@@ -195,11 +217,13 @@ __global__ void __launch_bounds__(kMlpThreads) edge_mlp_kernel(MlpArgs a) {
             const int K = a.K[L], N = a.K[L + 1];
             const bool last = (L == a.n_layers - 1);
             const float* W = (a.mode == DEDF_MLP_IN_FIELD && L == 0) ? a.pre_w[scale] : a.W[L];
+            if (a.w_smem) W = sW + w_off[L] + ((a.mode == DEDF_MLP_IN_FIELD && L == 0) ? scale * K * N : 0);
             const int n_rg = kMlpTE / 4, n_cg = N / 4;
             for (int item = tid; item < n_rg * n_cg; item += kMlpThreads) {
                 const int cg = item % n_cg, rg = item / n_cg;
                 float acc[4][4] = {};
-                gemm_item_4x4<true>(in, lda, n_rg, rg, W, N, 4 * cg, K, acc);
+                if (a.w_smem) gemm_item_4x4<true, true>(in, lda, n_rg, rg, W, N, 4 * cg, K, acc);
+                else gemm_item_4x4<true, false>(in, lda, n_rg, rg, W, N, 4 * cg, K, acc);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int r = rg + i * n_rg;
@@ -740,39 +764,6 @@ __global__ void __launch_bounds__(256) edge_tp_reduce_kernel(TpReduceArgs a) {
 // of P edges = [P weight rows | P gathered source-feature rows | P spherical harmonics (padded to 12) | P alphas].
 // The CG math reads only shared memory; the output row is staged and written with coalesced float4 stores.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
 constexpr int kK1Warps = 12;
 constexpr int kK1Stages = 3;
 constexpr int kK1TaskD = 16;      // destinations per warp task (row pointers live in lanes 0..16)
@@ -1073,9 +1064,20 @@ extern "C" int dedf_edge_mlp(const dedf_mlp_desc* d, int max_edges, cudaStream_t
         if ((a.flags[i] & 1) && (!a.ln_g[i] || !a.ln_b[i])) return DEDF_ERR_ARG;
     }
     a.out_offset = d->out_offset; a.out = d->out;
-    const size_t smem = (size_t)2 * kMlpTE * pad_lda(kMlpMaxW) * sizeof(float);
+    const size_t act_bytes = (size_t)2 * kMlpTE * pad_lda(kMlpMaxW) * sizeof(float);
+    // stage the weights in shared memory when they fit beside the activation buffers (all but the field's RadialProfile)
+    size_t w_floats = (size_t)((a.mode == DEDF_MLP_IN_FIELD) ? a.n_scales : 1) * a.K[0] * a.K[1];
+    for (int i = 1; i < a.n_layers; ++i) w_floats += (size_t)a.K[i] * a.K[i + 1];
+    constexpr size_t kMaxSmem = 220 * 1024;
+    bool w_ok = act_bytes + w_floats * sizeof(float) <= kMaxSmem;
+    for (int i = 0; i < a.n_layers && w_ok; ++i) {
+        if (a.mode == DEDF_MLP_IN_FIELD && i == 0) { for (int s = 0; s < a.n_scales; ++s) w_ok = w_ok && (reinterpret_cast<uintptr_t>(a.pre_w[s]) & 15) == 0; }
+        else w_ok = (reinterpret_cast<uintptr_t>(a.W[i]) & 15) == 0;
+    }
+    a.w_smem = w_ok ? 1 : 0;
+    const size_t smem = act_bytes + (w_ok ? w_floats * sizeof(float) : 0);
     static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(edge_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
+    if (!attr_done) { cudaFuncSetAttribute(edge_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem); attr_done = true; }
     const int n_tiles = (max_edges + kMlpTE - 1) / kMlpTE + DEDF_MAX_SCALES;
     edge_mlp_kernel<<<grid_for(n_tiles, 1, kNumSMs * 3), kMlpThreads, smem, stream>>>(a);
     DEDF_CHECK_LAUNCH();

@@ -29,6 +29,7 @@ struct NodeLinArgs {
     int gate;                              // 1: out.m0 = scalars + gates, gates = out.m1 + out.m2
     const float* res; float res_scale;     // y = (y + res) * res_scale   (res may be null)
     float* y;                              // (n, Fy)
+    int bulk_w;                            // weights are 16-byte aligned with sizes % 16 == 0: stage them with TMA bulk copies
 };
 
 template <bool kVecW, bool kWShared>
@@ -46,13 +47,29 @@ __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a
     // Stage the weight matrices in shared memory once per CTA (they are reused by every tile): the K loop then runs at
     // shared-memory latency instead of L2 latency, which is what bounds the small (few-tile) launches of the coarse scales.
     const float* W0 = a.W0; const float* W1 = a.W1; const float* W2 = a.W2;
+    __shared__ __align__(8) uint64_t wbar;
+    bool w_pending = false;
     if (kWShared) {
         float* sW = s_mean + ((TN + 3) & ~3);
         const int n0w = a.W0 ? a.in.m0 * a.out.m0 : 0, n1w = a.W1 ? a.in.m1 * a.out.m1 : 0, n2w = a.W2 ? a.in.m2 * a.out.m2 : 0;
         const int o1 = (n0w + 3) & ~3, o2 = o1 + ((n1w + 3) & ~3);
-        for (int i = tid; i < n0w; i += kNodeThreads) sW[i] = __ldg(a.W0 + i);
-        for (int i = tid; i < n1w; i += kNodeThreads) sW[o1 + i] = __ldg(a.W1 + i);
-        for (int i = tid; i < n2w; i += kNodeThreads) sW[o2 + i] = __ldg(a.W2 + i);
+        if (a.bulk_w) {
+            // TMA: one thread issues 1-D bulk copies of the three matrices; they land while the layer-norm statistics
+            // and the A tiles of the first tile are being prepared (waited for right before the GEMM)
+            if (tid == 0) {
+                mbar_init(&wbar, 1);
+                mbar_init_fence();
+                mbar_expect_tx(&wbar, (uint32_t)(n0w + n1w + n2w) * 4u);
+                if (n0w) bulk_g2s_chunked(sW, a.W0, (uint32_t)n0w * 4u, &wbar);
+                if (n1w) bulk_g2s_chunked(sW + o1, a.W1, (uint32_t)n1w * 4u, &wbar);
+                if (n2w) bulk_g2s_chunked(sW + o2, a.W2, (uint32_t)n2w * 4u, &wbar);
+            }
+            w_pending = true;
+        } else {
+            for (int i = tid; i < n0w; i += kNodeThreads) sW[i] = __ldg(a.W0 + i);
+            for (int i = tid; i < n1w; i += kNodeThreads) sW[o1 + i] = __ldg(a.W1 + i);
+            for (int i = tid; i < n2w; i += kNodeThreads) sW[o2 + i] = __ldg(a.W2 + i);
+        }
         if (a.W0) W0 = sW;
         if (a.W1) W1 = sW + o1;
         if (a.W2) W2 = sW + o2;
@@ -107,6 +124,7 @@ __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a
             }
         }
         __syncthreads();
+        if (w_pending) { mbar_wait(&wbar, 0); w_pending = false; }     // weights have landed (first tile only)
         // ---- block-diagonal GEMM -----------------------------------------------------
         const int cg0 = (a.out.m0 + 3) / 4, cg1 = (a.out.m1 + 3) / 4, cg2 = (a.out.m2 + 3) / 4;
         const int I0 = (a.W0 ? (TN / 4) * cg0 : 0), I1 = (a.W1 ? (3 * TN / 4) * cg1 : 0), I2 = (a.W2 ? (5 * TN / 4) * cg2 : 0);
@@ -243,6 +261,8 @@ extern "C" int dedf_node_linear(const float* x, int n, const int* irr_in, const 
                             (size_t)((a.W2 ? a.in.m2 * a.out.m2 : 0) + 3) / 4 * 4;
     constexpr size_t kMaxSmem = 220 * 1024;
     const bool wshared = (base_floats + w_floats) * sizeof(float) <= kMaxSmem;
+    auto ok16 = [](const float* p, int n) { return !p || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (n & 3) == 0); };
+    a.bulk_w = wshared && ok16(a.W0, a.in.m0 * a.out.m0) && ok16(a.W1, a.in.m1 * a.out.m1) && ok16(a.W2, a.in.m2 * a.out.m2);
     const size_t smem = (base_floats + (wshared ? w_floats : 0)) * sizeof(float);
     if (smem > kMaxSmem) return DEDF_ERR_UNSUPPORTED;
     static bool attr_done = false;

@@ -34,7 +34,7 @@ PROFILE = None      # set to {} to collect {entry point: [(start_event, end_even
 _KERNELS = {"dedf_grid_build": 4, "dedf_radius_grid_count": 2, "dedf_radius_grid_fill": 1, "dedf_fps": 1, "dedf_radius_count": 2, "dedf_radius_fill": 1, "dedf_edge_geom": 1, "dedf_edge_mlp": 1,
             "dedf_edge_tp_lin": 1, "dedf_segment_softmax_reduce": 1, "dedf_edge_tp_reduce": 1, "dedf_node_linear": 1,
             "dedf_gather_rows": 1, "dedf_weight_post": 1, "dedf_add_scale": 1, "dedf_time_embed": 1, "dedf_query_transform": 1, "dedf_score_tp": 1,
-            "dedf_pose_update": 2, "dedf_sample_advance": 1}
+            "dedf_pose_update": 2, "dedf_sample_advance": 1, "dedf_prefetch_l2": 1, "dedf_tc_selftest": 1}
 
 
 def _call(name: str, *args) -> None:
@@ -114,6 +114,31 @@ def plan_value(fn):
 
 def replaying() -> bool:
     return _PLAN is not None and _PLAN.mode == "replay"
+
+
+# ----------------------------------------------------------------------------
+# L2 weight prefetch
+# ----------------------------------------------------------------------------
+def prefetch_table(tensors: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor, int, list]:
+    """Device table (pointers, byte counts) of the given CUDA tensors for ``prefetch_l2`` (keeps the tensors alive)."""
+    ts = [t for t in tensors if t is not None and t.is_cuda and t.numel() > 0]
+    dev = ts[0].device
+    ptrs = torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64).to(dev)
+    sizes = torch.tensor([t.numel() * t.element_size() for t in ts], dtype=torch.int64).to(dev)
+    return ptrs, sizes, len(ts), ts
+
+
+def prefetch_l2(table) -> None:
+    ptrs, sizes, n, _ = table
+    _call("dedf_prefetch_l2", ptrs.data_ptr(), sizes.data_ptr(), n, stream())
+
+
+def tc_selftest(A: torch.Tensor, B: torch.Tensor, n_split: int = 3) -> torch.Tensor:
+    """D = A @ B.T on the tcgen05 tensor cores (A: (128, K), B: (N, K)); see include/dedf.h."""
+    assert A.shape[0] == 128 and A.shape[1] == B.shape[1]
+    D = torch.empty(128, B.shape[0], dtype=torch.float32, device=A.device)
+    _call("dedf_tc_selftest", ptr(A.contiguous()), ptr(B.contiguous()), B.shape[0], A.shape[1], n_split, ptr(D), stream())
+    return D
 
 
 # ----------------------------------------------------------------------------

@@ -212,6 +212,16 @@ int dedf_sample_advance(const double* sched, int n_steps, int* counter, float* t
 /* library self-description: returns the compute capability the kernels were built for (100) */
 int dedf_build_arch(void);
 
+/* Self-test of the tcgen05 path (tc.cuh): D[128,N] = A[128,K] . B[N,K]^T on the tensor cores with the accumulator in TMEM;
+ * n_split = 1: plain TF32 (10-bit mantissa), n_split = 3: 3xTF32 error-compensated split (fp32-level accuracy).
+ * N % 16 == 0, 16 <= N <= 256, K % 8 == 0.  One CTA; used by tests/test_gpu_kernels.py. */
+int dedf_tc_selftest(const float* A, const float* B, int N, int K, int n_split, float* D, cudaStream_t stream);
+
+/* Warm the L2 with the model's weights: issues prefetch.global.L2 over n device ranges (ptrs_dev[i], bytes_dev[i]).
+ * The reference has no counterpart (its ~10^3 launches per forward re-read the weights through the cache hierarchy
+ * implicitly); here the few-CTA kernels of the coarse UNet scales would otherwise pay DRAM latency per weight row. */
+int dedf_prefetch_l2(const void* const* ptrs_dev, const long long* bytes_dev, int n, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
