@@ -40,6 +40,7 @@ class MlpDesc(C.Structure):
         ("W", c_fp * MLP_MAX_LAYERS), ("b", c_fp * MLP_MAX_LAYERS),
         ("ln_g", c_fp * MLP_MAX_LAYERS), ("ln_b", c_fp * MLP_MAX_LAYERS),
         ("flags", c_int * MLP_MAX_LAYERS), ("out_offset", c_fp), ("out", c_fp),
+        ("W_tc", c_fp * MLP_MAX_LAYERS), ("pre_w_tc", c_fp),
     ]
 
 
@@ -61,6 +62,7 @@ _PROTOS = {
     "dedf_radius_grid_fill": [c_fp, c_int, c_fp, c_int, c_f, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_fp, c_fp],
     "dedf_edge_geom": [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, C.POINTER(c_int), C.POINTER(c_f), c_f, c_f, c_fp, c_fp, c_fp, c_fp],
     "dedf_edge_mlp": [C.POINTER(MlpDesc), c_int, c_fp],
+    "dedf_edge_mlp_tc": [C.POINTER(MlpDesc), c_int, c_fp],
     "dedf_edge_tp_lin": [c_int, c_int, c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp],
     "dedf_segment_softmax_reduce": [c_fp, c_int, c_int, c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp],
     "dedf_edge_tp_reduce": [c_int, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_int, c_fp, c_fp],

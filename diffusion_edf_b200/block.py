@@ -59,7 +59,10 @@ class UnetEquiformerBlock(nn.Module):
         d.rbf_cutoff, d.rbf_offset = radial.cutoff, radial.offset
         rad.fill_desc(d, 0)
         d.out = L.ptr(w)
-        ops.edge_mlp(d, g.n_edges)
+        if ops.USE_TC_MLP and d.W_tc[0]:
+            ops.edge_mlp_tc(d, g.n_edges)
+        else:
+            ops.edge_mlp(d, g.n_edges)
         attn = self.ga.attend(msg_src, msg_dst, g, sh, w, None)
         out = self.ga.proj(attn, res=f_dst)                          # node_output = node_input_dst + ga(...)
         return self.ffn(out, ln=self.norm_2, res=out)                # + ffn(norm_2(node_output))

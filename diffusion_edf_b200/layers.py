@@ -46,6 +46,35 @@ class _Packed:
         return self._val
 
 
+def pack_tc(W: torch.Tensor) -> torch.Tensor:
+    """(K, N) "in x out" fp32 weights -> the tensor-core kernel's B-operand stream (include/dedf.h, dedf_mlp_desc.W_tc):
+    tf32 hi / lo split, N blocks of <= 256 columns, 8-wide K chunks, each part chunk-major [2][Nb][4]."""
+    K, N = W.shape
+    nb = (N + 255) // 256
+    assert K % 8 == 0 and N % nb == 0
+    nbw = N // nb
+    W = W.detach().contiguous().float()
+    hi = (W.view(torch.int32) & -8192).view(torch.float32)          # clear the 13 low mantissa bits
+    parts = torch.stack([hi, W - hi])                                # (2, K, N)
+    v = parts.view(2, K // 8, 2, 4, nb, nbw)                         # [part, kc, j, r, nb, n]
+    return v.permute(4, 1, 0, 2, 5, 3).contiguous().view(-1)         # [nb, kc, part, j, n, r]
+
+
+def tc_mlp_ok(dims: Sequence[int]) -> bool:
+    """Can dedf_edge_mlp_tc run an MLP with these layer widths?"""
+    n = len(dims) - 1
+    if n < 1 or n > L.MLP_MAX_LAYERS:
+        return False
+    for i in range(n):
+        K, N = dims[i], dims[i + 1]
+        nb = (N + 255) // 256
+        if K < 8 or K % 8 or K > 128 or N < 16 or N % nb or (N // nb) % 16 or N > 512:
+            return False
+        if i < n - 1 and N > 128:
+            return False
+    return True
+
+
 class _TP(nn.Module):
     """Stands in for e3nn's o3.TensorProduct: only owns ``weight`` (key ``tp.weight``)."""
 
@@ -172,12 +201,13 @@ class RadialProfile(nn.Module):
             b = [m.bias.detach().contiguous() if m.bias is not None else None for m in lin]
             g = [m.weight.detach().contiguous() for m in lns]
             bb = [m.bias.detach().contiguous() for m in lns]
-            return W, b, g, bb, self.offset.detach().contiguous()
+            Wtc = [pack_tc(w) for w in W] if tc_mlp_ok(self.ch_list) else None
+            return W, b, g, bb, self.offset.detach().contiguous(), Wtc
         return self._packed.get(self, build)
 
     def fill_desc(self, d: L.MlpDesc, first_layer: int = 0) -> None:
         """Describe the MLP layers starting at slot ``first_layer`` of ``d`` (dims[first_layer] must be ch_list[0])."""
-        W, b, g, bb, off = self.packed()
+        W, b, g, bb, off, Wtc = self.packed()
         n = len(W)
         assert first_layer + n <= L.MLP_MAX_LAYERS
         for i in range(n):
@@ -185,6 +215,7 @@ class RadialProfile(nn.Module):
             d.dims[s] = self.ch_list[i]
             d.dims[s + 1] = self.ch_list[i + 1]
             d.W[s] = L.ptr(W[i])
+            d.W_tc[s] = L.ptr(Wtc[i]) if Wtc is not None else None
             d.b[s] = L.ptr(b[i])
             last = i == n - 1
             d.ln_g[s] = None if last else L.ptr(g[i])
@@ -193,7 +224,7 @@ class RadialProfile(nn.Module):
         d.n_layers = first_layer + n
         d.out_offset = L.ptr(off)
         # keep the packed tensors alive for as long as the descriptor is
-        d._keep = (W, b, g, bb, off)
+        d._keep = (W, b, g, bb, off, Wtc)
 
 
 class GaussianRadialBasisLayerFiniteCutoff(nn.Module):

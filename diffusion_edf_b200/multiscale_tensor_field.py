@@ -19,7 +19,7 @@ from . import ops
 from .block import EquiformerBlock
 from .gnn_data import FeaturedPoints
 from .irreps import Irreps
-from .layers import GaussianRadialBasis
+from .layers import GaussianRadialBasis, pack_tc, tc_mlp_ok
 
 
 class _GraphParser(nn.Module):
@@ -86,6 +86,7 @@ class MultiscaleTensorField(nn.Module):
                                               use_dst_point_attn=use_dst_point_attn, use_edge_weights=True)
         self.gnn_blocks = nn.ModuleList()
         self._pre_cache = (None, None)
+        self._pre_tc = None
         self._sin_freq = None
 
     # ------------------------------------------------------------------ packed params
@@ -98,6 +99,9 @@ class MultiscaleTensorField(nn.Module):
                 wl = [m[0].weight.detach()[:, :ld].t().contiguous() for m in self.edge_scalars_pre_linears]
                 wt = [m[0].weight.detach()[:, ld:].t().contiguous() for m in self.edge_scalars_pre_linears]
                 b = [m[0].bias.detach().contiguous() for m in self.edge_scalars_pre_linears]
+                # tensor-core layout of the length halves, all scales back to back (dedf_mlp_desc.pre_w_tc)
+                dims = [ld] + list(self.gnn_block_init.ga.sep_act.dtp_rad.ch_list)
+                self._pre_tc = torch.cat([pack_tc(w) for w in wl]).contiguous() if tc_mlp_ok(dims) else None
             self._pre_cache = (key, (wl, wt, b))
         return self._pre_cache[1]
 
@@ -136,7 +140,6 @@ class MultiscaleTensorField(nn.Module):
         K = self.fc_neurons[0]
         E = max(1, g.n_edges)
         dev = xq.device
-        h0 = torch.empty(E, K, dtype=torch.float32, device=dev)
         d = L.MlpDesc()
         d.mode = L.MLP_IN_FIELD
         d.n_edges_dev = L.ptr(g.n_edges_dev, torch.int32)
@@ -170,21 +173,28 @@ class MultiscaleTensorField(nn.Module):
         if time_rows is not None:
             d.row_bias = L.ptr(time_rows)          # W_time t_emb + b, per pose
             d.n_rb, d.rb_div = time_rows.shape[1], rows_per_time
-        d.n_layers = 1
         d.dims[0], d.dims[1] = self.length_emb_dim, K
         d.flags[0] = 2
-        d.out = L.ptr(h0)
-        ops.edge_mlp(d, g.n_edges)
-
         rad = self.gnn_block_init.ga.sep_act.dtp_rad
         w = torch.empty(E, self.gnn_block_init.ga.sep_act.numel, dtype=torch.float32, device=dev)
-        d2 = L.MlpDesc()
-        d2.mode = L.MLP_IN_ROWS
-        d2.n_edges_dev = L.ptr(g.n_edges_dev, torch.int32)
-        d2.x_in = L.ptr(h0)
-        rad.fill_desc(d2, 0)
-        d2.out = L.ptr(w)
-        ops.edge_mlp(d2, g.n_edges)
+        if ops.USE_TC_MLP and self._pre_tc is not None:
+            # tensor cores: pre-linear + RadialProfile in ONE launch (the (E, K) pre-linear output stays on chip)
+            rad.fill_desc(d, 1)
+            d.pre_w_tc = L.ptr(self._pre_tc)
+            d.out = L.ptr(w)
+            ops.edge_mlp_tc(d, g.n_edges)
+        else:
+            h0 = torch.empty(E, K, dtype=torch.float32, device=dev)
+            d.n_layers = 1
+            d.out = L.ptr(h0)
+            ops.edge_mlp(d, g.n_edges)
+            d2 = L.MlpDesc()
+            d2.mode = L.MLP_IN_ROWS
+            d2.n_edges_dev = L.ptr(g.n_edges_dev, torch.int32)
+            d2.x_in = L.ptr(h0)
+            rad.fill_desc(d2, 0)
+            d2.out = L.ptr(w)
+            ops.edge_mlp(d2, g.n_edges)
 
         out = self.gnn_block_init(msg_src, g, sh, w, logit)
         return FeaturedPoints(x=query_points.x, f=out, b=query_points.b, w=query_points.w)

@@ -31,7 +31,7 @@ class Csr(NamedTuple):
 GRID_MIN_SOURCES = 1024     # radius searches over at least this many sources use the grid-hash kernels
 LAUNCHES = 0
 PROFILE = None      # set to {} to collect {entry point: [(start_event, end_event), ...]}
-_KERNELS = {"dedf_grid_build": 4, "dedf_radius_grid_count": 2, "dedf_radius_grid_fill": 1, "dedf_fps": 1, "dedf_radius_count": 2, "dedf_radius_fill": 1, "dedf_edge_geom": 1, "dedf_edge_mlp": 1,
+_KERNELS = {"dedf_grid_build": 4, "dedf_radius_grid_count": 2, "dedf_radius_grid_fill": 1, "dedf_fps": 1, "dedf_radius_count": 2, "dedf_radius_fill": 1, "dedf_edge_geom": 1, "dedf_edge_mlp": 1, "dedf_edge_mlp_tc": 1,
             "dedf_edge_tp_lin": 1, "dedf_segment_softmax_reduce": 1, "dedf_edge_tp_reduce": 1, "dedf_node_linear": 1,
             "dedf_gather_rows": 1, "dedf_weight_post": 1, "dedf_add_scale": 1, "dedf_time_embed": 1, "dedf_query_transform": 1, "dedf_score_tp": 1,
             "dedf_pose_update": 2, "dedf_sample_advance": 1, "dedf_prefetch_l2": 1, "dedf_tc_selftest": 1}
@@ -286,8 +286,15 @@ def edge_geom(x_src: torch.Tensor, x_dst: torch.Tensor, g: Csr, radii: Optional[
     return length, sh, logit
 
 
+USE_TC_MLP = True       # per-edge MLPs on the tcgen05 tensor cores (3xTF32) where the layer widths allow it
+
+
 def edge_mlp(desc: L.MlpDesc, max_edges: int) -> None:
     _call("dedf_edge_mlp", C.byref(desc), max_edges, stream())
+
+
+def edge_mlp_tc(desc: L.MlpDesc, max_edges: int) -> None:
+    _call("dedf_edge_mlp_tc", C.byref(desc), max_edges, stream())
 
 
 def edge_tp_lin(mul1: int, epilogue: int, x_src: torch.Tensor, x_dst: Optional[torch.Tensor], per_edge_x: bool, g: Csr,

@@ -169,6 +169,8 @@ class ScoreModelBase(nn.Module):
             c = getattr(m, "_packed", None)
             if c is not None and getattr(c, "_val", None) is not None:
                 walk(c._val)
+            if isinstance(getattr(m, "_pre_tc", None), torch.Tensor):
+                out.append(m._pre_tc)
             for name in ("_time_cache", "_tp_cache", "_pre_cache"):      # (key, value) caches of the head / field
                 c = getattr(m, name, None)
                 if isinstance(c, tuple) and len(c) == 2 and c[1] is not None:

@@ -115,11 +115,24 @@ typedef struct dedf_mlp_desc {
     int flags[DEDF_MLP_MAX_LAYERS];           /* bit0 LayerNorm, bit1 SiLU */
     const float* out_offset;       /* RadialProfile.offset (dims[n_layers]) or NULL */
     float* out;                    /* (E, dims[n_layers]) */
+    /* tensor-core kernel only (dedf_edge_mlp_tc): weights pre-split into tf32 hi / lo parts and laid out as the MMA's B
+     * operand: per layer, for each N block nb (N <= 256: one block; else N/2) and each 8-wide K chunk kc:
+     * [hi: 2 x Nb x 4 floats | lo: same], element (n, kk) of a part at ((kk / 4) * Nb + n) * 4 + kk % 4
+     * (diffusion_edf_b200/layers.py pack_tc).  pre_w_tc: the n_scales first-layer matrices of FIELD mode, back to back. */
+    const float* W_tc[DEDF_MLP_MAX_LAYERS];
+    const float* pre_w_tc;
 } dedf_mlp_desc;
 
 /* RadialProfile MLP on the edge scalars (equiformer/radial_func.py:56-59) fused with the computation of its
  * input embedding. */
 int dedf_edge_mlp(const dedf_mlp_desc* desc_host, int max_edges, cudaStream_t stream);
+
+/* Same MLP on the tcgen05 tensor cores (kind::tf32 with the 3xTF32 hi/lo split: fp32-level accuracy), accumulator in TMEM,
+ * weights streamed by TMA bulk copies, 128 edges per tile, one edge per epilogue thread.  Modes RBF and FIELD; in FIELD
+ * mode the layers are [pre-linear (per scale, + time row bias, SiLU), RadialProfile...] in ONE launch (dims / b / ln / flags
+ * describe all of them; layer 0 uses pre_w_tc).  Needs dims[i] % 8 == 0, dims[i] <= 128 for inputs and hidden layers,
+ * output width <= 512 (split in two N blocks above 256). */
+int dedf_edge_mlp_tc(const dedf_mlp_desc* desc_host, int max_edges, cudaStream_t stream);
 
 /* gather message[src] (+ message_dst[dst]) -> DepthwiseTensorProduct 'uvu' with the 9 spherical harmonics
  * (equiformer/tensor_product_rescale.py:352-382 -> o3.TensorProduct) -> LinearRS block-diagonal linear ->
