@@ -77,14 +77,20 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
 // Tile = 128 edges = the M of one tcgen05.mma (cta_group::1); accumulator row m lives in TMEM lane m, so the thread that
 // owns edge m reads its whole output row with tcgen05.ld and does bias / LayerNorm / SiLU without any cross-thread traffic,
 // then writes the next layer's A operand (hi / lo tf32 split, chunk-major) straight back into shared memory.
-// Warp roles: warps 0-3 = one edge per thread (input embedding, epilogues, output rows); warp 4 lane 0 = weight producer
-// (TMA 1-D bulk copies of pre-packed hi/lo weight chunks into a 4-stage ring, mbarrier complete_tx); warp 5 lane 0 = MMA issuer
-// (3 tcgen05.mma per K=8 step: Ahi.Bhi + Alo.Bhi + Ahi.Blo; tcgen05.commit frees ring stages and publishes the accumulator).
+// Warp roles: warps 0-15 = 4 warpgroups; a warp may only touch TMEM lanes 32*(warp%4)..+31, so the four threads
+// (warp%4, lane) of the 4 warpgroups share edge row 32*(warp%4)+lane and split its columns (LayerNorm statistics are exchanged
+// through shared memory); warp 16 lane 0 = weight producer (TMA 1-D bulk copies of pre-packed hi/lo weight chunks into a
+// 4-stage ring, mbarrier complete_tx); warp 17 lane 0 = MMA issuer (3 tcgen05.mma per K=8 step: Ahi.Bhi + Alo.Bhi + Ahi.Blo;
+// tcgen05.commit frees ring stages and publishes the accumulator).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kTcM = 128;
 constexpr int kTcStages = 4;
-constexpr int kTcThreads = 192;
-constexpr int kTcMaxHidden = 128;      // widest hidden layer (one row lives in 128 registers during its epilogue)
+constexpr int kTcEpiWG = 4;            // epilogue warpgroups: the 4 threads with the same (warp % 4, lane) share one edge row
+constexpr int kTcEpiThreads = kTcEpiWG * kTcM;          // 512
+constexpr int kTcProdWarp = kTcEpiThreads / 32;         // warp 16: weight producer (+ TMEM alloc)
+constexpr int kTcMmaWarp = kTcProdWarp + 1;             // warp 17: MMA issuer
+constexpr int kTcThreads = kTcEpiThreads + 64;          // 576
+constexpr int kTcMaxHidden = 128;      // widest hidden layer
 
 struct MlpTcArgs {
     int mode;                          // DEDF_MLP_IN_RBF / DEDF_MLP_IN_FIELD
@@ -111,6 +117,8 @@ struct MlpTcArgs {
     int a_bytes;                       // bytes of one A operand (hi or lo) = 128 * max K * 4
     int stage_bytes;                   // ring stage size (>= widest N block * 64)
     int tmem_cols;
+    int out_cw;                        // output staging chunk width (columns)
+    long long* dbg;                    // optional (host debug): per-phase clock64() stamps of CTA 0
 };
 
 __device__ __forceinline__ int tc_nblocks(int N) { return (N + 255) / 256; }
@@ -120,13 +128,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
     unsigned char* sA_hi = smem;
     unsigned char* sA_lo = sA_hi + a.a_bytes;
     unsigned char* sB = sA_lo + a.a_bytes;
-    float* s_tab = reinterpret_cast<float*>(sB + kTcStages * a.stage_bytes);     // [n_scales][K0][3] = mean, std, weight
+    float* s_tab = reinterpret_cast<float*>(sB + kTcStages * a.stage_bytes);     // [n_scales][K0][4] = mean, 1/std, weight, -
+    float* s_freq = s_tab + (size_t)(a.mode == DEDF_MLP_IN_FIELD ? a.n_scales : 1) * a.K[0] * 4;   // [K0/2] sinusoidal frequencies
+    float* s_par = s_freq + ((a.K[0] / 2 + 3) & ~3);                               // hidden layer L: [b | ln_g | ln_b] x kTcMaxHidden
+    float* s_last = s_par + (DEDF_MLP_MAX_LAYERS - 1) * 3 * kTcMaxHidden;          // last layer: bias + offset, [N_last]
     __shared__ __align__(8) uint64_t full_bar[kTcStages], empty_bar[kTcStages], a_ready, acc_ready;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K0 = a.K[0];
     const bool field = (a.mode == DEDF_MLP_IN_FIELD);
     const int E = *a.n_edges;
+    int dbg_i = 0;
+#define TC_STAMP(tidx) do { if (a.dbg && blockIdx.x == 0 && tid == (tidx) && dbg_i < 64) a.dbg[(tidx == 0 ? 0 : (tidx == kTcProdWarp * 32 ? 64 : 128)) + dbg_i++] = clock64(); } while (0)
+    TC_STAMP(0); TC_STAMP(kTcProdWarp * 32); TC_STAMP(kTcMmaWarp * 32);
 
     // ---- tiles: FIELD mode keeps a tile inside one scale (the first layer's weights differ per scale) ----
     int n_tiles, tile_base[DEDF_MAX_SCALES + 1];
@@ -156,12 +170,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
     // ---- one-time setup ----
     if (tid == 0) {
         for (int s = 0; s < kTcStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&a_ready, kTcM);
+        mbar_init(&a_ready, kTcEpiThreads);
         mbar_init(&acc_ready, 1);
         mbar_init_fence();
     }
-    if (warp == 4) tc::tmem_alloc(&tmem_base_s, (uint32_t)a.tmem_cols);
-    if (tid < kTcM) {          // input-encoder tables
+    if (warp == kTcProdWarp) tc::tmem_alloc(&tmem_base_s, (uint32_t)a.tmem_cols);
+    if (tid < kTcM) {          // input-encoder / parameter tables
         const int ns = field ? a.n_scales : 1;
         for (int i = tid; i < ns * K0; i += kTcM) {
             const int s = i / K0, k = i % K0;
@@ -179,15 +193,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                 sd = ((sl > 20.f) ? sl : log1pf(expf(sl))) + 1e-5f;
                 wg = sigmoidf_(a.rbf_weight_logit[k]) * 4.0f;
             }
-            s_tab[i * 3] = mean; s_tab[i * 3 + 1] = sd; s_tab[i * 3 + 2] = wg;
+            s_tab[i * 4] = mean; s_tab[i * 4 + 1] = 1.0f / sd; s_tab[i * 4 + 2] = wg; s_tab[i * 4 + 3] = 0.f;
+        }
+        if (field && a.enc_freq) for (int i = tid; i < K0 / 2; i += kTcM) s_freq[i] = a.enc_freq[i];
+        for (int L = 0; L + 1 < a.n_layers; ++L) {
+            const int N = a.K[L + 1];
+            for (int c = tid; c < N; c += kTcM) {
+                s_par[(L * 3 + 0) * kTcMaxHidden + c] = a.b[L] ? a.b[L][c] : 0.f;
+                s_par[(L * 3 + 1) * kTcMaxHidden + c] = (a.flags[L] & 1) ? a.ln_g[L][c] : 1.f;
+                s_par[(L * 3 + 2) * kTcMaxHidden + c] = (a.flags[L] & 1) ? a.ln_b[L][c] : 0.f;
+            }
+        }
+        {
+            const int L = a.n_layers - 1, N = a.K[L + 1];
+            for (int c = tid; c < N; c += kTcM) s_last[c] = (a.b[L] ? a.b[L][c] : 0.f) + (a.out_offset ? a.out_offset[c] : 0.f);
         }
     }
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    TC_STAMP(0); TC_STAMP(kTcProdWarp * 32); TC_STAMP(kTcMmaWarp * 32);
 
-    if (warp == 4) {
+    if (warp == kTcProdWarp) {
         // =========================== weight producer ===========================
         if (lane == 0) {
             uint32_t st = 0, ph = 0;
@@ -198,6 +226,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                     const int NB = tc_nblocks(N), Nb = N / NB, nkc = K / 8;
                     const uint32_t bytes = (uint32_t)Nb * 64u;
                     const float* Wl = a.Wp[L] + ((field && L == 0) ? (size_t)scale * 2 * K * N : 0);
+                    TC_STAMP(kTcProdWarp * 32);
                     for (int i = 0; i < NB * nkc; ++i) {
                         tc::mbar_wait_bounded(&empty_bar[st], ph ^ 1u);
                         mbar_expect_tx(&full_bar[st], bytes);
@@ -208,7 +237,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == kTcMmaWarp) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             uint32_t st = 0, ph = 0, pa = 0;
@@ -218,8 +247,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                     const int K = a.K[L], N = a.K[L + 1];
                     const int NB = tc_nblocks(N), Nb = N / NB, nkc = K / 8;
                     const uint32_t idesc = tc::idesc_tf32(kTcM, Nb);
+                    TC_STAMP(kTcMmaWarp * 32);
                     tc::mbar_wait_bounded(&a_ready, pa); pa ^= 1u;      // A operand written, accumulator drained
                     tc::fence_after();
+                    TC_STAMP(kTcMmaWarp * 32);
                     for (int nb = 0; nb < NB; ++nb) {
                         for (int kc = 0; kc < nkc; ++kc) {
                             tc::mbar_wait_bounded(&full_bar[st], ph);
@@ -239,19 +270,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                         }
                     }
                     tc::commit(&acc_ready);
+                    TC_STAMP(kTcMmaWarp * 32);
                 }
             }
         }
         __syncwarp();
     } else {
-        // =========================== one edge per thread ===========================
-        const int m = tid;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        // =========================== epilogue warpgroups: 4 threads per edge row ===========================
+        const int wg = warp >> 2;                                   // column slice of this thread
+        const int m = ((warp & 3) << 5) | lane;                     // edge row = TMEM lane
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        float* s_red = s_last + 512;                                // [2][kTcEpiWG][kTcM] LayerNorm partial sums
         uint32_t pc = 0;
-        // input embedding of edge e of `scale` -> A operand (hi / lo)
+        auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory"); };
+        // input embedding of edge e of `scale` -> this thread's K0/4 columns of the A operand (hi / lo)
         auto gen_input = [&](int e, bool valid, int scale) {
             const float len = valid ? a.length[e] : 0.f;
-            const float* tab = s_tab + (size_t)scale * K0 * 3;
+            const float* tab = s_tab + (size_t)scale * K0 * 4;
             float xs = 0.f, dd = 0.f, cut = 1.f, nrm = 1.f;
             bool sinus = false;
             if (field) {
@@ -264,7 +299,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                 nrm = sqrtf((float)K0);
             }
             const int half = K0 / 2;
-            for (int k4 = 0; k4 < K0; k4 += 4) {
+            for (int k4 = wg * 4; k4 < K0; k4 += 4 * kTcEpiWG) {
                 float v[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -272,11 +307,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                     float t;
                     if (sinus) {
                         const int kk = (k < half) ? k : k - half;
-                        const float arg = __fmul_rn(xs, a.enc_freq[kk]);
+                        const float arg = __fmul_rn(xs, s_freq[kk]);
                         t = (k < half) ? sinf(arg) : cosf(arg);
                     } else {
-                        const float z = (dd - tab[k * 3]) / tab[k * 3 + 1];
-                        t = expf(-0.5f * z * z) * tab[k * 3 + 2];
+                        const float4 p = *reinterpret_cast<const float4*>(tab + k * 4);
+                        const float z = (dd - p.x) * p.y;
+                        t = expf(-0.5f * z * z) * p.z;
                         if (!field) t = t * cut * nrm;
                     }
                     v[j] = valid ? t : 0.f;
@@ -303,55 +339,70 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
             for (int L = 0; L < a.n_layers; ++L) {
                 const int N = a.K[L + 1];
                 const bool last = (L == a.n_layers - 1);
+                TC_STAMP(0);
                 tc::mbar_wait_bounded(&acc_ready, pc); pc ^= 1u;
                 tc::fence_after();
+                TC_STAMP(0);
                 if (!last) {
-                    float v[kTcMaxHidden];
-#pragma unroll
-                    for (int q = 0; q < kTcMaxHidden / 16; ++q) {
-                        if (q * 16 < N) {
-                            float t[16];
-                            tc::tmem_ld16(t_lane + q * 16, t);
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) v[q * 16 + j] = t[j];
-                        }
-                    }
-                    tc::fence_before();
+                    // this thread's columns [c_lo, c_lo + 16 n16): 32 per thread at N = 128, 16 at N = 64, fewer warpgroups below
+                    const int n16 = (N >= 128) ? 2 : 1;
+                    const int c_lo = wg * 16 * n16;
+                    const bool act_cols = c_lo < N;
+                    float v[32];
                     const float* rb = nullptr;
                     if (field && L == 0 && a.row_bias && valid)
                         rb = a.row_bias + ((size_t)scale * a.n_rb + min(a.edge_dst[e] / a.rb_div, a.n_rb - 1)) * N;
-                    const float* bL = a.b[L];
+                    const float* pb = s_par + (L * 3 + 0) * kTcMaxHidden;
+                    const float* pg = s_par + (L * 3 + 1) * kTcMaxHidden;
+                    const float* pbb = s_par + (L * 3 + 2) * kTcMaxHidden;
                     float s = 0.f;
 #pragma unroll
-                    for (int c = 0; c < kTcMaxHidden; ++c) {
-                        if (c < N) {
-                            float t = v[c];
-                            if (bL) t += __ldg(bL + c);
-                            if (rb) t += __ldg(rb + c);
-                            v[c] = t; s += t;
+                    for (int q = 0; q < 2; ++q) {
+                        if (q < n16 && act_cols) {
+                            float t[16];
+                            tc::tmem_ld16(t_lane + c_lo + q * 16, t);
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const int c = c_lo + q * 16 + j;
+                                const float4 b4 = *reinterpret_cast<const float4*>(pb + c);
+                                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (rb) r4 = __ldg(reinterpret_cast<const float4*>(rb + c));
+                                v[q * 16 + j] = t[j] + b4.x + r4.x; v[q * 16 + j + 1] = t[j + 1] + b4.y + r4.y;
+                                v[q * 16 + j + 2] = t[j + 2] + b4.z + r4.z; v[q * 16 + j + 3] = t[j + 3] + b4.w + r4.w;
+                                s += (v[q * 16 + j] + v[q * 16 + j + 1]) + (v[q * 16 + j + 2] + v[q * 16 + j + 3]);
+                            }
                         }
                     }
-                    if (a.flags[L] & 1) {
-                        const float mean = s / (float)N;
+                    tc::fence_before();
+                    float mean = 0.f, rstd = 1.f;
+                    const bool ln = (a.flags[L] & 1) != 0, act = (a.flags[L] & 2) != 0;
+                    if (ln) {      // two-pass statistics over the row, partial sums exchanged between the 4 threads of the row
+                        s_red[wg * kTcM + m] = act_cols ? s : 0.f;
+                        epi_sync();
+                        mean = ((s_red[m] + s_red[kTcM + m]) + (s_red[2 * kTcM + m] + s_red[3 * kTcM + m])) / (float)N;
                         float ss = 0.f;
 #pragma unroll
-                        for (int c = 0; c < kTcMaxHidden; ++c) if (c < N) { const float t = v[c] - mean; ss += t * t; }
-                        const float rstd = rsqrtf(ss / (float)N + 1e-5f);
-                        const float* g = a.ln_g[L]; const float* bb = a.ln_b[L];
-#pragma unroll
-                        for (int c = 0; c < kTcMaxHidden; ++c) if (c < N) v[c] = (v[c] - mean) * rstd * __ldg(g + c) + __ldg(bb + c);
-                    }
-                    if (a.flags[L] & 2) {
-#pragma unroll
-                        for (int c = 0; c < kTcMaxHidden; ++c) if (c < N) v[c] = siluf_(v[c]);
+                        for (int c = 0; c < 32; ++c) if (c < 16 * n16 && act_cols) { const float t = v[c] - mean; ss += t * t; }
+                        s_red[(kTcEpiWG + wg) * kTcM + m] = ss;
+                        epi_sync();
+                        const float* r2 = s_red + kTcEpiWG * kTcM;
+                        rstd = rsqrtf(((r2[m] + r2[kTcM + m]) + (r2[2 * kTcM + m] + r2[3 * kTcM + m])) / (float)N + 1e-5f);
                     }
 #pragma unroll
-                    for (int c4 = 0; c4 < kTcMaxHidden; c4 += 4) {
-                        if (c4 < N) {
+                    for (int c4 = 0; c4 < 32; c4 += 4) {
+                        if (c4 < 16 * n16 && act_cols) {
+                            const int c = c_lo + c4;
+                            float o[4] = {v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]};
+                            if (ln) {
+                                const float4 g4 = *reinterpret_cast<const float4*>(pg + c), b4 = *reinterpret_cast<const float4*>(pbb + c);
+                                o[0] = (o[0] - mean) * rstd * g4.x + b4.x; o[1] = (o[1] - mean) * rstd * g4.y + b4.y;
+                                o[2] = (o[2] - mean) * rstd * g4.z + b4.z; o[3] = (o[3] - mean) * rstd * g4.w + b4.w;
+                            }
+                            if (act) { o[0] = siluf_(o[0]); o[1] = siluf_(o[1]); o[2] = siluf_(o[2]); o[3] = siluf_(o[3]); }
                             float4 hi, lo;
-                            hi.x = tc::tf32_hi(v[c4]); hi.y = tc::tf32_hi(v[c4 + 1]); hi.z = tc::tf32_hi(v[c4 + 2]); hi.w = tc::tf32_hi(v[c4 + 3]);
-                            lo.x = v[c4] - hi.x; lo.y = v[c4 + 1] - hi.y; lo.z = v[c4 + 2] - hi.z; lo.w = v[c4 + 3] - hi.w;
-                            const uint32_t off = (uint32_t)((c4 >> 2) * kTcM + m) * 16u;
+                            hi.x = tc::tf32_hi(o[0]); hi.y = tc::tf32_hi(o[1]); hi.z = tc::tf32_hi(o[2]); hi.w = tc::tf32_hi(o[3]);
+                            lo.x = o[0] - hi.x; lo.y = o[1] - hi.y; lo.z = o[2] - hi.z; lo.w = o[3] - hi.w;
+                            const uint32_t off = (uint32_t)((c >> 2) * kTcM + m) * 16u;
                             *reinterpret_cast<float4*>(sA_hi + off) = hi;
                             *reinterpret_cast<float4*>(sA_lo + off) = lo;
                         }
@@ -359,22 +410,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                     tc::fence_async_smem();
                     tc::mbar_arrive(&a_ready);
                 } else {
-                    float* orow = a.out + (size_t)e * N;
-                    for (int c0 = 0; c0 < N; c0 += 16) {
-                        float t[16];
-                        tc::tmem_ld16(t_lane + c0, t);
-                        if (valid) {
+                    // output rows: TMEM -> registers (+ bias + offset) -> the row's slot of the staging tile (the free A buffers;
+                    // row stride CW + 4 floats: conflict-free float4 stores), 16-column chunks dealt round-robin to the 4
+                    // threads of the row -> ONE TMA bulk store per row and staging pass, issued by warpgroup 0
+                    float* s_out = reinterpret_cast<float*>(sA_hi);
+                    const int CW = a.out_cw, ldo = CW + 4;
+                    for (int cb = 0; cb < N; cb += CW) {
+                        const int cw = min(CW, N - cb);
+                        float* srow = s_out + (size_t)m * ldo;
+                        for (int c0 = wg * 16; c0 < cw; c0 += 16 * kTcEpiWG) {
+                            float t[16];
+                            tc::tmem_ld16(t_lane + cb + c0, t);
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
-                                float4 o = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
-                                if (a.b[L]) { o.x += __ldg(a.b[L] + c0 + j); o.y += __ldg(a.b[L] + c0 + j + 1); o.z += __ldg(a.b[L] + c0 + j + 2); o.w += __ldg(a.b[L] + c0 + j + 3); }
-                                if (a.out_offset) {
-                                    const float4 of = __ldg(reinterpret_cast<const float4*>(a.out_offset + c0 + j));
-                                    o.x += of.x; o.y += of.y; o.z += of.z; o.w += of.w;
-                                }
-                                *reinterpret_cast<float4*>(orow + c0 + j) = o;
+                                const float4 of = *reinterpret_cast<const float4*>(s_last + cb + c0 + j);
+                                *reinterpret_cast<float4*>(srow + c0 + j) = make_float4(t[j] + of.x, t[j + 1] + of.y, t[j + 2] + of.z, t[j + 3] + of.w);
                             }
                         }
+                        tc::fence_async_smem();
+                        epi_sync();                                   // the whole row is staged
+                        if (wg == 0) {
+                            if (valid)
+                                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                             ::"l"(a.out + (size_t)e * N + cb), "r"(smem_u32(srow)), "r"((uint32_t)cw * 4u) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        }
+                        epi_sync();                                   // staging tile reusable (next pass / next tile's input)
                     }
                     tc::fence_before();
                     // the accumulator is drained and the A buffers are free: stage the next tile's input right away
@@ -389,9 +451,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
             }
         }
     }
+    TC_STAMP(0); TC_STAMP(kTcProdWarp * 32); TC_STAMP(kTcMmaWarp * 32);
     tc::fence_before();
     __syncthreads();
-    if (warp == 4) tc::tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    if (warp == kTcProdWarp) tc::tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    TC_STAMP(0);
+#undef TC_STAMP
 }
 
 }  // namespace dedf
@@ -407,6 +472,10 @@ extern "C" int dedf_tc_selftest(const float* A, const float* B, int N, int K, in
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
+
+static long long* g_tc_dbg = nullptr;
+/* debug hook (not part of the public header): 192 x int64 device buffer receiving clock64() stamps of CTA 0 */
+extern "C" int dedf_tc_set_debug(long long* dbg) { g_tc_dbg = dbg; return DEDF_OK; }
 
 extern "C" int dedf_edge_mlp_tc(const dedf_mlp_desc* d, int max_edges, cudaStream_t stream) {
     if (max_edges <= 0) return DEDF_OK;
@@ -427,7 +496,7 @@ extern "C" int dedf_edge_mlp_tc(const dedf_mlp_desc* d, int max_edges, cudaStrea
         const int K = a.K[i], N = a.K[i + 1];
         const int NB = (N + 255) / 256;
         if (K < 8 || (K % 8) || K > 128 || N < 16 || (N % NB) || ((N / NB) % 16)) return DEDF_ERR_UNSUPPORTED;
-        if (i < d->n_layers - 1 && N > kTcMaxHidden) return DEDF_ERR_UNSUPPORTED;
+        if (i < d->n_layers - 1 && !(N == 128 || N <= 64)) return DEDF_ERR_UNSUPPORTED;     // epilogue column split
         if (NB * (N / NB) > 512) return DEDF_ERR_UNSUPPORTED;
         max_k = K > max_k ? K : max_k; max_nb = (N / NB) > max_nb ? (N / NB) : max_nb; max_n = N > max_n ? N : max_n;
         a.Wp[i] = (d->mode == DEDF_MLP_IN_FIELD && i == 0) ? d->pre_w_tc : d->W_tc[i];
@@ -448,12 +517,22 @@ extern "C" int dedf_edge_mlp_tc(const dedf_mlp_desc* d, int max_edges, cudaStrea
         }
     }
     a.out_offset = d->out_offset; a.out = d->out;
+    a.dbg = g_tc_dbg;
     a.a_bytes = kTcM * max_k * 4;
     a.stage_bytes = ((max_nb * 64) + 1023) / 1024 * 1024;
     a.tmem_cols = 32;
     while (a.tmem_cols < max_n) a.tmem_cols <<= 1;
     const int ns = (d->mode == DEDF_MLP_IN_FIELD) ? a.n_scales : 1;
-    const size_t smem = (size_t)2 * a.a_bytes + (size_t)kTcStages * a.stage_bytes + (size_t)ns * a.K[0] * 3 * sizeof(float);
+    {   // widest staging chunk (multiple of 16 columns, <= one N block) whose 128 padded rows fit in the two A buffers
+        const int n_last = a.K[a.n_layers];
+        int cw = ((2 * a.a_bytes) / (kTcM * 4) - 4) / 16 * 16;
+        if (cw > n_last) cw = n_last;
+        if (cw < 16) return DEDF_ERR_UNSUPPORTED;
+        a.out_cw = cw;
+        if (n_last > 512 || (n_last % 4)) return DEDF_ERR_UNSUPPORTED;
+    }
+    const size_t smem = (size_t)2 * a.a_bytes + (size_t)kTcStages * a.stage_bytes +
+                        ((size_t)ns * a.K[0] * 4 + ((a.K[0] / 2 + 3) & ~3) + (DEDF_MLP_MAX_LAYERS - 1) * 3 * kTcMaxHidden + 512 + 2 * kTcEpiWG * kTcM) * sizeof(float);
     if (smem > 220 * 1024) return DEDF_ERR_UNSUPPORTED;
     static bool attr_done = false;
     if (!attr_done) { cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done = true; }

@@ -70,7 +70,7 @@ def tc_mlp_ok(dims: Sequence[int]) -> bool:
         nb = (N + 255) // 256
         if K < 8 or K % 8 or K > 128 or N < 16 or N % nb or (N // nb) % 16 or N > 512:
             return False
-        if i < n - 1 and N > 128:
+        if i < n - 1 and not (N == 128 or N <= 64):
             return False
     return True
 
