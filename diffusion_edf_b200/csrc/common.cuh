@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace dedf {
 
@@ -120,6 +121,33 @@ inline int grid_for(long long work_items, int per_block, int max_blocks) {
     if (b < 1) b = 1;
     if (b > max_blocks) b = max_blocks;
     return (int)b;
+}
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// Kernels launched through launch_pdl() may start while the previous kernel of the stream is still running: everything a
+// kernel does BEFORE pdl_wait() (barrier init, TMEM allocation, TMA prefetch of weights, parameter tables) overlaps with
+// the tail of its predecessor; pdl_wait() returns once the predecessor has completed and its writes are visible.  Every
+// kernel launched this way calls pdl_wait() unconditionally in every thread before touching anything a previous kernel
+// produced (so completion stays transitive along the stream) and then pdl_launch() to let its own successor start.
+// DEDF_PDL=0 in the environment turns the attribute off (plain stream order).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DEDF_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 #define DEDF_CHECK_LAUNCH()                                         \

@@ -32,6 +32,7 @@ struct GeomArgs {
 };
 
 __global__ void __launch_bounds__(256) edge_geom_kernel(GeomArgs a) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     const int E = *a.n_edges;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
         const int s = a.edge_src[e], d = a.edge_dst[e];
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(kMlpThreads) edge_mlp_kernel(MlpArgs a) {
         }
         w_pending = true;
     }
+    pdl_wait(); pdl_launch();     // PDL: the weight copies above overlap the previous kernel's tail
     const int E = *a.n_edges;
 
     // tiles: FIELD mode keeps tiles inside one scale (first layer weights differ per scale)
@@ -308,6 +310,7 @@ struct TpLinCfg {
 template <int G, int EPI>
 __global__ void __launch_bounds__(TpLinCfg<G, EPI>::THREADS, 2)
 edge_tp_lin_kernel(TpLinArgs a, int lda0, int lda1, int lda2) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     using C = TpLinCfg<G, EPI>;
     using D = Dtp<G>;
     constexpr int TE = C::TE, P = D::P;
@@ -522,6 +525,7 @@ struct SoftmaxArgs {
 };
 
 __global__ void __launch_bounds__(128) segment_softmax_reduce_kernel(SoftmaxArgs a) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int F = a.m0 + 3 * a.m1 + 5 * a.m2;
@@ -1023,7 +1027,7 @@ extern "C" int dedf_edge_geom(const float* x_src, const float* x_dst, const int*
     a.length = length; a.sh = sh; a.logit = logit; a.ns_lo = ns_lo; a.ns_hi = ns_hi; a.n_scales = n_scales;
     for (int s = 0; s < n_scales; ++s) { a.src_off[s] = src_off ? src_off[s] : 0; a.r[s] = r ? r[s] : -1.f; }
     a.src_off[n_scales] = src_off ? src_off[n_scales] : 0x7fffffff;
-    edge_geom_kernel<<<grid_for(max_edges, 256, kNumSMs * 8), 256, 0, stream>>>(a);
+    launch_pdl(edge_geom_kernel, dim3(grid_for(max_edges, 256, kNumSMs * 8)), dim3(256), 0, stream, a);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -1079,7 +1083,7 @@ extern "C" int dedf_edge_mlp(const dedf_mlp_desc* d, int max_edges, cudaStream_t
     static bool attr_done = false;
     if (!attr_done) { cudaFuncSetAttribute(edge_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem); attr_done = true; }
     const int n_tiles = (max_edges + kMlpTE - 1) / kMlpTE + DEDF_MAX_SCALES;
-    edge_mlp_kernel<<<grid_for(n_tiles, 1, kNumSMs * 3), kMlpThreads, smem, stream>>>(a);
+    launch_pdl(edge_mlp_kernel, dim3(grid_for(n_tiles, 1, kNumSMs * 3)), dim3(kMlpThreads), smem, stream, a);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -1096,7 +1100,7 @@ static int launch_tp_lin(const TpLinArgs& a, int max_edges, cudaStream_t stream)
         attr_done = true;
     }
     const int n_tiles = (max_edges + C::TE - 1) / C::TE;
-    edge_tp_lin_kernel<G, EPI><<<grid_for(n_tiles, 1, kNumSMs * 2), C::THREADS, smem, stream>>>(a, lda0, lda1, lda2);
+    launch_pdl((edge_tp_lin_kernel<G, EPI>), dim3(grid_for(n_tiles, 1, kNumSMs * 2)), dim3(C::THREADS), smem, stream, a, lda0, lda1, lda2);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -1128,7 +1132,7 @@ extern "C" int dedf_segment_softmax_reduce(const int* row_ptr, int n_dst, int n_
     if (m0 % 4 || m1 % 4 || m2 % 4 || m0 + 3 * m1 + 5 * m2 > 256) return DEDF_ERR_UNSUPPORTED;
     if (n_dst <= 0) return DEDF_OK;
     SoftmaxArgs a{row_ptr, n_dst, n_seg, logits, val, out, m0, m1, m2};
-    segment_softmax_reduce_kernel<<<grid_for(n_dst, 4, kNumSMs * 16), 128, 0, stream>>>(a);
+    launch_pdl(segment_softmax_reduce_kernel, dim3(grid_for(n_dst, 4, kNumSMs * 16)), dim3(128), 0, stream, a);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

@@ -247,6 +247,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(256)
 radius_kernel(RadiusArgs a, int* __restrict__ counts, const int* __restrict__ row_ptr,
               int* __restrict__ edge_src, int* __restrict__ edge_dst) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const long long n_items = (long long)a.n_dst * a.n_scales;
@@ -298,6 +299,7 @@ radius_kernel(RadiusArgs a, int* __restrict__ counts, const int* __restrict__ ro
 __global__ void __launch_bounds__(1024, 1)
 exclusive_scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ row_ptr, int capacity,
                       int* __restrict__ n_edges_out, int* __restrict__ overflow) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     __shared__ int s_part[1024];
     const int tid = threadIdx.x;
     const int chunk = (n + 1023) / 1024;
@@ -346,12 +348,14 @@ __device__ __forceinline__ unsigned grid_hash(int3 c, unsigned mask) {
 }
 
 __global__ void grid_count_kernel(const float* __restrict__ x, int n, float inv_cell, unsigned mask, int* __restrict__ bucket_cnt) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         atomicAdd(bucket_cnt + grid_hash(grid_cell(x[3 * i], x[3 * i + 1], x[3 * i + 2], inv_cell), mask), 1);
 }
 
 __global__ void grid_fill_kernel(const float* __restrict__ x, int n, float inv_cell, unsigned mask, const int* __restrict__ bucket_start,
                                  int* __restrict__ bucket_fill, int* __restrict__ sorted_idx) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned b = grid_hash(grid_cell(x[3 * i], x[3 * i + 1], x[3 * i + 2], inv_cell), mask);
         sorted_idx[bucket_start[b] + atomicAdd(bucket_fill + b, 1)] = i;
@@ -362,6 +366,7 @@ __global__ void grid_fill_kernel(const float* __restrict__ x, int n, float inv_c
 // coordinates out in the same order so that the query kernel streams them
 __global__ void grid_sort_kernel(const float* __restrict__ x, int n_buckets, const int* __restrict__ bucket_start,
                                  int* __restrict__ sorted_idx, float* __restrict__ sorted_xyz) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += gridDim.x * blockDim.x) {
         const int s = bucket_start[b], e = bucket_start[b + 1];
         for (int i = s + 1; i < e; ++i) {
@@ -389,6 +394,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(kGridWarps * 32)
 radius_grid_kernel(GridArgs a, int* __restrict__ counts, const int* __restrict__ row_ptr, int* __restrict__ edge_src,
                    int* __restrict__ edge_dst) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     __shared__ int s_hits[kGridWarps][kGridMaxHits];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int* hits = s_hits[warp];
@@ -580,10 +586,10 @@ extern "C" int dedf_radius_count(const float* x_src, const float* x_dst, int n_d
     if (!counts || !row_ptr) return DEDF_ERR_ARG;
     const long long items = (long long)n_dst * n_scales;
     if (items > 0) {
-        radius_kernel<false><<<grid_for(items, 8, kNumSMs * 8), 256, 0, stream>>>(a, counts, nullptr, nullptr, nullptr);
+        launch_pdl((radius_kernel<false>), dim3(grid_for(items, 8, kNumSMs * 8)), dim3(256), 0, stream, a, counts, nullptr, nullptr, nullptr);
         DEDF_CHECK_LAUNCH();
     }
-    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(counts, (int)items, row_ptr, capacity, n_edges_out, overflow);
+    launch_pdl(exclusive_scan_kernel, dim3(1), dim3(1024), 0, stream, counts, (int)items, row_ptr, capacity, n_edges_out, overflow);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -598,7 +604,7 @@ extern "C" int dedf_radius_fill(const float* x_src, const float* x_dst, int n_ds
     if (!row_ptr || !edge_src || !edge_dst) return DEDF_ERR_ARG;
     const long long items = (long long)n_dst * n_scales;
     if (items == 0) return DEDF_OK;
-    radius_kernel<true><<<grid_for(items, 8, kNumSMs * 8), 256, 0, stream>>>(a, nullptr, row_ptr, edge_src, edge_dst);
+    launch_pdl((radius_kernel<true>), dim3(grid_for(items, 8, kNumSMs * 8)), dim3(256), 0, stream, a, nullptr, row_ptr, edge_src, edge_dst);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -626,12 +632,12 @@ extern "C" int dedf_grid_build(const float* x_src, int n_src, float r, int n_buc
     const float inv_cell = 1.0f / (r * 1.001f);
     const unsigned mask = (unsigned)(n_buckets - 1);
     cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * n_buckets, stream);
-    if (n_src > 0) { grid_count_kernel<<<grid_for(n_src, 256, kNumSMs * 8), 256, 0, stream>>>(x_src, n_src, inv_cell, mask, bucket_cnt); DEDF_CHECK_LAUNCH(); }
-    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(bucket_cnt, n_buckets, bucket_start, 0, nullptr, nullptr);
+    if (n_src > 0) { launch_pdl(grid_count_kernel, dim3(grid_for(n_src, 256, kNumSMs * 8)), dim3(256), 0, stream, x_src, n_src, inv_cell, mask, bucket_cnt); DEDF_CHECK_LAUNCH(); }
+    launch_pdl(exclusive_scan_kernel, dim3(1), dim3(1024), 0, stream, bucket_cnt, n_buckets, bucket_start, 0, nullptr, nullptr);
     DEDF_CHECK_LAUNCH();
     cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * n_buckets, stream);
-    if (n_src > 0) { grid_fill_kernel<<<grid_for(n_src, 256, kNumSMs * 8), 256, 0, stream>>>(x_src, n_src, inv_cell, mask, bucket_start, bucket_cnt, sorted_idx); DEDF_CHECK_LAUNCH(); }
-    grid_sort_kernel<<<grid_for(n_buckets, 256, kNumSMs * 8), 256, 0, stream>>>(x_src, n_buckets, bucket_start, sorted_idx, sorted_xyz);
+    if (n_src > 0) { launch_pdl(grid_fill_kernel, dim3(grid_for(n_src, 256, kNumSMs * 8)), dim3(256), 0, stream, x_src, n_src, inv_cell, mask, bucket_start, bucket_cnt, sorted_idx); DEDF_CHECK_LAUNCH(); }
+    launch_pdl(grid_sort_kernel, dim3(grid_for(n_buckets, 256, kNumSMs * 8)), dim3(256), 0, stream, x_src, n_buckets, bucket_start, sorted_idx, sorted_xyz);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -645,8 +651,8 @@ extern "C" int dedf_radius_grid_count(const float* x_src, int n_src, const float
     int rc = fill_grid_args(a, x_src, n_src, x_dst, n_dst, r, n_buckets, bucket_start, sorted_idx, sorted_xyz, b_src, b_dst, excl_mode, excl, max_nb);
     if (rc) return rc;
     if (!counts || !row_ptr) return DEDF_ERR_ARG;
-    if (n_dst > 0) { radius_grid_kernel<false><<<grid_for(n_dst, kGridWarps, kNumSMs * 4), kGridWarps * 32, 0, stream>>>(a, counts, nullptr, nullptr, nullptr); DEDF_CHECK_LAUNCH(); }
-    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(counts, n_dst, row_ptr, capacity, n_edges_out, overflow);
+    if (n_dst > 0) { launch_pdl((radius_grid_kernel<false>), dim3(grid_for(n_dst, kGridWarps, kNumSMs * 4)), dim3(kGridWarps * 32), 0, stream, a, counts, nullptr, nullptr, nullptr); DEDF_CHECK_LAUNCH(); }
+    launch_pdl(exclusive_scan_kernel, dim3(1), dim3(1024), 0, stream, counts, n_dst, row_ptr, capacity, n_edges_out, overflow);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -660,7 +666,7 @@ extern "C" int dedf_radius_grid_fill(const float* x_src, int n_src, const float*
     if (rc) return rc;
     if (!row_ptr || !edge_src || !edge_dst) return DEDF_ERR_ARG;
     if (n_dst == 0) return DEDF_OK;
-    radius_grid_kernel<true><<<grid_for(n_dst, kGridWarps, kNumSMs * 4), kGridWarps * 32, 0, stream>>>(a, nullptr, row_ptr, edge_src, edge_dst);
+    launch_pdl((radius_grid_kernel<true>), dim3(grid_for(n_dst, kGridWarps, kNumSMs * 4)), dim3(kGridWarps * 32), 0, stream, a, nullptr, row_ptr, edge_src, edge_dst);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

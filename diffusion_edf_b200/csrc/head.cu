@@ -32,6 +32,7 @@ struct TimeArgs {
 };
 
 __global__ void __launch_bounds__(128) time_embed_kernel(TimeArgs a) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     extern __shared__ float sm[];
     float* enc = sm;                 // enc_dim
     float* h = enc + a.enc_dim;      // h_dim
@@ -133,6 +134,7 @@ struct QueryArgs {
 };
 
 __global__ void __launch_bounds__(128) query_transform_kernel(QueryArgs a) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     __shared__ float sR[9], sD2[25], sq[4], st[3];
     const int t = blockIdx.x, tid = threadIdx.x;
     if (tid == 0) {
@@ -197,6 +199,7 @@ struct ScoreArgs {
 };
 
 __global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     extern __shared__ float sm[];
     const int M0 = a.irr.m0, M1 = a.irr.m1, M2 = a.irr.m2, F = a.irr.dim();
     const int D0 = M0 + M1 + M2, D1 = M0 + 3 * M1 + 2 * M2;   // 112, 192 channels
@@ -411,7 +414,7 @@ extern "C" int dedf_time_embed(const dedf_time_desc* d, const float* time, int n
         if (!a.W1[s] || !a.b1[s] || !a.W2[s] || !a.b2[s] || !a.Wp[s] || !a.bp[s]) return DEDF_ERR_ARG;
     }
     const size_t smem = (size_t)(a.enc_dim + a.h_dim + a.e_dim) * sizeof(float);
-    time_embed_kernel<<<dim3(n_t, d->n_scales), 128, smem, stream>>>(a);
+    launch_pdl(time_embed_kernel, dim3(dim3(n_t, d->n_scales)), dim3(128), smem, stream, a);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -421,7 +424,7 @@ extern "C" int dedf_query_transform(const float* Ts, int n_t, const float* qx, c
     if (!Ts || !qx || !qf || !irr || !x_out || !f_out) return DEDF_ERR_ARG;
     if (n_t <= 0 || n_q <= 0) return DEDF_OK;
     QueryArgs a{Ts, n_t, qx, qf, n_q, Irr{irr[0], irr[1], irr[2]}, x_out, f_out};
-    query_transform_kernel<<<n_t, 128, 0, stream>>>(a);
+    launch_pdl(query_transform_kernel, dim3(n_t), dim3(128), 0, stream, a);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -445,7 +448,7 @@ extern "C" int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, cons
     if (smem > 96 * 1024) return DEDF_ERR_UNSUPPORTED;
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(score_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); done = true; }
-    score_tp_kernel<<<n_t, 256, smem, stream>>>(a);
+    launch_pdl(score_tp_kernel, dim3(n_t), dim3(256), smem, stream, a);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a
         if (a.W1) W1 = sW + o1;
         if (a.W2) W2 = sW + o2;
     }
+    pdl_wait(); pdl_launch();     // PDL: the weight copies above overlap the previous kernel's tail
     const int n_tiles = (a.n + TN - 1) / TN;
     const int Fy = a.gate ? (Fout - a.out.m1 - a.out.m2) : Fout;
     const int m0s = a.gate ? (a.out.m0 - a.out.m1 - a.out.m2) : a.out.m0;   // scalars that survive the gate
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(kNodeThreads) node_linear_kernel(NodeLinArgs a
 // y[i, :] = x[idx[i], :]
 __global__ void gather_rows_kernel(const float* __restrict__ x, const long long* __restrict__ idx, int n, int F,
                                    float* __restrict__ y) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n * F; i += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(i / F), c = (int)(i % F);
         y[i] = x[(size_t)idx[r] * F + c];
@@ -203,6 +205,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, const long long*
 // y = (a + b) * s
 __global__ void add_scale_kernel(const float* __restrict__ a, const float* __restrict__ b, float s, long long n,
                                  float* __restrict__ y) {
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = (a[i] + b[i]) * s;
 }
@@ -277,10 +280,10 @@ extern "C" int dedf_node_linear(const float* x, int n, const int* irr_in, const 
     // float4 weight loads need every output multiplicity to be a multiple of 4 (true for all feature irreps)
     const bool vec = (a.out.m0 % 4 == 0) && (a.out.m1 % 4 == 0) && (a.out.m2 % 4 == 0);
     const int grid = grid_for(n_tiles, 1, kNumSMs * 2);
-    if (vec && wshared) node_linear_kernel<true, true><<<grid, kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
-    else if (vec) node_linear_kernel<true, false><<<grid, kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
-    else if (wshared) node_linear_kernel<false, true><<<grid, kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
-    else node_linear_kernel<false, false><<<grid, kNodeThreads, smem, stream>>>(a, lda0, lda1, lda2, ldo);
+    if (vec && wshared) launch_pdl((node_linear_kernel<true, true>), dim3(grid), dim3(kNodeThreads), smem, stream, a, lda0, lda1, lda2, ldo);
+    else if (vec) launch_pdl((node_linear_kernel<true, false>), dim3(grid), dim3(kNodeThreads), smem, stream, a, lda0, lda1, lda2, ldo);
+    else if (wshared) launch_pdl((node_linear_kernel<false, true>), dim3(grid), dim3(kNodeThreads), smem, stream, a, lda0, lda1, lda2, ldo);
+    else launch_pdl((node_linear_kernel<false, false>), dim3(grid), dim3(kNodeThreads), smem, stream, a, lda0, lda1, lda2, ldo);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -288,7 +291,7 @@ extern "C" int dedf_node_linear(const float* x, int n, const int* irr_in, const 
 extern "C" int dedf_gather_rows(const float* x, const long long* idx, int n, int F, float* y, cudaStream_t stream) {
     if (!x || !idx || !y || F <= 0) return DEDF_ERR_ARG;
     if (n <= 0) return DEDF_OK;
-    gather_rows_kernel<<<grid_for((long long)n * F, 256, kNumSMs * 8), 256, 0, stream>>>(x, idx, n, F, y);
+    launch_pdl(gather_rows_kernel, dim3(grid_for((long long)n * F, 256, kNumSMs * 8)), dim3(256), 0, stream, x, idx, n, F, y);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -296,7 +299,7 @@ extern "C" int dedf_gather_rows(const float* x, const long long* idx, int n, int
 extern "C" int dedf_add_scale(const float* a, const float* b, float s, long long n, float* y, cudaStream_t stream) {
     if (!a || !b || !y) return DEDF_ERR_ARG;
     if (n <= 0) return DEDF_OK;
-    add_scale_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, stream>>>(a, b, s, n, y);
+    launch_pdl(add_scale_kernel, dim3(grid_for(n, 256, kNumSMs * 8)), dim3(256), 0, stream, a, b, s, n, y);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem_base = tmem_base_s;
+
     if (tid == 0) {
         const uint32_t idesc = tc::idesc_tf32(128, N);
         for (int ks = 0; ks < K / 8; ++ks) {
@@ -137,35 +138,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K0 = a.K[0];
     const bool field = (a.mode == DEDF_MLP_IN_FIELD);
-    const int E = *a.n_edges;
     int dbg_i = 0;
 #define TC_STAMP(tidx) do { if (a.dbg && blockIdx.x == 0 && tid == (tidx) && dbg_i < 64) a.dbg[(tidx == 0 ? 0 : (tidx == kTcProdWarp * 32 ? 64 : 128)) + dbg_i++] = clock64(); } while (0)
     TC_STAMP(0); TC_STAMP(kTcProdWarp * 32); TC_STAMP(kTcMmaWarp * 32);
-
-    // ---- tiles: FIELD mode keeps a tile inside one scale (the first layer's weights differ per scale) ----
-    int n_tiles, tile_base[DEDF_MAX_SCALES + 1];
-    if (field) {
-        tile_base[0] = 0;
-        for (int s = 0; s < a.n_scales; ++s) {
-            const int es = a.row_ptr[(size_t)(s + 1) * a.n_dst] - a.row_ptr[(size_t)s * a.n_dst];
-            tile_base[s + 1] = tile_base[s] + (es + kTcM - 1) / kTcM;
-        }
-        n_tiles = tile_base[a.n_scales];
-    } else {
-        n_tiles = (E + kTcM - 1) / kTcM;
-    }
-    auto tile_range = [&](int tile, int& e0, int& e1, int& scale) {
-        scale = 0;
-        if (field) {
-            while (tile >= tile_base[scale + 1]) ++scale;
-            const int sbeg = a.row_ptr[(size_t)scale * a.n_dst], send = a.row_ptr[(size_t)(scale + 1) * a.n_dst];
-            e0 = sbeg + (tile - tile_base[scale]) * kTcM;
-            e1 = min(e0 + kTcM, send);
-        } else {
-            e0 = tile * kTcM;
-            e1 = min(e0 + kTcM, E);
-        }
-    };
 
     // ---- one-time setup ----
     if (tid == 0) {
@@ -213,6 +188,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait(); pdl_launch();     // PDL: everything above (barriers, TMEM, parameter tables) overlapped the previous kernel
+    const int E = *a.n_edges;
+    // ---- tiles: FIELD mode keeps a tile inside one scale (the first layer's weights differ per scale) ----
+    int n_tiles, tile_base[DEDF_MAX_SCALES + 1];
+    if (field) {
+        tile_base[0] = 0;
+        for (int s = 0; s < a.n_scales; ++s) {
+            const int es = a.row_ptr[(size_t)(s + 1) * a.n_dst] - a.row_ptr[(size_t)s * a.n_dst];
+            tile_base[s + 1] = tile_base[s] + (es + kTcM - 1) / kTcM;
+        }
+        n_tiles = tile_base[a.n_scales];
+    } else {
+        n_tiles = (E + kTcM - 1) / kTcM;
+    }
+    auto tile_range = [&](int tile, int& e0, int& e1, int& scale) {
+        scale = 0;
+        if (field) {
+            while (tile >= tile_base[scale + 1]) ++scale;
+            const int sbeg = a.row_ptr[(size_t)scale * a.n_dst], send = a.row_ptr[(size_t)(scale + 1) * a.n_dst];
+            e0 = sbeg + (tile - tile_base[scale]) * kTcM;
+            e1 = min(e0 + kTcM, send);
+        } else {
+            e0 = tile * kTcM;
+            e1 = min(e0 + kTcM, E);
+        }
+    };
     TC_STAMP(0); TC_STAMP(kTcProdWarp * 32); TC_STAMP(kTcMmaWarp * 32);
 
     if (warp == kTcProdWarp) {
@@ -537,7 +538,7 @@ extern "C" int dedf_edge_mlp_tc(const dedf_mlp_desc* d, int max_edges, cudaStrea
     static bool attr_done = false;
     if (!attr_done) { cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done = true; }
     const int n_tiles = (max_edges + kTcM - 1) / kTcM + DEDF_MAX_SCALES;
-    edge_mlp_tc_kernel<<<grid_for(n_tiles, 1, kNumSMs), kTcThreads, smem, stream>>>(a);
+    launch_pdl(edge_mlp_tc_kernel, dim3(grid_for(n_tiles, 1, kNumSMs)), dim3(kTcThreads), smem, stream, a);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
