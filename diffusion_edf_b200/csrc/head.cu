@@ -46,23 +46,27 @@ __global__ void __launch_bounds__(128) time_embed_kernel(TimeArgs a) {
         enc[i] = (i < half) ? sinf(arg) : cosf(arg);
     }
     __syncthreads();
-    for (int o = tid; o < a.h_dim; o += blockDim.x) {
-        float acc = a.b1[s][o];
-        for (int i = 0; i < a.enc_dim; ++i) acc = fmaf(enc[i], a.W1[s][(size_t)i * a.h_dim + o], acc);
-        h[o] = siluf_(acc);
-    }
+    // GEMVs: the weight loads of a column are independent of the accumulation chain; 8 of them are kept in flight
+    // (the launch is a handful of CTAs whose time is pure load latency otherwise)
+    auto gemv = [&](const float* __restrict__ W, const float* __restrict__ bias, const float* x, int K, int N, int o) {
+        float acc0 = bias[o], acc1 = 0.f;
+        int i = 0;
+        for (; i + 8 <= K; i += 8) {
+            float w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = __ldg(W + (size_t)(i + j) * N + o);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) { acc0 = fmaf(x[i + j], w[j], acc0); acc1 = fmaf(x[i + j + 1], w[j + 1], acc1); }
+        }
+        for (; i < K; ++i) acc0 = fmaf(x[i], __ldg(W + (size_t)i * N + o), acc0);
+        return acc0 + acc1;
+    };
+    for (int o = tid; o < a.h_dim; o += blockDim.x) h[o] = siluf_(gemv(a.W1[s], a.b1[s], enc, a.enc_dim, a.h_dim, o));
     __syncthreads();
-    for (int o = tid; o < a.e_dim; o += blockDim.x) {
-        float acc = a.b2[s][o];
-        for (int i = 0; i < a.h_dim; ++i) acc = fmaf(h[i], a.W2[s][(size_t)i * a.e_dim + o], acc);
-        e[o] = acc;
-    }
+    for (int o = tid; o < a.e_dim; o += blockDim.x) e[o] = gemv(a.W2[s], a.b2[s], h, a.h_dim, a.e_dim, o);
     __syncthreads();
-    for (int o = tid; o < a.out_dim; o += blockDim.x) {
-        float acc = a.bp[s][o];
-        for (int i = 0; i < a.e_dim; ++i) acc = fmaf(e[i], a.Wp[s][(size_t)i * a.out_dim + o], acc);
-        a.out[((size_t)s * a.n_t + t) * a.out_dim + o] = acc;
-    }
+    for (int o = tid; o < a.out_dim; o += blockDim.x)
+        a.out[((size_t)s * a.n_t + t) * a.out_dim + o] = gemv(a.Wp[s], a.bp[s], e, a.e_dim, a.out_dim, o);
 }
 
 // ---------------------------------------------------------------------------
@@ -198,100 +202,157 @@ struct ScoreArgs {
     float* ang_out; float* lin_out;    // (n_t,3)
 };
 
+constexpr int kScoreQB = 2;     // query nodes processed together (every weight load serves both, for both tensor products)
+
 __global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
     pdl_wait(); pdl_launch();     // PDL: see common.cuh
     extern __shared__ float sm[];
+    constexpr int QB = kScoreQB;
     const int M0 = a.irr.m0, M1 = a.irr.m1, M2 = a.irr.m2, F = a.irr.dim();
     const int D0 = M0 + M1 + M2, D1 = M0 + 3 * M1 + 2 * M2;   // 112, 192 channels
-    const int NV = a.n_vec;
+    const int NV = a.n_vec, NY = 1 + 4 * NV;
     // t buffers: T[p][u][j]
     const int tsz[9] = {M0, M0 * 3, M1, M1 * 3, M1 * 3, M1 * 5, M2 * 3, M2 * 5, M2 * 5};
     int toff[10]; toff[0] = 0;
     for (int p = 0; p < 9; ++p) toff[p + 1] = toff[p] + tsz[p];
-    float* sa = sm;                 // F
-    float* sb = sa + F;             // F
-    float* st = sb + F;             // toff[9]
-    float* sd0 = st + toff[9];      // D0
-    float* sd1 = sd0 + D0;          // D1*3
-    float* sy = sd1 + 3 * D1;       // 1 + NV + 3 NV
-    float* sres = sy + (1 + 4 * NV);   // [n_q][2][3]
+    const int TT = toff[9];
+    float* sa = sm;                     // [QB][F]
+    float* sb = sa + QB * F;            // [QB][F]
+    float* st = sb + QB * F;            // [2][QB][TT]
+    float* sd0 = st + 2 * QB * TT;      // [2][QB][D0]
+    float* sd1 = sd0 + 2 * QB * D0;     // [2][QB][3 D1]
+    float* sy = sd1 + 2 * QB * 3 * D1;  // [2][QB][NY]
+    float* sres = sy + 2 * QB * NY;     // [n_q][2][3]
     const int t = blockIdx.x, tid = threadIdx.x;
-    // weight offsets (mul1 x mul2 row-major per path)
+    // weight offsets (per path: [mul2][mul1], i.e. transposed blocks, see ScoreArgs)
     const int m1s[9] = {M0, M0, M1, M1, M1, M1, M2, M2, M2};
     const int m2s[9] = {M0, M1, M0, M1, M1, M2, M1, M2, M2};
     const int l2s[9] = {0, 1, 0, 1, 1, 2, 1, 2, 2};
-    int woff[10]; woff[0] = 0;
-    for (int p = 0; p < 9; ++p) woff[p + 1] = woff[p] + m1s[p] * m2s[p];
+    int woff[10], uoff[10]; woff[0] = 0; uoff[0] = 0;
+    for (int p = 0; p < 9; ++p) { woff[p + 1] = woff[p] + m1s[p] * m2s[p]; uoff[p + 1] = uoff[p] + m1s[p]; }
+    const int NU = uoff[9];             // (path, u) pairs
     const int boff[3] = {0, M0, M0 + 3 * M1};   // offsets of l blocks in a feature vector
 
-    for (int q = 0; q < a.n_q; ++q) {
-        const size_t node = (size_t)t * a.n_q + q;
+    for (int q0 = 0; q0 < a.n_q; q0 += QB) {
+        const int nq = min(QB, a.n_q - q0);
         __syncthreads();
-        for (int i = tid; i < F; i += blockDim.x) { sa[i] = a.qf_rot[node * F + i]; sb[i] = a.key_f[node * F + i]; }
-        for (int which = 0; which < 2; ++which) {
-            __syncthreads();
-            // step 1: t_p[u][j] = sum_v W_p[u][v] b_{l2}[v][j].  The host passes W_p TRANSPOSED ([mul2][mul1]) and consecutive
-            // threads take consecutive u, so every weight load is a coalesced row segment and b[v][j] is a broadcast.
-            for (int i = tid; i < toff[9]; i += blockDim.x) {
-                int p = 0;
-                while (i >= toff[p + 1]) ++p;
-                const int d2 = 2 * l2s[p] + 1;
-                const int j = (i - toff[p]) / m1s[p], u = (i - toff[p]) % m1s[p];
-                const float* w = a.Wd[which] + woff[p] + u;
-                const float* b = sb + boff[l2s[p]] + j;
-                float acc = 0.f;
-                for (int v = 0; v < m2s[p]; ++v) acc = fmaf(__ldg(w + (size_t)v * m1s[p]), b[v * d2], acc);
-                st[toff[p] + u * d2 + j] = acc;
+        for (int i = tid; i < QB * F; i += blockDim.x) {
+            const int qq = i / F, c = i % F;
+            const size_t node = (size_t)t * a.n_q + q0 + min(qq, nq - 1);
+            sa[i] = a.qf_rot[node * F + c]; sb[i] = a.key_f[node * F + c];
+        }
+        __syncthreads();
+        // step 1: t_p[u][j] = sum_v W_p[u][v] b_{l2}[v][j] for both tensor products and both query nodes: one thread per
+        // (which, path, u); consecutive threads take consecutive u (coalesced weight rows, 4 loads in flight), b is broadcast
+        for (int i = tid; i < 2 * NU; i += blockDim.x) {
+            const int which = i / NU, r = i % NU;
+            int p = 0;
+            while (r >= uoff[p + 1]) ++p;
+            const int u = r - uoff[p], d2 = 2 * l2s[p] + 1, m1 = m1s[p], m2 = m2s[p];
+            const float* w = a.Wd[which] + woff[p] + u;
+            const float* b = sb + boff[l2s[p]];
+            float acc[QB][5];
+#pragma unroll
+            for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) acc[qq][j] = 0.f;
+            for (int v = 0; v < m2; v += 4) {          // every mul is a multiple of 4
+                float wv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) wv[k] = __ldg(w + (size_t)(v + k) * m1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+                        for (int j = 0; j < 5; ++j)
+                            if (j < d2) acc[qq][j] = fmaf(wv[k], b[qq * F + (v + k) * d2 + j], acc[qq][j]);
             }
-            __syncthreads();
-            // step 2: d[p][u][:] = cg(a[u], t_p[u])  ->  sd0 [112] , sd1 [192][3] in i_out order
-            //   lo=0 block: [p0 (M0) | p3 (M1) | p7 (M2)] ; lo=1 block: [p1 (M0) | p2 (M1) | p4 (M1) | p5 (M1) | p6 (M2) | p8 (M2)]
-            const int ntask = 2 * M0 + 4 * M1 + 3 * M2;
-            for (int i = tid; i < ntask; i += blockDim.x) {
-                int p, u;
-                if (i < M0) { p = 0; u = i; }
-                else if (i < 2 * M0) { p = 1; u = i - M0; }
-                else if (i < 2 * M0 + 4 * M1) { p = 2 + (i - 2 * M0) / M1; u = (i - 2 * M0) % M1; }
-                else { p = 6 + (i - 2 * M0 - 4 * M1) / M2; u = (i - 2 * M0 - 4 * M1) % M2; }
-                float o[3];
-                switch (p) {
-                    case 0: sd0[u] = sa[u] * st[toff[0] + u]; break;
-                    case 1: { const float x = sa[u]; const float* y = st + toff[1] + 3 * u;
-                              sd1[(u) * 3 + 0] = x * y[0]; sd1[(u) * 3 + 1] = x * y[1]; sd1[(u) * 3 + 2] = x * y[2]; } break;
-                    case 2: { const float* x = sa + boff[1] + 3 * u; const float y = st[toff[2] + u];
-                              float* d = sd1 + (M0 + u) * 3; d[0] = x[0] * y; d[1] = x[1] * y; d[2] = x[2] * y; } break;
-                    case 3: cg_110(sa + boff[1] + 3 * u, st + toff[3] + 3 * u, o); sd0[M0 + u] = o[0]; break;
-                    case 4: { cg_111(sa + boff[1] + 3 * u, st + toff[4] + 3 * u, o);
-                              float* d = sd1 + (M0 + M1 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
-                    case 5: { cg_121(sa + boff[1] + 3 * u, st + toff[5] + 5 * u, o);
-                              float* d = sd1 + (M0 + 2 * M1 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
-                    case 6: { cg_211(sa + boff[2] + 5 * u, st + toff[6] + 3 * u, o);
-                              float* d = sd1 + (M0 + 3 * M1 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
-                    case 7: cg_220(sa + boff[2] + 5 * u, st + toff[7] + 5 * u, o); sd0[M0 + M1 + u] = o[0]; break;
-                    default: { cg_221(sa + boff[2] + 5 * u, st + toff[8] + 5 * u, o);
-                               float* d = sd1 + (M0 + 3 * M1 + M2 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+#pragma unroll
+            for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+                    if (j < d2) st[(which * QB + qq) * TT + toff[p] + u * d2 + j] = acc[qq][j];
+        }
+        __syncthreads();
+        // step 2: d[p][u][:] = cg(a[u], t_p[u])  ->  sd0 [112] , sd1 [192][3] in i_out order
+        //   lo=0 block: [p0 (M0) | p3 (M1) | p7 (M2)] ; lo=1 block: [p1 (M0) | p2 (M1) | p4 (M1) | p5 (M1) | p6 (M2) | p8 (M2)]
+        const int ntask = 2 * M0 + 4 * M1 + 3 * M2;
+        for (int i = tid; i < 2 * QB * ntask; i += blockDim.x) {
+            const int wq = i / ntask, r = i % ntask;          // wq = which * QB + qq
+            const float* xa = sa + (wq % QB) * F;
+            const float* tt = st + wq * TT;
+            float* d0 = sd0 + wq * D0;
+            float* d1 = sd1 + wq * 3 * D1;
+            int p, u;
+            if (r < M0) { p = 0; u = r; }
+            else if (r < 2 * M0) { p = 1; u = r - M0; }
+            else if (r < 2 * M0 + 4 * M1) { p = 2 + (r - 2 * M0) / M1; u = (r - 2 * M0) % M1; }
+            else { p = 6 + (r - 2 * M0 - 4 * M1) / M2; u = (r - 2 * M0 - 4 * M1) % M2; }
+            float o[3];
+            switch (p) {
+                case 0: d0[u] = xa[u] * tt[toff[0] + u]; break;
+                case 1: { const float x = xa[u]; const float* y = tt + toff[1] + 3 * u;
+                          d1[u * 3 + 0] = x * y[0]; d1[u * 3 + 1] = x * y[1]; d1[u * 3 + 2] = x * y[2]; } break;
+                case 2: { const float* x = xa + boff[1] + 3 * u; const float y = tt[toff[2] + u];
+                          float* d = d1 + (M0 + u) * 3; d[0] = x[0] * y; d[1] = x[1] * y; d[2] = x[2] * y; } break;
+                case 3: cg_110(xa + boff[1] + 3 * u, tt + toff[3] + 3 * u, o); d0[M0 + u] = o[0]; break;
+                case 4: { cg_111(xa + boff[1] + 3 * u, tt + toff[4] + 3 * u, o);
+                          float* d = d1 + (M0 + M1 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+                case 5: { cg_121(xa + boff[1] + 3 * u, tt + toff[5] + 5 * u, o);
+                          float* d = d1 + (M0 + 2 * M1 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+                case 6: { cg_211(xa + boff[2] + 5 * u, tt + toff[6] + 3 * u, o);
+                          float* d = d1 + (M0 + 3 * M1 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+                case 7: cg_220(xa + boff[2] + 5 * u, tt + toff[7] + 5 * u, o); d0[M0 + M1 + u] = o[0]; break;
+                default: { cg_221(xa + boff[2] + 5 * u, tt + toff[8] + 5 * u, o);
+                           float* d = d1 + (M0 + 3 * M1 + M2 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+            }
+        }
+        __syncthreads();
+        // step 3: linear  (D0 -> 1+NV scalars with bias ; D1 -> NV vectors), one thread per (which, output) for both query nodes
+        for (int i = tid; i < 2 * NY; i += blockDim.x) {
+            const int which = i / NY, o = i % NY;
+            float acc[QB];
+            if (o < 1 + NV) {
+                const float* W = a.Wl0[which] + o;
+#pragma unroll
+                for (int qq = 0; qq < QB; ++qq) acc[qq] = a.bl[which][o];
+                for (int r = 0; r < D0; r += 4) {      // D0 = 7 G / 2 is a multiple of 4 for G in (16, 32)
+                    float wv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) wv[k] = __ldg(W + (size_t)(r + k) * (1 + NV));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int qq = 0; qq < QB; ++qq) acc[qq] = fmaf(sd0[(which * QB + qq) * D0 + r + k], wv[k], acc[qq]);
+                }
+            } else {
+                const int c = (o - 1 - NV) / 3, k3 = (o - 1 - NV) % 3;
+                const float* W = a.Wl1[which] + c;
+#pragma unroll
+                for (int qq = 0; qq < QB; ++qq) acc[qq] = 0.f;
+                for (int r = 0; r < D1; r += 4) {
+                    float wv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) wv[k] = __ldg(W + (size_t)(r + k) * NV);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int qq = 0; qq < QB; ++qq) acc[qq] = fmaf(sd1[(which * QB + qq) * 3 * D1 + (r + k) * 3 + k3], wv[k], acc[qq]);
                 }
             }
-            __syncthreads();
-            // step 3: linear  (D0 -> 1+NV scalars with bias ; D1 -> NV vectors)
-            for (int i = tid; i < (1 + NV) + 3 * NV; i += blockDim.x) {
-                float acc;
-                if (i < 1 + NV) {
-                    acc = a.bl[which][i];
-                    for (int r = 0; r < D0; ++r) acc = fmaf(sd0[r], __ldg(a.Wl0[which] + (size_t)r * (1 + NV) + i), acc);
-                } else {
-                    const int c = (i - 1 - NV) / 3, k = (i - 1 - NV) % 3;
-                    acc = 0.f;
-                    for (int r = 0; r < D1; ++r) acc = fmaf(sd1[r * 3 + k], __ldg(a.Wl1[which] + (size_t)r * NV + c), acc);
-                }
-                sy[i] = acc;
-            }
-            __syncthreads();
-            // step 4: gate, mean over the NV vectors (drop the scalar), rotate by q^-1
-            if (tid < 3) {
+#pragma unroll
+            for (int qq = 0; qq < QB; ++qq) sy[(which * QB + qq) * NY + o] = acc[qq];
+        }
+        __syncthreads();
+        // step 4: gate, mean over the NV vectors (drop the scalar)
+        if (tid < 2 * QB * 3) {
+            const int wq = tid / 3, k3 = tid % 3, which = wq / QB, qq = wq % QB;
+            if (qq < nq) {
+                const float* y = sy + wq * NY;
                 float s = 0.f;
-                for (int c = 0; c < NV; ++c) s += sy[1 + NV + 3 * c + tid] * (kCSigmoid * sigmoidf_(sy[1 + c]));
-                sres[(q * 2 + which) * 3 + tid] = s / (float)NV;
+                for (int c = 0; c < NV; ++c) s += y[1 + NV + 3 * c + k3] * (kCSigmoid * sigmoidf_(y[1 + c]));
+                sres[((q0 + qq) * 2 + which) * 3 + k3] = s / (float)NV;
             }
         }
     }
@@ -444,7 +505,8 @@ extern "C" int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, cons
     const int M0 = a.irr.m0, M1 = a.irr.m1, M2 = a.irr.m2, F = a.irr.dim();
     const int tt = M0 + 3 * M0 + M1 + 3 * M1 + 3 * M1 + 5 * M1 + 3 * M2 + 5 * M2 + 5 * M2;
     const int D0 = M0 + M1 + M2, D1 = M0 + 3 * M1 + 2 * M2;
-    const size_t smem = (size_t)(2 * F + tt + D0 + 3 * D1 + 1 + 4 * n_vec + 6 * n_q) * sizeof(float);
+    const size_t smem = (size_t)(kScoreQB * (2 * F + 2 * (tt + D0 + 3 * D1 + 1 + 4 * n_vec)) + 6 * n_q) * sizeof(float);
+    if ((M0 % 4) || (M1 % 4) || (M2 % 4) || (D0 % 4) || (D1 % 4)) return DEDF_ERR_UNSUPPORTED;
     if (smem > 96 * 1024) return DEDF_ERR_UNSUPPORTED;
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(score_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); done = true; }
