@@ -291,14 +291,22 @@ struct TpLinArgs {
     float* logits;           // (E, 4)
     float* out;              // (E, F_out)
     int per_edge_x;          // 1: x_src is (E, F) indexed by the edge itself (no gather)
+    long long* dbg;          // optional (host debug): clock64() stamps of CTA 0
 };
 
 enum { EPI_ACT = 0, EPI_LIN = 1 };
 
+#ifndef DEDF_TPLIN_TE32
+#define DEDF_TPLIN_TE32 16
+#endif
+constexpr int kTpLinTE32 = DEDF_TPLIN_TE32;
+
 template <int G, int EPI>
 struct TpLinCfg {
     using D = Dtp<G>;
-    static constexpr int TE = 512 / G;                       // edges per tile (16 / 32)
+    // edges per tile (16 / 32).  Measured alternative (profiles/run_tp_lin.py): G = 32 with 8-edge tiles and an L1 large
+    // enough for the whole weight set halves the latency of a K step but doubles the steps per edge: 953 us vs 683 us.
+    static constexpr int TE = (G == 32) ? kTpLinTE32 : 32;
     static constexpr int MA = (EPI == EPI_ACT) ? D::M0 : 0;  // alpha channels (= mul of 0e in the heads irreps)
     static constexpr int N0 = (EPI == EPI_ACT) ? (MA + D::M0 + D::M1 + D::M2) : D::M0;
     static constexpr int N1 = D::M1, N2 = D::M2;
@@ -330,10 +338,13 @@ edge_tp_lin_kernel(TpLinArgs a, int lda0, int lda1, int lda2) {
     const int E = *a.n_edges;
     const int n_tiles = (E + TE - 1) / TE;
 
+    int dbg_i = 0;
+#define TPL_STAMP() do { if (a.dbg && blockIdx.x == 0 && tid == 0 && dbg_i < 60) a.dbg[dbg_i++] = clock64(); } while (0)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int e0 = tile * TE;
         const int rows = min(TE, E - e0);
         __syncthreads();
+        TPL_STAMP();
         for (int i = tid; i < TE; i += C::THREADS) {
             const bool ok = i < rows;
             s_src[i] = ok ? (a.per_edge_x ? (e0 + i) : a.edge_src[e0 + i]) : 0;
@@ -341,6 +352,7 @@ edge_tp_lin_kernel(TpLinArgs a, int lda0, int lda1, int lda2) {
         }
         for (int i = tid; i < TE * 9; i += C::THREADS) s_sh[i] = (i / 9 < rows) ? a.sh[(size_t)e0 * 9 + i] : 0.f;
         __syncthreads();
+        TPL_STAMP();
 
         // ---------------- CG phase: one pack of P edges per warp iteration ----------------
         for (int pack = warp; pack < TE / P; pack += NWARPS) {
@@ -433,6 +445,7 @@ edge_tp_lin_kernel(TpLinArgs a, int lda0, int lda1, int lda2) {
             }
         }
         __syncthreads();
+        TPL_STAMP();
 
         // ---------------- GEMM phase: one 4x4 item per thread ----------------
         constexpr int I0 = (TE / 4) * (C::N0 / 4), I1 = (3 * TE / 4) * (C::N1 / 4), I2 = (5 * TE / 4) * (C::N2 / 4);
@@ -444,6 +457,7 @@ edge_tp_lin_kernel(TpLinArgs a, int lda0, int lda1, int lda2) {
         if (which == 0) gemm_item_4x4<true>(A0, lda0, TE / 4, rg, a.W0, C::N0, 4 * cg, D::D0, acc);
         else if (which == 1) gemm_item_4x4<true>(A1, lda1, 3 * TE / 4, rg, a.W1, C::N1, 4 * cg, D::D1, acc);
         else if (which == 2) gemm_item_4x4<true>(A2, lda2, 5 * TE / 4, rg, a.W2, C::N2, 4 * cg, D::D2, acc);
+        TPL_STAMP();
         __syncthreads();   // all A reads done -> the region may be overwritten with the outputs
         if (which == 0) {
 #pragma unroll
@@ -459,6 +473,7 @@ edge_tp_lin_kernel(TpLinArgs a, int lda0, int lda1, int lda2) {
                 *reinterpret_cast<float4*>(O2 + (rg + i * (5 * TE / 4)) * C::N2 + 4 * cg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
         __syncthreads();
+        TPL_STAMP();
 
         // ---------------- epilogue: one warp per edge ----------------
         for (int e = warp; e < rows; e += NWARPS) {
@@ -1097,6 +1112,11 @@ static int launch_tp_lin(const TpLinArgs& a, int max_edges, cudaStream_t stream)
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(edge_tp_lin_kernel<G, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // ask for just enough shared memory for the resident CTAs: the rest of the 256 KB stays L1 and caches the weights
+        const int ctas = (smem * 4 <= 120 * 1024) ? 4 : 2;
+        int pct = (int)((smem * ctas + 2048 * ctas) * 100 / (228 * 1024)) + 1;
+        if (pct > 100) pct = 100;
+        cudaFuncSetAttribute(edge_tp_lin_kernel<G, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         attr_done = true;
     }
     const int n_tiles = (max_edges + C::TE - 1) / C::TE;
@@ -1104,6 +1124,10 @@ static int launch_tp_lin(const TpLinArgs& a, int max_edges, cudaStream_t stream)
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
+
+static long long* g_tpl_dbg = nullptr;
+/* debug hook (not in the public header): 64 x int64 device buffer receiving clock64() stamps of CTA 0 of dedf_edge_tp_lin */
+extern "C" int dedf_tp_lin_set_debug(long long* dbg) { g_tpl_dbg = dbg; return DEDF_OK; }
 
 extern "C" int dedf_edge_tp_lin(int mul1, int epilogue, const float* x_src, const float* x_dst, int per_edge_x,
                                 const int* edge_src, const int* edge_dst, const int* n_edges_dev, int max_edges,
@@ -1119,6 +1143,7 @@ extern "C" int dedf_edge_tp_lin(int mul1, int epilogue, const float* x_src, cons
     a.x_src = x_src; a.x_dst = x_dst; a.edge_src = edge_src; a.edge_dst = edge_dst; a.n_edges = n_edges_dev; a.sh = sh;
     a.w = w; a.w_stride = w_stride; a.W0 = W0; a.W1 = W1; a.W2 = W2; a.bias0 = bias0; a.alpha_dot = alpha_dot;
     a.edge_logit = edge_logit; a.logits = logits; a.out = out; a.per_edge_x = per_edge_x;
+    a.dbg = g_tpl_dbg;
     if (mul1 == 32 && epilogue == DEDF_EPI_ACT) return launch_tp_lin<32, EPI_ACT>(a, max_edges, stream);
     if (mul1 == 32 && epilogue == DEDF_EPI_LIN) return launch_tp_lin<32, EPI_LIN>(a, max_edges, stream);
     if (mul1 == 16 && epilogue == DEDF_EPI_ACT) return launch_tp_lin<16, EPI_ACT>(a, max_edges, stream);
