@@ -42,14 +42,12 @@ class UnetEquiformerBlock(nn.Module):
         self.norm_2 = EquivariantLayerNormV2(self.irreps_dst)
         self.ffn = FeedForwardNetwork(self.irreps_dst, self.irreps_dst, mlp_mid(self.irreps_emb, irreps_mlp_mid))
 
-    def forward(self, f_src: torch.Tensor, f_dst: torch.Tensor, g: ops.Csr, sh: torch.Tensor, length: torch.Tensor,
-                radial: GaussianRadialBasisLayerFiniteCutoff) -> torch.Tensor:
-        msg_src = self.linear_src(f_src)
-        msg_dst = self.linear_dst(f_dst)
-        # per-edge TP weights: RadialProfile(GaussianRadialBasisLayerFiniteCutoff(length))
+    def radial_weights(self, g: ops.Csr, length: torch.Tensor, radial: GaussianRadialBasisLayerFiniteCutoff) -> torch.Tensor:
+        """Per-edge TP weights RadialProfile(GaussianRadialBasisLayerFiniteCutoff(length)): geometry only, no features
+        (the key encoder computes them on a side stream while the previous block's features are still in flight)."""
         rad = self.ga.sep_act.dtp_rad
         E = max(1, g.n_edges)
-        w = torch.empty(E, self.ga.sep_act.numel, dtype=torch.float32, device=f_src.device)
+        w = torch.empty(E, self.ga.sep_act.numel, dtype=torch.float32, device=length.device)
         d = L.MlpDesc()
         d.mode = L.MLP_IN_RBF
         d.n_edges_dev = L.ptr(g.n_edges_dev, torch.int32)
@@ -63,6 +61,14 @@ class UnetEquiformerBlock(nn.Module):
             ops.edge_mlp_tc(d, g.n_edges)
         else:
             ops.edge_mlp(d, g.n_edges)
+        return w
+
+    def forward(self, f_src: torch.Tensor, f_dst: torch.Tensor, g: ops.Csr, sh: torch.Tensor, length: torch.Tensor,
+                radial: GaussianRadialBasisLayerFiniteCutoff, w: Optional[torch.Tensor] = None) -> torch.Tensor:
+        msg_src = self.linear_src(f_src)
+        msg_dst = self.linear_dst(f_dst)
+        if w is None:
+            w = self.radial_weights(g, length, radial)
         attn = self.ga.attend(msg_src, msg_dst, g, sh, w, None)
         out = self.ga.proj(attn, res=f_dst)                          # node_output = node_input_dst + ga(...)
         return self.ffn(out, ln=self.norm_2, res=out)                # + ffn(norm_2(node_output))

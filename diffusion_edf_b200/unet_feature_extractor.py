@@ -99,65 +99,131 @@ class UnetFeatureExtractor(nn.Module):
             self.up_blocks.append(blk)
         self.project_outputs = nn.ModuleList([ProjectIfMismatch(self.irreps_emb[n], self.irreps_output)
                                               for n in range(self.n_scales)])
-
-    @staticmethod
-    def _run(layer, f_src, f_dst, geom: _Geom):
-        return layer["gnn"](f_src, f_dst, geom.g, geom.sh, geom.length, layer["radial"])
+        self.overlap_geometry = True     # graph construction + radial MLPs on a side stream (see _geometry)
+        self._side = None
 
     @staticmethod
     def _geom(x_src, x_dst, g) -> _Geom:
         length, sh, _ = ops.edge_geom(x_src, x_dst, g)
         return _Geom(g, length, sh)
 
-    def forward(self, pcd: FeaturedPoints) -> List[FeaturedPoints]:
-        x, b = pcd.x.contiguous(), pcd.b.contiguous()
-        assert pcd.f.ndim == 2 and x.ndim == 2 and b.ndim == 1 and len(pcd.f) == len(x) == len(b)
-        f = self.input_emb(pcd.f.contiguous())
-        outs, graphs = [(f, x, b)], []          # graphs: ("pool", n, idx, x_src, b_src) / ("self", geom)
+    # ------------------------------------------------------------------ geometry pass (feature independent)
+    def _geometry(self, x: torch.Tensor, b: torch.Tensor, done):
+        """FPS pooling, radius graphs, edge geometry and the per-edge radial TP weights of EVERY block, in the order the
+        feature pass consumes them.  Nothing here reads a feature, so forward() runs it on a side stream: after the first
+        FPS the whole graph-construction / radial-MLP pipeline overlaps the attention blocks of the previous scales.
+        ``done(item)`` is called after each item's kernels are enqueued (it records the event the feature pass waits on)."""
+        items = []
+
+        def emit(kind, **kw):
+            it = dict(kind=kind, **kw)
+            done(it)
+            items.append(it)
+            return it
+
+        def block(layer, geom):
+            return layer["gnn"].radial_weights(geom.g, geom.length, layer["radial"])
+
+        levels = []          # per scale: (x_src, b_src, idx, x_dst, b_dst, self geom)
         geom = None
         for n, blk in enumerate(self.down_blocks):
-            # ---- FPS pooling + bipartite radius graph (connectivity.py:59-76) ----
             idx = ops.fps(x, b, self.pool_ratio[n], random_start=not self.deterministic)
             x_dst = ops.gather_rows(x, idx)
             b_dst = b.index_select(0, idx)
-            f_dst = ops.gather_rows(f, idx)
             g = ops.radius_csr(x, x_dst, [self.radius[n]], b_src=b, b_dst=b_dst, excl_mode=1, excl=idx, max_num_neighbors=1000)
-            f_dst = blk["pool_proj"](f_dst)
-            f_new = self._run(blk["pool_layer"], f, f_dst, self._geom(x, x_dst, g))
-            graphs.append(("pool", n, idx, x, b))
-            f, x, b = f_new, x_dst, b_dst
-            outs.append((f, x, b))
-            # ---- self radius graph + remaining layers ----
-            g = ops.radius_csr(x, x, [self.radius[n]], b_src=b, b_dst=b, excl_mode=2, max_num_neighbors=1001)
-            geom = self._geom(x, x, g)
+            gp = self._geom(x, x_dst, g)
+            emit("pool", n=n, idx=idx, x_dst=x_dst, b_dst=b_dst, geom=gp, w=block(blk["pool_layer"], gp))
+            g = ops.radius_csr(x_dst, x_dst, [self.radius[n]], b_src=b_dst, b_dst=b_dst, excl_mode=2, max_num_neighbors=1001)
+            geom = self._geom(x_dst, x_dst, g)
             for layer in blk["layer_stack"]:
-                f = self._run(layer, f, f, geom)
-                outs.append((f, x, b))
-                graphs.append(("self", geom))
+                emit("self", geom=geom, w=block(layer, geom))
+            levels.append((x, b, idx, x_dst, b_dst, geom))
+            x, b = x_dst, b_dst
         for layer in self.mid_block:
-            f = self._run(layer, f, f, geom)
+            emit("self", geom=geom, w=block(layer, geom))
+        for n, blk in enumerate(self.up_blocks):
+            scale = self.n_scales - 1 - n
+            x_fine, b_fine, idx, x_c, b_c, gself = levels[scale]
+            for layer in blk["layer_stack"]:
+                emit("self", geom=gself, w=block(layer, gself))      # swapped self graph == the same graph
+            if n != self.n_scales - 1:
+                # swapped pool graph: sources = pooled points, destinations = finer points
+                g = ops.radius_csr(x_c, x_fine, [self.radius[scale]], b_src=b_c, b_dst=b_fine, excl_mode=3, excl=idx,
+                                   max_num_neighbors=1000)
+                gu = self._geom(x_c, x_fine, g)
+                emit("unpool", geom=gu, w=block(blk["unpool_layer"], gu))
+        return items
+
+    def forward(self, pcd: FeaturedPoints) -> List[FeaturedPoints]:
+        x, b = pcd.x.contiguous(), pcd.b.contiguous()
+        assert pcd.f.ndim == 2 and x.ndim == 2 and b.ndim == 1 and len(pcd.f) == len(x) == len(b)
+        main = torch.cuda.current_stream()
+        use_side = self.overlap_geometry and x.is_cuda
+        if use_side:
+            if self._side is None or self._side.device != x.device:
+                self._side = torch.cuda.Stream(device=x.device)
+            side = self._side
+            side.wait_stream(main)                       # fork (inputs are ready on the main stream)
+
+            def done(it):
+                ev = torch.cuda.Event()
+                ev.record(side)
+                it["event"] = ev
+            with torch.cuda.stream(side):
+                items = self._geometry(x, b, done)
+        else:
+            items = self._geometry(x, b, lambda it: None)
+        pos = [0]
+
+        def take(kind):
+            it = items[pos[0]]
+            pos[0] += 1
+            assert it["kind"] == kind, (it["kind"], kind)
+            if use_side:
+                main.wait_event(it["event"])
+                for v in it.values():                    # tensors allocated on the side stream, consumed on the main one
+                    for t in (v if isinstance(v, (tuple, list)) else (v,)):
+                        if isinstance(t, torch.Tensor):
+                            t.record_stream(main)
+                gm = it["geom"]
+                for t in (gm.length, gm.sh, gm.g.row_ptr, gm.g.edge_src, gm.g.edge_dst):
+                    t.record_stream(main)
+            return it
+
+        def run(layer, f_src, f_dst, it):
+            gm = it["geom"]
+            return layer["gnn"](f_src, f_dst, gm.g, gm.sh, gm.length, layer["radial"], w=it["w"])
+
+        f = self.input_emb(pcd.f.contiguous())
+        outs = [(f, x, b)]
+        for n, blk in enumerate(self.down_blocks):
+            it = take("pool")
+            f_dst = blk["pool_proj"](ops.gather_rows(f, it["idx"]))
+            f = run(blk["pool_layer"], f, f_dst, it)
+            x, b = it["x_dst"], it["b_dst"]
+            outs.append((f, x, b))
+            for layer in blk["layer_stack"]:
+                f = run(layer, f, f, take("self"))
+                outs.append((f, x, b))
+        for layer in self.mid_block:
+            f = run(layer, f, f, take("self"))
         f_skip, _, _ = outs.pop()
         f = ops.add_scale(f, f_skip, 1.0 / math.sqrt(3))
         ups = []
         for n, blk in enumerate(self.up_blocks):
             for layer in blk["layer_stack"]:
                 f_dst, x_dst, b_dst = outs.pop()
-                kind = graphs.pop()
-                assert kind[0] == "self"
                 f_dst = ops.add_scale(f, f_dst, 1.0 / math.sqrt(3))
-                f = self._run(layer, f, f_dst, kind[1])      # swapped self graph == the same graph (see module docstring)
+                f = run(layer, f, f_dst, take("self"))
                 x, b = x_dst, b_dst
             ups.append((f, x, b))
             f_dst, x_dst, b_dst = outs.pop()
-            kind = graphs.pop()
-            assert kind[0] == "pool"
             if n != self.n_scales - 1:
-                _, scale, idx, x_fine, b_fine = kind
-                # swapped pool graph: sources = pooled points (current x), destinations = finer points
-                g = ops.radius_csr(x, x_fine, [self.radius[scale]], b_src=b, b_dst=b_fine, excl_mode=3, excl=idx,
-                                   max_num_neighbors=1000)
-                f = self._run(blk["unpool_layer"], f, f_dst, self._geom(x, x_fine, g))
+                f = run(blk["unpool_layer"], f, f_dst, take("unpool"))
                 x, b = x_dst, b_dst
+        assert pos[0] == len(items)
+        if use_side:
+            main.wait_stream(side)                       # join (required under CUDA-graph capture)
         ups = ups[::-1]
         pcds = []
         for s, proj in enumerate(self.project_outputs):
