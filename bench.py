@@ -172,7 +172,10 @@ def _k1_roofline(dev, peak_gbs, peak_src):
             "workload": "C4: N=100k nodes, degree 32, 64x0e+32x1e+16x2e, per-edge weights (E,480)",
             "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
             "peak_source": peak_src, "ms_per_launch": ms, "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": len(times),
-            "traffic": None, "l2": "flushed between launches (512 MB fill)",
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, from the committed ncu --set full capture
+            # (profiles/r1_k1_s3_ncu_full_summary.txt: 7.669 GB + 0.607 GB); re-take when the kernel changes
+            "traffic": 8.276e9, "traffic_source": "profiles/r1_k1_s3_ncu_full_summary.txt (ncu --set full, per launch)",
+            "l2": "flushed between launches (512 MB fill)",
             "note": "algorithmic bytes count 9 harmonics per edge; the kernel actually moves 12 (rows padded to 48 B for TMA)"}
 
 
@@ -305,10 +308,13 @@ def run_cuda(args):
         "metric": METRIC, "value": world * N_POSES / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
+        "precision_note": "fp32 arithmetic throughout; the per-edge MLP GEMMs run on the tcgen05 tensor cores as 3xTF32 (hi/lo split, "
+                          "fp32 accumulation in TMEM), which the parity tests hold to the same 1e-4 bound as the CUDA-core kernels",
         "config": {"workload": WORKLOAD, "poses_per_gpu": N_POSES, "scene_points": N_POINTS, "weights": "random init, seed 0",
                    "parallelism": f"pose-sharded x{world}; rank 0 encodes the scene, 1 NCCL broadcast of the packed field per step" if world > 1 else "single GPU",
                    "l2": "flushed between timed steps (256 MB fill)", "timing": "CUDA events per step, max over ranks",
-                   "execution": "whole forward replayed as one CUDA graph (graphs.py); step_breakdown measured eagerly"},
+                   "execution": "whole forward replayed as one CUDA graph (graphs.py) with a forked geometry stream (graph construction + "
+                                "radial MLPs overlap the attention blocks) and programmatic dependent launch; step_breakdown measured eagerly"},
         "e2e": {"value": world * N_POSES / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "timing": "wall clock incl. pinned H2D of scene+poses and D2H of the scores"},
         "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
