@@ -78,6 +78,28 @@ _PROTOS = {
     "dedf_sample_advance": [c_fp, c_int, c_fp, c_fp, c_fp, c_fp],
     "dedf_prefetch_l2": [c_fp, c_fp, c_int, c_fp],
     "dedf_tc_selftest": [c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp],
+    "dedf_lin_wgrad": [c_fp, c_fp, c_int, C.POINTER(c_int), C.POINTER(c_int), c_fp, c_fp, c_fp, c_fp, c_fp],
+    "dedf_ln_fwd": [c_fp, c_int, C.POINTER(c_int), c_fp, c_fp, c_f, c_fp, c_fp],
+    "dedf_ln_bwd": [c_fp, c_fp, c_int, C.POINTER(c_int), c_fp, c_f, c_fp, c_fp, c_fp, c_fp],
+    "dedf_gate_fwd": [c_fp, c_int, C.POINTER(c_int), c_fp, c_fp],
+    "dedf_gate_bwd": [c_fp, c_fp, c_int, C.POINTER(c_int), c_fp, c_fp],
+    "dedf_act_fwd": [c_fp, c_ll, c_fp, c_fp],
+    "dedf_act_bwd": [c_fp, c_fp, c_ll, c_fp, c_fp],
+    "dedf_dtp_fwd": [c_int, c_fp, c_fp, c_fp, c_ll, c_int, c_fp, c_fp],
+    "dedf_dtp_bwd": [c_int, c_fp, c_fp, c_fp, c_ll, c_fp, c_int, c_fp, c_fp, c_fp],
+    "dedf_gather_rows_i32": [c_fp, c_fp, c_int, c_int, c_fp, c_fp],
+    "dedf_scatter_add_rows": [c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp],
+    "dedf_alpha_fwd": [c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_fp],
+    "dedf_alpha_bwd": [c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_fp],
+    "dedf_softmax_reduce_bwd": [c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp, c_fp],
+    "dedf_rbf_fwd": [c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_f, c_f, c_int, c_fp, c_fp],
+    "dedf_rbf_bwd": [c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_f, c_f, c_int, c_fp, c_fp, c_fp, c_fp, c_fp],
+    "dedf_sinusoid": [c_fp, c_int, c_int, c_fp, c_f, c_fp, c_fp],
+    "dedf_score_tp_fwd": [c_fp, c_fp, c_fp, c_int, C.POINTER(c_int), c_fp, c_fp],
+    "dedf_score_tp_bwd": [c_fp, c_fp, c_fp, c_int, C.POINTER(c_int), c_fp, c_fp, c_fp, c_fp, c_fp],
+    "dedf_query_transform_bwd": [c_fp, c_int, c_int, C.POINTER(c_int), c_fp, c_fp, c_fp],
+    "dedf_assemble_fwd": [c_fp, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp],
+    "dedf_assemble_bwd": [c_fp, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp],
     "dedf_build_arch": [],
 }
 

@@ -49,7 +49,7 @@ def _call(name: str, *args) -> None:
     else:
         rc = fn(*args)
     check(rc, name)
-    LAUNCHES += _KERNELS[name]
+    LAUNCHES += _KERNELS.get(name, 1)
 
 
 # ----------------------------------------------------------------------------

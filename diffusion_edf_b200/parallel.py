@@ -130,3 +130,44 @@ def sharded_sample(model, T_seed: torch.Tensor, key_pcd: Optional[FeaturedPoints
         return traj
     rows = all_gather_rows(traj.transpose(0, 1).contiguous(), T_seed.shape[0])       # (nT, S, 7)
     return rows.transpose(0, 1).contiguous()
+
+
+def allreduce_gradients(params, average: bool = True, bucket_bytes: int = 32 << 20) -> int:
+    """Data-parallel training step (BASELINE config C5: one synthetic demo per rank): sum (or average) the gradients of
+    ``params`` over all ranks.  Gradients are flattened into buckets of ~``bucket_bytes`` so that the ~1.8 M fp32
+    parameters (7.4 MB) travel in ONE all-reduce (NCCL over NVLink on GPUs; gloo in the CPU tests).  Parameters whose
+    gradient is None on this rank contribute zeros (every rank must issue the same collectives).  Returns the number of
+    collectives issued."""
+    params = [p for p in params if p.requires_grad]
+    if not dist.is_initialized() or dist.get_world_size() == 1 or not params:
+        return 0
+    world = dist.get_world_size()
+    n_coll, bucket, size = 0, [], 0
+
+    def flush():
+        nonlocal n_coll, bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if average:
+            flat.div_(world)
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+        n_coll += 1
+        bucket, size = [], 0
+
+    for p in params:
+        bucket.append(p)
+        size += p.numel() * p.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    return n_coll

@@ -35,17 +35,26 @@ class ScoreModelBase(nn.Module):
 
     # ------------------------------------------------------------------ training loss (forward value)
     def get_train_loss(self, Ts, time, key_pcd, query_pcd, target_ang_score, target_lin_score):
-        """Forward value of the reference's loss and its statistics (score_model_base.py:41-107).  The CUDA path
-        has no backward kernels yet: calling it with parameters that require grad raises."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("diffusion_edf_b200 has forward kernels only (no autograd through the CUDA path yet); "
-                                      "call under torch.no_grad() or with requires_grad_(False)")
+        """The reference's loss, statistics and (when parameters require grad) a differentiable graph
+        (score_model_base.py:41-107).  With gradients enabled the model runs through the training path
+        (train_path.py: un-fused CUDA primitives with hand-written backward kernels); otherwise through the fused
+        inference kernels."""
         assert target_ang_score.ndim == 2 and target_ang_score.shape[-1] == 3
         assert target_lin_score.ndim == 2 and target_lin_score.shape[-1] == 3
         assert len(time) == len(target_ang_score) == len(target_lin_score)
-        key_ms = self.get_key_pcd_multiscale(key_pcd)
-        q = self.get_query_pcd(query_pcd)
-        ang, lin = self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad:
+            from . import train_path
+            from .keypoint_extractor import StaticKeypointModel
+            if not isinstance(self.query_model, StaticKeypointModel):
+                raise NotImplementedError("the training path covers StaticKeypointModel configs (pick_*); KeypointExtractor is forward-only")
+            key_ms = train_path.unet_forward(self.key_model, key_pcd)
+            q = self.get_query_pcd(query_pcd)
+            ang, lin = train_path.score_head(self.score_head, Ts, key_ms, q, time)
+        else:
+            key_ms = self.get_key_pcd_multiscale(key_pcd)
+            q = self.get_query_pcd(query_pcd)
+            ang, lin = self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)
         t_ang = target_ang_score * torch.sqrt(time[..., None]) * self.ang_mult
         t_lin = target_lin_score * torch.sqrt(time[..., None]) * self.lin_mult
         ang_loss = torch.sum(torch.square(t_ang - ang), dim=-1).mean(dim=-1)

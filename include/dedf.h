@@ -223,6 +223,63 @@ int dedf_sample_advance(const double* sched, int n_steps, int* counter, float* t
                         cudaStream_t stream);
 
 /* library self-description: returns the compute capability the kernels were built for (100) */
+/* ---- training path (un-fused primitives + their backward kernels) ---------------------------------------------
+ * The reference trains through torch autograd over e3nn / torch_scatter ops (trainer.py:308-346 ->
+ * score_model_base.py:41-107).  diffusion_edf_b200/autograd_ops.py wraps the pairs below in torch.autograd.Function so
+ * that loss.backward() runs these kernels; torch itself only moves memory (cat / slice / reshape).  Parameter
+ * gradients are ACCUMULATED (atomics) into caller-zeroed buffers. */
+
+/* dW_l (in.m_l, out.m_l) and dbias (out.m0) of a block-diagonal linear y_l = W_l^T x_l (LinearRS, FCTP with 1x0e, nn.Linear =
+ * irreps (K,0,0) -> (N,0,0)); dx is dedf_node_linear with the transposed weights.  tensor_product_rescale.py:176-185 */
+int dedf_lin_wgrad(const float* x, const float* dy, int n, const int* irr_in_host, const int* irr_out_host, float* dW0,
+                   float* dW1, float* dW2, float* dbias0, cudaStream_t stream);
+/* EquivariantLayerNormV2 ('component', affine), equiformer/layer_norm.py:91-156; nn.LayerNorm is irreps (N,0,0). */
+int dedf_ln_fwd(const float* x, int n, const int* irr_host, const float* w, const float* b, float eps, float* y, cudaStream_t stream);
+int dedf_ln_bwd(const float* x, const float* g, int n, const int* irr_host, const float* w, float eps, float* dx, float* dw,
+                float* db, cudaStream_t stream);
+/* Gate (equiformer/fast_activation.py:210-224): irr_pre = pre-gate irreps (m0 = scalars + gates); plain SiLU: act_*. */
+int dedf_gate_fwd(const float* pre, int n, const int* irr_pre_host, float* y, cudaStream_t stream);
+int dedf_gate_bwd(const float* pre, const float* g, int n, const int* irr_pre_host, float* dpre, cudaStream_t stream);
+int dedf_act_fwd(const float* x, long long n, float* y, cudaStream_t stream);
+int dedf_act_bwd(const float* x, const float* g, long long n, float* dx, cudaStream_t stream);
+/* DepthwiseTensorProduct 'uvu' (tensor_product_rescale.py:352-382): out (E, 49 mul1) in the sorted-irreps layout; w per edge
+ * (w_stride = 15 mul1) or shared (w_stride = 0, dw accumulated). */
+int dedf_dtp_fwd(int mul1, const float* x, const float* sh, const float* w, long long w_stride, int n_edges, float* out,
+                 cudaStream_t stream);
+int dedf_dtp_bwd(int mul1, const float* x, const float* sh, const float* w, long long w_stride, const float* g, int n_edges,
+                 float* dx, float* dw, cudaStream_t stream);
+int dedf_gather_rows_i32(const float* x, const int* idx, int n, int F, float* y, cudaStream_t stream);
+int dedf_scatter_add_rows(const float* g, const void* idx, int idx_is_i64, int n, int F, float* out, cudaStream_t stream);
+/* attention logits sum_k c SLReLU(pre[e,h,k]) alpha_dot[h,k] + edge_logit[e]   (graph_attention.py:241-246) */
+int dedf_alpha_fwd(const float* pre, int n_edges, int ma, const float* alpha_dot, const float* edge_logit, float* logits,
+                   cudaStream_t stream);
+int dedf_alpha_bwd(const float* pre, int n_edges, int ma, const float* alpha_dot, const float* g, float* dpre, float* dalpha_dot,
+                   cudaStream_t stream);
+/* backward of dedf_segment_softmax_reduce (graph_attention.py:254-265) */
+int dedf_softmax_reduce_bwd(const int* row_ptr, int n_dst, int n_seg, const float* logits, const float* val, const float* gout,
+                            int m0, int m1, int m2, float* dlogits, float* dval, cudaStream_t stream);
+/* Gaussian radial bases with learnable mean / std_logit / weight_logit (radial_func.py:168-278); mode 0: GaussianRadialBasis
+ * (d = len * inv_span), mode 1: GaussianRadialBasisLayerFiniteCutoff (d = (len - offset) * inv_span, inner soft cut-off). */
+int dedf_rbf_fwd(const float* len, int n_edges, int k, const float* mean, const float* std_logit, const float* weight_logit,
+                 float offset, float inv_span, int mode, float* out, cudaStream_t stream);
+int dedf_rbf_bwd(const float* len, int n_edges, int k, const float* mean, const float* std_logit, const float* weight_logit,
+                 float offset, float inv_span, int mode, const float* g, float* dmean, float* dstd_logit, float* dweight_logit,
+                 cudaStream_t stream);
+/* SinusoidalPositionEmbeddings (radial_func.py:291-316): out[r] = [sin(x scale f_k) | cos(x scale f_k)] */
+int dedf_sinusoid(const float* x, int n, int dim, const float* freq, float scale, float* out, cudaStream_t stream);
+/* the 'uvu' score tensor product (score_head.py:123-139), un-fused: out (n, D0 + 3 D1); w = tp.weight in the reference layout */
+int dedf_score_tp_fwd(const float* a, const float* b, const float* w, int n, const int* irr_host, float* out, cudaStream_t stream);
+int dedf_score_tp_bwd(const float* a, const float* b, const float* w, int n, const int* irr_host, const float* g, float* da,
+                      float* db, float* dw, cudaStream_t stream);
+/* adjoint of dedf_query_transform w.r.t. the query features (accumulates over poses) */
+int dedf_query_transform_bwd(const float* Ts, int n_t, int n_q, const int* irr_host, const float* g, float* dqf, cudaStream_t stream);
+/* score_head.py:196-209 on the gated (n_t n_q, 1 + 3 n_vec) outputs of the lin / ang products */
+int dedf_assemble_fwd(const float* Ts, int n_t, int n_q, int n_vec, const float* ylin, const float* yang, const float* qx,
+                      const float* qw, float lin_mult, float* ang, float* lin, cudaStream_t stream);
+int dedf_assemble_bwd(const float* Ts, int n_t, int n_q, int n_vec, const float* ylin, const float* yang, const float* qx,
+                      const float* qw, float lin_mult, const float* gang, const float* glin, float* dylin, float* dyang,
+                      float* dqw, cudaStream_t stream);
+
 int dedf_build_arch(void);
 
 /* Self-test of the tcgen05 path (tc.cuh): D[128,N] = A[128,K] . B[N,K]^T on the tensor cores with the accumulator in TMEM;

@@ -174,9 +174,12 @@ def test_train_loss_forward_value(cuda):
     assert abs(loss.item() - loss_o.item()) <= 1e-4 * abs(loss_o.item())
     assert set(stats) >= {"Loss/train", "Loss/angular", "Loss/linear", "alignment/normalized/ang"}
     assert abs(stats["Loss/train"] - loss_o.item()) <= 1e-4 * abs(loss_o.item())
-    with pytest.raises(NotImplementedError):     # no backward kernels yet: must fail loudly, not silently skip gradients
-        model.get_train_loss(Ts.to(cuda), t.to(cuda), FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)),
-                             _fp(FeaturedPoints, grasp, cuda), ta.to(cuda), tl.to(cuda))
+    # with gradients enabled the training path (train_path.py) must give the same loss value (tests/test_gpu_train.py
+    # checks the gradients themselves)
+    loss_g, *_ = model.get_train_loss(Ts.to(cuda), t.to(cuda), FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)),
+                                      _fp(FeaturedPoints, grasp, cuda), ta.to(cuda), tl.to(cuda))
+    assert loss_g.requires_grad
+    assert abs(loss_g.item() - loss_o.item()) <= 1e-4 * abs(loss_o.item())
 
 
 def test_equivariance_full_size(cuda):

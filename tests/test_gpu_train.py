@@ -1,0 +1,74 @@
+"""Training path: get_train_loss with gradients through the hand-written backward kernels (csrc/train.cu) against
+torch autograd through the CPU oracle on the same seeded inputs and identical parameters (eval mode: no dropout).
+Tolerance: loss 1e-4 relative (the forward bar of BASELINE.json's north_star); gradients 2e-3 of each tensor's max-norm
+(fp32 atomics in a different summation order; the oracle itself runs in fp32)."""
+import pytest
+import torch
+
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(cuda, n_pts=1200, n_poses=6, seed=3):
+    from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel
+    from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs
+    from oracle import model as OM
+    torch.manual_seed(0)
+    oracle = OM.MultiscaleScoreModel(**model_kwargs(), deterministic=True).eval()
+    model = MultiscaleScoreModel(**model_kwargs(), deterministic=True).eval()
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda)
+    x, rgb = make_scene(n_pts, seed=seed, half_extent=10.0)
+    Ts, t = make_poses(n_poses, x, seed=seed, spread=5.0)
+    g = torch.Generator().manual_seed(seed)
+    tgt_a, tgt_l = torch.randn(n_poses, 3, generator=g), torch.randn(n_poses, 3, generator=g)
+    b = torch.zeros(len(x), dtype=torch.long)
+    grasp = (torch.zeros(8, 3), torch.zeros(8, 3), torch.zeros(8, dtype=torch.long))
+    return oracle, model, OM, FeaturedPoints, (x, rgb, b), grasp, Ts, t, tgt_a, tgt_l
+
+
+def test_train_loss_and_gradients_match_oracle(cuda):
+    oracle, model, OM, FP, (x, rgb, b), grasp, Ts, t, tgt_a, tgt_l = _setup(cuda)
+    loss_o, *_ = oracle.get_train_loss(Ts, t, OM.FeaturedPoints(x, rgb, b), OM.FeaturedPoints(*grasp), tgt_a, tgt_l)
+    loss_o.backward()
+    d = lambda v: v.to(cuda)
+    loss, fp_info, tensor_info, stats = model.get_train_loss(d(Ts), d(t), FP(d(x), d(rgb), d(b)), FP(*[d(v) for v in grasp]), d(tgt_a), d(tgt_l))
+    assert loss.requires_grad
+    loss.backward()
+    assert abs(float(loss) - float(loss_o)) <= 1e-4 * abs(float(loss_o)), (float(loss), float(loss_o))
+    assert abs(stats["Loss/train"] - float(loss_o)) <= 1e-4 * abs(float(loss_o))
+    po = dict(oracle.named_parameters())
+    worst, n_checked = [], 0
+    for name, p in model.named_parameters():
+        go = po[name].grad
+        if go is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, f"{name}: oracle has no gradient"
+            continue
+        assert p.grad is not None, f"{name}: no gradient on the CUDA path"
+        if float(go.abs().max()) < 1e-12:
+            assert float(p.grad.abs().max()) < 1e-6, name
+            continue
+        e = rel_err(p.grad, go)
+        worst.append((e, name))
+        n_checked += 1
+    worst.sort(reverse=True)
+    assert n_checked > 300, n_checked
+    assert worst[0][0] <= 2e-3, f"largest gradient errors: {worst[:8]}"
+
+
+def test_training_step_reduces_loss(cuda):
+    """A few Adam steps (the reference's optimiser settings, train_configs.yaml:70-75) on one synthetic demo batch."""
+    oracle, model, OM, FP, (x, rgb, b), grasp, Ts, t, tgt_a, tgt_l = _setup(cuda, n_pts=800, n_poses=4, seed=5)
+    d = lambda v: v.to(cuda)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-4, amsgrad=True)
+    args = (d(Ts), d(t), FP(d(x), d(rgb), d(b)), FP(*[d(v) for v in grasp]), d(tgt_a), d(tgt_l))
+    losses = []
+    for _ in range(6):
+        opt.zero_grad(set_to_none=True)
+        loss, *_ = model.get_train_loss(*args)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert losses[-1] < losses[0], losses

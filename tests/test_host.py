@@ -207,3 +207,42 @@ def test_place_config_state_dict_matches_oracle():
     assert set(sm) == set(so) and all(sm[k].shape == so[k].shape for k in sm)
     assert sm["query_model.weight_field.gnn_block_init.ffn.fctp_2.tp.weight"].shape == (192 * 64,)
     assert sm["query_model.weight_post.2.weight"].shape == (1, 64)
+
+
+def _grad_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from diffusion_edf_b200 import parallel
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2)),
+          torch.nn.Parameter(torch.zeros(4), requires_grad=False)]
+    ps[0].grad = torch.full((5, 3), float(rank + 1))
+    ps[1].grad = torch.arange(7, dtype=torch.float32) * (rank + 1)
+    # ps[2].grad stays None on rank 1 (a parameter one rank's demo did not touch): must count as zeros there
+    if rank == 0:
+        ps[2].grad = torch.ones(2, 2) * 4
+    n = parallel.allreduce_gradients(ps, average=True, bucket_bytes=64)      # tiny buckets: several collectives
+    q.put((rank, n, ps[0].grad.tolist(), ps[1].grad.tolist(), ps[2].grad.tolist(), ps[3].grad is None))
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_gloo_world2():
+    """Trainer config C5 plumbing: gradients averaged over ranks, bucketed, None gradients treated as zeros."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + os.getpid() % 2000
+    ps = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert r[1] >= 2                                            # bucketed into more than one all-reduce
+        assert r[2] == [[1.5] * 3] * 5
+        assert r[3] == [1.5 * i for i in range(7)]
+        assert r[4] == [[2.0, 2.0], [2.0, 2.0]]
+        assert r[5]
