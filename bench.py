@@ -26,6 +26,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/INFO; the contract is ONE JSON line on stdout
+if not os.environ.get("DEDF_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch  # noqa: E402
 
 N_POINTS, N_POSES = 10_000, 128
@@ -206,9 +210,12 @@ def run_cuda(args):
         key = FeaturedPoints(dv[0], dv[1], dv[2])
         grasp = FeaturedPoints(dv[5], dv[6], dv[7])
         with torch.no_grad():
-            if world == 1:
+            if world == 1 or not args.share_encoder:
+                # data parallel over poses: every rank runs the whole forward (scene encode included) on its own 128 poses,
+                # replayed as one CUDA graph; no data-path collective (the ranks only meet at the timing barrier)
                 (ang, lin), _ = model(dv[3], dv[4], key, grasp)
             else:
+                # variant: rank 0 encodes the scene and broadcasts the packed field (the set-up of the denoise loop, C3)
                 ang, lin = parallel.sharded_forward(model, dv[3], dv[4], key if rank == 0 else None, grasp, src=0, sizes=sizes)
         return ang, lin
 
@@ -241,7 +248,7 @@ def run_cuda(args):
     ms_local = sum(a.elapsed_time(bb) for a, bb in ev) / args.steps
     # ---------------- e2e: host (pinned) inputs -> H2D -> forward -> D2H of the scores, wall clock
     out_host = [torch.empty(N_POSES, 3).pin_memory(), torch.empty(N_POSES, 3).pin_memory()]
-    h2d = sum(v.numel() * v.element_size() for i, v in enumerate(host) if (rank == 0 or i >= 3))
+    h2d = sum(v.numel() * v.element_size() for i, v in enumerate(host) if (rank == 0 or i >= 3 or not args.share_encoder))
     d2h = sum(v.numel() * v.element_size() for v in out_host)
 
     def e2e_step():
@@ -311,7 +318,9 @@ def run_cuda(args):
         "precision_note": "fp32 arithmetic throughout; the per-edge MLP GEMMs run on the tcgen05 tensor cores as 3xTF32 (hi/lo split, "
                           "fp32 accumulation in TMEM), which the parity tests hold to the same 1e-4 bound as the CUDA-core kernels",
         "config": {"workload": WORKLOAD, "poses_per_gpu": N_POSES, "scene_points": N_POINTS, "weights": "random init, seed 0",
-                   "parallelism": f"pose-sharded x{world}; rank 0 encodes the scene, 1 NCCL broadcast of the packed field per step" if world > 1 else "single GPU",
+                   "parallelism": ("single GPU" if world == 1 else
+                                   f"pose-sharded x{world}; rank 0 encodes the scene, 1 NCCL broadcast of the packed field per step" if args.share_encoder else
+                                   f"data parallel x{world}: every rank runs the full forward on its own 128 poses (no data-path collective)"),
                    "l2": "flushed between timed steps (256 MB fill)", "timing": "CUDA events per step, max over ranks",
                    "execution": "whole forward replayed as one CUDA graph (graphs.py) with a forked geometry stream (graph construction + "
                                 "radial MLPs overlap the attention blocks) and programmatic dependent launch; step_breakdown measured eagerly"},
@@ -329,6 +338,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--share-encoder", action="store_true",
+                    help="N > 1: rank 0 encodes the scene and broadcasts the field instead of every rank encoding it")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
