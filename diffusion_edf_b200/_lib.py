@@ -100,6 +100,8 @@ _PROTOS = {
     "dedf_query_transform_bwd": [c_fp, c_int, c_int, C.POINTER(c_int), c_fp, c_fp, c_fp],
     "dedf_assemble_fwd": [c_fp, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp],
     "dedf_assemble_bwd": [c_fp, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp],
+    "dedf_dropout_mask": [c_ull, c_ull, c_ll, c_f, c_fp, c_fp],
+    "dedf_group_scale": [c_fp, c_fp, c_int, C.POINTER(c_int), c_int, c_fp, c_fp],
     "dedf_build_arch": [],
 }
 

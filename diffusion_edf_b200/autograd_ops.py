@@ -331,3 +331,37 @@ class AssembleFn(Function):
         ops._call("dedf_assemble_bwd", ptr(Ts), Ts.shape[0], qx.shape[0], n_vec, ptr(ylin), ptr(yang), ptr(qx), ptr(qw.detach()),
                   lin_mult, ptr(gang.contiguous()), ptr(glin.contiguous()), ptr(dyl), ptr(dya), ptr(dqw), stream())
         return dyl, dya, None, None, dqw, None, None
+
+
+# ------------------------------------------------------------------------------------------------ train-mode dropout
+def dropout_mask(shape, p: float, device) -> torch.Tensor:
+    """Philox mask of 0 / 1/(1-p).  Every mask takes a fresh 62-bit Philox seed from torch's CPU generator (no device
+    synchronisation), so torch.manual_seed() makes a training run reproducible."""
+    seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    n = 1
+    for v in shape:
+        n *= int(v)
+    out = torch.empty(*shape, dtype=torch.float32, device=device)
+    ops._call("dedf_dropout_mask", seed, 0, n, float(p), ptr(out), stream())
+    return out
+
+
+class GroupScaleFn(Function):
+    """x * mask broadcast per attention head (mode 0) or per irrep channel (mode 1); the mask is a constant."""
+
+    @staticmethod
+    def forward(ctx, x, mask, irr: Irr, mode: int):
+        x, mask = x.contiguous(), mask.contiguous()
+        y = torch.empty_like(x)
+        ops._call("dedf_group_scale", ptr(x), ptr(mask), x.shape[0], L.int_array(irr), mode, ptr(y), stream())
+        ctx.save_for_backward(mask)
+        ctx.cfg = (tuple(irr), mode)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        g = g.contiguous()
+        d = torch.empty_like(g)
+        ops._call("dedf_group_scale", ptr(g), ptr(mask), g.shape[0], L.int_array(ctx.cfg[0]), ctx.cfg[1], ptr(d), stream())
+        return d, None, None, None

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "cg_slots.cuh"
 #include "so3.cuh"
+#include <curand_kernel.h>
 #include "../../include/dedf.h"
 
 namespace dedf {
@@ -685,6 +686,34 @@ __global__ void assemble_bwd_kernel(const float* __restrict__ Ts, int n_t, int n
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// train-mode dropout (graph_attention.py:111-112 alpha_dropout = nn.Dropout on the attention weights; :119-120 proj_drop =
+// EquivariantDropout: one Bernoulli per (node, irrep channel), equiformer/drop.py:76-96)
+// ---------------------------------------------------------------------------------------------------------------
+// out[i] = 0 with probability p, else 1 / (1 - p)   (Philox, counter = offset + i)
+__global__ void dropout_mask_kernel(unsigned long long seed, unsigned long long offset, long long n, float p, float* __restrict__ out) {
+    const float keep = 1.0f / (1.0f - p);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, (unsigned long long)i + offset, 0, &st);
+        out[i] = (curand_uniform(&st) <= p) ? 0.f : keep;
+    }
+}
+// y[r, c] = x[r, c] * mask[r, g(c)]: mode 0: g = attention head of channel c (mask (n,4)); mode 1: g = irrep channel (mask (n, m0+m1+m2))
+__global__ void group_scale_kernel(const float* __restrict__ x, const float* __restrict__ mask, int n, Irr irr, int mode, float* __restrict__ y) {
+    const int F = irr.dim(), NG = mode ? irr.nirr() : 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n * F; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / F), c = (int)(i % F);
+        int u;
+        if (c < irr.m0) u = c;
+        else if (c < irr.off2()) u = irr.m0 + (c - irr.m0) / 3;
+        else u = irr.m0 + irr.m1 + (c - irr.off2()) / 5;
+        int gidx = u;
+        if (!mode) gidx = (u < irr.m0) ? u / (irr.m0 / 4) : (u < irr.m0 + irr.m1) ? (u - irr.m0) / (irr.m1 / 4) : (u - irr.m0 - irr.m1) / (irr.m2 / 4);
+        y[i] = x[i] * mask[(size_t)r * NG + gidx];
+    }
+}
+
 }  // namespace dedf
 
 using namespace dedf;
@@ -889,6 +918,23 @@ extern "C" int dedf_assemble_bwd(const float* Ts, int n_t, int n_q, int n_vec, c
     if (!Ts || !ylin || !yang || !qx || !qw || !gang || !glin || !dylin || !dyang || !dqw) return DEDF_ERR_ARG;
     if (n_t <= 0) return DEDF_OK;
     assemble_bwd_kernel<<<(n_t + 127) / 128, 128, 0, stream>>>(Ts, n_t, n_q, n_vec, ylin, yang, qx, qw, lin_mult, gang, glin, dylin, dyang, dqw);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_dropout_mask(unsigned long long seed, unsigned long long offset, long long n, float p, float* out, cudaStream_t stream) {
+    if (!out || p < 0.f || p >= 1.f) return DEDF_ERR_ARG;
+    if (n <= 0) return DEDF_OK;
+    dropout_mask_kernel<<<DEDF_GRID(n), 256, 0, stream>>>(seed, offset, n, p, out);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+extern "C" int dedf_group_scale(const float* x, const float* mask, int n, const int* irr, int mode, float* y, cudaStream_t stream) {
+    if (!x || !mask || !irr || !y) return DEDF_ERR_ARG;
+    if (mode == 0 && (irr[0] % 4 || irr[1] % 4 || irr[2] % 4)) return DEDF_ERR_UNSUPPORTED;
+    if (n <= 0) return DEDF_OK;
+    const Irr ir{irr[0], irr[1], irr[2]};
+    group_scale_kernel<<<DEDF_GRID((long long)n * ir.dim()), 256, 0, stream>>>(x, mask, n, ir, mode, y);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

@@ -53,6 +53,7 @@ class MultiscaleTensorField(nn.Module):
         if cutoff_method != "edge_attn" or attn_type != "mlp" or n_layers != 1:
             raise NotImplementedError("only cutoff_method='edge_attn', attn_type='mlp', n_layers=1 are implemented")
         self.use_dst_feature = False
+        self.alpha_drop, self.proj_drop = float(alpha_drop), float(proj_drop)       # train mode only (train_path.py)
         self.num_heads = num_heads
         fc_neurons = list(fc_neurons)
         self.length_emb_dim, self.context_emb_dim = length_emb_dim, edge_context_emb_dim

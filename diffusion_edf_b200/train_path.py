@@ -5,8 +5,8 @@ gather + tensor product + linear and never materialise the (E, 49 G) tensor-prod
 for the weight gradients.  Mirrors the reference's arithmetic order (not the inference path's exact reassociations):
   gnn_block.py:164-218 / block.py:141-174 (EquiformerBlock), graph_attention.py:84-122, :218-273 (GraphAttentionMLP(2)),
   multiscale_tensor_field.py:192-260, graph_parser.py:146-224, unet_feature_extractor.py:260-417, score_head.py:142-211.
-Dropout (alpha_drop / proj_drop, active in the reference's train mode) is not applied: gradients are those of the
-deterministic network (the parity tests compare against the oracle in eval mode).
+Train-mode dropout (alpha_drop on the attention weights, proj_drop = EquivariantDropout after proj) is applied when the
+module is in train() mode, with Philox masks; the parity tests compare against the oracle in eval mode.
 """
 from __future__ import annotations
 
@@ -73,7 +73,8 @@ def ffn(mod, x: torch.Tensor) -> torch.Tensor:
 
 
 def graph_attention(ga: GraphAttention, msg_src: torch.Tensor, msg_dst: Optional[torch.Tensor], g: ops.Csr, sh: torch.Tensor,
-                    w: torch.Tensor, edge_logit: Optional[torch.Tensor]) -> torch.Tensor:
+                    w: torch.Tensor, edge_logit: Optional[torch.Tensor], drop=(0.0, 0.0)) -> torch.Tensor:
+    """-> proj(sum_e softmax_e value_e) incl. the train-mode dropouts ``drop`` = (alpha_drop, proj_drop)."""
     G = ga.irreps_emb.m[1]
     E = g.n_edges
     es, ed = g.edge_src[:E].contiguous(), g.edge_dst[:E].contiguous()
@@ -87,10 +88,16 @@ def graph_attention(ga: GraphAttention, msg_src: torch.Tensor, msg_dst: Optional
     v = A.GateFn.apply(linear_rs(ga.sep_act.lin, m), ga.sep_act.lin.irreps_out.m)
     m2 = A.DtpFn.apply(v, sh, ga.sep_value.dtp.tp.weight, G)
     val = linear_rs(ga.sep_value.lin, m2)
-    return A.SoftmaxReduceFn.apply(logits, val, g, ga.irreps_emb.m)
+    if drop[0] > 0.0:       # nn.Dropout on alpha (E, heads): sum_e (alpha_e m_e) v_e == sum_e alpha_e (m_e v_e)
+        val = A.GroupScaleFn.apply(val, A.dropout_mask((E, 4), drop[0], val.device), ga.irreps_emb.m, 0)
+    out = linear_rs(ga.proj, A.SoftmaxReduceFn.apply(logits, val, g, ga.irreps_emb.m))
+    if drop[1] > 0.0:       # EquivariantDropout: one Bernoulli per (node, irrep channel)
+        irr = ga.proj.irreps_out
+        out = A.GroupScaleFn.apply(out, A.dropout_mask((out.shape[0], irr.num_irreps), drop[1], out.device), irr.m, 1)
+    return out
 
 
-def unet_block(blk, f_src, f_dst, geom, radial) -> torch.Tensor:
+def unet_block(blk, f_src, f_dst, geom, radial, drop=(0.0, 0.0)) -> torch.Tensor:
     """block.EquiformerBlock (UNet): norm_1_* are computed-and-discarded in the reference (block.py:149-153)."""
     msg_src = linear_rs(blk.linear_src, f_src)
     msg_dst = linear_rs(blk.linear_dst, f_dst)
@@ -98,8 +105,8 @@ def unet_block(blk, f_src, f_dst, geom, radial) -> torch.Tensor:
     emb = A.RbfFn.apply(geom.length[:E], radial.mean, radial.std_logit, radial.weight_logit, radial.offset,
                         1.0 / (radial.cutoff - radial.offset), 1)
     w = radial_profile(blk.ga.sep_act.dtp_rad, emb)
-    attn = graph_attention(blk.ga, msg_src, msg_dst, geom.g, geom.sh[:E], w, None)
-    out = A.AddScaleFn.apply(linear_rs(blk.ga.proj, attn), f_dst, 1.0)
+    attn = graph_attention(blk.ga, msg_src, msg_dst, geom.g, geom.sh[:E], w, None, drop)
+    out = A.AddScaleFn.apply(attn, f_dst, 1.0)
     return A.AddScaleFn.apply(ffn(blk.ffn, layer_norm(blk.norm_2, out)), out, 1.0)
 
 
@@ -110,8 +117,10 @@ def unet_forward(net, pcd: FeaturedPoints) -> List[FeaturedPoints]:
     outs, graphs = [(f, x, b)], []
     geom = None
 
+    drop = (net.alpha_drop, net.proj_drop) if net.training else (0.0, 0.0)
+
     def run(layer, f_src, f_dst, gm):
-        return unet_block(layer["gnn"], f_src, f_dst, gm, layer["radial"])
+        return unet_block(layer["gnn"], f_src, f_dst, gm, layer["radial"], drop)
 
     for n, blk in enumerate(net.down_blocks):
         idx = ops.fps(x, b, net.pool_ratio[n], random_start=not net.deterministic)
@@ -202,8 +211,8 @@ def tensor_field(field, query_x: torch.Tensor, query_b: torch.Tensor, keys: List
         raise NotImplementedError("training step with an empty query graph")
     edge_scalars = torch.cat(scalars, dim=0)
     w = radial_profile(blk.ga.sep_act.dtp_rad, edge_scalars)
-    attn = graph_attention(blk.ga, msg_src, None, g, sh[:E], w, logit[:E])
-    emb = linear_rs(blk.ga.proj, attn)
+    drop = (field.alpha_drop, field.proj_drop) if field.training else (0.0, 0.0)
+    emb = graph_attention(blk.ga, msg_src, None, g, sh[:E], w, logit[:E], drop)
     skip = emb if blk.skip_2.is_identity else project_if_mismatch(blk.skip_2, emb)
     return A.AddScaleFn.apply(ffn(blk.ffn, layer_norm(blk.post_norm, emb)), skip, 1.0)
 

@@ -53,6 +53,7 @@ class UnetFeatureExtractor(nn.Module):
         self.irreps_edge_attr = [Irreps(i) for i in irreps_edge_attr]
         self.num_heads, self.fc_neurons, self.pool_ratio, self.n_layers = num_heads, fc_neurons, pool_ratio, n_layers
         self.deterministic = deterministic
+        self.alpha_drop, self.proj_drop = float(alpha_drop), float(proj_drop)     # train mode only (train_path.py)
         self.n_layers_midstream = n_layers_midstream
         if irreps_input is None:
             raise NotImplementedError("irreps_input=None")

@@ -280,6 +280,12 @@ int dedf_assemble_bwd(const float* Ts, int n_t, int n_q, int n_vec, const float*
                       const float* qw, float lin_mult, const float* gang, const float* glin, float* dylin, float* dyang,
                       float* dqw, cudaStream_t stream);
 
+/* train-mode dropout: Philox mask (0 or 1/(1-p)); y = x * mask broadcast per attention head (mode 0, mask (n,4): nn.Dropout
+ * on the attention weights, graph_attention.py:111-112) or per irrep channel (mode 1, mask (n, m0+m1+m2):
+ * EquivariantDropout, equiformer/drop.py:76-96).  The backward of group_scale is group_scale on the gradient. */
+int dedf_dropout_mask(unsigned long long seed, unsigned long long offset, long long n, float p, float* out, cudaStream_t stream);
+int dedf_group_scale(const float* x, const float* mask, int n, const int* irr_host, int mode, float* y, cudaStream_t stream);
+
 int dedf_build_arch(void);
 
 /* Self-test of the tcgen05 path (tc.cuh): D[128,N] = A[128,K] . B[N,K]^T on the tensor cores with the accumulator in TMEM;

@@ -47,7 +47,7 @@ def step():
 
 losses = []
 for _ in range(3):
-    losses.append(float(step()[0]))
+    losses.append(float(step()[0].detach()))
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
@@ -57,7 +57,7 @@ t0 = time.perf_counter()
 e0.record()
 for _ in range(steps):
     loss, n_coll = step()
-    losses.append(float(loss))
+    losses.append(float(loss.detach()))
 e1.record()
 torch.cuda.synchronize()
 wall = time.perf_counter() - t0

@@ -36,7 +36,7 @@ def test_train_loss_and_gradients_match_oracle(cuda):
     loss, fp_info, tensor_info, stats = model.get_train_loss(d(Ts), d(t), FP(d(x), d(rgb), d(b)), FP(*[d(v) for v in grasp]), d(tgt_a), d(tgt_l))
     assert loss.requires_grad
     loss.backward()
-    assert abs(float(loss) - float(loss_o)) <= 1e-4 * abs(float(loss_o)), (float(loss), float(loss_o))
+    assert abs(float(loss.detach()) - float(loss_o.detach())) <= 1e-4 * abs(float(loss_o.detach())), (float(loss.detach()), float(loss_o.detach()))
     assert abs(stats["Loss/train"] - float(loss_o)) <= 1e-4 * abs(float(loss_o))
     po = dict(oracle.named_parameters())
     worst, n_checked = [], 0
@@ -72,3 +72,29 @@ def test_training_step_reduces_loss(cuda):
         losses.append(float(loss))
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < losses[0], losses
+
+
+def test_train_mode_dropout(cuda):
+    """train() mode applies the reference's dropouts (alpha_drop / proj_drop = 0.1, graph_attention.py:111-120) with Philox
+    masks: reproducible under torch.manual_seed, different from the eval-mode loss, unbiased masks."""
+    from diffusion_edf_b200 import autograd_ops as A
+    oracle, model, OM, FP, (x, rgb, b), grasp, Ts, t, tgt_a, tgt_l = _setup(cuda, n_pts=800, n_poses=4, seed=7)
+    d = lambda v: v.to(cuda)
+    args = (d(Ts), d(t), FP(d(x), d(rgb), d(b)), FP(*[d(v) for v in grasp]), d(tgt_a), d(tgt_l))
+    loss_eval = float(model.get_train_loss(*args)[0].detach())
+    model.train()
+    losses = []
+    for _ in range(2):
+        torch.manual_seed(123)
+        loss, *_ = model.get_train_loss(*args)
+        loss.backward()
+        losses.append(float(loss.detach()))
+    assert losses[0] == losses[1], losses                      # same seed, same masks
+    assert abs(losses[0] - loss_eval) > 1e-6 * abs(loss_eval)   # dropout really changed the forward
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    torch.manual_seed(5)
+    m = A.dropout_mask((200_000,), 0.1, cuda)
+    vals = torch.unique(m)
+    assert len(vals) == 2 and float(vals[0]) == 0.0 and abs(float(vals[1]) - 1 / 0.9) < 1e-6
+    assert abs(float(m.mean()) - 1.0) < 0.01 and abs(float((m == 0).float().mean()) - 0.1) < 0.005
+    model.eval()
