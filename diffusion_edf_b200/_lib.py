@@ -83,8 +83,8 @@ _PROTOS = {
     "dedf_ln_bwd": [c_fp, c_fp, c_int, C.POINTER(c_int), c_fp, c_f, c_fp, c_fp, c_fp, c_fp],
     "dedf_gate_fwd": [c_fp, c_int, C.POINTER(c_int), c_fp, c_fp],
     "dedf_gate_bwd": [c_fp, c_fp, c_int, C.POINTER(c_int), c_fp, c_fp],
-    "dedf_act_fwd": [c_fp, c_ll, c_fp, c_fp],
-    "dedf_act_bwd": [c_fp, c_fp, c_ll, c_fp, c_fp],
+    "dedf_act_fwd": [c_fp, c_ll, c_int, c_fp, c_fp],
+    "dedf_act_bwd": [c_fp, c_fp, c_ll, c_int, c_fp, c_fp],
     "dedf_dtp_fwd": [c_int, c_fp, c_fp, c_fp, c_ll, c_int, c_fp, c_fp],
     "dedf_dtp_bwd": [c_int, c_fp, c_fp, c_fp, c_ll, c_fp, c_int, c_fp, c_fp, c_fp],
     "dedf_gather_rows_i32": [c_fp, c_fp, c_int, c_int, c_fp, c_fp],
@@ -102,6 +102,7 @@ _PROTOS = {
     "dedf_assemble_bwd": [c_fp, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp],
     "dedf_dropout_mask": [c_ull, c_ull, c_ll, c_f, c_fp, c_fp],
     "dedf_group_scale": [c_fp, c_fp, c_int, C.POINTER(c_int), c_int, c_fp, c_fp],
+    "dedf_ebm_energy": [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_f, c_fp, c_fp],
     "dedf_build_arch": [],
 }
 

@@ -109,21 +109,36 @@ class GateFn(Function):
         return d, None
 
 
-class SiluFn(Function):
+class ActFn(Function):
+    """Elementwise activation: mode 0 SiLU (nn.SiLU, no normalisation constant), mode 1 sigmoid."""
+
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, mode: int):
         x = x.contiguous()
         y = torch.empty_like(x)
-        ops._call("dedf_act_fwd", ptr(x), x.numel(), ptr(y), stream())
+        ops._call("dedf_act_fwd", ptr(x), x.numel(), mode, ptr(y), stream())
         ctx.save_for_backward(x)
+        ctx.mode = mode
         return y
 
     @staticmethod
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
         d = torch.empty_like(x)
-        ops._call("dedf_act_bwd", ptr(x), ptr(g.contiguous()), x.numel(), ptr(d), stream())
-        return d
+        ops._call("dedf_act_bwd", ptr(x), ptr(g.contiguous()), x.numel(), ctx.mode, ptr(d), stream())
+        return d, None
+
+
+class SiluFn:
+    @staticmethod
+    def apply(x):
+        return ActFn.apply(x, 0)
+
+
+class SigmoidFn:
+    @staticmethod
+    def apply(x):
+        return ActFn.apply(x, 1)
 
 
 class DtpFn(Function):

@@ -399,6 +399,25 @@ __global__ void cast_pose_kernel(const double* __restrict__ T, int n, float* __r
     if (counter && i == 0) *counter += 1;      // runs after pose_update_kernel on the same stream
 }
 
+// EbmScoreModelHead.compute_energy tail (score_head_ebm.py:171-172): one CTA per pose
+__global__ void __launch_bounds__(128) ebm_energy_kernel(const float* __restrict__ key_f, const float* __restrict__ query_f,
+                                                        const float* __restrict__ qw, int n_q, int F, float scale, float* __restrict__ out) {
+    pdl_wait(); pdl_launch();
+    __shared__ float red[4];
+    const int t = blockIdx.x, tid = threadIdx.x;
+    float acc = 0.f;
+    for (int q = 0; q < n_q; ++q) {
+        const size_t row = ((size_t)t * n_q + q) * F;
+        float s = 0.f;
+        for (int c = tid; c < F; c += blockDim.x) { const float d = key_f[row + c] - query_f[row + c]; s = fmaf(d, d, s); }
+        acc = fmaf(qw[q], s, acc);
+    }
+    acc = warp_sum(acc);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) out[t] = (red[0] + red[1] + red[2] + red[3]) * scale;
+}
+
 }  // namespace dedf
 
 using namespace dedf;
@@ -479,6 +498,15 @@ extern "C" int dedf_sample_advance(const double* sched, int n_steps, int* counte
     if (!sched || !counter || !time_out || !cur_row || n_steps <= 0) return DEDF_ERR_ARG;
     SampleState s{sched, n_steps, counter, time_out, cur_row};
     sample_advance_kernel<<<1, 32, 0, stream>>>(s);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_ebm_energy(const float* key_f, const float* query_f, const float* qw, int n_t, int n_q, int F, float scale,
+                               float* out, cudaStream_t stream) {
+    if (!key_f || !query_f || !qw || !out || F <= 0) return DEDF_ERR_ARG;
+    if (n_t <= 0) return DEDF_OK;
+    launch_pdl(ebm_energy_kernel, dim3(n_t), dim3(128), 0, stream, key_f, query_f, qw, n_q, F, scale, out);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

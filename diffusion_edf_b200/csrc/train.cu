@@ -182,11 +182,16 @@ __global__ void gate_bwd_kernel(const float* __restrict__ pre, const float* __re
     }
 }
 
-__global__ void act_fwd_kernel(const float* __restrict__ x, long long n, float* __restrict__ y) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = siluf_(x[i]);
+// mode 0: SiLU ; mode 1: sigmoid
+__global__ void act_fwd_kernel(const float* __restrict__ x, long long n, int mode, float* __restrict__ y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = mode ? sigmoidf_(x[i]) : siluf_(x[i]);
 }
-__global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, long long n, float* __restrict__ dx) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dx[i] = g[i] * dsiluf_(x[i]);
+__global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, long long n, int mode, float* __restrict__ dx) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float s = sigmoidf_(x[i]);
+        dx[i] = g[i] * (mode ? s * (1.0f - s) : dsiluf_(x[i]));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -772,17 +777,17 @@ extern "C" int dedf_gate_bwd(const float* pre, const float* g, int n, const int*
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
-extern "C" int dedf_act_fwd(const float* x, long long n, float* y, cudaStream_t stream) {
-    if (!x || !y) return DEDF_ERR_ARG;
+extern "C" int dedf_act_fwd(const float* x, long long n, int mode, float* y, cudaStream_t stream) {
+    if (!x || !y || mode < 0 || mode > 1) return DEDF_ERR_ARG;
     if (n <= 0) return DEDF_OK;
-    act_fwd_kernel<<<DEDF_GRID(n), 256, 0, stream>>>(x, n, y);
+    act_fwd_kernel<<<DEDF_GRID(n), 256, 0, stream>>>(x, n, mode, y);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
-extern "C" int dedf_act_bwd(const float* x, const float* g, long long n, float* dx, cudaStream_t stream) {
-    if (!x || !g || !dx) return DEDF_ERR_ARG;
+extern "C" int dedf_act_bwd(const float* x, const float* g, long long n, int mode, float* dx, cudaStream_t stream) {
+    if (!x || !g || !dx || mode < 0 || mode > 1) return DEDF_ERR_ARG;
     if (n <= 0) return DEDF_OK;
-    act_bwd_kernel<<<DEDF_GRID(n), 256, 0, stream>>>(x, g, n, dx);
+    act_bwd_kernel<<<DEDF_GRID(n), 256, 0, stream>>>(x, g, n, mode, dx);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

@@ -27,15 +27,17 @@ class MultiscaleScoreModel(ScoreModelBase):
             self.query_model = KeypointExtractor(**query_kwargs, deterministic=deterministic)
         else:
             raise ValueError(f"Unknown query model: {query_model}")
-        if score_head_kwargs.get("ebm", False):
-            raise NotImplementedError("EbmScoreModelHead is out of scope (SURVEY.md 8f)")
+        head_cls = ScoreModelHead
+        if score_head_kwargs.get("ebm", False):       # critic configs (*_ebm): energy only, see score_head_ebm.py
+            from .score_head_ebm import EbmScoreModelHead
+            head_cls = EbmScoreModelHead
         kw = score_head_kwargs["key_tensor_field_kwargs"]
         # same in-place kwargs mutation as the reference (multiscale_score_model.py:79-85)
         assert "irreps_input" not in kw and "use_src_point_attn" not in kw and "use_dst_point_attn" not in kw
         kw["irreps_input"] = self.key_model.irreps_output
         kw["use_src_point_attn"] = False
         kw["use_dst_point_attn"] = False
-        self.score_head = ScoreModelHead(max_time=float(score_head_kwargs["max_time"]),
+        self.score_head = head_cls(max_time=float(score_head_kwargs["max_time"]),
                                          time_emb_mlp=score_head_kwargs["time_emb_mlp"], key_tensor_field_kwargs=kw,
                                          irreps_query_edf=self.query_model.irreps_output,
                                          lin_mult=float(score_head_kwargs["lin_mult"]), ang_mult=float(score_head_kwargs["ang_mult"]),

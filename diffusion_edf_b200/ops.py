@@ -401,3 +401,10 @@ def pose_update(T: torch.Tensor, ang: torch.Tensor, lin: torch.Tensor, noise: Op
 def sample_advance(sched: torch.Tensor, counter: torch.Tensor, time_out: torch.Tensor, cur_row: torch.Tensor) -> None:
     _call("dedf_sample_advance", ptr(sched, torch.float64), sched.shape[0], ptr(counter, torch.int32), ptr(time_out),
           ptr(cur_row, torch.float64), stream())
+
+
+def ebm_energy(key_f: torch.Tensor, query_f: torch.Tensor, qw: torch.Tensor, n_t: int, n_q: int, scale: float) -> torch.Tensor:
+    """energy[t] = scale * sum_q w_q |key_f[t,q] - query_f[t,q]|^2   (score_head_ebm.py:171-172)."""
+    out = torch.empty(n_t, dtype=torch.float32, device=key_f.device)
+    _call("dedf_ebm_energy", ptr(key_f.contiguous()), ptr(query_f.contiguous()), ptr(qw), n_t, n_q, key_f.shape[1], scale, ptr(out), stream())
+    return out

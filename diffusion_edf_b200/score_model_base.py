@@ -45,11 +45,12 @@ class ScoreModelBase(nn.Module):
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
             from . import train_path
-            from .keypoint_extractor import StaticKeypointModel
-            if not isinstance(self.query_model, StaticKeypointModel):
-                raise NotImplementedError("the training path covers StaticKeypointModel configs (pick_*); KeypointExtractor is forward-only")
+            from .keypoint_extractor import KeypointExtractor
             key_ms = train_path.unet_forward(self.key_model, key_pcd)
-            q = self.get_query_pcd(query_pcd)
+            if isinstance(self.query_model, KeypointExtractor):
+                q = train_path.keypoint_extractor(self.query_model, query_pcd)      # place configs
+            else:
+                q = self.get_query_pcd(query_pcd)                                    # StaticKeypointModel: torch views of parameters
             ang, lin = train_path.score_head(self.score_head, Ts, key_ms, q, time)
         else:
             key_ms = self.get_key_pcd_multiscale(key_pcd)

@@ -64,6 +64,20 @@ def model_kwargs_place() -> Dict:
     return kw
 
 
+def model_kwargs_ebm() -> Dict:
+    """model_kwargs of configs/panda_mug/pick_ebm/score_model_configs.yaml (the critic): pick_lowres with ``ebm: True``, no
+    time encoding, key-field radii [3.5, 5, 6.5, 8] cm (all finite, no length_enc_max_r) and UNet pool ratio 0.25."""
+    kw = copy.deepcopy(PANDA_MUG_PICK_LOWRES)
+    sh = kw["score_head_kwargs"]
+    sh["ebm"] = True
+    sh["edge_time_encoding"] = False
+    sh["query_time_encoding"] = False
+    sh["key_tensor_field_kwargs"]["r_cluster_multiscale"] = [3.5, 5.0, 6.5, 8.0]
+    sh["key_tensor_field_kwargs"].pop("length_enc_max_r", None)
+    kw["key_kwargs"]["feature_extractor_kwargs"]["pool_ratio"] = [0.25, 0.25, 0.25, 0.25]
+    return kw
+
+
 def make_scene(n_points: int = 10_000, seed: int = 0, half_extent: float = 30.0) -> Tuple[torch.Tensor, torch.Tensor]:
     """Surface-like cloud (cm): table plane z=0 over [-h,h]^2 plus spheres / cylinders / boxes of radius 3-8 cm,
     jitter sigma 0.3 cm, 1 cm voxel average, random-subsampled / padded to exactly ``n_points``.  -> (x (N,3), rgb (N,3))"""

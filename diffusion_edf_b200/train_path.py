@@ -242,3 +242,20 @@ def score_head(head, Ts: torch.Tensor, keys: List[FeaturedPoints], query: Featur
         ys.append(A.GateFn.apply(y, tp.lin.irreps_out.m))
     ang, lin = A.AssembleFn.apply(ys[0], ys[1], Ts, qx, query.w, head.n_irreps_prescore, head.lin_mult)
     return ang, lin
+
+
+# ------------------------------------------------------------------------------------------------ place configs' query model
+def keypoint_extractor(mod, input_points: FeaturedPoints) -> FeaturedPoints:
+    """KeypointExtractor.forward (keypoint_extractor.py:139-197) with gradients: own UNet -> bbox + FPS query points (no
+    gradient: indices) -> feature field and weight field at the query points -> weight head."""
+    if mod.weight_mult_logit is not None or not mod.use_sigmoid:
+        raise NotImplementedError("training path: weight_activation='sigmoid', weight_mult=None (every shipped place config)")
+    keys = unet_forward(mod.feature_extractor, input_points)
+    with torch.no_grad():
+        q = mod.get_query_points(input_points)
+    f = tensor_field(mod.tensor_field, q.x, q.b, keys, None, 1)
+    wf = tensor_field(mod.weight_field, q.x, q.b, keys, None, 1)
+    ln, lin = mod.weight_post[0], mod.weight_post[2]
+    h = A.SiluFn.apply(A.LayerNormFn.apply(wf, ln.weight, ln.bias, (ln.normalized_shape[0], 0, 0), ln.eps))
+    w = A.SigmoidFn.apply(nn_linear(lin, h)).reshape(-1)
+    return FeaturedPoints(x=q.x, f=f, b=q.b, w=w)

@@ -223,6 +223,10 @@ int dedf_sample_advance(const double* sched, int n_steps, int* counter, float* t
                         cudaStream_t stream);
 
 /* library self-description: returns the compute capability the kernels were built for (100) */
+/* EbmScoreModelHead.compute_energy tail (score_head_ebm.py:171-172): energy[t] = scale * sum_q w_q |key_f[t,q,:] - query_f[t,q,:]|^2 */
+int dedf_ebm_energy(const float* key_f, const float* query_f, const float* qw, int n_t, int n_q, int F, float scale, float* out,
+                    cudaStream_t stream);
+
 /* ---- training path (un-fused primitives + their backward kernels) ---------------------------------------------
  * The reference trains through torch autograd over e3nn / torch_scatter ops (trainer.py:308-346 ->
  * score_model_base.py:41-107).  diffusion_edf_b200/autograd_ops.py wraps the pairs below in torch.autograd.Function so
@@ -237,11 +241,11 @@ int dedf_lin_wgrad(const float* x, const float* dy, int n, const int* irr_in_hos
 int dedf_ln_fwd(const float* x, int n, const int* irr_host, const float* w, const float* b, float eps, float* y, cudaStream_t stream);
 int dedf_ln_bwd(const float* x, const float* g, int n, const int* irr_host, const float* w, float eps, float* dx, float* dw,
                 float* db, cudaStream_t stream);
-/* Gate (equiformer/fast_activation.py:210-224): irr_pre = pre-gate irreps (m0 = scalars + gates); plain SiLU: act_*. */
+/* Gate (equiformer/fast_activation.py:210-224): irr_pre = pre-gate irreps (m0 = scalars + gates); plain SiLU / sigmoid: act_*. */
 int dedf_gate_fwd(const float* pre, int n, const int* irr_pre_host, float* y, cudaStream_t stream);
 int dedf_gate_bwd(const float* pre, const float* g, int n, const int* irr_pre_host, float* dpre, cudaStream_t stream);
-int dedf_act_fwd(const float* x, long long n, float* y, cudaStream_t stream);
-int dedf_act_bwd(const float* x, const float* g, long long n, float* dx, cudaStream_t stream);
+int dedf_act_fwd(const float* x, long long n, int mode, float* y, cudaStream_t stream);      /* mode 0: SiLU, 1: sigmoid */
+int dedf_act_bwd(const float* x, const float* g, long long n, int mode, float* dx, cudaStream_t stream);
 /* DepthwiseTensorProduct 'uvu' (tensor_product_rescale.py:352-382): out (E, 49 mul1) in the sorted-irreps layout; w per edge
  * (w_stride = 15 mul1) or shared (w_stride = 0, dw accumulated). */
 int dedf_dtp_fwd(int mul1, const float* x, const float* sh, const float* w, long long w_stride, int n_edges, float* out,

@@ -447,6 +447,48 @@ class ScoreModelHead(nn.Module):
         return ang_vel, lin_vel
 
 
+class EbmScoreModelHead(nn.Module):
+    """Energy-based head (critic), /root/reference/diffusion_edf/score_head_ebm.py:32-222.  ``compute_energy`` is what
+    agent.py:163-174 calls to re-rank samples; ``forward`` (the score as the gradient of the energy w.r.t. the pose,
+    :192-222) is restated with torch autograd."""
+
+    def __init__(self, max_time, time_emb_mlp, key_tensor_field_kwargs, irreps_query_edf, lin_mult, ang_mult,
+                 time_enc_n=10000.0, edge_time_encoding=False, query_time_encoding=True):
+        super().__init__()
+        assert not edge_time_encoding and not query_time_encoding, "the shipped *_ebm configs use no time encoding"
+        self.lin_mult, self.ang_mult = lin_mult, ang_mult
+        kw = dict(key_tensor_field_kwargs)
+        self.n_scales = len(kw["r_cluster_multiscale"])
+        self.time_emb_mlp = list(time_emb_mlp)
+        self.time_enc = enc.SinusoidalPositionEmbeddings(dim=time_emb_mlp[0], max_val=max_time, n=time_enc_n)
+        self.time_mlps_multiscale = nn.ModuleList()
+        for _ in range(self.n_scales):                      # present in the state_dict, unused without time encoding
+            layers = []
+            for i in range(1, len(time_emb_mlp)):
+                layers.append(nn.Linear(time_emb_mlp[i - 1], time_emb_mlp[i]))
+                if i != len(time_emb_mlp) - 1:
+                    layers.append(nn.SiLU())
+            self.time_mlps_multiscale.append(nn.Sequential(*layers))
+        kw["irreps_query"] = None
+        kw["edge_context_emb_dim"] = None
+        self.key_tensor_field = MultiscaleTensorField(**kw)
+        self.irreps_key_edf = self.key_tensor_field.irreps_output
+        self.irreps_query_edf = Irreps(irreps_query_edf)
+        self.query_transform = TransformPcd(self.irreps_query_edf)
+        self.register_buffer("q_indices", torch.tensor([[1, 2, 3], [0, 3, 2], [3, 0, 1], [2, 1, 0]], dtype=torch.long), persistent=False)
+        self.register_buffer("q_factor", torch.tensor([[-0.5, -0.5, -0.5], [0.5, -0.5, 0.5], [0.5, 0.5, -0.5], [-0.5, 0.5, 0.5]]), persistent=False)
+        self.energy_rescale_factor = 1.0 / float(self.irreps_key_edf.dim)
+
+    def compute_energy(self, Ts, key_pcd_multiscale: List[FeaturedPoints], query_pcd: FeaturedPoints, time):
+        nT, nQ = len(Ts), len(query_pcd.x)
+        qt = self.query_transform(pcd=query_pcd, Ts=Ts)
+        qf = qt.f.clone().reshape(-1, qt.f.shape[-1])
+        flat = FeaturedPoints(x=qt.x.reshape(-1, 3), f=torch.empty_like(qf), b=qt.b.reshape(-1), w=None)
+        field = self.key_tensor_field(query_points=flat, input_points_multiscale=key_pcd_multiscale, context_emb=None)
+        energy = (field.f - qf).square().sum(dim=-1) * self.energy_rescale_factor
+        return torch.einsum("q,tq->t", query_pcd.w, energy.view(nT, nQ))
+
+
 class StaticKeypointModel(nn.Module):
     def __init__(self, keypoint_coords, irreps_output):
         super().__init__()
@@ -657,7 +699,8 @@ class MultiscaleScoreModel(nn.Module):
             self.query_model = KeypointExtractor(**query_kwargs, deterministic=deterministic)
         kw = dict(score_head_kwargs["key_tensor_field_kwargs"])
         kw.update(irreps_input=self.key_model.irreps_output, use_src_point_attn=False, use_dst_point_attn=False)
-        self.score_head = ScoreModelHead(max_time=float(score_head_kwargs["max_time"]),
+        head_cls = EbmScoreModelHead if score_head_kwargs.get("ebm", False) else ScoreModelHead
+        self.score_head = head_cls(max_time=float(score_head_kwargs["max_time"]),
                                          time_emb_mlp=score_head_kwargs["time_emb_mlp"],
                                          key_tensor_field_kwargs=kw, irreps_query_edf=self.query_model.irreps_output,
                                          lin_mult=float(score_head_kwargs["lin_mult"]), ang_mult=float(score_head_kwargs["ang_mult"]),

@@ -304,3 +304,34 @@ def test_place_model_with_keypoint_extractor(cuda):
         keys_o = oracle.get_key_pcd_multiscale(OM.FeaturedPoints(x, rgb, b))
         tr_o = oracle.sample(Ts, keys_o, qo, noise=torch.zeros(4, 5, 6, dtype=torch.float64), **kw)
         assert (tr_g.cpu() - tr_o).abs().max() < 2e-3
+
+
+def test_ebm_critic_energy(cuda):
+    """SURVEY 8f rank 2 (critic use): EbmScoreModelHead.compute_energy of the *_ebm configs (agent.py:163-174 re-ranks the
+    sampled poses by it) against the oracle; state_dict keys identical; forward() (score from the energy gradient) raises."""
+    from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel
+    from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs_ebm
+    torch.manual_seed(21)
+    oracle = OM.MultiscaleScoreModel(**model_kwargs_ebm(), deterministic=True).eval()
+    _perturb_zero_params(oracle)
+    model = MultiscaleScoreModel(**model_kwargs_ebm(), deterministic=True).eval()
+    assert set(model.state_dict()) == set(oracle.state_dict())
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda)
+    x, rgb = make_scene(1500, seed=21, half_extent=12.0)
+    Ts, _ = make_poses(12, x, seed=21, spread=3.0)
+    t = torch.ones(12)
+    b = torch.zeros(len(x), dtype=torch.long)
+    grasp = OM.FeaturedPoints(torch.zeros(3, 3), torch.zeros(3, 3), torch.zeros(3, dtype=torch.long))
+    with torch.no_grad():
+        keys_o = oracle.get_key_pcd_multiscale(OM.FeaturedPoints(x, rgb, b))
+        q_o = oracle.get_query_pcd(grasp)
+        e_o = oracle.score_head.compute_energy(Ts, keys_o, q_o, t)
+        keys = model.get_key_pcd_multiscale(FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)))
+        q = model.get_query_pcd(_fp(FeaturedPoints, grasp, cuda))
+        e = model.score_head.compute_energy(Ts.to(cuda), keys, q, t.to(cuda))
+    assert e.shape == (12,)
+    assert_close(e, e_o, 2e-4, "energy")
+    assert torch.equal(e.cpu().argsort(), e_o.argsort())          # what the agent actually uses: the ranking
+    with pytest.raises(NotImplementedError):
+        model.score_head(Ts.to(cuda), keys, q, t.to(cuda))

@@ -98,3 +98,40 @@ def test_train_mode_dropout(cuda):
     assert len(vals) == 2 and float(vals[0]) == 0.0 and abs(float(vals[1]) - 1 / 0.9) < 1e-6
     assert abs(float(m.mean()) - 1.0) < 0.01 and abs(float((m == 0).float().mean()) - 0.1) < 0.005
     model.eval()
+
+
+def test_place_config_gradients_match_oracle(cuda):
+    """SURVEY 8f rank 1 on the training path: KeypointExtractor query model (second UNet, two tensor fields without context
+    embedding, sigmoid weight head) + score head with many query points."""
+    from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel
+    from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs_place
+    from oracle import model as OM
+    torch.manual_seed(11)
+    oracle = OM.MultiscaleScoreModel(**model_kwargs_place(), deterministic=True).eval()
+    model = MultiscaleScoreModel(**model_kwargs_place(), deterministic=True).eval()
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda)
+    x, rgb = make_scene(900, seed=11, half_extent=10.0)
+    gx, grgb = make_scene(700, seed=12, half_extent=8.0)
+    gx[:, 2] += 9.0
+    Ts, t = make_poses(4, x, seed=11, spread=5.0)
+    g = torch.Generator().manual_seed(1)
+    ta, tl = torch.randn(4, 3, generator=g), torch.randn(4, 3, generator=g)
+    b, gb = torch.zeros(len(x), dtype=torch.long), torch.zeros(len(gx), dtype=torch.long)
+    loss_o, *_ = oracle.get_train_loss(Ts, t, OM.FeaturedPoints(x, rgb, b), OM.FeaturedPoints(gx, grgb, gb), ta, tl)
+    loss_o.backward()
+    d = lambda v: v.to(cuda)
+    loss, *_ = model.get_train_loss(d(Ts), d(t), FeaturedPoints(d(x), d(rgb), d(b)), FeaturedPoints(d(gx), d(grgb), d(gb)), d(ta), d(tl))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_o.detach())) <= 2e-4 * abs(float(loss_o.detach()))
+    po = dict(oracle.named_parameters())
+    worst = []
+    for name, p in model.named_parameters():
+        go = po[name].grad
+        if go is None or float(go.abs().max()) < 1e-12:
+            continue
+        assert p.grad is not None, name
+        worst.append((rel_err(p.grad, go), name))
+    worst.sort(reverse=True)
+    assert len(worst) > 500 and any(n.startswith("query_model.weight_field") for _, n in worst)
+    assert worst[0][0] <= 3e-3, f"largest gradient errors: {worst[:8]}"
