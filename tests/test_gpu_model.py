@@ -332,6 +332,10 @@ def test_ebm_critic_energy(cuda):
         e = model.score_head.compute_energy(Ts.to(cuda), keys, q, t.to(cuda))
     assert e.shape == (12,)
     assert_close(e, e_o, 2e-4, "energy")
-    assert torch.equal(e.cpu().argsort(), e_o.argsort())          # what the agent actually uses: the ranking
+    # what the agent actually uses is the ranking: in the oracle's order the CUDA energies must be sorted too (up to the
+    # tolerance: poses without neighbours have near-identical energies)
+    es = e.cpu()[e_o.argsort()]
+    assert bool((es[1:] - es[:-1] >= -2e-4 * float(e_o.abs().max())).all())
+    assert float(e_o.max() - e_o.min()) > 1e-3 * float(e_o.abs().max())          # the test poses do differ in energy
     with pytest.raises(NotImplementedError):
         model.score_head(Ts.to(cuda), keys, q, t.to(cuda))
