@@ -103,6 +103,9 @@ _PROTOS = {
     "dedf_dropout_mask": [c_ull, c_ull, c_ll, c_f, c_fp, c_fp],
     "dedf_group_scale": [c_fp, c_fp, c_int, C.POINTER(c_int), c_int, c_fp, c_fp],
     "dedf_ebm_energy": [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_f, c_fp, c_fp],
+    "dedf_bbox": [c_fp, c_int, c_fp, c_fp, c_fp],
+    "dedf_voxel_count": [c_fp, c_int, c_fp, c_f, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp],
+    "dedf_voxel_reduce": [c_fp, c_fp, c_int, c_int, c_fp, c_f, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp],
     "dedf_build_arch": [],
 }
 

@@ -227,6 +227,20 @@ int dedf_sample_advance(const double* sched, int n_steps, int* counter, float* t
 int dedf_ebm_energy(const float* key_f, const float* query_f, const float* qw, int n_t, int n_q, int F, float scale, float* out,
                     cudaStream_t stream);
 
+/* ---- pre-processing in front of the path -------------------------------------------------------
+ * voxel_filter (edf_interface/edf_interface/data/pcd_utils.py:123-152; preprocess.downsample, preprocess.py:69-80): voxel index =
+ * trunc((p - min) / voxel_size), output sorted by the C-order ravelled index, features averaged, coordinates averaged
+ * (center = 0) or voxel centres (center = 1).  dedf_bbox -> host reads mins / maxs (the reference syncs here too) and sizes the
+ * dense grid (sx, sy, sz <= 2^27 cells); dedf_voxel_count fills key (n) / cnt (S, caller-zeroed) / off (S) / rank (S) and the
+ * number of occupied voxels; dedf_voxel_reduce writes the (n_occupied, 3) / (n_occupied, F) outputs, summing every voxel's
+ * points in ascending point-index order (deterministic, bit-identical to a sequential scatter). */
+int dedf_bbox(const float* points, int n, float* mins, float* maxs, cudaStream_t stream);
+int dedf_voxel_count(const float* points, int n, const float* mins, float voxel_size, int sx, int sy, int sz, int* key,
+                     int* cnt_zeroed, int* off, int* rank, int* n_occupied, cudaStream_t stream);
+int dedf_voxel_reduce(const float* points, const float* feats, int n, int F, const float* mins, float voxel_size, int sx, int sy,
+                      int sz, const int* key, const int* cnt, const int* off, const int* rank, int* cursor_zeroed, int* sorted,
+                      int center, float* out_points, float* out_feats, cudaStream_t stream);
+
 /* ---- training path (un-fused primitives + their backward kernels) ---------------------------------------------
  * The reference trains through torch autograd over e3nn / torch_scatter ops (trainer.py:308-346 ->
  * score_model_base.py:41-107).  diffusion_edf_b200/autograd_ops.py wraps the pairs below in torch.autograd.Function so

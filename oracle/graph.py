@@ -94,3 +94,31 @@ def scatter_logsumexp(src: torch.Tensor, index: torch.Tensor, dim_size: int, eps
     s = scatter_sum(torch.exp(src - mx_safe[index]), index, dim_size)
     out = torch.log(s + eps) + mx_safe
     return torch.where(torch.isinf(mx), torch.zeros_like(out), out)
+
+
+def voxel_filter(points: torch.Tensor, features: torch.Tensor, voxel_size: float, coord_reduction: str = "average"):
+    """/root/reference/edf_interface/edf_interface/data/pcd_utils.py:123-152 restated without numpy / torch_scatter:
+    torch_scatter.scatter(sum) over the ravelled voxel index == index_add_ (sequential on the CPU: ascending point order),
+    np.ravel_multi_index == C-order ravel, ``nonzero()`` == ascending ravelled index."""
+    mins = points.min(dim=-2).values
+    vox_idx = torch.div((points - mins), voxel_size, rounding_mode="trunc").type(torch.long)
+    shape = vox_idx.max(dim=-2).values + 1
+    raveled = (vox_idx[:, 0] * shape[1] + vox_idx[:, 1]) * shape[2] + vox_idx[:, 2]
+    size = int(shape[0] * shape[1] * shape[2])
+    n_pts = torch.zeros(size, dtype=torch.long).index_add_(0, raveled, torch.ones_like(raveled))
+    nonzero = n_pts.nonzero().squeeze(-1)
+    n_pts = n_pts[nonzero]
+    feat = torch.zeros(size, features.shape[1], dtype=features.dtype).index_add_(0, raveled, features)[nonzero]
+    feat = feat / n_pts.unsqueeze(-1)
+    if coord_reduction == "center":
+        iz = nonzero % shape[2]
+        iy = (nonzero // shape[2]) % shape[1]
+        ix = nonzero // (shape[2] * shape[1])
+        coord = torch.stack([ix, iy, iz], dim=-1)
+        coord = coord * voxel_size + mins + (voxel_size / 2)
+    elif coord_reduction == "average":
+        coord = torch.zeros(size, 3, dtype=points.dtype).index_add_(0, raveled, points)[nonzero]
+        coord = coord / n_pts.unsqueeze(-1)
+    else:
+        raise ValueError(f"Unknown coordinate reduction method: {coord_reduction}")
+    return coord, feat

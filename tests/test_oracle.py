@@ -203,3 +203,15 @@ def test_sample_zero_temperature_is_deterministic_and_shaped():
         b2 = m.sample(T0, keys, q, **kw)
     assert a.shape == (5, 2, 7) and a.dtype == torch.float64 and torch.equal(a, b2) and torch.equal(a[-1], a[-2])
     assert (a[1:, :, :4].norm(dim=-1) - 1).abs().max() < 1e-12      # row 0 is the fp32-normalised seed itself
+
+
+def test_voxel_filter_matches_reference_golden():
+    """oracle.graph.voxel_filter against vectors produced by the reference's own voxel_filter source on the reference's test
+    scene (tests/golden/make_golden_voxel.py): bit-exact, both coordinate reductions."""
+    import numpy as np
+    from oracle.graph import voxel_filter
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "voxel_golden.npz"))
+    p, c = torch.tensor(g["points"]), torch.tensor(g["colors"])
+    for red in ("average", "center"):
+        co, fe = voxel_filter(p, c, float(g["voxel_size"]), red)
+        assert torch.equal(co, torch.tensor(g[f"coord_{red}"])) and torch.equal(fe, torch.tensor(g[f"feat_{red}"]))
