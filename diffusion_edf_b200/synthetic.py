@@ -64,6 +64,16 @@ def model_kwargs_place() -> Dict:
     return kw
 
 
+def model_kwargs_highres() -> Dict:
+    """model_kwargs of configs/panda_mug/pick_highres/score_model_configs.yaml: pick_lowres with key-field radii
+    [3.5, 5, 6.5, 8] cm (all finite, no length_enc_max_r) and UNet pool ratio 0.25."""
+    kw = copy.deepcopy(PANDA_MUG_PICK_LOWRES)
+    kw["score_head_kwargs"]["key_tensor_field_kwargs"]["r_cluster_multiscale"] = [3.5, 5.0, 6.5, 8.0]
+    kw["score_head_kwargs"]["key_tensor_field_kwargs"].pop("length_enc_max_r", None)
+    kw["key_kwargs"]["feature_extractor_kwargs"]["pool_ratio"] = [0.25, 0.25, 0.25, 0.25]
+    return kw
+
+
 def model_kwargs_ebm() -> Dict:
     """model_kwargs of configs/panda_mug/pick_ebm/score_model_configs.yaml (the critic): pick_lowres with ``ebm: True``, no
     time encoding, key-field radii [3.5, 5, 6.5, 8] cm (all finite, no length_enc_max_r) and UNet pool ratio 0.25."""

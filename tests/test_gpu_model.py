@@ -339,3 +339,25 @@ def test_ebm_critic_energy(cuda):
     assert float(e_o.max() - e_o.min()) > 1e-3 * float(e_o.abs().max())          # the test poses do differ in energy
     with pytest.raises(NotImplementedError):
         model.score_head(Ts.to(cuda), keys, q, t.to(cuda))
+
+
+def test_highres_config_forward(cuda):
+    """configs/*/pick_highres: all four key-field radii finite (no infinite scale), time encoding on, pool ratio 0.25."""
+    from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel
+    from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs_highres
+    torch.manual_seed(31)
+    oracle = OM.MultiscaleScoreModel(**model_kwargs_highres(), deterministic=True).eval()
+    _perturb_zero_params(oracle)
+    model = MultiscaleScoreModel(**model_kwargs_highres(), deterministic=True).eval()
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda)
+    x, rgb = make_scene(1500, seed=31, half_extent=12.0)
+    Ts, t = make_poses(9, x, seed=31, spread=2.5)
+    b = torch.zeros(len(x), dtype=torch.long)
+    grasp = OM.FeaturedPoints(torch.zeros(3, 3), torch.zeros(3, 3), torch.zeros(3, dtype=torch.long))
+    with torch.no_grad():
+        (ang_o, lin_o), _ = oracle(Ts, t, OM.FeaturedPoints(x, rgb, b), grasp)
+        for _ in range(2):          # eager record pass, then the CUDA-graph replay
+            (ang, lin), _ = model(Ts.to(cuda), t.to(cuda), FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)), _fp(FeaturedPoints, grasp, cuda))
+            assert_close(ang, ang_o, 5e-4, "ang")
+            assert_close(lin, lin_o, 5e-4, "lin")

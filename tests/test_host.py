@@ -246,3 +246,21 @@ def test_allreduce_gradients_gloo_world2():
         assert r[3] == [1.5 * i for i in range(7)]
         assert r[4] == [[2.0, 2.0], [2.0, 2.0]]
         assert r[5]
+
+
+def test_every_shipped_panda_config_constructs():
+    """All 18 panda_{mug,bottle,bowl}/{pick,place}_{lowres,highres,ebm} score_model_configs.yaml of the reference build with their
+    model_kwargs passed verbatim (trainer.py:136-137).  Reads /root/reference: authoring container only."""
+    import copy
+    import glob
+    import yaml
+    from diffusion_edf_b200 import MultiscaleScoreModel
+    files = sorted(glob.glob("/root/reference/configs/panda_*/*/score_model_configs.yaml"))
+    if not files:
+        pytest.skip("/root/reference is not present")
+    assert len(files) == 18
+    for f in files:
+        cfg = yaml.safe_load(open(f))
+        assert cfg["model_name"] == "MultiscaleScoreModel"
+        m = MultiscaleScoreModel(**copy.deepcopy(cfg["model_kwargs"]))
+        assert sum(p.numel() for p in m.parameters()) > 1_000_000, f
