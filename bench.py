@@ -26,9 +26,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/INFO; the contract is ONE JSON line on stdout
-if not os.environ.get("DEDF_KEEP_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# The contract is ONE JSON line on stdout.  NCCL prints its version banner on stdout when NCCL_DEBUG is set (this image sets
+# it); everything any library writes to file descriptor 1 is therefore sent to stderr until the result line is printed.
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    sys.stdout.flush()
+    os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(obj), flush=True)
+    os.dup2(2, 1)
+
 
 import torch  # noqa: E402
 
@@ -127,7 +136,7 @@ def run_reference(args):
     value = N_POSES / (ms / 1e3)
     sample = (f"{steps} full forwards of the C2 workload (10k-pt scene, {N_POSES} poses) on {cores} host threads"
               + ("" if steps == args.steps else f"; {args.steps} steps requested, bounded to {steps} by the {budget_s:.0f}s budget"))
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "steps_requested": args.steps, "warmup": 1 + warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -135,7 +144,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
@@ -311,7 +320,7 @@ def run_cuda(args):
         cpu_s = statistics.median(ts[1:])
         cpu = {"value": N_POSES / cpu_s, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"2 full forwards of the same C2 workload (after 1 warm-up) through oracle/ on {cores} host threads, median"}
-    print(json.dumps({
+    emit({
         "metric": METRIC, "value": world * N_POSES / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -328,7 +337,7 @@ def run_cuda(args):
                 "ms_per_step": e2e_ms, "timing": "wall clock incl. pinned H2D of scene+poses and D2H of the scores"},
         "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
         "clocks": clocks, "roofline": roof, "step_breakdown": breakdown, "cpu_baseline": cpu,
-    }))
+    })
 
 
 def main():
