@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) edge_geom_kernel(GeomArgs a) {
 // ===========================================================================
 constexpr int kMlpTE = 64;          // edges per tile
 constexpr int kMlpThreads = 256;
-constexpr int kMlpMaxW = 128;       // widest hidden layer kept in shared memory
+constexpr int kMlpMaxW = 192;       // widest layer input / hidden layer kept in shared memory (sapien configs: 64 + 128 edge scalars)
 
 struct MlpArgs {
     int mode;                       // DEDF_MLP_IN_ROWS / _RBF / _FIELD

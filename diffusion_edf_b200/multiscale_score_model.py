@@ -10,7 +10,7 @@ from .gnn_data import FeaturedPoints
 from .keypoint_extractor import KeypointExtractor, StaticKeypointModel
 from .score_head import ScoreModelHead
 from .score_model_base import ScoreModelBase
-from .unet_feature_extractor import UnetFeatureExtractor
+from .unet_feature_extractor import ForwardOnlyFeatureExtractor, UnetFeatureExtractor
 
 
 class MultiscaleScoreModel(ScoreModelBase):
@@ -18,9 +18,12 @@ class MultiscaleScoreModel(ScoreModelBase):
                  deterministic: bool = False):
         super().__init__()
         name = key_kwargs["feature_extractor_name"]
-        if name != "UnetFeatureExtractor":
-            raise NotImplementedError(f"feature extractor {name!r} (only UnetFeatureExtractor is on the CUDA path)")
-        self.key_model = UnetFeatureExtractor(**key_kwargs["feature_extractor_kwargs"], deterministic=deterministic)
+        if name == "UnetFeatureExtractor":
+            self.key_model = UnetFeatureExtractor(**key_kwargs["feature_extractor_kwargs"], deterministic=deterministic)
+        elif name == "ForwardOnlyFeatureExtractor":
+            self.key_model = ForwardOnlyFeatureExtractor(**key_kwargs["feature_extractor_kwargs"], deterministic=deterministic)
+        else:
+            raise NotImplementedError(f"feature extractor {name!r}")
         if query_model == "StaticKeypointModel":
             self.query_model = StaticKeypointModel(**query_kwargs)
         elif query_model == "KeypointExtractor":

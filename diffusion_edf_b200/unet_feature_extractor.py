@@ -46,8 +46,9 @@ class UnetFeatureExtractor(nn.Module):
                  fc_neurons: List[List[int]], n_layers: List[int], pool_ratio: List[float], radius: List[Optional[float]],
                  deterministic: bool = False, pool_method="fps", irreps_mlp_mid=3, attn_type="mlp", alpha_drop=0.1,
                  proj_drop=0.1, drop_path_rate=0.0, n_layers_midstream: int = 2, n_scales: Optional[int] = None,
-                 output_scalespace: Optional[List[int]] = None):
+                 output_scalespace: Optional[List[int]] = None, forward_only: bool = False):
         super().__init__()
+        self.forward_only = forward_only         # ForwardOnlyFeatureExtractor: down path only
         self.irreps_output = Irreps(irreps_output)
         self.irreps_emb = [Irreps(i) for i in irreps_emb]
         self.irreps_edge_attr = [Irreps(i) for i in irreps_edge_attr]
@@ -89,9 +90,9 @@ class UnetFeatureExtractor(nn.Module):
                                                 for _ in range(n_layers[n] - 1)])
             self.down_blocks.append(blk)
         self.mid_block = nn.ModuleList([layer(self.n_scales - 1, self.irreps_emb[-1], self.irreps_emb[-1], head[-1])
-                                        for _ in range(n_layers_midstream)])
+                                        for _ in range(0 if forward_only else n_layers_midstream)])
         self.up_blocks = nn.ModuleList()
-        for n in range(self.n_scales - 1, -1, -1):
+        for n in (() if forward_only else range(self.n_scales - 1, -1, -1)):
             blk = nn.ModuleDict()
             blk["parity_inversion"] = ParityInversionSh(self.irreps_edge_attr[n])
             blk["layer_stack"] = nn.ModuleList([layer(n, self.irreps_emb[n], self.irreps_emb[n], head[n])
@@ -142,7 +143,7 @@ class UnetFeatureExtractor(nn.Module):
             x, b = x_dst, b_dst
         for layer in self.mid_block:
             emit("self", geom=geom, w=block(layer, geom))
-        for n, blk in enumerate(self.up_blocks):
+        for n, blk in enumerate(self.up_blocks):                     # (empty for the forward-only encoder)
             scale = self.n_scales - 1 - n
             x_fine, b_fine, idx, x_c, b_c, gself = levels[scale]
             for layer in blk["layer_stack"]:
@@ -197,6 +198,7 @@ class UnetFeatureExtractor(nn.Module):
 
         f = self.input_emb(pcd.f.contiguous())
         outs = [(f, x, b)]
+        scale_outs = []
         for n, blk in enumerate(self.down_blocks):
             it = take("pool")
             f_dst = blk["pool_proj"](ops.gather_rows(f, it["idx"]))
@@ -206,6 +208,13 @@ class UnetFeatureExtractor(nn.Module):
             for layer in blk["layer_stack"]:
                 f = run(layer, f, f, take("self"))
                 outs.append((f, x, b))
+            scale_outs.append((f, x, b))
+        if self.forward_only:            # forward_only_feature_extractor.py:191-275: every scale outputs its down-path features
+            assert pos[0] == len(items)
+            if use_side:
+                main.wait_stream(side)
+            return [FeaturedPoints(x=scale_outs[s][1], f=proj(scale_outs[s][0]), b=scale_outs[s][2], w=None)
+                    for s, proj in enumerate(self.project_outputs) if s in self.output_scalespace]
         for layer in self.mid_block:
             f = run(layer, f, f, take("self"))
         f_skip, _, _ = outs.pop()
@@ -233,3 +242,11 @@ class UnetFeatureExtractor(nn.Module):
             fs, xs, bs = ups[s]
             pcds.append(FeaturedPoints(x=xs, f=proj(fs), b=bs, w=None))
         return pcds
+
+
+class ForwardOnlyFeatureExtractor(UnetFeatureExtractor):
+    """Key encoder of the sapien* highres configs (/root/reference/diffusion_edf/forward_only_feature_extractor.py:19-275):
+    the UNet's down path only; same constructor kwargs and the same parameter names as the UNet's down path."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs, forward_only=True)

@@ -681,6 +681,31 @@ class UnetFeatureExtractor(nn.Module):
                 for s, proj in enumerate(self.project_outputs) if s in self.output_scalespace]
 
 
+class ForwardOnlyFeatureExtractor(UnetFeatureExtractor):
+    """/root/reference/diffusion_edf/forward_only_feature_extractor.py:19-275: the UNet's down path only (no mid-stream, no up
+    path); scale n outputs the features after its layer stack.  Same parameter names as the down path of the UNet."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        del self.mid_block, self.up_blocks
+
+    def forward(self, pcd: FeaturedPoints) -> List[FeaturedPoints]:
+        x, f, b = pcd.x, self.input_emb(pcd.f), pcd.b
+        outs = []
+        for n, blk in enumerate(self.down_blocks):
+            f_dst, x_dst, e_src, e_dst, b_dst = self._fps_pool(n, x, f, b)
+            f_dst = blk["pool_proj"](f_dst)
+            f = self._run(blk["pool_layer"], f, f_dst, b_dst, self._geom(n, x, x_dst, e_src, e_dst))
+            x, b = x_dst, b_dst
+            e_src, e_dst = self._radius_graph(n, x, b)
+            g = self._geom(n, x, x, e_src, e_dst)
+            for layer in blk["layer_stack"]:
+                f = self._run(layer, f, f, b, g)
+            outs.append((f, x, b))
+        return [FeaturedPoints(x=outs[s][1], f=proj(outs[s][0]), b=outs[s][2], w=None)
+                for s, proj in enumerate(self.project_outputs) if s in self.output_scalespace]
+
+
 # ==========================================================================
 # top-level model
 # ==========================================================================
@@ -690,8 +715,8 @@ class MultiscaleScoreModel(nn.Module):
         super().__init__()
         self.register_buffer("q_indices", torch.tensor([[1, 2, 3], [0, 3, 2], [3, 0, 1], [2, 1, 0]], dtype=torch.long), persistent=False)
         self.register_buffer("q_factor", torch.tensor([[-0.5, -0.5, -0.5], [0.5, -0.5, 0.5], [0.5, 0.5, -0.5], [-0.5, 0.5, 0.5]]), persistent=False)
-        assert key_kwargs["feature_extractor_name"] == "UnetFeatureExtractor"
-        self.key_model = UnetFeatureExtractor(**key_kwargs["feature_extractor_kwargs"], deterministic=deterministic)
+        fe_cls = {"UnetFeatureExtractor": UnetFeatureExtractor, "ForwardOnlyFeatureExtractor": ForwardOnlyFeatureExtractor}[key_kwargs["feature_extractor_name"]]
+        self.key_model = fe_cls(**key_kwargs["feature_extractor_kwargs"], deterministic=deterministic)
         if query_model == "StaticKeypointModel":
             self.query_model = StaticKeypointModel(**query_kwargs)
         else:

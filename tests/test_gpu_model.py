@@ -361,3 +361,30 @@ def test_highres_config_forward(cuda):
             (ang, lin), _ = model(Ts.to(cuda), t.to(cuda), FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)), _fp(FeaturedPoints, grasp, cuda))
             assert_close(ang, ang_o, 5e-4, "ang")
             assert_close(lin, lin_o, 5e-4, "lin")
+
+
+def test_sapien_highres_forward_only_encoder(cuda):
+    """configs/sapien*/{pick,place}_highres -- ForwardOnlyFeatureExtractor key encoder (down path only, one scale,
+    7 layers), 192 edge scalars (64 length + 128 time), a single key-field radius."""
+    from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel
+    from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs_sapien_highres
+    torch.manual_seed(41)
+    oracle = OM.MultiscaleScoreModel(**model_kwargs_sapien_highres(), deterministic=True).eval()
+    _perturb_zero_params(oracle)
+    model = MultiscaleScoreModel(**model_kwargs_sapien_highres(), deterministic=True).eval()
+    assert set(model.state_dict()) == set(oracle.state_dict())
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda)
+    x, rgb = make_scene(1200, seed=41, half_extent=10.0)
+    Ts, t = make_poses(7, x, seed=41, spread=2.5)
+    b = torch.zeros(len(x), dtype=torch.long)
+    grasp = OM.FeaturedPoints(torch.zeros(3, 3), torch.zeros(3, 3), torch.zeros(3, dtype=torch.long))
+    with torch.no_grad():
+        (ang_o, lin_o), dbg_o = oracle(Ts, t, OM.FeaturedPoints(x, rgb, b), grasp, debug=True)
+        for _ in range(2):
+            (ang, lin), _ = model(Ts.to(cuda), t.to(cuda), FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)), _fp(FeaturedPoints, grasp, cuda))
+            assert_close(ang, ang_o, 5e-4, "ang")
+            assert_close(lin, lin_o, 5e-4, "lin")
+        keys = model.get_key_pcd_multiscale(FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)))
+        assert len(keys) == 1 and torch.equal(keys[0].x.cpu(), dbg_o[0][0].x)
+        assert_close(keys[0].f, dbg_o[0][0].f, 2e-4, "key features")

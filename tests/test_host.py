@@ -249,16 +249,18 @@ def test_allreduce_gradients_gloo_world2():
 
 
 def test_every_shipped_panda_config_constructs():
-    """All 18 panda_{mug,bottle,bowl}/{pick,place}_{lowres,highres,ebm} score_model_configs.yaml of the reference build with their
-    model_kwargs passed verbatim (trainer.py:136-137).  Reads /root/reference: authoring container only."""
+    """All 18 panda_{mug,bottle,bowl}/{pick,place}_{lowres,highres,ebm} score_model_configs.yaml and the 4 sapien*/*_highres ones
+    (ForwardOnlyFeatureExtractor) build with their model_kwargs passed verbatim (trainer.py:136-137).  Reads /root/reference:
+    authoring container only."""
     import copy
     import glob
     import yaml
     from diffusion_edf_b200 import MultiscaleScoreModel
-    files = sorted(glob.glob("/root/reference/configs/panda_*/*/score_model_configs.yaml"))
+    files = sorted(glob.glob("/root/reference/configs/panda_*/*/score_model_configs.yaml")) + \
+        sorted(glob.glob("/root/reference/configs/sapien*/*_highres/score_model_configs.yaml"))
     if not files:
         pytest.skip("/root/reference is not present")
-    assert len(files) == 18
+    assert len(files) == 22
     for f in files:
         cfg = yaml.safe_load(open(f))
         assert cfg["model_name"] == "MultiscaleScoreModel"
