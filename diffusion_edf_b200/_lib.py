@@ -106,6 +106,8 @@ _PROTOS = {
     "dedf_bbox": [c_fp, c_int, c_fp, c_fp, c_fp],
     "dedf_voxel_count": [c_fp, c_int, c_fp, c_f, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp],
     "dedf_voxel_reduce": [c_fp, c_fp, c_int, c_int, c_fp, c_f, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp],
+    "dedf_edge_gather_scalar": [c_fp, c_fp, c_fp, c_int, c_fp, c_fp],
+    "dedf_rowdot": [c_fp, c_fp, c_int, c_int, c_fp, c_fp],
     "dedf_build_arch": [],
 }
 

@@ -380,3 +380,26 @@ class GroupScaleFn(Function):
         d = torch.empty_like(g)
         ops._call("dedf_group_scale", ptr(g), ptr(mask), g.shape[0], L.int_array(ctx.cfg[0]), ctx.cfg[1], ptr(d), stream())
         return d, None, None, None
+
+
+class RowScaleFn(Function):
+    """y[r, :] = x[r, :] * s[r, 0] with gradients to both (source-point attention: s = w[edge_src], graph_attention.py:258-259)."""
+
+    @staticmethod
+    def forward(ctx, x, s, irr: Irr):
+        x, s = x.contiguous(), s.contiguous()
+        y = torch.empty_like(x)
+        ops._call("dedf_group_scale", ptr(x), ptr(s), x.shape[0], L.int_array(irr), 2, ptr(y), stream())
+        ctx.save_for_backward(x, s)
+        ctx.irr = tuple(irr)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, s = ctx.saved_tensors
+        g = g.contiguous()
+        dx = torch.empty_like(x)
+        ops._call("dedf_group_scale", ptr(g), ptr(s), g.shape[0], L.int_array(ctx.irr), 2, ptr(dx), stream())
+        ds = torch.empty_like(s)
+        ops._call("dedf_rowdot", ptr(g), ptr(x), x.shape[0], x.shape[1], ptr(ds), stream())
+        return dx, ds, None

@@ -82,9 +82,10 @@ class EquiformerBlock(nn.Module):
                  bias: bool = True, use_src_point_attn: bool = False, use_dst_point_attn: bool = False,
                  use_edge_weights: bool = True, **_ignored):
         super().__init__()
-        if use_dst_feature or use_src_point_attn or use_dst_point_attn or not use_edge_weights or not skip_connection:
-            raise NotImplementedError("only the edge-time-encoding tensor field (no dst features / point attention) is "
+        if use_dst_feature or use_dst_point_attn or not use_edge_weights or not skip_connection:
+            raise NotImplementedError("only the edge-time-encoding tensor field (no dst features / dst point attention) is "
                                       "implemented on the CUDA path")
+        self.use_src_point_attn = use_src_point_attn
         self.irreps_src = Irreps(irreps_src)
         self.irreps_emb = Irreps(irreps_emb) if irreps_emb is not None else Irreps(irreps_dst)
         self.irreps_output = Irreps(irreps_output) if irreps_output is not None else Irreps(irreps_dst)
@@ -100,8 +101,9 @@ class EquiformerBlock(nn.Module):
         return self.linear_src(f_src, ln=self.prenorm_src)
 
     def forward(self, msg_src: torch.Tensor, g: ops.Csr, sh: torch.Tensor, w: torch.Tensor,
-                edge_logit: torch.Tensor) -> torch.Tensor:
-        attn = self.ga.attend(msg_src, None, g, sh, w, edge_logit)
+                edge_logit: torch.Tensor, src_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+        assert (src_weight is not None) == self.use_src_point_attn, "source-point attention needs the source weights (FeaturedPoints.w)"
+        attn = self.ga.attend(msg_src, None, g, sh, w, edge_logit, src_weight)
         emb = self.ga.proj(attn)
         skip = emb if self.skip_2.is_identity else self.skip_2(emb)
         return self.ffn(emb, ln=self.post_norm, res=skip)

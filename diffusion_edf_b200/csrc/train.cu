@@ -704,9 +704,10 @@ __global__ void dropout_mask_kernel(unsigned long long seed, unsigned long long 
         out[i] = (curand_uniform(&st) <= p) ? 0.f : keep;
     }
 }
-// y[r, c] = x[r, c] * mask[r, g(c)]: mode 0: g = attention head of channel c (mask (n,4)); mode 1: g = irrep channel (mask (n, m0+m1+m2))
+// y[r, c] = x[r, c] * mask[r, g(c)]: mode 0: g = attention head of channel c (mask (n,4)); mode 1: g = irrep channel (mask (n, m0+m1+m2));
+// mode 2: one factor per row (mask (n,1): the source-point weight of an edge, gnn_block.py:190-193 -> graph_attention.py:258-259)
 __global__ void group_scale_kernel(const float* __restrict__ x, const float* __restrict__ mask, int n, Irr irr, int mode, float* __restrict__ y) {
-    const int F = irr.dim(), NG = mode ? irr.nirr() : 4;
+    const int F = irr.dim(), NG = (mode == 1) ? irr.nirr() : (mode == 2) ? 1 : 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n * F; i += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(i / F), c = (int)(i % F);
         int u;
@@ -714,8 +715,26 @@ __global__ void group_scale_kernel(const float* __restrict__ x, const float* __r
         else if (c < irr.off2()) u = irr.m0 + (c - irr.m0) / 3;
         else u = irr.m0 + irr.m1 + (c - irr.off2()) / 5;
         int gidx = u;
-        if (!mode) gidx = (u < irr.m0) ? u / (irr.m0 / 4) : (u < irr.m0 + irr.m1) ? (u - irr.m0) / (irr.m1 / 4) : (u - irr.m0 - irr.m1) / (irr.m2 / 4);
+        if (mode == 2) gidx = 0;
+        else if (!mode) gidx = (u < irr.m0) ? u / (irr.m0 / 4) : (u < irr.m0 + irr.m1) ? (u - irr.m0) / (irr.m1 / 4) : (u - irr.m0 - irr.m1) / (irr.m2 / 4);
         y[i] = x[i] * mask[(size_t)r * NG + gidx];
+    }
+}
+
+// out[e] = w[edge_src[e]] for e < *n_edges, 0 beyond (edge buffers may be sized by a capacity)
+__global__ void edge_gather_scalar_kernel(const float* __restrict__ w, const int* __restrict__ edge_src, const int* __restrict__ n_edges,
+                                          int max_edges, float* __restrict__ out) {
+    const int E = *n_edges;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < max_edges; e += gridDim.x * blockDim.x) out[e] = (e < E) ? w[edge_src[e]] : 0.f;
+}
+// out[r] = sum_c a[r, c] b[r, c]   (gradient of a per-row scale factor)
+__global__ void rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, int F, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n; r += gridDim.x * wpb) {
+        float s = 0.f;
+        for (int c = lane; c < F; c += 32) s = fmaf(a[(size_t)r * F + c], b[(size_t)r * F + c], s);
+        s = warp_sum(s);
+        if (lane == 0) out[r] = s;
     }
 }
 
@@ -940,6 +959,22 @@ extern "C" int dedf_group_scale(const float* x, const float* mask, int n, const 
     if (n <= 0) return DEDF_OK;
     const Irr ir{irr[0], irr[1], irr[2]};
     group_scale_kernel<<<DEDF_GRID((long long)n * ir.dim()), 256, 0, stream>>>(x, mask, n, ir, mode, y);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_edge_gather_scalar(const float* w, const int* edge_src, const int* n_edges_dev, int max_edges, float* out,
+                                       cudaStream_t stream) {
+    if (!w || !edge_src || !n_edges_dev || !out) return DEDF_ERR_ARG;
+    if (max_edges <= 0) return DEDF_OK;
+    edge_gather_scalar_kernel<<<DEDF_GRID(max_edges), 256, 0, stream>>>(w, edge_src, n_edges_dev, max_edges, out);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+extern "C" int dedf_rowdot(const float* a, const float* b, int n, int F, float* out, cudaStream_t stream) {
+    if (!a || !b || !out || F <= 0) return DEDF_ERR_ARG;
+    if (n <= 0) return DEDF_OK;
+    rowdot_kernel<<<grid_for(n, 8, kNumSMs * 8), 256, 0, stream>>>(a, b, n, F, out);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

@@ -317,8 +317,9 @@ class GraphAttention(nn.Module):
         return self._packed.get(self, build)
 
     def attend(self, msg_src: torch.Tensor, msg_dst: Optional[torch.Tensor], g: ops.Csr, sh: torch.Tensor,
-               w: torch.Tensor, edge_logit: Optional[torch.Tensor]) -> torch.Tensor:
-        """-> sum_e softmax(logit)_e * value_e per destination, (n_dst, F) (before ``proj``)."""
+               w: torch.Tensor, edge_logit: Optional[torch.Tensor], src_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """-> sum_e softmax(logit)_e * value_e per destination, (n_dst, F) (before ``proj``).  ``src_weight`` (N_src,): source-point
+        attention, alpha_e *= w[src_e] AFTER the softmax (graph_attention.py:258-259) == scaling the value rows."""
         p = self.packed()
         G = self.irreps_emb.m[1]
         F = self.irreps_emb.dim
@@ -330,4 +331,6 @@ class GraphAttention(nn.Module):
                         alpha_dot=p["alpha_dot"], edge_logit=edge_logit, logits=logits, out=v)
         val = torch.empty(E, F, dtype=torch.float32, device=dev)
         ops.edge_tp_lin(G, L.EPI_LIN, v, None, True, g, sh, p["wv"], 0, p["V0"], p["V1"], p["V2"], p["vb"], out=val)
+        if src_weight is not None:
+            val = ops.row_scale(val, ops.edge_gather_scalar(src_weight, g), self.irreps_emb.m)
         return ops.segment_softmax_reduce(g, logits, val, self.irreps_emb.m)

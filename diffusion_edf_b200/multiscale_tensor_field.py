@@ -117,6 +117,9 @@ class MultiscaleTensorField(nn.Module):
         for p in input_points_multiscale:
             off.append(off[-1] + p.x.shape[0])
         msg = self.gnn_block_init.source_messages(f)
+        if self.gnn_block_init.use_src_point_attn:          # PointAttentiveScoreModel: source weights ride along (gnn_data.py:220-234)
+            assert all(isinstance(p.w, torch.Tensor) for p in input_points_multiscale), "source-point attention needs FeaturedPoints.w"
+            return x, b, off, msg, torch.cat([p.w for p in input_points_multiscale], dim=0).contiguous()
         return x, b, off, msg
 
     # ------------------------------------------------------------------ forward
@@ -128,7 +131,9 @@ class MultiscaleTensorField(nn.Module):
         if context_emb is not None:
             raise NotImplementedError("pass the time rows produced by ScoreModelHead (time_rows=...), not context_emb")
         assert (time_rows is not None) == (self.context_emb_dim is not None)
-        x_src, b_src, src_off, msg_src = sources if sources is not None else self.encode_sources(input_points_multiscale)
+        srcs = sources if sources is not None else self.encode_sources(input_points_multiscale)
+        x_src, b_src, src_off, msg_src = srcs[:4]
+        w_src = srcs[4] if len(srcs) > 4 else None
         xq = query_points.x.contiguous()
         radii = self.r_cluster_multiscale
         g = ops.radius_csr(x_src, xq, radii, src_off=src_off, b_src=b_src, b_dst=query_points.b.contiguous(),
@@ -197,5 +202,5 @@ class MultiscaleTensorField(nn.Module):
             d2.out = L.ptr(w)
             ops.edge_mlp(d2, g.n_edges)
 
-        out = self.gnn_block_init(msg_src, g, sh, w, logit)
+        out = self.gnn_block_init(msg_src, g, sh, w, logit, w_src)
         return FeaturedPoints(x=query_points.x, f=out, b=query_points.b, w=query_points.w)

@@ -408,3 +408,18 @@ def ebm_energy(key_f: torch.Tensor, query_f: torch.Tensor, qw: torch.Tensor, n_t
     out = torch.empty(n_t, dtype=torch.float32, device=key_f.device)
     _call("dedf_ebm_energy", ptr(key_f.contiguous()), ptr(query_f.contiguous()), ptr(qw), n_t, n_q, key_f.shape[1], scale, ptr(out), stream())
     return out
+
+
+def edge_gather_scalar(w: torch.Tensor, g: Csr) -> torch.Tensor:
+    """(E, 1) per-edge factor w[edge_src[e]] (0 beyond the true edge count when the buffers are capacity-sized)."""
+    E = max(1, g.n_edges)
+    out = torch.empty(E, 1, dtype=torch.float32, device=w.device)
+    _call("dedf_edge_gather_scalar", ptr(w.contiguous()), ptr(g.edge_src, torch.int32), ptr(g.n_edges_dev, torch.int32), g.n_edges, ptr(out), stream())
+    return out
+
+
+def row_scale(x: torch.Tensor, factor: torch.Tensor, irr) -> torch.Tensor:
+    """x[r, :] * factor[r, 0]."""
+    y = torch.empty_like(x)
+    _call("dedf_group_scale", ptr(x.contiguous()), ptr(factor.contiguous()), x.shape[0], L.int_array(irr), 2, ptr(y), stream())
+    return y

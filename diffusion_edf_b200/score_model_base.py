@@ -46,7 +46,10 @@ class ScoreModelBase(nn.Module):
         if needs_grad:
             from . import train_path
             from .keypoint_extractor import KeypointExtractor
-            key_ms = train_path.unet_forward(self.key_model, key_pcd)
+            if isinstance(self.key_model, KeypointExtractor):                        # PointAttentiveScoreModel
+                key_ms = [train_path.keypoint_extractor(self.key_model, key_pcd)]
+            else:
+                key_ms = train_path.unet_forward(self.key_model, key_pcd)
             if isinstance(self.query_model, KeypointExtractor):
                 q = train_path.keypoint_extractor(self.query_model, query_pcd)      # place configs
             else:

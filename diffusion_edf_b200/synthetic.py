@@ -102,6 +102,41 @@ def model_kwargs_sapien_highres() -> Dict:
     }
 
 
+def model_kwargs_sapien_lowres() -> Dict:
+    """model_kwargs of configs/sapien/pick_lowres/score_model_configs.yaml (model_name PointAttentiveScoreModel): the key side is a
+    KeypointExtractor (4-scale UNet at 64x0e+32x1e+16x2e, pool 0.25, keypoint pool ratio 0.05, no bbox), the score head has one
+    all-pairs scale with source-point attention and 192 edge scalars."""
+    fe = {
+        "irreps_input": "3x0e", "irreps_output": "64x0e+32x1e+16x2e", "n_scales": 4,
+        "irreps_emb": ["64x0e+32x1e+16x2e"] * 4, "irreps_edge_attr": ["1x0e+1x1e+1x2e"] * 4, "num_heads": [4, 4, 4, 4],
+        "fc_neurons": [[64, 32, 32]] * 4, "n_layers": [2, 2, 2, 2], "pool_ratio": [0.25] * 4, "radius": [3.0, None, None, None],
+        "irreps_mlp_mid": 3, "pool_method": "fps", "attn_type": "mlp", "alpha_drop": 0.1, "proj_drop": 0.1, "drop_path_rate": 0.0,
+        "n_layers_midstream": 2,
+    }
+    return {
+        "score_head_kwargs": {
+            "max_time": 1.0, "time_emb_mlp": [512, 256, 128], "ang_mult": 2.5, "lin_mult": 15.0,
+            "edge_time_encoding": True, "query_time_encoding": False,
+            "key_tensor_field_kwargs": {
+                "irreps_output": "64x0e+32x1e+16x2e", "irreps_sh": "1x0e+1x1e+1x2e", "num_heads": 4,
+                "fc_neurons": [-1, 128, 64], "length_emb_dim": 64, "r_cluster_multiscale": [None],
+                "n_layers": 1, "irreps_mlp_mid": 3, "cutoff_method": "edge_attn", "r_mincut_nonscalar_sh": 0.1,
+                "length_enc_max_r": 100.0,
+            },
+        },
+        "key_kwargs": {
+            "weight_activation": "sigmoid", "weight_mult": None,
+            "keypoint_kwargs": {"pool_ratio": 0.05, "weight_pre_emb_dim": 64},
+            "feature_extractor_name": "UnetFeatureExtractor", "feature_extractor_kwargs": fe,
+            "tensor_field_kwargs": {"irreps_output": "64x0e+32x1e+16x2e", "irreps_sh": "1x0e+1x1e+1x2e", "num_heads": 4,
+                                    "fc_neurons": [-1, 32, 32], "length_emb_dim": 64, "r_cluster_multiscale": [5.0, 10.0, 20.0, 40.0],
+                                    "n_layers": 1, "irreps_mlp_mid": 3, "cutoff_method": "edge_attn"},
+        },
+        "query_model": "StaticKeypointModel",
+        "query_kwargs": {"irreps_output": "64x0e+32x1e+16x2e", "keypoint_coords": [[0.0, -4.5, 10.0], [0.0, 4.5, 10.0]]},
+    }
+
+
 def model_kwargs_ebm() -> Dict:
     """model_kwargs of configs/panda_mug/pick_ebm/score_model_configs.yaml (the critic): pick_lowres with ``ebm: True``, no
     time encoding, key-field radii [3.5, 5, 6.5, 8] cm (all finite, no length_enc_max_r) and UNet pool ratio 0.25."""

@@ -73,7 +73,8 @@ def ffn(mod, x: torch.Tensor) -> torch.Tensor:
 
 
 def graph_attention(ga: GraphAttention, msg_src: torch.Tensor, msg_dst: Optional[torch.Tensor], g: ops.Csr, sh: torch.Tensor,
-                    w: torch.Tensor, edge_logit: Optional[torch.Tensor], drop=(0.0, 0.0)) -> torch.Tensor:
+                    w: torch.Tensor, edge_logit: Optional[torch.Tensor], drop=(0.0, 0.0),
+                    src_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
     """-> proj(sum_e softmax_e value_e) incl. the train-mode dropouts ``drop`` = (alpha_drop, proj_drop)."""
     G = ga.irreps_emb.m[1]
     E = g.n_edges
@@ -88,6 +89,8 @@ def graph_attention(ga: GraphAttention, msg_src: torch.Tensor, msg_dst: Optional
     v = A.GateFn.apply(linear_rs(ga.sep_act.lin, m), ga.sep_act.lin.irreps_out.m)
     m2 = A.DtpFn.apply(v, sh, ga.sep_value.dtp.tp.weight, G)
     val = linear_rs(ga.sep_value.lin, m2)
+    if src_weight is not None:      # source-point attention: alpha_e *= w[src_e] after the softmax == scaling the value rows
+        val = A.RowScaleFn.apply(val, A.GatherFn.apply(src_weight.reshape(-1, 1), es), ga.irreps_emb.m)
     if drop[0] > 0.0:       # nn.Dropout on alpha (E, heads): sum_e (alpha_e m_e) v_e == sum_e alpha_e (m_e v_e)
         val = A.GroupScaleFn.apply(val, A.dropout_mask((E, 4), drop[0], val.device), ga.irreps_emb.m, 0)
     out = linear_rs(ga.proj, A.SoftmaxReduceFn.apply(logits, val, g, ga.irreps_emb.m))
@@ -175,6 +178,7 @@ def tensor_field(field, query_x: torch.Tensor, query_b: torch.Tensor, keys: List
     """MultiscaleTensorField.forward (multiscale_tensor_field.py:192-260) -> (n_query, F)."""
     x_src = torch.cat([p.x for p in keys], dim=0).contiguous()
     f_src = torch.cat([p.f for p in keys], dim=0)
+    w_src = torch.cat([p.w for p in keys], dim=0) if field.gnn_block_init.use_src_point_attn else None
     b_src = torch.cat([p.b for p in keys], dim=0).contiguous()
     off = [0]
     for p in keys:
@@ -212,7 +216,7 @@ def tensor_field(field, query_x: torch.Tensor, query_b: torch.Tensor, keys: List
     edge_scalars = torch.cat(scalars, dim=0)
     w = radial_profile(blk.ga.sep_act.dtp_rad, edge_scalars)
     drop = (field.alpha_drop, field.proj_drop) if field.training else (0.0, 0.0)
-    emb = graph_attention(blk.ga, msg_src, None, g, sh[:E], w, logit[:E], drop)
+    emb = graph_attention(blk.ga, msg_src, None, g, sh[:E], w, logit[:E], drop, w_src)
     skip = emb if blk.skip_2.is_identity else project_if_mismatch(blk.skip_2, emb)
     return A.AddScaleFn.apply(ffn(blk.ffn, layer_norm(blk.post_norm, emb)), skip, 1.0)
 

@@ -299,10 +299,15 @@ int dedf_assemble_bwd(const float* Ts, int n_t, int n_q, int n_vec, const float*
                       float* dqw, cudaStream_t stream);
 
 /* train-mode dropout: Philox mask (0 or 1/(1-p)); y = x * mask broadcast per attention head (mode 0, mask (n,4): nn.Dropout
- * on the attention weights, graph_attention.py:111-112) or per irrep channel (mode 1, mask (n, m0+m1+m2):
- * EquivariantDropout, equiformer/drop.py:76-96).  The backward of group_scale is group_scale on the gradient. */
+ * on the attention weights, graph_attention.py:111-112), per irrep channel (mode 1, mask (n, m0+m1+m2):
+ * EquivariantDropout, equiformer/drop.py:76-96) or per row (mode 2, mask (n,1)).  The backward of group_scale is group_scale on the gradient. */
 int dedf_dropout_mask(unsigned long long seed, unsigned long long offset, long long n, float p, float* out, cudaStream_t stream);
 int dedf_group_scale(const float* x, const float* mask, int n, const int* irr_host, int mode, float* y, cudaStream_t stream);
+/* source-point attention (gnn_block.py:190-193 -> graph_attention.py:258-259: alpha_e *= w[src_e] after the softmax):
+ * dedf_edge_gather_scalar builds the (E,1) factor (0 beyond *n_edges_dev), dedf_group_scale mode 2 applies it per row;
+ * dedf_rowdot is the gradient w.r.t. the factor. */
+int dedf_edge_gather_scalar(const float* w, const int* edge_src, const int* n_edges_dev, int max_edges, float* out, cudaStream_t stream);
+int dedf_rowdot(const float* a, const float* b, int n, int F, float* out, cudaStream_t stream);
 
 int dedf_build_arch(void);
 

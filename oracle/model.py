@@ -14,6 +14,8 @@ Module / attribute names mirror the reference so ``state_dict`` keys agree
 """
 from __future__ import annotations
 
+import copy
+
 import math
 from typing import Dict, List, NamedTuple, Optional, Sequence, Tuple, Union
 
@@ -799,3 +801,30 @@ class MultiscaleScoreModel(nn.Module):
                 Ts.append(T.clone())
         Ts.append(T.clone())
         return torch.stack(Ts, dim=0)
+
+
+class PointAttentiveScoreModel(MultiscaleScoreModel):
+    """/root/reference/diffusion_edf/point_attentive_score_model.py:20-99: KeypointExtractor on the key side, one key "scale",
+    source-point attention in the score head.  forward / get_train_loss / sample are inherited."""
+
+    def __init__(self, query_model: str, score_head_kwargs: Dict, key_kwargs: Dict, query_kwargs: Dict, deterministic: bool = False):
+        nn.Module.__init__(self)
+        self.register_buffer("q_indices", torch.tensor([[1, 2, 3], [0, 3, 2], [3, 0, 1], [2, 1, 0]], dtype=torch.long), persistent=False)
+        self.register_buffer("q_factor", torch.tensor([[-0.5, -0.5, -0.5], [0.5, -0.5, 0.5], [0.5, 0.5, -0.5], [-0.5, 0.5, 0.5]]), persistent=False)
+        self.key_model = KeypointExtractor(**copy.deepcopy(key_kwargs), deterministic=deterministic)
+        if query_model == "StaticKeypointModel":
+            self.query_model = StaticKeypointModel(**query_kwargs)
+        else:
+            assert query_model == "KeypointExtractor"
+            self.query_model = KeypointExtractor(**copy.deepcopy(query_kwargs), deterministic=deterministic)
+        kw = dict(score_head_kwargs["key_tensor_field_kwargs"])
+        kw.update(irreps_input=self.key_model.irreps_output, use_src_point_attn=True, use_dst_point_attn=False)
+        self.score_head = ScoreModelHead(max_time=float(score_head_kwargs["max_time"]), time_emb_mlp=score_head_kwargs["time_emb_mlp"],
+                                         key_tensor_field_kwargs=kw, irreps_query_edf=self.query_model.irreps_output,
+                                         lin_mult=float(score_head_kwargs["lin_mult"]), ang_mult=float(score_head_kwargs["ang_mult"]),
+                                         edge_time_encoding=score_head_kwargs["edge_time_encoding"],
+                                         query_time_encoding=score_head_kwargs["query_time_encoding"])
+        self.lin_mult, self.ang_mult = self.score_head.lin_mult, self.score_head.ang_mult
+
+    def get_key_pcd_multiscale(self, pcd):
+        return [self.key_model(pcd)]

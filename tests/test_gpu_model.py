@@ -388,3 +388,48 @@ def test_sapien_highres_forward_only_encoder(cuda):
         keys = model.get_key_pcd_multiscale(FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)))
         assert len(keys) == 1 and torch.equal(keys[0].x.cpu(), dbg_o[0][0].x)
         assert_close(keys[0].f, dbg_o[0][0].f, 2e-4, "key features")
+
+
+def test_point_attentive_score_model(cuda):
+    """configs/sapien*/*_lowres -- PointAttentiveScoreModel (KeypointExtractor on the key side, one all-pairs key
+    scale, source-point attention after the softmax) forward and gradients against the oracle."""
+    from diffusion_edf_b200 import FeaturedPoints, PointAttentiveScoreModel
+    from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs_sapien_lowres
+    torch.manual_seed(51)
+    oracle = OM.PointAttentiveScoreModel(**model_kwargs_sapien_lowres(), deterministic=True).eval()
+    _perturb_zero_params(oracle)
+    model = PointAttentiveScoreModel(**model_kwargs_sapien_lowres(), deterministic=True).eval()
+    assert set(model.state_dict()) == set(oracle.state_dict())
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda)
+    x, rgb = make_scene(1200, seed=51, half_extent=10.0)
+    Ts, t = make_poses(5, x, seed=51, spread=3.0)
+    b = torch.zeros(len(x), dtype=torch.long)
+    grasp = OM.FeaturedPoints(torch.zeros(3, 3), torch.zeros(3, 3), torch.zeros(3, dtype=torch.long))
+    key_d = FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda))
+    with torch.no_grad():
+        (ang_o, lin_o), dbg_o = oracle(Ts, t, OM.FeaturedPoints(x, rgb, b), grasp, debug=True)
+        (ang, lin), dbg = model(Ts.to(cuda), t.to(cuda), key_d, _fp(FeaturedPoints, grasp, cuda), debug=True)
+        assert len(dbg[0]) == 1 and torch.equal(dbg[0][0].x.cpu(), dbg_o[0][0].x) and len(dbg_o[0][0].x) >= 50
+        assert_close(dbg[0][0].w, dbg_o[0][0].w, 5e-4, "key point weights")
+        assert_close(ang, ang_o, 1e-3, "ang")
+        assert_close(lin, lin_o, 1e-3, "lin")
+    # training path
+    g = torch.Generator().manual_seed(2)
+    ta, tl = torch.randn(5, 3, generator=g), torch.randn(5, 3, generator=g)
+    loss_o, *_ = oracle.get_train_loss(Ts, t, OM.FeaturedPoints(x, rgb, b), grasp, ta, tl)
+    loss_o.backward()
+    loss, *_ = model.get_train_loss(Ts.to(cuda), t.to(cuda), key_d, _fp(FeaturedPoints, grasp, cuda), ta.to(cuda), tl.to(cuda))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_o.detach())) <= 5e-4 * abs(float(loss_o.detach()))
+    po = dict(oracle.named_parameters())
+    worst = []
+    for name, p in model.named_parameters():
+        go = po[name].grad
+        if go is None or float(go.abs().max()) < 1e-12:
+            continue
+        assert p.grad is not None, name
+        worst.append((rel_err(p.grad, go), name))
+    worst.sort(reverse=True)
+    assert any(n.startswith("key_model.weight_post") for _, n in worst)      # the key-point weights get a gradient through the attention
+    assert worst[0][0] <= 5e-3, f"largest gradient errors: {worst[:8]}"

@@ -248,21 +248,25 @@ def test_allreduce_gradients_gloo_world2():
         assert r[5]
 
 
-def test_every_shipped_panda_config_constructs():
-    """All 18 panda_{mug,bottle,bowl}/{pick,place}_{lowres,highres,ebm} score_model_configs.yaml and the 4 sapien*/*_highres ones
-    (ForwardOnlyFeatureExtractor) build with their model_kwargs passed verbatim (trainer.py:136-137).  Reads /root/reference:
-    authoring container only."""
+def test_every_shipped_config_constructs():
+    """All 26 score_model_configs.yaml of the reference (panda_{mug,bottle,bowl}/{pick,place}_{lowres,highres,ebm}, sapien*/...) build
+    with their model_kwargs passed verbatim (trainer.py:124-137: the class is looked up by ``model_name``) and expose the same
+    state_dict keys as the oracle restatement.  Reads /root/reference: authoring container only."""
     import copy
     import glob
     import yaml
-    from diffusion_edf_b200 import MultiscaleScoreModel
-    files = sorted(glob.glob("/root/reference/configs/panda_*/*/score_model_configs.yaml")) + \
-        sorted(glob.glob("/root/reference/configs/sapien*/*_highres/score_model_configs.yaml"))
+    import diffusion_edf_b200 as D
+    from oracle import model as OM
+    files = sorted(glob.glob("/root/reference/configs/*/*/score_model_configs.yaml"))
     if not files:
         pytest.skip("/root/reference is not present")
-    assert len(files) == 22
+    assert len(files) == 26
+    names = set()
     for f in files:
         cfg = yaml.safe_load(open(f))
-        assert cfg["model_name"] == "MultiscaleScoreModel"
-        m = MultiscaleScoreModel(**copy.deepcopy(cfg["model_kwargs"]))
-        assert sum(p.numel() for p in m.parameters()) > 1_000_000, f
+        names.add(cfg["model_name"])
+        m = getattr(D, cfg["model_name"])(**copy.deepcopy(cfg["model_kwargs"]))
+        o = getattr(OM, cfg["model_name"])(**copy.deepcopy(cfg["model_kwargs"]))
+        assert set(m.state_dict()) == set(o.state_dict()), f
+        assert sum(p.numel() for p in m.parameters()) > 500_000, f
+    assert names == {"MultiscaleScoreModel", "PointAttentiveScoreModel"}
