@@ -75,7 +75,7 @@ _PROTOS = {
     "dedf_score_tp": [c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_int, C.POINTER(c_int), C.POINTER(c_fp), C.POINTER(c_fp),
                       C.POINTER(c_fp), C.POINTER(c_fp), c_int, c_f, c_fp, c_fp, c_fp],
     "dedf_pose_update": [c_fp, c_int, c_fp, c_fp, c_fp, c_ull, c_ull, c_d, c_d, c_d, c_d, c_d, c_d, c_fp, c_fp, c_fp, c_fp, c_fp],
-    "dedf_sample_advance": [c_fp, c_int, c_fp, c_fp, c_fp, c_fp],
+    "dedf_sample_advance": [c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_fp],
     "dedf_prefetch_l2": [c_fp, c_fp, c_int, c_fp],
     "dedf_tc_selftest": [c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp],
     "dedf_lin_wgrad": [c_fp, c_fp, c_int, C.POINTER(c_int), C.POINTER(c_int), c_fp, c_fp, c_fp, c_fp, c_fp],

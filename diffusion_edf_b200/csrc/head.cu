@@ -326,14 +326,21 @@ struct SampleState {
     int* counter;                       // current step (device)
     float* time_out;                    // (1) fp32 time of the current step, read by time_embed
     double* cur;                        // (4) current row, read by pose_update
+    // optional: time rows of EVERY step, precomputed in one dedf_time_embed launch before the loop (the schedule is known up front)
+    const float* rows_all;              // (n_scales, n_steps, K)
+    float* rows_cur;                    // (n_scales, 1, K): this step's rows, read by the edge MLP as its per-pose bias
+    int n_scales, K;
 };
 
 __global__ void sample_advance_kernel(SampleState s) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const int i = min(*s.counter, s.n_steps - 1);
+    const int i = min(*s.counter, s.n_steps - 1);
+    if (threadIdx.x == 0) {
         for (int k = 0; k < 4; ++k) s.cur[k] = s.sched[(size_t)i * 4 + k];
         s.time_out[0] = (float)s.sched[(size_t)i * 4];
     }
+    if (s.rows_all)
+        for (int j = threadIdx.x; j < s.n_scales * s.K; j += blockDim.x)
+            s.rows_cur[j] = s.rows_all[((size_t)(j / s.K) * s.n_steps + i) * s.K + (j % s.K)];
 }
 
 struct PoseArgs {
@@ -494,10 +501,11 @@ extern "C" int dedf_pose_update(double* T, int n_t, const float* ang, const floa
 }
 
 extern "C" int dedf_sample_advance(const double* sched, int n_steps, int* counter, float* time_out, double* cur_row,
-                                   cudaStream_t stream) {
+                                   const float* rows_all, float* rows_cur, int n_scales, int k, cudaStream_t stream) {
     if (!sched || !counter || !time_out || !cur_row || n_steps <= 0) return DEDF_ERR_ARG;
-    SampleState s{sched, n_steps, counter, time_out, cur_row};
-    sample_advance_kernel<<<1, 32, 0, stream>>>(s);
+    if (rows_all && (!rows_cur || n_scales <= 0 || k <= 0)) return DEDF_ERR_ARG;
+    SampleState s{sched, n_steps, counter, time_out, cur_row, rows_all, rows_cur, n_scales, k};
+    sample_advance_kernel<<<1, 256, 0, stream>>>(s);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

@@ -398,9 +398,11 @@ def pose_update(T: torch.Tensor, ang: torch.Tensor, lin: torch.Tensor, noise: Op
           ptr(dev_row, torch.float64), ptr(dev_counter, torch.int32), stream())
 
 
-def sample_advance(sched: torch.Tensor, counter: torch.Tensor, time_out: torch.Tensor, cur_row: torch.Tensor) -> None:
+def sample_advance(sched: torch.Tensor, counter: torch.Tensor, time_out: torch.Tensor, cur_row: torch.Tensor,
+                   rows_all: Optional[torch.Tensor] = None, rows_cur: Optional[torch.Tensor] = None) -> None:
+    ns, k = (rows_all.shape[0], rows_all.shape[2]) if rows_all is not None else (0, 0)
     _call("dedf_sample_advance", ptr(sched, torch.float64), sched.shape[0], ptr(counter, torch.int32), ptr(time_out),
-          ptr(cur_row, torch.float64), stream())
+          ptr(cur_row, torch.float64), ptr(rows_all), ptr(rows_cur), ns, k, stream())
 
 
 def ebm_energy(key_f: torch.Tensor, query_f: torch.Tensor, qw: torch.Tensor, n_t: int, n_q: int, scale: float) -> torch.Tensor:

@@ -119,7 +119,7 @@ class ScoreModelHead(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, Ts: torch.Tensor, key_pcd_multiscale: List[FeaturedPoints], query_pcd: FeaturedPoints,
                 time: torch.Tensor, *, sources=None, shared_time: bool = False,
-                edge_capacity: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                edge_capacity: Optional[int] = None, time_rows: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         assert Ts.ndim == 2 and Ts.shape[-1] == 7, f"{Ts.shape}"
         assert time.ndim == 1 and (len(time) == len(Ts) or shared_time), f"{time.shape}"
         assert query_pcd.f.ndim == 2 and query_pcd.f.shape[-1] == self.query_edf_dim, f"{query_pcd.f.shape}"
@@ -127,7 +127,8 @@ class ScoreModelHead(nn.Module):
         Ts = Ts.contiguous()
         nT, nQ = len(Ts), len(query_pcd.x)
         # time encoding -> per-scale MLP -> time half of the edge pre-linear: (n_scales, nT or 1, K)
-        time_rows = ops.time_embed(self._time_desc(), (time[:1] if shared_time else time).contiguous())
+        if time_rows is None:        # (sample() precomputes the rows of the whole schedule and passes the current step's)
+            time_rows = ops.time_embed(self._time_desc(), (time[:1] if shared_time else time).contiguous())
         # query transform: x' = R x + t, f' = D(q) f
         qx, qf = query_pcd.x.contiguous(), query_pcd.f.contiguous()
         xq, fq = ops.query_transform(Ts, qx, qf, self.irreps_query_edf.m)
@@ -139,6 +140,10 @@ class ScoreModelHead(nn.Module):
         ang, lin = ops.score_tp(Ts, fq, field.f, qx, query_pcd.w.contiguous(), self.irreps_key_edf.m, Wd, Wl0, Wl1, bl,
                                 self.n_irreps_prescore, self.lin_mult)
         return ang, lin
+
+    def time_rows_for(self, times: torch.Tensor) -> torch.Tensor:
+        """Time half of the edge pre-linear for a whole schedule in one launch: (n_scales, len(times), K)."""
+        return ops.time_embed(self._time_desc(), times.to(torch.float32).contiguous())
 
     def warmup(self, Ts, key_pcd_multiscale, query_pcd, time):
         return self.forward(Ts=Ts, key_pcd_multiscale=key_pcd_multiscale, query_pcd=query_pcd, time=time)

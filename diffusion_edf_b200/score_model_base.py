@@ -116,11 +116,13 @@ class ScoreModelBase(nn.Module):
         cap = nT * n_q * sum(min(p.x.shape[0], 1000) for p in scene_pcd_multiscale)      # worst-case edge count
         # the graph path pre-sizes every edge buffer for the worst case (~4.5 KB per edge, twice: warm-up + graph pool)
         fits = 2 * cap * 4500 < 0.5 * torch.cuda.mem_get_info(dev)[0]
+        # all poses share the time of a step and the schedule is known up front: ONE time-embedding launch for the whole loop
+        rows_all = self.score_head.time_rows_for(torch.tensor([r[0] for r in rows], dtype=torch.float32, device=dev))
         if not (self.use_cuda_graph and fits):
             for step, (t, a_ang, a_lin, temperature) in enumerate(rows):
                 time = torch.full((1,), t, dtype=torch.float32, device=dev)
                 ang, lin = self.score_head(Ts=T32, key_pcd_multiscale=scene_pcd_multiscale, query_pcd=grasp_pcd, time=time,
-                                           sources=sources, shared_time=True)
+                                           sources=sources, shared_time=True, time_rows=rows_all[:, step:step + 1].contiguous())
                 nz = noise[step] if noise is not None else None
                 ops.pose_update(T, ang, lin, nz, int(self.sample_seed), step, t, self.ang_mult, self.lin_mult, a_ang, a_lin,
                                 temperature, traj[step + 1], T32)
@@ -133,10 +135,12 @@ class ScoreModelBase(nn.Module):
         counter = torch.zeros(1, dtype=torch.int32, device=dev)
         time_cur = torch.zeros(1, dtype=torch.float32, device=dev)
         cur_row = torch.zeros(4, dtype=torch.float64, device=dev)
+        rows_cur = torch.zeros(rows_all.shape[0], 1, rows_all.shape[2], dtype=torch.float32, device=dev)
+
         def one_step():
-            ops.sample_advance(sched, counter, time_cur, cur_row)
+            ops.sample_advance(sched, counter, time_cur, cur_row, rows_all, rows_cur)
             ang, lin = self.score_head(Ts=T32, key_pcd_multiscale=scene_pcd_multiscale, query_pcd=grasp_pcd, time=time_cur,
-                                       sources=sources, shared_time=True, edge_capacity=cap)
+                                       sources=sources, shared_time=True, edge_capacity=cap, time_rows=rows_cur)
             ops.pose_update(T, ang, lin, noise, int(self.sample_seed), 0, 0.0, self.ang_mult, self.lin_mult, 0.0, 0.0, 0.0,
                             traj, T32, dev_row=cur_row, dev_counter=counter)
 

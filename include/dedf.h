@@ -218,9 +218,11 @@ int dedf_pose_update(double* T, int n_t, const float* ang, const float* lin, con
 
 /* Loads row `*counter` of the device-resident schedule (n_steps, 4) = [t, alpha_ang, alpha_lin, temperature] into
  * cur_row and writes the fp32 time of the step to time_out[0] (the `time` input of dedf_time_embed), so that one denoise
- * step (score_model_base.py:146-199) is a parameter-free, replayable sequence of launches. */
+ * step (score_model_base.py:146-199) is a parameter-free, replayable sequence of launches.  Optional: rows_all
+ * (n_scales, n_steps, k) = the output of ONE dedf_time_embed launch over the whole schedule (known before the loop starts);
+ * this step's rows are copied to rows_cur (n_scales, 1, k), which the edge MLP reads as its per-pose bias. */
 int dedf_sample_advance(const double* sched, int n_steps, int* counter, float* time_out, double* cur_row,
-                        cudaStream_t stream);
+                        const float* rows_all, float* rows_cur, int n_scales, int k, cudaStream_t stream);
 
 /* library self-description: returns the compute capability the kernels were built for (100) */
 /* EbmScoreModelHead.compute_energy tail (score_head_ebm.py:171-172): energy[t] = scale * sum_q w_q |key_f[t,q,:] - query_f[t,q,:]|^2 */
