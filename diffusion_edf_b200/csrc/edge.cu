@@ -541,67 +541,85 @@ struct SoftmaxArgs {
 
 __global__ void __launch_bounds__(128) segment_softmax_reduce_kernel(SoftmaxArgs a) {
     pdl_wait(); pdl_launch();     // PDL: see common.cuh
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
+    // One CTA (4 warps) per destination: the statistics passes stride the destination's edges with all 128 threads, the
+    // weighted sum gives every warp a quarter of the edges (interleaved) and folds the four partial rows through shared
+    // memory in a fixed order -- deterministic, no atomics.  (A warp per destination left the small graphs of the coarse
+    // scales and of the score head -- a few hundred destinations -- on a fraction of the SMs with one long dependent chain.)
+    __shared__ float s_red[4][4];
+    __shared__ float s_acc[4][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = a.m0 + 3 * a.m1 + 5 * a.m2;
     constexpr int MAXC = 8;   // channels per lane (F <= 256)
-    for (int d = blockIdx.x * wpb + (threadIdx.x >> 5); d < a.n_dst; d += gridDim.x * wpb) {
-        // pass 1: per-head max
+    // head of each of this lane's channels
+    int hd[MAXC];
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+        const int c = lane + 32 * j;
+        int h = 0;
+        if (c < a.m0) h = c / (a.m0 / 4);
+        else if (c < a.m0 + 3 * a.m1) h = ((c - a.m0) / 3) / (a.m1 / 4);
+        else if (c < F) h = ((c - a.m0 - 3 * a.m1) / 5) / (a.m2 / 4);
+        hd[j] = h;
+    }
+    for (int d = blockIdx.x; d < a.n_dst; d += gridDim.x) {
+        // pass 1: per-head max over all edges of the destination
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         int deg = 0;
         for (int s = 0; s < a.n_seg; ++s) {
             const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
             deg += e - b;
-            for (int i = b + lane; i < e; i += 32) {
+            for (int i = b + tid; i < e; i += 128) {
                 const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
                 mx[0] = fmaxf(mx[0], l.x); mx[1] = fmaxf(mx[1], l.y); mx[2] = fmaxf(mx[2], l.z); mx[3] = fmaxf(mx[3], l.w);
             }
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) mx[h] = warp_max(mx[h]);
+        __syncthreads();                       // previous destination's readers of s_red / s_acc are done
+        if (lane == 0) { s_red[warp][0] = mx[0]; s_red[warp][1] = mx[1]; s_red[warp][2] = mx[2]; s_red[warp][3] = mx[3]; }
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 4; ++h) mx[h] = fmaxf(fmaxf(s_red[0][h], s_red[1][h]), fmaxf(s_red[2][h], s_red[3][h]));
         // pass 2: sum of exp
         float sm[4] = {0.f, 0.f, 0.f, 0.f};
         for (int s = 0; s < a.n_seg; ++s) {
             const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
-            for (int i = b + lane; i < e; i += 32) {
+            for (int i = b + tid; i < e; i += 128) {
                 const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
                 sm[0] += __expf(l.x - mx[0]); sm[1] += __expf(l.y - mx[1]); sm[2] += __expf(l.z - mx[2]); sm[3] += __expf(l.w - mx[3]);
             }
         }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) sm[h] = warp_sum(sm[h]);
+        __syncthreads();
+        if (lane == 0) { s_red[warp][0] = sm[0]; s_red[warp][1] = sm[1]; s_red[warp][2] = sm[2]; s_red[warp][3] = sm[3]; }
+        __syncthreads();
         float logZ[4];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) { sm[h] = warp_sum(sm[h]); logZ[h] = (deg > 0) ? (logf(sm[h] + 1e-12f) + mx[h]) : 0.f; }
-        // head of each of this lane's channels
-        int hd[MAXC];
-#pragma unroll
-        for (int j = 0; j < MAXC; ++j) {
-            const int c = lane + 32 * j;
-            int h = 0;
-            if (c < a.m0) h = c / (a.m0 / 4);
-            else if (c < a.m0 + 3 * a.m1) h = ((c - a.m0) / 3) / (a.m1 / 4);
-            else if (c < F) h = ((c - a.m0 - 3 * a.m1) / 5) / (a.m2 / 4);
-            hd[j] = h;
+        for (int h = 0; h < 4; ++h) {
+            const float t = (s_red[0][h] + s_red[1][h]) + (s_red[2][h] + s_red[3][h]);
+            logZ[h] = (deg > 0) ? (logf(t + 1e-12f) + mx[h]) : 0.f;
         }
-        // pass 3: weighted sum, 4 edges in flight per iteration (independent loads)
+        // pass 3: weighted sum; warp w takes the edges w, w+4, ... of every segment, two edges in flight
         float acc[MAXC];
 #pragma unroll
         for (int j = 0; j < MAXC; ++j) acc[j] = 0.f;
         for (int s = 0; s < a.n_seg; ++s) {
             const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
-            for (int i0 = b; i0 < e; i0 += 4) {
-                float4 l[4];
-                float v[4][MAXC];
+            for (int i0 = b + warp; i0 < e; i0 += 8) {
+                float4 l[2];
+                float v[2][MAXC];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = min(i0 + u, e - 1);
+                for (int u = 0; u < 2; ++u) {
+                    const int i = min(i0 + 4 * u, e - 1);
                     l[u] = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
                     const float* vp = a.val + (size_t)i * F;
 #pragma unroll
                     for (int j = 0; j < MAXC; ++j) { const int c = lane + 32 * j; v[u][j] = (c < F) ? vp[c] : 0.f; }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const bool on = (i0 + u) < e;
+                for (int u = 0; u < 2; ++u) {
+                    const bool on = (i0 + 4 * u) < e;
                     const float al0 = on ? __expf(l[u].x - logZ[0]) : 0.f, al1 = on ? __expf(l[u].y - logZ[1]) : 0.f;
                     const float al2 = on ? __expf(l[u].z - logZ[2]) : 0.f, al3 = on ? __expf(l[u].w - logZ[3]) : 0.f;
 #pragma unroll
@@ -613,10 +631,9 @@ __global__ void __launch_bounds__(128) segment_softmax_reduce_kernel(SoftmaxArgs
             }
         }
 #pragma unroll
-        for (int j = 0; j < MAXC; ++j) {
-            const int c = lane + 32 * j;
-            if (c < F) a.out[(size_t)d * F + c] = acc[j];
-        }
+        for (int j = 0; j < MAXC; ++j) s_acc[warp][lane + 32 * j] = acc[j];
+        __syncthreads();
+        for (int c = tid; c < F; c += 128) a.out[(size_t)d * F + c] = (s_acc[0][c] + s_acc[1][c]) + (s_acc[2][c] + s_acc[3][c]);
     }
 }
 
@@ -1157,7 +1174,7 @@ extern "C" int dedf_segment_softmax_reduce(const int* row_ptr, int n_dst, int n_
     if (m0 % 4 || m1 % 4 || m2 % 4 || m0 + 3 * m1 + 5 * m2 > 256) return DEDF_ERR_UNSUPPORTED;
     if (n_dst <= 0) return DEDF_OK;
     SoftmaxArgs a{row_ptr, n_dst, n_seg, logits, val, out, m0, m1, m2};
-    launch_pdl(segment_softmax_reduce_kernel, dim3(grid_for(n_dst, 4, kNumSMs * 16)), dim3(128), 0, stream, a);
+    launch_pdl(segment_softmax_reduce_kernel, dim3(grid_for(n_dst, 1, kNumSMs * 16)), dim3(128), 0, stream, a);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
