@@ -108,6 +108,7 @@ _PROTOS = {
     "dedf_voxel_reduce": [c_fp, c_fp, c_int, c_int, c_fp, c_f, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp],
     "dedf_edge_gather_scalar": [c_fp, c_fp, c_fp, c_int, c_fp, c_fp],
     "dedf_rowdot": [c_fp, c_fp, c_int, c_int, c_fp, c_fp],
+    "dedf_value_reduce": [c_int, c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp],
     "dedf_build_arch": [],
 }
 

@@ -638,6 +638,249 @@ __global__ void __launch_bounds__(128) segment_softmax_reduce_kernel(SoftmaxArgs
 }
 
 // ===========================================================================
+// value path, reassociated: out[d] = lin( sum_e alpha_{e,h} dtp(v_e, sh_e, w_shared) ) + bias * sum_e alpha_{e,h}
+// ===========================================================================
+// graph_attention.py:237-239 + :254-266 computes value_e = lin(dtp(v_e, sh_e)) per EDGE (79 kMAC each) and then the
+// alpha-weighted sum per destination.  sep_value.lin is linear with nothing after it and the heads partition its OUTPUT
+// channels, so per head h   sum_e alpha_{e,h} lin_h(d_e) = lin_h(sum_e alpha_{e,h} d_e) + b_h sum_e alpha_{e,h}:
+// the (E, 49 G) tensor-product outputs are reduced over the incoming edges first (4 head copies, in registers) and the
+// linear layer runs once per destination instead of once per edge -- the K1 pattern (gather -> depthwise CG -> x alpha ->
+// segment reduce) inside the real attention block, with the softmax statistics and the linear epilogue fused in.
+//
+// One CTA per destination.  Warp (cw, hp): channel group cw (16 l=0, 8 l=1, 4 l=2 channels) x head pair hp (heads 2hp, 2hp+1).
+// Edges are staged 64 at a time in shared memory (value rows and logits by TMA bulk copies); a warp walks them in packs of 8
+// so that all 32 lanes run the same code: 4 x (2 edges x 16 l=0 channels), 2 x (4 edges x 8 l=1 channels), 1 x (8 edges x 4 l=2
+// channels); lanes that share a channel are folded with shuffles at the end.  Deterministic, no atomics.
+struct ValueReduceArgs {
+    const int* row_ptr; int n_dst; int n_seg;
+    const float* v;          // (E, F) gated values (ACT epilogue output)
+    const float* sh;         // (E, 9)
+    const float* logits;     // (E, 4)
+    const float* post;       // (E) optional factor applied to alpha after the softmax (source-point attention) or null
+    const float* wv;         // (NUMEL) shared depthwise-TP weights (sep_value.dtp.tp.weight)
+    const float* V0; const float* V1; const float* V2;   // sep_value.lin blocks (D_l, M_l) row-major
+    const float* vb;         // (M0) bias or null
+    float* out;              // (n_dst, F)
+};
+
+constexpr int kVrChunk = 64;
+
+template <int G>
+__global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs a) {
+    using D = Dtp<G>;
+    constexpr int NCW = G / 8, NW = 2 * NCW, NT = NW * 32, CH = kVrChunk;
+    constexpr int B1 = D::D0, B2 = D::D0 + 3 * D::D1;             // block offsets inside one head copy of the reduced TP output
+    extern __shared__ __align__(16) float smem[];
+    float* s_v = smem;                          // [CH][F]
+    float* s_lg = s_v + CH * D::F;              // [CH][4] logits -> alpha (in place)
+    float* s_sh = s_lg + CH * 4;                // [CH][12]
+    float* s_D = s_sh + CH * 12;                // [4 heads][FOUT]
+    __shared__ float s_red[NW][4], s_sal[4];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cw = warp % NCW, hp = warp / NCW;
+    const int ch0 = cw * 16 + (lane & 15), ch1 = cw * 8 + (lane & 7), ch2 = cw * 4 + (lane & 3);
+    float w0[3], w1[6], w2[6];
+    w0[0] = a.wv[D::W_K0 + ch0]; w0[1] = a.wv[D::W_K1 + ch0]; w0[2] = a.wv[D::W_K2 + ch0];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { w1[i] = a.wv[D::W_K3 + ch1 + i * D::M1]; w2[i] = a.wv[D::W_K9 + ch2 + i * D::M2]; }
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
+    __syncthreads();
+    uint32_t ph = 0;
+
+    for (int d = blockIdx.x; d < a.n_dst; d += gridDim.x) {
+        // ---- softmax statistics over all incoming edges (all segments): per-head max, log Z ----
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int deg = 0;
+        for (int s = 0; s < a.n_seg; ++s) {
+            const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
+            deg += e - b;
+            for (int i = b + tid; i < e; i += NT) {
+                const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
+                mx[0] = fmaxf(mx[0], l.x); mx[1] = fmaxf(mx[1], l.y); mx[2] = fmaxf(mx[2], l.z); mx[3] = fmaxf(mx[3], l.w);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) mx[h] = warp_max(mx[h]);
+        __syncthreads();
+        if (lane == 0) { s_red[warp][0] = mx[0]; s_red[warp][1] = mx[1]; s_red[warp][2] = mx[2]; s_red[warp][3] = mx[3]; }
+        if (tid < 4) s_sal[tid] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { float m = s_red[0][h]; for (int w = 1; w < NW; ++w) m = fmaxf(m, s_red[w][h]); mx[h] = m; }
+        float sm[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int s = 0; s < a.n_seg; ++s) {
+            const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
+            for (int i = b + tid; i < e; i += NT) {
+                const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
+                sm[0] += __expf(l.x - mx[0]); sm[1] += __expf(l.y - mx[1]); sm[2] += __expf(l.z - mx[2]); sm[3] += __expf(l.w - mx[3]);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) sm[h] = warp_sum(sm[h]);
+        __syncthreads();
+        if (lane == 0) { s_red[warp][0] = sm[0]; s_red[warp][1] = sm[1]; s_red[warp][2] = sm[2]; s_red[warp][3] = sm[3]; }
+        __syncthreads();
+        float logZ[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            float t = 0.f;
+            for (int w = 0; w < NW; ++w) t += s_red[w][h];
+            logZ[h] = (deg > 0) ? (logf(t + 1e-12f) + mx[h]) : 0.f;
+        }
+
+        // ---- edge loop: accumulate alpha_h * dtp(v_e, sh_e, w) for this warp's channels and its two heads ----
+        float acc0[2][9], acc1[2][20], acc2[2][22];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc0[h][k] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 20; ++k) acc1[h][k] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 22; ++k) acc2[h][k] = 0.f;
+        }
+        for (int s = 0; s < a.n_seg; ++s) {
+            const int sb = a.row_ptr[(size_t)s * a.n_dst + d], se = a.row_ptr[(size_t)s * a.n_dst + d + 1];
+            for (int c0 = sb; c0 < se; c0 += CH) {
+                const int n = min(CH, se - c0);
+                __syncthreads();                                   // previous chunk fully consumed
+                if (tid == 0) {
+                    mbar_expect_tx(&bar, (uint32_t)n * (D::F + 4) * 4u);
+                    bulk_g2s_chunked(s_v, a.v + (size_t)c0 * D::F, (uint32_t)n * D::F * 4u, &bar);
+                    bulk_g2s(s_lg, a.logits + (size_t)c0 * 4, (uint32_t)n * 16u, &bar);
+                }
+                for (int i = tid; i < n * 9; i += NT) s_sh[(i / 9) * 12 + (i % 9)] = a.sh[(size_t)c0 * 9 + i];
+                mbar_wait(&bar, ph); ph ^= 1u;
+                __syncthreads();
+                // logits -> alpha (x optional post factor), in place; per-head sums for the bias term (fixed order)
+                if (tid < CH) {
+                    float4 al = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (tid < n) {
+                        const float4 l = *reinterpret_cast<const float4*>(s_lg + tid * 4);
+                        const float pf = a.post ? a.post[c0 + tid] : 1.0f;
+                        al = make_float4(__expf(l.x - logZ[0]) * pf, __expf(l.y - logZ[1]) * pf, __expf(l.z - logZ[2]) * pf, __expf(l.w - logZ[3]) * pf);
+                    }
+                    *reinterpret_cast<float4*>(s_lg + tid * 4) = al;
+                    float t0 = warp_sum(al.x), t1 = warp_sum(al.y), t2 = warp_sum(al.z), t3 = warp_sum(al.w);
+                    if (lane == 0) { s_red[warp][0] = t0; s_red[warp][1] = t1; s_red[warp][2] = t2; s_red[warp][3] = t3; }
+                }
+                __syncthreads();
+                if (tid < 4) s_sal[tid] += s_red[0][tid] + s_red[1][tid];      // CH = 64 = the first two warps
+                // packs of 8 edges
+                for (int p0 = 0; p0 < n; p0 += 8) {
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {                           // l = 0: 2 edges x 16 channels
+                        const int e = p0 + 2 * it + (lane >> 4);
+                        const bool ok = e < n;
+                        const float x = ok ? s_v[e * D::F + ch0] : 0.f;
+                        const float al0 = ok ? s_lg[e * 4 + 2 * hp] : 0.f, al1 = ok ? s_lg[e * 4 + 2 * hp + 1] : 0.f;
+                        float o[9];
+                        dtp_l0(x, w0[0], w0[1], w0[2], s_sh + (ok ? e : 0) * 12, o);
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) { acc0[0][k] = fmaf(al0, o[k], acc0[0][k]); acc0[1][k] = fmaf(al1, o[k], acc0[1][k]); }
+                    }
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {                           // l = 1: 4 edges x 8 channels
+                        const int e = p0 + 4 * it + (lane >> 3);
+                        const bool ok = e < n;
+                        const float* xs = s_v + (ok ? e : 0) * D::F + D::M0 + 3 * ch1;
+                        const float xv[3] = {ok ? xs[0] : 0.f, ok ? xs[1] : 0.f, ok ? xs[2] : 0.f};
+                        const float al0 = ok ? s_lg[e * 4 + 2 * hp] : 0.f, al1 = ok ? s_lg[e * 4 + 2 * hp + 1] : 0.f;
+                        float o[20];
+                        dtp_l1(xv, w1, s_sh + (ok ? e : 0) * 12, o);
+#pragma unroll
+                        for (int k = 0; k < 20; ++k) { acc1[0][k] = fmaf(al0, o[k], acc1[0][k]); acc1[1][k] = fmaf(al1, o[k], acc1[1][k]); }
+                    }
+                    {                                                          // l = 2: 8 edges x 4 channels
+                        const int e = p0 + (lane >> 2);
+                        const bool ok = e < n;
+                        const float* xs = s_v + (ok ? e : 0) * D::F + D::M0 + 3 * D::M1 + 5 * ch2;
+                        float xv[5];
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) xv[i] = ok ? xs[i] : 0.f;
+                        const float al0 = ok ? s_lg[e * 4 + 2 * hp] : 0.f, al1 = ok ? s_lg[e * 4 + 2 * hp + 1] : 0.f;
+                        float o[22];
+                        dtp_l2(xv, w2, s_sh + (ok ? e : 0) * 12, o);
+#pragma unroll
+                        for (int k = 0; k < 22; ++k) { acc2[0][k] = fmaf(al0, o[k], acc2[0][k]); acc2[1][k] = fmaf(al1, o[k], acc2[1][k]); }
+                    }
+                }
+            }
+        }
+        // ---- fold the lanes that share a channel, write the 4 head copies of the reduced TP output to shared memory ----
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc0[h][k] += __shfl_xor_sync(0xffffffffu, acc0[h][k], 16);
+#pragma unroll
+            for (int k = 0; k < 20; ++k) { acc1[h][k] += __shfl_xor_sync(0xffffffffu, acc1[h][k], 8); acc1[h][k] += __shfl_xor_sync(0xffffffffu, acc1[h][k], 16); }
+#pragma unroll
+            for (int k = 0; k < 22; ++k) {
+                acc2[h][k] += __shfl_xor_sync(0xffffffffu, acc2[h][k], 4); acc2[h][k] += __shfl_xor_sync(0xffffffffu, acc2[h][k], 8);
+                acc2[h][k] += __shfl_xor_sync(0xffffffffu, acc2[h][k], 16);
+            }
+        }
+        __syncthreads();                                           // s_D of the previous destination has been read
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float* Dh = s_D + (size_t)(2 * hp + h) * D::FOUT;
+            if (lane < 16) {
+                Dh[D::C0_K0 + ch0] = acc0[h][0];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) Dh[B1 + (D::C1_K1 + ch0) * 3 + k] = acc0[h][1 + k];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) Dh[B2 + (D::C2_K2 + ch0) * 5 + k] = acc0[h][4 + k];
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    Dh[B1 + (D::C1_K3 + ch1) * 3 + k] = acc1[h][k]; Dh[B1 + (D::C1_K5 + ch1) * 3 + k] = acc1[h][4 + k];
+                    Dh[B1 + (D::C1_K7 + ch1) * 3 + k] = acc1[h][12 + k];
+                }
+                Dh[D::C0_K4 + ch1] = acc1[h][3];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { Dh[B2 + (D::C2_K6 + ch1) * 5 + k] = acc1[h][7 + k]; Dh[B2 + (D::C2_K8 + ch1) * 5 + k] = acc1[h][15 + k]; }
+            }
+            if (lane < 4) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    Dh[B2 + (D::C2_K9 + ch2) * 5 + k] = acc2[h][k]; Dh[B2 + (D::C2_K11 + ch2) * 5 + k] = acc2[h][8 + k];
+                    Dh[B2 + (D::C2_K14 + ch2) * 5 + k] = acc2[h][17 + k];
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { Dh[B1 + (D::C1_K10 + ch2) * 3 + k] = acc2[h][5 + k]; Dh[B1 + (D::C1_K13 + ch2) * 3 + k] = acc2[h][14 + k]; }
+                Dh[D::C0_K12 + ch2] = acc2[h][13];
+            }
+        }
+        __syncthreads();
+        // ---- linear layer, once per destination: out[c] = sum_k V_l[k, u] D_{head(u)}[k, m] (+ bias * sum alpha) ----
+        for (int c = tid; c < D::F; c += NT) {
+            int l, u, m;
+            if (c < D::M0) { l = 0; u = c; m = 0; }
+            else if (c < D::M0 + 3 * D::M1) { l = 1; u = (c - D::M0) / 3; m = (c - D::M0) % 3; }
+            else { l = 2; u = (c - D::M0 - 3 * D::M1) / 5; m = (c - D::M0 - 3 * D::M1) % 5; }
+            const int ML = (l == 0) ? D::M0 : (l == 1) ? D::M1 : D::M2;
+            const int KL = (l == 0) ? D::D0 : (l == 1) ? D::D1 : D::D2;
+            const int dd = 2 * l + 1;
+            const int h = u / (ML / 4);
+            const float* V = ((l == 0) ? a.V0 : (l == 1) ? a.V1 : a.V2) + u;
+            const float* Dl = s_D + (size_t)h * D::FOUT + ((l == 0) ? 0 : (l == 1) ? B1 : B2) + m;
+            float acc = 0.f, accb = 0.f;
+            for (int k = 0; k < KL; k += 4) {                      // every D_l is a multiple of 4
+                const float v0 = __ldg(V + (size_t)k * ML), v1 = __ldg(V + (size_t)(k + 1) * ML), v2 = __ldg(V + (size_t)(k + 2) * ML), v3 = __ldg(V + (size_t)(k + 3) * ML);
+                acc = fmaf(v0, Dl[k * dd], acc); accb = fmaf(v1, Dl[(k + 1) * dd], accb);
+                acc = fmaf(v2, Dl[(k + 2) * dd], acc); accb = fmaf(v3, Dl[(k + 3) * dd], accb);
+            }
+            acc += accb;
+            if (l == 0 && a.vb) acc = fmaf(a.vb[u], s_sal[h], acc);
+            a.out[(size_t)d * D::F + c] = acc;
+        }
+    }
+}
+
+// ===========================================================================
 // K1: gather -> depthwise CG TP (per-edge weights) -> x alpha_h -> segment reduce
 // ===========================================================================
 struct TpReduceArgs {
@@ -1219,4 +1462,27 @@ extern "C" int dedf_edge_tp_reduce(int mul1, const float* x, const int* row_ptr,
     } else return DEDF_ERR_UNSUPPORTED;
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
+}
+
+template <int G>
+static int launch_value_reduce(const ValueReduceArgs& a, cudaStream_t stream) {
+    using D = Dtp<G>;
+    const size_t smem = ((size_t)kVrChunk * (D::F + 4 + 12) + 4 * (size_t)D::FOUT) * sizeof(float);
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(value_reduce_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
+    launch_pdl(value_reduce_kernel<G>, dim3(grid_for(a.n_dst, 1, kNumSMs * 8)), dim3(G * 8), smem, stream, a);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_value_reduce(int mul1, const int* row_ptr, int n_dst, int n_seg, const float* v, const float* sh, const float* logits,
+                                 const float* post, const float* wv, const float* V0, const float* V1, const float* V2, const float* vb,
+                                 float* out, cudaStream_t stream) {
+    if (!row_ptr || !v || !sh || !logits || !wv || !V0 || !V1 || !V2 || !out || n_seg < 1) return DEDF_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(logits) & 15)) return DEDF_ERR_ARG;
+    if (n_dst <= 0) return DEDF_OK;
+    ValueReduceArgs a{row_ptr, n_dst, n_seg, v, sh, logits, post, wv, V0, V1, V2, vb, out};
+    if (mul1 == 32) return launch_value_reduce<32>(a, stream);
+    if (mul1 == 16) return launch_value_reduce<16>(a, stream);
+    return DEDF_ERR_UNSUPPORTED;
 }

@@ -329,6 +329,10 @@ class GraphAttention(nn.Module):
         v = torch.empty(E, F, dtype=torch.float32, device=dev)
         ops.edge_tp_lin(G, L.EPI_ACT, msg_src, msg_dst, False, g, sh, w, self.sep_act.numel, p["W0"], p["W1"], p["W2"], p["b0"],
                         alpha_dot=p["alpha_dot"], edge_logit=edge_logit, logits=logits, out=v)
+        if ops.USE_VALUE_REDUCE:
+            # reassociated value path: reduce the tensor-product outputs over the incoming edges, THEN the linear layer
+            post = ops.edge_gather_scalar(src_weight, g) if src_weight is not None else None
+            return ops.value_reduce(G, g, v, sh, logits, post, p["wv"], p["V0"], p["V1"], p["V2"], p["vb"])
         val = torch.empty(E, F, dtype=torch.float32, device=dev)
         ops.edge_tp_lin(G, L.EPI_LIN, v, None, True, g, sh, p["wv"], 0, p["V0"], p["V1"], p["V2"], p["vb"], out=val)
         if src_weight is not None:

@@ -286,6 +286,7 @@ def edge_geom(x_src: torch.Tensor, x_dst: torch.Tensor, g: Csr, radii: Optional[
     return length, sh, logit
 
 
+USE_VALUE_REDUCE = True     # value path reassociated: linear once per destination (dedf_value_reduce) instead of once per edge
 USE_TC_MLP = True       # per-edge MLPs on the tcgen05 tensor cores (3xTF32) where the layer widths allow it
 
 
@@ -425,3 +426,12 @@ def row_scale(x: torch.Tensor, factor: torch.Tensor, irr) -> torch.Tensor:
     y = torch.empty_like(x)
     _call("dedf_group_scale", ptr(x.contiguous()), ptr(factor.contiguous()), x.shape[0], L.int_array(irr), 2, ptr(y), stream())
     return y
+
+
+def value_reduce(mul1: int, g: Csr, v: torch.Tensor, sh: torch.Tensor, logits: torch.Tensor, post: Optional[torch.Tensor], wv: torch.Tensor,
+                 V0: torch.Tensor, V1: torch.Tensor, V2: torch.Tensor, vb: Optional[torch.Tensor]) -> torch.Tensor:
+    """out[d] = lin(sum_e softmax(logits)_e,h (x post_e) * dtp(v_e, sh_e, wv)) + bias * sum_e alpha  -> (n_dst, F)."""
+    out = torch.empty(g.n_dst, v.shape[1], dtype=torch.float32, device=v.device)
+    _call("dedf_value_reduce", mul1, ptr(g.row_ptr, torch.int32), g.n_dst, g.n_seg, ptr(v), ptr(sh), ptr(logits), ptr(post), ptr(wv),
+          ptr(V0), ptr(V1), ptr(V2), ptr(vb), ptr(out), stream())
+    return out

@@ -153,6 +153,14 @@ int dedf_edge_tp_lin(int mul1, int epilogue, const float* x_src, const float* x_
 int dedf_segment_softmax_reduce(const int* row_ptr, int n_dst, int n_seg, const float* logits, const float* val,
                                 int m0, int m1, int m2, float* out, cudaStream_t stream);
 
+/* The value path of the attention, reassociated: out[d] = lin(sum_e alpha_{e,h} dtp(v_e, sh_e, w_shared)) +
+ * bias * sum_e alpha_{e,h} with alpha = per-destination softmax of `logits` (x `post[e]` after the softmax when non-NULL).
+ * Replaces sep_value (graph_attention.py:237-239: DepthwiseTensorProduct + LinearRS per EDGE) + scatter_logsumexp + exp +
+ * scatter(sum) (:254-266): the linear layer runs once per destination.  v (E,F) and logits (E,4) must be 16-byte aligned. */
+int dedf_value_reduce(int mul1, const int* row_ptr, int n_dst, int n_seg, const float* v, const float* sh, const float* logits,
+                      const float* post, const float* wv, const float* V0, const float* V1, const float* V2, const float* vb,
+                      float* out, cudaStream_t stream);
+
 /* "K1": out[d] = sum_{e -> d} alpha[e, head(u)] * DTP(x[src_e], sh_e, w_e)   (N_dst, 1568 | 784), op-equivalent to
  * scatter(alpha * o3.TensorProduct(x[edge_src], sh, weight), edge_dst) of graph_attention.py:231-232,264-265.
  * sh_stride = 9: packed harmonics, plain loads.  sh_stride = 12: rows padded to 48 bytes, which lets every operand
