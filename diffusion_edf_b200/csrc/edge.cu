@@ -670,13 +670,16 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
     using D = Dtp<G>;
     constexpr int NCW = G / 8, NW = 2 * NCW, NT = NW * 32, CH = kVrChunk;
     constexpr int B1 = D::D0, B2 = D::D0 + 3 * D::D1;             // block offsets inside one head copy of the reduced TP output
+    constexpr int NV0 = D::D0 * D::M0, NV1 = D::D1 * D::M1, NV2 = D::D2 * D::M2;
     extern __shared__ __align__(16) float smem[];
     float* s_v = smem;                          // [CH][F]
     float* s_lg = s_v + CH * D::F;              // [CH][4] logits -> alpha (in place)
     float* s_sh = s_lg + CH * 4;                // [CH][12]
     float* s_D = s_sh + CH * 12;                // [4 heads][FOUT]
+    float* s_V = s_D + 4 * D::FOUT;             // sep_value.lin weights [V0 | V1 | V2], staged once per CTA
     __shared__ float s_red[NW][4], s_sal[4];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_cum[DEDF_MAX_SCALES + 1], s_beg[DEDF_MAX_SCALES];
+    __shared__ __align__(8) uint64_t bar, vbar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cw = warp % NCW, hp = warp / NCW;
     const int ch0 = cw * 16 + (lane & 15), ch1 = cw * 8 + (lane & 7), ch2 = cw * 4 + (lane & 3);
@@ -684,18 +687,51 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
     w0[0] = a.wv[D::W_K0 + ch0]; w0[1] = a.wv[D::W_K1 + ch0]; w0[2] = a.wv[D::W_K2 + ch0];
 #pragma unroll
     for (int i = 0; i < 6; ++i) { w1[i] = a.wv[D::W_K3 + ch1 + i * D::M1]; w2[i] = a.wv[D::W_K9 + ch2 + i * D::M2]; }
-    if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+    if (tid == 0) {
+        mbar_init(&bar, 1); mbar_init(&vbar, 1);
+        mbar_init_fence();
+        // the linear layer's weights do not depend on the previous kernel: their copy overlaps its tail (PDL)
+        mbar_expect_tx(&vbar, (uint32_t)(NV0 + NV1 + NV2) * 4u);
+        bulk_g2s_chunked(s_V, a.V0, NV0 * 4u, &vbar);
+        bulk_g2s_chunked(s_V + NV0, a.V1, NV1 * 4u, &vbar);
+        bulk_g2s_chunked(s_V + NV0 + NV1, a.V2, NV2 * 4u, &vbar);
+    }
     pdl_wait(); pdl_launch();     // PDL: see common.cuh
     __syncthreads();
     uint32_t ph = 0;
+    bool v_pending = true;
+
+    // stage edges [f0, f0 + n) of destination d's FLAT edge list (all segments back to back) into the chunk buffers
+    auto issue_chunk = [&](int f0, int n) {       // thread 0 only; s_cum / s_beg are valid
+        mbar_expect_tx(&bar, (uint32_t)n * (D::F + 4) * 4u);
+        for (int s = 0; s < a.n_seg; ++s) {
+            const int lo = max(f0, s_cum[s]), hi = min(f0 + n, s_cum[s + 1]);
+            if (lo < hi) {
+                const size_t e = (size_t)s_beg[s] + (lo - s_cum[s]);
+                bulk_g2s_chunked(s_v + (size_t)(lo - f0) * D::F, a.v + e * D::F, (uint32_t)(hi - lo) * D::F * 4u, &bar);
+                bulk_g2s(s_lg + (lo - f0) * 4, a.logits + e * 4, (uint32_t)(hi - lo) * 16u, &bar);
+            }
+        }
+    };
 
     for (int d = blockIdx.x; d < a.n_dst; d += gridDim.x) {
-        // ---- softmax statistics over all incoming edges (all segments): per-head max, log Z ----
+        __syncthreads();                                           // previous destination done with every shared buffer
+        if (tid == 0) {
+            int c = 0;
+            for (int s = 0; s < a.n_seg; ++s) {
+                const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
+                s_cum[s] = c; s_beg[s] = b; c += e - b;
+            }
+            s_cum[a.n_seg] = c;
+            if (c > 0) issue_chunk(0, min(CH, c));                 // the first chunk flies while the statistics are computed
+        }
+        if (tid < 4) s_sal[tid] = 0.f;
+        __syncthreads();
+        const int deg = s_cum[a.n_seg];
+        // ---- softmax statistics over all incoming edges: per-head max, log Z (logits straight from global / L2) ----
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        int deg = 0;
         for (int s = 0; s < a.n_seg; ++s) {
-            const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
-            deg += e - b;
+            const int b = s_beg[s], e = b + (s_cum[s + 1] - s_cum[s]);
             for (int i = b + tid; i < e; i += NT) {
                 const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
                 mx[0] = fmaxf(mx[0], l.x); mx[1] = fmaxf(mx[1], l.y); mx[2] = fmaxf(mx[2], l.z); mx[3] = fmaxf(mx[3], l.w);
@@ -703,15 +739,13 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) mx[h] = warp_max(mx[h]);
-        __syncthreads();
         if (lane == 0) { s_red[warp][0] = mx[0]; s_red[warp][1] = mx[1]; s_red[warp][2] = mx[2]; s_red[warp][3] = mx[3]; }
-        if (tid < 4) s_sal[tid] = 0.f;
         __syncthreads();
 #pragma unroll
         for (int h = 0; h < 4; ++h) { float m = s_red[0][h]; for (int w = 1; w < NW; ++w) m = fmaxf(m, s_red[w][h]); mx[h] = m; }
         float sm[4] = {0.f, 0.f, 0.f, 0.f};
         for (int s = 0; s < a.n_seg; ++s) {
-            const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
+            const int b = s_beg[s], e = b + (s_cum[s + 1] - s_cum[s]);
             for (int i = b + tid; i < e; i += NT) {
                 const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
                 sm[0] += __expf(l.x - mx[0]); sm[1] += __expf(l.y - mx[1]); sm[2] += __expf(l.z - mx[2]); sm[3] += __expf(l.w - mx[3]);
@@ -741,71 +775,78 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
 #pragma unroll
             for (int k = 0; k < 22; ++k) acc2[h][k] = 0.f;
         }
-        for (int s = 0; s < a.n_seg; ++s) {
-            const int sb = a.row_ptr[(size_t)s * a.n_dst + d], se = a.row_ptr[(size_t)s * a.n_dst + d + 1];
-            for (int c0 = sb; c0 < se; c0 += CH) {
-                const int n = min(CH, se - c0);
+        for (int f0 = 0; f0 < deg; f0 += CH) {
+            const int n = min(CH, deg - f0);
+            if (f0 > 0) {
                 __syncthreads();                                   // previous chunk fully consumed
-                if (tid == 0) {
-                    mbar_expect_tx(&bar, (uint32_t)n * (D::F + 4) * 4u);
-                    bulk_g2s_chunked(s_v, a.v + (size_t)c0 * D::F, (uint32_t)n * D::F * 4u, &bar);
-                    bulk_g2s(s_lg, a.logits + (size_t)c0 * 4, (uint32_t)n * 16u, &bar);
+                if (tid == 0) issue_chunk(f0, n);
+            }
+            // harmonics of the chunk (9-float rows are not 16-byte aligned: plain loads), per segment piece
+            for (int i = tid; i < n * 9; i += NT) {
+                const int r = i / 9, f = f0 + r;
+                int s = 0;
+                while (f >= s_cum[s + 1]) ++s;
+                s_sh[r * 12 + (i % 9)] = a.sh[((size_t)s_beg[s] + (f - s_cum[s])) * 9 + (i % 9)];
+            }
+            mbar_wait(&bar, ph); ph ^= 1u;
+            __syncthreads();
+            // logits -> alpha (x optional post factor), in place; per-head sums for the bias term (fixed order)
+            if (tid < CH) {
+                float4 al = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tid < n) {
+                    const float4 l = *reinterpret_cast<const float4*>(s_lg + tid * 4);
+                    float pf = 1.0f;
+                    if (a.post) {
+                        const int f = f0 + tid;
+                        int s = 0;
+                        while (f >= s_cum[s + 1]) ++s;
+                        pf = a.post[(size_t)s_beg[s] + (f - s_cum[s])];
+                    }
+                    al = make_float4(__expf(l.x - logZ[0]) * pf, __expf(l.y - logZ[1]) * pf, __expf(l.z - logZ[2]) * pf, __expf(l.w - logZ[3]) * pf);
                 }
-                for (int i = tid; i < n * 9; i += NT) s_sh[(i / 9) * 12 + (i % 9)] = a.sh[(size_t)c0 * 9 + i];
-                mbar_wait(&bar, ph); ph ^= 1u;
-                __syncthreads();
-                // logits -> alpha (x optional post factor), in place; per-head sums for the bias term (fixed order)
-                if (tid < CH) {
-                    float4 al = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (tid < n) {
-                        const float4 l = *reinterpret_cast<const float4*>(s_lg + tid * 4);
-                        const float pf = a.post ? a.post[c0 + tid] : 1.0f;
-                        al = make_float4(__expf(l.x - logZ[0]) * pf, __expf(l.y - logZ[1]) * pf, __expf(l.z - logZ[2]) * pf, __expf(l.w - logZ[3]) * pf);
-                    }
-                    *reinterpret_cast<float4*>(s_lg + tid * 4) = al;
-                    float t0 = warp_sum(al.x), t1 = warp_sum(al.y), t2 = warp_sum(al.z), t3 = warp_sum(al.w);
-                    if (lane == 0) { s_red[warp][0] = t0; s_red[warp][1] = t1; s_red[warp][2] = t2; s_red[warp][3] = t3; }
+                *reinterpret_cast<float4*>(s_lg + tid * 4) = al;
+                float t0 = warp_sum(al.x), t1 = warp_sum(al.y), t2 = warp_sum(al.z), t3 = warp_sum(al.w);
+                if (lane == 0) { s_red[warp][0] = t0; s_red[warp][1] = t1; s_red[warp][2] = t2; s_red[warp][3] = t3; }
+            }
+            __syncthreads();
+            if (tid < 4) s_sal[tid] += s_red[0][tid] + s_red[1][tid];      // CH = 64 = the first two warps
+            // packs of 8 edges
+            for (int p0 = 0; p0 < n; p0 += 8) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {                           // l = 0: 2 edges x 16 channels
+                    const int e = p0 + 2 * it + (lane >> 4);
+                    const bool ok = e < n;
+                    const float x = ok ? s_v[e * D::F + ch0] : 0.f;
+                    const float al0 = ok ? s_lg[e * 4 + 2 * hp] : 0.f, al1 = ok ? s_lg[e * 4 + 2 * hp + 1] : 0.f;
+                    float o[9];
+                    dtp_l0(x, w0[0], w0[1], w0[2], s_sh + (ok ? e : 0) * 12, o);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) { acc0[0][k] = fmaf(al0, o[k], acc0[0][k]); acc0[1][k] = fmaf(al1, o[k], acc0[1][k]); }
                 }
-                __syncthreads();
-                if (tid < 4) s_sal[tid] += s_red[0][tid] + s_red[1][tid];      // CH = 64 = the first two warps
-                // packs of 8 edges
-                for (int p0 = 0; p0 < n; p0 += 8) {
 #pragma unroll
-                    for (int it = 0; it < 4; ++it) {                           // l = 0: 2 edges x 16 channels
-                        const int e = p0 + 2 * it + (lane >> 4);
-                        const bool ok = e < n;
-                        const float x = ok ? s_v[e * D::F + ch0] : 0.f;
-                        const float al0 = ok ? s_lg[e * 4 + 2 * hp] : 0.f, al1 = ok ? s_lg[e * 4 + 2 * hp + 1] : 0.f;
-                        float o[9];
-                        dtp_l0(x, w0[0], w0[1], w0[2], s_sh + (ok ? e : 0) * 12, o);
+                for (int it = 0; it < 2; ++it) {                           // l = 1: 4 edges x 8 channels
+                    const int e = p0 + 4 * it + (lane >> 3);
+                    const bool ok = e < n;
+                    const float* xs = s_v + (ok ? e : 0) * D::F + D::M0 + 3 * ch1;
+                    const float xv[3] = {ok ? xs[0] : 0.f, ok ? xs[1] : 0.f, ok ? xs[2] : 0.f};
+                    const float al0 = ok ? s_lg[e * 4 + 2 * hp] : 0.f, al1 = ok ? s_lg[e * 4 + 2 * hp + 1] : 0.f;
+                    float o[20];
+                    dtp_l1(xv, w1, s_sh + (ok ? e : 0) * 12, o);
 #pragma unroll
-                        for (int k = 0; k < 9; ++k) { acc0[0][k] = fmaf(al0, o[k], acc0[0][k]); acc0[1][k] = fmaf(al1, o[k], acc0[1][k]); }
-                    }
+                    for (int k = 0; k < 20; ++k) { acc1[0][k] = fmaf(al0, o[k], acc1[0][k]); acc1[1][k] = fmaf(al1, o[k], acc1[1][k]); }
+                }
+                {                                                          // l = 2: 8 edges x 4 channels
+                    const int e = p0 + (lane >> 2);
+                    const bool ok = e < n;
+                    const float* xs = s_v + (ok ? e : 0) * D::F + D::M0 + 3 * D::M1 + 5 * ch2;
+                    float xv[5];
 #pragma unroll
-                    for (int it = 0; it < 2; ++it) {                           // l = 1: 4 edges x 8 channels
-                        const int e = p0 + 4 * it + (lane >> 3);
-                        const bool ok = e < n;
-                        const float* xs = s_v + (ok ? e : 0) * D::F + D::M0 + 3 * ch1;
-                        const float xv[3] = {ok ? xs[0] : 0.f, ok ? xs[1] : 0.f, ok ? xs[2] : 0.f};
-                        const float al0 = ok ? s_lg[e * 4 + 2 * hp] : 0.f, al1 = ok ? s_lg[e * 4 + 2 * hp + 1] : 0.f;
-                        float o[20];
-                        dtp_l1(xv, w1, s_sh + (ok ? e : 0) * 12, o);
+                    for (int i = 0; i < 5; ++i) xv[i] = ok ? xs[i] : 0.f;
+                    const float al0 = ok ? s_lg[e * 4 + 2 * hp] : 0.f, al1 = ok ? s_lg[e * 4 + 2 * hp + 1] : 0.f;
+                    float o[22];
+                    dtp_l2(xv, w2, s_sh + (ok ? e : 0) * 12, o);
 #pragma unroll
-                        for (int k = 0; k < 20; ++k) { acc1[0][k] = fmaf(al0, o[k], acc1[0][k]); acc1[1][k] = fmaf(al1, o[k], acc1[1][k]); }
-                    }
-                    {                                                          // l = 2: 8 edges x 4 channels
-                        const int e = p0 + (lane >> 2);
-                        const bool ok = e < n;
-                        const float* xs = s_v + (ok ? e : 0) * D::F + D::M0 + 3 * D::M1 + 5 * ch2;
-                        float xv[5];
-#pragma unroll
-                        for (int i = 0; i < 5; ++i) xv[i] = ok ? xs[i] : 0.f;
-                        const float al0 = ok ? s_lg[e * 4 + 2 * hp] : 0.f, al1 = ok ? s_lg[e * 4 + 2 * hp + 1] : 0.f;
-                        float o[22];
-                        dtp_l2(xv, w2, s_sh + (ok ? e : 0) * 12, o);
-#pragma unroll
-                        for (int k = 0; k < 22; ++k) { acc2[0][k] = fmaf(al0, o[k], acc2[0][k]); acc2[1][k] = fmaf(al1, o[k], acc2[1][k]); }
-                    }
+                    for (int k = 0; k < 22; ++k) { acc2[0][k] = fmaf(al0, o[k], acc2[0][k]); acc2[1][k] = fmaf(al1, o[k], acc2[1][k]); }
                 }
             }
         }
@@ -822,7 +863,6 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
                 acc2[h][k] += __shfl_xor_sync(0xffffffffu, acc2[h][k], 16);
             }
         }
-        __syncthreads();                                           // s_D of the previous destination has been read
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             float* Dh = s_D + (size_t)(2 * hp + h) * D::FOUT;
@@ -854,6 +894,7 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
                 Dh[D::C0_K12 + ch2] = acc2[h][13];
             }
         }
+        if (v_pending) { mbar_wait(&vbar, 0); v_pending = false; }
         __syncthreads();
         // ---- linear layer, once per destination: out[c] = sum_k V_l[k, u] D_{head(u)}[k, m] (+ bias * sum alpha) ----
         for (int c = tid; c < D::F; c += NT) {
@@ -865,13 +906,12 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
             const int KL = (l == 0) ? D::D0 : (l == 1) ? D::D1 : D::D2;
             const int dd = 2 * l + 1;
             const int h = u / (ML / 4);
-            const float* V = ((l == 0) ? a.V0 : (l == 1) ? a.V1 : a.V2) + u;
+            const float* V = s_V + ((l == 0) ? 0 : (l == 1) ? NV0 : NV0 + NV1) + u;
             const float* Dl = s_D + (size_t)h * D::FOUT + ((l == 0) ? 0 : (l == 1) ? B1 : B2) + m;
             float acc = 0.f, accb = 0.f;
             for (int k = 0; k < KL; k += 4) {                      // every D_l is a multiple of 4
-                const float v0 = __ldg(V + (size_t)k * ML), v1 = __ldg(V + (size_t)(k + 1) * ML), v2 = __ldg(V + (size_t)(k + 2) * ML), v3 = __ldg(V + (size_t)(k + 3) * ML);
-                acc = fmaf(v0, Dl[k * dd], acc); accb = fmaf(v1, Dl[(k + 1) * dd], accb);
-                acc = fmaf(v2, Dl[(k + 2) * dd], acc); accb = fmaf(v3, Dl[(k + 3) * dd], accb);
+                acc = fmaf(V[k * ML], Dl[k * dd], acc); accb = fmaf(V[(k + 1) * ML], Dl[(k + 1) * dd], accb);
+                acc = fmaf(V[(k + 2) * ML], Dl[(k + 2) * dd], acc); accb = fmaf(V[(k + 3) * ML], Dl[(k + 3) * dd], accb);
             }
             acc += accb;
             if (l == 0 && a.vb) acc = fmaf(a.vb[u], s_sal[h], acc);
@@ -1467,7 +1507,7 @@ extern "C" int dedf_edge_tp_reduce(int mul1, const float* x, const int* row_ptr,
 template <int G>
 static int launch_value_reduce(const ValueReduceArgs& a, cudaStream_t stream) {
     using D = Dtp<G>;
-    const size_t smem = ((size_t)kVrChunk * (D::F + 4 + 12) + 4 * (size_t)D::FOUT) * sizeof(float);
+    const size_t smem = ((size_t)kVrChunk * (D::F + 4 + 12) + 4 * (size_t)D::FOUT + (size_t)D::D0 * D::M0 + (size_t)D::D1 * D::M1 + (size_t)D::D2 * D::M2) * sizeof(float);
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(value_reduce_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
     launch_pdl(value_reduce_kernel<G>, dim3(grid_for(a.n_dst, 1, kNumSMs * 8)), dim3(G * 8), smem, stream, a);
@@ -1480,6 +1520,8 @@ extern "C" int dedf_value_reduce(int mul1, const int* row_ptr, int n_dst, int n_
                                  float* out, cudaStream_t stream) {
     if (!row_ptr || !v || !sh || !logits || !wv || !V0 || !V1 || !V2 || !out || n_seg < 1) return DEDF_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(logits) & 15)) return DEDF_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(V0) & 15) || (reinterpret_cast<uintptr_t>(V1) & 15) || (reinterpret_cast<uintptr_t>(V2) & 15)) return DEDF_ERR_ARG;
+    if (n_seg > DEDF_MAX_SCALES) return DEDF_ERR_ARG;
     if (n_dst <= 0) return DEDF_OK;
     ValueReduceArgs a{row_ptr, n_dst, n_seg, v, sh, logits, post, wv, V0, V1, V2, vb, out};
     if (mul1 == 32) return launch_value_reduce<32>(a, stream);
