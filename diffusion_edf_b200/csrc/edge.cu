@@ -300,6 +300,10 @@ enum { EPI_ACT = 0, EPI_LIN = 1 };
 #define DEDF_TPLIN_TE32 16
 #endif
 constexpr int kTpLinTE32 = DEDF_TPLIN_TE32;
+#ifndef DEDF_TPLIN_PREFETCH
+#define DEDF_TPLIN_PREFETCH 0
+#endif
+constexpr int kTpLinPrefetch = DEDF_TPLIN_PREFETCH;   // k-steps of weight rows prefetched into L1 ahead of the K loop
 
 template <int G, int EPI>
 struct TpLinCfg {
@@ -454,9 +458,9 @@ edge_tp_lin_kernel(TpLinArgs a, int lda0, int lda1, int lda2) {
         if (tid < I0) { which = 0; cg = tid % (C::N0 / 4); rg = tid / (C::N0 / 4); }
         else if (tid < I0 + I1) { which = 1; const int t = tid - I0; cg = t % (C::N1 / 4); rg = t / (C::N1 / 4); }
         else if (tid < I0 + I1 + I2) { which = 2; const int t = tid - I0 - I1; cg = t % (C::N2 / 4); rg = t / (C::N2 / 4); }
-        if (which == 0) gemm_item_4x4<true>(A0, lda0, TE / 4, rg, a.W0, C::N0, 4 * cg, D::D0, acc);
-        else if (which == 1) gemm_item_4x4<true>(A1, lda1, 3 * TE / 4, rg, a.W1, C::N1, 4 * cg, D::D1, acc);
-        else if (which == 2) gemm_item_4x4<true>(A2, lda2, 5 * TE / 4, rg, a.W2, C::N2, 4 * cg, D::D2, acc);
+        if (which == 0) gemm_item_4x4<true, false, kTpLinPrefetch>(A0, lda0, TE / 4, rg, a.W0, C::N0, 4 * cg, D::D0, acc);
+        else if (which == 1) gemm_item_4x4<true, false, kTpLinPrefetch>(A1, lda1, 3 * TE / 4, rg, a.W1, C::N1, 4 * cg, D::D1, acc);
+        else if (which == 2) gemm_item_4x4<true, false, kTpLinPrefetch>(A2, lda2, 5 * TE / 4, rg, a.W2, C::N2, 4 * cg, D::D2, acc);
         TPL_STAMP();
         __syncthreads();   // all A reads done -> the region may be overwritten with the outputs
         if (which == 0) {

@@ -16,7 +16,12 @@
 namespace dedf {
 
 // acc[i][j] += sum_k A[row_i][k] * W[k][col0 + j]     (K % 4 == 0, N % 4 == 0)
-template <bool kVecW, bool kWShared = false>
+//
+// kPrefetch > 0 (global W only): every iteration also issues one `prefetch.global.L1` for the W row this thread's
+// column group needs kPrefetch k-steps ahead (row k + kPrefetch + (rg & 3): the 4 threads that share a column group
+// cover the 4 rows of a step between them).  The K loop of the edge kernels is bound by the L2 latency of the first
+// touch of each weight row (profiles/r1_tp_lin_act_ncu_full_summary.txt); the prefetch turns it into an L1 hit.
+template <bool kVecW, bool kWShared = false, int kPrefetch = 0>
 __device__ __forceinline__ void gemm_item_4x4(const float* __restrict__ A, int lda, int n_rg, int rg,
                                               const float* __restrict__ W, int N, int col0, int K,
                                               float acc[4][4]) {
@@ -27,6 +32,10 @@ __device__ __forceinline__ void gemm_item_4x4(const float* __restrict__ A, int l
     const int K4 = K & ~3;
 #pragma unroll 2
     for (int k = 0; k < K4; k += 4) {
+        if (kPrefetch > 0 && !kWShared) {
+            const int kp = k + kPrefetch + (rg & 3);
+            if (kp < K) asm volatile("prefetch.global.L1 [%0];" ::"l"(W + (size_t)kp * N + col0));
+        }
         const float4 x0 = *reinterpret_cast<const float4*>(a0 + k);
         const float4 x1 = *reinterpret_cast<const float4*>(a1 + k);
         const float4 x2 = *reinterpret_cast<const float4*>(a2 + k);

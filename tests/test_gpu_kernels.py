@@ -177,6 +177,67 @@ def test_graph_attention_pieces(cuda, G):
 
 
 @pytest.mark.parametrize("G", [32, 16])
+def test_value_reduce_multisegment(cuda, G):
+    """dedf_value_reduce (the value path reassociated) on a ragged multi-segment graph: destinations with no
+    edges at all, with edges in one segment only, with more than one 64-edge chunk; the post-softmax factor; against the
+    reference arithmetic (sep_value per edge -> scatter_logsumexp -> exp -> scatter sum, graph_attention.py:237-266) and
+    against the un-reassociated kernels; bit-reproducible."""
+    from diffusion_edf_b200 import _lib as L, layers, ops
+    gen = torch.Generator().manual_seed(40 + G)
+    torch.manual_seed(40 + G)
+    irr = OIrreps(IRR[G])
+    F = irr.dim
+    n_dst, n_seg = 23, 3
+    deg = torch.poisson(torch.full((n_seg, n_dst), 12.0), generator=gen).long()
+    deg[:, 0] = 0                      # isolated destination
+    deg[0, 1] = 0; deg[2, 1] = 0       # one segment only
+    deg[1, 2] = 150                    # three chunks of 64
+    deg[:, 3] = torch.tensor([64, 0, 64])   # exactly two full chunks
+    flat = deg.reshape(-1)
+    row_ptr = torch.zeros(n_seg * n_dst + 1, dtype=torch.long)
+    row_ptr[1:] = flat.cumsum(0)
+    E = int(row_ptr[-1])
+    ed = torch.arange(n_dst).repeat(n_seg).repeat_interleave(flat)
+    es = torch.randint(0, 50, (E,), generator=gen)
+    sh, _ = _random_sh(E, gen)
+    v = torch.randn(E, F, generator=gen)
+    logit = torch.randn(E, 4, generator=gen) * 3
+    post = torch.rand(E, generator=gen)
+    oga = OM.GraphAttentionMLP2(irr, SH, irr, [32, 16, 16], 4)
+    with torch.no_grad():
+        for prm in oga.parameters():
+            if prm.abs().sum() == 0:
+                prm.uniform_(-0.5, 0.5)
+    pga = layers.GraphAttention(IRR[G], IRR[G], [32, 16, 16], 4)
+    pga.load_state_dict(oga.state_dict())
+    pga = pga.to(cuda)
+    p = pga.packed()
+    rp = row_ptr.int().to(cuda)
+    csr = ops.Csr(rp, es.int().to(cuda), ed.int().to(cuda), rp[-1:], E, n_dst, n_seg)
+    for use_post in (False, True):
+        with torch.no_grad():
+            val_ref = oga.sep_value(v, edge_attr=sh, edge_scalars=None)
+            logZ = OG.scatter_logsumexp(logit, ed, n_dst)
+            alpha = torch.exp(logit - logZ[ed])
+            if use_post:
+                alpha = alpha * post[:, None]
+            ref = ON.heads2vec(OG.scatter_sum(ON.vec2heads(val_ref, oga.irreps_head, 4) * alpha[..., None], ed, n_dst), oga.irreps_head)
+        pc = post.to(cuda) if use_post else None
+        out = ops.value_reduce(G, csr, v.to(cuda), sh.to(cuda), logit.to(cuda), pc, p["wv"], p["V0"], p["V1"], p["V2"], p["vb"])
+        assert_close(out, ref, TOL, f"value_reduce(post={use_post})")
+        assert float(out[0].abs().max()) == 0.0, "isolated destination must give zeros"
+        out2 = ops.value_reduce(G, csr, v.to(cuda), sh.to(cuda), logit.to(cuda), pc, p["wv"], p["V0"], p["V1"], p["V2"], p["vb"])
+        assert torch.equal(out, out2), "value_reduce must be deterministic"
+        # the un-reassociated kernels (linear per edge, then the softmax-weighted sum)
+        val = torch.empty(E, F, device=cuda)
+        ops.edge_tp_lin(G, L.EPI_LIN, v.to(cuda), None, True, csr, sh.to(cuda), p["wv"], 0, p["V0"], p["V1"], p["V2"], p["vb"], out=val)
+        if use_post:
+            val = ops.row_scale(val, pc, pga.irreps_emb.m)
+        old = ops.segment_softmax_reduce(csr, logit.to(cuda), val, pga.irreps_emb.m)
+        assert_close(out, old, TOL, f"value_reduce vs tp_lin+softmax (post={use_post})")
+
+
+@pytest.mark.parametrize("G", [32, 16])
 def test_edge_tp_reduce_k1(cuda, G):
     """K1 == scatter(alpha_head(u) * o3.TensorProduct(x[src], sh, w), dst)."""
     from diffusion_edf_b200 import ops
