@@ -1,0 +1,466 @@
+// edge_tp_act_tc: the attention block's per-edge hot op on the tensor cores.
+//
+//   message = x_src[src] (+ x_dst[dst]) -> depthwise CG tensor product with the 9 harmonics and the per-edge radial
+//   weights (o3.TensorProduct 'uvu', equiformer/tensor_product_rescale.py:352-382) -> block-diagonal LinearRS
+//   (sep_alpha | sep_act.lin) -> SmoothLeakyReLU . alpha_dot (+ edge logit) = attention logits, Gate = value rows
+//   (graph_attention.py:231-246, fast_activation.py:210-224)
+//
+// Same arithmetic and outputs as edge_tp_lin_kernel<G, EPI_ACT> (edge.cu); the block-diagonal linear layer (104 kMAC per
+// edge, 90 % of the FLOPs) moves from the fp32 FMA pipe to tcgen05.mma kind::tf32 with the 3xTF32 split (tc.cuh), fp32
+// accumulators in TMEM.  What makes it fit:
+//
+//   * K is consumed in CHUNKS of input channels: chunk j = l=0 channels [8j, 8j+8), l=1 channels [4j, 4j+4), l=2 channels
+//     [2j, 2j+2) (8 chunks for 64x0e+32x1e+16x2e, 4 for 32x0e+16x1e+8x2e).  One chunk contributes 14 / 24 / 22 columns
+//     to the l_out = 0 / 1 / 2 GEMMs (padded to 16 / 24 / 24); the host packs the weight rows in the same order
+//     (layers.pack_tp_act_tc).  The (E, 1568) tensor-product output therefore never exists, not even per tile: a chunk
+//     of it (32 edges) is 26 KB per hi / lo part, double-buffered.
+//   * the tile's rows are the M side: 32 rows (l_out = 0), 96 rows (m, e) (l_out = 1), 160 rows (l_out = 2, two MMAs);
+//     M is always 128 and the rows past the stored ones alias the following shared memory (finite or not, they only
+//     reach accumulator rows nobody reads).
+//   * warp roles: 6 producer warps (lane = edge; warps 0-3 take one l=1 channel + two l=0 channels of the chunk, warps
+//     4-5 one l=2 channel: balanced to 7 %), each thread writing whole float4 K-groups of the chunk-major operand;
+//     warp 6 = TMA weight ring; warp 7 = MMA issuer (33 tcgen05.mma per chunk); warps 8-11 = epilogue (TMEM -> bias,
+//     activations, gates -> staged value rows -> one bulk store per edge row), double-buffered accumulators (2 x 256
+//     TMEM columns) so the epilogue of tile t overlaps the production of tile t + 1.
+#include "common.cuh"
+#include "tc.cuh"
+#include "cg_slots.cuh"
+#include "../../include/dedf.h"
+
+namespace dedf {
+
+constexpr int kTaTE = 32;
+constexpr int kTaProdWarps = 6;
+constexpr int kTaTmaWarp = 6, kTaMmaWarp = 7, kTaEpiWarp0 = 8;
+constexpr int kTaEpiWarps = 8;                      // two warpgroups: each takes half of the tile's edges / output columns
+constexpr int kTaThreads = (kTaEpiWarp0 + kTaEpiWarps) * 32;
+constexpr int kTaAccCols = 128;                     // TMEM columns of one accumulator buffer
+constexpr int kTaStages = 2;                        // A chunk stages and weight ring stages
+constexpr int kKC0 = 16, kKC1 = 24, kKC2 = 24;      // K columns per chunk of the three GEMMs
+constexpr int kR0 = kTaTE, kR1 = 3 * kTaTE, kR2 = 5 * kTaTE;   // stored rows
+constexpr int kA0Off = 0;
+constexpr int kA1Off = kA0Off + (kKC0 / 4) * kR0 * 16;          //  2048
+constexpr int kA2Off = kA1Off + (kKC1 / 4) * kR1 * 16;          // 11264
+constexpr int kAPart = kA2Off + (kKC2 / 4) * kR2 * 16;          // 26624 (hi or lo)
+constexpr int kAStage = 2 * kAPart;
+
+template <int G>
+struct TaCfg {
+    using D = Dtp<G>;
+    static constexpr int NCH = D::M0 / 8;                                  // chunks
+    static constexpr int MA = D::M0;                                       // alpha channels
+    static constexpr int N0 = MA + D::M0 + D::M1 + D::M2;                  // 176 / 88
+    static constexpr int N0P = (N0 + 15) / 16 * 16;                        // 176 / 96
+    static constexpr int N1P = (D::M1 + 15) / 16 * 16;                     // 32 / 16
+    static constexpr int N2P = (D::M2 + 15) / 16 * 16;                     // 16 / 16
+    static constexpr int W0Off = 0;
+    static constexpr int W1Off = W0Off + (kKC0 / 4) * N0P * 16;
+    static constexpr int W2Off = W1Off + (kKC1 / 4) * N1P * 16;
+    static constexpr int WPart = W2Off + (kKC2 / 4) * N2P * 16;            // 15872 / 9216
+    static constexpr int WStage = 2 * WPart;
+    static constexpr int MT0 = (N0P + 127) / 128;                          // M tiles of the (swapped) l_out = 0 GEMM
+    static constexpr int T0 = 0, T1 = 2 * kTaTE, T2A = T1 + N1P, T2B = T2A + N2P;   // TMEM columns of the accumulators
+    static_assert(T2B + N2P <= kTaAccCols, "accumulator buffer");
+    static constexpr int LDO = D::F + 4;                                   // staged value row stride (floats)
+    static constexpr int NG = D::M1 + D::M2;                               // gates
+    // dynamic shared memory
+    static constexpr int OffA = 0;
+    static constexpr int OffW = OffA + kTaStages * kAStage;
+    static constexpr int OffOut = OffW + kTaStages * WStage;
+    static constexpr int OffGate = OffOut + kTaTE * LDO * 4;
+    static constexpr int NGP = NG + 1;                                     // gate table row stride (odd: conflict-free both ways)
+    static constexpr int OffRed = OffGate + kTaTE * NGP * 4;               // [MA][33] attention-logit terms
+    static constexpr int OffPar = OffRed + MA * 33 * 4;
+    static constexpr int Smem = OffPar + (N0P + MA) * 4;
+};
+
+struct TpActArgs {
+    const float* x_src; const float* x_dst;
+    const int* edge_src; const int* edge_dst; const int* n_edges;
+    const float* sh; const float* w; long long w_stride;
+    const float* Wp;          // packed weight chunks (layers.pack_tp_act_tc)
+    const float* bias0; const float* alpha_dot; const float* edge_logit;
+    float* logits; float* out;
+    long long* dbg;
+};
+
+template <int G>
+__global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs a) {
+    using C = TaCfg<G>;
+    using D = Dtp<G>;
+    constexpr int NCH = C::NCH;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sA = smem + C::OffA;
+    unsigned char* sW = smem + C::OffW;
+    float* s_out = reinterpret_cast<float*>(smem + C::OffOut);
+    float* s_gate = reinterpret_cast<float*>(smem + C::OffGate);      // [32][NGP]
+    float* s_red = reinterpret_cast<float*>(smem + C::OffRed);        // [MA][33]
+    float* s_b0 = reinterpret_cast<float*>(smem + C::OffPar);         // [N0P] bias
+    float* s_adot = s_b0 + C::N0P;                                    // [MA]
+    __shared__ __align__(8) uint64_t fullA[kTaStages], emptyA[kTaStages], fullW[kTaStages], emptyW[kTaStages], accFull[2], accEmpty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- one-time setup (overlaps the previous kernel under PDL: parameters only) ----
+    if (tid == 0) {
+        for (int s = 0; s < kTaStages; ++s) {
+            mbar_init(&fullA[s], kTaProdWarps); mbar_init(&emptyA[s], 1);
+            mbar_init(&fullW[s], 1); mbar_init(&emptyW[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) { mbar_init(&accFull[b], 1); mbar_init(&accEmpty[b], kTaEpiWarps); }
+        mbar_init_fence();
+    }
+    if (warp == kTaTmaWarp) tc::tmem_alloc(&tmem_base_s, 2 * kTaAccCols);
+    for (int i = tid; i < kTaStages * kAStage / 16; i += kTaThreads)            // pad columns must be finite (x zero weights)
+        reinterpret_cast<float4*>(sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < C::N0P; i += kTaThreads) s_b0[i] = (i < C::N0 && a.bias0) ? a.bias0[i] : 0.f;
+    for (int i = tid; i < C::MA; i += kTaThreads) s_adot[i] = a.alpha_dot[i];
+    tc::fence_async_smem();
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    pdl_wait(); pdl_launch();
+    const int E = *a.n_edges;
+    const int n_tiles = (E + kTaTE - 1) / kTaTE;
+
+    if (warp < kTaProdWarps) {
+        // =========================== producers: CG chunk -> hi / lo A operand ===========================
+        const int e = lane;
+        uint32_t st = 0, ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int e0 = tile * kTaTE;
+            const bool ok = e0 + e < E;
+            const int eg = ok ? e0 + e : E - 1;
+            const int src = a.edge_src[eg], dst = a.edge_dst[eg];
+            float sh[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) sh[i] = ok ? a.sh[(size_t)eg * 9 + i] : 0.f;
+            const float* xs = a.x_src + (size_t)src * D::F;
+            const float* xd = a.x_dst ? a.x_dst + (size_t)dst * D::F : nullptr;
+            const float* wr = a.w + (size_t)eg * a.w_stride;
+            const float okf = ok ? 1.f : 0.f;
+            if (warp < 4) {
+                const int i = warp;
+                float2 xab, w0, w1, w2; float x1[3], w6[6];
+                auto load = [&](int j) {
+                    const int ch = 8 * j + 2 * i, p = 4 * j + i;
+                    xab = *reinterpret_cast<const float2*>(xs + ch);
+                    if (xd) { const float2 t = *reinterpret_cast<const float2*>(xd + ch); xab.x += t.x; xab.y += t.y; }
+                    w0 = *reinterpret_cast<const float2*>(wr + D::W_K0 + ch);
+                    w1 = *reinterpret_cast<const float2*>(wr + D::W_K1 + ch);
+                    w2 = *reinterpret_cast<const float2*>(wr + D::W_K2 + ch);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) x1[k] = xs[D::M0 + 3 * p + k];
+                    if (xd) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) x1[k] += xd[D::M0 + 3 * p + k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) w6[k] = wr[D::W_K3 + p + k * D::M1];
+                };
+                load(0);
+#pragma unroll 1
+                for (int j = 0; j < NCH; ++j) {
+                    float oa[9], ob[9], o[20];
+                    dtp_l0(xab.x * okf, w0.x, w1.x, w2.x, sh, oa);
+                    dtp_l0(xab.y * okf, w0.y, w1.y, w2.y, sh, ob);
+                    { float xz[3] = {x1[0] * okf, x1[1] * okf, x1[2] * okf}; dtp_l1(xz, w6, sh, o); }
+                    if (j + 1 < NCH) load(j + 1);                          // next chunk's gathers fly during the stores
+                    tc::mbar_wait_bounded(&emptyA[st], ph ^ 1u);
+                    unsigned char* hi = sA + st * kAStage;
+                    unsigned char* lo = hi + kAPart;
+                    auto put4 = [&](int off, float v0, float v1, float v2, float v3) {
+                        const float4 h = make_float4(tc::tf32_hi(v0), tc::tf32_hi(v1), tc::tf32_hi(v2), tc::tf32_hi(v3));
+                        *reinterpret_cast<float4*>(hi + off) = h;
+                        *reinterpret_cast<float4*>(lo + off) = make_float4(v0 - h.x, v1 - h.y, v2 - h.z, v3 - h.w);
+                    };
+                    auto put1 = [&](int off, float v) {
+                        const float h = tc::tf32_hi(v);
+                        *reinterpret_cast<float*>(hi + off) = h;
+                        *reinterpret_cast<float*>(lo + off) = v - h;
+                    };
+                    // l_out = 0, group i: [k0 a, k0 b, k4 p, (k12: the l=2 warps)]
+                    {
+                        const int off = kA0Off + (i * kR0 + e) * 16;
+                        put1(off, oa[0]); put1(off + 4, ob[0]); put1(off + 8, o[3]);
+                    }
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) {      // l_out = 1, group i: [k3, k5, k7, k1 a]; group 4 column i: k1 b
+                        put4(kA1Off + (i * kR1 + m * kTaTE + e) * 16, o[m], o[4 + m], o[12 + m], oa[1 + m]);
+                        put1(kA1Off + (4 * kR1 + m * kTaTE + e) * 16 + i * 4, ob[1 + m]);
+                    }
+#pragma unroll
+                    for (int m = 0; m < 5; ++m)        // l_out = 2, group i: [k2 a, k2 b, k6, k8]
+                        put4(kA2Off + (i * kR2 + m * kTaTE + e) * 16, oa[4 + m], ob[4 + m], o[7 + m], o[15 + m]);
+                    tc::fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&fullA[st]);
+                    if (++st == kTaStages) { st = 0; ph ^= 1u; }
+                }
+            } else {
+                const int t = warp - 4;
+                float x2[5], w6[6];
+                auto load = [&](int j) {
+                    const int q = 2 * j + t;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) x2[k] = xs[D::M0 + 3 * D::M1 + 5 * q + k];
+                    if (xd) {
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) x2[k] += xd[D::M0 + 3 * D::M1 + 5 * q + k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) w6[k] = wr[D::W_K9 + q + k * D::M2];
+                };
+                load(0);
+#pragma unroll 1
+                for (int j = 0; j < NCH; ++j) {
+                    float o[22];
+                    { float xz[5] = {x2[0] * okf, x2[1] * okf, x2[2] * okf, x2[3] * okf, x2[4] * okf}; dtp_l2(xz, w6, sh, o); }
+                    if (j + 1 < NCH) load(j + 1);
+                    tc::mbar_wait_bounded(&emptyA[st], ph ^ 1u);
+                    unsigned char* hi = sA + st * kAStage;
+                    unsigned char* lo = hi + kAPart;
+                    auto put4 = [&](int off, float v0, float v1, float v2, float v3) {
+                        const float4 h = make_float4(tc::tf32_hi(v0), tc::tf32_hi(v1), tc::tf32_hi(v2), tc::tf32_hi(v3));
+                        *reinterpret_cast<float4*>(hi + off) = h;
+                        *reinterpret_cast<float4*>(lo + off) = make_float4(v0 - h.x, v1 - h.y, v2 - h.z, v3 - h.w);
+                    };
+                    auto put2 = [&](int off, float v0, float v1) {
+                        const float2 h = make_float2(tc::tf32_hi(v0), tc::tf32_hi(v1));
+                        *reinterpret_cast<float2*>(hi + off) = h;
+                        *reinterpret_cast<float2*>(lo + off) = make_float2(v0 - h.x, v1 - h.y);
+                    };
+                    {   // l_out = 0, group t, column 3: k12
+                        const int off = kA0Off + (t * kR0 + e) * 16 + 12;
+                        const float h = tc::tf32_hi(o[13]);
+                        *reinterpret_cast<float*>(hi + off) = h;
+                        *reinterpret_cast<float*>(lo + off) = o[13] - h;
+                    }
+#pragma unroll
+                    for (int m = 0; m < 3; ++m)        // l_out = 1, group 5, columns 2t, 2t+1: [k10, k13]
+                        put2(kA1Off + (5 * kR1 + m * kTaTE + e) * 16 + t * 8, o[5 + m], o[14 + m]);
+#pragma unroll
+                    for (int m = 0; m < 5; ++m)        // l_out = 2, group 4 + t: [k9, k11, k14, 0]
+                        put4(kA2Off + ((4 + t) * kR2 + m * kTaTE + e) * 16, o[m], o[8 + m], o[17 + m], 0.f);
+                    tc::fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&fullA[st]);
+                    if (++st == kTaStages) { st = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == kTaTmaWarp) {
+        // =========================== weight ring ===========================
+        if (lane == 0) {
+            uint32_t st = 0, ph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int j = 0; j < NCH; ++j) {
+                    tc::mbar_wait_bounded(&emptyW[st], ph ^ 1u);
+                    mbar_expect_tx(&fullW[st], (uint32_t)C::WStage);
+                    bulk_g2s_chunked(sW + st * C::WStage, reinterpret_cast<const unsigned char*>(a.Wp) + (size_t)j * C::WStage,
+                                     (uint32_t)C::WStage, &fullW[st]);
+                    if (++st == kTaStages) { st = 0; ph ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == kTaMmaWarp) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            uint32_t st = 0, ph = 0;
+            const uint32_t a_base = smem_u32(sA), w_base = smem_u32(sW);
+            const uint32_t id0 = tc::idesc_tf32(128, kTaTE), id1 = tc::idesc_tf32(128, C::N1P), id2 = tc::idesc_tf32(128, C::N2P);
+            int it = 0;
+            long long wA = 0, wW = 0, wE = 0, tIssue = 0;
+            const long long tStart = clock64();
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t buf = (uint32_t)it & 1u;
+                { const long long c = clock64();
+                tc::mbar_wait_bounded(&accEmpty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);     // epilogue drained this buffer
+                wE += clock64() - c; }
+                tc::fence_after();
+                const uint32_t d0 = tmem_base + buf * (uint32_t)kTaAccCols;
+                for (int j = 0; j < NCH; ++j) {
+                    { const long long c = clock64();
+                    tc::mbar_wait_bounded(&fullA[st], ph);
+                    const long long c2 = clock64();
+                    tc::mbar_wait_bounded(&fullW[st], ph);
+                    const long long c3 = clock64(); wA += c2 - c; wW += c3 - c2; }
+                    tc::fence_after();
+                    const long long ci = clock64();
+                    const uint32_t ah = a_base + st * kAStage, al = ah + kAPart;
+                    const uint32_t wh = w_base + st * C::WStage, wl = wh + C::WPart;
+                    auto gemm = [&](uint32_t a_off, uint32_t lbo_a, uint32_t w_off, uint32_t lbo_w, int ksteps, uint32_t idesc, uint32_t d) {
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t dah = tc::smem_desc(ah + a_off + ks * 2 * lbo_a, lbo_a, 128);
+                            const uint64_t dal = tc::smem_desc(al + a_off + ks * 2 * lbo_a, lbo_a, 128);
+                            const uint64_t dwh = tc::smem_desc(wh + w_off + ks * 2 * lbo_w, lbo_w, 128);
+                            const uint64_t dwl = tc::smem_desc(wl + w_off + ks * 2 * lbo_w, lbo_w, 128);
+                            tc::mma_tf32(d, dah, dwh, idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                            tc::mma_tf32(d, dal, dwh, idesc, 1u);
+                            tc::mma_tf32(d, dah, dwl, idesc, 1u);
+                        }
+                    };
+                    // l_out = 0 with the operands swapped: D0^T[n][e] = W0^T[n][k] . A0[e][k]  (M = output channels, N = 32 edges)
+                    for (int mt = 0; mt < C::MT0; ++mt) {
+                        for (int ks = 0; ks < kKC0 / 8; ++ks) {
+                            const uint32_t wo = C::W0Off + ks * 2 * (C::N0P * 16) + mt * 128 * 16, ao = kA0Off + ks * 2 * (kR0 * 16);
+                            const uint64_t dwh = tc::smem_desc(wh + wo, C::N0P * 16, 128), dwl = tc::smem_desc(wl + wo, C::N0P * 16, 128);
+                            const uint64_t dah = tc::smem_desc(ah + ao, kR0 * 16, 128), dal = tc::smem_desc(al + ao, kR0 * 16, 128);
+                            const uint32_t d = d0 + C::T0 + mt * kTaTE;
+                            tc::mma_tf32(d, dwh, dah, id0, (j > 0 || ks > 0) ? 1u : 0u);
+                            tc::mma_tf32(d, dwh, dal, id0, 1u);
+                            tc::mma_tf32(d, dwl, dah, id0, 1u);
+                        }
+                    }
+                    gemm(kA1Off, kR1 * 16, C::W1Off, C::N1P * 16, kKC1 / 8, id1, d0 + C::T1);
+                    gemm(kA2Off, kR2 * 16, C::W2Off, C::N2P * 16, kKC2 / 8, id2, d0 + C::T2A);            // rows (m, e), m = 0..3
+                    gemm(kA2Off + 32 * 16, kR2 * 16, C::W2Off, C::N2P * 16, kKC2 / 8, id2, d0 + C::T2B);   // m = 4 lands in lanes 96..127
+                    tc::commit(&emptyA[st]);
+                    tc::commit(&emptyW[st]);
+                    tIssue += clock64() - ci;
+                    if (++st == kTaStages) { st = 0; ph ^= 1u; }
+                }
+                tc::commit(&accFull[buf]);
+            }
+            if (a.dbg && blockIdx.x == 0) {      // host debug: where the MMA issuer of CTA 0 spent its cycles
+                a.dbg[0] = clock64() - tStart; a.dbg[1] = wA; a.dbg[2] = wW; a.dbg[3] = wE; a.dbg[4] = tIssue; a.dbg[5] = it;
+            }
+        }
+        __syncwarp();
+    } else {
+        // =========================== epilogue ===========================
+        const int q = warp & 3;                            // TMEM lane quarter
+        const int wg = (warp - kTaEpiWarp0) >> 2;          // warpgroup: edges [16 wg, 16 wg + 16) of the l_out = 0 tile, half of the 1e columns
+        auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kTaEpiWarps * 32) : "memory"); };
+        constexpr int HD = C::MA / 4;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = (uint32_t)it & 1u;
+            const int e0 = tile * kTaTE;
+            tc::mbar_wait_bounded(&accFull[buf], ((uint32_t)it >> 1) & 1u);
+            tc::fence_after();
+            const uint32_t tq = tmem_base + buf * (uint32_t)kTaAccCols + ((uint32_t)(q * 32) << 16);
+            // ---- phase 1: the 0e GEMM (lane = output channel n, column = edge): logit terms | scalars | gates ----
+#pragma unroll
+            for (int mt = 0; mt < C::MT0; ++mt) {
+                const int n = mt * 128 + q * 32 + lane;
+                if (mt * 128 + q * 32 < C::N0) {           // warp-uniform
+                    float t[16];
+                    tc::tmem_ld16(tq + C::T0 + mt * kTaTE + 16 * wg, t);
+                    if (n < C::N0) {
+                        const float b = s_b0[n];
+                        if (n < C::MA) {                   // graph_attention.py:241-246
+                            const float ad = kCSlrelu * s_adot[n];
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) s_red[n * 33 + 16 * wg + k] = slreluf_(t[k] + b) * ad;
+                        } else if (n < C::MA + D::M0) {    // fast_activation.py:210-224: scalars | gates | gated
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) s_out[(16 * wg + k) * C::LDO + (n - C::MA)] = kCSilu * siluf_(t[k] + b);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) s_gate[(16 * wg + k) * C::NGP + (n - C::MA - D::M0)] = kCSigmoid * sigmoidf_(t[k] + b);
+                        }
+                    }
+                }
+            }
+            epi_sync();
+            // ---- phase 2: logits (thread = (edge, head, half of the head's channels)) ----
+            {
+                const int e = 16 * wg + (lane & 15), kh = lane >> 4, h = q;
+                float sum = 0.f;
+#pragma unroll
+                for (int k = 0; k < HD / 2; ++k) sum += s_red[(h * HD + kh * (HD / 2) + k) * 33 + e];
+                sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+                if (kh == 0 && e0 + e < E) a.logits[(size_t)(e0 + e) * 4 + h] = sum + (a.edge_logit ? a.edge_logit[e0 + e] : 0.f);
+            }
+            // ---- 1e / 2e GEMMs (lane = edge, quarter = component m, column = channel): x gate ----
+            {
+                const int e = lane;
+                float* orow = s_out + e * C::LDO;
+                const float* grow = s_gate + e * C::NGP;
+                if (q < 3) {
+                    constexpr int W1 = (D::M1 >= 32) ? 16 : D::M1;          // columns per warpgroup (16 | all 16 in warpgroup 0)
+                    if (wg * W1 < D::M1) {
+                        float t[16];
+                        tc::tmem_ld16(tq + C::T1 + wg * W1, t);
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            if (k < W1) orow[D::M0 + 3 * (wg * W1 + k) + q] = t[k] * grow[wg * W1 + k];
+                    }
+                }
+                if (wg == 0) {
+                    float t[16];
+                    tc::tmem_ld16(tq + C::T2A, t);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (k < D::M2) orow[D::M0 + 3 * D::M1 + 5 * k + q] = t[k] * grow[D::M1 + k];
+                } else if (q == 3) {
+                    float t[16];
+                    tc::tmem_ld16(tq + C::T2B, t);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (k < D::M2) orow[D::M0 + 3 * D::M1 + 5 * k + 4] = t[k] * grow[D::M1 + k];
+                }
+            }
+            tc::fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&accEmpty[buf]);
+            tc::fence_async_smem();
+            epi_sync();                                    // the 32 value rows are staged
+            if (warp == kTaEpiWarp0) {
+                if (e0 + lane < E)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(a.out + (size_t)(e0 + lane) * D::F), "r"(smem_u32(s_out + lane * C::LDO)), "r"((uint32_t)D::F * 4u) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            epi_sync();                                    // staging tile, gate and logit tables reusable
+        }
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == kTaTmaWarp) tc::tmem_dealloc(tmem_base, 2 * kTaAccCols);
+}
+
+template <int G>
+static int launch_tp_act_tc(const TpActArgs& a, int max_edges, cudaStream_t stream) {
+    using C = TaCfg<G>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(edge_tp_act_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::Smem);
+        attr_done = true;
+    }
+    const int n_tiles = (max_edges + kTaTE - 1) / kTaTE;
+    launch_pdl((edge_tp_act_tc_kernel<G>), dim3(grid_for(n_tiles, 1, kNumSMs)), dim3(kTaThreads), (size_t)C::Smem, stream, a);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+}  // namespace dedf
+
+using namespace dedf;
+
+static long long* g_ta_dbg = nullptr;
+/* debug hook (not in the public header): 8 x int64 device buffer receiving the MMA issuer's cycle accounting of CTA 0 */
+extern "C" int dedf_tp_act_tc_set_debug(long long* dbg) { g_ta_dbg = dbg; return DEDF_OK; }
+
+extern "C" int dedf_edge_tp_act_tc(int mul1, const float* x_src, const float* x_dst, const int* edge_src, const int* edge_dst,
+                                   const int* n_edges_dev, int max_edges, const float* sh, const float* w, long long w_stride,
+                                   const float* W_tc, const float* bias0, const float* alpha_dot, const float* edge_logit,
+                                   float* logits, float* out, cudaStream_t stream) {
+    if (max_edges <= 0) return DEDF_OK;
+    if (!x_src || !edge_src || !edge_dst || !n_edges_dev || !sh || !w || !W_tc || !alpha_dot || !logits || !out) return DEDF_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(W_tc) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(logits) & 15) ||
+        (reinterpret_cast<uintptr_t>(w) & 7) || (reinterpret_cast<uintptr_t>(x_src) & 7) || (x_dst && (reinterpret_cast<uintptr_t>(x_dst) & 7)) ||
+        (w_stride & 1))
+        return DEDF_ERR_ARG;
+    TpActArgs a{};
+    a.x_src = x_src; a.x_dst = x_dst; a.edge_src = edge_src; a.edge_dst = edge_dst; a.n_edges = n_edges_dev; a.sh = sh;
+    a.w = w; a.w_stride = w_stride; a.Wp = W_tc; a.bias0 = bias0; a.alpha_dot = alpha_dot; a.edge_logit = edge_logit;
+    a.logits = logits; a.out = out; a.dbg = g_ta_dbg;
+    if (mul1 == 32) return launch_tp_act_tc<32>(a, max_edges, stream);
+    if (mul1 == 16) return launch_tp_act_tc<16>(a, max_edges, stream);
+    return DEDF_ERR_UNSUPPORTED;
+}

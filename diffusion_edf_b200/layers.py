@@ -60,6 +60,54 @@ def pack_tc(W: torch.Tensor) -> torch.Tensor:
     return v.permute(4, 1, 0, 2, 5, 3).contiguous().view(-1)         # [nb, kc, part, j, n, r]
 
 
+def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor) -> torch.Tensor:
+    """Block-diagonal weights of the attention block's per-edge linear layer -> the B-operand stream of dedf_edge_tp_act_tc.
+
+    W0 (D0, N0) = [sep_alpha | sep_act.lin 0e], W1 (D1, m1), W2 (D2, m2), rows in the depthwise tensor product's i_out order
+    (SURVEY App. E).  The kernel consumes K in chunks of input channels: chunk j = 0e channels 8j..8j+7, 1e channels
+    4j..4j+3, 2e channels 2j..2j+1; producer warp i (0..3) owns 0e channels a = 8j+2i, b = a+1 and 1e channel p = 4j+i,
+    producer warp 4+t owns 2e channel q = 2j+t.  Per chunk and GEMM the K columns are grouped in fours (one float4 store of
+    one producer thread), pads are zero rows:
+        l_out=0 (16): group i = [k0 a, k0 b, k4 p, k12 q_i if i < 2 else 0]
+        l_out=1 (24): group i = [k3 p, k5 p, k7 p, k1 a];  group 4 = [k1 b_0..b_3];  group 5 = [k10 q0, k13 q0, k10 q1, k13 q1]
+        l_out=2 (24): group i = [k2 a, k2 b, k6 p, k8 p];  group 4+t = [k9 q_t, k11 q_t, k14 q_t, 0]
+    Each block is stored chunk-major [K/4][N padded to 16][4], the chunk as [l0 | l1 | l2] hi then [l0 | l1 | l2] lo."""
+    M0, M1, M2 = 2 * G, G, G // 2
+    C0 = dict(k0=0, k4=M0, k12=M0 + M1)
+    C1 = dict(k1=0, k3=M0, k5=M0 + M1, k7=M0 + 2 * M1, k10=M0 + 3 * M1, k13=M0 + 3 * M1 + M2)
+    C2 = dict(k2=0, k6=M0, k8=M0 + M1, k9=M0 + 2 * M1, k11=M0 + 2 * M1 + M2, k14=M0 + 2 * M1 + 2 * M2)
+    W0, W1, W2 = (w.detach().float().contiguous() for w in (W0, W1, W2))
+    assert W0.shape[0] == M0 + M1 + M2 and W1.shape == (M0 + 3 * M1 + 2 * M2, M1) and W2.shape == (M0 + 2 * M1 + 3 * M2, M2)
+
+    def block(W, rows):
+        K, N = len(rows), W.shape[1]
+        Np = (N + 15) // 16 * 16
+        sel = torch.zeros(K, Np, dtype=torch.float32, device=W.device)
+        for k, r in enumerate(rows):
+            if r is not None:
+                sel[k, :N] = W[r]
+        return sel.view(K // 4, 4, Np).permute(0, 2, 1).contiguous().view(-1)      # [K/4][Np][4]
+
+    chunks = []
+    for j in range(M0 // 8):
+        a = [8 * j + 2 * i for i in range(4)]
+        p = [4 * j + i for i in range(4)]
+        q = [2 * j, 2 * j + 1]
+        r0, r1, r2 = [], [], []
+        for i in range(4):
+            r0 += [C0["k0"] + a[i], C0["k0"] + a[i] + 1, C0["k4"] + p[i], C0["k12"] + q[i] if i < 2 else None]
+            r1 += [C1["k3"] + p[i], C1["k5"] + p[i], C1["k7"] + p[i], C1["k1"] + a[i]]
+            r2 += [C2["k2"] + a[i], C2["k2"] + a[i] + 1, C2["k6"] + p[i], C2["k8"] + p[i]]
+        r1 += [C1["k1"] + a[i] + 1 for i in range(4)]
+        r1 += [C1["k10"] + q[0], C1["k13"] + q[0], C1["k10"] + q[1], C1["k13"] + q[1]]
+        for t in range(2):
+            r2 += [C2["k9"] + q[t], C2["k11"] + q[t], C2["k14"] + q[t], None]
+        full = torch.cat([block(W0, r0), block(W1, r1), block(W2, r2)])
+        hi = (full.view(torch.int32) & -8192).view(torch.float32)
+        chunks += [hi, full - hi]
+    return torch.cat(chunks).contiguous()
+
+
 def tc_mlp_ok(dims: Sequence[int]) -> bool:
     """Can dedf_edge_mlp_tc run an MLP with these layer widths?"""
     n = len(dims) - 1
@@ -312,7 +360,10 @@ class GraphAttention(nn.Module):
             W0 = torch.cat([a0.view(d0, ma), l0.view(d0, n_lin0)], dim=1).contiguous()
             b0 = torch.cat([ab, lb]).contiguous()
             (v0, v1, v2), vb = self.sep_value.lin.packed()
-            return dict(W0=W0, W1=l1, W2=l2, b0=b0, alpha_dot=self.alpha_dot.detach().reshape(-1).contiguous(),
+            G = self.irreps_emb.m[1]
+            d1, d2 = dtp_out(self.irreps_emb).m[1], dtp_out(self.irreps_emb).m[2]
+            Wtc = pack_tp_act_tc(G, W0, l1.view(d1, -1), l2.view(d2, -1)) if G in (16, 32) else None
+            return dict(W0=W0, W1=l1, W2=l2, Wtc=Wtc, b0=b0, alpha_dot=self.alpha_dot.detach().reshape(-1).contiguous(),
                         wv=self.sep_value.dtp.tp.weight.detach().contiguous(), V0=v0, V1=v1, V2=v2, vb=vb)
         return self._packed.get(self, build)
 
@@ -327,8 +378,11 @@ class GraphAttention(nn.Module):
         dev = msg_src.device
         logits = torch.empty(E, 4, dtype=torch.float32, device=dev)
         v = torch.empty(E, F, dtype=torch.float32, device=dev)
-        ops.edge_tp_lin(G, L.EPI_ACT, msg_src, msg_dst, False, g, sh, w, self.sep_act.numel, p["W0"], p["W1"], p["W2"], p["b0"],
-                        alpha_dot=p["alpha_dot"], edge_logit=edge_logit, logits=logits, out=v)
+        if ops.USE_TC_TPACT and p["Wtc"] is not None:
+            ops.edge_tp_act_tc(G, msg_src, msg_dst, g, sh, w, self.sep_act.numel, p["Wtc"], p["b0"], p["alpha_dot"], edge_logit, logits, v)
+        else:
+            ops.edge_tp_lin(G, L.EPI_ACT, msg_src, msg_dst, False, g, sh, w, self.sep_act.numel, p["W0"], p["W1"], p["W2"], p["b0"],
+                            alpha_dot=p["alpha_dot"], edge_logit=edge_logit, logits=logits, out=v)
         if ops.USE_VALUE_REDUCE:
             # reassociated value path: reduce the tensor-product outputs over the incoming edges, THEN the linear layer
             post = ops.edge_gather_scalar(src_weight, g) if src_weight is not None else None

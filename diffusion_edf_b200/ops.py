@@ -287,6 +287,7 @@ def edge_geom(x_src: torch.Tensor, x_dst: torch.Tensor, g: Csr, radii: Optional[
 
 
 USE_VALUE_REDUCE = True     # value path reassociated: linear once per destination (dedf_value_reduce) instead of once per edge
+USE_TC_TPACT = True     # attention logits + gated values: block-diagonal linear on the tensor cores (dedf_edge_tp_act_tc)
 USE_TC_MLP = True       # per-edge MLPs on the tcgen05 tensor cores (3xTF32) where the layer widths allow it
 
 
@@ -305,6 +306,14 @@ def edge_tp_lin(mul1: int, epilogue: int, x_src: torch.Tensor, x_dst: Optional[t
                                     ptr(g.edge_src, torch.int32), ptr(g.edge_dst, torch.int32),
                                     ptr(g.n_edges_dev, torch.int32), g.n_edges, ptr(sh), ptr(w), w_stride, ptr(W0), ptr(W1),
                                     ptr(W2), ptr(bias0), ptr(alpha_dot), ptr(edge_logit), ptr(logits), ptr(out), stream())
+
+
+def edge_tp_act_tc(mul1: int, x_src: torch.Tensor, x_dst: Optional[torch.Tensor], g: Csr, sh: torch.Tensor, w: torch.Tensor,
+                   w_stride: int, W_tc: torch.Tensor, bias0, alpha_dot, edge_logit, logits: torch.Tensor, out: torch.Tensor) -> None:
+    """dedf_edge_tp_lin(EPI_ACT) with the linear layer on the tcgen05 tensor cores."""
+    _call("dedf_edge_tp_act_tc", mul1, ptr(x_src), ptr(x_dst), ptr(g.edge_src, torch.int32), ptr(g.edge_dst, torch.int32),
+          ptr(g.n_edges_dev, torch.int32), g.n_edges, ptr(sh), ptr(w), w_stride, ptr(W_tc), ptr(bias0), ptr(alpha_dot),
+          ptr(edge_logit), ptr(logits), ptr(out), stream())
 
 
 def segment_softmax_reduce(g: Csr, logits: torch.Tensor, val: torch.Tensor, irr: Tuple[int, int, int]) -> torch.Tensor:

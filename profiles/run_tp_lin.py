@@ -43,7 +43,11 @@ def lin():
     ops.edge_tp_lin(G, L.EPI_LIN, v, None, True, g, sh, p["wv"], 0, p["V0"], p["V1"], p["V2"], p["vb"], out=val)
 
 
-for name, fn in (("ACT", act), ("LIN", lin)):
+def act_tc():
+    ops.edge_tp_act_tc(G, msg, None, g, sh, w, ga.sep_act.numel, p["Wtc"], p["b0"], p["alpha_dot"], None, logits, v)
+
+
+for name, fn in (("ACT", act), ("ACT_TC", act_tc), ("LIN", lin)):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -59,5 +63,10 @@ for name, fn in (("ACT", act), ("LIN", lin)):
     torch.cuda.synchronize()
     lib.dedf_tp_lin_set_debug(None)
     d = [z for z in dbg.cpu().tolist() if z]
+    if name == "ACT_TC":
+        lib.dedf_tp_act_tc_set_debug.argtypes = [ctypes.c_void_p]
+        d2 = torch.zeros(8, dtype=torch.int64, device=dev)
+        lib.dedf_tp_act_tc_set_debug(d2.data_ptr()); fn(); torch.cuda.synchronize(); lib.dedf_tp_act_tc_set_debug(None)
+        print("    MMA issuer CTA0 [total, wait A, wait W, wait acc, issue, tiles]:", d2.cpu().tolist()[:6])
     print(f"{name} G={G} E={E}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us;  CTA0 stamps (cycles, per tile: start, staged, CG done, GEMM done, O written):")
     print("   ", [z - d[0] for z in d][:31])

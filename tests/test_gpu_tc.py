@@ -120,3 +120,70 @@ def test_tensor_field_tc_vs_fp32(cuda, shared_time):
                 ops.USE_TC_MLP = True
     for a, b in zip(res[0], res[1]):
         assert rel_err(a, b) <= 2e-5
+
+
+# --------------------------------------------------------------------------- attention logits + gated values (dedf_edge_tp_act_tc)
+@pytest.mark.parametrize("G,E,use_dst,use_logit", [(32, 1, True, True), (32, 333, True, True), (32, 64, False, False),
+                                                   (16, 777, True, False), (16, 31, False, True), (32, 21_001, True, True),
+                                                   (16, 30_000, True, True)])
+def test_edge_tp_act_tc(cuda, G, E, use_dst, use_logit):
+    """gather -> depthwise TP -> [sep_alpha | sep_act.lin] -> SmoothLeakyReLU.alpha_dot / Gate (graph_attention.py:231-246)
+    with the linear layer on the tensor cores, against the oracle arithmetic (small cases) and the fp32 CUDA-core kernel
+    (every case): one edge, ragged last tile, several tiles per CTA (both TMEM accumulator buffers and ring wrap-around)."""
+    from diffusion_edf_b200 import _lib as L, layers, ops
+    from oracle import model as OM
+    from oracle import nn as ON
+    from oracle import so3
+    from oracle.irreps import Irreps as OIrreps
+    IRR = {32: "64x0e+32x1e+16x2e", 16: "32x0e+16x1e+8x2e"}
+    gen = torch.Generator().manual_seed(G * 7 + E)
+    torch.manual_seed(G * 7 + E)
+    irr = OIrreps(IRR[G])
+    F, numel = irr.dim, 15 * G
+    n_src, n_dst = 97, 41
+    es = torch.randint(0, n_src, (E,), generator=gen)
+    ed = torch.randint(0, n_dst, (E,), generator=gen).sort().values
+    sh = so3.spherical_harmonics(2, torch.randn(E, 3, generator=gen))
+    msg_src = torch.randn(n_src, F, generator=gen)
+    msg_dst = torch.randn(n_dst, F, generator=gen) if use_dst else None
+    w = torch.randn(E, numel, generator=gen) / 3.0 ** 0.5
+    edge_logit = -torch.rand(E, generator=gen) * 3 if use_logit else None
+    oga = OM.GraphAttentionMLP2(irr, OIrreps("1x0e+1x1e+1x2e"), irr, [32, 16, 16], 4)
+    with torch.no_grad():
+        for prm in oga.parameters():
+            if prm.abs().sum() == 0:
+                prm.uniform_(-0.5, 0.5)
+    pga = layers.GraphAttention(IRR[G], IRR[G], [32, 16, 16], 4)
+    pga.load_state_dict(oga.state_dict())
+    pga = pga.to(cuda)
+    p = pga.packed()
+    row_ptr = torch.zeros(n_dst + 1, dtype=torch.long)
+    row_ptr[1:] = torch.bincount(ed, minlength=n_dst).cumsum(0)
+    rp = row_ptr.int().to(cuda)
+    csr = ops.Csr(rp, es.int().to(cuda), ed.int().to(cuda), rp[-1:], E, n_dst, 1)
+    dv = lambda t: None if t is None else t.to(cuda)
+    logits = torch.full((E, 4), float("nan"), device=cuda)
+    v = torch.full((E, F), float("nan"), device=cuda)
+    ops.edge_tp_act_tc(G, dv(msg_src), dv(msg_dst), csr, dv(sh), dv(w), numel, p["Wtc"], p["b0"], p["alpha_dot"], dv(edge_logit), logits, v)
+    logits2 = torch.empty(E, 4, device=cuda)
+    v2 = torch.empty(E, F, device=cuda)
+    ops.edge_tp_lin(G, L.EPI_ACT, dv(msg_src), dv(msg_dst), False, csr, dv(sh), dv(w), numel, p["W0"], p["W1"], p["W2"], p["b0"],
+                    alpha_dot=p["alpha_dot"], edge_logit=dv(edge_logit), logits=logits2, out=v2)
+    assert torch.isfinite(logits).all() and torch.isfinite(v).all()
+    assert rel_err(logits, logits2) < 2e-5, f"logits vs fp32 kernel: {rel_err(logits, logits2):.3e}"
+    assert rel_err(v, v2) < 2e-5, f"values vs fp32 kernel: {rel_err(v, v2):.3e}"
+    if E <= 1000:
+        with torch.no_grad():
+            message = msg_src[es] + (msg_dst[ed] if use_dst else 0)
+            d1 = oga.sep_act.dtp(message, sh, w)
+            la = oga.sep_alpha(d1).reshape(E, 4, -1)
+            v_ref = oga.sep_act.gate(oga.sep_act.lin(d1))
+            la = oga.c_slrelu * ON.smooth_leaky_relu(la)
+            logit_ref = torch.einsum("ehk,hk->eh", la, oga.alpha_dot.squeeze(0)) + (edge_logit[:, None] if use_logit else 0)
+        assert rel_err(logits, logit_ref) < 1e-4, f"logits vs oracle: {rel_err(logits, logit_ref):.3e}"
+        assert rel_err(v, v_ref) < 1e-4, f"values vs oracle: {rel_err(v, v_ref):.3e}"
+    # same launch twice: bit-identical
+    logits3 = torch.empty(E, 4, device=cuda)
+    v3 = torch.empty(E, F, device=cuda)
+    ops.edge_tp_act_tc(G, dv(msg_src), dv(msg_dst), csr, dv(sh), dv(w), numel, p["Wtc"], p["b0"], p["alpha_dot"], dv(edge_logit), logits3, v3)
+    assert torch.equal(logits, logits3) and torch.equal(v, v3)
