@@ -34,7 +34,8 @@ constexpr int kTaProdWarps = 6;
 constexpr int kTaTmaWarp = 6, kTaMmaWarp = 7, kTaEpiWarp0 = 8;
 constexpr int kTaEpiWarps = 8;                      // two warpgroups: each takes half of the tile's edges / output columns
 constexpr int kTaThreads = (kTaEpiWarp0 + kTaEpiWarps) * 32;
-constexpr int kTaAccCols = 128;                     // TMEM columns of one accumulator buffer
+constexpr int kTaAccCols = 128;
+constexpr int kTaXLd = 36;                          // staged message slice: 8 (0e) + 12 (1e) + 12 (2e, 10 used) floats + 4 pad                     // TMEM columns of one accumulator buffer
 constexpr int kTaStages = 2;                        // A chunk stages and weight ring stages
 constexpr int kKC0 = 16, kKC1 = 24, kKC2 = 24;      // K columns per chunk of the three GEMMs
 constexpr int kR0 = kTaTE, kR1 = 3 * kTaTE, kR2 = 5 * kTaTE;   // stored rows
@@ -70,14 +71,15 @@ struct TaCfg {
     static constexpr int OffGate = OffOut + kTaTE * LDO * 4;
     static constexpr int NGP = NG + 1;                                     // gate table row stride (odd: conflict-free both ways)
     static constexpr int OffRed = OffGate + kTaTE * NGP * 4;               // [MA][33] attention-logit terms
-    static constexpr int OffPar = OffRed + MA * 33 * 4;
+    static constexpr int OffX = OffRed + MA * 33 * 4;                      // [2][32][kTaXLd] staged message slices
+    static constexpr int OffPar = OffX + 2 * kTaTE * kTaXLd * 4;
     static constexpr int Smem = OffPar + (N0P + MA) * 4;
 };
 
 struct TpActArgs {
     const float* x_src; const float* x_dst;
     const int* edge_src; const int* edge_dst; const int* n_edges;
-    const float* sh; const float* w; long long w_stride;
+    const float* sh; const float* w; long long w_stride; int w_perm;
     const float* Wp;          // packed weight chunks (layers.pack_tp_act_tc)
     const float* bias0; const float* alpha_dot; const float* edge_logit;
     float* logits; float* out;
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
     float* s_out = reinterpret_cast<float*>(smem + C::OffOut);
     float* s_gate = reinterpret_cast<float*>(smem + C::OffGate);      // [32][NGP]
     float* s_red = reinterpret_cast<float*>(smem + C::OffRed);        // [MA][33]
+    float* s_x = reinterpret_cast<float*>(smem + C::OffX);
     float* s_b0 = reinterpret_cast<float*>(smem + C::OffPar);         // [N0P] bias
     float* s_adot = s_b0 + C::N0P;                                    // [MA]
     __shared__ __align__(8) uint64_t fullA[kTaStages], emptyA[kTaStages], fullW[kTaStages], emptyW[kTaStages], accFull[2], accEmpty[2];
@@ -126,8 +129,18 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
 
     if (warp < kTaProdWarps) {
         // =========================== producers: CG chunk -> hi / lo A operand ===========================
+        // Every load below has lane = edge, i.e. 32 different rows per instruction: what bounds the producers is the
+        // NUMBER of gather instructions.  The chunk's slice of the message row (x_src[src] + x_dst[dst]: 8 + 12 + 10
+        // floats) is therefore fetched as 8 float4 slices spread over the 6 warps, staged in shared memory (two stages,
+        // one named barrier per chunk) and read back by the warp that needs it; the per-edge radial weights come as
+        // 3 float4 / 3 float2 per lane when the caller permuted their columns chunk-major (w_perm).
         const int e = lane;
         uint32_t st = 0, ph = 0;
+        auto prod_sync = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(kTaProdWarps * 32) : "memory"); };
+        const int sliceA = warp, sliceB = (warp < 2) ? 6 + warp : -1;
+        auto slice_off = [&](int j, int sl) {
+            return (sl < 2) ? 8 * j + 4 * sl : (sl < 5) ? D::M0 + 12 * j + 4 * (sl - 2) : D::M0 + 3 * D::M1 + 10 * j - 2 * (j & 1) + 4 * (sl - 5);
+        };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int e0 = tile * kTaTE;
             const bool ok = e0 + e < E;
@@ -140,33 +153,53 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
             const float* xd = a.x_dst ? a.x_dst + (size_t)dst * D::F : nullptr;
             const float* wr = a.w + (size_t)eg * a.w_stride;
             const float okf = ok ? 1.f : 0.f;
+            float4 xa, xb = make_float4(0.f, 0.f, 0.f, 0.f);
+            auto ldx = [&](int j) {
+                const int oa = slice_off(j, sliceA);
+                xa = *reinterpret_cast<const float4*>(xs + oa);
+                if (xd) { const float4 t = *reinterpret_cast<const float4*>(xd + oa); xa.x += t.x; xa.y += t.y; xa.z += t.z; xa.w += t.w; }
+                if (sliceB >= 0) {
+                    const int ob = slice_off(j, sliceB);
+                    xb = *reinterpret_cast<const float4*>(xs + ob);
+                    if (xd) { const float4 t = *reinterpret_cast<const float4*>(xd + ob); xb.x += t.x; xb.y += t.y; xb.z += t.z; xb.w += t.w; }
+                }
+            };
+            auto stx = [&](int stage) {
+                float* row = s_x + (stage * kTaTE + e) * kTaXLd;
+                *reinterpret_cast<float4*>(row + 4 * sliceA) = make_float4(xa.x * okf, xa.y * okf, xa.z * okf, xa.w * okf);
+                if (sliceB >= 0) *reinterpret_cast<float4*>(row + 4 * sliceB) = make_float4(xb.x * okf, xb.y * okf, xb.z * okf, xb.w * okf);
+            };
             if (warp < 4) {
                 const int i = warp;
-                float2 xab, w0, w1, w2; float x1[3], w6[6];
-                auto load = [&](int j) {
-                    const int ch = 8 * j + 2 * i, p = 4 * j + i;
-                    xab = *reinterpret_cast<const float2*>(xs + ch);
-                    if (xd) { const float2 t = *reinterpret_cast<const float2*>(xd + ch); xab.x += t.x; xab.y += t.y; }
-                    w0 = *reinterpret_cast<const float2*>(wr + D::W_K0 + ch);
-                    w1 = *reinterpret_cast<const float2*>(wr + D::W_K1 + ch);
-                    w2 = *reinterpret_cast<const float2*>(wr + D::W_K2 + ch);
+                float2 w0, w1, w2; float w6[6];
+                auto ldw = [&](int j) {
+                    if (a.w_perm) {
+                        const float4* q = reinterpret_cast<const float4*>(wr + 60 * j + 12 * i);
+                        const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+                        w0 = make_float2(q0.x, q0.y); w1 = make_float2(q0.z, q0.w); w2 = make_float2(q1.x, q1.y);
+                        w6[0] = q1.z; w6[1] = q1.w; w6[2] = q2.x; w6[3] = q2.y; w6[4] = q2.z; w6[5] = q2.w;
+                    } else {
+                        const int ch = 8 * j + 2 * i, p = 4 * j + i;
+                        w0 = *reinterpret_cast<const float2*>(wr + D::W_K0 + ch);
+                        w1 = *reinterpret_cast<const float2*>(wr + D::W_K1 + ch);
+                        w2 = *reinterpret_cast<const float2*>(wr + D::W_K2 + ch);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) x1[k] = xs[D::M0 + 3 * p + k];
-                    if (xd) {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) x1[k] += xd[D::M0 + 3 * p + k];
+                        for (int k = 0; k < 6; ++k) w6[k] = wr[D::W_K3 + p + k * D::M1];
                     }
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) w6[k] = wr[D::W_K3 + p + k * D::M1];
                 };
-                load(0);
+                ldx(0); ldw(0); stx(0);
+                prod_sync();
 #pragma unroll 1
                 for (int j = 0; j < NCH; ++j) {
+                    const float* xrow = s_x + ((j & 1) * kTaTE + e) * kTaXLd;
+                    const float2 xab = *reinterpret_cast<const float2*>(xrow + 2 * i);
+                    float x1[3] = {xrow[8 + 3 * i], xrow[9 + 3 * i], xrow[10 + 3 * i]};
+                    if (j + 1 < NCH) ldx(j + 1);                           // next chunk's gathers fly during the math and the stores
                     float oa[9], ob[9], o[20];
-                    dtp_l0(xab.x * okf, w0.x, w1.x, w2.x, sh, oa);
-                    dtp_l0(xab.y * okf, w0.y, w1.y, w2.y, sh, ob);
-                    { float xz[3] = {x1[0] * okf, x1[1] * okf, x1[2] * okf}; dtp_l1(xz, w6, sh, o); }
-                    if (j + 1 < NCH) load(j + 1);                          // next chunk's gathers fly during the stores
+                    dtp_l0(xab.x, w0.x, w1.x, w2.x, sh, oa);
+                    dtp_l0(xab.y, w0.y, w1.y, w2.y, sh, ob);
+                    dtp_l1(x1, w6, sh, o);
+                    if (j + 1 < NCH) ldw(j + 1);
                     tc::mbar_wait_bounded(&emptyA[st], ph ^ 1u);
                     unsigned char* hi = sA + st * kAStage;
                     unsigned char* lo = hi + kAPart;
@@ -197,27 +230,33 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&fullA[st]);
                     if (++st == kTaStages) { st = 0; ph ^= 1u; }
+                    if (j + 1 < NCH) stx((j + 1) & 1);
+                    prod_sync();
                 }
             } else {
                 const int t = warp - 4;
-                float x2[5], w6[6];
-                auto load = [&](int j) {
-                    const int q = 2 * j + t;
+                float w6[6];
+                auto ldw = [&](int j) {
+                    if (a.w_perm) {
+                        const float2* q = reinterpret_cast<const float2*>(wr + 60 * j + 48 + 6 * t);
+                        const float2 q0 = q[0], q1 = q[1], q2 = q[2];
+                        w6[0] = q0.x; w6[1] = q0.y; w6[2] = q1.x; w6[3] = q1.y; w6[4] = q2.x; w6[5] = q2.y;
+                    } else {
+                        const int q = 2 * j + t;
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) x2[k] = xs[D::M0 + 3 * D::M1 + 5 * q + k];
-                    if (xd) {
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) x2[k] += xd[D::M0 + 3 * D::M1 + 5 * q + k];
+                        for (int k = 0; k < 6; ++k) w6[k] = wr[D::W_K9 + q + k * D::M2];
                     }
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) w6[k] = wr[D::W_K9 + q + k * D::M2];
                 };
-                load(0);
+                ldx(0); ldw(0); stx(0);
+                prod_sync();
 #pragma unroll 1
                 for (int j = 0; j < NCH; ++j) {
+                    const float* xrow = s_x + ((j & 1) * kTaTE + e) * kTaXLd + 20 + 2 * (j & 1) + 5 * t;
+                    float x2[5] = {xrow[0], xrow[1], xrow[2], xrow[3], xrow[4]};
+                    if (j + 1 < NCH) ldx(j + 1);
                     float o[22];
-                    { float xz[5] = {x2[0] * okf, x2[1] * okf, x2[2] * okf, x2[3] * okf, x2[4] * okf}; dtp_l2(xz, w6, sh, o); }
-                    if (j + 1 < NCH) load(j + 1);
+                    dtp_l2(x2, w6, sh, o);
+                    if (j + 1 < NCH) ldw(j + 1);
                     tc::mbar_wait_bounded(&emptyA[st], ph ^ 1u);
                     unsigned char* hi = sA + st * kAStage;
                     unsigned char* lo = hi + kAPart;
@@ -247,6 +286,8 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&fullA[st]);
                     if (++st == kTaStages) { st = 0; ph ^= 1u; }
+                    if (j + 1 < NCH) stx((j + 1) & 1);
+                    prod_sync();
                 }
             }
         }
@@ -448,17 +489,17 @@ extern "C" int dedf_tp_act_tc_set_debug(long long* dbg) { g_ta_dbg = dbg; return
 
 extern "C" int dedf_edge_tp_act_tc(int mul1, const float* x_src, const float* x_dst, const int* edge_src, const int* edge_dst,
                                    const int* n_edges_dev, int max_edges, const float* sh, const float* w, long long w_stride,
-                                   const float* W_tc, const float* bias0, const float* alpha_dot, const float* edge_logit,
+                                   int w_perm, const float* W_tc, const float* bias0, const float* alpha_dot, const float* edge_logit,
                                    float* logits, float* out, cudaStream_t stream) {
     if (max_edges <= 0) return DEDF_OK;
     if (!x_src || !edge_src || !edge_dst || !n_edges_dev || !sh || !w || !W_tc || !alpha_dot || !logits || !out) return DEDF_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(W_tc) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(logits) & 15) ||
-        (reinterpret_cast<uintptr_t>(w) & 7) || (reinterpret_cast<uintptr_t>(x_src) & 7) || (x_dst && (reinterpret_cast<uintptr_t>(x_dst) & 7)) ||
-        (w_stride & 1))
+        (reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(x_src) & 15) || (x_dst && (reinterpret_cast<uintptr_t>(x_dst) & 15)) ||
+        (w_stride & 3))
         return DEDF_ERR_ARG;
     TpActArgs a{};
     a.x_src = x_src; a.x_dst = x_dst; a.edge_src = edge_src; a.edge_dst = edge_dst; a.n_edges = n_edges_dev; a.sh = sh;
-    a.w = w; a.w_stride = w_stride; a.Wp = W_tc; a.bias0 = bias0; a.alpha_dot = alpha_dot; a.edge_logit = edge_logit;
+    a.w = w; a.w_stride = w_stride; a.w_perm = w_perm ? 1 : 0; a.Wp = W_tc; a.bias0 = bias0; a.alpha_dot = alpha_dot; a.edge_logit = edge_logit;
     a.logits = logits; a.out = out; a.dbg = g_ta_dbg;
     if (mul1 == 32) return launch_tp_act_tc<32>(a, max_edges, stream);
     if (mul1 == 16) return launch_tp_act_tc<16>(a, max_edges, stream);

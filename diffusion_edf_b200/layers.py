@@ -108,6 +108,24 @@ def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor)
     return torch.cat(chunks).contiguous()
 
 
+def tp_act_w_perm(G: int) -> torch.Tensor:
+    """Column order of the per-edge tensor-product weights that dedf_edge_tp_act_tc reads with vector loads (w_perm = 1):
+    new column c holds original column perm[c].  Chunk j (60 columns): for producer warp i = 0..3 the 12 weights
+    [k0 a, k0 b, k1 a, k1 b, k2 a, k2 b, k3 p .. k8 p] (a = 8j+2i, b = a+1, p = 4j+i), then for t = 0, 1 the 6 weights
+    [k9 q .. k14 q] (q = 2j+t)."""
+    M0, M1, M2 = 2 * G, G, G // 2
+    perm = []
+    for j in range(M0 // 8):
+        for i in range(4):
+            a, p = 8 * j + 2 * i, 4 * j + i
+            perm += [a, a + 1, M0 + a, M0 + a + 1, 2 * M0 + a, 2 * M0 + a + 1] + [3 * M0 + s * M1 + p for s in range(6)]
+        for t in range(2):
+            q = 2 * j + t
+            perm += [3 * M0 + 6 * M1 + s * M2 + q for s in range(6)]
+    assert sorted(perm) == list(range(3 * M0 + 6 * M1 + 6 * M2))
+    return torch.tensor(perm, dtype=torch.long)
+
+
 def tc_mlp_ok(dims: Sequence[int]) -> bool:
     """Can dedf_edge_mlp_tc run an MLP with these layer widths?"""
     n = len(dims) - 1
@@ -240,8 +258,17 @@ class RadialProfile(nn.Module):
         nn.init.uniform_(self.offset, -bound, bound)
         self.ch_list = list(ch_list)
         self._packed = _Packed()
+        self._packed_perm = _Packed()
+        # set by the consumer (GraphAttention): column order in which dedf_edge_tp_act_tc wants the output (tp_act_w_perm)
+        self.out_perm: Optional[torch.Tensor] = None
+
+    def permuted(self) -> bool:
+        """Is the kernel-side output in ``out_perm`` column order right now?  (The parameters / state_dict never are.)"""
+        return self.out_perm is not None and ops.USE_TC_TPACT
 
     def packed(self):
+        perm = self.out_perm if self.permuted() else None
+
         def build():
             lin = [m for m in self.net if isinstance(m, nn.Linear)]
             lns = [m for m in self.net if isinstance(m, nn.LayerNorm)]
@@ -249,9 +276,15 @@ class RadialProfile(nn.Module):
             b = [m.bias.detach().contiguous() if m.bias is not None else None for m in lin]
             g = [m.weight.detach().contiguous() for m in lns]
             bb = [m.bias.detach().contiguous() for m in lns]
+            off = self.offset.detach().contiguous()
+            if perm is not None:      # a column permutation of the output = of the last layer's weights, bias and offset
+                pm = perm.to(W[-1].device)
+                W[-1] = W[-1][:, pm].contiguous()
+                b[-1] = b[-1][pm].contiguous() if b[-1] is not None else None
+                off = off[pm].contiguous()
             Wtc = [pack_tc(w) for w in W] if tc_mlp_ok(self.ch_list) else None
-            return W, b, g, bb, self.offset.detach().contiguous(), Wtc
-        return self._packed.get(self, build)
+            return W, b, g, bb, off, Wtc
+        return (self._packed_perm if perm is not None else self._packed).get(self, build)
 
     def fill_desc(self, d: L.MlpDesc, first_layer: int = 0) -> None:
         """Describe the MLP layers starting at slot ``first_layer`` of ``d`` (dims[first_layer] must be ch_list[0])."""
@@ -349,6 +382,8 @@ class GraphAttention(nn.Module):
         nn.init.xavier_uniform_(self.alpha_dot)
         self.proj = LinearRS(self.irreps_emb, self.irreps_out)
         self._packed = _Packed()
+        if self.irreps_emb.m[1] in (16, 32) and self.irreps_emb.m == (2 * self.irreps_emb.m[1], self.irreps_emb.m[1], self.irreps_emb.m[1] // 2):
+            self.sep_act.dtp_rad.out_perm = tp_act_w_perm(self.irreps_emb.m[1])
 
     def packed(self):
         def build():
@@ -368,9 +403,12 @@ class GraphAttention(nn.Module):
         return self._packed.get(self, build)
 
     def attend(self, msg_src: torch.Tensor, msg_dst: Optional[torch.Tensor], g: ops.Csr, sh: torch.Tensor,
-               w: torch.Tensor, edge_logit: Optional[torch.Tensor], src_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+               w: torch.Tensor, edge_logit: Optional[torch.Tensor], src_weight: Optional[torch.Tensor] = None,
+               w_perm: Optional[bool] = None) -> torch.Tensor:
         """-> sum_e softmax(logit)_e * value_e per destination, (n_dst, F) (before ``proj``).  ``src_weight`` (N_src,): source-point
-        attention, alpha_e *= w[src_e] AFTER the softmax (graph_attention.py:258-259) == scaling the value rows."""
+        attention, alpha_e *= w[src_e] AFTER the softmax (graph_attention.py:258-259) == scaling the value rows.
+        ``w``: per-edge tensor-product weights as produced by the kernels from ``self.sep_act.dtp_rad.packed()`` (column order
+        ``dtp_rad.permuted()``); pass ``w_perm=False`` for weights in the reference's order."""
         p = self.packed()
         G = self.irreps_emb.m[1]
         F = self.irreps_emb.dim
@@ -379,8 +417,12 @@ class GraphAttention(nn.Module):
         logits = torch.empty(E, 4, dtype=torch.float32, device=dev)
         v = torch.empty(E, F, dtype=torch.float32, device=dev)
         if ops.USE_TC_TPACT and p["Wtc"] is not None:
-            ops.edge_tp_act_tc(G, msg_src, msg_dst, g, sh, w, self.sep_act.numel, p["Wtc"], p["b0"], p["alpha_dot"], edge_logit, logits, v)
+            # ``w`` comes from self.sep_act.dtp_rad, whose kernel-side output is in the chunk-major column order while the flag is on
+            ops.edge_tp_act_tc(G, msg_src, msg_dst, g, sh, w, self.sep_act.numel, p["Wtc"], p["b0"], p["alpha_dot"], edge_logit, logits, v,
+                               w_perm=self.sep_act.dtp_rad.permuted() if w_perm is None else w_perm)
         else:
+            if self.sep_act.dtp_rad.permuted() if w_perm is None else w_perm:
+                raise L.DedfError("tensor-product weights in chunk-major column order need dedf_edge_tp_act_tc")
             ops.edge_tp_lin(G, L.EPI_ACT, msg_src, msg_dst, False, g, sh, w, self.sep_act.numel, p["W0"], p["W1"], p["W2"], p["b0"],
                             alpha_dot=p["alpha_dot"], edge_logit=edge_logit, logits=logits, out=v)
         if ops.USE_VALUE_REDUCE:

@@ -309,10 +309,12 @@ def edge_tp_lin(mul1: int, epilogue: int, x_src: torch.Tensor, x_dst: Optional[t
 
 
 def edge_tp_act_tc(mul1: int, x_src: torch.Tensor, x_dst: Optional[torch.Tensor], g: Csr, sh: torch.Tensor, w: torch.Tensor,
-                   w_stride: int, W_tc: torch.Tensor, bias0, alpha_dot, edge_logit, logits: torch.Tensor, out: torch.Tensor) -> None:
-    """dedf_edge_tp_lin(EPI_ACT) with the linear layer on the tcgen05 tensor cores."""
+                   w_stride: int, W_tc: torch.Tensor, bias0, alpha_dot, edge_logit, logits: torch.Tensor, out: torch.Tensor,
+                   w_perm: bool = False) -> None:
+    """dedf_edge_tp_lin(EPI_ACT) with the linear layer on the tcgen05 tensor cores.  ``w_perm``: the columns of ``w`` are in
+    the kernel's chunk-major order (layers.tp_act_w_perm)."""
     _call("dedf_edge_tp_act_tc", mul1, ptr(x_src), ptr(x_dst), ptr(g.edge_src, torch.int32), ptr(g.edge_dst, torch.int32),
-          ptr(g.n_edges_dev, torch.int32), g.n_edges, ptr(sh), ptr(w), w_stride, ptr(W_tc), ptr(bias0), ptr(alpha_dot),
+          ptr(g.n_edges_dev, torch.int32), g.n_edges, ptr(sh), ptr(w), w_stride, 1 if w_perm else 0, ptr(W_tc), ptr(bias0), ptr(alpha_dot),
           ptr(edge_logit), ptr(logits), ptr(out), stream())
 
 

@@ -151,10 +151,12 @@ int dedf_edge_tp_lin(int mul1, int epilogue, const float* x_src, const float* x_
 /* dedf_edge_tp_lin with the EPI_ACT epilogue on the tcgen05 tensor cores (3xTF32, fp32 accumulators in TMEM): same
  * inputs, same outputs (graph_attention.py:231-246).  W_tc: the block-diagonal weights [sep_alpha | sep_act.lin] packed
  * per channel chunk as tf32 hi / lo B operands (diffusion_edf_b200/layers.py: pack_tp_act_tc documents the order);
- * bias0 (MA + m0 + m1 + m2) as for dedf_edge_tp_lin.  w_stride must be even; gathers only (no per-edge x). */
+ * bias0 (MA + m0 + m1 + m2) as for dedf_edge_tp_lin.  Gathers only (no per-edge x); x_src, x_dst, w 16-byte aligned,
+ * w_stride % 4 == 0.  w_perm != 0: the columns of w are in the kernel's chunk-major order (layers.tp_act_w_perm: the
+ * producer of w - the radial MLP - permutes its last layer), which turns 9 / 6 scalar gathers per lane into 3 vector ones. */
 int dedf_edge_tp_act_tc(int mul1, const float* x_src, const float* x_dst, const int* edge_src, const int* edge_dst,
                         const int* n_edges_dev, int max_edges, const float* sh, const float* w, long long w_stride,
-                        const float* W_tc, const float* bias0, const float* alpha_dot, const float* edge_logit,
+                        int w_perm, const float* W_tc, const float* bias0, const float* alpha_dot, const float* edge_logit,
                         float* logits, float* out, cudaStream_t stream);
 
 /* torch_scatter.scatter_logsumexp + exp + scatter(sum) (graph_attention.py:254-265): per destination and head

@@ -47,7 +47,25 @@ def act_tc():
     ops.edge_tp_act_tc(G, msg, None, g, sh, w, ga.sep_act.numel, p["Wtc"], p["b0"], p["alpha_dot"], None, logits, v)
 
 
-for name, fn in (("ACT", act), ("ACT_TC", act_tc), ("LIN", lin)):
+from diffusion_edf_b200 import layers
+w_p = w[:, layers.tp_act_w_perm(G).to(dev)].contiguous()
+msg_d = torch.randn(n_dst, F, device=dev)
+
+
+def act_tc_perm():
+    ops.edge_tp_act_tc(G, msg, None, g, sh, w_p, ga.sep_act.numel, p["Wtc"], p["b0"], p["alpha_dot"], None, logits, v, w_perm=True)
+
+
+def act_tc_perm_dst():
+    ops.edge_tp_act_tc(G, msg, msg_d, g, sh, w_p, ga.sep_act.numel, p["Wtc"], p["b0"], p["alpha_dot"], None, logits, v, w_perm=True)
+
+
+def act_dst():
+    ops.edge_tp_lin(G, L.EPI_ACT, msg, msg_d, False, g, sh, w, ga.sep_act.numel, p["W0"], p["W1"], p["W2"], p["b0"],
+                    alpha_dot=p["alpha_dot"], edge_logit=None, logits=logits, out=v)
+
+
+for name, fn in (("ACT", act), ("ACT+dst", act_dst), ("ACT_TC", act_tc), ("ACT_TC perm", act_tc_perm), ("ACT_TC perm+dst", act_tc_perm_dst), ("LIN", lin)):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -63,7 +81,7 @@ for name, fn in (("ACT", act), ("ACT_TC", act_tc), ("LIN", lin)):
     torch.cuda.synchronize()
     lib.dedf_tp_lin_set_debug(None)
     d = [z for z in dbg.cpu().tolist() if z]
-    if name == "ACT_TC":
+    if name.startswith("ACT_TC"):
         lib.dedf_tp_act_tc_set_debug.argtypes = [ctypes.c_void_p]
         d2 = torch.zeros(8, dtype=torch.int64, device=dev)
         lib.dedf_tp_act_tc_set_debug(d2.data_ptr()); fn(); torch.cuda.synchronize(); lib.dedf_tp_act_tc_set_debug(None)

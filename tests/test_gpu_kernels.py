@@ -172,7 +172,7 @@ def test_graph_attention_pieces(cuda, G):
     assert_close(attn, attn_ref, TOL, "softmax-reduce")
     assert float(attn[0].abs().max()) == 0.0, "isolated destination must give zeros"
     # whole attend() path
-    attn2 = pga.attend(msg_src.to(cuda), msg_dst.to(cuda), csr, sh.to(cuda), w.to(cuda), edge_logit.to(cuda))
+    attn2 = pga.attend(msg_src.to(cuda), msg_dst.to(cuda), csr, sh.to(cuda), w.to(cuda), edge_logit.to(cuda), w_perm=False)
     assert_close(attn2, attn_ref, TOL, "attend")
 
 

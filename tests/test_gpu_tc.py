@@ -182,8 +182,41 @@ def test_edge_tp_act_tc(cuda, G, E, use_dst, use_logit):
             logit_ref = torch.einsum("ehk,hk->eh", la, oga.alpha_dot.squeeze(0)) + (edge_logit[:, None] if use_logit else 0)
         assert rel_err(logits, logit_ref) < 1e-4, f"logits vs oracle: {rel_err(logits, logit_ref):.3e}"
         assert rel_err(v, v_ref) < 1e-4, f"values vs oracle: {rel_err(v, v_ref):.3e}"
-    # same launch twice: bit-identical
+    # same launch twice: bit-identical; per-edge weights handed over in the kernel's chunk-major column order: bit-identical too
     logits3 = torch.empty(E, 4, device=cuda)
     v3 = torch.empty(E, F, device=cuda)
     ops.edge_tp_act_tc(G, dv(msg_src), dv(msg_dst), csr, dv(sh), dv(w), numel, p["Wtc"], p["b0"], p["alpha_dot"], dv(edge_logit), logits3, v3)
     assert torch.equal(logits, logits3) and torch.equal(v, v3)
+    w_perm = w[:, layers.tp_act_w_perm(G)].contiguous()
+    logits3.fill_(float("nan")); v3.fill_(float("nan"))
+    ops.edge_tp_act_tc(G, dv(msg_src), dv(msg_dst), csr, dv(sh), dv(w_perm), numel, p["Wtc"], p["b0"], p["alpha_dot"], dv(edge_logit), logits3, v3,
+                       w_perm=True)
+    assert torch.equal(logits, logits3) and torch.equal(v, v3)
+
+
+def test_full_forward_tc_attention_on_off(cuda):
+    """Whole MultiscaleScoreModel.forward (UNet encoder with G = 16 and G = 32 blocks, tensor field, score head) with the
+    attention block's linear layer on the tensor cores + chunk-major radial weights (ops.USE_TC_TPACT) and with the fp32
+    CUDA-core kernel + reference column order: same scores to fp32 round-off."""
+    from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel, ops
+    from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs
+    torch.manual_seed(0)
+    model = MultiscaleScoreModel(**model_kwargs(), deterministic=True).eval().to(cuda)
+    model.use_cuda_graph = False
+    x, rgb = make_scene(2500, seed=5, half_extent=12.0)
+    Ts, t = make_poses(19, x, seed=5, spread=6.0)
+    key = FeaturedPoints(x.to(cuda), rgb.to(cuda), torch.zeros(len(x), dtype=torch.long, device=cuda))
+    grasp = FeaturedPoints(torch.zeros(8, 3, device=cuda), torch.zeros(8, 3, device=cuda), torch.zeros(8, dtype=torch.long, device=cuda))
+    res = []
+    with torch.no_grad():
+        for tc in (True, False):
+            ops.USE_TC_TPACT = tc
+            try:
+                n0 = ops.LAUNCHES
+                (ang, lin), _ = model(Ts.to(cuda), t.to(cuda), key, grasp)
+                res.append((ang.clone(), lin.clone()))
+            finally:
+                ops.USE_TC_TPACT = True
+    for a, b in zip(res[0], res[1]):
+        assert torch.isfinite(a).all()
+        assert rel_err(a, b) <= 5e-5, rel_err(a, b)
