@@ -17,11 +17,19 @@
 //   * the tile's rows are the M side: 32 rows (l_out = 0), 96 rows (m, e) (l_out = 1), 160 rows (l_out = 2, two MMAs);
 //     M is always 128 and the rows past the stored ones alias the following shared memory (finite or not, they only
 //     reach accumulator rows nobody reads).
+//   * the 2e output's m = 4 rows ride in rows 96..127 of the 1e operand and the 1e / 2e weights sit side by side in one
+//     B operand (N = 48 / 32): one MMA serves both, the cross terms land in accumulator cells nobody reads.  The 0e GEMM
+//     runs with the operands swapped (M = output channels, N = 32 edges) so that its epilogue work spreads over all four
+//     TMEM lane quarters instead of one.
 //   * warp roles: 6 producer warps (lane = edge; warps 0-3 take one l=1 channel + two l=0 channels of the chunk, warps
 //     4-5 one l=2 channel: balanced to 7 %), each thread writing whole float4 K-groups of the chunk-major operand;
-//     warp 6 = TMA weight ring; warp 7 = MMA issuer (33 tcgen05.mma per chunk); warps 8-11 = epilogue (TMEM -> bias,
-//     activations, gates -> staged value rows -> one bulk store per edge row), double-buffered accumulators (2 x 256
-//     TMEM columns) so the epilogue of tile t overlaps the production of tile t + 1.
+//     8 epilogue warps (TMEM -> bias, activations, gates -> staged value rows -> one bulk store per edge row), one TMA
+//     weight-ring warp, one MMA issuer (30 tcgen05.mma per chunk); double-buffered accumulators (2 x 128 TMEM columns)
+//     so the epilogue of tile t overlaps the production of tile t + 1.
+//   * measured (profiles/run_tp_lin.py, 86 k edges, G = 32): 248 us vs 686 us for the fp32 FMA kernel.  The MMA issuer's
+//     cycle accounting (dedf_tp_act_tc_set_debug) shows the tensor pipe waiting on shared-memory bandwidth: every
+//     M = 128 x K = 8 tf32 MMA fetches 4 KB for the M side whatever N is, the producers store 53 KB per chunk next to it;
+//     a second producer group (12 warps) made both slower (275 us).
 #include "common.cuh"
 #include "tc.cuh"
 #include "cg_slots.cuh"
@@ -38,7 +46,7 @@ constexpr int kTaAccCols = 128;
 constexpr int kTaXLd = 36;                          // staged message slice: 8 (0e) + 12 (1e) + 12 (2e, 10 used) floats + 4 pad                     // TMEM columns of one accumulator buffer
 constexpr int kTaStages = 2;                        // A chunk stages and weight ring stages
 constexpr int kKC0 = 16, kKC1 = 24, kKC2 = 24;      // K columns per chunk of the three GEMMs
-constexpr int kR0 = kTaTE, kR1 = 3 * kTaTE, kR2 = 5 * kTaTE;   // stored rows
+constexpr int kR0 = kTaTE, kR1 = 4 * kTaTE, kR2 = 4 * kTaTE;   // stored rows: 0e (e) | 1e (m, e) m < 3 + 2e m = 4 | 2e (m, e) m < 4
 constexpr int kA0Off = 0;
 constexpr int kA1Off = kA0Off + (kKC0 / 4) * kR0 * 16;          //  2048
 constexpr int kA2Off = kA1Off + (kKC1 / 4) * kR1 * 16;          // 11264
@@ -55,13 +63,14 @@ struct TaCfg {
     static constexpr int N1P = (D::M1 + 15) / 16 * 16;                     // 32 / 16
     static constexpr int N2P = (D::M2 + 15) / 16 * 16;                     // 16 / 16
     static constexpr int W0Off = 0;
+    static constexpr int N1C = N1P + N2P;                                  // combined 1e | 2e (m = 4) GEMM: 48 / 32 columns
     static constexpr int W1Off = W0Off + (kKC0 / 4) * N0P * 16;
-    static constexpr int W2Off = W1Off + (kKC1 / 4) * N1P * 16;
+    static constexpr int W2Off = W1Off + (kKC1 / 4) * N1C * 16;
     static constexpr int WPart = W2Off + (kKC2 / 4) * N2P * 16;            // 15872 / 9216
     static constexpr int WStage = 2 * WPart;
     static constexpr int MT0 = (N0P + 127) / 128;                          // M tiles of the (swapped) l_out = 0 GEMM
-    static constexpr int T0 = 0, T1 = 2 * kTaTE, T2A = T1 + N1P, T2B = T2A + N2P;   // TMEM columns of the accumulators
-    static_assert(T2B + N2P <= kTaAccCols, "accumulator buffer");
+    static constexpr int T0 = 0, T1 = 2 * kTaTE, T2B = T1 + N1P, T2A = T1 + N1C;   // TMEM columns of the accumulators
+    static_assert(T2A + N2P <= kTaAccCols && kKC1 == kKC2, "accumulator buffer / combined GEMM");
     static constexpr int LDO = D::F + 4;                                   // staged value row stride (floats)
     static constexpr int NG = D::M1 + D::M2;                               // gates
     // dynamic shared memory
@@ -224,8 +233,9 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                         put1(kA1Off + (4 * kR1 + m * kTaTE + e) * 16 + i * 4, ob[1 + m]);
                     }
 #pragma unroll
-                    for (int m = 0; m < 5; ++m)        // l_out = 2, group i: [k2 a, k2 b, k6, k8]
-                        put4(kA2Off + (i * kR2 + m * kTaTE + e) * 16, oa[4 + m], ob[4 + m], o[7 + m], o[15 + m]);
+                    for (int m = 0; m < 5; ++m)        // l_out = 2, group i: [k2 a, k2 b, k6, k8]; m = 4 rides in rows 96.. of the 1e operand
+                        put4(m < 4 ? kA2Off + (i * kR2 + m * kTaTE + e) * 16 : kA1Off + (i * kR1 + 3 * kTaTE + e) * 16,
+                             oa[4 + m], ob[4 + m], o[7 + m], o[15 + m]);
                     tc::fence_async_smem();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&fullA[st]);
@@ -281,7 +291,8 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                         put2(kA1Off + (5 * kR1 + m * kTaTE + e) * 16 + t * 8, o[5 + m], o[14 + m]);
 #pragma unroll
                     for (int m = 0; m < 5; ++m)        // l_out = 2, group 4 + t: [k9, k11, k14, 0]
-                        put4(kA2Off + ((4 + t) * kR2 + m * kTaTE + e) * 16, o[m], o[8 + m], o[17 + m], 0.f);
+                        put4(m < 4 ? kA2Off + ((4 + t) * kR2 + m * kTaTE + e) * 16 : kA1Off + ((4 + t) * kR1 + 3 * kTaTE + e) * 16,
+                             o[m], o[8 + m], o[17 + m], 0.f);
                     tc::fence_async_smem();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&fullA[st]);
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
         if (lane == 0) {
             uint32_t st = 0, ph = 0;
             const uint32_t a_base = smem_u32(sA), w_base = smem_u32(sW);
-            const uint32_t id0 = tc::idesc_tf32(128, kTaTE), id1 = tc::idesc_tf32(128, C::N1P), id2 = tc::idesc_tf32(128, C::N2P);
+            const uint32_t id0 = tc::idesc_tf32(128, kTaTE), id1 = tc::idesc_tf32(128, C::N1C), id2 = tc::idesc_tf32(128, C::N2P);
             int it = 0;
             long long wA = 0, wW = 0, wE = 0, tIssue = 0;
             const long long tStart = clock64();
@@ -332,32 +343,36 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                     const long long ci = clock64();
                     const uint32_t ah = a_base + st * kAStage, al = ah + kAPart;
                     const uint32_t wh = w_base + st * C::WStage, wl = wh + C::WPart;
-                    auto gemm = [&](uint32_t a_off, uint32_t lbo_a, uint32_t w_off, uint32_t lbo_w, int ksteps, uint32_t idesc, uint32_t d) {
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t dah = tc::smem_desc(ah + a_off + ks * 2 * lbo_a, lbo_a, 128);
-                            const uint64_t dal = tc::smem_desc(al + a_off + ks * 2 * lbo_a, lbo_a, 128);
-                            const uint64_t dwh = tc::smem_desc(wh + w_off + ks * 2 * lbo_w, lbo_w, 128);
-                            const uint64_t dwl = tc::smem_desc(wl + w_off + ks * 2 * lbo_w, lbo_w, 128);
-                            tc::mma_tf32(d, dah, dwh, idesc, (j > 0 || ks > 0) ? 1u : 0u);
-                            tc::mma_tf32(d, dal, dwh, idesc, 1u);
-                            tc::mma_tf32(d, dah, dwl, idesc, 1u);
+                    // One MMA = (GEMM g, K step ks, pass p of the 3xTF32 split); the four GEMMs of the chunk are issued round-robin
+                    // so that consecutive instructions target different TMEM columns (measured: ~64 cycles per MMA either way --
+                    // what an M = 128 x K = 8 tf32 MMA costs with N <= 48 is the fetch of its 4 KB M-side operand).
+                    //   g = 0, 1: l_out = 0 with the operands swapped, D0^T[n][e] = W0^T[n][k] . A0[e][k] (M = channels, N = 32 edges)
+                    //   g = 2:    rows 0..95 = 1e rows (m, e) against [W1 | .], rows 96..127 = the 2e m = 4 rows against [. | W2]:
+                    //             one MMA with N = N1P + N2P, the cross terms land in accumulator cells nobody reads
+                    //   g = 3:    2e rows (m, e), m = 0..3
+                    auto issue = [&](int g, int i) {
+                        const int ks = i / 3, p = i % 3;
+                        const uint32_t acc = (j > 0 || i > 0) ? 1u : 0u;
+                        if (g < 2) {
+                            const uint32_t wo = C::W0Off + ks * 2 * (C::N0P * 16) + g * 128 * 16, ao = kA0Off + ks * 2 * (kR0 * 16);
+                            const uint64_t dw = tc::smem_desc((p == 2 ? wl : wh) + wo, C::N0P * 16, 128);
+                            const uint64_t da = tc::smem_desc((p == 1 ? al : ah) + ao, kR0 * 16, 128);
+                            tc::mma_tf32(d0 + C::T0 + g * kTaTE, dw, da, id0, acc);
+                        } else {
+                            const uint32_t a_off = (g == 2) ? kA1Off : kA2Off, lbo_a = (g == 2 ? kR1 : kR2) * 16;
+                            const uint32_t w_off = (g == 2) ? C::W1Off : C::W2Off, lbo_w = (g == 2 ? C::N1C : C::N2P) * 16;
+                            const uint64_t da = tc::smem_desc((p == 1 ? al : ah) + a_off + ks * 2 * lbo_a, lbo_a, 128);
+                            const uint64_t dw = tc::smem_desc((p == 2 ? wl : wh) + w_off + ks * 2 * lbo_w, lbo_w, 128);
+                            tc::mma_tf32(d0 + (g == 2 ? C::T1 : C::T2A), da, dw, g == 2 ? id1 : id2, acc);
                         }
                     };
-                    // l_out = 0 with the operands swapped: D0^T[n][e] = W0^T[n][k] . A0[e][k]  (M = output channels, N = 32 edges)
-                    for (int mt = 0; mt < C::MT0; ++mt) {
-                        for (int ks = 0; ks < kKC0 / 8; ++ks) {
-                            const uint32_t wo = C::W0Off + ks * 2 * (C::N0P * 16) + mt * 128 * 16, ao = kA0Off + ks * 2 * (kR0 * 16);
-                            const uint64_t dwh = tc::smem_desc(wh + wo, C::N0P * 16, 128), dwl = tc::smem_desc(wl + wo, C::N0P * 16, 128);
-                            const uint64_t dah = tc::smem_desc(ah + ao, kR0 * 16, 128), dal = tc::smem_desc(al + ao, kR0 * 16, 128);
-                            const uint32_t d = d0 + C::T0 + mt * kTaTE;
-                            tc::mma_tf32(d, dwh, dah, id0, (j > 0 || ks > 0) ? 1u : 0u);
-                            tc::mma_tf32(d, dwh, dal, id0, 1u);
-                            tc::mma_tf32(d, dwl, dah, id0, 1u);
-                        }
+                    constexpr int n0 = 3 * (kKC0 / 8), n12 = 3 * (kKC1 / 8);
+#pragma unroll
+                    for (int i = 0; i < n12; ++i) {
+                        if (i < n0) { issue(0, i); if (C::MT0 > 1) issue(1, i); }
+                        issue(2, i);
+                        issue(3, i);
                     }
-                    gemm(kA1Off, kR1 * 16, C::W1Off, C::N1P * 16, kKC1 / 8, id1, d0 + C::T1);
-                    gemm(kA2Off, kR2 * 16, C::W2Off, C::N2P * 16, kKC2 / 8, id2, d0 + C::T2A);            // rows (m, e), m = 0..3
-                    gemm(kA2Off + 32 * 16, kR2 * 16, C::W2Off, C::N2P * 16, kKC2 / 8, id2, d0 + C::T2B);   // m = 4 lands in lanes 96..127
                     tc::commit(&emptyA[st]);
                     tc::commit(&emptyW[st]);
                     tIssue += clock64() - ci;

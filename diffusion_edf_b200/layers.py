@@ -71,7 +71,8 @@ def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor)
         l_out=0 (16): group i = [k0 a, k0 b, k4 p, k12 q_i if i < 2 else 0]
         l_out=1 (24): group i = [k3 p, k5 p, k7 p, k1 a];  group 4 = [k1 b_0..b_3];  group 5 = [k10 q0, k13 q0, k10 q1, k13 q1]
         l_out=2 (24): group i = [k2 a, k2 b, k6 p, k8 p];  group 4+t = [k9 q_t, k11 q_t, k14 q_t, 0]
-    Each block is stored chunk-major [K/4][N padded to 16][4], the chunk as [l0 | l1 | l2] hi then [l0 | l1 | l2] lo."""
+    Each block is stored chunk-major [K/4][N padded to 16][4], the chunk as [l0 | l1+l2 | l2] hi then the same for lo; the
+    middle block holds the l_out=1 and l_out=2 weights side by side (the m = 4 rows of the 2e output share the 1e MMA)."""
     M0, M1, M2 = 2 * G, G, G // 2
     C0 = dict(k0=0, k4=M0, k12=M0 + M1)
     C1 = dict(k1=0, k3=M0, k5=M0 + M1, k7=M0 + 2 * M1, k10=M0 + 3 * M1, k13=M0 + 3 * M1 + M2)
@@ -88,6 +89,18 @@ def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor)
                 sel[k, :N] = W[r]
         return sel.view(K // 4, 4, Np).permute(0, 2, 1).contiguous().view(-1)      # [K/4][Np][4]
 
+    def block2(Wa, ra, Wb, rb):
+        # [Wa | Wb] side by side: the 1e rows and the 2e m = 4 rows share one MMA (rows 0..95 read the Wa columns, 96..127 the Wb ones)
+        K, Na, Nb = len(ra), Wa.shape[1], Wb.shape[1]
+        Nap, Nbp = (Na + 15) // 16 * 16, (Nb + 15) // 16 * 16
+        sel = torch.zeros(K, Nap + Nbp, dtype=torch.float32, device=Wa.device)
+        for k in range(K):
+            if ra[k] is not None:
+                sel[k, :Na] = Wa[ra[k]]
+            if rb[k] is not None:
+                sel[k, Nap:Nap + Nb] = Wb[rb[k]]
+        return sel.view(K // 4, 4, Nap + Nbp).permute(0, 2, 1).contiguous().view(-1)
+
     chunks = []
     for j in range(M0 // 8):
         a = [8 * j + 2 * i for i in range(4)]
@@ -102,7 +115,7 @@ def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor)
         r1 += [C1["k10"] + q[0], C1["k13"] + q[0], C1["k10"] + q[1], C1["k13"] + q[1]]
         for t in range(2):
             r2 += [C2["k9"] + q[t], C2["k11"] + q[t], C2["k14"] + q[t], None]
-        full = torch.cat([block(W0, r0), block(W1, r1), block(W2, r2)])
+        full = torch.cat([block(W0, r0), block2(W1, r1, W2, r2), block(W2, r2)])
         hi = (full.view(torch.int32) & -8192).view(torch.float32)
         chunks += [hi, full - hi]
     return torch.cat(chunks).contiguous()
