@@ -64,6 +64,7 @@ _PROTOS = {
     "dedf_edge_mlp": [C.POINTER(MlpDesc), c_int, c_fp],
     "dedf_edge_mlp_tc": [C.POINTER(MlpDesc), c_int, c_fp],
     "dedf_edge_tp_lin": [c_int, c_int, c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp],
+    "dedf_l2_persist": [c_fp, c_ll, c_fp],
     "dedf_edge_tp_act_tc": [c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_ll, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp],
     "dedf_segment_softmax_reduce": [c_fp, c_int, c_int, c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp],
     "dedf_edge_tp_reduce": [c_int, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_int, c_fp, c_fp],

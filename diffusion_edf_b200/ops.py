@@ -325,6 +325,16 @@ def segment_softmax_reduce(g: Csr, logits: torch.Tensor, val: torch.Tensor, irr:
     return out
 
 
+K1_PERSIST_BYTES = None        # opt-in (bytes): pin a gathered feature table at least this big in L2 (dedf_l2_persist); measured slower, DESIGN 8
+
+
+def l2_persist(t: Optional[torch.Tensor]) -> None:
+    """Keep ``t`` resident in L2 for the kernels launched into the current stream from now on; ``None`` removes the window."""
+    lib = L.load()
+    rc = lib.dedf_l2_persist(ptr(t) if t is not None else None, t.numel() * t.element_size() if t is not None else 0, stream())
+    L.check(rc, "dedf_l2_persist")
+
+
 def edge_tp_reduce(mul1: int, x: torch.Tensor, row_ptr: torch.Tensor, edge_src: torch.Tensor, sh: torch.Tensor,
                    w: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
     """K1: out[d] = sum_{e->d} alpha[e, head(u)] * DTP(x[src_e], sh_e, w_e)  -> (N_dst, 49 * mul1).
@@ -332,8 +342,13 @@ def edge_tp_reduce(mul1: int, x: torch.Tensor, row_ptr: torch.Tensor, edge_src: 
     n_dst = row_ptr.numel() - 1
     assert sh.shape[1] in (9, 12)
     out = torch.empty(n_dst, 49 * mul1, dtype=torch.float32, device=x.device)
+    persist = K1_PERSIST_BYTES is not None and x.numel() * 4 >= K1_PERSIST_BYTES and not torch.cuda.is_current_stream_capturing()
+    if persist:
+        l2_persist(x)
     _call("dedf_edge_tp_reduce", mul1, ptr(x), ptr(row_ptr, torch.int32), ptr(edge_src, torch.int32), ptr(sh), sh.shape[1], ptr(w),
                                        ptr(alpha), n_dst, ptr(out), stream())
+    if persist:
+        l2_persist(None)
     return out
 
 

@@ -337,6 +337,10 @@ int dedf_build_arch(void);
  * N % 16 == 0, 16 <= N <= 256, K % 8 == 0.  One CTA; used by tests/test_gpu_kernels.py. */
 int dedf_tc_selftest(const float* A, const float* B, int N, int K, int n_split, float* D, cudaStream_t stream);
 
+/* cudaAccessPolicyWindow on `stream`: keep [base, base + bytes) resident in L2 (persisting hits, streaming misses) for the
+ * kernels launched afterwards; bytes = 0 removes the window.  No reference counterpart (used around dedf_edge_tp_reduce). */
+int dedf_l2_persist(const void* base, long long bytes, cudaStream_t stream);
+
 /* Warm the L2 with the model's weights: issues prefetch.global.L2 over n device ranges (ptrs_dev[i], bytes_dev[i]).
  * The reference has no counterpart (its ~10^3 launches per forward re-read the weights through the cache hierarchy
  * implicitly); here the few-CTA kernels of the coarse UNet scales would otherwise pay DRAM latency per weight row. */

@@ -10,6 +10,8 @@ from diffusion_edf_b200 import ops
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 variant = sys.argv[3] if len(sys.argv) > 3 else "tma"
+if len(sys.argv) > 4 and sys.argv[4] == "nopersist":
+    ops.K1_PERSIST_BYTES = None            # A/B: without the L2 access-policy window on the gathered table
 dev = torch.device("cuda:0")
 deg, E = 32, N * 32
 g = torch.Generator().manual_seed(0)
