@@ -80,13 +80,16 @@ def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor)
     W0, W1, W2 = (w.detach().float().contiguous() for w in (W0, W1, W2))
     assert W0.shape[0] == M0 + M1 + M2 and W1.shape == (M0 + 3 * M1 + 2 * M2, M1) and W2.shape == (M0 + 2 * M1 + 3 * M2, M2)
 
+    def rows_of(W, rows):
+        # (K, N) gather of weight rows, zero rows for the pads -- one index_select instead of a copy per row
+        idx = torch.tensor([r if r is not None else W.shape[0] for r in rows], dtype=torch.long, device=W.device)
+        return torch.cat([W, W.new_zeros(1, W.shape[1])])[idx]
+
     def block(W, rows):
         K, N = len(rows), W.shape[1]
         Np = (N + 15) // 16 * 16
         sel = torch.zeros(K, Np, dtype=torch.float32, device=W.device)
-        for k, r in enumerate(rows):
-            if r is not None:
-                sel[k, :N] = W[r]
+        sel[:, :N] = rows_of(W, rows)
         return sel.view(K // 4, 4, Np).permute(0, 2, 1).contiguous().view(-1)      # [K/4][Np][4]
 
     def block2(Wa, ra, Wb, rb):
@@ -94,11 +97,8 @@ def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor)
         K, Na, Nb = len(ra), Wa.shape[1], Wb.shape[1]
         Nap, Nbp = (Na + 15) // 16 * 16, (Nb + 15) // 16 * 16
         sel = torch.zeros(K, Nap + Nbp, dtype=torch.float32, device=Wa.device)
-        for k in range(K):
-            if ra[k] is not None:
-                sel[k, :Na] = Wa[ra[k]]
-            if rb[k] is not None:
-                sel[k, Nap:Nap + Nb] = Wb[rb[k]]
+        sel[:, :Na] = rows_of(Wa, ra)
+        sel[:, Nap:Nap + Nb] = rows_of(Wb, rb)
         return sel.view(K // 4, 4, Nap + Nbp).permute(0, 2, 1).contiguous().view(-1)
 
     chunks = []
