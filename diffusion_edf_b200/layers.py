@@ -77,7 +77,8 @@ def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor)
     C0 = dict(k0=0, k4=M0, k12=M0 + M1)
     C1 = dict(k1=0, k3=M0, k5=M0 + M1, k7=M0 + 2 * M1, k10=M0 + 3 * M1, k13=M0 + 3 * M1 + M2)
     C2 = dict(k2=0, k6=M0, k8=M0 + M1, k9=M0 + 2 * M1, k11=M0 + 2 * M1 + M2, k14=M0 + 2 * M1 + 2 * M2)
-    W0, W1, W2 = (w.detach().float().contiguous() for w in (W0, W1, W2))
+    dev = W0.device
+    W0, W1, W2 = (w.detach().float().cpu().contiguous() for w in (W0, W1, W2))     # a few hundred tiny ops: do them on the host
     assert W0.shape[0] == M0 + M1 + M2 and W1.shape == (M0 + 3 * M1 + 2 * M2, M1) and W2.shape == (M0 + 2 * M1 + 3 * M2, M2)
 
     def rows_of(W, rows):
@@ -118,7 +119,7 @@ def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor)
         full = torch.cat([block(W0, r0), block2(W1, r1, W2, r2), block(W2, r2)])
         hi = (full.view(torch.int32) & -8192).view(torch.float32)
         chunks += [hi, full - hi]
-    return torch.cat(chunks).contiguous()
+    return torch.cat(chunks).contiguous().to(dev)
 
 
 def tp_act_w_perm(G: int) -> torch.Tensor:
