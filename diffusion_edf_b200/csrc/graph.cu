@@ -243,14 +243,32 @@ struct RadiusArgs {
     float r[DEDF_MAX_SCALES];      // < 0: all pairs
 };
 
-template <bool FILL>
+// SMEM: the concatenated source clouds (and their batch ids) are staged in shared memory once per CTA -- the score head's
+// query points meet the same <= 2.5k scene points at every scale, and a warp's walk is a chain of dependent iterations, so
+// the latency of one iteration (global: ~600 cycles, shared: ~30) is what the kernel costs.  Four 32-source chunks are
+// evaluated per iteration before their ordered compaction; chunks past the max_nb cap keep nothing, as before.
+template <bool FILL, bool SMEM>
 __global__ void __launch_bounds__(256)
 radius_kernel(RadiusArgs a, int* __restrict__ counts, const int* __restrict__ row_ptr,
               int* __restrict__ edge_src, int* __restrict__ edge_dst) {
+    extern __shared__ __align__(16) float s_radius[];
     pdl_wait(); pdl_launch();     // PDL: see common.cuh
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const long long n_items = (long long)a.n_dst * a.n_scales;
+    const int n_total = a.src_off[a.n_scales];
+    const float* xs = a.x_src;
+    const int* s_b = nullptr;
+    if (SMEM) {
+        for (int i = threadIdx.x; i < 3 * n_total; i += blockDim.x) s_radius[i] = a.x_src[i];
+        if (a.b_src) {
+            int* sb = reinterpret_cast<int*>(s_radius + 3 * n_total);
+            for (int i = threadIdx.x; i < n_total; i += blockDim.x) sb[i] = (int)a.b_src[i];
+            s_b = sb;
+        }
+        __syncthreads();
+        xs = s_radius;
+    }
     for (long long item = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < n_items;
          item += (long long)gridDim.x * warps_per_block) {
         const int s = (int)(item / a.n_dst), d = (int)(item % a.n_dst);
@@ -266,32 +284,57 @@ radius_kernel(RadiusArgs a, int* __restrict__ counts, const int* __restrict__ ro
         int cnt_all = 0, cnt_keep = 0;
         int base = 0, seg_end = 0x7fffffff;
         if (FILL) { base = row_ptr[item]; seg_end = row_ptr[item + 1]; }
-        for (int c = s0; c < s1 && cnt_all < a.max_nb; c += 32) {
-            const int i = c + lane;
-            bool hit = false, excluded = false;
-            if (i < s1) {
-                hit = all || sqdist_exact(a.x_src[3 * i], a.x_src[3 * i + 1], a.x_src[3 * i + 2], qx, qy, qz) < r2;
-                if (a.b_src && !all) hit = hit && (a.b_src[i] == qb);   // the all-pairs scale ignores batches (graph_parser.py:276-278)
-                const int li = i - s0;   // index local to this scale's cloud
-                if (a.excl_mode == 1) excluded = ((long long)li == ex);
-                else if (a.excl_mode == 2) excluded = (li == d);
-                else if (a.excl_mode == 3) excluded = (a.excl[li] == (long long)d);
-            }
-            const unsigned lt = (1u << lane) - 1u;
-            const unsigned bal_all = __ballot_sync(0xffffffffu, hit);
-            const bool keep = hit && !excluded && (cnt_all + __popc(bal_all & lt) < a.max_nb);
-            const unsigned bal_keep = __ballot_sync(0xffffffffu, keep);
-            if (FILL && keep) {
-                const int pos = base + cnt_keep + __popc(bal_keep & lt);
-                if (pos < seg_end) {
-                    edge_src[pos] = i;              // flat index into the concatenated clouds
-                    edge_dst[pos] = d;
+        constexpr int U = 4;
+        for (int c = s0; c < s1 && cnt_all < a.max_nb; c += 32 * U) {
+            bool hit[U], excluded[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = c + 32 * u + lane;
+                hit[u] = false; excluded[u] = false;
+                if (i < s1) {
+                    hit[u] = all || sqdist_exact(xs[3 * i], xs[3 * i + 1], xs[3 * i + 2], qx, qy, qz) < r2;
+                    if (a.b_src && !all)      // the all-pairs scale ignores batches (graph_parser.py:276-278)
+                        hit[u] = hit[u] && (SMEM ? ((long long)s_b[i] == qb) : (a.b_src[i] == qb));
+                    const int li = i - s0;   // index local to this scale's cloud
+                    if (a.excl_mode == 1) excluded[u] = ((long long)li == ex);
+                    else if (a.excl_mode == 2) excluded[u] = (li == d);
+                    else if (a.excl_mode == 3) excluded[u] = (a.excl[li] == (long long)d);
                 }
             }
-            cnt_all += __popc(bal_all);
-            cnt_keep += __popc(bal_keep);
+            const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = c + 32 * u + lane;
+                const unsigned bal_all = __ballot_sync(0xffffffffu, hit[u]);
+                const bool keep = hit[u] && !excluded[u] && (cnt_all + __popc(bal_all & lt) < a.max_nb);
+                const unsigned bal_keep = __ballot_sync(0xffffffffu, keep);
+                if (FILL && keep) {
+                    const int pos = base + cnt_keep + __popc(bal_keep & lt);
+                    if (pos < seg_end) {
+                        edge_src[pos] = i;              // flat index into the concatenated clouds
+                        edge_dst[pos] = d;
+                    }
+                }
+                cnt_all += __popc(bal_all);
+                cnt_keep += __popc(bal_keep);
+            }
         }
         if (!FILL && lane == 0) counts[item] = cnt_keep;
+    }
+}
+
+// launch the brute-force radius kernel, staging the sources in shared memory when they fit
+template <bool FILL>
+static void launch_radius(const RadiusArgs& a, long long items, int* counts, const int* row_ptr, int* edge_src, int* edge_dst,
+                          cudaStream_t stream) {
+    const int n_total = a.src_off[a.n_scales];
+    const size_t smem = (size_t)n_total * (12 + (a.b_src ? 4 : 0));
+    if (smem > 0 && smem <= 96 * 1024 && !getenv("DEDF_NO_SMEM_RADIUS")) {
+        static bool done = false;
+        if (!done) { cudaFuncSetAttribute(radius_kernel<FILL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); done = true; }
+        launch_pdl((radius_kernel<FILL, true>), dim3(grid_for(items, 8, kNumSMs * 2)), dim3(256), smem, stream, a, counts, row_ptr, edge_src, edge_dst);
+    } else {
+        launch_pdl((radius_kernel<FILL, false>), dim3(grid_for(items, 8, kNumSMs * 8)), dim3(256), 0, stream, a, counts, row_ptr, edge_src, edge_dst);
     }
 }
 
@@ -586,7 +629,7 @@ extern "C" int dedf_radius_count(const float* x_src, const float* x_dst, int n_d
     if (!counts || !row_ptr) return DEDF_ERR_ARG;
     const long long items = (long long)n_dst * n_scales;
     if (items > 0) {
-        launch_pdl((radius_kernel<false>), dim3(grid_for(items, 8, kNumSMs * 8)), dim3(256), 0, stream, a, counts, nullptr, nullptr, nullptr);
+        launch_radius<false>(a, items, counts, nullptr, nullptr, nullptr, stream);
         DEDF_CHECK_LAUNCH();
     }
     launch_pdl(exclusive_scan_kernel, dim3(1), dim3(1024), 0, stream, counts, (int)items, row_ptr, capacity, n_edges_out, overflow);
@@ -604,7 +647,7 @@ extern "C" int dedf_radius_fill(const float* x_src, const float* x_dst, int n_ds
     if (!row_ptr || !edge_src || !edge_dst) return DEDF_ERR_ARG;
     const long long items = (long long)n_dst * n_scales;
     if (items == 0) return DEDF_OK;
-    launch_pdl((radius_kernel<true>), dim3(grid_for(items, 8, kNumSMs * 8)), dim3(256), 0, stream, a, nullptr, row_ptr, edge_src, edge_dst);
+    launch_radius<true>(a, items, nullptr, row_ptr, edge_src, edge_dst, stream);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
