@@ -142,12 +142,19 @@ struct ScoreArgs {
     float* ang_out; float* lin_out;    // (n_t,3)
 };
 
-constexpr int kScoreQB = 2;     // query nodes processed together (every weight load serves both, for both tensor products)
+constexpr int kScoreQB = 2;     // (pose, query node) rows processed together: every weight load serves all of them, for both tensor
+                                // products.  Large batches take 2 poses per CTA and 4 rows at a time (the kernel is then bound by the
+                                // L2 stream of the 218 KB of weights per CTA pass).
 
-__global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
-    pdl_wait(); pdl_launch();     // PDL: see common.cuh
-    extern __shared__ float sm[];
-    constexpr int QB = kScoreQB;
+constexpr int kScoreThreads = 384;   // 2 (NU) = 704 tasks in step 1 -> 2 rounds; 2 NY = 258 tasks in step 3 -> 1 round (256 threads: 3 and 2)
+
+// Persistent: min(n_t / pb, 148) CTAs; each stages the tensor-product weights of both products (2 x 70 KB) and the 1e linear
+// layers (2 x 24 KB) in shared memory ONCE -- by TMA bulk copies issued before the PDL wait, they are parameters -- and then
+// walks its poses: the per-pose chain of dependent L2 round trips (45 us at one pose per CTA) becomes shared-memory reads.
+template <int QB>
+__global__ void __launch_bounds__(kScoreThreads) score_tp_kernel(ScoreArgs a, int pb, int w_smem) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t wbar;
     const int M0 = a.irr.m0, M1 = a.irr.m1, M2 = a.irr.m2, F = a.irr.dim();
     const int D0 = M0 + M1 + M2, D1 = M0 + 3 * M1 + 2 * M2;   // 112, 192 channels
     const int NV = a.n_vec, NY = 1 + 4 * NV;
@@ -162,8 +169,8 @@ __global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
     float* sd0 = st + 2 * QB * TT;      // [2][QB][D0]
     float* sd1 = sd0 + 2 * QB * D0;     // [2][QB][3 D1]
     float* sy = sd1 + 2 * QB * 3 * D1;  // [2][QB][NY]
-    float* sres = sy + 2 * QB * NY;     // [n_q][2][3]
-    const int t = blockIdx.x, tid = threadIdx.x;
+    float* sres = sy + 2 * QB * NY;     // [pb n_q][2][3]
+    const int tid = threadIdx.x;
     // weight offsets (per path: [mul2][mul1], i.e. transposed blocks, see ScoreArgs)
     const int m1s[9] = {M0, M0, M1, M1, M1, M1, M2, M2, M2};
     const int m2s[9] = {M0, M1, M0, M1, M1, M2, M1, M2, M2};
@@ -172,13 +179,35 @@ __global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
     for (int p = 0; p < 9; ++p) { woff[p + 1] = woff[p] + m1s[p] * m2s[p]; uoff[p + 1] = uoff[p] + m1s[p]; }
     const int NU = uoff[9];             // (path, u) pairs
     const int boff[3] = {0, M0, M0 + 3 * M1};   // offsets of l blocks in a feature vector
+    // resident weights
+    const int nWd = woff[9], nWl1 = D1 * NV;
+    float* sw = sres + (((6 * pb * a.n_q) + 3) & ~3);
+    const float* Wd[2] = {a.Wd[0], a.Wd[1]};
+    const float* Wl1[2] = {a.Wl1[0], a.Wl1[1]};
+    if (w_smem) {
+        if (tid == 0) {
+            mbar_init(&wbar, 1);
+            mbar_init_fence();
+            mbar_expect_tx(&wbar, (uint32_t)(2 * (nWd + nWl1)) * 4u);
+            for (int i = 0; i < 2; ++i) {
+                bulk_g2s_chunked(sw + i * nWd, a.Wd[i], (uint32_t)nWd * 4u, &wbar);
+                bulk_g2s_chunked(sw + 2 * nWd + i * nWl1, a.Wl1[i], (uint32_t)nWl1 * 4u, &wbar);
+            }
+        }
+        for (int i = 0; i < 2; ++i) { Wd[i] = sw + i * nWd; Wl1[i] = sw + 2 * nWd + i * nWl1; }
+    }
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
+    if (w_smem) { __syncthreads(); mbar_wait(&wbar, 0); }
 
-    for (int q0 = 0; q0 < a.n_q; q0 += QB) {
-        const int nq = min(QB, a.n_q - q0);
+    for (int t0 = blockIdx.x * pb; t0 < a.n_t; t0 += gridDim.x * pb) {
+    const int np = min(pb, a.n_t - t0);
+    const int rows_total = np * a.n_q;  // (pose, query node) rows of this pass: consecutive nodes of qf_rot / key_f
+    for (int q0 = 0; q0 < rows_total; q0 += QB) {
+        const int nq = min(QB, rows_total - q0);
         __syncthreads();
         for (int i = tid; i < QB * F; i += blockDim.x) {
             const int qq = i / F, c = i % F;
-            const size_t node = (size_t)t * a.n_q + q0 + min(qq, nq - 1);
+            const size_t node = (size_t)t0 * a.n_q + q0 + min(qq, nq - 1);
             sa[i] = a.qf_rot[node * F + c]; sb[i] = a.key_f[node * F + c];
         }
         __syncthreads();
@@ -189,17 +218,32 @@ __global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
             int p = 0;
             while (r >= uoff[p + 1]) ++p;
             const int u = r - uoff[p], d2 = 2 * l2s[p] + 1, m1 = m1s[p], m2 = m2s[p];
-            const float* w = a.Wd[which] + woff[p] + u;
+            const float* w = Wd[which] + woff[p] + u;
             const float* b = sb + boff[l2s[p]];
             float acc[QB][5];
 #pragma unroll
             for (int qq = 0; qq < QB; ++qq)
 #pragma unroll
                 for (int j = 0; j < 5; ++j) acc[qq][j] = 0.f;
-            for (int v = 0; v < m2; v += 4) {          // every mul is a multiple of 4
+            // the chain of dependent L2 round trips is what this step costs: 8 weight loads in flight (4 for a tail; every mul
+            // is a multiple of 4)
+            int v = 0;
+            for (; v + 8 <= m2; v += 8) {
+                float wv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) wv[k] = w[(size_t)(v + k) * m1];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+                        for (int j = 0; j < 5; ++j)
+                            if (j < d2) acc[qq][j] = fmaf(wv[k], b[qq * F + (v + k) * d2 + j], acc[qq][j]);
+            }
+            for (; v < m2; v += 4) {
                 float wv[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) wv[k] = __ldg(w + (size_t)(v + k) * m1);
+                for (int k = 0; k < 4; ++k) wv[k] = w[(size_t)(v + k) * m1];
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -257,7 +301,17 @@ __global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
                 const float* W = a.Wl0[which] + o;
 #pragma unroll
                 for (int qq = 0; qq < QB; ++qq) acc[qq] = a.bl[which][o];
-                for (int r = 0; r < D0; r += 4) {      // D0 = 7 G / 2 is a multiple of 4 for G in (16, 32)
+                int r = 0;
+                for (; r + 8 <= D0; r += 8) {           // D0 = 7 G / 2 is a multiple of 8 for G in (16, 32)
+                    float wv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) wv[k] = __ldg(W + (size_t)(r + k) * (1 + NV));
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+#pragma unroll
+                        for (int qq = 0; qq < QB; ++qq) acc[qq] = fmaf(sd0[(which * QB + qq) * D0 + r + k], wv[k], acc[qq]);
+                }
+                for (; r < D0; r += 4) {
                     float wv[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) wv[k] = __ldg(W + (size_t)(r + k) * (1 + NV));
@@ -268,13 +322,23 @@ __global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
                 }
             } else {
                 const int c = (o - 1 - NV) / 3, k3 = (o - 1 - NV) % 3;
-                const float* W = a.Wl1[which] + c;
+                const float* W = Wl1[which] + c;
 #pragma unroll
                 for (int qq = 0; qq < QB; ++qq) acc[qq] = 0.f;
-                for (int r = 0; r < D1; r += 4) {
+                int r = 0;
+                for (; r + 8 <= D1; r += 8) {
+                    float wv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) wv[k] = W[(size_t)(r + k) * NV];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+#pragma unroll
+                        for (int qq = 0; qq < QB; ++qq) acc[qq] = fmaf(sd1[(which * QB + qq) * 3 * D1 + (r + k) * 3 + k3], wv[k], acc[qq]);
+                }
+                for (; r < D1; r += 4) {
                     float wv[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) wv[k] = __ldg(W + (size_t)(r + k) * NV);
+                    for (int k = 0; k < 4; ++k) wv[k] = W[(size_t)(r + k) * NV];
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -297,14 +361,15 @@ __global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
         }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < np) {
+        const int t = t0 + tid;
         const float* T = a.Ts + (size_t)t * 7;
         const float qinv[4] = {T[0], -T[1], -T[2], -T[3]};
         float lin[3] = {0.f, 0.f, 0.f}, ang[3] = {0.f, 0.f, 0.f};
         for (int q = 0; q < a.n_q; ++q) {
             float l[3], s[3];
-            quat_apply<float>(qinv, sres + (q * 2 + 0) * 3, l);
-            quat_apply<float>(qinv, sres + (q * 2 + 1) * 3, s);
+            quat_apply<float>(qinv, sres + ((tid * a.n_q + q) * 2 + 0) * 3, l);
+            quat_apply<float>(qinv, sres + ((tid * a.n_q + q) * 2 + 1) * 3, s);
             const float px = a.qx[3 * q] / a.lin_mult, py = a.qx[3 * q + 1] / a.lin_mult, pz = a.qx[3 * q + 2] / a.lin_mult;
             const float ox = py * l[2] - pz * l[1], oy = pz * l[0] - px * l[2], oz = px * l[1] - py * l[0];
             const float w = a.qw[q];
@@ -313,6 +378,7 @@ __global__ void __launch_bounds__(256) score_tp_kernel(ScoreArgs a) {
         }
         for (int i = 0; i < 3; ++i) { a.lin_out[(size_t)t * 3 + i] = lin[i]; a.ang_out[(size_t)t * 3 + i] = ang[i]; }
     }
+    }   // poses of this CTA
 }
 
 // ---------------------------------------------------------------------------
@@ -471,12 +537,23 @@ extern "C" int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, cons
     const int M0 = a.irr.m0, M1 = a.irr.m1, M2 = a.irr.m2, F = a.irr.dim();
     const int tt = M0 + 3 * M0 + M1 + 3 * M1 + 3 * M1 + 5 * M1 + 3 * M2 + 5 * M2 + 5 * M2;
     const int D0 = M0 + M1 + M2, D1 = M0 + 3 * M1 + 2 * M2;
-    const size_t smem = (size_t)(kScoreQB * (2 * F + 2 * (tt + D0 + 3 * D1 + 1 + 4 * n_vec)) + 6 * n_q) * sizeof(float);
     if ((M0 % 4) || (M1 % 4) || (M2 % 4) || (D0 % 4) || (D1 % 4)) return DEDF_ERR_UNSUPPORTED;
-    if (smem > 96 * 1024) return DEDF_ERR_UNSUPPORTED;
+    const int pb = 1, qb = kScoreQB;
+    const size_t act = (size_t)(qb * (2 * F + 2 * (tt + D0 + 3 * D1 + 1 + 4 * n_vec)) + ((6 * pb * n_q + 3) & ~3)) * sizeof(float);
+    const int nWd = M0 * M0 + M0 * M1 + M1 * M0 + 2 * M1 * M1 + M1 * M2 + M2 * M1 + 2 * M2 * M2;
+    const size_t wbytes = (size_t)2 * (nWd + D1 * n_vec) * sizeof(float);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    // Up to two poses per SM: persistent CTAs with the weights resident in shared memory (37 us vs 70 us at 128 poses).
+    // Larger batches: one CTA per pose, weights through L1/L2, three CTAs per SM hide each other's latency (139 us at 1024
+    // poses; the resident variant runs one 12-warp CTA per SM and takes 181 us).
+    const bool w_smem = n_t <= 2 * kNumSMs && act + wbytes <= 226 * 1024 && al16(Wd[0]) && al16(Wd[1]) && al16(Wl1[0]) && al16(Wl1[1]) &&
+                        (nWd % 4 == 0) && ((D1 * n_vec) % 4 == 0) && !getenv("DEDF_NO_SMEM_SCORE");
+    const size_t smem = act + (w_smem ? wbytes : 0);
+    if (smem > 226 * 1024) return DEDF_ERR_UNSUPPORTED;
     static bool done = false;
-    if (!done) { cudaFuncSetAttribute(score_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); done = true; }
-    launch_pdl(score_tp_kernel, dim3(n_t), dim3(256), smem, stream, a);
+    if (!done) { cudaFuncSetAttribute(score_tp_kernel<kScoreQB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); done = true; }
+    if (w_smem) launch_pdl(score_tp_kernel<kScoreQB>, dim3(grid_for(n_t, pb, kNumSMs)), dim3(kScoreThreads), smem, stream, a, pb, 1);
+    else launch_pdl(score_tp_kernel<kScoreQB>, dim3((n_t + pb - 1) / pb), dim3(256), smem, stream, a, pb, 0);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

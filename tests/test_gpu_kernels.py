@@ -404,13 +404,15 @@ def test_time_embed(cuda):
             assert_close(rows[s], ref, TOL, f"time rows scale {s}")
 
 
-def test_score_tp(cuda):
+@pytest.mark.parametrize("nT,nQ", [(9, 3), (1, 1), (593, 2), (601, 1), (592, 3)])
+def test_score_tp(cuda, nT, nQ):
+    """Small batches run one pose per CTA, large ones (>= 4 waves) two poses per CTA and 4 (pose, query) rows per weight
+    pass: odd pose counts, 1 / 2 / 3 query nodes."""
     from diffusion_edf_b200 import ops
     from diffusion_edf_b200.score_head import _ScoreTP
     from diffusion_edf_b200.irreps import Irreps
     torch.manual_seed(8)
     irr = OIrreps(IRR[32])
-    nT, nQ = 9, 3
     pres = OIrreps("1x0e") + OIrreps("32x1e")
     o_lin = ON.SeparableFCTP(irr, irr, pres, None, use_activation=True, internal_weights=True)
     o_ang = ON.SeparableFCTP(irr, irr, pres, None, use_activation=True, internal_weights=True)
