@@ -269,6 +269,35 @@ def test_sample_graph_replay_equals_eager_loop(cuda):
     assert (eager - graphed).abs().max() < 1e-9
 
 
+def test_sample_full_size_pose_independence(cuda):
+    """BASELINE config C3 at full width (10k-point scene, 1024 seeds; a few steps): poses are independent given the scene
+    field (score_head.py:153-209 is row-wise in nT), so denoising a slice of the seeds alone must give the slice of the full
+    run -- the property pose sharding over ranks (parallel.sharded_sample) rests on.  Zero temperature (each rank draws its
+    own noise stream); also checks the trajectory layout and that every pose stays a unit quaternion."""
+    from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel
+    from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs
+    torch.manual_seed(0)
+    model = MultiscaleScoreModel(**model_kwargs(), deterministic=True).eval().to(cuda)
+    model.requires_grad_(False)
+    x, rgb = make_scene(10_000, seed=0)
+    T0, _ = make_poses(1024, x, seed=0)
+    kw = dict(diffusion_schedules=[[1.0, 0.5]], N_steps=[6], timesteps=[0.04], temperatures=[0.0], log_t_schedule=True,
+              time_exponent_temp=1.0, time_exponent_alpha=0.5)
+    with torch.no_grad():
+        keys = model.get_key_pcd_multiscale(FeaturedPoints(x.to(cuda), rgb.to(cuda), torch.zeros(len(x), dtype=torch.long, device=cuda)))
+        q = model.get_query_pcd(FeaturedPoints(torch.zeros(8, 3, device=cuda), torch.zeros(8, 3, device=cuda), torch.zeros(8, dtype=torch.long, device=cuda)))
+        full = model.sample(T0.to(cuda), keys, q, **kw)
+        part = model.sample(T0[512:640].contiguous().to(cuda), keys, q, **kw)
+        again = model.sample(T0.to(cuda), keys, q, **kw)
+    assert full.shape == (6 + 2, 1024, 7) and full.dtype == torch.float64 and torch.isfinite(full).all()
+    assert torch.equal(full, again), "the denoise loop must be reproducible run to run"
+    assert (full[:, :, :4].norm(dim=-1) - 1).abs().max() < 1e-6      # the seeds themselves are fp32-normalised
+    moved = (full[-1, :, 4:] - full[0, :, 4:]).norm(dim=-1)
+    assert moved.max() > 1e-3, "the poses did not move"
+    err = (full[:, 512:640] - part).abs().max()
+    assert err < 1e-6 * full[:, :, 4:].abs().max(), f"slice of the full run vs the slice alone: {float(err):.3e}"
+
+
 def test_place_model_with_keypoint_extractor(cuda):
     """the place configs' query model (second UNet on the grasp cloud + bbox + FPS + two tensor fields without
     context embedding + weight head) and a score head with many query points."""
