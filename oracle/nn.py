@@ -103,7 +103,7 @@ class TensorProduct(nn.Module):
             (m1, l1, _), (m2, l2, _), (mo, lo, _) = self.in1[i1], self.in2[i2], self.out[io]
             a = x1[:, s1[i1]].reshape(N, m1, 2 * l1 + 1)
             b = x2[:, s2[i2]].reshape(N, m2, 2 * l2 + 1)
-            C = wigner_3j(l1, l2, lo).to(x1.dtype) * math.sqrt(2 * lo + 1)
+            C = wigner_3j(l1, l2, lo).to(device=x1.device, dtype=x1.dtype) * math.sqrt(2 * lo + 1)
             t = torch.einsum("zui,zvj,ijk->zuvk", a, b, C)
             z = "z" if per_sample else ""
             if mode == "uvu":

@@ -160,5 +160,5 @@ def z_rot_mat(angle: torch.Tensor, l: int) -> torch.Tensor:
 
 def wigner_D_euler(l: int, alpha, beta, gamma) -> torch.Tensor:
     """wigner.py:44-81 (Xa @ J @ Xb @ J @ Xc)."""
-    J = J_matrix(l).to(alpha.dtype)
+    J = J_matrix(l).to(device=alpha.device, dtype=alpha.dtype)
     return z_rot_mat(alpha, l) @ J @ z_rot_mat(beta, l) @ J @ z_rot_mat(gamma, l)
