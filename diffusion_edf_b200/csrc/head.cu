@@ -148,11 +148,52 @@ constexpr int kScoreQB = 2;     // (pose, query node) rows processed together: e
 
 constexpr int kScoreThreads = 384;   // 2 (NU) = 704 tasks in step 1 -> 2 rounds; 2 NY = 258 tasks in step 3 -> 1 round (256 threads: 3 and 2)
 
+// step 1 of score_tp for one (path, u): t[qq][j] += sum_v w[v] b[qq][v][j], KB consecutive v per call.  D2 = 2 l2 + 1 is a
+// compile-time constant (no predicated-off FMAs) and the KB x D2 operand values of a row are contiguous in shared memory: they
+// are fetched as float4s (one LDS per four FMAs instead of one per FMA).  Same summation order as a plain loop over v.
+template <int D2, int QB, int KB>
+__device__ __forceinline__ void score_s1_batch(const float* __restrict__ w, int m1, const float* __restrict__ b, int F, float (&acc)[QB][D2]) {
+    float wv[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) wv[k] = w[(size_t)k * m1];
+#pragma unroll
+    for (int qq = 0; qq < QB; ++qq) {
+        float bb[KB * D2];
+        const float4* bp = reinterpret_cast<const float4*>(b + qq * F);
+#pragma unroll
+        for (int x = 0; x < KB * D2 / 4; ++x) {
+            const float4 t = bp[x];
+            bb[4 * x] = t.x; bb[4 * x + 1] = t.y; bb[4 * x + 2] = t.z; bb[4 * x + 3] = t.w;
+        }
+#pragma unroll
+        for (int k = 0; k < KB; ++k)
+#pragma unroll
+            for (int j = 0; j < D2; ++j) acc[qq][j] = fmaf(wv[k], bb[k * D2 + j], acc[qq][j]);
+    }
+}
+template <int D2, int QB>
+__device__ __forceinline__ void score_s1_path(const float* __restrict__ w, int m1, int m2, const float* __restrict__ b, int F,
+                                              float* __restrict__ tout, int TT) {
+    float acc[QB][D2];
+#pragma unroll
+    for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+        for (int j = 0; j < D2; ++j) acc[qq][j] = 0.f;
+    // the chain of dependent weight loads is what a small batch pays for: 8 in flight (4 for a tail; every mul is a multiple of 4)
+    int v = 0;
+    for (; v + 8 <= m2; v += 8) score_s1_batch<D2, QB, 8>(w + (size_t)v * m1, m1, b + v * D2, F, acc);
+    for (; v < m2; v += 4) score_s1_batch<D2, QB, 4>(w + (size_t)v * m1, m1, b + v * D2, F, acc);
+#pragma unroll
+    for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+        for (int j = 0; j < D2; ++j) tout[qq * TT + j] = acc[qq][j];
+}
+
 // Persistent: min(n_t / pb, 148) CTAs; each stages the tensor-product weights of both products (2 x 70 KB) and the 1e linear
 // layers (2 x 24 KB) in shared memory ONCE -- by TMA bulk copies issued before the PDL wait, they are parameters -- and then
 // walks its poses: the per-pose chain of dependent L2 round trips (45 us at one pose per CTA) becomes shared-memory reads.
 template <int QB>
-__global__ void __launch_bounds__(kScoreThreads) score_tp_kernel(ScoreArgs a, int pb, int w_smem) {
+__global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kernel(ScoreArgs a, int pb, int w_smem) {
     extern __shared__ __align__(16) float sm[];
     __shared__ __align__(8) uint64_t wbar;
     const int M0 = a.irr.m0, M1 = a.irr.m1, M2 = a.irr.m2, F = a.irr.dim();
@@ -167,9 +208,9 @@ __global__ void __launch_bounds__(kScoreThreads) score_tp_kernel(ScoreArgs a, in
     float* sb = sa + QB * F;            // [QB][F]
     float* st = sb + QB * F;            // [2][QB][TT]
     float* sd0 = st + 2 * QB * TT;      // [2][QB][D0]
-    float* sd1 = sd0 + 2 * QB * D0;     // [2][QB][3 D1]
-    float* sy = sd1 + 2 * QB * 3 * D1;  // [2][QB][NY]
-    float* sres = sy + 2 * QB * NY;     // [pb n_q][2][3]
+    float* sd1 = sd0 + 2 * QB * D0;     // [2][QB][3][D1]  planar in the vector component: step 3 reads 4 consecutive channels per LDS
+    float* sy = st;                     // [2][QB][NY]     aliases the t buffers (dead after step 2; NY <= TT checked by the launcher)
+    float* sres = sd1 + 2 * QB * 3 * D1;  // [pb n_q][2][3]
     const int tid = threadIdx.x;
     // weight offsets (per path: [mul2][mul1], i.e. transposed blocks, see ScoreArgs)
     const int m1s[9] = {M0, M0, M1, M1, M1, M1, M2, M2, M2};
@@ -217,46 +258,13 @@ __global__ void __launch_bounds__(kScoreThreads) score_tp_kernel(ScoreArgs a, in
             const int which = i / NU, r = i % NU;
             int p = 0;
             while (r >= uoff[p + 1]) ++p;
-            const int u = r - uoff[p], d2 = 2 * l2s[p] + 1, m1 = m1s[p], m2 = m2s[p];
+            const int u = r - uoff[p], l2 = l2s[p];
             const float* w = Wd[which] + woff[p] + u;
-            const float* b = sb + boff[l2s[p]];
-            float acc[QB][5];
-#pragma unroll
-            for (int qq = 0; qq < QB; ++qq)
-#pragma unroll
-                for (int j = 0; j < 5; ++j) acc[qq][j] = 0.f;
-            // the chain of dependent L2 round trips is what this step costs: 8 weight loads in flight (4 for a tail; every mul
-            // is a multiple of 4)
-            int v = 0;
-            for (; v + 8 <= m2; v += 8) {
-                float wv[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) wv[k] = w[(size_t)(v + k) * m1];
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-#pragma unroll
-                    for (int qq = 0; qq < QB; ++qq)
-#pragma unroll
-                        for (int j = 0; j < 5; ++j)
-                            if (j < d2) acc[qq][j] = fmaf(wv[k], b[qq * F + (v + k) * d2 + j], acc[qq][j]);
-            }
-            for (; v < m2; v += 4) {
-                float wv[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) wv[k] = w[(size_t)(v + k) * m1];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int qq = 0; qq < QB; ++qq)
-#pragma unroll
-                        for (int j = 0; j < 5; ++j)
-                            if (j < d2) acc[qq][j] = fmaf(wv[k], b[qq * F + (v + k) * d2 + j], acc[qq][j]);
-            }
-#pragma unroll
-            for (int qq = 0; qq < QB; ++qq)
-#pragma unroll
-                for (int j = 0; j < 5; ++j)
-                    if (j < d2) st[(which * QB + qq) * TT + toff[p] + u * d2 + j] = acc[qq][j];
+            const float* b = sb + boff[l2];
+            float* tout = st + (size_t)(which * QB) * TT + toff[p] + u * (2 * l2 + 1);
+            if (l2 == 0) score_s1_path<1, QB>(w, m1s[p], m2s[p], b, F, tout, TT);
+            else if (l2 == 1) score_s1_path<3, QB>(w, m1s[p], m2s[p], b, F, tout, TT);
+            else score_s1_path<5, QB>(w, m1s[p], m2s[p], b, F, tout, TT);
         }
         __syncthreads();
         // step 2: d[p][u][:] = cg(a[u], t_p[u])  ->  sd0 [112] , sd1 [192][3] in i_out order
@@ -277,19 +285,19 @@ __global__ void __launch_bounds__(kScoreThreads) score_tp_kernel(ScoreArgs a, in
             switch (p) {
                 case 0: d0[u] = xa[u] * tt[toff[0] + u]; break;
                 case 1: { const float x = xa[u]; const float* y = tt + toff[1] + 3 * u;
-                          d1[u * 3 + 0] = x * y[0]; d1[u * 3 + 1] = x * y[1]; d1[u * 3 + 2] = x * y[2]; } break;
+                          d1[u] = x * y[0]; d1[D1 + u] = x * y[1]; d1[2 * D1 + u] = x * y[2]; } break;
                 case 2: { const float* x = xa + boff[1] + 3 * u; const float y = tt[toff[2] + u];
-                          float* d = d1 + (M0 + u) * 3; d[0] = x[0] * y; d[1] = x[1] * y; d[2] = x[2] * y; } break;
+                          float* d = d1 + M0 + u; d[0] = x[0] * y; d[D1] = x[1] * y; d[2 * D1] = x[2] * y; } break;
                 case 3: cg_110(xa + boff[1] + 3 * u, tt + toff[3] + 3 * u, o); d0[M0 + u] = o[0]; break;
                 case 4: { cg_111(xa + boff[1] + 3 * u, tt + toff[4] + 3 * u, o);
-                          float* d = d1 + (M0 + M1 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+                          float* d = d1 + M0 + M1 + u; d[0] = o[0]; d[D1] = o[1]; d[2 * D1] = o[2]; } break;
                 case 5: { cg_121(xa + boff[1] + 3 * u, tt + toff[5] + 5 * u, o);
-                          float* d = d1 + (M0 + 2 * M1 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+                          float* d = d1 + M0 + 2 * M1 + u; d[0] = o[0]; d[D1] = o[1]; d[2 * D1] = o[2]; } break;
                 case 6: { cg_211(xa + boff[2] + 5 * u, tt + toff[6] + 3 * u, o);
-                          float* d = d1 + (M0 + 3 * M1 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+                          float* d = d1 + M0 + 3 * M1 + u; d[0] = o[0]; d[D1] = o[1]; d[2 * D1] = o[2]; } break;
                 case 7: cg_220(xa + boff[2] + 5 * u, tt + toff[7] + 5 * u, o); d0[M0 + M1 + u] = o[0]; break;
                 default: { cg_221(xa + boff[2] + 5 * u, tt + toff[8] + 5 * u, o);
-                           float* d = d1 + (M0 + 3 * M1 + M2 + u) * 3; d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; } break;
+                           float* d = d1 + M0 + 3 * M1 + M2 + u; d[0] = o[0]; d[D1] = o[1]; d[2 * D1] = o[2]; } break;
             }
         }
         __syncthreads();
@@ -297,52 +305,41 @@ __global__ void __launch_bounds__(kScoreThreads) score_tp_kernel(ScoreArgs a, in
         for (int i = tid; i < 2 * NY; i += blockDim.x) {
             const int which = i / NY, o = i % NY;
             float acc[QB];
-            if (o < 1 + NV) {
-                const float* W = a.Wl0[which] + o;
+            const bool scalar = o < 1 + NV;
+            const int k3 = scalar ? 0 : (o - 1 - NV) % 3;
+            const int K = scalar ? D0 : D1;
+            const int ldw = scalar ? (1 + NV) : NV;
+            const float* W = scalar ? (a.Wl0[which] + o) : (Wl1[which] + (o - 1 - NV) / 3);
+            // activations of row qq: sd0[wq][D0] or the k3 plane of sd1[wq][3][D1]; 4 consecutive channels per LDS
+            const float* S = scalar ? (sd0 + (size_t)(which * QB) * D0) : (sd1 + (size_t)(which * QB) * 3 * D1 + k3 * D1);
+            const int lds = scalar ? D0 : 3 * D1;
 #pragma unroll
-                for (int qq = 0; qq < QB; ++qq) acc[qq] = a.bl[which][o];
-                int r = 0;
-                for (; r + 8 <= D0; r += 8) {           // D0 = 7 G / 2 is a multiple of 8 for G in (16, 32)
-                    float wv[8];
+            for (int qq = 0; qq < QB; ++qq) acc[qq] = scalar ? a.bl[which][o] : 0.f;
+            int r = 0;
+            for (; r + 8 <= K; r += 8) {
+                float wv[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) wv[k] = __ldg(W + (size_t)(r + k) * (1 + NV));
+                for (int k = 0; k < 8; ++k) wv[k] = W[(size_t)(r + k) * ldw];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-#pragma unroll
-                        for (int qq = 0; qq < QB; ++qq) acc[qq] = fmaf(sd0[(which * QB + qq) * D0 + r + k], wv[k], acc[qq]);
+                for (int qq = 0; qq < QB; ++qq) {
+                    const float4 s0 = *reinterpret_cast<const float4*>(S + qq * lds + r);
+                    const float4 s1 = *reinterpret_cast<const float4*>(S + qq * lds + r + 4);
+                    float t = acc[qq];
+                    t = fmaf(s0.x, wv[0], t); t = fmaf(s0.y, wv[1], t); t = fmaf(s0.z, wv[2], t); t = fmaf(s0.w, wv[3], t);
+                    t = fmaf(s1.x, wv[4], t); t = fmaf(s1.y, wv[5], t); t = fmaf(s1.z, wv[6], t); t = fmaf(s1.w, wv[7], t);
+                    acc[qq] = t;
                 }
-                for (; r < D0; r += 4) {
-                    float wv[4];
+            }
+            for (; r < K; r += 4) {
+                float wv[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) wv[k] = __ldg(W + (size_t)(r + k) * (1 + NV));
+                for (int k = 0; k < 4; ++k) wv[k] = W[(size_t)(r + k) * ldw];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-#pragma unroll
-                        for (int qq = 0; qq < QB; ++qq) acc[qq] = fmaf(sd0[(which * QB + qq) * D0 + r + k], wv[k], acc[qq]);
-                }
-            } else {
-                const int c = (o - 1 - NV) / 3, k3 = (o - 1 - NV) % 3;
-                const float* W = Wl1[which] + c;
-#pragma unroll
-                for (int qq = 0; qq < QB; ++qq) acc[qq] = 0.f;
-                int r = 0;
-                for (; r + 8 <= D1; r += 8) {
-                    float wv[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) wv[k] = W[(size_t)(r + k) * NV];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-#pragma unroll
-                        for (int qq = 0; qq < QB; ++qq) acc[qq] = fmaf(sd1[(which * QB + qq) * 3 * D1 + (r + k) * 3 + k3], wv[k], acc[qq]);
-                }
-                for (; r < D1; r += 4) {
-                    float wv[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) wv[k] = W[(size_t)(r + k) * NV];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-#pragma unroll
-                        for (int qq = 0; qq < QB; ++qq) acc[qq] = fmaf(sd1[(which * QB + qq) * 3 * D1 + (r + k) * 3 + k3], wv[k], acc[qq]);
+                for (int qq = 0; qq < QB; ++qq) {
+                    const float4 s0 = *reinterpret_cast<const float4*>(S + qq * lds + r);
+                    float t = acc[qq];
+                    t = fmaf(s0.x, wv[0], t); t = fmaf(s0.y, wv[1], t); t = fmaf(s0.z, wv[2], t); t = fmaf(s0.w, wv[3], t);
+                    acc[qq] = t;
                 }
             }
 #pragma unroll
@@ -539,7 +536,8 @@ extern "C" int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, cons
     const int D0 = M0 + M1 + M2, D1 = M0 + 3 * M1 + 2 * M2;
     if ((M0 % 4) || (M1 % 4) || (M2 % 4) || (D0 % 4) || (D1 % 4)) return DEDF_ERR_UNSUPPORTED;
     const int pb = 1, qb = kScoreQB;
-    const size_t act = (size_t)(qb * (2 * F + 2 * (tt + D0 + 3 * D1 + 1 + 4 * n_vec)) + ((6 * pb * n_q + 3) & ~3)) * sizeof(float);
+    if (1 + 4 * n_vec > tt) return DEDF_ERR_UNSUPPORTED;      // the linear outputs reuse the t buffers
+    const size_t act = (size_t)(qb * (2 * F + 2 * (tt + D0 + 3 * D1)) + ((6 * pb * n_q + 3) & ~3)) * sizeof(float);
     const int nWd = M0 * M0 + M0 * M1 + M1 * M0 + 2 * M1 * M1 + M1 * M2 + M2 * M1 + 2 * M2 * M2;
     const size_t wbytes = (size_t)2 * (nWd + D1 * n_vec) * sizeof(float);
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -548,6 +546,20 @@ extern "C" int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, cons
     // poses; the resident variant runs one 12-warp CTA per SM and takes 181 us).
     const bool w_smem = n_t <= 2 * kNumSMs && act + wbytes <= 226 * 1024 && al16(Wd[0]) && al16(Wd[1]) && al16(Wl1[0]) && al16(Wl1[1]) &&
                         (nWd % 4 == 0) && ((D1 * n_vec) % 4 == 0) && !getenv("DEDF_NO_SMEM_SCORE");
+    // More than two poses per SM: 8 (pose, query node) rows per weight pass.  Every weight load then serves 8 rows of both tensor
+    // products, so the L2 stream of the 218 KB of weights -- what bounds the one-pose-per-CTA form -- shrinks 4x.
+    if (n_t > 2 * kNumSMs && !getenv("DEDF_SCORE_QB2")) {
+        constexpr int QB8 = 8;
+        const int pb8 = QB8 / n_q > 1 ? QB8 / n_q : 1;
+        const size_t act8 = (size_t)(QB8 * (2 * F + 2 * (tt + D0 + 3 * D1)) + ((6 * pb8 * n_q + 3) & ~3)) * sizeof(float);
+        if (act8 <= 226 * 1024) {
+            static bool done8 = false;
+            if (!done8) { cudaFuncSetAttribute(score_tp_kernel<QB8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); done8 = true; }
+            launch_pdl(score_tp_kernel<QB8>, dim3((n_t + pb8 - 1) / pb8), dim3(kScoreThreads), act8, stream, a, pb8, 0);
+            DEDF_CHECK_LAUNCH();
+            return DEDF_OK;
+        }
+    }
     const size_t smem = act + (w_smem ? wbytes : 0);
     if (smem > 226 * 1024) return DEDF_ERR_UNSUPPORTED;
     static bool done = false;
