@@ -270,17 +270,19 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
         // step 2: d[p][u][:] = cg(a[u], t_p[u])  ->  sd0 [112] , sd1 [192][3] in i_out order
         //   lo=0 block: [p0 (M0) | p3 (M1) | p7 (M2)] ; lo=1 block: [p1 (M0) | p2 (M1) | p4 (M1) | p5 (M1) | p6 (M2) | p8 (M2)]
         const int ntask = 2 * M0 + 4 * M1 + 3 * M2;
-        for (int i = tid; i < 2 * QB * ntask; i += blockDim.x) {
-            const int wq = i / ntask, r = i % ntask;          // wq = which * QB + qq
-            const float* xa = sa + (wq % QB) * F;
-            const float* tt = st + wq * TT;
-            float* d0 = sd0 + wq * D0;
-            float* d1 = sd1 + wq * 3 * D1;
+        // one thread per (path, u): the task is decoded once and applied to the 2 QB (product, row) copies
+        for (int r = tid; r < ntask; r += blockDim.x) {
             int p, u;
             if (r < M0) { p = 0; u = r; }
             else if (r < 2 * M0) { p = 1; u = r - M0; }
             else if (r < 2 * M0 + 4 * M1) { p = 2 + (r - 2 * M0) / M1; u = (r - 2 * M0) % M1; }
             else { p = 6 + (r - 2 * M0 - 4 * M1) / M2; u = (r - 2 * M0 - 4 * M1) % M2; }
+#pragma unroll 2
+            for (int wq = 0; wq < 2 * QB; ++wq) {             // wq = which * QB + qq
+            const float* xa = sa + (wq % QB) * F;
+            const float* tt = st + wq * TT;
+            float* d0 = sd0 + wq * D0;
+            float* d1 = sd1 + wq * 3 * D1;
             float o[3];
             switch (p) {
                 case 0: d0[u] = xa[u] * tt[toff[0] + u]; break;
@@ -298,6 +300,7 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
                 case 7: cg_220(xa + boff[2] + 5 * u, tt + toff[7] + 5 * u, o); d0[M0 + M1 + u] = o[0]; break;
                 default: { cg_221(xa + boff[2] + 5 * u, tt + toff[8] + 5 * u, o);
                            float* d = d1 + M0 + 3 * M1 + M2 + u; d[0] = o[0]; d[D1] = o[1]; d[2 * D1] = o[2]; } break;
+            }
             }
         }
         __syncthreads();
@@ -347,14 +350,17 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
         }
         __syncthreads();
         // step 4: gate, mean over the NV vectors (drop the scalar)
-        if (tid < 2 * QB * 3) {
-            const int wq = tid / 3, k3 = tid % 3, which = wq / QB, qq = wq % QB;
-            if (qq < nq) {
-                const float* y = sy + wq * NY;
-                float s = 0.f;
-                for (int c = 0; c < NV; ++c) s += y[1 + NV + 3 * c + k3] * (kCSigmoid * sigmoidf_(y[1 + c]));
-                sres[((q0 + qq) * 2 + which) * 3 + k3] = s / (float)NV;
-            }
+        // 8 lanes per (product, row, component), each NV / 8 vectors apart, folded with shuffles (2 QB 3 8 is a multiple of 32:
+        // whole warps enter or skip the loop)
+        for (int i = tid; i < 2 * QB * 3 * 8; i += blockDim.x) {
+            const int part = i & 7, o3 = i >> 3, wq = o3 / 3, k3 = o3 % 3, which = wq / QB, qq = wq % QB;
+            const float* y = sy + wq * NY;
+            float s = 0.f;
+            for (int c = part; c < NV; c += 8) s += y[1 + NV + 3 * c + k3] * (kCSigmoid * sigmoidf_(y[1 + c]));
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (part == 0 && qq < nq) sres[((q0 + qq) * 2 + which) * 3 + k3] = s / (float)NV;
         }
     }
     __syncthreads();
