@@ -260,10 +260,27 @@ radius_kernel(RadiusArgs a, int* __restrict__ counts, const int* __restrict__ ro
     const float* xs = a.x_src;
     const int* s_b = nullptr;
     if (SMEM) {
-        for (int i = threadIdx.x; i < 3 * n_total; i += blockDim.x) s_radius[i] = a.x_src[i];
+        // Batches of independent loads, then the stores: written as one load + one store per iteration the loop is a chain of
+        // ~30 serialised L2 round trips per thread (the stores cannot be hoisted over possibly aliasing loads), which was two
+        // thirds of this kernel's 31 us at 128 poses (ncu: long-scoreboard stalls on the STS, profiles/r1_s5_radius_head128_ncu.txt).
+        constexpr int UX = 16, UB = 8;
+        const int n3 = 3 * n_total, bd = blockDim.x;
+        for (int i0 = threadIdx.x; i0 < n3; i0 += bd * UX) {
+            float v[UX];
+#pragma unroll
+            for (int k = 0; k < UX; ++k) { const int i = i0 + k * bd; v[k] = (i < n3) ? __ldg(a.x_src + i) : 0.f; }
+#pragma unroll
+            for (int k = 0; k < UX; ++k) { const int i = i0 + k * bd; if (i < n3) s_radius[i] = v[k]; }
+        }
         if (a.b_src) {
-            int* sb = reinterpret_cast<int*>(s_radius + 3 * n_total);
-            for (int i = threadIdx.x; i < n_total; i += blockDim.x) sb[i] = (int)a.b_src[i];
+            int* sb = reinterpret_cast<int*>(s_radius + n3);
+            for (int i0 = threadIdx.x; i0 < n_total; i0 += bd * UB) {
+                long long v[UB];
+#pragma unroll
+                for (int k = 0; k < UB; ++k) { const int i = i0 + k * bd; v[k] = (i < n_total) ? __ldg(a.b_src + i) : 0ll; }
+#pragma unroll
+                for (int k = 0; k < UB; ++k) { const int i = i0 + k * bd; if (i < n_total) sb[i] = (int)v[k]; }
+            }
             s_b = sb;
         }
         __syncthreads();
