@@ -47,11 +47,18 @@ __global__ void __launch_bounds__(128) time_embed_kernel(TimeArgs a) {
         enc[i] = (i < half) ? sinf(arg) : cosf(arg);
     }
     __syncthreads();
-    // GEMVs: the weight loads of a column are independent of the accumulation chain; 8 of them are kept in flight
+    // GEMVs: the weight loads of a column are independent of the accumulation chain; 16 of them are kept in flight
     // (the launch is a handful of CTAs whose time is pure load latency otherwise)
     auto gemv = [&](const float* __restrict__ W, const float* __restrict__ bias, const float* x, int K, int N, int o) {
         float acc0 = bias[o], acc1 = 0.f;
         int i = 0;
+        for (; i + 16 <= K; i += 16) {      // 16 in flight: the three layers are 32 + 16 + 8 dependent round trips at 8
+            float w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = __ldg(W + (size_t)(i + j) * N + o);
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) { acc0 = fmaf(x[i + j], w[j], acc0); acc1 = fmaf(x[i + j + 1], w[j + 1], acc1); }
+        }
         for (; i + 8 <= K; i += 8) {
             float w[8];
 #pragma unroll
