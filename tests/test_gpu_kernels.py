@@ -1,6 +1,7 @@
 """Per-kernel parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
 Tolerance: 1e-4 relative (max |a-b| / max |b|), the bound BASELINE.json's north_star states for fp32."""
 import math
+import os
 
 import pytest
 import torch
@@ -235,6 +236,48 @@ def test_value_reduce_multisegment(cuda, G):
             val = ops.row_scale(val, pc, pga.irreps_emb.m)
         old = ops.segment_softmax_reduce(csr, logit.to(cuda), val, pga.irreps_emb.m)
         assert_close(out, old, TOL, f"value_reduce vs tp_lin+softmax (post={use_post})")
+
+
+@pytest.mark.skipif(os.environ.get("DEDF_EXPERIMENTAL") != "1", reason="experimental kernel, not yet run on a GPU (DESIGN 12); set DEDF_EXPERIMENTAL=1")
+@pytest.mark.parametrize("G", [32, 16])
+def test_value_reduce_split_experimental(cuda, G):
+    """value_reduce_split_kernel (DEDF_VR_SPLIT=1: the warp pair of a channel group splits the 15 CG paths instead of the head
+    pairs) against the default kernel on a ragged multi-segment graph: same per-lane accumulation order and the same fold
+    order per output, so the results should agree to the last bits (the bound below is loose on purpose)."""
+    from diffusion_edf_b200 import layers, ops
+    gen = torch.Generator().manual_seed(70 + G)
+    torch.manual_seed(70 + G)
+    F = OIrreps(IRR[G]).dim
+    n_dst, n_seg = 37, 4
+    deg = torch.poisson(torch.full((n_seg, n_dst), 9.0), generator=gen).long()
+    deg[:, 0] = 0
+    deg[1, 2] = 150
+    deg[:, 3] = torch.tensor([64, 0, 64, 0])
+    flat = deg.reshape(-1)
+    row_ptr = torch.zeros(n_seg * n_dst + 1, dtype=torch.long)
+    row_ptr[1:] = flat.cumsum(0)
+    E = int(row_ptr[-1])
+    ed = torch.arange(n_dst).repeat(n_seg).repeat_interleave(flat)
+    es = torch.randint(0, 50, (E,), generator=gen)
+    sh, _ = _random_sh(E, gen)
+    v = torch.randn(E, F, generator=gen).to(cuda)
+    logit = (torch.randn(E, 4, generator=gen) * 3).to(cuda)
+    pga = layers.GraphAttention(IRR[G], IRR[G], [32, 16, 16], 4)
+    with torch.no_grad():
+        for prm in pga.parameters():
+            prm.uniform_(-0.5, 0.5)
+    pga = pga.to(cuda)
+    p = pga.packed()
+    rp = row_ptr.int().to(cuda)
+    csr = ops.Csr(rp, es.int().to(cuda), ed.int().to(cuda), rp[-1:], E, n_dst, n_seg)
+    ref = ops.value_reduce(G, csr, v, sh.to(cuda), logit, None, p["wv"], p["V0"], p["V1"], p["V2"], p["vb"])
+    os.environ["DEDF_VR_SPLIT"] = "1"
+    try:
+        out = ops.value_reduce(G, csr, v, sh.to(cuda), logit, None, p["wv"], p["V0"], p["V1"], p["V2"], p["vb"])
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["DEDF_VR_SPLIT"]
+    assert_close(out, ref, 1e-5, "value_reduce_split vs value_reduce")
 
 
 @pytest.mark.parametrize("G", [32, 16])
