@@ -35,7 +35,7 @@ extern "C" int dedf_l2_persist(const void* base, long long bytes, cudaStream_t s
         attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
         cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
         cudaCtxResetPersistingL2Cache();
-        return (cudaGetLastError() == cudaSuccess) ? dedf::DEDF_OK : dedf::DEDF_ERR_LAUNCH;
+        return (cudaGetLastError() == cudaSuccess) ? DEDF_OK : DEDF_ERR_LAUNCH;
     }
     static bool limit_set = false;
     if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist); limit_set = true; }
@@ -46,13 +46,13 @@ extern "C" int dedf_l2_persist(const void* base, long long bytes, cudaStream_t s
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-    return (cudaGetLastError() == cudaSuccess) ? dedf::DEDF_OK : dedf::DEDF_ERR_LAUNCH;
+    return (cudaGetLastError() == cudaSuccess) ? DEDF_OK : DEDF_ERR_LAUNCH;
 }
 
 extern "C" int dedf_prefetch_l2(const void* const* ptrs_dev, const long long* bytes_dev, int n, cudaStream_t stream) {
-    if (n <= 0) return dedf::DEDF_OK;
-    if (!ptrs_dev || !bytes_dev) return dedf::DEDF_ERR_ARG;
+    if (n <= 0) return DEDF_OK;
+    if (!ptrs_dev || !bytes_dev) return DEDF_ERR_ARG;
     dedf::prefetch_l2_kernel<<<dedf::grid_for(n, 1, dedf::kNumSMs * 4), 256, 0, stream>>>(ptrs_dev, bytes_dev, n);
-    if (cudaGetLastError() != cudaSuccess) return dedf::DEDF_ERR_LAUNCH;
-    return dedf::DEDF_OK;
+    if (cudaGetLastError() != cudaSuccess) return DEDF_ERR_LAUNCH;
+    return DEDF_OK;
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include "../../include/dedf.h"
 
 namespace dedf {
 
@@ -15,12 +16,7 @@ constexpr float kCSlrelu = 1.531320475574866f;
 
 constexpr int kNumSMs = 148;  // B200
 
-enum : int {
-    DEDF_OK = 0,
-    DEDF_ERR_ARG = -1,       // bad argument (null pointer, unsupported irreps, ...)
-    DEDF_ERR_LAUNCH = -2,    // cudaGetLastError() after a launch
-    DEDF_ERR_UNSUPPORTED = -3,
-};
+// return codes: DEDF_OK / DEDF_ERR_* of include/dedf.h
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }

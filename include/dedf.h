@@ -29,6 +29,10 @@
 extern "C" {
 #endif
 
+/* return codes of every entry point */
+enum { DEDF_OK = 0, DEDF_ERR_ARG = -1 /* null pointer, bad size, misaligned operand */, DEDF_ERR_LAUNCH = -2 /* cudaGetLastError() after a launch */,
+       DEDF_ERR_UNSUPPORTED = -3 /* irreps / widths outside the implemented family */ };
+
 #define DEDF_MAX_SCALES 8
 #define DEDF_MLP_MAX_LAYERS 4
 

@@ -270,3 +270,34 @@ def test_every_shipped_config_constructs():
         assert set(m.state_dict()) == set(o.state_dict()), f
         assert sum(p.numel() for p in m.parameters()) > 500_000, f
     assert names == {"MultiscaleScoreModel", "PointAttentiveScoreModel"}
+
+
+def test_entry_points_validate_arguments_before_touching_the_gpu():
+    """The C ABI's error behaviour (include/dedf.h: 'returns 0 or a negative DEDF_ERR_* code, never throws'): null pointers and
+    bad sizes are rejected with DEDF_ERR_ARG by the argument checks, which run before any CUDA call -- so this runs without
+    a GPU.  The header's return codes are the values the library returns."""
+    from diffusion_edf_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "dedf.h")).read()
+    codes = dict(re.findall(r"(DEDF_(?:OK|ERR_\w+)) = (-?\d+)", header))
+    assert codes == {"DEDF_OK": "0", "DEDF_ERR_ARG": "-1", "DEDF_ERR_LAUNCH": "-2", "DEDF_ERR_UNSUPPORTED": "-3"}
+    ERR_ARG = int(codes["DEDF_ERR_ARG"])
+    buf = (ctypes.c_float * 64)()                    # a non-null HOST pointer: only ever compared against null below
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    # farthest point sampling: null cloud, m > n, start out of range
+    assert lib.dedf_fps(None, 10, 2, 0, None, 0, p, None, None) == ERR_ARG
+    assert lib.dedf_fps(p, 10, 11, 0, None, 0, p, None, None) == ERR_ARG
+    assert lib.dedf_fps(p, 10, 2, 10, None, 0, p, None, None) == ERR_ARG
+    # hash grid: bucket count must be a power of two >= 32
+    assert lib.dedf_grid_build(p, 10, 1.0, 48, p, p, p, p, None) == ERR_ARG
+    assert lib.dedf_grid_build(p, 10, -1.0, 64, p, p, p, p, None) == ERR_ARG
+    # value path: null operands, too many segments
+    assert lib.dedf_value_reduce(32, None, 4, 1, p, p, p, None, p, p, p, p, None, p, None) == ERR_ARG
+    assert lib.dedf_value_reduce(32, p, 4, 99, p, p, p, None, p, p, p, p, None, p, None) == ERR_ARG
+    # an empty problem is a no-op, not an error
+    assert lib.dedf_value_reduce(32, p, 0, 1, p, p, p, None, p, p, p, p, None, p, None) == 0
+    # score tensor products: null pose array
+    irr = (ctypes.c_int * 3)(64, 32, 16)
+    two = (ctypes.c_void_p * 2)(p.value, p.value)
+    assert lib.dedf_score_tp(None, 4, p, p, p, p, 2, irr, two, two, two, two, 32, 15.0, p, p, None) == ERR_ARG
+    assert lib.dedf_score_tp(p, 0, p, p, p, p, 2, irr, two, two, two, two, 32, 15.0, p, p, None) == 0
