@@ -33,15 +33,15 @@ ref_shim.install()
 
 from diffusion_edf.gnn_data import FeaturedPoints as RefFP          # noqa: E402
 from diffusion_edf.multiscale_score_model import MultiscaleScoreModel as RefModel    # noqa: E402
+from diffusion_edf.point_attentive_score_model import PointAttentiveScoreModel as RefPointAttentive    # noqa: E402
 
-from diffusion_edf_b200.synthetic import model_kwargs, model_kwargs_place    # noqa: E402
-from tests.golden.model_cases import SAMPLE_KW, inputs, seeded_oracle, weight_checksums    # noqa: E402
-from oracle import model as OM                                      # noqa: E402
+from tests.golden.model_cases import KINDS, SAMPLE_KW, feature_rows, inputs, seeded_oracle, spec, weight_checksums    # noqa: E402
 
-def run(kind, kwargs, out):
+def run(kind, out):
+    kwargs, cls, has_scores, has_sample = spec(kind)
     oracle = seeded_oracle(kind)
     sd = oracle.state_dict()
-    ref = RefModel(**kwargs, deterministic=True).eval()
+    ref = (RefPointAttentive if cls == "PointAttentiveScoreModel" else RefModel)(**kwargs, deterministic=True).eval()
     res = ref.load_state_dict(sd, strict=False)
     assert not res.unexpected_keys, res.unexpected_keys[:5]
     # what the oracle does not carry are e3nn bookkeeping buffers only (output masks, empty weight buffers of weightless products)
@@ -53,25 +53,35 @@ def run(kind, kwargs, out):
     with torch.no_grad():
         key_ms = ref.get_key_pcd_multiscale(key)
         q = ref.get_query_pcd(grasp)
-        ang, lin = ref.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=t)
         for s, p in enumerate(key_ms):
-            out[f"{kind}/key{s}_x"], out[f"{kind}/key{s}_f"] = p.x.numpy(), p.f.numpy()
+            out[f"{kind}/key{s}_x"], out[f"{kind}/key{s}_f"] = p.x.numpy(), p.f[feature_rows(len(p.x))].numpy()
+            if p.w is not None:
+                out[f"{kind}/key{s}_w"] = p.w.numpy()
         out[f"{kind}/query_x"], out[f"{kind}/query_f"], out[f"{kind}/query_w"] = q.x.numpy(), q.f.numpy(), q.w.numpy()
-        out[f"{kind}/ang"], out[f"{kind}/lin"] = ang.numpy(), lin.numpy()
-        g = torch.Generator().manual_seed(11)
-        ta, tl = torch.randn(len(Ts), 3, generator=g), torch.randn(len(Ts), 3, generator=g)
-        loss, _, _, stats = ref.get_train_loss(Ts, t, key, grasp, ta, tl)
-        out[f"{kind}/target_ang"], out[f"{kind}/target_lin"] = ta.numpy(), tl.numpy()
-        out[f"{kind}/loss"] = np.array([float(loss)] + [float(stats[k]) for k in sorted(stats)], dtype=np.float64)
-        traj = ref.sample(Ts, scene_pcd_multiscale=key_ms, grasp_pcd=q, **SAMPLE_KW)
-        out[f"{kind}/traj"] = traj.numpy()
-    print(kind, "ang", ang.abs().max().item(), "loss", float(loss), "traj", tuple(traj.shape), "missing (bookkeeping only):", len(res.missing_keys))
+        msg = ""
+        if has_scores:
+            ang, lin = ref.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=t)
+            out[f"{kind}/ang"], out[f"{kind}/lin"] = ang.numpy(), lin.numpy()
+            g = torch.Generator().manual_seed(11)
+            ta, tl = torch.randn(len(Ts), 3, generator=g), torch.randn(len(Ts), 3, generator=g)
+            loss, _, _, stats = ref.get_train_loss(Ts, t, key, grasp, ta, tl)
+            out[f"{kind}/target_ang"], out[f"{kind}/target_lin"] = ta.numpy(), tl.numpy()
+            out[f"{kind}/loss"] = np.array([float(loss)] + [float(stats[k]) for k in sorted(stats)], dtype=np.float64)
+            msg = f"ang {ang.abs().max().item():.4f} loss {float(loss):.4f}"
+        else:
+            e = ref.score_head.compute_energy(Ts, key_ms, q, t)
+            out[f"{kind}/energy"] = e.numpy()
+            msg = f"energy {e.min().item():.4f}..{e.max().item():.4f}"
+        if has_sample:
+            traj = ref.sample(Ts, scene_pcd_multiscale=key_ms, grasp_pcd=q, **SAMPLE_KW)
+            out[f"{kind}/traj"] = traj.numpy()
+    print(kind, msg, "key scales", [len(p.x) for p in key_ms], "query", len(q.x), "missing (bookkeeping only):", len(res.missing_keys))
 
 
 def main():
     out = {}
-    run("pick", model_kwargs(), out)
-    run("place", model_kwargs_place(), out)
+    for kind in KINDS:
+        run(kind, out)
     np.savez_compressed(os.path.join(HERE, "ref_model_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "ref_model_golden.npz"), os.path.getsize(os.path.join(HERE, "ref_model_golden.npz")) // 1024, "KiB")
 

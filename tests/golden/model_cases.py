@@ -3,7 +3,7 @@ own source; tests/test_oracle.py re-creates them).  Needs neither /root/referenc
 import numpy as np
 import torch
 
-from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs, model_kwargs_place
+from diffusion_edf_b200.synthetic import make_poses, make_scene
 
 SAMPLE_KW = dict(diffusion_schedules=[[1.0, 0.15], [0.15, 0.09]], N_steps=[3, 3], timesteps=[0.04, 0.04], temperatures=[0.0, 0.0],
                  log_t_schedule=True, time_exponent_temp=1.0, time_exponent_alpha=0.5)
@@ -16,16 +16,50 @@ def weight_checksums(sd):
     return np.array([len(keys), tot] + probe, dtype=np.float64)
 
 
+KINDS = ("pick", "place", "highres", "sapien_highres", "sapien_lowres", "ebm")
+# kind -> (kwargs function of diffusion_edf_b200.synthetic, model class name, has scores, has sample)
+_SPEC = {"pick": ("model_kwargs", "MultiscaleScoreModel", True, True), "place": ("model_kwargs_place", "MultiscaleScoreModel", True, True),
+         "highres": ("model_kwargs_highres", "MultiscaleScoreModel", True, False),
+         "sapien_highres": ("model_kwargs_sapien_highres", "MultiscaleScoreModel", True, False),
+         "sapien_lowres": ("model_kwargs_sapien_lowres", "PointAttentiveScoreModel", True, False),
+         "ebm": ("model_kwargs_ebm", "MultiscaleScoreModel", False, False)}
+
+
+def spec(kind):
+    from diffusion_edf_b200 import synthetic
+    fn, cls, has_scores, has_sample = _SPEC[kind]
+    return getattr(synthetic, fn)(), cls, has_scores, has_sample
+
+
 def inputs(kind):
+    small_grasp = (torch.zeros(3, 3), torch.zeros(3, 3))
     if kind == "pick":
         x, rgb = make_scene(1500, seed=3, half_extent=12.0)
         Ts, t = make_poses(6, x, seed=3, spread=6.0)
         gx, gf = torch.zeros(8, 3), torch.zeros(8, 3)
-    else:
+    elif kind == "place":
         x, rgb = make_scene(1200, seed=5, half_extent=10.0)
         Ts, t = make_poses(4, x, seed=5, spread=5.0)
         gx, gf = make_scene(700, seed=6, half_extent=8.0)
         gx[:, 2] += 9.0                                      # part of the grasp cloud inside the keypoint bbox (z >= 8)
+    elif kind == "highres":
+        x, rgb = make_scene(1500, seed=31, half_extent=12.0)
+        Ts, t = make_poses(9, x, seed=31, spread=2.5)
+        gx, gf = small_grasp
+    elif kind == "sapien_highres":
+        x, rgb = make_scene(1200, seed=41, half_extent=10.0)
+        Ts, t = make_poses(7, x, seed=41, spread=2.5)
+        gx, gf = small_grasp
+    elif kind == "sapien_lowres":
+        x, rgb = make_scene(1200, seed=51, half_extent=10.0)
+        Ts, t = make_poses(5, x, seed=51, spread=3.0)
+        gx, gf = small_grasp
+    else:
+        assert kind == "ebm"
+        x, rgb = make_scene(1500, seed=21, half_extent=12.0)
+        Ts, _ = make_poses(12, x, seed=21, spread=3.0)
+        t = torch.ones(12)
+        gx, gf = small_grasp
     return x, rgb, torch.zeros(len(x), dtype=torch.long), Ts, t, gx, gf, torch.zeros(len(gx), dtype=torch.long)
 
 
@@ -33,8 +67,9 @@ def seeded_oracle(kind):
     """The oracle model of a case: shipped kwargs, seed 0, and the parameters that are initialised to 0 / 1 (biases, layer-norm
     affine weights) randomised so that the golden numbers exercise them."""
     from oracle import model as OM
+    kwargs, cls, _, _ = spec(kind)
     torch.manual_seed(0)
-    oracle = OM.MultiscaleScoreModel(**(model_kwargs() if kind == "pick" else model_kwargs_place()), deterministic=True).eval()
+    oracle = getattr(OM, cls)(**kwargs, deterministic=True).eval()
     with torch.no_grad():
         for n, p in oracle.named_parameters():
             if p.abs().sum() == 0:
@@ -42,3 +77,8 @@ def seeded_oracle(kind):
             elif n.endswith("affine_weight"):
                 p.uniform_(0.7, 1.3)
     return oracle
+
+
+def feature_rows(n: int) -> slice:
+    """Rows of a key scale's feature matrix kept in the fixture (all coordinates are kept): about 64 evenly spaced rows."""
+    return slice(0, n, max(1, n // 64))

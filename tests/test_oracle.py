@@ -218,15 +218,17 @@ def test_voxel_filter_matches_reference_golden():
 
 
 # ------------------------------------------------------------------ the reference's own model code (tests/golden/make_golden_model.py)
-@pytest.mark.parametrize("kind", ["pick", "place"])
+@pytest.mark.parametrize("kind", ["pick", "place", "highres", "sapien_highres", "sapien_lowres", "ebm"])
 def test_oracle_matches_reference_code_golden(kind):
-    """ref_model_golden.npz holds what the REFERENCE'S OWN SOURCE computes (forward, get_train_loss, zero-temperature sample) when
-    its un-installable third-party libraries are replaced by stand-ins built on oracle/so3.py and oracle/graph.py
-    (tests/golden/ref_shim.py).  The oracle, re-created from the same seed, must reproduce it: this pins the hand restatement
-    of the reference's module code (UNet, tensor field, attention blocks, score head, keypoint extractor, denoise loop)."""
-    from tests.golden.model_cases import SAMPLE_KW, inputs, seeded_oracle, weight_checksums
+    """ref_model_golden.npz holds what the REFERENCE'S OWN SOURCE computes (key scales, query points, scores or energies,
+    get_train_loss, zero-temperature sample) for every shipped model family when its un-installable third-party libraries are
+    replaced by stand-ins built on oracle/so3.py and oracle/graph.py (tests/golden/ref_shim.py).  The oracle, re-created from
+    the same seed, must reproduce it: this pins the hand restatement of the reference's module code (UNet / forward-only
+    encoder, tensor field, attention blocks, score heads, keypoint extractor, point-attentive model, denoise loop)."""
+    from tests.golden.model_cases import SAMPLE_KW, feature_rows, inputs, seeded_oracle, spec, weight_checksums
     G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_model_golden.npz"))
     g = lambda k: torch.from_numpy(G[f"{kind}/{k}"])                      # noqa: E731
+    _, _, has_scores, has_sample = spec(kind)
     oracle = seeded_oracle(kind)
     if not np.allclose(weight_checksums(oracle.state_dict()), G[f"{kind}/weights"], rtol=1e-9, atol=0):
         pytest.skip("this torch build draws different initial weights from seed 0 than the one the fixture was made with")
@@ -240,17 +242,24 @@ def test_oracle_matches_reference_code_golden(kind):
     with torch.no_grad():
         key_ms = oracle.get_key_pcd_multiscale(key)
         q = oracle.get_query_pcd(grasp)
-        ang, lin = oracle.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=t)
+        assert len(key_ms) == sum(1 for k in G.files if k.startswith(f"{kind}/key") and k.endswith("_x"))
         for s, p in enumerate(key_ms):
             assert torch.equal(p.x, g(f"key{s}_x")), f"pooled coordinates of scale {s}"
-            close(p.f, g(f"key{s}_f"), 2e-5, f"key features scale {s}")
+            close(p.f[feature_rows(len(p.x))], g(f"key{s}_f"), 2e-5, f"key features scale {s}")
+            if f"{kind}/key{s}_w" in G.files:
+                close(p.w, g(f"key{s}_w"), 2e-5, f"key point weights scale {s}")
         assert torch.equal(q.x, g("query_x"))
         close(q.f, g("query_f"), 2e-5, "query features")
         close(q.w, g("query_w"), 2e-5, "query weights")
-        close(ang, g("ang"), 2e-5, "ang")
-        close(lin, g("lin"), 2e-5, "lin")
-        out = oracle.get_train_loss(Ts, t, key, grasp, g("target_ang"), g("target_lin"))
-        close(torch.tensor([float(out[0])], dtype=torch.float64), g("loss")[:1], 2e-5, "training loss")     # g("loss")[1:]: the statistics dict
-        traj = oracle.sample(Ts, key_ms, q, **SAMPLE_KW)
-        assert traj.shape == g("traj").shape and traj.dtype == torch.float64
-        close(traj, g("traj"), 1e-4, "zero-temperature trajectory")       # fp32 scores integrated over 6 steps (observed 1e-5)
+        if has_scores:
+            ang, lin = oracle.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=t)
+            close(ang, g("ang"), 2e-5, "ang")
+            close(lin, g("lin"), 2e-5, "lin")
+            out = oracle.get_train_loss(Ts, t, key, grasp, g("target_ang"), g("target_lin"))
+            close(torch.tensor([float(out[0])], dtype=torch.float64), g("loss")[:1], 2e-5, "training loss")     # g("loss")[1:]: the statistics dict
+        else:
+            close(oracle.score_head.compute_energy(Ts, key_ms, q, t), g("energy"), 2e-5, "energy")
+        if has_sample:
+            traj = oracle.sample(Ts, key_ms, q, **SAMPLE_KW)
+            assert traj.shape == g("traj").shape and traj.dtype == torch.float64
+            close(traj, g("traj"), 1e-4, "zero-temperature trajectory")       # fp32 scores integrated over 6 steps (observed 1e-5)
