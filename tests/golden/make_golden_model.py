@@ -78,8 +78,27 @@ def run(kind, out):
     print(kind, msg, "key scales", [len(p.x) for p in key_ms], "query", len(q.x), "missing (bookkeeping only):", len(res.missing_keys))
 
 
+def run_c1(out):
+    """BASELINE.json configs[0]: the reference's MultiscaleTensorField on the lmax = 1 plumbing case."""
+    from diffusion_edf.multiscale_tensor_field import MultiscaleTensorField as RefField
+    from tests.golden.model_cases import C1_KWARGS, c1_inputs, c1_seeded_oracle
+    oracle = c1_seeded_oracle()
+    ref = RefField(**C1_KWARGS).eval()
+    res = ref.load_state_dict(oracle.state_dict(), strict=False)
+    assert not res.unexpected_keys and all(ref.state_dict()[k].numel() == 0 or k.endswith("output_mask") for k in res.missing_keys)
+    x0, f0, xq = c1_inputs()
+    z = lambda n: torch.zeros(n, dtype=torch.long)                   # noqa: E731
+    keys = [RefFP(x=x0, f=f0, b=z(256)), RefFP(x=x0[:32], f=f0[:32], b=z(32))]
+    with torch.no_grad():
+        o = ref(query_points=RefFP(x=xq, f=torch.empty(64, 0), b=z(64)), input_points_multiscale=keys)
+    out["c1/weights"] = weight_checksums(oracle.state_dict())
+    out["c1/out_f"] = o.f.numpy()
+    print("c1 out", tuple(o.f.shape), float(o.f.abs().max()))
+
+
 def main():
     out = {}
+    run_c1(out)
     for kind in KINDS:
         run(kind, out)
     np.savez_compressed(os.path.join(HERE, "ref_model_golden.npz"), **out)

@@ -82,3 +82,30 @@ def seeded_oracle(kind):
 def feature_rows(n: int) -> slice:
     """Rows of a key scale's feature matrix kept in the fixture (all coordinates are kept): about 64 evenly spaced rows."""
     return slice(0, n, max(1, n // 64))
+
+
+# BASELINE.json configs[0] ("C1"): MultiscaleTensorField, 1 layer, lmax = 1, 256-point cloud (SURVEY.md 8d)
+C1_KWARGS = dict(irreps_input="16x0e+8x1e", irreps_output="16x0e+8x1e", irreps_sh="1x0e+1x1e", num_heads=4, fc_neurons=[-1, 16, 16],
+                 length_emb_dim=16, irreps_query=None, edge_context_emb_dim=None, r_cluster_multiscale=[2.0, None],
+                 length_enc_max_r=10.0, r_mincut_nonscalar_sh=0.1, n_layers=1)
+
+
+def c1_inputs():
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.rand(256, 3, generator=g) * 6 - 3
+    f0 = torch.randn(256, 40, generator=g)
+    xq = torch.rand(64, 3, generator=g) * 6 - 3
+    return x0, f0, xq
+
+
+def c1_seeded_oracle():
+    from oracle import model as OM
+    torch.manual_seed(0)
+    tf = OM.MultiscaleTensorField(**C1_KWARGS).eval()
+    with torch.no_grad():
+        for n, p in tf.named_parameters():
+            if p.abs().sum() == 0:
+                p.uniform_(-0.3, 0.3)
+            elif n.endswith("affine_weight"):
+                p.uniform_(0.7, 1.3)
+    return tf

@@ -263,3 +263,21 @@ def test_oracle_matches_reference_code_golden(kind):
             traj = oracle.sample(Ts, key_ms, q, **SAMPLE_KW)
             assert traj.shape == g("traj").shape and traj.dtype == torch.float64
             close(traj, g("traj"), 1e-4, "zero-temperature trajectory")       # fp32 scores integrated over 6 steps (observed 1e-5)
+
+
+def test_config_c1_matches_reference_code_golden():
+    """BASELINE.json configs[0] (lmax = 1 MultiscaleTensorField, 256-point cloud, CPU): the oracle against the output of the
+    reference's own MultiscaleTensorField source (tests/golden/make_golden_model.py::run_c1)."""
+    from tests.golden.model_cases import c1_inputs, c1_seeded_oracle, weight_checksums
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_model_golden.npz"))
+    tf = c1_seeded_oracle()
+    if not np.allclose(weight_checksums(tf.state_dict()), G["c1/weights"], rtol=1e-9, atol=0):
+        pytest.skip("this torch build draws different initial weights from seed 0 than the one the fixture was made with")
+    x0, f0, xq = c1_inputs()
+    z = lambda n: torch.zeros(n, dtype=torch.long)                   # noqa: E731
+    keys = [OM.FeaturedPoints(x0, f0, z(256)), OM.FeaturedPoints(x0[:32], f0[:32], z(32))]
+    with torch.no_grad():
+        out = tf(OM.FeaturedPoints(xq, torch.empty(64, 0), z(64)), keys)
+    ref = torch.from_numpy(G["c1/out_f"])
+    assert out.f.shape == ref.shape == (64, 40)
+    assert float((out.f - ref).abs().max() / ref.abs().max()) < 2e-5
