@@ -301,3 +301,20 @@ def test_entry_points_validate_arguments_before_touching_the_gpu():
     two = (ctypes.c_void_p * 2)(p.value, p.value)
     assert lib.dedf_score_tp(None, 4, p, p, p, p, 2, irr, two, two, two, two, 32, 15.0, p, p, None) == ERR_ARG
     assert lib.dedf_score_tp(p, 0, p, p, p, p, 2, irr, two, two, two, two, 32, 15.0, p, p, None) == 0
+
+
+def test_ctypes_signatures_have_the_headers_arity():
+    """Every entry point's ctypes argtypes list (diffusion_edf_b200/_lib.py) has exactly as many parameters as its declaration in
+    include/dedf.h -- a drifted binding would read garbage for the trailing arguments instead of failing."""
+    from diffusion_edf_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "dedf.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    n = 0
+    for name, params in re.findall(r"^int (dedf_\w+)\((.*?)\);", header, flags=re.M | re.S):
+        params = params.strip()
+        arity = 0 if params in ("", "void") else len(params.split(","))
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None and len(fn.argtypes) == arity, f"{name}: header has {arity} parameters, ctypes {None if fn.argtypes is None else len(fn.argtypes)}"
+        n += 1
+    assert n >= 16
