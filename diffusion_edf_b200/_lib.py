@@ -44,6 +44,40 @@ class MlpDesc(C.Structure):
     ]
 
 
+class NodeChainDesc(C.Structure):
+    _fields_ = [
+        ("x", c_fp), ("n", c_int), ("irr_emb", c_int * 3), ("irr_pre", c_int * 3),
+        ("P0", c_fp), ("P1", c_fp), ("P2", c_fp), ("pb", c_fp), ("res1", c_fp),
+        ("ln_w", c_fp), ("ln_b", c_fp), ("ln_eps", c_f),
+        ("A0", c_fp), ("A1", c_fp), ("A2", c_fp), ("ab", c_fp),
+        ("B0", c_fp), ("B1", c_fp), ("B2", c_fp), ("bb", c_fp), ("y", c_fp),
+    ]
+
+
+class HeadFrontDesc(C.Structure):
+    _fields_ = [
+        ("Ts", c_fp), ("n_t", c_int), ("qx", c_fp), ("n_q", c_int),
+        ("x_src", c_fp), ("b_src", c_fp), ("b_q", c_fp),
+        ("n_scales", c_int), ("src_off", c_int * (MAX_SCALES + 1)), ("r", c_f * MAX_SCALES),
+        ("max_num_neighbors", c_int), ("ns_lo", c_f), ("ns_hi", c_f), ("capacity", c_int),
+        ("x_dst", c_fp), ("row_ptr", c_fp), ("counts", c_fp), ("edge_src", c_fp), ("edge_dst", c_fp),
+        ("length", c_fp), ("sh", c_fp), ("logit", c_fp), ("n_edges", c_fp), ("overflow", c_fp),
+        ("cta_sum", c_fp), ("barrier", c_fp),
+        ("step", c_fp), ("n_steps", c_int), ("rows_all", c_fp), ("rows_cur", c_fp), ("rows_k", c_int),
+        ("stage_early", c_int),
+    ]
+
+
+class ScoreStepDesc(C.Structure):
+    _fields_ = [
+        ("Ts", c_fp), ("n_t", c_int), ("qf", c_fp), ("key_f", c_fp), ("qx", c_fp), ("qw", c_fp), ("n_q", c_int),
+        ("irr", c_int * 3), ("Wd", c_fp * 2), ("Wl0", c_fp * 2), ("Wl1", c_fp * 2), ("bl", c_fp * 2),
+        ("n_vec", c_int), ("lin_mult", c_f), ("ang_out", c_fp), ("lin_out", c_fp),
+        ("T64", c_fp), ("sched", c_fp), ("n_steps", c_int), ("counter", c_fp), ("noise", c_fp), ("seed", c_ull), ("seed_dev", c_fp),
+        ("ang_mult", c_d), ("lin_mult_d", c_d), ("traj", c_fp), ("T32", c_fp), ("ticket", c_fp),
+    ]
+
+
 class TimeDesc(C.Structure):
     _fields_ = [
         ("max_time", c_f), ("enc_n", c_f), ("enc_freq", c_fp),
@@ -69,6 +103,10 @@ _PROTOS = {
     "dedf_segment_softmax_reduce": [c_fp, c_int, c_int, c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp],
     "dedf_edge_tp_reduce": [c_int, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_int, c_fp, c_fp],
     "dedf_node_linear": [c_fp, c_int, C.POINTER(c_int), C.POINTER(c_int), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_f, c_int, c_fp, c_f, c_fp, c_fp],
+    "dedf_head_front": [C.POINTER(HeadFrontDesc), c_fp],
+    "dedf_node_chain": [C.POINTER(NodeChainDesc), c_fp],
+    "dedf_node_linear_pair": [c_fp, c_int, C.POINTER(c_int), C.POINTER(c_fp), c_fp, c_fp, c_fp, c_int, C.POINTER(c_int), C.POINTER(c_fp), c_fp, c_fp,
+                              C.POINTER(c_int), c_fp],
     "dedf_weight_post": [c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp],
     "dedf_gather_rows": [c_fp, c_fp, c_int, c_int, c_fp, c_fp],
     "dedf_add_scale": [c_fp, c_fp, c_f, c_ll, c_fp, c_fp],
@@ -76,8 +114,10 @@ _PROTOS = {
     "dedf_query_transform": [c_fp, c_int, c_fp, c_fp, c_int, C.POINTER(c_int), c_fp, c_fp, c_fp],
     "dedf_score_tp": [c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_int, C.POINTER(c_int), C.POINTER(c_fp), C.POINTER(c_fp),
                       C.POINTER(c_fp), C.POINTER(c_fp), c_int, c_f, c_fp, c_fp, c_fp],
+    "dedf_score_tp_step": [C.POINTER(ScoreStepDesc), c_fp],
     "dedf_pose_update": [c_fp, c_int, c_fp, c_fp, c_fp, c_ull, c_ull, c_d, c_d, c_d, c_d, c_d, c_d, c_fp, c_fp, c_fp, c_fp, c_fp],
     "dedf_sample_advance": [c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_fp],
+    "dedf_flag_if_differs": [c_fp, c_fp, c_ll, c_fp, c_fp],
     "dedf_prefetch_l2": [c_fp, c_fp, c_int, c_fp],
     "dedf_tc_selftest": [c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp],
     "dedf_lin_wgrad": [c_fp, c_fp, c_int, C.POINTER(c_int), C.POINTER(c_int), c_fp, c_fp, c_fp, c_fp, c_fp],

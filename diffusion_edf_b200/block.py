@@ -26,6 +26,19 @@ def mlp_mid(irreps_emb: Irreps, mult) -> Irreps:
     return Irreps(mult)
 
 
+def node_tail(proj: LinearRS, norm: EquivariantLayerNormV2, ffn: FeedForwardNetwork, attn: torch.Tensor,
+              res1: Optional[torch.Tensor]) -> torch.Tensor:
+    """y1 = proj(attn) (+ res1);  y1 + ffn(norm(y1)): one dedf_node_chain launch when the irreps allow it, else three
+    dedf_node_linear launches (same arithmetic, bit-identical)."""
+    emb, pre = proj.irreps_out, ffn.fctp_1.irreps_out
+    if proj.irreps_in == emb and ffn.fctp_1.irreps_in == emb and ffn.fctp_2.irreps_out == emb and ops.node_chain_ok(emb.m, pre.m):
+        (P, pb), (A, ab), (B, bb) = proj.packed(), ffn.fctp_1.packed(), ffn.fctp_2.packed()
+        return ops.node_chain(attn.contiguous(), emb.m, pre.m, P, pb, res1.contiguous() if res1 is not None else None,
+                              norm.affine_weight.detach(), norm.affine_bias.detach(), norm.eps, A, ab, B, bb)
+    out = proj(attn, res=res1) if res1 is not None else proj(attn)
+    return ffn(out, ln=norm, res=out)
+
+
 class UnetEquiformerBlock(nn.Module):
     def __init__(self, irreps_src, irreps_dst, irreps_edge_attr, irreps_head, num_heads: int, fc_neurons: Sequence[int],
                  irreps_mlp_mid=3, src_bias: bool = False, dst_bias: bool = True, **_ignored):
@@ -65,13 +78,18 @@ class UnetEquiformerBlock(nn.Module):
 
     def forward(self, f_src: torch.Tensor, f_dst: torch.Tensor, g: ops.Csr, sh: torch.Tensor, length: torch.Tensor,
                 radial: GaussianRadialBasisLayerFiniteCutoff, w: Optional[torch.Tensor] = None) -> torch.Tensor:
-        msg_src = self.linear_src(f_src)
-        msg_dst = self.linear_dst(f_dst)
+        ms = list(self.irreps_src.m) + list(self.irreps_dst.m) + list(self.irreps_emb.m)
+        if ops.USE_LINEAR_PAIR and all(m > 0 and m % 4 == 0 for m in ms):
+            (Ws, bs), (Wd, bd) = self.linear_src.packed(), self.linear_dst.packed()
+            msg_src, msg_dst = ops.node_linear_pair(f_src.contiguous(), self.irreps_src.m, Ws, bs, f_dst.contiguous(), self.irreps_dst.m, Wd, bd,
+                                                    self.irreps_emb.m)
+        else:
+            msg_src = self.linear_src(f_src)
+            msg_dst = self.linear_dst(f_dst)
         if w is None:
             w = self.radial_weights(g, length, radial)
         attn = self.ga.attend(msg_src, msg_dst, g, sh, w, None)
-        out = self.ga.proj(attn, res=f_dst)                          # node_output = node_input_dst + ga(...)
-        return self.ffn(out, ln=self.norm_2, res=out)                # + ffn(norm_2(node_output))
+        return node_tail(self.ga.proj, self.norm_2, self.ffn, attn, f_dst)
 
 
 class EquiformerBlock(nn.Module):
@@ -104,6 +122,7 @@ class EquiformerBlock(nn.Module):
                 edge_logit: torch.Tensor, src_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
         assert (src_weight is not None) == self.use_src_point_attn, "source-point attention needs the source weights (FeaturedPoints.w)"
         attn = self.ga.attend(msg_src, None, g, sh, w, edge_logit, src_weight)
+        if self.skip_2.is_identity:
+            return node_tail(self.ga.proj, self.post_norm, self.ffn, attn, None)
         emb = self.ga.proj(attn)
-        skip = emb if self.skip_2.is_identity else self.skip_2(emb)
-        return self.ffn(emb, ln=self.post_norm, res=skip)
+        return self.ffn(emb, ln=self.post_norm, res=self.skip_2(emb))

@@ -14,9 +14,26 @@ __global__ void __launch_bounds__(256) prefetch_l2_kernel(const void* const* __r
     }
 }
 
+// flag |= 1 if a[i] != b[i] for any i (int64 words): guards a replayed CUDA graph against inputs whose data-dependent layout
+// (batch ids) differs from the one the plan was recorded with
+__global__ void __launch_bounds__(256) flag_if_differs_kernel(const long long* __restrict__ a, const long long* __restrict__ b, long long n,
+                                                              int* __restrict__ flag) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) bad |= (a[i] != b[i]);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
 }  // namespace dedf
 
 extern "C" int dedf_build_arch(void) { return 100; }
+
+extern "C" int dedf_flag_if_differs(const long long* a, const long long* b, long long n, int* flag, cudaStream_t stream) {
+    if (n <= 0) return DEDF_OK;
+    if (!a || !b || !flag) return DEDF_ERR_ARG;
+    dedf::flag_if_differs_kernel<<<dedf::grid_for(n, 256, dedf::kNumSMs), 256, 0, stream>>>(a, b, n, flag);
+    if (cudaGetLastError() != cudaSuccess) return DEDF_ERR_LAUNCH;
+    return DEDF_OK;
+}
 
 /* Pin an address range in L2 for the kernels launched into `stream` from now on (cudaAccessPolicyWindow, persisting hits /
  * streaming misses); bytes = 0 removes the window and releases the persisting lines.  Used around K1: the gathered feature
@@ -37,8 +54,11 @@ extern "C" int dedf_l2_persist(const void* base, long long bytes, cudaStream_t s
         cudaCtxResetPersistingL2Cache();
         return (cudaGetLastError() == cudaSuccess) ? DEDF_OK : DEDF_ERR_LAUNCH;
     }
-    static bool limit_set = false;
-    if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist); limit_set = true; }
+    {   // the persisting carve-out is a per-device limit: query it instead of remembering (several devices, several callers)
+        size_t cur = 0;
+        cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+        if (cur < (size_t)max_persist) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+    }
     const long long win = bytes < (long long)max_window ? bytes : (long long)max_window;
     attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
     attr.accessPolicyWindow.num_bytes = (size_t)win;

@@ -925,341 +925,6 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
 }
 
 // ---------------------------------------------------------------------------
-// EXPERIMENTAL (DEDF_VR_SPLIT=1; NOT yet run on a GPU -- written after the round's GPU minutes were spent): the same kernel with
-// the work of a warp pair split by PATH instead of by head pair.  value_reduce_kernel is issue-bound (ncu: 8 warps per SM,
-// issue slots 49 % busy) and its two warps of a channel group both evaluate all 15 CG paths, once per head pair: per pack
-// 214 CG FMAs + 196 fold FMAs per warp.  Here every CG output is produced by exactly one of the two warps and folded into all
-// four heads: 85 + 208 and 129 + 184 FMAs -- a quarter fewer instructions, same registers (4 x 27 accumulators instead of
-// 2 x 51), same shared-memory traffic.  tests/test_gpu_kernels.py::test_value_reduce_split_experimental (run with
-// DEDF_EXPERIMENTAL=1) compares it with the kernel above.
-// ---------------------------------------------------------------------------
-template <int G>
-__global__ void __launch_bounds__(G * 8, 1) value_reduce_split_kernel(ValueReduceArgs a) {
-    using D = Dtp<G>;
-    constexpr int NCW = G / 8, NW = 2 * NCW, NT = NW * 32, CH = kVrChunk;
-    constexpr int B1 = D::D0, B2 = D::D0 + 3 * D::D1;             // block offsets inside one head copy of the reduced TP output
-    constexpr int NV0 = D::D0 * D::M0, NV1 = D::D1 * D::M1, NV2 = D::D2 * D::M2;
-    extern __shared__ __align__(16) float smem[];
-    float* s_v = smem;                          // [CH][F]
-    float* s_lg = s_v + CH * D::F;              // [CH][4] logits -> alpha (in place)
-    float* s_sh = s_lg + CH * 4;                // [CH][12]
-    float* s_D = s_sh + CH * 12;                // [4 heads][FOUT]
-    float* s_V = s_D + 4 * D::FOUT;             // sep_value.lin weights [V0 | V1 | V2], staged once per CTA
-    __shared__ float s_red[NW][4], s_sal[4];
-    __shared__ int s_cum[DEDF_MAX_SCALES + 1], s_beg[DEDF_MAX_SCALES];
-    __shared__ __align__(8) uint64_t bar, vbar;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cw = warp % NCW, part = warp / NCW;   // part 0: paths k0 k2 | k3 k4 k5 | k9 k10 k11 k12 ; part 1: k1 | k6 k7 k8 | k13 k14
-    const int ch0 = cw * 16 + (lane & 15), ch1 = cw * 8 + (lane & 7), ch2 = cw * 4 + (lane & 3);
-    float w0[3], w1[6], w2[6];
-    w0[0] = a.wv[D::W_K0 + ch0]; w0[1] = a.wv[D::W_K1 + ch0]; w0[2] = a.wv[D::W_K2 + ch0];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { w1[i] = a.wv[D::W_K3 + ch1 + i * D::M1]; w2[i] = a.wv[D::W_K9 + ch2 + i * D::M2]; }
-    if (tid == 0) {
-        mbar_init(&bar, 1); mbar_init(&vbar, 1);
-        mbar_init_fence();
-        // the linear layer's weights do not depend on the previous kernel: their copy overlaps its tail (PDL)
-        mbar_expect_tx(&vbar, (uint32_t)(NV0 + NV1 + NV2) * 4u);
-        bulk_g2s_chunked(s_V, a.V0, NV0 * 4u, &vbar);
-        bulk_g2s_chunked(s_V + NV0, a.V1, NV1 * 4u, &vbar);
-        bulk_g2s_chunked(s_V + NV0 + NV1, a.V2, NV2 * 4u, &vbar);
-    }
-    pdl_wait(); pdl_launch();     // PDL: see common.cuh
-    __syncthreads();
-    uint32_t ph = 0;
-    bool v_pending = true;
-
-    // stage edges [f0, f0 + n) of destination d's FLAT edge list (all segments back to back) into the chunk buffers
-    auto issue_chunk = [&](int f0, int n) {       // thread 0 only; s_cum / s_beg are valid
-        mbar_expect_tx(&bar, (uint32_t)n * (D::F + 4) * 4u);
-        for (int s = 0; s < a.n_seg; ++s) {
-            const int lo = max(f0, s_cum[s]), hi = min(f0 + n, s_cum[s + 1]);
-            if (lo < hi) {
-                const size_t e = (size_t)s_beg[s] + (lo - s_cum[s]);
-                bulk_g2s_chunked(s_v + (size_t)(lo - f0) * D::F, a.v + e * D::F, (uint32_t)(hi - lo) * D::F * 4u, &bar);
-                bulk_g2s(s_lg + (lo - f0) * 4, a.logits + e * 4, (uint32_t)(hi - lo) * 16u, &bar);
-            }
-        }
-    };
-
-    for (int d = blockIdx.x; d < a.n_dst; d += gridDim.x) {
-        __syncthreads();                                           // previous destination done with every shared buffer
-        if (tid == 0) {
-            int c = 0;
-            for (int s = 0; s < a.n_seg; ++s) {
-                const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
-                s_cum[s] = c; s_beg[s] = b; c += e - b;
-            }
-            s_cum[a.n_seg] = c;
-            if (c > 0) issue_chunk(0, min(CH, c));                 // the first chunk flies while the statistics are computed
-        }
-        if (tid < 4) s_sal[tid] = 0.f;
-        __syncthreads();
-        const int deg = s_cum[a.n_seg];
-        // ---- softmax statistics over all incoming edges: per-head max, log Z (logits straight from global / L2) ----
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        for (int s = 0; s < a.n_seg; ++s) {
-            const int b = s_beg[s], e = b + (s_cum[s + 1] - s_cum[s]);
-            for (int i = b + tid; i < e; i += NT) {
-                const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
-                mx[0] = fmaxf(mx[0], l.x); mx[1] = fmaxf(mx[1], l.y); mx[2] = fmaxf(mx[2], l.z); mx[3] = fmaxf(mx[3], l.w);
-            }
-        }
-#pragma unroll
-        for (int h = 0; h < 4; ++h) mx[h] = warp_max(mx[h]);
-        if (lane == 0) { s_red[warp][0] = mx[0]; s_red[warp][1] = mx[1]; s_red[warp][2] = mx[2]; s_red[warp][3] = mx[3]; }
-        __syncthreads();
-#pragma unroll
-        for (int h = 0; h < 4; ++h) { float m = s_red[0][h]; for (int w = 1; w < NW; ++w) m = fmaxf(m, s_red[w][h]); mx[h] = m; }
-        float sm[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int s = 0; s < a.n_seg; ++s) {
-            const int b = s_beg[s], e = b + (s_cum[s + 1] - s_cum[s]);
-            for (int i = b + tid; i < e; i += NT) {
-                const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
-                sm[0] += __expf(l.x - mx[0]); sm[1] += __expf(l.y - mx[1]); sm[2] += __expf(l.z - mx[2]); sm[3] += __expf(l.w - mx[3]);
-            }
-        }
-#pragma unroll
-        for (int h = 0; h < 4; ++h) sm[h] = warp_sum(sm[h]);
-        __syncthreads();
-        if (lane == 0) { s_red[warp][0] = sm[0]; s_red[warp][1] = sm[1]; s_red[warp][2] = sm[2]; s_red[warp][3] = sm[3]; }
-        __syncthreads();
-        float logZ[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            float t = 0.f;
-            for (int w = 0; w < NW; ++w) t += s_red[w][h];
-            logZ[h] = (deg > 0) ? (logf(t + 1e-12f) + mx[h]) : 0.f;
-        }
-
-        // ---- edge loop: accumulate alpha_h * dtp(v_e, sh_e, w) for this warp's channels and its two heads ----
-        // accumulators, 4 heads x this warp's share of the 51 outputs of a channel slot:
-        //   part 0 (27): [0] k0 | [1..5] k2 || [6..8] k3 | [9] k4 | [10..12] k5 || [13..17] k9 | [18..20] k10 | [21..25] k11 | [26] k12
-        //   part 1 (24): [0..2] k1 || [3..7] k6 | [8..10] k7 | [11..15] k8 || [16..18] k13 | [19..23] k14
-        float acc[4][27];
-#pragma unroll
-        for (int h = 0; h < 4; ++h)
-#pragma unroll
-            for (int k = 0; k < 27; ++k) acc[h][k] = 0.f;
-#define DEDF_VR_ACC(base, cnt, o)                                                                   \
-    _Pragma("unroll") for (int k_ = 0; k_ < (cnt); ++k_) {                                          \
-        acc[0][(base) + k_] = fmaf(al.x, (o)[k_], acc[0][(base) + k_]); acc[1][(base) + k_] = fmaf(al.y, (o)[k_], acc[1][(base) + k_]); \
-        acc[2][(base) + k_] = fmaf(al.z, (o)[k_], acc[2][(base) + k_]); acc[3][(base) + k_] = fmaf(al.w, (o)[k_], acc[3][(base) + k_]); \
-    }
-        for (int f0 = 0; f0 < deg; f0 += CH) {
-            const int n = min(CH, deg - f0);
-            if (f0 > 0) {
-                __syncthreads();                                   // previous chunk fully consumed
-                if (tid == 0) issue_chunk(f0, n);
-            }
-            // harmonics of the chunk (9-float rows are not 16-byte aligned: plain loads), per segment piece
-            for (int i = tid; i < n * 9; i += NT) {
-                const int r = i / 9, f = f0 + r;
-                int s = 0;
-                while (f >= s_cum[s + 1]) ++s;
-                s_sh[r * 12 + (i % 9)] = a.sh[((size_t)s_beg[s] + (f - s_cum[s])) * 9 + (i % 9)];
-            }
-            mbar_wait(&bar, ph); ph ^= 1u;
-            __syncthreads();
-            // logits -> alpha (x optional post factor), in place; per-head sums for the bias term (fixed order)
-            if (tid < CH) {
-                float4 al = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (tid < n) {
-                    const float4 l = *reinterpret_cast<const float4*>(s_lg + tid * 4);
-                    float pf = 1.0f;
-                    if (a.post) {
-                        const int f = f0 + tid;
-                        int s = 0;
-                        while (f >= s_cum[s + 1]) ++s;
-                        pf = a.post[(size_t)s_beg[s] + (f - s_cum[s])];
-                    }
-                    al = make_float4(__expf(l.x - logZ[0]) * pf, __expf(l.y - logZ[1]) * pf, __expf(l.z - logZ[2]) * pf, __expf(l.w - logZ[3]) * pf);
-                }
-                *reinterpret_cast<float4*>(s_lg + tid * 4) = al;
-                float t0 = warp_sum(al.x), t1 = warp_sum(al.y), t2 = warp_sum(al.z), t3 = warp_sum(al.w);
-                if (lane == 0) { s_red[warp][0] = t0; s_red[warp][1] = t1; s_red[warp][2] = t2; s_red[warp][3] = t3; }
-            }
-            __syncthreads();
-            if (tid < 4) s_sal[tid] += s_red[0][tid] + s_red[1][tid];      // CH = 64 = the first two warps
-            // packs of 8 edges; every CG output is computed by exactly one warp of the pair and folded into all 4 heads
-            for (int p0 = 0; p0 < n; p0 += 8) {
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {                           // l = 0: 2 edges x 16 channels
-                    const int e = p0 + 2 * it + (lane >> 4);
-                    const bool ok = e < n;
-                    const float x = ok ? s_v[e * D::F + ch0] : 0.f;
-                    const float4 al = ok ? *reinterpret_cast<const float4*>(s_lg + e * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float* sh = s_sh + (ok ? e : 0) * 12;
-                    if (part == 0) {
-                        const float a0 = x * w0[0], a2 = x * w0[2];
-                        float o[6];
-                        o[0] = a0 * sh[0];
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) o[1 + k] = a2 * sh[4 + k];
-                        DEDF_VR_ACC(0, 6, o)
-                    } else {
-                        const float a1 = x * w0[1];
-                        float o[3];
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) o[k] = a1 * sh[1 + k];
-                        DEDF_VR_ACC(0, 3, o)
-                    }
-                }
-#pragma unroll
-                for (int it = 0; it < 2; ++it) {                           // l = 1: 4 edges x 8 channels
-                    const int e = p0 + 4 * it + (lane >> 3);
-                    const bool ok = e < n;
-                    const float* xs = s_v + (ok ? e : 0) * D::F + D::M0 + 3 * ch1;
-                    const float xv[3] = {ok ? xs[0] : 0.f, ok ? xs[1] : 0.f, ok ? xs[2] : 0.f};
-                    const float4 al = ok ? *reinterpret_cast<const float4*>(s_lg + e * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float* sh = s_sh + (ok ? e : 0) * 12;
-                    float t[5], o[5];
-                    if (part == 0) {
-                        const float a3 = w1[0] * sh[0];
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) o[k] = a3 * xv[k];
-                        DEDF_VR_ACC(6, 3, o)
-                        cg_110(xv, sh + 1, t); o[0] = w1[1] * t[0];
-                        DEDF_VR_ACC(9, 1, o)
-                        cg_111(xv, sh + 1, t);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) o[k] = w1[2] * t[k];
-                        DEDF_VR_ACC(10, 3, o)
-                    } else {
-                        cg_112(xv, sh + 1, t);
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) o[k] = w1[3] * t[k];
-                        DEDF_VR_ACC(3, 5, o)
-                        cg_121(xv, sh + 4, t);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) o[k] = w1[4] * t[k];
-                        DEDF_VR_ACC(8, 3, o)
-                        cg_122(xv, sh + 4, t);
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) o[k] = w1[5] * t[k];
-                        DEDF_VR_ACC(11, 5, o)
-                    }
-                }
-                {                                                          // l = 2: 8 edges x 4 channels
-                    const int e = p0 + (lane >> 2);
-                    const bool ok = e < n;
-                    const float* xs = s_v + (ok ? e : 0) * D::F + D::M0 + 3 * D::M1 + 5 * ch2;
-                    float xv[5];
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) xv[i] = ok ? xs[i] : 0.f;
-                    const float4 al = ok ? *reinterpret_cast<const float4*>(s_lg + e * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float* sh = s_sh + (ok ? e : 0) * 12;
-                    float t[5], o[5];
-                    if (part == 0) {
-                        const float a9 = w2[0] * sh[0];
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) o[k] = a9 * xv[k];
-                        DEDF_VR_ACC(13, 5, o)
-                        cg_211(xv, sh + 1, t);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) o[k] = w2[1] * t[k];
-                        DEDF_VR_ACC(18, 3, o)
-                        cg_212(xv, sh + 1, t);
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) o[k] = w2[2] * t[k];
-                        DEDF_VR_ACC(21, 5, o)
-                        cg_220(xv, sh + 4, t); o[0] = w2[3] * t[0];
-                        DEDF_VR_ACC(26, 1, o)
-                    } else {
-                        cg_221(xv, sh + 4, t);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) o[k] = w2[4] * t[k];
-                        DEDF_VR_ACC(16, 3, o)
-                        cg_222(xv, sh + 4, t);
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) o[k] = w2[5] * t[k];
-                        DEDF_VR_ACC(19, 5, o)
-                    }
-                }
-            }
-        }
-#undef DEDF_VR_ACC
-        // ---- fold the lanes that share a channel (l0: 2 edges, l1: 4, l2: 8 per pack step) ----
-        const int nl0 = part == 0 ? 6 : 3, nl1 = part == 0 ? 13 : 16;      // accumulator index ranges [0, nl0) l0, [nl0, nl1) l1, rest l2
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-#pragma unroll
-            for (int k = 0; k < 27; ++k) {
-                float v = acc[h][k];                                   // same order as value_reduce_kernel: 4, 8, 16
-                const float v4 = v + __shfl_xor_sync(0xffffffffu, v, 4);
-                v = (k >= nl1) ? v4 : v;
-                const float v8 = v + __shfl_xor_sync(0xffffffffu, v, 8);
-                v = (k >= nl0) ? v8 : v;
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                acc[h][k] = v;
-            }
-        }
-        // ---- write the 4 head copies of the reduced TP output to shared memory (every output by the warp that owns its path) ----
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            float* Dh = s_D + (size_t)h * D::FOUT;
-            if (part == 0) {
-                if (lane < 16) {
-                    Dh[D::C0_K0 + ch0] = acc[h][0];
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) Dh[B2 + (D::C2_K2 + ch0) * 5 + k] = acc[h][1 + k];
-                }
-                if (lane < 8) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) { Dh[B1 + (D::C1_K3 + ch1) * 3 + k] = acc[h][6 + k]; Dh[B1 + (D::C1_K5 + ch1) * 3 + k] = acc[h][10 + k]; }
-                    Dh[D::C0_K4 + ch1] = acc[h][9];
-                }
-                if (lane < 4) {
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) { Dh[B2 + (D::C2_K9 + ch2) * 5 + k] = acc[h][13 + k]; Dh[B2 + (D::C2_K11 + ch2) * 5 + k] = acc[h][21 + k]; }
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) Dh[B1 + (D::C1_K10 + ch2) * 3 + k] = acc[h][18 + k];
-                    Dh[D::C0_K12 + ch2] = acc[h][26];
-                }
-            } else {
-                if (lane < 16) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) Dh[B1 + (D::C1_K1 + ch0) * 3 + k] = acc[h][k];
-                }
-                if (lane < 8) {
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) { Dh[B2 + (D::C2_K6 + ch1) * 5 + k] = acc[h][3 + k]; Dh[B2 + (D::C2_K8 + ch1) * 5 + k] = acc[h][11 + k]; }
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) Dh[B1 + (D::C1_K7 + ch1) * 3 + k] = acc[h][8 + k];
-                }
-                if (lane < 4) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) Dh[B1 + (D::C1_K13 + ch2) * 3 + k] = acc[h][16 + k];
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) Dh[B2 + (D::C2_K14 + ch2) * 5 + k] = acc[h][19 + k];
-                }
-            }
-        }
-        if (v_pending) { mbar_wait(&vbar, 0); v_pending = false; }
-        __syncthreads();
-        // ---- linear layer, once per destination: out[c] = sum_k V_l[k, u] D_{head(u)}[k, m] (+ bias * sum alpha) ----
-        for (int c = tid; c < D::F; c += NT) {
-            int l, u, m;
-            if (c < D::M0) { l = 0; u = c; m = 0; }
-            else if (c < D::M0 + 3 * D::M1) { l = 1; u = (c - D::M0) / 3; m = (c - D::M0) % 3; }
-            else { l = 2; u = (c - D::M0 - 3 * D::M1) / 5; m = (c - D::M0 - 3 * D::M1) % 5; }
-            const int ML = (l == 0) ? D::M0 : (l == 1) ? D::M1 : D::M2;
-            const int KL = (l == 0) ? D::D0 : (l == 1) ? D::D1 : D::D2;
-            const int dd = 2 * l + 1;
-            const int h = u / (ML / 4);
-            const float* V = s_V + ((l == 0) ? 0 : (l == 1) ? NV0 : NV0 + NV1) + u;
-            const float* Dl = s_D + (size_t)h * D::FOUT + ((l == 0) ? 0 : (l == 1) ? B1 : B2) + m;
-            float acc = 0.f, accb = 0.f;
-            for (int k = 0; k < KL; k += 4) {                      // every D_l is a multiple of 4
-                acc = fmaf(V[k * ML], Dl[k * dd], acc); accb = fmaf(V[(k + 1) * ML], Dl[(k + 1) * dd], accb);
-                acc = fmaf(V[(k + 2) * ML], Dl[(k + 2) * dd], acc); accb = fmaf(V[(k + 3) * ML], Dl[(k + 3) * dd], accb);
-            }
-            acc += accb;
-            if (l == 0 && a.vb) acc = fmaf(a.vb[u], s_sal[h], acc);
-            a.out[(size_t)d * D::F + c] = acc;
-        }
-    }
-}
 
 
 // ===========================================================================
@@ -1850,14 +1515,6 @@ template <int G>
 static int launch_value_reduce(const ValueReduceArgs& a, cudaStream_t stream) {
     using D = Dtp<G>;
     const size_t smem = ((size_t)kVrChunk * (D::F + 4 + 12) + 4 * (size_t)D::FOUT + (size_t)D::D0 * D::M0 + (size_t)D::D1 * D::M1 + (size_t)D::D2 * D::M2) * sizeof(float);
-    const char* split = getenv("DEDF_VR_SPLIT");             // experimental path-split variant (see value_reduce_split_kernel)
-    if (split && split[0] == '1') {
-        static bool done_s = false;
-        if (!done_s) { cudaFuncSetAttribute(value_reduce_split_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done_s = true; }
-        launch_pdl(value_reduce_split_kernel<G>, dim3(grid_for(a.n_dst, 1, kNumSMs * 8)), dim3(G * 8), smem, stream, a);
-        DEDF_CHECK_LAUNCH();
-        return DEDF_OK;
-    }
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(value_reduce_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
     launch_pdl(value_reduce_kernel<G>, dim3(grid_for(a.n_dst, 1, kNumSMs * 8)), dim3(G * 8), smem, stream, a);

@@ -298,11 +298,14 @@ radius_kernel(RadiusArgs a, int* __restrict__ counts, const int* __restrict__ ro
         const long long ex = (a.excl_mode == 1) ? a.excl[d] : -1;
         // ``max_nb`` caps the hits INCLUDING excluded ones (torch_cluster truncates first, the
         // reference filters self pairs afterwards: connectivity.py:68-70, radius_graph's +1).
+        // ... and only for radius scales: InfiniteBipartite builds the full meshgrid, its max_neighbors is a placeholder
+        // (graph_parser.py:274-278)
+        const int cap_nb = all ? 0x7fffffff : a.max_nb;
         int cnt_all = 0, cnt_keep = 0;
         int base = 0, seg_end = 0x7fffffff;
         if (FILL) { base = row_ptr[item]; seg_end = row_ptr[item + 1]; }
         constexpr int U = 4;
-        for (int c = s0; c < s1 && cnt_all < a.max_nb; c += 32 * U) {
+        for (int c = s0; c < s1 && cnt_all < cap_nb; c += 32 * U) {
             bool hit[U], excluded[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -323,7 +326,7 @@ radius_kernel(RadiusArgs a, int* __restrict__ counts, const int* __restrict__ ro
             for (int u = 0; u < U; ++u) {
                 const int i = c + 32 * u + lane;
                 const unsigned bal_all = __ballot_sync(0xffffffffu, hit[u]);
-                const bool keep = hit[u] && !excluded[u] && (cnt_all + __popc(bal_all & lt) < a.max_nb);
+                const bool keep = hit[u] && !excluded[u] && (cnt_all + __popc(bal_all & lt) < cap_nb);
                 const unsigned bal_keep = __ballot_sync(0xffffffffu, keep);
                 if (FILL && keep) {
                     const int pos = base + cnt_keep + __popc(bal_keep & lt);

@@ -147,7 +147,55 @@ struct ScoreArgs {
     int n_vec;                         // NV = 32
     float lin_mult;
     float* ang_out; float* lin_out;    // (n_t,3)
+    const float* qf;                   // (n_q, F) UN-rotated query features: used when qf_rot is null -- D(q) is applied here
+                                       // (the arithmetic of query_transform_kernel), so a denoise step needs no separate launch
+    // optional fused Langevin step (denoise loop): the pose update of pose_update_kernel + cast_pose_kernel for the CTA's poses
+    double* T64; const double* sched; int n_steps; int* counter; const double* noise; unsigned long long seed;
+    const unsigned long long* seed_dev;    // optional device copy of the seed (a cached graph serves any seed)
+    double ang_mult_d, lin_mult_d; double* traj; float* T32; unsigned* ticket;
 };
+
+// One annealed-Langevin step of pose i in float64 (score_model_base.py:178-193), shared by pose_update_kernel and the fused
+// tail of score_tp_kernel.  z: 6 standard normals or null -> Philox (seed, subsequence = pose, window = step).
+constexpr unsigned long long kPhiloxPerStep = 16;   // cuRAND's Philox offset counts 32-bit outputs and one step draws 3 x
+                                                    // curand_normal2_double = 12 of them: steps are 16 outputs apart
+__device__ __forceinline__ void langevin_step(double* T, const float* ang, const float* lin, const double* z_in,
+                                              unsigned long long seed, unsigned long long pose, unsigned long long step,
+                                              double t, double ang_mult, double lin_mult, double alpha_ang, double alpha_lin,
+                                              double temperature) {
+    double z[6];
+    if (z_in) {
+        for (int k = 0; k < 6; ++k) z[k] = z_in[k];
+    } else {
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, pose, step * kPhiloxPerStep, &st);
+        for (int k = 0; k < 6; k += 2) { double2 n = curand_normal2_double(&st); z[k] = n.x; z[k + 1] = n.y; }
+    }
+    const double sq_t = sqrt(t);
+    double ang_disp[3], lin_disp[3];
+    for (int k = 0; k < 3; ++k) {
+        const double as = (double)ang[k] / (ang_mult * sq_t);
+        const double ls = (double)lin[k] / (lin_mult * sq_t);
+        ang_disp[k] = (alpha_ang / 2) * as + sqrt(temperature * alpha_ang) * z[k];
+        lin_disp[k] = (alpha_lin / 2) * ls + sqrt(temperature * alpha_lin) * z[3 + k];
+    }
+    const double q[4] = {T[0], T[1], T[2], T[3]};
+    // L = T[q_indices] * q_factor   (score_model_base.py:31-32,188)
+    const int qi[4][3] = {{1, 2, 3}, {0, 3, 2}, {3, 0, 1}, {2, 1, 0}};
+    const double qf[4][3] = {{-0.5, -0.5, -0.5}, {0.5, -0.5, 0.5}, {0.5, 0.5, -0.5}, {-0.5, 0.5, 0.5}};
+    double qn[4], nrm = 0;
+    for (int r = 0; r < 4; ++r) {
+        double dq = 0;
+        for (int c = 0; c < 3; ++c) dq += q[qi[r][c]] * qf[r][c] * ang_disp[c];
+        qn[r] = q[r] + dq;
+        nrm += qn[r] * qn[r];
+    }
+    nrm = sqrt(nrm);
+    double dx[3];
+    quat_apply<double>(q, lin_disp, dx);
+    for (int r = 0; r < 4; ++r) T[r] = qn[r] / nrm;
+    for (int k = 0; k < 3; ++k) T[4 + k] += dx[k];
+}
 
 constexpr int kScoreQB = 2;     // (pose, query node) rows processed together: every weight load serves all of them, for both tensor
                                 // products.  Large batches take 2 poses per CTA and 4 rows at a time (the kernel is then bound by the
@@ -218,6 +266,7 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
     float* sd1 = sd0 + 2 * QB * D0;     // [2][QB][3][D1]  planar in the vector component: step 3 reads 4 consecutive channels per LDS
     float* sy = st;                     // [2][QB][NY]     aliases the t buffers (dead after step 2; NY <= TT checked by the launcher)
     float* sres = sd1 + 2 * QB * 3 * D1;  // [pb n_q][2][3]
+    float* srd = sres + (((6 * pb * a.n_q) + 3) & ~3);   // [pb][36]: R (9) and D^2 (25) of the pass's poses (on-the-fly rotation)
     const int tid = threadIdx.x;
     // weight offsets (per path: [mul2][mul1], i.e. transposed blocks, see ScoreArgs)
     const int m1s[9] = {M0, M0, M1, M1, M1, M1, M2, M2, M2};
@@ -229,7 +278,7 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
     const int boff[3] = {0, M0, M0 + 3 * M1};   // offsets of l blocks in a feature vector
     // resident weights
     const int nWd = woff[9], nWl1 = D1 * NV;
-    float* sw = sres + (((6 * pb * a.n_q) + 3) & ~3);
+    float* sw = srd + 36 * pb;
     const float* Wd[2] = {a.Wd[0], a.Wd[1]};
     const float* Wl1[2] = {a.Wl1[0], a.Wl1[1]};
     if (w_smem) {
@@ -245,18 +294,53 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
         for (int i = 0; i < 2; ++i) { Wd[i] = sw + i * nWd; Wl1[i] = sw + 2 * nWd + i * nWl1; }
     }
     pdl_wait(); pdl_launch();     // PDL: see common.cuh
+    const int step_now = a.T64 ? *a.counter : 0;
     if (w_smem) { __syncthreads(); mbar_wait(&wbar, 0); }
 
     for (int t0 = blockIdx.x * pb; t0 < a.n_t; t0 += gridDim.x * pb) {
     const int np = min(pb, a.n_t - t0);
     const int rows_total = np * a.n_q;  // (pose, query node) rows of this pass: consecutive nodes of qf_rot / key_f
+    if (!a.qf_rot) {
+        __syncthreads();                // (the previous pass is done with srd)
+        if (tid < np) {                 // R(q / |q|) and D^2 from R, exactly as query_transform_kernel
+            const float* T = a.Ts + (size_t)(t0 + tid) * 7;
+            const float nrm = sqrtf(T[0] * T[0] + T[1] * T[1] + T[2] * T[2] + T[3] * T[3]);
+            float qn[4] = {T[0] / nrm, T[1] / nrm, T[2] / nrm, T[3] / nrm};
+            float R[9]; quat_to_matrix<float>(qn, R);
+            float D[25]; wigner_d2_from_R(R, D);
+            float* o = srd + tid * 36;
+            for (int i = 0; i < 9; ++i) o[i] = R[i];
+            for (int i = 0; i < 25; ++i) o[9 + i] = D[i];
+        }
+    }
     for (int q0 = 0; q0 < rows_total; q0 += QB) {
         const int nq = min(QB, rows_total - q0);
         __syncthreads();
         for (int i = tid; i < QB * F; i += blockDim.x) {
             const int qq = i / F, c = i % F;
-            const size_t node = (size_t)t0 * a.n_q + q0 + min(qq, nq - 1);
-            sa[i] = a.qf_rot[node * F + c]; sb[i] = a.key_f[node * F + c];
+            const int row = q0 + min(qq, nq - 1);
+            const size_t node = (size_t)t0 * a.n_q + row;
+            float v;
+            if (a.qf_rot) {
+                v = a.qf_rot[node * F + c];
+            } else {
+                const float* f = a.qf + (size_t)(row % a.n_q) * F;
+                const float* sR = srd + (row / a.n_q) * 36;
+                const float* sD2 = sR + 9;
+                if (c < M0) v = f[c];
+                else if (c < M0 + 3 * M1) {
+                    const int u = (c - M0) / 3, m = (c - M0) % 3;
+                    const float* fu = f + M0 + 3 * u;
+                    v = sR[m * 3] * fu[0] + sR[m * 3 + 1] * fu[1] + sR[m * 3 + 2] * fu[2];
+                } else {
+                    const int u = (c - M0 - 3 * M1) / 5, m = (c - M0 - 3 * M1) % 5;
+                    const float* fu = f + M0 + 3 * M1 + 5 * u;
+                    v = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) v = fmaf(sD2[m * 5 + j], fu[j], v);
+                }
+            }
+            sa[i] = v; sb[i] = a.key_f[node * F + c];
         }
         __syncthreads();
         // step 1: t_p[u][j] = sum_v W_p[u][v] b_{l2}[v][j] for both tensor products and both query nodes: one thread per
@@ -387,8 +471,26 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
             ang[0] += w * (ox + s[0]); ang[1] += w * (oy + s[1]); ang[2] += w * (oz + s[2]);
         }
         for (int i = 0; i < 3; ++i) { a.lin_out[(size_t)t * 3 + i] = lin[i]; a.ang_out[(size_t)t * 3 + i] = ang[i]; }
+        if (a.T64) {
+            // fused Langevin step of pose t (pose_update_kernel + cast_pose_kernel); every CTA read `step_now` before any
+            // CTA can advance the counter (the last ticket holder does, below)
+            const double* row = a.sched + (size_t)min(step_now, a.n_steps - 1) * 4;
+            double* Td = a.T64 + (size_t)t * 7;
+            langevin_step(Td, ang, lin, a.noise ? a.noise + ((size_t)step_now * a.n_t + t) * 6 : nullptr,
+                          a.seed_dev ? *a.seed_dev : a.seed, (unsigned long long)t,
+                          (unsigned long long)step_now, row[0], a.ang_mult_d, a.lin_mult_d, row[1], row[2], row[3]);
+            if (a.traj) for (int k = 0; k < 7; ++k) a.traj[((size_t)(step_now + 1) * a.n_t + t) * 7 + k] = Td[k];
+            for (int k = 0; k < 7; ++k) a.T32[(size_t)t * 7 + k] = (float)Td[k];
+        }
     }
     }   // poses of this CTA
+    if (a.T64) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) { *a.ticket = 0; __threadfence(); *a.counter = step_now + 1; }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -423,7 +525,8 @@ struct PoseArgs {
     double* T; int n_t;                 // (n_t,7) in place
     const float* ang; const float* lin; // dimensionless scores (n_t,3)
     const double* noise;                // (n_t,6) standard normals (ang, lin) or null -> Philox
-    unsigned long long seed, offset;
+    unsigned long long seed, offset;    // Philox: (seed, subsequence = pose); `offset` = STEP index, each step owns a disjoint
+                                        // window of kPhiloxPerStep 32-bit outputs of the pose's stream (see pose_update_kernel)
     double t, ang_mult, lin_mult, alpha_ang, alpha_lin, temperature;
     double* traj_out;                   // optional (n_t,7) copy of the new pose
     const double* dev_row;              // optional device row [t, alpha_ang, alpha_lin, temperature] overriding the host values
@@ -440,39 +543,9 @@ __global__ void pose_update_kernel(PoseArgs a) {
         if (a.noise) a.noise += (size_t)step * a.n_t * 6;
         if (a.traj_out) a.traj_out += (size_t)(step + 1) * a.n_t * 7;
     }
-    double z[6];
-    if (a.noise) {
-        for (int k = 0; k < 6; ++k) z[k] = a.noise[(size_t)i * 6 + k];
-    } else {
-        curandStatePhilox4_32_10_t st;
-        curand_init(a.seed, (unsigned long long)i, a.offset, &st);
-        for (int k = 0; k < 6; k += 2) { double2 n = curand_normal2_double(&st); z[k] = n.x; z[k + 1] = n.y; }
-    }
     double* T = a.T + (size_t)i * 7;
-    const double sq_t = sqrt(a.t);
-    double ang_disp[3], lin_disp[3];
-    for (int k = 0; k < 3; ++k) {
-        const double as = (double)a.ang[(size_t)i * 3 + k] / (a.ang_mult * sq_t);
-        const double ls = (double)a.lin[(size_t)i * 3 + k] / (a.lin_mult * sq_t);
-        ang_disp[k] = (a.alpha_ang / 2) * as + sqrt(a.temperature * a.alpha_ang) * z[k];
-        lin_disp[k] = (a.alpha_lin / 2) * ls + sqrt(a.temperature * a.alpha_lin) * z[3 + k];
-    }
-    const double q[4] = {T[0], T[1], T[2], T[3]};
-    // L = T[q_indices] * q_factor   (score_model_base.py:31-32,188)
-    const int qi[4][3] = {{1, 2, 3}, {0, 3, 2}, {3, 0, 1}, {2, 1, 0}};
-    const double qf[4][3] = {{-0.5, -0.5, -0.5}, {0.5, -0.5, 0.5}, {0.5, 0.5, -0.5}, {-0.5, 0.5, 0.5}};
-    double qn[4], nrm = 0;
-    for (int r = 0; r < 4; ++r) {
-        double dq = 0;
-        for (int c = 0; c < 3; ++c) dq += q[qi[r][c]] * qf[r][c] * ang_disp[c];
-        qn[r] = q[r] + dq;
-        nrm += qn[r] * qn[r];
-    }
-    nrm = sqrt(nrm);
-    double dx[3];
-    quat_apply<double>(q, lin_disp, dx);
-    for (int r = 0; r < 4; ++r) T[r] = qn[r] / nrm;
-    for (int k = 0; k < 3; ++k) T[4 + k] += dx[k];
+    langevin_step(T, a.ang + (size_t)i * 3, a.lin + (size_t)i * 3, a.noise ? a.noise + (size_t)i * 6 : nullptr, a.seed,
+                  (unsigned long long)i, a.offset, a.t, a.ang_mult, a.lin_mult, a.alpha_ang, a.alpha_lin, a.temperature);
     if (a.traj_out) for (int k = 0; k < 7; ++k) a.traj_out[(size_t)i * 7 + k] = T[k];
 }
 
@@ -532,39 +605,29 @@ extern "C" int dedf_query_transform(const float* Ts, int n_t, const float* qx, c
     return DEDF_OK;
 }
 
-extern "C" int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, const float* key_f, const float* qx,
-                             const float* qw, int n_q, const int* irr, const float* const* Wd, const float* const* Wl0,
-                             const float* const* Wl1, const float* const* bl, int n_vec, float lin_mult,
-                             float* ang_out, float* lin_out, cudaStream_t stream) {
-    if (!Ts || !qf_rot || !key_f || !qx || !qw || !irr || !Wd || !Wl0 || !Wl1 || !bl || !ang_out || !lin_out) return DEDF_ERR_ARG;
-    if (n_t <= 0) return DEDF_OK;
-    ScoreArgs a{};
-    a.Ts = Ts; a.n_t = n_t; a.qf_rot = qf_rot; a.key_f = key_f; a.qx = qx; a.qw = qw; a.n_q = n_q;
-    a.irr = Irr{irr[0], irr[1], irr[2]};
-    for (int i = 0; i < 2; ++i) { a.Wd[i] = Wd[i]; a.Wl0[i] = Wl0[i]; a.Wl1[i] = Wl1[i]; a.bl[i] = bl[i];
-                                  if (!Wd[i] || !Wl0[i] || !Wl1[i] || !bl[i]) return DEDF_ERR_ARG; }
-    a.n_vec = n_vec; a.lin_mult = lin_mult; a.ang_out = ang_out; a.lin_out = lin_out;
+static int launch_score_tp(ScoreArgs a, cudaStream_t stream) {
+    const int n_t = a.n_t, n_q = a.n_q, n_vec = a.n_vec;
     const int M0 = a.irr.m0, M1 = a.irr.m1, M2 = a.irr.m2, F = a.irr.dim();
     const int tt = M0 + 3 * M0 + M1 + 3 * M1 + 3 * M1 + 5 * M1 + 3 * M2 + 5 * M2 + 5 * M2;
     const int D0 = M0 + M1 + M2, D1 = M0 + 3 * M1 + 2 * M2;
     if ((M0 % 4) || (M1 % 4) || (M2 % 4) || (D0 % 4) || (D1 % 4)) return DEDF_ERR_UNSUPPORTED;
     const int pb = 1, qb = kScoreQB;
     if (1 + 4 * n_vec > tt) return DEDF_ERR_UNSUPPORTED;      // the linear outputs reuse the t buffers
-    const size_t act = (size_t)(qb * (2 * F + 2 * (tt + D0 + 3 * D1)) + ((6 * pb * n_q + 3) & ~3)) * sizeof(float);
+    const size_t act = (size_t)(qb * (2 * F + 2 * (tt + D0 + 3 * D1)) + ((6 * pb * n_q + 3) & ~3) + 36 * pb) * sizeof(float);
     const int nWd = M0 * M0 + M0 * M1 + M1 * M0 + 2 * M1 * M1 + M1 * M2 + M2 * M1 + 2 * M2 * M2;
     const size_t wbytes = (size_t)2 * (nWd + D1 * n_vec) * sizeof(float);
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     // Up to two poses per SM: persistent CTAs with the weights resident in shared memory (37 us vs 70 us at 128 poses).
     // Larger batches: one CTA per pose, weights through L1/L2, three CTAs per SM hide each other's latency (139 us at 1024
     // poses; the resident variant runs one 12-warp CTA per SM and takes 181 us).
-    const bool w_smem = n_t <= 2 * kNumSMs && act + wbytes <= 226 * 1024 && al16(Wd[0]) && al16(Wd[1]) && al16(Wl1[0]) && al16(Wl1[1]) &&
+    const bool w_smem = n_t <= 2 * kNumSMs && act + wbytes <= 226 * 1024 && al16(a.Wd[0]) && al16(a.Wd[1]) && al16(a.Wl1[0]) && al16(a.Wl1[1]) &&
                         (nWd % 4 == 0) && ((D1 * n_vec) % 4 == 0) && !getenv("DEDF_NO_SMEM_SCORE");
     // More than two poses per SM: 8 (pose, query node) rows per weight pass.  Every weight load then serves 8 rows of both tensor
     // products, so the L2 stream of the 218 KB of weights -- what bounds the one-pose-per-CTA form -- shrinks 4x.
     if (n_t > 2 * kNumSMs && !getenv("DEDF_SCORE_QB2")) {
         constexpr int QB8 = 8;
         const int pb8 = QB8 / n_q > 1 ? QB8 / n_q : 1;
-        const size_t act8 = (size_t)(QB8 * (2 * F + 2 * (tt + D0 + 3 * D1)) + ((6 * pb8 * n_q + 3) & ~3)) * sizeof(float);
+        const size_t act8 = (size_t)(QB8 * (2 * F + 2 * (tt + D0 + 3 * D1)) + ((6 * pb8 * n_q + 3) & ~3) + 36 * pb8) * sizeof(float);
         if (act8 <= 226 * 1024) {
             static bool done8 = false;
             if (!done8) { cudaFuncSetAttribute(score_tp_kernel<QB8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); done8 = true; }
@@ -581,6 +644,40 @@ extern "C" int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, cons
     else launch_pdl(score_tp_kernel<kScoreQB>, dim3((n_t + pb - 1) / pb), dim3(256), smem, stream, a, pb, 0);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
+}
+
+extern "C" int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, const float* key_f, const float* qx,
+                             const float* qw, int n_q, const int* irr, const float* const* Wd, const float* const* Wl0,
+                             const float* const* Wl1, const float* const* bl, int n_vec, float lin_mult,
+                             float* ang_out, float* lin_out, cudaStream_t stream) {
+    if (!Ts || !qf_rot || !key_f || !qx || !qw || !irr || !Wd || !Wl0 || !Wl1 || !bl || !ang_out || !lin_out) return DEDF_ERR_ARG;
+    if (n_t <= 0) return DEDF_OK;
+    ScoreArgs a{};
+    a.Ts = Ts; a.n_t = n_t; a.qf_rot = qf_rot; a.key_f = key_f; a.qx = qx; a.qw = qw; a.n_q = n_q;
+    a.irr = Irr{irr[0], irr[1], irr[2]};
+    for (int i = 0; i < 2; ++i) { a.Wd[i] = Wd[i]; a.Wl0[i] = Wl0[i]; a.Wl1[i] = Wl1[i]; a.bl[i] = bl[i];
+                                  if (!Wd[i] || !Wl0[i] || !Wl1[i] || !bl[i]) return DEDF_ERR_ARG; }
+    a.n_vec = n_vec; a.lin_mult = lin_mult; a.ang_out = ang_out; a.lin_out = lin_out;
+    return launch_score_tp(a, stream);
+}
+
+extern "C" int dedf_score_tp_step(const dedf_score_step_desc* d, cudaStream_t stream) {
+    if (!d || !d->Ts || !d->qf || !d->key_f || !d->qx || !d->qw || !d->ang_out || !d->lin_out) return DEDF_ERR_ARG;
+    if (d->n_t <= 0) return DEDF_OK;
+    ScoreArgs a{};
+    a.Ts = d->Ts; a.n_t = d->n_t; a.qf_rot = nullptr; a.qf = d->qf; a.key_f = d->key_f; a.qx = d->qx; a.qw = d->qw; a.n_q = d->n_q;
+    a.irr = Irr{d->irr[0], d->irr[1], d->irr[2]};
+    for (int i = 0; i < 2; ++i) { a.Wd[i] = d->Wd[i]; a.Wl0[i] = d->Wl0[i]; a.Wl1[i] = d->Wl1[i]; a.bl[i] = d->bl[i];
+                                  if (!a.Wd[i] || !a.Wl0[i] || !a.Wl1[i] || !a.bl[i]) return DEDF_ERR_ARG; }
+    a.n_vec = d->n_vec; a.lin_mult = d->lin_mult; a.ang_out = d->ang_out; a.lin_out = d->lin_out;
+    if (d->T64) {           // fused Langevin step
+        if (!d->sched || d->n_steps < 1 || !d->counter || !d->T32 || !d->ticket) return DEDF_ERR_ARG;
+        if (d->T32 != d->Ts) return DEDF_ERR_ARG;       // the fp32 copy the network reads IS the one the step refreshes
+        a.T64 = d->T64; a.sched = d->sched; a.n_steps = d->n_steps; a.counter = d->counter; a.noise = d->noise; a.seed = d->seed;
+        a.seed_dev = d->seed_dev;
+        a.ang_mult_d = d->ang_mult; a.lin_mult_d = d->lin_mult_d; a.traj = d->traj; a.T32 = d->T32; a.ticket = d->ticket;
+    }
+    return launch_score_tp(a, stream);
 }
 
 extern "C" int dedf_pose_update(double* T, int n_t, const float* ang, const float* lin, const double* noise,

@@ -1,0 +1,310 @@
+// The front of one score-head evaluation in ONE launch: pose transform of the query points, multi-scale radius search against
+// the (static) scene scales, CSR construction, and the edge geometry.
+//
+// Replaces five launches of the un-fused path (query_transform [points], radius count, exclusive scan, radius fill, edge_geom)
+// and, inside a denoise loop, dedf_sample_advance:
+//   gnn_data.py:88-100 + edf_interface/.../pcd_utils.py:55-81   x' = R(q) x + t            (TransformPcd, points only)
+//   graph_parser.py:336-345 (torch_cluster.radius, <= max_num_neighbors, ascending sources), :272-286 (all pairs)
+//   multiscale_tensor_field.py:236-247   per-scale edge lists concatenated in scale order, sources offset by sum N_prev
+//   graph_parser.py:146-224               edge vector / length / spherical harmonics / soft cut-offs / edge logits
+//
+// Edges come out in exactly the order of the un-fused kernels -- (scale, destination, source ascending) -- and with exactly
+// their arithmetic (same exact squared distance, same geometry expressions), so every index is bit-identical.
+//
+// Structure: items = (scale, destination) pairs in CSR order, partitioned over the CTAs in contiguous, COST-balanced ranges
+// (an item of a scale with N_s sources costs ceil(N_s / 128) warp iterations).  Each CTA stages the source clouds of the
+// scales it touches in shared memory (scene data: BEFORE the PDL wait, overlapping the previous kernel's tail), then
+//   phase 1: one warp per item walks the sources 128 at a time, counts the neighbours (ballots);
+//   grid barrier (all CTAs are co-resident: grid <= #SMs; dependents are released only after it);
+//   phase 2: CTA offset = sum of the preceding CTAs' totals, block scan of its own counts -> row_ptr; the warps walk their
+//            items again and write edge_src / edge_dst / length / sh / logit for every kept neighbour.
+// The walk is brute force on purpose: with the sources in shared memory it costs ~1 us for the score head's <= 2.5 k scene
+// points, keeps the sources ascending for free and has no per-scene state to cache; the grid-hash kernels (graph.cu) are for the
+// 10^4-point clouds of the key encoder.
+#include "common.cuh"
+#include "so3.cuh"
+#include "../../include/dedf.h"
+
+namespace dedf {
+
+__device__ __forceinline__ float sqdist_exact_hf(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+constexpr int kFrontThreads = 256;
+constexpr int kFrontWarps = kFrontThreads / 32;
+constexpr int kFrontU = 4;                      // 32-source chunks per warp iteration
+
+struct FrontArgs {
+    const float* Ts; int n_t;
+    const float* qx; int n_q;
+    const float* x_src; const long long* b_src; const long long* b_q;
+    int n_scales, max_nb, capacity;
+    int src_off[DEDF_MAX_SCALES + 1];
+    float r[DEDF_MAX_SCALES];
+    float ns_lo, ns_hi;
+    float* x_dst; int* row_ptr; int* counts; int* edge_src; int* edge_dst;
+    float* length; float* sh; float* logit;
+    int* n_edges; int* overflow;
+    int* cta_sum; unsigned* barrier;
+    // denoise loop (optional): this step's rows of the precomputed time embedding
+    const int* step; int n_steps; const float* rows_all; float* rows_cur; int rows_k;
+    int stage_early;                            // the sources are static (denoise loop): stage them before the PDL wait
+    long long cost[DEDF_MAX_SCALES + 1];        // cumulative cost at the start of every scale (n_dst * c_s summed)
+    int c[DEDF_MAX_SCALES];                     // cost per item of the scale
+};
+
+// first item whose cumulative cost reaches `t`
+__device__ __forceinline__ int front_bound(const FrontArgs& a, long long t, int n_dst) {
+    int s = 0;
+    while (s + 1 < a.n_scales && t >= a.cost[s + 1]) ++s;
+    if (t >= a.cost[a.n_scales]) return a.n_scales * n_dst;
+    const long long d = (t - a.cost[s] + a.c[s] - 1) / a.c[s];
+    return s * n_dst + (int)(d < n_dst ? d : n_dst);
+}
+
+// reusable grid barrier (count, generation); every CTA of the grid must be resident (grid <= #SMs, see the launcher)
+__device__ __forceinline__ void front_grid_barrier(unsigned* bar, unsigned n_ctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned* vgen = bar + 1;
+        const unsigned gen = *vgen;                 // read BEFORE arriving: the generation cannot advance until we have
+        __threadfence();
+        if (atomicAdd(bar, 1u) == n_ctas - 1) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            long long spins = 0;
+            while (*vgen == gen) {
+                __nanosleep(32);
+                if (++spins > (1ll << 25)) __trap();      // ~1 s: a protocol bug becomes a launch error, not a hung GPU
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <bool FILL>
+__device__ __forceinline__ int front_walk(const FrontArgs& a, const float* xs, const int* sb, int stage_lo, int item, int n_dst,
+                                          int lane, int base, int seg_end) {
+    const int s = item / n_dst, d = item - s * n_dst;
+    const int s0 = a.src_off[s], s1 = a.src_off[s + 1];
+    const float r = a.r[s];
+    const bool all = r < 0.f;
+    const float r2 = r * r;
+    const int cap_nb = all ? 0x7fffffff : a.max_nb;     // the all-pairs scale has no neighbour cap (graph_parser.py:274-278)
+    // x' = R(q) x + t, the arithmetic of query_transform_kernel
+    const int t = d / a.n_q, qi = d - t * a.n_q;
+    const float* T = a.Ts + (size_t)t * 7;
+    const float q4[4] = {T[0], T[1], T[2], T[3]};
+    const float p[3] = {a.qx[3 * qi], a.qx[3 * qi + 1], a.qx[3 * qi + 2]};
+    float o[3];
+    quat_apply<float>(q4, p, o);
+    const float qx = o[0] + T[4], qy = o[1] + T[5], qz = o[2] + T[6];
+    if (!FILL && s == 0 && lane == 0) { a.x_dst[3 * d] = qx; a.x_dst[3 * d + 1] = qy; a.x_dst[3 * d + 2] = qz; }
+    const long long qb = a.b_q ? a.b_q[qi] : 0;
+    int cnt_all = 0, cnt_keep = 0;
+    for (int c0 = s0; c0 < s1 && cnt_all < cap_nb; c0 += 32 * kFrontU) {
+        bool hit[kFrontU];
+        float sx[kFrontU], sy[kFrontU], sz[kFrontU];
+#pragma unroll
+        for (int u = 0; u < kFrontU; ++u) {
+            const int i = c0 + 32 * u + lane;
+            hit[u] = false;
+            if (i < s1) {
+                const float* ps = xs + 3 * (i - stage_lo);
+                sx[u] = ps[0]; sy[u] = ps[1]; sz[u] = ps[2];
+                hit[u] = all || sqdist_exact_hf(sx[u], sy[u], sz[u], qx, qy, qz) < r2;
+                if (sb && !all) hit[u] = hit[u] && ((long long)sb[i - stage_lo] == qb);     // all pairs ignores batches (:276-278)
+            }
+        }
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int u = 0; u < kFrontU; ++u) {
+            const unsigned bal = __ballot_sync(0xffffffffu, hit[u]);
+            const bool keep = hit[u] && (cnt_all + __popc(bal & lt) < cap_nb);
+            const unsigned bal_keep = __ballot_sync(0xffffffffu, keep);
+            if (FILL && keep) {
+                const int pos = base + cnt_keep + __popc(bal_keep & lt);
+                if (pos < seg_end) {
+                    const int i = c0 + 32 * u + lane;
+                    a.edge_src[pos] = i;
+                    a.edge_dst[pos] = d;
+                    // edge geometry: the expressions of edge_geom_kernel
+                    const float vx = sx[u] - qx, vy = sy[u] - qy, vz = sz[u] - qz;
+                    const float len = sqrtf(vx * vx + vy * vy + vz * vz);
+                    const float inv = 1.0f / fmaxf(len, 1e-12f);
+                    float shv[9];
+                    sph_harm_l2(vx * inv, vy * inv, vz * inv, shv);
+                    if (a.ns_hi > 0.f) {
+                        const float cc = soft_step3((len - a.ns_lo) / (a.ns_hi - a.ns_lo));
+#pragma unroll
+                        for (int j = 1; j < 9; ++j) shv[j] *= cc;
+                    }
+                    a.length[pos] = len;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) a.sh[(size_t)pos * 9 + j] = shv[j];
+                    float lg = 0.f;
+                    if (!all) {
+                        const float cut = 1.0f - soft_step3((len - 0.8f * r) / (r - 0.8f * r));
+                        lg = logf(fmaxf(cut, 1e-12f));
+                    }
+                    a.logit[pos] = lg;
+                }
+            }
+            cnt_all += __popc(bal);
+            cnt_keep += __popc(bal_keep);
+        }
+    }
+    return cnt_keep;
+}
+
+__global__ void __launch_bounds__(kFrontThreads) head_front_kernel(FrontArgs a) {
+    extern __shared__ __align__(16) float s_x[];
+    __shared__ int s_scan[kFrontThreads];
+    __shared__ int s_base, s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_dst = a.n_t * a.n_q;
+    const int n_items = a.n_scales * n_dst;
+    const long long ctot = a.cost[a.n_scales];
+    const int G = gridDim.x, b = blockIdx.x;
+    const int i_lo = front_bound(a, (ctot * b + G - 1) / G, n_dst), i_hi = (b == G - 1) ? n_items : front_bound(a, (ctot * (b + 1) + G - 1) / G, n_dst);
+    // ---- stage the source clouds of this CTA's scales (scene data: independent of the previous kernel) ----
+    int stage_lo = 0, stage_hi = 0;
+    if (i_hi > i_lo) {
+        stage_lo = a.src_off[i_lo / n_dst];
+        stage_hi = a.src_off[(i_hi - 1) / n_dst + 1];
+    }
+    const int n_st = stage_hi - stage_lo;
+    int* s_b = a.b_src ? reinterpret_cast<int*>(s_x + 3 * n_st) : nullptr;
+    if (!a.stage_early) pdl_wait();     // the sources were produced earlier in this stream (plain forward): wait first
+    {
+        constexpr int UX = 12;
+        const float* src = a.x_src + 3 * (size_t)stage_lo;
+        const int n3 = 3 * n_st;
+        for (int i0 = tid; i0 < n3; i0 += kFrontThreads * UX) {
+            float v[UX];
+#pragma unroll
+            for (int k = 0; k < UX; ++k) { const int i = i0 + k * kFrontThreads; v[k] = (i < n3) ? __ldg(src + i) : 0.f; }
+#pragma unroll
+            for (int k = 0; k < UX; ++k) { const int i = i0 + k * kFrontThreads; if (i < n3) s_x[i] = v[k]; }
+        }
+        if (s_b) for (int i = tid; i < n_st; i += kFrontThreads) s_b[i] = (int)__ldg(a.b_src + stage_lo + i);
+    }
+    if (a.stage_early) pdl_wait();      // the poses come from the previous kernel (the previous step's pose update)
+    if (b == 0 && a.rows_all) {   // this step's time rows (the job of dedf_sample_advance)
+        const int st = min(*a.step, a.n_steps - 1);
+        for (int j = tid; j < a.n_scales * a.rows_k; j += kFrontThreads)
+            a.rows_cur[j] = a.rows_all[((size_t)(j / a.rows_k) * a.n_steps + st) * a.rows_k + (j % a.rows_k)];
+    }
+    __syncthreads();
+    // ---- phase 1: counts ----
+    int my_sum = 0;
+    for (int item = i_lo + warp; item < i_hi; item += kFrontWarps) {
+        const int cnt = front_walk<false>(a, s_x, s_b, stage_lo, item, n_dst, lane, 0, 0);
+        if (lane == 0) { a.counts[item] = cnt; my_sum += cnt; }
+    }
+    s_scan[tid] = (lane == 0) ? my_sum : 0;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < kFrontWarps; ++w) t += s_scan[w * 32];
+        a.cta_sum[b] = t;
+    }
+    front_grid_barrier(a.barrier, (unsigned)G);
+    pdl_launch();                 // only now: every CTA of this grid is resident, dependents cannot starve the barrier
+    // ---- phase 2: CSR offsets ----
+    if (warp == 0) {
+        int t = 0;
+        for (int j = lane; j < G; j += 32) {
+            const int v = __ldcg(a.cta_sum + j);
+            if (j < b) t += v;
+        }
+        t = __reduce_add_sync(0xffffffffu, t);
+        if (lane == 0) s_base = t;
+    }
+    __syncthreads();
+    const int cap = a.capacity > 0 ? a.capacity : 0x7fffffff;
+    int run = s_base;
+    for (int c0 = i_lo; c0 < i_hi; c0 += kFrontThreads) {
+        const int item = c0 + tid;
+        const int v = (item < i_hi) ? a.counts[item] : 0;
+        // inclusive block scan (Hillis-Steele over 256 entries)
+        s_scan[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < kFrontThreads; o <<= 1) {
+            const int u = (tid >= o) ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += u;
+            __syncthreads();
+        }
+        if (item < i_hi) a.row_ptr[item] = min(run + s_scan[tid] - v, cap);
+        const int chunk_total = s_scan[kFrontThreads - 1];
+        __syncthreads();
+        run += chunk_total;
+    }
+    if (tid == 0) s_total = run;
+    if (b == G - 1 && tid == 0) {
+        a.row_ptr[n_items] = min(run, cap);
+        *a.n_edges = min(run, cap);
+        if (a.overflow && run > cap) atomicOr(a.overflow, 1);
+    }
+    __syncthreads();              // this CTA's row_ptr entries are visible to its own warps
+    // ---- phase 3: fill + geometry ----
+    for (int item = i_lo + warp; item < i_hi; item += kFrontWarps) {
+        const int base = a.row_ptr[item];
+        const int end = (item + 1 < i_hi) ? a.row_ptr[item + 1] : min(s_total, cap);
+        front_walk<true>(a, s_x, s_b, stage_lo, item, n_dst, lane, base, end);
+    }
+}
+
+}  // namespace dedf
+
+using namespace dedf;
+
+extern "C" int dedf_head_front(const dedf_head_front_desc* d, cudaStream_t stream) {
+    if (!d || !d->Ts || !d->qx || !d->x_src || !d->x_dst || !d->row_ptr || !d->counts || !d->edge_src || !d->edge_dst || !d->length ||
+        !d->sh || !d->logit || !d->n_edges || !d->cta_sum || !d->barrier) return DEDF_ERR_ARG;
+    if (d->n_scales < 1 || d->n_scales > DEDF_MAX_SCALES || d->n_q < 1 || d->capacity < 0) return DEDF_ERR_ARG;
+    if (d->rows_all && (!d->rows_cur || !d->step || d->n_steps < 1 || d->rows_k < 1)) return DEDF_ERR_ARG;
+    if (d->n_t <= 0) return DEDF_OK;
+    FrontArgs a{};
+    a.Ts = d->Ts; a.n_t = d->n_t; a.qx = d->qx; a.n_q = d->n_q; a.x_src = d->x_src; a.b_src = d->b_src; a.b_q = d->b_q;
+    a.n_scales = d->n_scales; a.max_nb = d->max_num_neighbors; a.capacity = d->capacity;
+    a.ns_lo = d->ns_lo; a.ns_hi = d->ns_hi;
+    a.x_dst = d->x_dst; a.row_ptr = d->row_ptr; a.counts = d->counts; a.edge_src = d->edge_src; a.edge_dst = d->edge_dst;
+    a.length = d->length; a.sh = d->sh; a.logit = d->logit; a.n_edges = d->n_edges; a.overflow = d->overflow;
+    a.cta_sum = d->cta_sum; a.barrier = d->barrier;
+    a.stage_early = d->stage_early;
+    a.step = d->step; a.n_steps = d->n_steps; a.rows_all = d->rows_all; a.rows_cur = d->rows_cur; a.rows_k = d->rows_k;
+    const long long n_dst = (long long)d->n_t * d->n_q;
+    if (n_dst * d->n_scales > 0x7fffffffLL) return DEDF_ERR_ARG;
+    int max_stage = 0;
+    a.cost[0] = 0;
+    for (int s = 0; s < d->n_scales; ++s) {
+        a.src_off[s] = d->src_off[s]; a.r[s] = d->r[s];
+        const int ns = d->src_off[s + 1] - d->src_off[s];
+        if (ns < 0) return DEDF_ERR_ARG;
+        a.c[s] = (ns + 32 * kFrontU - 1) / (32 * kFrontU);
+        if (a.c[s] < 1) a.c[s] = 1;
+        a.cost[s + 1] = a.cost[s] + n_dst * a.c[s];
+    }
+    a.src_off[d->n_scales] = d->src_off[d->n_scales];
+    // a CTA's contiguous item range can span several scales: size the staging buffer for all of them
+    max_stage = d->src_off[d->n_scales] - d->src_off[0];
+    const size_t smem = (size_t)max_stage * (12 + (d->b_src ? 4 : 0)) + 16;
+    if (smem > 200 * 1024) return DEDF_ERR_UNSUPPORTED;         // larger scenes: the un-fused grid-hash path
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(head_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done = true; }
+    // grid <= #SMs (one CTA per SM is guaranteed co-resident: 256 threads, <= 200 KB): the grid barrier needs that
+    const long long items = n_dst * d->n_scales;
+    int grid = (int)((items + 1) / 2);                           // at least ~2 items per CTA
+    if (grid > kNumSMs) grid = kNumSMs;
+    if (grid < 1) grid = 1;
+    launch_pdl(head_front_kernel, dim3(grid), dim3(kFrontThreads), smem, stream, a);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}

@@ -22,6 +22,9 @@ from . import ops
 
 class GraphedCallable:
     def __init__(self, fn: Callable[..., Tuple[torch.Tensor, ...]], example_inputs: Sequence[torch.Tensor], margin: float = 1.5):
+        """Integer (int64) inputs are treated as LAYOUT inputs (batch ids): the recorded plan holds host values derived from them
+        (FPS segments, unique batch ids), so a replay first checks on the device that they equal the ones the plan was recorded
+        with and raises the overflow flag otherwise -- the call then re-plans instead of replaying stale segments."""
         self.fn = fn
         self.plan = ops.Plan(margin=margin)
         self.static_in: List[torch.Tensor] = [t.detach().clone() for t in example_inputs]
@@ -30,10 +33,12 @@ class GraphedCallable:
         self.static_out = None
         self.replays = 0
         self.n_kernels = 0
+        self.layout_ref: List[torch.Tensor] = []
         self._build()
 
     def _build(self):
         with torch.no_grad():
+            self.layout_ref = [t.clone() if t.dtype == torch.long else None for t in self.static_in]
             with ops.use_plan(self.plan, "record"):
                 self.eager_out = self.fn(*self.static_in)
             cur = torch.cuda.current_stream()
@@ -48,6 +53,9 @@ class GraphedCallable:
             k0 = ops.LAUNCHES
             with torch.cuda.graph(self.graph):
                 self.overflow.zero_()
+                for cur_in, ref in zip(self.static_in, self.layout_ref):
+                    if ref is not None and ref.numel():
+                        ops.flag_if_differs(cur_in, ref, self.overflow)
                 with ops.use_plan(self.plan, "replay", self.overflow):
                     self.static_out = self.fn(*self.static_in)
             self.n_kernels = ops.LAUNCHES - k0                 # kernels of libdedf.so inside one replay

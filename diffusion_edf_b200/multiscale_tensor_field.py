@@ -52,6 +52,8 @@ class MultiscaleTensorField(nn.Module):
             raise NotImplementedError("query (dst) features are not used by the shipped configs (query_time_encoding: False)")
         if cutoff_method != "edge_attn" or attn_type != "mlp" or n_layers != 1:
             raise NotImplementedError("only cutoff_method='edge_attn', attn_type='mlp', n_layers=1 are implemented")
+        if drop_path_rate and float(drop_path_rate) > 0.0:
+            raise NotImplementedError("drop_path_rate > 0 (GraphDropPath, gnn_block.py:156,205-214) is not implemented; every shipped config uses 0.0")
         self.use_dst_feature = False
         self.alpha_drop, self.proj_drop = float(alpha_drop), float(proj_drop)       # train mode only (train_path.py)
         self.num_heads = num_heads
@@ -133,7 +135,6 @@ class MultiscaleTensorField(nn.Module):
         assert (time_rows is not None) == (self.context_emb_dim is not None)
         srcs = sources if sources is not None else self.encode_sources(input_points_multiscale)
         x_src, b_src, src_off, msg_src = srcs[:4]
-        w_src = srcs[4] if len(srcs) > 4 else None
         xq = query_points.x.contiguous()
         radii = self.r_cluster_multiscale
         g = ops.radius_csr(x_src, xq, radii, src_off=src_off, b_src=b_src, b_dst=query_points.b.contiguous(),
@@ -141,11 +142,35 @@ class MultiscaleTensorField(nn.Module):
         ns = self.r_mincut_nonscalar_sh
         length, sh, logit = ops.edge_geom(x_src, xq, g, radii=radii, src_off=src_off, ns_cut=(0.2 * ns, 1.0 * ns),
                                           want_logit=True)
+        out = self.attend_edges(g, length, sh, logit, srcs, time_rows, rows_per_time)
+        return FeaturedPoints(x=query_points.x, f=out, b=query_points.b, w=query_points.w)
+
+    def forward_poses(self, Ts: torch.Tensor, query_pcd: FeaturedPoints, sources, *, time_rows: Optional[torch.Tensor] = None,
+                      max_neighbors: int = 1000, edge_capacity: Optional[int] = None, step: Optional[torch.Tensor] = None,
+                      rows_all: Optional[torch.Tensor] = None, static_sources: bool = False) -> torch.Tensor:
+        """The field at the pose-transformed query points ``T_t . x_q`` for every pose t and query point q, rows ordered (t, q):
+        ``forward(TransformPcd(query_pcd, Ts).flatten(), ...)`` with the point transform, the radius search, the CSR and the edge
+        geometry fused into one launch (dedf_head_front).  -> (n_t * n_q, F) features.  Denoise loop: ``step`` (device step index)
+        and ``rows_all`` (n_scales, n_steps, K) select this step's time rows, which are written to ``time_rows`` (n_scales, 1, K)."""
+        x_src, b_src, src_off, msg_src = sources[:4]
+        ns = self.r_mincut_nonscalar_sh
+        g, length, sh, logit, _ = ops.head_front(Ts, query_pcd.x.contiguous(), query_pcd.b.contiguous(), x_src, b_src, src_off,
+                                                 self.r_cluster_multiscale, (0.2 * ns, 1.0 * ns), max_num_neighbors=max_neighbors,
+                                                 capacity=edge_capacity, step=step, rows_all=rows_all,
+                                                 rows_cur=time_rows if rows_all is not None else None, static_sources=static_sources)
+        return self.attend_edges(g, length, sh, logit, sources, time_rows, query_pcd.x.shape[0])
+
+    def attend_edges(self, g: ops.Csr, length: torch.Tensor, sh: torch.Tensor, logit: torch.Tensor, srcs, time_rows: Optional[torch.Tensor],
+                     rows_per_time: int) -> torch.Tensor:
+        """Edge scalars -> per-edge tensor-product weights -> the attention block, on a finished graph."""
+        assert (time_rows is not None) == (self.context_emb_dim is not None)
+        x_src, b_src, src_off, msg_src = srcs[:4]
+        w_src = srcs[4] if len(srcs) > 4 else None
         # length embedding + pre-linear (+ time rows) -> h0 ; RadialProfile -> per-edge TP weights
         wl, _, pre_bias = self.packed_prelinear()
         K = self.fc_neurons[0]
         E = max(1, g.n_edges)
-        dev = xq.device
+        dev = length.device
         d = L.MlpDesc()
         d.mode = L.MLP_IN_FIELD
         d.n_edges_dev = L.ptr(g.n_edges_dev, torch.int32)
@@ -202,5 +227,4 @@ class MultiscaleTensorField(nn.Module):
             d2.out = L.ptr(w)
             ops.edge_mlp(d2, g.n_edges)
 
-        out = self.gnn_block_init(msg_src, g, sh, w, logit, w_src)
-        return FeaturedPoints(x=query_points.x, f=out, b=query_points.b, w=query_points.w)
+        return self.gnn_block_init(msg_src, g, sh, w, logit, w_src)

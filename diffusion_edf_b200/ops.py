@@ -133,6 +133,12 @@ def prefetch_l2(table) -> None:
     _call("dedf_prefetch_l2", ptrs.data_ptr(), sizes.data_ptr(), n, stream())
 
 
+def flag_if_differs(a: torch.Tensor, b: torch.Tensor, flag: torch.Tensor) -> None:
+    """flag |= 1 on the device if the int64 tensors differ (no host synchronisation)."""
+    assert a.shape == b.shape
+    _call("dedf_flag_if_differs", ptr(a, torch.long), ptr(b, torch.long), a.numel(), ptr(flag, torch.int32), stream())
+
+
 def tc_selftest(A: torch.Tensor, B: torch.Tensor, n_split: int = 3) -> torch.Tensor:
     """D = A @ B.T on the tcgen05 tensor cores (A: (128, K), B: (N, K)); see include/dedf.h."""
     assert A.shape[0] == 128 and A.shape[1] == B.shape[1]
@@ -247,6 +253,83 @@ def radius_csr(x_src: torch.Tensor, x_dst: torch.Tensor, radii: Sequence[Optiona
                                max_num_neighbors, ptr(row_ptr, torch.int32), ptr(edge_src, torch.int32),
                                ptr(edge_dst, torch.int32), stream())
     return Csr(row_ptr, edge_src[:n_edges], edge_dst[:n_edges], n_edges_dev, n_edges, n_dst, n_scales)
+
+
+USE_HEAD_FRONT = True   # pose transform + radius search + CSR + edge geometry of the score head in one launch (dedf_head_front)
+_FRONT_WS = {}          # (device, stream) -> (cta_sum, barrier): the kernel's device-wide barrier state, zeroed once
+
+
+def head_front(Ts: torch.Tensor, qx: torch.Tensor, b_q: Optional[torch.Tensor], x_src: torch.Tensor, b_src: Optional[torch.Tensor],
+               src_off: Sequence[int], radii: Sequence[Optional[float]], ns_cut: Tuple[float, float], max_num_neighbors: int = 1000,
+               capacity: Optional[int] = None, overflow: Optional[torch.Tensor] = None, step: Optional[torch.Tensor] = None,
+               rows_all: Optional[torch.Tensor] = None, rows_cur: Optional[torch.Tensor] = None, static_sources: bool = False):
+    """-> (Csr, length (E), sh (E, 9), logit (E), x_dst (n_t * n_q, 3)); see include/dedf.h (dedf_head_front).  Exact CSR with one host
+    sync to size the edge buffers, unless ``capacity`` is given (or a ``Plan`` is replaying): then nothing synchronises, the CSR is
+    clamped on the device and ``overflow`` is raised if the capacity was exceeded."""
+    n_t, n_q, n_scales = Ts.shape[0], qx.shape[0], len(radii)
+    n_dst = n_t * n_q
+    dev = Ts.device
+    if capacity is None and replaying():
+        capacity = _PLAN.capacity(_PLAN.value(None))
+        overflow = _PLAN.overflow
+    key = (dev, stream())
+    if key not in _FRONT_WS:
+        _FRONT_WS[key] = (torch.empty(256, dtype=torch.int32, device=dev), torch.zeros(2, dtype=torch.int32, device=dev))
+    cta_sum, barrier = _FRONT_WS[key]
+    d = L.HeadFrontDesc()
+    d.Ts, d.n_t, d.qx, d.n_q = ptr(Ts), n_t, ptr(qx), n_q
+    d.x_src, d.b_src, d.b_q = ptr(x_src), ptr(b_src, torch.long), ptr(b_q, torch.long)
+    d.n_scales = n_scales
+    for s in range(n_scales + 1):
+        d.src_off[s] = int(src_off[s])
+    for s, r in enumerate(radii):
+        d.r[s] = -1.0 if r is None else float(r)
+    d.max_num_neighbors, d.ns_lo, d.ns_hi = int(max_num_neighbors), float(ns_cut[0]), float(ns_cut[1])
+    x_dst = torch.empty(n_dst, 3, dtype=torch.float32, device=dev)
+    row_ptr = torch.empty(n_scales * n_dst + 1, dtype=torch.int32, device=dev)
+    counts = torch.empty(max(1, n_scales * n_dst), dtype=torch.int32, device=dev)
+    n_edges_dev = torch.empty(1, dtype=torch.int32, device=dev)
+    d.x_dst, d.row_ptr, d.counts = ptr(x_dst), ptr(row_ptr, torch.int32), ptr(counts, torch.int32)
+    d.n_edges, d.cta_sum, d.barrier = ptr(n_edges_dev, torch.int32), ptr(cta_sum, torch.int32), ptr(barrier, torch.int32)
+    d.stage_early = 1 if static_sources else 0
+    if rows_all is not None:
+        d.step, d.n_steps, d.rows_all, d.rows_cur, d.rows_k = ptr(step, torch.int32), rows_all.shape[1], ptr(rows_all), ptr(rows_cur), rows_all.shape[2]
+
+    def run(cap: int):
+        e_src = torch.empty(cap, dtype=torch.int32, device=dev)
+        e_dst = torch.empty(cap, dtype=torch.int32, device=dev)
+        length = torch.empty(cap, dtype=torch.float32, device=dev)
+        sh = torch.empty(cap, 9, dtype=torch.float32, device=dev)
+        logit = torch.empty(cap, dtype=torch.float32, device=dev)
+        d.capacity = cap
+        d.edge_src, d.edge_dst = ptr(e_src, torch.int32), ptr(e_dst, torch.int32)
+        d.length, d.sh, d.logit = ptr(length), ptr(sh), ptr(logit)
+        _call("dedf_head_front", C.byref(d), stream())
+        return e_src, e_dst, length, sh, logit
+
+    if capacity is not None:
+        cap = max(1, int(capacity))
+        d.overflow = ptr(overflow, torch.int32)
+        e_src, e_dst, length, sh, logit = run(cap)
+        return Csr(row_ptr, e_src, e_dst, n_edges_dev, cap, n_dst, n_scales), length, sh, logit, x_dst
+    # eager: guess a capacity, read the true count back (the one host sync of a graph build), re-run if the guess was too small
+    ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+    d.overflow = ptr(ovf, torch.int32)
+    bufs = [run(max(1024, 64 * n_dst))]
+
+    def read_count() -> int:
+        # the device clamps the count to the capacity: the overflow flag says whether it is the true one
+        n, over = torch.cat([n_edges_dev, ovf]).tolist()
+        if over:
+            n = int(counts.sum().item())
+            ovf.zero_()
+            bufs[0] = run(max(1, n))
+        return int(n)
+
+    n_edges = plan_value(read_count)
+    e_src, e_dst, length, sh, logit = bufs[0]
+    E = max(1, n_edges)
+    return (Csr(row_ptr, e_src[:n_edges], e_dst[:n_edges], n_edges_dev, n_edges, n_dst, n_scales), length[:E], sh[:E], logit[:E], x_dst)
 
 
 def radius(x: torch.Tensor, y: torch.Tensor, r: float, batch_x: Optional[torch.Tensor] = None,
@@ -370,6 +453,45 @@ def node_linear(x: torch.Tensor, irr_in, irr_out, W: Sequence[Optional[torch.Ten
     return y
 
 
+USE_NODE_CHAIN = True   # proj -> (+res) -> LN -> fctp_1 -> gate -> fctp_2 -> +res in one launch (dedf_node_chain) instead of three
+USE_LINEAR_PAIR = True  # linear_src / linear_dst of a UNet block in one launch (dedf_node_linear_pair)
+
+
+def node_chain_ok(irr_emb, irr_pre) -> bool:
+    """Can dedf_node_chain run these irreps?  (every multiplicity a positive multiple of 4, gate scalars left over)"""
+    ms = list(irr_emb) + list(irr_pre) + [irr_pre[0] - irr_pre[1] - irr_pre[2]]
+    return USE_NODE_CHAIN and all(m > 0 and m % 4 == 0 for m in ms)
+
+
+def node_chain(x: torch.Tensor, irr_emb, irr_pre, P, pb, res1: Optional[torch.Tensor], ln_w, ln_b, ln_eps: float,
+               A, ab, B, bb) -> torch.Tensor:
+    """y1 = proj(x) + pb (+ res1);  y = y1 + fctp_2(Gate(fctp_1(LN(y1))))  -- see include/dedf.h (dedf_node_chain)."""
+    d = L.NodeChainDesc()
+    y = torch.empty_like(x)
+    d.x, d.n = ptr(x), x.shape[0]
+    for i in range(3):
+        d.irr_emb[i], d.irr_pre[i] = int(irr_emb[i]), int(irr_pre[i])
+    d.P0, d.P1, d.P2, d.pb = ptr(P[0]), ptr(P[1]), ptr(P[2]), ptr(pb)
+    d.res1 = ptr(res1)
+    d.ln_w, d.ln_b, d.ln_eps = ptr(ln_w), ptr(ln_b), float(ln_eps)
+    d.A0, d.A1, d.A2, d.ab = ptr(A[0]), ptr(A[1]), ptr(A[2]), ptr(ab)
+    d.B0, d.B1, d.B2, d.bb = ptr(B[0]), ptr(B[1]), ptr(B[2]), ptr(bb)
+    d.y = ptr(y)
+    _call("dedf_node_chain", C.byref(d), stream())
+    return y
+
+
+def node_linear_pair(xa: torch.Tensor, irr_in_a, Wa, ba, xb: torch.Tensor, irr_in_b, Wb, bb, irr_out) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(LinearRS_a(xa), LinearRS_b(xb)) with a common output irreps, one launch."""
+    fo = irr_out[0] + 3 * irr_out[1] + 5 * irr_out[2]
+    ya = torch.empty(xa.shape[0], fo, dtype=torch.float32, device=xa.device)
+    yb = torch.empty(xb.shape[0], fo, dtype=torch.float32, device=xb.device)
+    arr = lambda W: (L.c_fp * 3)(ptr(W[0]), ptr(W[1]), ptr(W[2]))
+    _call("dedf_node_linear_pair", ptr(xa), xa.shape[0], L.int_array(irr_in_a), arr(Wa), ptr(ba), ptr(ya),
+          ptr(xb), xb.shape[0], L.int_array(irr_in_b), arr(Wb), ptr(bb), ptr(yb), L.int_array(irr_out), stream())
+    return ya, yb
+
+
 def weight_post(x: torch.Tensor, ln_g, ln_b, w, b, use_sigmoid: bool, mult_logit: Optional[torch.Tensor]) -> torch.Tensor:
     y = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
     _call("dedf_weight_post", ptr(x), x.shape[0], x.shape[1], ptr(ln_g), ptr(ln_b), ptr(w), ptr(b), 1 if use_sigmoid else 0,
@@ -413,6 +535,29 @@ def score_tp(Ts, qf_rot, key_f, qx, qw, irr, Wd: List[torch.Tensor], Wl0, Wl1, b
     arr = lambda ts: (L.c_fp * 2)(ptr(ts[0]), ptr(ts[1]))
     _call("dedf_score_tp", ptr(Ts), n_t, ptr(qf_rot), ptr(key_f), ptr(qx), ptr(qw), qx.shape[0], L.int_array(irr),
                                  arr(Wd), arr(Wl0), arr(Wl1), arr(bl), n_vec, lin_mult, ptr(ang), ptr(lin), stream())
+    return ang, lin
+
+
+def score_tp_step(Ts, qf, key_f, qx, qw, irr, Wd: List[torch.Tensor], Wl0, Wl1, bl, n_vec: int, lin_mult: float, state=None):
+    """dedf_score_tp with the feature rotation D(q) psi applied inside (``qf`` = un-rotated query features) and, with ``state``
+    (denoise.StepState), the float64 Langevin update of the poses fused behind it.  -> (ang, lin)."""
+    n_t = Ts.shape[0]
+    ang = torch.empty(n_t, 3, dtype=torch.float32, device=Ts.device)
+    lin = torch.empty(n_t, 3, dtype=torch.float32, device=Ts.device)
+    d = L.ScoreStepDesc()
+    d.Ts, d.n_t, d.qf, d.key_f, d.qx, d.qw, d.n_q = ptr(Ts), n_t, ptr(qf), ptr(key_f), ptr(qx), ptr(qw), qx.shape[0]
+    for i in range(3):
+        d.irr[i] = int(irr[i])
+    for i in range(2):
+        d.Wd[i], d.Wl0[i], d.Wl1[i], d.bl[i] = ptr(Wd[i]), ptr(Wl0[i]), ptr(Wl1[i]), ptr(bl[i])
+    d.n_vec, d.lin_mult, d.ang_out, d.lin_out = int(n_vec), float(lin_mult), ptr(ang), ptr(lin)
+    if state is not None:
+        d.T64, d.sched, d.n_steps = ptr(state.T64, torch.float64), ptr(state.sched, torch.float64), state.sched.shape[0]
+        d.counter, d.noise = ptr(state.counter, torch.int32), ptr(state.noise, torch.float64)
+        d.seed, d.seed_dev = 0, ptr(state.seed, torch.int64)
+        d.ang_mult, d.lin_mult_d = float(state.ang_mult), float(state.lin_mult)
+        d.traj, d.T32, d.ticket = ptr(state.traj, torch.float64), ptr(Ts), ptr(state.ticket, torch.int32)
+    _call("dedf_score_tp_step", C.byref(d), stream())
     return ang, lin
 
 

@@ -124,8 +124,12 @@ def sharded_sample(model, T_seed: torch.Tensor, key_pcd: Optional[FeaturedPoints
     if world > 1:
         keys, query = broadcast_scene_field(keys, query, src=src, device=T_seed.device)
     lo, hi = shard_range(T_seed.shape[0], rank, world)
-    model.sample_seed = int(getattr(model, "sample_seed", 0)) * 1000003 + rank      # independent noise per rank
-    traj = model.sample(T_seed[lo:hi].contiguous(), keys, query, **sample_kwargs)    # (S, n_local, 7)
+    base_seed = int(getattr(model, "sample_seed", 0))
+    model.sample_seed = base_seed * 1000003 + rank      # independent noise per rank (restored below: calls do not compound)
+    try:
+        traj = model.sample(T_seed[lo:hi].contiguous(), keys, query, **sample_kwargs)    # (S, n_local, 7)
+    finally:
+        model.sample_seed = base_seed
     if world == 1 or not gather:
         return traj
     rows = all_gather_rows(traj.transpose(0, 1).contiguous(), T_seed.shape[0])       # (nT, S, 7)

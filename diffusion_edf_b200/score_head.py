@@ -129,17 +129,44 @@ class ScoreModelHead(nn.Module):
         # time encoding -> per-scale MLP -> time half of the edge pre-linear: (n_scales, nT or 1, K)
         if time_rows is None:        # (sample() precomputes the rows of the whole schedule and passes the current step's)
             time_rows = ops.time_embed(self._time_desc(), (time[:1] if shared_time else time).contiguous())
-        # query transform: x' = R x + t, f' = D(q) f
         qx, qf = query_pcd.x.contiguous(), query_pcd.f.contiguous()
+        Wd, Wl0, Wl1, bl = self._tp_packed()
+        field = self.key_tensor_field
+        if ops.USE_HEAD_FRONT and self._front_ok(key_pcd_multiscale, sources):
+            # fused front (points transform + radius search + CSR + geometry) and D(q) psi inside the score kernel
+            srcs = sources if sources is not None else field.encode_sources(key_pcd_multiscale)
+            key_f = field.forward_poses(Ts, query_pcd, srcs, time_rows=time_rows, edge_capacity=edge_capacity)
+            return ops.score_tp_step(Ts, qf, key_f, qx, query_pcd.w.contiguous(), self.irreps_key_edf.m, Wd, Wl0, Wl1, bl,
+                                     self.n_irreps_prescore, self.lin_mult)
+        # query transform: x' = R x + t, f' = D(q) f
         xq, fq = ops.query_transform(Ts, qx, qf, self.irreps_query_edf.m)
         bq = query_pcd.b.unsqueeze(0).expand(nT, -1).reshape(-1).contiguous()
         flat = FeaturedPoints(x=xq, f=fq, b=bq, w=None)
-        field = self.key_tensor_field(query_points=flat, input_points_multiscale=key_pcd_multiscale,
-                                      time_rows=time_rows, rows_per_time=nQ, sources=sources, edge_capacity=edge_capacity)
-        Wd, Wl0, Wl1, bl = self._tp_packed()
-        ang, lin = ops.score_tp(Ts, fq, field.f, qx, query_pcd.w.contiguous(), self.irreps_key_edf.m, Wd, Wl0, Wl1, bl,
+        out = field(query_points=flat, input_points_multiscale=key_pcd_multiscale,
+                    time_rows=time_rows, rows_per_time=nQ, sources=sources, edge_capacity=edge_capacity)
+        ang, lin = ops.score_tp(Ts, fq, out.f, qx, query_pcd.w.contiguous(), self.irreps_key_edf.m, Wd, Wl0, Wl1, bl,
                                 self.n_irreps_prescore, self.lin_mult)
         return ang, lin
+
+    def _front_ok(self, key_pcd_multiscale, sources) -> bool:
+        """dedf_head_front stages the concatenated scene scales in shared memory (<= 200 KB: ~12 k points)."""
+        n = sources[0].shape[0] if sources is not None else sum(p.x.shape[0] for p in key_pcd_multiscale)
+        return n * 16 + 16 <= 200 * 1024
+
+    def denoise_step(self, T32: torch.Tensor, query_pcd: FeaturedPoints, sources, edge_capacity: int, overflow: torch.Tensor, state) -> None:
+        """One step of ScoreModelBase.sample on device-resident state (denoise.StepState): six launches, no host values.
+        score_model_base.py:174-199 with score_head.py:142-211 inside."""
+        field = self.key_tensor_field
+        Wd, Wl0, Wl1, bl = self._tp_packed()
+        with ops.use_plan(None):
+            ns = field.r_mincut_nonscalar_sh
+            g, length, sh, logit, _ = ops.head_front(T32, query_pcd.x, query_pcd.b, sources[0], sources[1], sources[2],
+                                                     field.r_cluster_multiscale, (0.2 * ns, 1.0 * ns), capacity=edge_capacity,
+                                                     overflow=overflow, step=state.counter, rows_all=state.rows_all,
+                                                     rows_cur=state.rows_cur, static_sources=True)
+            key_f = field.attend_edges(g, length, sh, logit, sources, state.rows_cur, query_pcd.x.shape[0])
+            ops.score_tp_step(T32, query_pcd.f, key_f, query_pcd.x, query_pcd.w, self.irreps_key_edf.m, Wd, Wl0, Wl1, bl,
+                              self.n_irreps_prescore, self.lin_mult, state=state)
 
     def time_rows_for(self, times: torch.Tensor) -> torch.Tensor:
         """Time half of the edge pre-linear for a whole schedule in one launch: (n_scales, len(times), K)."""

@@ -25,6 +25,7 @@ class ScoreModelBase(nn.Module):
         # CUDA-graph replay of forward() / the denoise step when no gradients are needed (see graphs.py)
         self.use_cuda_graph = True
         self._graphs = {}
+        self._denoise_graphs = {}
         self._prefetch_tab = None
 
     def get_key_pcd_multiscale(self, pcd: FeaturedPoints) -> List[FeaturedPoints]:
@@ -112,13 +113,10 @@ class ScoreModelBase(nn.Module):
                              float(temperatures[n]) * (t ** time_exponent_temp)])
         if noise is not None:
             noise = noise.to(torch.float64).contiguous()
-        n_q = grasp_pcd.x.shape[0]
-        cap = nT * n_q * sum(min(p.x.shape[0], 1000) for p in scene_pcd_multiscale)      # worst-case edge count
-        # the graph path pre-sizes every edge buffer for the worst case (~4.5 KB per edge, twice: warm-up + graph pool)
-        fits = 2 * cap * 4500 < 0.5 * torch.cuda.mem_get_info(dev)[0]
         # all poses share the time of a step and the schedule is known up front: ONE time-embedding launch for the whole loop
         rows_all = self.score_head.time_rows_for(torch.tensor([r[0] for r in rows], dtype=torch.float32, device=dev))
-        if not (self.use_cuda_graph and fits):
+        graph_ok = self.use_cuda_graph and ops.USE_HEAD_FRONT and self.score_head._front_ok(scene_pcd_multiscale, sources)
+        if not graph_ok:
             for step, (t, a_ang, a_lin, temperature) in enumerate(rows):
                 time = torch.full((1,), t, dtype=torch.float32, device=dev)
                 ang, lin = self.score_head(Ts=T32, key_pcd_multiscale=scene_pcd_multiscale, query_pcd=grasp_pcd, time=time,
@@ -128,41 +126,19 @@ class ScoreModelBase(nn.Module):
                                 temperature, traj[step + 1], T32)
             traj[total + 1].copy_(T)
             return traj
-        # ---- one CUDA graph per denoise step: schedule, step counter, poses, trajectory and noise all live on the device;
-        # edge buffers are sized for the worst case (every key point within reach of every query point), so there is no
-        # overflow to check and no host synchronisation in the loop.
-        sched = torch.tensor(rows, dtype=torch.float64, device=dev)
-        counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        time_cur = torch.zeros(1, dtype=torch.float32, device=dev)
-        cur_row = torch.zeros(4, dtype=torch.float64, device=dev)
-        rows_cur = torch.zeros(rows_all.shape[0], 1, rows_all.shape[2], dtype=torch.float32, device=dev)
-
-        def one_step():
-            ops.sample_advance(sched, counter, time_cur, cur_row, rows_all, rows_cur)
-            ang, lin = self.score_head(Ts=T32, key_pcd_multiscale=scene_pcd_multiscale, query_pcd=grasp_pcd, time=time_cur,
-                                       sources=sources, shared_time=True, edge_capacity=cap, time_rows=rows_cur)
-            ops.pose_update(T, ang, lin, noise, int(self.sample_seed), 0, 0.0, self.ang_mult, self.lin_mult, 0.0, 0.0, 0.0,
-                            traj, T32, dev_row=cur_row, dev_counter=counter)
-
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            one_step()                                        # warm-up (then restore the state it advanced)
-        cur.wait_stream(side)
-        T.copy_(traj[0]); T32.copy_(T); counter.zero_()
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        k0 = ops.LAUNCHES
-        with torch.cuda.graph(graph):
-            one_step()
-        n_kernels = ops.LAUNCHES - k0
-        T.copy_(traj[0]); T32.copy_(T); counter.zero_()       # capture does not execute, but keep the state explicit
-        for _ in range(total):
-            graph.replay()
-        ops.LAUNCHES += n_kernels * total
-        traj[total + 1].copy_(T)
-        return traj
+        # ---- one CUDA graph per denoise step, cached across calls (denoise.py): schedule, step counter, poses, trajectory, noise
+        # and seed all live on the device; edge buffers are sized from the seeds' edge count with a device-side overflow flag that
+        # is read once after the loop.
+        from .denoise import DenoiseGraph
+        key = (nT, total, tuple(int(v) for v in sources[2]), tuple(grasp_pcd.x.shape), noise is not None, str(dev), len(sources),
+               self._param_signature(), ops.USE_TC_MLP, ops.USE_TC_TPACT, ops.USE_VALUE_REDUCE, ops.USE_NODE_CHAIN)
+        dg = self._denoise_graphs.get(key)
+        if dg is None:
+            if len(self._denoise_graphs) >= 2:
+                self._denoise_graphs.clear()
+            dg = DenoiseGraph(self, nT, total, sources, grasp_pcd, noise is not None, dev)
+            self._denoise_graphs[key] = dg
+        return dg.run(T, sources, grasp_pcd, rows, rows_all, noise, int(self.sample_seed))
 
     # ------------------------------------------------------------------ forward
     def _param_signature(self):

@@ -5,8 +5,9 @@ gather + tensor product + linear and never materialise the (E, 49 G) tensor-prod
 for the weight gradients.  Mirrors the reference's arithmetic order (not the inference path's exact reassociations):
   gnn_block.py:164-218 / block.py:141-174 (EquiformerBlock), graph_attention.py:84-122, :218-273 (GraphAttentionMLP(2)),
   multiscale_tensor_field.py:192-260, graph_parser.py:146-224, unet_feature_extractor.py:260-417, score_head.py:142-211.
-Train-mode dropout (alpha_drop on the attention weights, proj_drop = EquivariantDropout after proj) is applied when the
-module is in train() mode, with Philox masks; the parity tests compare against the oracle in eval mode.
+Train-mode dropout (alpha_drop on the attention weights, proj_drop = EquivariantDropout after GraphAttention.proj AND after
+the FeedForwardNetwork's fctp_2, gnn_block.py:44-57) is applied when the module is in train() mode, with Philox masks; the
+parity tests compare against the oracle in eval mode.  drop_path_rate > 0 (GraphDropPath) is rejected by the constructors.
 """
 from __future__ import annotations
 
@@ -66,10 +67,16 @@ def project_if_mismatch(mod: ProjectIfMismatch, x: torch.Tensor) -> torch.Tensor
     return linear_rs(mod.skip, x)
 
 
-def ffn(mod, x: torch.Tensor) -> torch.Tensor:
+def ffn(mod, x: torch.Tensor, proj_drop: float = 0.0) -> torch.Tensor:
+    """FeedForwardNetwork.forward (gnn_block.py:51-57 / block.py:51-57): fctp_1 (+gate) -> fctp_2 -> EquivariantDropout(proj_drop)
+    on the output irreps in train mode."""
     h = linear_rs(mod.fctp_1, x)
     h = A.GateFn.apply(h, mod.fctp_1.irreps_out.m)
-    return linear_rs(mod.fctp_2, h)
+    out = linear_rs(mod.fctp_2, h)
+    if proj_drop > 0.0:
+        irr = mod.fctp_2.irreps_out
+        out = A.GroupScaleFn.apply(out, A.dropout_mask((out.shape[0], irr.num_irreps), proj_drop, out.device), irr.m, 1)
+    return out
 
 
 def graph_attention(ga: GraphAttention, msg_src: torch.Tensor, msg_dst: Optional[torch.Tensor], g: ops.Csr, sh: torch.Tensor,
@@ -110,7 +117,7 @@ def unet_block(blk, f_src, f_dst, geom, radial, drop=(0.0, 0.0)) -> torch.Tensor
     w = radial_profile(blk.ga.sep_act.dtp_rad, emb)
     attn = graph_attention(blk.ga, msg_src, msg_dst, geom.g, geom.sh[:E], w, None, drop)
     out = A.AddScaleFn.apply(attn, f_dst, 1.0)
-    return A.AddScaleFn.apply(ffn(blk.ffn, layer_norm(blk.norm_2, out)), out, 1.0)
+    return A.AddScaleFn.apply(ffn(blk.ffn, layer_norm(blk.norm_2, out), drop[1]), out, 1.0)
 
 
 # ------------------------------------------------------------------------------------------------ key encoder
@@ -118,6 +125,7 @@ def unet_forward(net, pcd: FeaturedPoints) -> List[FeaturedPoints]:
     x, b = pcd.x.contiguous(), pcd.b.contiguous()
     f = linear_rs(net.input_emb, pcd.f.contiguous())
     outs, graphs = [(f, x, b)], []
+    scale_outs = []
     geom = None
 
     drop = (net.alpha_drop, net.proj_drop) if net.training else (0.0, 0.0)
@@ -141,6 +149,12 @@ def unet_forward(net, pcd: FeaturedPoints) -> List[FeaturedPoints]:
             f = run(layer, f, f, geom)
             outs.append((f, x, b))
             graphs.append(("self", geom))
+        scale_outs.append((f, x, b))
+    if net.forward_only:
+        # ForwardOnlyFeatureExtractor (forward_only_feature_extractor.py:191-275): no mid / up path, no skips -- every scale
+        # outputs its down-path features through project_outputs (mirrors UnetFeatureExtractor.forward's forward_only branch)
+        return [FeaturedPoints(x=scale_outs[s][1], f=project_if_mismatch(proj, scale_outs[s][0]), b=scale_outs[s][2], w=None)
+                for s, proj in enumerate(net.project_outputs) if s in net.output_scalespace]
     for layer in net.mid_block:
         f = run(layer, f, f, geom)
     f_skip, _, _ = outs.pop()
@@ -218,7 +232,7 @@ def tensor_field(field, query_x: torch.Tensor, query_b: torch.Tensor, keys: List
     drop = (field.alpha_drop, field.proj_drop) if field.training else (0.0, 0.0)
     emb = graph_attention(blk.ga, msg_src, None, g, sh[:E], w, logit[:E], drop, w_src)
     skip = emb if blk.skip_2.is_identity else project_if_mismatch(blk.skip_2, emb)
-    return A.AddScaleFn.apply(ffn(blk.ffn, layer_norm(blk.post_norm, emb)), skip, 1.0)
+    return A.AddScaleFn.apply(ffn(blk.ffn, layer_norm(blk.post_norm, emb), drop[1]), skip, 1.0)
 
 
 def score_head(head, Ts: torch.Tensor, keys: List[FeaturedPoints], query: FeaturedPoints, time: torch.Tensor):

@@ -55,6 +55,8 @@ class UnetFeatureExtractor(nn.Module):
         self.num_heads, self.fc_neurons, self.pool_ratio, self.n_layers = num_heads, fc_neurons, pool_ratio, n_layers
         self.deterministic = deterministic
         self.alpha_drop, self.proj_drop = float(alpha_drop), float(proj_drop)     # train mode only (train_path.py)
+        if drop_path_rate and float(drop_path_rate) > 0.0:
+            raise NotImplementedError("drop_path_rate > 0 (GraphDropPath, block.py:133,163-171) is not implemented; every shipped config uses 0.0")
         self.n_layers_midstream = n_layers_midstream
         if irreps_input is None:
             raise NotImplementedError("irreps_input=None")

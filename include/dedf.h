@@ -184,6 +184,35 @@ int dedf_value_reduce(int mul1, const int* row_ptr, int n_dst, int n_seg, const 
 int dedf_edge_tp_reduce(int mul1, const float* x, const int* row_ptr, const int* edge_src, const float* sh,
                         int sh_stride, const float* w, const float* alpha, int n_dst, float* out, cudaStream_t stream);
 
+/* ---- the front of one score-head evaluation, fused ------------------------------------------------------------
+ * Pose transform of the query points (gnn_data.py:88-100, pcd_utils.py:55-81), multi-scale radius search against the
+ * concatenated scene scales (graph_parser.py:336-345 torch_cluster.radius with max_num_neighbors, :272-286 all pairs for
+ * r < 0; multiscale_tensor_field.py:236-247 concatenation order), CSR construction and the edge geometry
+ * (graph_parser.py:146-224: length, l<=2 harmonics with the non-scalar min-cut, edge logits) in ONE launch.  Outputs are
+ * bit-identical to dedf_query_transform (points) + dedf_radius_count / _fill + dedf_edge_geom.
+ * Destinations are (pose t, query point q) -> row t * n_q + q; batch id of a destination = b_q[q].
+ * capacity > 0: the edge buffers hold `capacity` edges; the CSR is clamped and *overflow raised when the true count exceeds it.
+ * Workspace (caller-owned): counts (n_scales * n_dst), cta_sum (>= 148 ints), barrier (2 uints, ZEROED ONCE by the caller and
+ * then left alone: a reusable device-wide barrier; one stream at a time may use a given barrier buffer).
+ * Denoise loop (optional, replaces dedf_sample_advance): rows_all (n_scales, n_steps, rows_k) precomputed time rows and
+ * *step (device step index) -> rows_cur (n_scales, 1, rows_k).  stage_early = 1 promises that x_src / b_src were written
+ * before the PREVIOUS kernel of the stream started (static scene): they are then staged before the dependency wait. */
+typedef struct dedf_head_front_desc {
+    const float* Ts; int n_t;                  /* (n_t, 7) [qw qx qy qz x y z] fp32 */
+    const float* qx; int n_q;                  /* (n_q, 3) query coordinates in the grasp frame */
+    const float* x_src; const long long* b_src; const long long* b_q;   /* sources (sum N_s, 3); optional batch ids */
+    int n_scales; int src_off[DEDF_MAX_SCALES + 1]; float r[DEDF_MAX_SCALES];
+    int max_num_neighbors; float ns_lo, ns_hi; int capacity;
+    float* x_dst;                              /* out (n_t * n_q, 3) */
+    int* row_ptr; int* counts; int* edge_src; int* edge_dst;            /* out: row_ptr (n_scales * n_dst + 1) */
+    float* length; float* sh; float* logit;    /* out (E), (E, 9), (E) */
+    int* n_edges; int* overflow;               /* out: device scalar(s); overflow may be NULL */
+    int* cta_sum; unsigned* barrier;           /* workspace */
+    const int* step; int n_steps; const float* rows_all; float* rows_cur; int rows_k;
+    int stage_early;
+} dedf_head_front_desc;
+int dedf_head_front(const dedf_head_front_desc* d, cudaStream_t stream);
+
 /* ---- per-node ---------------------------------------------------------------------------------------- */
 
 /* y = epilogue( LinearRS( [EquivariantLayerNormV2](x) ) ): equiformer/layer_norm.py:91-156,
@@ -193,6 +222,31 @@ int dedf_edge_tp_reduce(int mul1, const float* x, const int* row_ptr, const int*
 int dedf_node_linear(const float* x, int n, const int* irr_in_host, const int* irr_out_host, const float* W0,
                      const float* W1, const float* W2, const float* bias0, const float* ln_w, const float* ln_b,
                      float ln_eps, int gate, const float* res, float res_scale, float* y, cudaStream_t stream);
+
+/* The per-node tail of an Equiformer block in ONE launch (replaces three dedf_node_linear calls):
+ *     y1 = proj(x) + b_p (+ res1)                  graph_attention.py:118-121,268-272 + the block's first residual
+ *     y  = y1 + fctp_2(Gate(fctp_1(LN(y1))))       gnn_block.py:51-57,207-216 / block.py:51-57,165-173
+ * proj: irr_emb -> irr_emb; fctp_1: irr_emb -> irr_pre (pre-gate, m0 = scalars + gates); fctp_2: Gate(irr_pre) -> irr_emb.
+ * Weight blocks (in.m_l, out.m_l) row-major as for dedf_node_linear; every multiplicity must be a positive multiple of 4 and
+ * every pointer 16-byte aligned (else DEDF_ERR_UNSUPPORTED: the caller falls back to three dedf_node_linear launches).
+ * Bit-identical to that un-fused sequence (same micro-kernel and summation order). */
+typedef struct dedf_node_chain_desc {
+    const float* x; int n;                     /* (n, dim(irr_emb)) attention output */
+    int irr_emb[3], irr_pre[3];
+    const float *P0, *P1, *P2, *pb;            /* proj weights / 0e bias (pb may be NULL) */
+    const float* res1;                         /* optional (n, dim(irr_emb)) added to proj's output */
+    const float *ln_w, *ln_b; float ln_eps;    /* EquivariantLayerNormV2 affine_weight (num_irreps) / affine_bias (m0) */
+    const float *A0, *A1, *A2, *ab;            /* fctp_1 */
+    const float *B0, *B1, *B2, *bb;            /* fctp_2 */
+    float* y;                                  /* (n, dim(irr_emb)) */
+} dedf_node_chain_desc;
+int dedf_node_chain(const dedf_node_chain_desc* d, cudaStream_t stream);
+
+/* Two independent LinearRS problems (no norm / gate / residual) with a common output irreps in ONE launch: the
+ * linear_src / linear_dst pair at the head of every UNet block (block.py:149-153).  W_x = {W0, W1, W2} host arrays. */
+int dedf_node_linear_pair(const float* x_a, int n_a, const int* irr_in_a_host, const float* const* W_a_host3, const float* bias_a, float* y_a,
+                          const float* x_b, int n_b, const int* irr_in_b_host, const float* const* W_b_host3, const float* bias_b, float* y_b,
+                          const int* irr_out_host, cudaStream_t stream);
 
 /* KeypointExtractor.weight_post (keypoint_extractor.py:129-134, :186-190): y = act(Linear(SiLU(LayerNorm(x)))) * softplus(mult). */
 int dedf_weight_post(const float* x, int n, int dim, const float* ln_g, const float* ln_b, const float* w, const float* b,
@@ -228,11 +282,33 @@ int dedf_score_tp(const float* Ts, int n_t, const float* qf_rot, const float* ke
                   const float* const* Wl1_host2, const float* const* bl_host2, int n_vec, float lin_mult,
                   float* ang_out, float* lin_out, cudaStream_t stream);
 
+/* dedf_score_tp with the feature rotation D(q) psi of dedf_query_transform applied inside (qf = the UN-rotated query
+ * features (n_q, F)) and, optionally, the Langevin step of dedf_pose_update fused behind it for a replayed denoise loop
+ * (score_head.py:186-209 + score_model_base.py:174-199): when T64 != NULL, every pose's new state is integrated in float64
+ * from row *counter of the device schedule `sched` (n_steps, 4) = [t, alpha_ang, alpha_lin, temperature], written to T64
+ * (in place), to row *counter + 1 of `traj` and, cast to fp32, to T32 (which must be the `Ts` this call read);
+ * the last CTA to finish advances *counter.  noise (n_steps, n_t, 6) or NULL = Philox as in dedf_pose_update.
+ * ticket: one zero-initialised unsigned owned by the caller. */
+typedef struct dedf_score_step_desc {
+    const float* Ts; int n_t;
+    const float* qf; const float* key_f; const float* qx; const float* qw; int n_q;
+    int irr[3];
+    const float* Wd[2]; const float* Wl0[2]; const float* Wl1[2]; const float* bl[2];
+    int n_vec; float lin_mult;
+    float* ang_out; float* lin_out;
+    double* T64; const double* sched; int n_steps; int* counter; const double* noise; unsigned long long seed;
+    const unsigned long long* seed_dev;        /* optional: the seed is read from device memory instead (graph replay) */
+    double ang_mult, lin_mult_d; double* traj; float* T32; unsigned* ticket;
+} dedf_score_step_desc;
+int dedf_score_tp_step(const dedf_score_step_desc* d, cudaStream_t stream);
+
 /* One annealed-Langevin step on SE(3) in float64 (score_model_base.py:178-193).  noise (n_t, 6) standard normals
- * or NULL (Philox4x32-10 with (seed, pose, offset)).  Optionally copies the new poses to traj_out (f64) and
+ * or NULL: Philox4x32-10, seed = `seed`, subsequence = pose index, and `offset` = the STEP index -- every step owns a
+ * disjoint window of 16 32-bit outputs of the pose's stream (a step consumes 12), so no two steps share a draw.
+ * Optionally copies the new poses to traj_out (f64) and
  * T_f32_out (f32, the network input of the next step).
  * Graph-replay mode: dev_row (4 doubles [t, alpha_ang, alpha_lin, temperature], see dedf_sample_advance) overrides the
- * host scalars and dev_counter (device step index) selects the Philox offset, the noise rows (noise + step*n_t*6) and
+ * host scalars and dev_counter (device step index) selects the Philox step window, the noise rows (noise + step*n_t*6) and
  * the trajectory row (traj_out + (step+1)*n_t*7); the counter is incremented at the end of the call. */
 int dedf_pose_update(double* T, int n_t, const float* ang, const float* lin, const double* noise,
                      unsigned long long seed, unsigned long long offset, double t, double ang_mult, double lin_mult,
@@ -342,8 +418,15 @@ int dedf_build_arch(void);
 int dedf_tc_selftest(const float* A, const float* B, int N, int K, int n_split, float* D, cudaStream_t stream);
 
 /* cudaAccessPolicyWindow on `stream`: keep [base, base + bytes) resident in L2 (persisting hits, streaming misses) for the
- * kernels launched afterwards; bytes = 0 removes the window.  No reference counterpart (used around dedf_edge_tp_reduce). */
+ * kernels launched afterwards; bytes = 0 removes the window.  No reference counterpart (used around dedf_edge_tp_reduce).
+ * Unlike the kernel entry points this one is HOST-side configuration: it launches nothing, but it may raise the device's
+ * persisting-L2 limit (cudaDeviceSetLimit) and must not be called during stream capture. */
 int dedf_l2_persist(const void* base, long long bytes, cudaStream_t stream);
+
+/* *flag |= 1 if the int64 arrays a and b (n words) differ anywhere.  Guard of a replayed CUDA graph: the plan of a forward
+ * bakes in host values derived from the batch ids (FPS segments, query batch ids); a call with the same shapes but another
+ * batch layout must re-plan instead of replaying stale segments. */
+int dedf_flag_if_differs(const long long* a, const long long* b, long long n, int* flag, cudaStream_t stream);
 
 /* Warm the L2 with the model's weights: issues prefetch.global.L2 over n device ranges (ptrs_dev[i], bytes_dev[i]).
  * The reference has no counterpart (its ~10^3 launches per forward re-read the weights through the cache hierarchy

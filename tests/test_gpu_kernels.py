@@ -238,48 +238,6 @@ def test_value_reduce_multisegment(cuda, G):
         assert_close(out, old, TOL, f"value_reduce vs tp_lin+softmax (post={use_post})")
 
 
-@pytest.mark.skipif(os.environ.get("DEDF_EXPERIMENTAL") != "1", reason="experimental kernel, not yet run on a GPU (DESIGN 12); set DEDF_EXPERIMENTAL=1")
-@pytest.mark.parametrize("G", [32, 16])
-def test_value_reduce_split_experimental(cuda, G):
-    """value_reduce_split_kernel (DEDF_VR_SPLIT=1: the warp pair of a channel group splits the 15 CG paths instead of the head
-    pairs) against the default kernel on a ragged multi-segment graph: same per-lane accumulation order and the same fold
-    order per output, so the results should agree to the last bits (the bound below is loose on purpose)."""
-    from diffusion_edf_b200 import layers, ops
-    gen = torch.Generator().manual_seed(70 + G)
-    torch.manual_seed(70 + G)
-    F = OIrreps(IRR[G]).dim
-    n_dst, n_seg = 37, 4
-    deg = torch.poisson(torch.full((n_seg, n_dst), 9.0), generator=gen).long()
-    deg[:, 0] = 0
-    deg[1, 2] = 150
-    deg[:, 3] = torch.tensor([64, 0, 64, 0])
-    flat = deg.reshape(-1)
-    row_ptr = torch.zeros(n_seg * n_dst + 1, dtype=torch.long)
-    row_ptr[1:] = flat.cumsum(0)
-    E = int(row_ptr[-1])
-    ed = torch.arange(n_dst).repeat(n_seg).repeat_interleave(flat)
-    es = torch.randint(0, 50, (E,), generator=gen)
-    sh, _ = _random_sh(E, gen)
-    v = torch.randn(E, F, generator=gen).to(cuda)
-    logit = (torch.randn(E, 4, generator=gen) * 3).to(cuda)
-    pga = layers.GraphAttention(IRR[G], IRR[G], [32, 16, 16], 4)
-    with torch.no_grad():
-        for prm in pga.parameters():
-            prm.uniform_(-0.5, 0.5)
-    pga = pga.to(cuda)
-    p = pga.packed()
-    rp = row_ptr.int().to(cuda)
-    csr = ops.Csr(rp, es.int().to(cuda), ed.int().to(cuda), rp[-1:], E, n_dst, n_seg)
-    ref = ops.value_reduce(G, csr, v, sh.to(cuda), logit, None, p["wv"], p["V0"], p["V1"], p["V2"], p["vb"])
-    os.environ["DEDF_VR_SPLIT"] = "1"
-    try:
-        out = ops.value_reduce(G, csr, v, sh.to(cuda), logit, None, p["wv"], p["V0"], p["V1"], p["V2"], p["vb"])
-        torch.cuda.synchronize()
-    finally:
-        del os.environ["DEDF_VR_SPLIT"]
-    assert_close(out, ref, 1e-5, "value_reduce_split vs value_reduce")
-
-
 @pytest.mark.parametrize("G", [32, 16])
 def test_edge_tp_reduce_k1(cuda, G):
     """K1 == scatter(alpha_head(u) * o3.TensorProduct(x[src], sh, w), dst)."""
@@ -390,6 +348,61 @@ def test_ln_linear_gate_residual(cuda, G):
     with torch.no_grad():
         ref = o_proj(xx)
     assert_close(p_proj.to(cuda)(xx.to(cuda)), ref, TOL, "ProjectIfMismatch")
+
+
+@pytest.mark.parametrize("G,n", [(32, 41), (16, 41), (32, 300), (16, 2000), (32, 8)])
+def test_node_chain_is_bit_identical_to_three_launches(cuda, G, n):
+    """dedf_node_chain (proj -> +res -> LN -> fctp_1 -> gate -> fctp_2 -> +res in one launch) against the three dedf_node_linear
+    launches it replaces: same micro-kernel and summation order, so the results must be EQUAL, with and without the first
+    residual; and against the oracle (graph_attention.py:118-121, gnn_block.py:51-57,207-216)."""
+    from diffusion_edf_b200 import layers, ops
+    from diffusion_edf_b200.block import node_tail
+    torch.manual_seed(40 + G)
+    irr = OIrreps(IRR[G])
+    mid = ON.sort_even_first(irr * 3)[0].simplify()
+    o_ln = ON.EquivariantLayerNormV2(irr)
+    o_ffn = OM.FeedForwardNetwork(irr, irr, mid)
+    o_proj = ON.LinearRS(irr, irr)
+    with torch.no_grad():
+        o_ln.affine_weight.uniform_(0.5, 1.5); o_ln.affine_bias.uniform_(-0.5, 0.5)
+        for b in list(o_ffn.fctp_1.bias) + list(o_ffn.fctp_2.bias) + list(o_proj.bias):
+            b.uniform_(-0.5, 0.5)
+    p_ln = layers.EquivariantLayerNormV2(IRR[G]); p_ln.load_state_dict(o_ln.state_dict())
+    p_ffn = layers.FeedForwardNetwork(IRR[G], IRR[G], str(mid)); p_ffn.load_state_dict(o_ffn.state_dict())
+    p_proj = layers.LinearRS(IRR[G], IRR[G]); p_proj.load_state_dict(o_proj.state_dict())
+    p_ln, p_ffn, p_proj = p_ln.to(cuda), p_ffn.to(cuda), p_proj.to(cuda)
+    x = torch.randn(n, irr.dim) * torch.rand(n, 1) * 3
+    res = torch.randn(n, irr.dim)
+    for r in (None, res):
+        with torch.no_grad():
+            y1 = o_proj(x) + (r if r is not None else 0.0)
+            ref = y1 + o_ffn(o_ln(y1))
+        rg = r.to(cuda) if r is not None else None
+        assert ops.USE_NODE_CHAIN
+        fused = node_tail(p_proj, p_ln, p_ffn, x.to(cuda), rg)
+        ops.USE_NODE_CHAIN = False
+        try:
+            unfused = node_tail(p_proj, p_ln, p_ffn, x.to(cuda), rg)
+        finally:
+            ops.USE_NODE_CHAIN = True
+        assert torch.equal(fused, unfused), f"max diff {(fused - unfused).abs().max().item():.3e}"
+        assert_close(fused, ref, TOL, "node chain vs oracle")
+
+
+def test_node_linear_pair(cuda):
+    """linear_src / linear_dst of a UNet block in one launch == the two separate launches (incl. the 120 -> 240 pool block)."""
+    from diffusion_edf_b200 import layers, ops
+    torch.manual_seed(44)
+    for irr_src, irr_dst, ns, nd in ((IRR[16], IRR[32], 400, 80), (IRR[32], IRR[32], 80, 80), (IRR[16], IRR[16], 2000, 401)):
+        ls = layers.LinearRS(irr_src, irr_dst, bias=False).to(cuda)
+        ld = layers.LinearRS(irr_dst, irr_dst, bias=True).to(cuda)
+        with torch.no_grad():
+            ld.bias[0].uniform_(-0.5, 0.5)
+        xs = torch.randn(ns, ls.irreps_in.dim, device=cuda)
+        xd = torch.randn(nd, ld.irreps_in.dim, device=cuda)
+        (Ws, bs), (Wd, bd) = ls.packed(), ld.packed()
+        ya, yb = ops.node_linear_pair(xs, ls.irreps_in.m, Ws, bs, xd, ld.irreps_in.m, Wd, bd, ld.irreps_out.m)
+        assert torch.equal(ya, ls(xs)) and torch.equal(yb, ld(xd))
 
 
 def test_misc_node_ops(cuda):
@@ -518,3 +531,142 @@ def test_pose_update(cuda):
     assert torch.equal(T1, T2) and torch.isfinite(T1).all()
     assert (T1[:, :4].norm(dim=-1) - 1).abs().max() < 1e-12
     assert (T1 - Td).abs().max() > 1e-3
+
+
+def test_pose_update_philox_steps_are_disjoint(cuda):
+    """The Philox noise of different steps must not overlap (round-1 bug: offset = step counted single 32-bit outputs while a
+    step consumes 12, so step s+4 re-read step s's normals).  With zero scores, identity rotation and temperature 1 the linear
+    displacement IS sqrt(alpha_lin) z[3:6] and the quaternion increment is 0.5 sqrt(alpha_ang) z[0:3]: recover z per step."""
+    from diffusion_edf_b200 import ops
+    n, steps = 512, 12
+    zero = torch.zeros(n, 3, device=cuda)
+    a_ang = a_lin = 1e-6          # tiny: the first-order quaternion update is then exact to 1e-12
+    zs = []
+    for s in range(steps):
+        T = torch.zeros(n, 7, dtype=torch.float64, device=cuda); T[:, 0] = 1.0
+        ops.pose_update(T, zero, zero, None, 77, s, 0.5, 2.5, 15.0, a_ang, a_lin, 1.0, None, None)
+        q = T[:, :4] / T[:, :1]
+        z = torch.cat([2.0 * q[:, 1:] / math.sqrt(a_ang), T[:, 4:] / math.sqrt(a_lin)], dim=-1)
+        zs.append(z.cpu())
+    Z = torch.stack(zs)                                   # (steps, n, 6)
+    assert torch.isfinite(Z).all()
+    # no value of one step reappears in another step of the same pose (the old bug reproduced z[2:4] of step s as z[0:2] of s+4)
+    for s in range(steps):
+        for d in (1, 2, 3, 4, 8):
+            if s + d < steps:
+                a, b = Z[s], Z[s + d]
+                same = (a[:, :, None] - b[:, None, :]).abs() < 1e-6
+                assert not same.any(), f"steps {s} and {s + d} share a normal draw"
+    # standard normal, uncorrelated across steps and components
+    flat = Z.permute(1, 0, 2).reshape(n, -1)             # (n, steps*6) samples of a 72-dim vector
+    assert abs(float(flat.mean())) < 0.02 and abs(float(flat.std()) - 1.0) < 0.02
+    C = torch.corrcoef(flat.T)
+    off = C - torch.eye(C.shape[0], dtype=C.dtype)
+    assert float(off.abs().max()) < 0.25, float(off.abs().max())      # 512 samples: |r| ~ 0.044 sigma, 0.25 = 5.6 sigma
+
+
+# --------------------------------------------------------------------------- fused head step
+@pytest.mark.parametrize("nT,nQ,batched", [(5, 2, False), (37, 3, True), (128, 2, False), (300, 1, False)])
+def test_head_front_is_bit_identical_to_the_unfused_kernels(cuda, nT, nQ, batched):
+    """dedf_head_front (pose transform + multi-scale radius search + CSR + edge geometry, one launch) against
+    dedf_query_transform + dedf_radius_count/_fill + dedf_edge_geom: identical indices and bit-identical floats; eager (exact
+    sizing) and capacity mode (clamp + overflow flag)."""
+    from diffusion_edf_b200 import ops
+    g = torch.Generator().manual_seed(500 + nT)
+    sizes = [700, 150, 40, 9]
+    radii = [5.0, 10.0, 20.0, None]
+    xs = torch.cat([(torch.rand(n, 3, generator=g) - 0.5) * 40 for n in sizes]).to(cuda)
+    off = [0]
+    for n in sizes:
+        off.append(off[-1] + n)
+    b_src = (torch.cat([torch.arange(n) % 2 for n in sizes]) if batched else torch.zeros(sum(sizes), dtype=torch.long)).to(cuda)
+    qx = (torch.randn(nQ, 3, generator=g) * 3).to(cuda)
+    b_q = (torch.arange(nQ) % 2 if batched else torch.zeros(nQ, dtype=torch.long)).to(cuda)
+    q = torch.nn.functional.normalize(torch.randn(nT, 4, generator=g), dim=-1)
+    Ts = torch.cat([q, (torch.rand(nT, 3, generator=g) - 0.5) * 40], -1).to(cuda)
+    # un-fused
+    x_ref, _ = ops.query_transform(Ts, qx, torch.zeros(nQ, 240, device=cuda), (64, 32, 16))
+    bq = b_q.unsqueeze(0).expand(nT, -1).reshape(-1).contiguous()
+    g0 = ops.radius_csr(xs, x_ref, radii, src_off=off, b_src=b_src, b_dst=bq, max_num_neighbors=1000)
+    l0, sh0, lg0 = ops.edge_geom(xs, x_ref, g0, radii=radii, src_off=off, ns_cut=(0.06, 0.3), want_logit=True)
+    # fused, exact sizing
+    g1, l1, sh1, lg1, x1 = ops.head_front(Ts, qx, b_q, xs, b_src, off, radii, (0.06, 0.3))
+    assert g1.n_edges == g0.n_edges and g0.n_edges > 0
+    assert torch.equal(x1, x_ref)
+    assert torch.equal(g1.row_ptr, g0.row_ptr) and torch.equal(g1.edge_src, g0.edge_src) and torch.equal(g1.edge_dst, g0.edge_dst)
+    E = g0.n_edges
+    assert torch.equal(l1[:E], l0[:E]) and torch.equal(sh1[:E], sh0[:E]) and torch.equal(lg1[:E], lg0[:E])
+    assert int(g1.n_edges_dev) == E
+    # capacity mode: roomy -> same graph, flag clear; tight -> clamped CSR, flag raised
+    ovf = torch.zeros(1, dtype=torch.int32, device=cuda)
+    g2, l2, sh2, lg2, _ = ops.head_front(Ts, qx, b_q, xs, b_src, off, radii, (0.06, 0.3), capacity=E + 100, overflow=ovf)
+    assert int(ovf) == 0 and int(g2.n_edges_dev) == E and torch.equal(g2.row_ptr, g0.row_ptr)
+    assert torch.equal(g2.edge_src[:E], g0.edge_src) and torch.equal(sh2[:E], sh0[:E])
+    g3, *_ = ops.head_front(Ts, qx, b_q, xs, b_src, off, radii, (0.06, 0.3), capacity=max(1, E // 2), overflow=ovf)
+    assert int(ovf) == 1 and int(g3.n_edges_dev) == max(1, E // 2) and int(g3.row_ptr.max()) == max(1, E // 2)
+    assert torch.equal(g3.edge_src[:E // 2], g0.edge_src[:E // 2])
+
+
+def test_head_front_all_pairs_scale_is_not_capped(cuda):
+    """InfiniteBipartite builds the full meshgrid: max_num_neighbors does not apply to it (graph_parser.py:274-278); both the
+    fused front and dedf_radius_count/_fill must keep every source of an r = None scale."""
+    from diffusion_edf_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    xs = (torch.rand(50, 3, generator=g) * 4).to(cuda)
+    qx = torch.zeros(1, 3, device=cuda)
+    Ts = torch.tensor([[1.0, 0, 0, 0, 1, 1, 1], [1.0, 0, 0, 0, 2, 2, 2]], device=cuda)
+    g1, *_ = ops.head_front(Ts, qx, None, xs, None, [0, 50], [None], (0.0, -1.0), max_num_neighbors=8)
+    assert g1.n_edges == 100
+    x_dst = Ts[:, 4:].contiguous()
+    g0 = ops.radius_csr(xs, x_dst, [None], src_off=[0, 50], max_num_neighbors=8)
+    assert g0.n_edges == 100 and torch.equal(g0.edge_src, g1.edge_src)
+    # a finite radius IS capped
+    g2 = ops.radius_csr(xs, x_dst, [100.0], src_off=[0, 50], max_num_neighbors=8)
+    assert g2.n_edges == 16
+
+
+@pytest.mark.parametrize("nT,nQ", [(7, 2), (130, 2), (300, 3)])
+def test_score_tp_step_matches_unfused(cuda, nT, nQ):
+    """dedf_score_tp_step: D(q) psi applied inside == dedf_query_transform + dedf_score_tp (bit-identical), and the fused float64
+    Langevin step == dedf_pose_update on those scores (bit-identical), incl. the step counter, trajectory row and fp32 pose copy."""
+    from diffusion_edf_b200 import ScoreModelHead, ops
+    from diffusion_edf_b200.denoise import StepState
+    from diffusion_edf_b200.synthetic import model_kwargs
+    torch.manual_seed(60 + nT)
+    kw = model_kwargs()["score_head_kwargs"]
+    tf = kw["key_tensor_field_kwargs"]
+    tf.update(irreps_input="64x0e+32x1e+16x2e", use_src_point_attn=False, use_dst_point_attn=False)
+    head = ScoreModelHead(1.0, [256, 128, 64], dict(tf), "64x0e+32x1e+16x2e", 15.0, 2.5, edge_time_encoding=True, query_time_encoding=False).to(cuda)
+    Wd, Wl0, Wl1, bl = head._tp_packed()
+    q = torch.nn.functional.normalize(torch.randn(nT, 4), dim=-1)
+    T64 = torch.cat([q, torch.randn(nT, 3) * 5], -1).double().to(cuda)
+    Ts = T64.float()
+    qx, qf, qw = torch.randn(nQ, 3, device=cuda), torch.randn(nQ, 240, device=cuda), torch.rand(nQ, device=cuda)
+    key_f = torch.randn(nT * nQ, 240, device=cuda)
+    _, fq = ops.query_transform(Ts, qx, qf, (64, 32, 16))
+    ang0, lin0 = ops.score_tp(Ts, fq, key_f, qx, qw, (64, 32, 16), Wd, Wl0, Wl1, bl, 32, 15.0)
+    ang1, lin1 = ops.score_tp_step(Ts, qf, key_f, qx, qw, (64, 32, 16), Wd, Wl0, Wl1, bl, 32, 15.0)
+    assert torch.equal(ang0, ang1) and torch.equal(lin0, lin1)
+    # fused step, Philox noise, step index 3 of a 5-step schedule
+    n_steps, step = 5, 3
+    sched = torch.rand(n_steps, 4, dtype=torch.float64, device=cuda) + 0.1
+    st = StepState(T64.clone(), sched, torch.full((1,), step, dtype=torch.int32, device=cuda), None,
+                   torch.full((1,), 99, dtype=torch.int64, device=cuda), torch.zeros(n_steps + 2, nT, 7, dtype=torch.float64, device=cuda),
+                   torch.zeros(1, dtype=torch.int32, device=cuda), torch.zeros(4, n_steps, 128, device=cuda), torch.zeros(4, 1, 128, device=cuda), 2.5, 15.0)
+    T32 = Ts.clone()
+    ang2, lin2 = ops.score_tp_step(T32, qf, key_f, qx, qw, (64, 32, 16), Wd, Wl0, Wl1, bl, 32, 15.0, state=st)
+    assert torch.equal(ang2, ang0) and torch.equal(lin2, lin0)
+    ref = T64.clone()
+    row = sched[step].tolist()
+    ops.pose_update(ref, ang0, lin0, None, 99, step, row[0], 2.5, 15.0, row[1], row[2], row[3], None, None)
+    assert torch.equal(st.T64, ref), float((st.T64 - ref).abs().max())
+    assert torch.equal(st.traj[step + 1], ref) and torch.equal(T32, ref.float())
+    assert int(st.counter) == step + 1 and int(st.ticket) == 0
+    # injected noise rows
+    noise = torch.randn(n_steps, nT, 6, dtype=torch.float64, device=cuda)
+    st2 = st._replace(T64=T64.clone(), counter=torch.full((1,), step, dtype=torch.int32, device=cuda), noise=noise)
+    T32 = Ts.clone()
+    ops.score_tp_step(T32, qf, key_f, qx, qw, (64, 32, 16), Wd, Wl0, Wl1, bl, 32, 15.0, state=st2)
+    ref = T64.clone()
+    ops.pose_update(ref, ang0, lin0, noise[step].contiguous(), 0, 0, row[0], 2.5, 15.0, row[1], row[2], row[3], None, None)
+    assert torch.equal(st2.T64, ref)

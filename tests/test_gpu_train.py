@@ -135,3 +135,39 @@ def test_place_config_gradients_match_oracle(cuda):
     worst.sort(reverse=True)
     assert len(worst) > 500 and any(n.startswith("query_model.weight_field") for _, n in worst)
     assert worst[0][0] <= 3e-3, f"largest gradient errors: {worst[:8]}"
+
+
+def test_sapien_highres_forward_only_gradients_match_oracle(cuda):
+    """ForwardOnlyFeatureExtractor (sapien highres configs) on the training path: down path only, no mid / up blocks, no skips
+    (forward_only_feature_extractor.py:191-275).  Round-1 advisor finding: train_path.unet_forward had no forward_only branch."""
+    from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel
+    from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs_sapien_highres
+    from oracle import model as OM
+    torch.manual_seed(43)
+    oracle = OM.MultiscaleScoreModel(**model_kwargs_sapien_highres(), deterministic=True).eval()
+    model = MultiscaleScoreModel(**model_kwargs_sapien_highres(), deterministic=True).eval()
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda)
+    x, rgb = make_scene(900, seed=43, half_extent=10.0)
+    Ts, t = make_poses(4, x, seed=43, spread=2.5)
+    g = torch.Generator().manual_seed(2)
+    ta, tl = torch.randn(4, 3, generator=g), torch.randn(4, 3, generator=g)
+    b = torch.zeros(len(x), dtype=torch.long)
+    grasp = (torch.zeros(3, 3), torch.zeros(3, 3), torch.zeros(3, dtype=torch.long))
+    loss_o, *_ = oracle.get_train_loss(Ts, t, OM.FeaturedPoints(x, rgb, b), OM.FeaturedPoints(*grasp), ta, tl)
+    loss_o.backward()
+    d = lambda v: v.to(cuda)
+    loss, *_ = model.get_train_loss(d(Ts), d(t), FeaturedPoints(d(x), d(rgb), d(b)), FeaturedPoints(*[d(v) for v in grasp]), d(ta), d(tl))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_o.detach())) <= 2e-4 * abs(float(loss_o.detach()))
+    po = dict(oracle.named_parameters())
+    worst = []
+    for name, p in model.named_parameters():
+        go = po[name].grad
+        if go is None or float(go.abs().max()) < 1e-12:
+            continue
+        assert p.grad is not None, name
+        worst.append((rel_err(p.grad, go), name))
+    worst.sort(reverse=True)
+    assert len(worst) > 100 and any(n.startswith("key_model.down_blocks") for _, n in worst)
+    assert worst[0][0] <= 3e-3, f"largest gradient errors: {worst[:8]}"

@@ -39,7 +39,7 @@ def test_abi_struct_layouts_match_header():
     """sizeof the ctypes mirrors == sizeof the C structs (compiled with gcc against the real header)."""
     import tempfile
     from diffusion_edf_b200 import _lib
-    src = '#include <stdio.h>\n#include "dedf.h"\nint main(){printf("%zu %zu\\n", sizeof(dedf_mlp_desc), sizeof(dedf_time_desc));return 0;}\n'
+    src = '#include <stdio.h>\n#include "dedf.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(dedf_mlp_desc), sizeof(dedf_time_desc), sizeof(dedf_node_chain_desc), sizeof(dedf_head_front_desc), sizeof(dedf_score_step_desc));return 0;}\n'
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "s.c")
         open(c, "w").write(src)
@@ -47,8 +47,9 @@ def test_abi_struct_layouts_match_header():
         r = subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include", c, "-o", exe], capture_output=True, text=True)
         if r.returncode != 0:
             pytest.skip("gcc / cuda headers unavailable: " + r.stderr[:200])
-        a, b = map(int, subprocess.check_output([exe]).split())
-    assert ctypes.sizeof(_lib.MlpDesc) == a and ctypes.sizeof(_lib.TimeDesc) == b
+        a, b, c2, c3, c4 = map(int, subprocess.check_output([exe]).split())
+    assert ctypes.sizeof(_lib.MlpDesc) == a and ctypes.sizeof(_lib.TimeDesc) == b and ctypes.sizeof(_lib.NodeChainDesc) == c2
+    assert ctypes.sizeof(_lib.HeadFrontDesc) == c3 and ctypes.sizeof(_lib.ScoreStepDesc) == c4
 
 
 def test_ops_fail_loudly_without_cuda_tensors():
