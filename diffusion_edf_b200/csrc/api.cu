@@ -30,7 +30,7 @@ extern "C" int dedf_build_arch(void) { return 100; }
 extern "C" int dedf_flag_if_differs(const long long* a, const long long* b, long long n, int* flag, cudaStream_t stream) {
     if (n <= 0) return DEDF_OK;
     if (!a || !b || !flag) return DEDF_ERR_ARG;
-    dedf::flag_if_differs_kernel<<<dedf::grid_for(n, 256, dedf::kNumSMs), 256, 0, stream>>>(a, b, n, flag);
+    dedf::flag_if_differs_kernel<<<dedf::grid_for(n, 256, kNumSMs), 256, 0, stream>>>(a, b, n, flag);
     if (cudaGetLastError() != cudaSuccess) return DEDF_ERR_LAUNCH;
     return DEDF_OK;
 }
@@ -72,7 +72,7 @@ extern "C" int dedf_l2_persist(const void* base, long long bytes, cudaStream_t s
 extern "C" int dedf_prefetch_l2(const void* const* ptrs_dev, const long long* bytes_dev, int n, cudaStream_t stream) {
     if (n <= 0) return DEDF_OK;
     if (!ptrs_dev || !bytes_dev) return DEDF_ERR_ARG;
-    dedf::prefetch_l2_kernel<<<dedf::grid_for(n, 1, dedf::kNumSMs * 4), 256, 0, stream>>>(ptrs_dev, bytes_dev, n);
+    dedf::prefetch_l2_kernel<<<dedf::grid_for(n, 1, kNumSMs * 4), 256, 0, stream>>>(ptrs_dev, bytes_dev, n);
     if (cudaGetLastError() != cudaSuccess) return DEDF_ERR_LAUNCH;
     return DEDF_OK;
 }

@@ -9,12 +9,21 @@ namespace dedf {
 
 // e3nn.math.normalize2mom constants (Monte-Carlo values of e3nn==0.4.4's recipe:
 // manual_seed(0), randn(1_000_000, float64)); used by fast_activation.py:69 in the
-// reference.  tests/test_constants.py checks them against the oracle's recomputation.
+// reference.  tests/test_host.py::test_kernel_constants_match_oracle checks them against the oracle's recomputation.
 constexpr float kCSilu = 1.6791767923989418f;
 constexpr float kCSigmoid = 1.8467055342154763f;
 constexpr float kCSlrelu = 1.531320475574866f;
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the current device (B200: 148), queried once per process: grids are sized in multiples of it.  Host only.
+inline int num_sms() {
+    static int n = 0;
+    if (n <= 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+#define kNumSMs (::dedf::num_sms())
 
 // return codes: DEDF_OK / DEDF_ERR_* of include/dedf.h
 
@@ -55,6 +64,47 @@ __device__ __forceinline__ void sph_harm_l2(float x, float y, float z, float* sh
     sh[6] = s5 * (y * y - 0.5f * (x * x + z * z));
     sh[7] = s15 * y * z;
     sh[8] = 0.5f * s15 * (z * z - x * x);
+}
+
+// ---- edge geometry with EXPLICIT rounding -------------------------------------------------------------------------------
+// Every multiply / add is an _rn intrinsic, so no compiler context can contract a pair into an FMA: the un-fused
+// edge_geom_kernel and the fused head_front_kernel produce the same bits for the same edge.
+// (graph_parser.py:146-224: length, o3.SphericalHarmonics(normalize=True, 'component'), non-scalar min-cut, edge logits)
+__device__ __forceinline__ float soft_step3_rn(float x) {
+    if (x <= 0.0f) return 0.0f;
+    if (x >= 1.0f) return 1.0f;
+    const float x3 = __fmul_rn(__fmul_rn(x, x), x);
+    return __fsub_rn(__fmul_rn(4.0f, x3), __fmul_rn(__fmul_rn(3.0f, x3), x));
+}
+// vec = x_src - x_dst; ns_hi <= 0: no non-scalar cut; r < 0: all-pairs scale (logit 0); lg may be null
+__device__ __forceinline__ void edge_geometry_rn(float vx, float vy, float vz, float ns_lo, float ns_hi, float r, float* len_out,
+                                                 float* sh, float* lg) {
+    const float len = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
+    const float inv = 1.0f / fmaxf(len, 1e-12f);          // F.normalize
+    const float x = __fmul_rn(vx, inv), y = __fmul_rn(vy, inv), z = __fmul_rn(vz, inv);
+    const float s3 = 1.7320508075688772f, s5 = 2.23606797749979f, s15 = 3.872983346207417f;
+    sh[0] = 1.0f;
+    sh[1] = __fmul_rn(s3, x); sh[2] = __fmul_rn(s3, y); sh[3] = __fmul_rn(s3, z);
+    sh[4] = __fmul_rn(__fmul_rn(s15, x), z);
+    sh[5] = __fmul_rn(__fmul_rn(s15, x), y);
+    sh[6] = __fmul_rn(s5, __fsub_rn(__fmul_rn(y, y), __fmul_rn(0.5f, __fadd_rn(__fmul_rn(x, x), __fmul_rn(z, z)))));
+    sh[7] = __fmul_rn(__fmul_rn(s15, y), z);
+    sh[8] = __fmul_rn(0.5f * s15, __fsub_rn(__fmul_rn(z, z), __fmul_rn(x, x)));
+    if (ns_hi > 0.f) {                                     // graph_parser.py:174-177, 199-204
+        const float c = soft_step3_rn(__fsub_rn(len, ns_lo) / __fsub_rn(ns_hi, ns_lo));
+#pragma unroll
+        for (int j = 1; j < 9; ++j) sh[j] = __fmul_rn(sh[j], c);
+    }
+    *len_out = len;
+    if (lg) {
+        float v = 0.f;
+        if (r >= 0.f) {                                    // graph_parser.py:170-173, 206-215
+            const float r8 = __fmul_rn(0.8f, r);
+            const float cut = __fsub_rn(1.0f, soft_step3_rn(__fsub_rn(len, r8) / __fsub_rn(r, r8)));
+            v = logf(fmaxf(cut, 1e-12f));
+        }
+        *lg = v;
+    }
 }
 
 // Feature layout of an irreps triple (m0 x0e + m1 x1e + m2 x2e), e3nn mul_ir order.

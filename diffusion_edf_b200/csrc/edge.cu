@@ -39,29 +39,14 @@ __global__ void __launch_bounds__(256) edge_geom_kernel(GeomArgs a) {
         const float vx = a.x_src[3 * s] - a.x_dst[3 * d];
         const float vy = a.x_src[3 * s + 1] - a.x_dst[3 * d + 1];
         const float vz = a.x_src[3 * s + 2] - a.x_dst[3 * d + 2];
-        const float len = sqrtf(vx * vx + vy * vy + vz * vz);
-        const float inv = 1.0f / fmaxf(len, 1e-12f);          // F.normalize
-        float sh[9];
-        sph_harm_l2(vx * inv, vy * inv, vz * inv, sh);
-        if (a.ns_hi > 0.f) {                                   // graph_parser.py:174-177, 199-204
-            const float c = soft_step3((len - a.ns_lo) / (a.ns_hi - a.ns_lo));
-#pragma unroll
-            for (int j = 1; j < 9; ++j) sh[j] *= c;
-        }
+        int sc = 0;
+        if (a.logit) while (sc + 1 < a.n_scales && s >= a.src_off[sc + 1]) ++sc;
+        float len, sh[9], lg;
+        edge_geometry_rn(vx, vy, vz, a.ns_lo, a.ns_hi, a.logit ? a.r[sc] : -1.f, &len, sh, &lg);
         a.length[e] = len;
 #pragma unroll
         for (int j = 0; j < 9; ++j) a.sh[(size_t)e * 9 + j] = sh[j];
-        if (a.logit) {
-            int sc = 0;
-            while (sc + 1 < a.n_scales && s >= a.src_off[sc + 1]) ++sc;
-            const float r = a.r[sc];
-            float lg = 0.f;
-            if (r >= 0.f) {                                    // graph_parser.py:170-173, 206-215
-                const float cut = 1.0f - soft_step3((len - 0.8f * r) / (r - 0.8f * r));
-                lg = logf(fmaxf(cut, 1e-12f));
-            }
-            a.logit[e] = lg;
-        }
+        if (a.logit) a.logit[e] = lg;
     }
 }
 

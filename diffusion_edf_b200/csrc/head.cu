@@ -104,9 +104,10 @@ __global__ void __launch_bounds__(128) query_transform_kernel(QueryArgs a) {
     const int F = a.irr.dim();
     for (int q = tid; q < a.n_q; q += blockDim.x) {
         float p[3] = {a.qx[3 * q], a.qx[3 * q + 1], a.qx[3 * q + 2]}, o[3];
-        quat_apply<float>(sq, p, o);
+        const float T7[7] = {sq[0], sq[1], sq[2], sq[3], st[0], st[1], st[2]};
+        transform_point_f(T7, p, o);
         float* xo = a.x_out + ((size_t)t * a.n_q + q) * 3;
-        xo[0] = o[0] + st[0]; xo[1] = o[1] + st[1]; xo[2] = o[2] + st[2];
+        xo[0] = o[0]; xo[1] = o[1]; xo[2] = o[2];
     }
     for (int i = tid; i < a.n_q * F; i += blockDim.x) {
         const int q = i / F, c = i % F;
@@ -471,10 +472,10 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
             ang[0] += w * (ox + s[0]); ang[1] += w * (oy + s[1]); ang[2] += w * (oz + s[2]);
         }
         for (int i = 0; i < 3; ++i) { a.lin_out[(size_t)t * 3 + i] = lin[i]; a.ang_out[(size_t)t * 3 + i] = ang[i]; }
-        if (a.T64) {
+        if (a.T64 && step_now < a.n_steps) {       // (a replay past the end of the schedule is a no-op, not an out-of-bounds row)
             // fused Langevin step of pose t (pose_update_kernel + cast_pose_kernel); every CTA read `step_now` before any
             // CTA can advance the counter (the last ticket holder does, below)
-            const double* row = a.sched + (size_t)min(step_now, a.n_steps - 1) * 4;
+            const double* row = a.sched + (size_t)step_now * 4;
             double* Td = a.T64 + (size_t)t * 7;
             langevin_step(Td, ang, lin, a.noise ? a.noise + ((size_t)step_now * a.n_t + t) * 6 : nullptr,
                           a.seed_dev ? *a.seed_dev : a.seed, (unsigned long long)t,

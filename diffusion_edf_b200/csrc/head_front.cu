@@ -34,7 +34,6 @@ __device__ __forceinline__ float sqdist_exact_hf(float ax, float ay, float az, f
 
 constexpr int kFrontThreads = 256;
 constexpr int kFrontWarps = kFrontThreads / 32;
-constexpr int kFrontU = 4;                      // 32-source chunks per warp iteration
 
 struct FrontArgs {
     const float* Ts; int n_t;
@@ -51,6 +50,7 @@ struct FrontArgs {
     // denoise loop (optional): this step's rows of the precomputed time embedding
     const int* step; int n_steps; const float* rows_all; float* rows_cur; int rows_k;
     int stage_early;                            // the sources are static (denoise loop): stage them before the PDL wait
+    long long* dbg;                             // optional (host debug hook): [grid][8] %globaltimer stamps per CTA
     long long cost[DEDF_MAX_SCALES + 1];        // cumulative cost at the start of every scale (n_dst * c_s summed)
     int c[DEDF_MAX_SCALES];                     // cost per item of the scale
 };
@@ -87,86 +87,113 @@ __device__ __forceinline__ void front_grid_barrier(unsigned* bar, unsigned n_cta
     __syncthreads();
 }
 
-template <bool FILL>
-__device__ __forceinline__ int front_walk(const FrontArgs& a, const float* xs, const int* sb, int stage_lo, int item, int n_dst,
-                                          int lane, int base, int seg_end) {
-    const int s = item / n_dst, d = item - s * n_dst;
-    const int s0 = a.src_off[s], s1 = a.src_off[s + 1];
-    const float r = a.r[s];
-    const bool all = r < 0.f;
-    const float r2 = r * r;
-    const int cap_nb = all ? 0x7fffffff : a.max_nb;     // the all-pairs scale has no neighbour cap (graph_parser.py:274-278)
-    // x' = R(q) x + t, the arithmetic of query_transform_kernel
-    const int t = d / a.n_q, qi = d - t * a.n_q;
-    const float* T = a.Ts + (size_t)t * 7;
-    const float q4[4] = {T[0], T[1], T[2], T[3]};
-    const float p[3] = {a.qx[3 * qi], a.qx[3 * qi + 1], a.qx[3 * qi + 2]};
-    float o[3];
-    quat_apply<float>(q4, p, o);
-    const float qx = o[0] + T[4], qy = o[1] + T[5], qz = o[2] + T[6];
-    if (!FILL && s == 0 && lane == 0) { a.x_dst[3 * d] = qx; a.x_dst[3 * d + 1] = qy; a.x_dst[3 * d + 2] = qz; }
-    const long long qb = a.b_q ? a.b_q[qi] : 0;
-    int cnt_all = 0, cnt_keep = 0;
-    for (int c0 = s0; c0 < s1 && cnt_all < cap_nb; c0 += 32 * kFrontU) {
-        bool hit[kFrontU];
-        float sx[kFrontU], sy[kFrontU], sz[kFrontU];
-#pragma unroll
-        for (int u = 0; u < kFrontU; ++u) {
-            const int i = c0 + 32 * u + lane;
-            hit[u] = false;
-            if (i < s1) {
-                const float* ps = xs + 3 * (i - stage_lo);
-                sx[u] = ps[0]; sy[u] = ps[1]; sz[u] = ps[2];
-                hit[u] = all || sqdist_exact_hf(sx[u], sy[u], sz[u], qx, qy, qz) < r2;
-                if (sb && !all) hit[u] = hit[u] && ((long long)sb[i - stage_lo] == qb);     // all pairs ignores batches (:276-278)
-            }
-        }
-        const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-        for (int u = 0; u < kFrontU; ++u) {
-            const unsigned bal = __ballot_sync(0xffffffffu, hit[u]);
-            const bool keep = hit[u] && (cnt_all + __popc(bal & lt) < cap_nb);
-            const unsigned bal_keep = __ballot_sync(0xffffffffu, keep);
-            if (FILL && keep) {
-                const int pos = base + cnt_keep + __popc(bal_keep & lt);
-                if (pos < seg_end) {
-                    const int i = c0 + 32 * u + lane;
-                    a.edge_src[pos] = i;
-                    a.edge_dst[pos] = d;
-                    // edge geometry: the expressions of edge_geom_kernel
-                    const float vx = sx[u] - qx, vy = sy[u] - qy, vz = sz[u] - qz;
-                    const float len = sqrtf(vx * vx + vy * vy + vz * vz);
-                    const float inv = 1.0f / fmaxf(len, 1e-12f);
-                    float shv[9];
-                    sph_harm_l2(vx * inv, vy * inv, vz * inv, shv);
-                    if (a.ns_hi > 0.f) {
-                        const float cc = soft_step3((len - a.ns_lo) / (a.ns_hi - a.ns_lo));
-#pragma unroll
-                        for (int j = 1; j < 9; ++j) shv[j] *= cc;
-                    }
-                    a.length[pos] = len;
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) a.sh[(size_t)pos * 9 + j] = shv[j];
-                    float lg = 0.f;
-                    if (!all) {
-                        const float cut = 1.0f - soft_step3((len - 0.8f * r) / (r - 0.8f * r));
-                        lg = logf(fmaxf(cut, 1e-12f));
-                    }
-                    a.logit[pos] = lg;
-                }
-            }
-            cnt_all += __popc(bal);
-            cnt_keep += __popc(bal_keep);
-        }
-    }
-    return cnt_keep;
+// One warp, one item (scale s, destination d): lane L owns the CONTIGUOUS block of sources [s0 + L B, s0 + (L+1) B), B odd (its
+// shared-memory reads are then conflict-free: stride 3 B words).  Blocks are in index order, so "hits of lower lanes, then my
+// earlier hits" IS the ascending source order torch_cluster returns: one warp scan of the per-lane counts replaces the chain of
+// dependent ballots of an ordered 32-at-a-time walk (which costs ~1 us per 128 sources at one warp per scheduler), and the
+// per-source loop is independent iterations.  max_num_neighbors keeps the first cap_nb hits, like torch_cluster.
+struct FrontItem { int s, d, s0, s1, B; float r, r2, qx, qy, qz; bool all; int cap_nb; long long qb; };
+
+__device__ __forceinline__ FrontItem front_item(const FrontArgs& a, const float* s_q, int item, int i_lo, int n_dst) {
+    FrontItem it;
+    it.s = item / n_dst; it.d = item - it.s * n_dst;
+    it.s0 = a.src_off[it.s]; it.s1 = a.src_off[it.s + 1];
+    it.B = (((it.s1 - it.s0) + 31) >> 5) | 1;
+    it.r = a.r[it.s]; it.all = it.r < 0.f; it.r2 = it.r * it.r;
+    it.cap_nb = it.all ? 0x7fffffff : a.max_nb;       // the all-pairs scale has no neighbour cap (graph_parser.py:274-278)
+    const float* q = s_q + 3 * (item - i_lo);
+    it.qx = q[0]; it.qy = q[1]; it.qz = q[2];
+    it.qb = a.b_q ? a.b_q[it.d % a.n_q] : 0;
+    return it;
 }
 
-__global__ void __launch_bounds__(kFrontThreads) head_front_kernel(FrontArgs a) {
+// branch-free (the loop over a lane's block must pipeline: 4 independent load + distance chains in flight)
+__device__ __forceinline__ bool front_hit(const FrontItem& it, const float* xs, const int* sb, int stage_lo, int i) {
+    const float* ps = xs + 3 * (i - stage_lo);
+    const float d2 = sqdist_exact_hf(ps[0], ps[1], ps[2], it.qx, it.qy, it.qz);
+    bool h = d2 < it.r2;
+    if (sb) h = h & (sb[i - stage_lo] == (int)it.qb);     // (uniform branch) batch ids; all pairs ignores them (graph_parser.py:276-278)
+    return h | it.all;
+}
+
+__device__ __forceinline__ int front_count(const FrontItem& it, const float* xs, const int* sb, int stage_lo, int lane) {
+    const int lo = it.s0 + lane * it.B, hi = min(lo + it.B, it.s1);
+    int cnt = 0;
+    int i = lo;
+    for (; i + 4 <= hi; i += 4) {
+        bool h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = front_hit(it, xs, sb, stage_lo, i + u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cnt += h[u] ? 1 : 0;
+    }
+    for (; i < hi; ++i) cnt += front_hit(it, xs, sb, stage_lo, i) ? 1 : 0;
+    return cnt;
+}
+
+__device__ __forceinline__ void front_emit(const FrontArgs& a, const FrontItem& it, const float* xs, int stage_lo, int i, int pos) {
+    const float* ps = xs + 3 * (i - stage_lo);
+    a.edge_src[pos] = i;                   // flat index into the concatenated clouds
+    a.edge_dst[pos] = it.d;
+    float len, shv[9], lg;
+    edge_geometry_rn(ps[0] - it.qx, ps[1] - it.qy, ps[2] - it.qz, a.ns_lo, a.ns_hi, it.all ? -1.f : it.r, &len, shv, &lg);
+    a.length[pos] = len;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) a.sh[(size_t)pos * 9 + j] = shv[j];
+    a.logit[pos] = lg;
+}
+
+__device__ __forceinline__ void front_fill(const FrontArgs& a, const FrontItem& it, const float* xs, const int* sb, int stage_lo, int lane,
+                                           int base, int seg_end) {
+    const int lo = it.s0 + lane * it.B, hi = min(lo + it.B, it.s1);
+    // hits of this lane's block as a bit mask (B <= 64), else they are re-evaluated while writing
+    unsigned long long mask = 0ull;
+    int cnt = 0;
+    const bool use_mask = it.B <= 64;
+    {
+        int i = lo;
+        for (; i + 4 <= hi; i += 4) {
+            bool h[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) h[u] = front_hit(it, xs, sb, stage_lo, i + u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { cnt += h[u] ? 1 : 0; mask |= (unsigned long long)(h[u] ? 1 : 0) << ((i + u - lo) & 63); }
+        }
+        for (; i < hi; ++i) {
+            const bool h = front_hit(it, xs, sb, stage_lo, i);
+            cnt += h ? 1 : 0;
+            mask |= (unsigned long long)(h ? 1 : 0) << ((i - lo) & 63);
+        }
+    }
+    // exclusive scan of the per-lane counts
+    int pre = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+    int rank = pre - cnt;
+    if (use_mask) {
+        while (mask) {
+            const int j = __ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            if (rank < it.cap_nb && base + rank < seg_end) front_emit(a, it, xs, stage_lo, lo + j, base + rank);
+            ++rank;
+        }
+    } else {
+        for (int i = lo; i < hi; ++i)
+            if (front_hit(it, xs, sb, stage_lo, i)) {
+                if (rank < it.cap_nb && base + rank < seg_end) front_emit(a, it, xs, stage_lo, i, base + rank);
+                ++rank;
+            }
+    }
+}
+
+__global__ void __launch_bounds__(kFrontThreads) head_front_kernel(FrontArgs a, int q_items) {
     extern __shared__ __align__(16) float s_x[];
     __shared__ int s_scan[kFrontThreads];
     __shared__ int s_base, s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int dbg_i = 0;
+#define FRONT_STAMP() do { if (a.dbg && tid == 0 && dbg_i < 8) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.dbg[blockIdx.x * 8 + dbg_i++] = t_; } } while (0)
+    FRONT_STAMP();
     const int n_dst = a.n_t * a.n_q;
     const int n_items = a.n_scales * n_dst;
     const long long ctot = a.cost[a.n_scales];
@@ -179,7 +206,8 @@ __global__ void __launch_bounds__(kFrontThreads) head_front_kernel(FrontArgs a) 
         stage_hi = a.src_off[(i_hi - 1) / n_dst + 1];
     }
     const int n_st = stage_hi - stage_lo;
-    int* s_b = a.b_src ? reinterpret_cast<int*>(s_x + 3 * n_st) : nullptr;
+    float* s_q = s_x + ((3 * (a.src_off[a.n_scales] - a.src_off[0]) + 3) & ~3);      // [q_items][3] transformed query points
+    int* s_b = a.b_src ? reinterpret_cast<int*>(s_q + 3 * q_items) : nullptr;
     if (!a.stage_early) pdl_wait();     // the sources were produced earlier in this stream (plain forward): wait first
     {
         constexpr int UX = 12;
@@ -194,17 +222,34 @@ __global__ void __launch_bounds__(kFrontThreads) head_front_kernel(FrontArgs a) 
         }
         if (s_b) for (int i = tid; i < n_st; i += kFrontThreads) s_b[i] = (int)__ldg(a.b_src + stage_lo + i);
     }
+    FRONT_STAMP();
     if (a.stage_early) pdl_wait();      // the poses come from the previous kernel (the previous step's pose update)
+    FRONT_STAMP();
     if (b == 0 && a.rows_all) {   // this step's time rows (the job of dedf_sample_advance)
         const int st = min(*a.step, a.n_steps - 1);
         for (int j = tid; j < a.n_scales * a.rows_k; j += kFrontThreads)
             a.rows_cur[j] = a.rows_all[((size_t)(j / a.rows_k) * a.n_steps + st) * a.rows_k + (j % a.rows_k)];
     }
+    // ---- x' = R(q) x + t for every item of this CTA (one thread each; the walks then never wait on global memory) ----
+    for (int k = tid; k < i_hi - i_lo; k += kFrontThreads) {
+        const int item = i_lo + k, s = item / n_dst, d = item - s * n_dst;
+        const int t = d / a.n_q, qi = d - t * a.n_q;
+        const float* T = a.Ts + (size_t)t * 7;
+        const float T7[7] = {T[0], T[1], T[2], T[3], T[4], T[5], T[6]};
+        const float p[3] = {a.qx[3 * qi], a.qx[3 * qi + 1], a.qx[3 * qi + 2]};
+        float o[3];
+        transform_point_f(T7, p, o);
+        s_q[3 * k] = o[0]; s_q[3 * k + 1] = o[1]; s_q[3 * k + 2] = o[2];
+        if (s == 0) { a.x_dst[3 * d] = o[0]; a.x_dst[3 * d + 1] = o[1]; a.x_dst[3 * d + 2] = o[2]; }
+    }
     __syncthreads();
+    FRONT_STAMP();
     // ---- phase 1: counts ----
     int my_sum = 0;
     for (int item = i_lo + warp; item < i_hi; item += kFrontWarps) {
-        const int cnt = front_walk<false>(a, s_x, s_b, stage_lo, item, n_dst, lane, 0, 0);
+        const FrontItem it = front_item(a, s_q, item, i_lo, n_dst);
+        int cnt = front_count(it, s_x, s_b, stage_lo, lane);
+        cnt = min(__reduce_add_sync(0xffffffffu, cnt), it.cap_nb);
         if (lane == 0) { a.counts[item] = cnt; my_sum += cnt; }
     }
     s_scan[tid] = (lane == 0) ? my_sum : 0;
@@ -214,7 +259,9 @@ __global__ void __launch_bounds__(kFrontThreads) head_front_kernel(FrontArgs a) 
         for (int w = 0; w < kFrontWarps; ++w) t += s_scan[w * 32];
         a.cta_sum[b] = t;
     }
+    FRONT_STAMP();
     front_grid_barrier(a.barrier, (unsigned)G);
+    FRONT_STAMP();
     pdl_launch();                 // only now: every CTA of this grid is resident, dependents cannot starve the barrier
     // ---- phase 2: CSR offsets ----
     if (warp == 0) {
@@ -232,17 +279,16 @@ __global__ void __launch_bounds__(kFrontThreads) head_front_kernel(FrontArgs a) 
     for (int c0 = i_lo; c0 < i_hi; c0 += kFrontThreads) {
         const int item = c0 + tid;
         const int v = (item < i_hi) ? a.counts[item] : 0;
-        // inclusive block scan (Hillis-Steele over 256 entries)
-        s_scan[tid] = v;
+        // inclusive block scan: warp scans + a scan of the 8 warp totals
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) s_scan[warp] = inc;
         __syncthreads();
-        for (int o = 1; o < kFrontThreads; o <<= 1) {
-            const int u = (tid >= o) ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += u;
-            __syncthreads();
-        }
-        if (item < i_hi) a.row_ptr[item] = min(run + s_scan[tid] - v, cap);
-        const int chunk_total = s_scan[kFrontThreads - 1];
+        int wbase = 0, chunk_total = 0;
+#pragma unroll
+        for (int w = 0; w < kFrontWarps; ++w) { const int tw = s_scan[w]; if (w < warp) wbase += tw; chunk_total += tw; }
+        if (item < i_hi) a.row_ptr[item] = min(run + wbase + inc - v, cap);
         __syncthreads();
         run += chunk_total;
     }
@@ -253,17 +299,27 @@ __global__ void __launch_bounds__(kFrontThreads) head_front_kernel(FrontArgs a) 
         if (a.overflow && run > cap) atomicOr(a.overflow, 1);
     }
     __syncthreads();              // this CTA's row_ptr entries are visible to its own warps
+    FRONT_STAMP();
     // ---- phase 3: fill + geometry ----
     for (int item = i_lo + warp; item < i_hi; item += kFrontWarps) {
         const int base = a.row_ptr[item];
         const int end = (item + 1 < i_hi) ? a.row_ptr[item + 1] : min(s_total, cap);
-        front_walk<true>(a, s_x, s_b, stage_lo, item, n_dst, lane, base, end);
+        const FrontItem it = front_item(a, s_q, item, i_lo, n_dst);
+        front_fill(a, it, s_x, s_b, stage_lo, lane, base, end);
     }
+    __syncthreads();
+    FRONT_STAMP();
+#undef FRONT_STAMP
 }
 
 }  // namespace dedf
 
 using namespace dedf;
+
+static long long* g_front_dbg = nullptr;
+/* debug hook (not part of the public header): [148][8] int64 device buffer receiving %globaltimer stamps of every CTA:
+ * start, staged, dependency wait over, points transformed, counted, barrier passed, CSR written, filled */
+extern "C" int dedf_head_front_set_debug(long long* dbg) { g_front_dbg = dbg; return DEDF_OK; }
 
 extern "C" int dedf_head_front(const dedf_head_front_desc* d, cudaStream_t stream) {
     if (!d || !d->Ts || !d->qx || !d->x_src || !d->x_dst || !d->row_ptr || !d->counts || !d->edge_src || !d->edge_dst || !d->length ||
@@ -278,7 +334,7 @@ extern "C" int dedf_head_front(const dedf_head_front_desc* d, cudaStream_t strea
     a.x_dst = d->x_dst; a.row_ptr = d->row_ptr; a.counts = d->counts; a.edge_src = d->edge_src; a.edge_dst = d->edge_dst;
     a.length = d->length; a.sh = d->sh; a.logit = d->logit; a.n_edges = d->n_edges; a.overflow = d->overflow;
     a.cta_sum = d->cta_sum; a.barrier = d->barrier;
-    a.stage_early = d->stage_early;
+    a.stage_early = d->stage_early; a.dbg = g_front_dbg;
     a.step = d->step; a.n_steps = d->n_steps; a.rows_all = d->rows_all; a.rows_cur = d->rows_cur; a.rows_k = d->rows_k;
     const long long n_dst = (long long)d->n_t * d->n_q;
     if (n_dst * d->n_scales > 0x7fffffffLL) return DEDF_ERR_ARG;
@@ -288,23 +344,26 @@ extern "C" int dedf_head_front(const dedf_head_front_desc* d, cudaStream_t strea
         a.src_off[s] = d->src_off[s]; a.r[s] = d->r[s];
         const int ns = d->src_off[s + 1] - d->src_off[s];
         if (ns < 0) return DEDF_ERR_ARG;
-        a.c[s] = (ns + 32 * kFrontU - 1) / (32 * kFrontU);
-        if (a.c[s] < 1) a.c[s] = 1;
+        a.c[s] = (((ns + 31) >> 5) | 1) + 8;                  // per-lane block length + the item's fixed cost (scan, loads)
         a.cost[s + 1] = a.cost[s] + n_dst * a.c[s];
     }
     a.src_off[d->n_scales] = d->src_off[d->n_scales];
     // a CTA's contiguous item range can span several scales: size the staging buffer for all of them
     max_stage = d->src_off[d->n_scales] - d->src_off[0];
-    const size_t smem = (size_t)max_stage * (12 + (d->b_src ? 4 : 0)) + 16;
-    if (smem > 200 * 1024) return DEDF_ERR_UNSUPPORTED;         // larger scenes: the un-fused grid-hash path
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(head_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done = true; }
     // grid <= #SMs (one CTA per SM is guaranteed co-resident: 256 threads, <= 200 KB): the grid barrier needs that
     const long long items = n_dst * d->n_scales;
     int grid = (int)((items + 1) / 2);                           // at least ~2 items per CTA
     if (grid > kNumSMs) grid = kNumSMs;
     if (grid < 1) grid = 1;
-    launch_pdl(head_front_kernel, dim3(grid), dim3(kFrontThreads), smem, stream, a);
+    // items of one CTA: its cost share divided by the cheapest item's cost (+ rounding at both ends)
+    int c_min = a.c[0];
+    for (int s = 1; s < d->n_scales; ++s) c_min = a.c[s] < c_min ? a.c[s] : c_min;
+    const long long q_items = (a.cost[d->n_scales] / grid + c_min) / c_min + 2;
+    const size_t smem = (((size_t)max_stage * 12 + 15) & ~(size_t)15) + (size_t)q_items * 12 + (d->b_src ? (size_t)max_stage * 4 : 0) + 16;
+    if (smem > 200 * 1024) return DEDF_ERR_UNSUPPORTED;         // larger scenes: the un-fused grid-hash path
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(head_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done = true; }
+    launch_pdl(head_front_kernel, dim3(grid), dim3(kFrontThreads), smem, stream, a, (int)q_items);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

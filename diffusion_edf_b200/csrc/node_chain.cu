@@ -314,8 +314,12 @@ extern "C" int dedf_node_chain(const dedf_node_chain_desc* d, cudaStream_t strea
     if (!al16(a.x) || !al16(a.y) || !al16(a.res1) || !al16(a.P0) || !al16(a.P1) || !al16(a.P2) || !al16(a.A0) || !al16(a.A1) || !al16(a.A2) ||
         !al16(a.B0) || !al16(a.B1) || !al16(a.B2)) return DEDF_ERR_UNSUPPORTED;
     if (d->n <= 0) return DEDF_OK;
-    // 16-node tiles when the three weight sets and the tiles fit; 8-node tiles for the wide irreps
-    int rc = launch_chain<16>(a, stream);
+    // Few nodes (the denoise step at 128 poses has 256): 4-node tiles put them on twice as many SMs and each GEMM phase is one
+    // round of work items instead of two -- the launch is latency, not throughput.  Otherwise 16-node tiles when the three
+    // weight sets and the tiles fit, 8-node tiles for the wide irreps.
+    int rc = DEDF_ERR_UNSUPPORTED;
+    if (d->n <= 4 * kNumSMs && !getenv("DEDF_CHAIN_NO_TN4")) rc = launch_chain<4>(a, stream);
+    if (rc == DEDF_ERR_UNSUPPORTED) rc = launch_chain<16>(a, stream);
     if (rc == DEDF_ERR_UNSUPPORTED) rc = launch_chain<8>(a, stream);
     return rc;
 }

@@ -31,6 +31,24 @@ __device__ __forceinline__ void quat_apply(const T* q, const T* p, T* o) {
     o[2] = -tw * az - tx * ay + ty * ax + tz * aw;
 }
 
+// transform_points (edf_interface/.../pcd_utils.py:55-81): x' = quaternion_apply(q, x) + t with the RAW (un-normalised) q.
+// The final add is an explicit __fadd_rn so that no caller's context can contract it into the rotation's last FMA: every kernel
+// that transforms a query point (query_transform_kernel, head_front_kernel) produces the same bits.
+__device__ __forceinline__ void transform_point_f(const float* T7, const float* p, float* out) {
+    const float aw = T7[0], ax = T7[1], ay = T7[2], az = T7[3];
+#define M_(a, b) __fmul_rn(a, b)
+    // quat_apply<float>, every operation rounded on its own (left to right as written there)
+    const float tw = __fsub_rn(__fsub_rn(M_(-ax, p[0]), M_(ay, p[1])), M_(az, p[2]));
+    const float tx = __fsub_rn(__fadd_rn(M_(aw, p[0]), M_(ay, p[2])), M_(az, p[1]));
+    const float ty = __fadd_rn(__fsub_rn(M_(aw, p[1]), M_(ax, p[2])), M_(az, p[0]));
+    const float tz = __fsub_rn(__fadd_rn(M_(aw, p[2]), M_(ax, p[1])), M_(ay, p[0]));
+    const float o0 = __fadd_rn(__fsub_rn(__fadd_rn(M_(-tw, ax), M_(tx, aw)), M_(ty, az)), M_(tz, ay));
+    const float o1 = __fsub_rn(__fadd_rn(__fadd_rn(M_(-tw, ay), M_(tx, az)), M_(ty, aw)), M_(tz, ax));
+    const float o2 = __fadd_rn(__fadd_rn(__fsub_rn(M_(-tw, az), M_(tx, ay)), M_(ty, ax)), M_(tz, aw));
+#undef M_
+    out[0] = __fadd_rn(o0, T7[4]); out[1] = __fadd_rn(o1, T7[5]); out[2] = __fadd_rn(o2, T7[6]);
+}
+
 // D^2(R): Y2_a(R x) = sum_b D_ab Y2_b(x), via the symmetric traceless matrices M_a of the l=2 harmonics
 // (|M_a|_F^2 = 7.5 for every a):  D_ab = <R^T M_a R, M_b>_F / 7.5
 __device__ __forceinline__ void wigner_d2_from_R(const float* R, float* D) {

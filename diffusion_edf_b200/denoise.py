@@ -49,6 +49,9 @@ class StepState(NamedTuple):
 
 class DenoiseGraph:
     MARGIN, MIN_PER_NODE, PAD = 3.0, 96, 1024
+    STEPS_PER_GRAPH = 25      # steps unrolled into one graph launch: a launch costs ~30 us of fixed overhead on top of its
+                              # kernels (profiles/r2_step_ablation_*.json), and consecutive steps inside one graph stay linked
+                              # by programmatic dependent launch (the front kernel's prologue overlaps the previous step's tail)
 
     def __init__(self, model, n_t: int, n_steps: int, sources: Sequence, query: FeaturedPoints, with_noise: bool, dev: torch.device):
         self.model, self.n_t, self.n_steps, self.dev = model, n_t, n_steps, dev
@@ -72,7 +75,9 @@ class DenoiseGraph:
         self.src = [t.detach().clone() if isinstance(t, torch.Tensor) else t for t in sources]
         self.query = FeaturedPoints(x=query.x.detach().clone(), f=query.f.detach().clone(), b=query.b.detach().clone(), w=query.w.detach().clone())
         self.capacity = 0
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None        # one step
+        self.graph_multi: Optional[torch.cuda.CUDAGraph] = None  # STEPS_PER_GRAPH steps
+        self.n_multi = min(self.STEPS_PER_GRAPH, n_steps)
         self.n_kernels = 0
         self.replans = 0
 
@@ -105,6 +110,13 @@ class DenoiseGraph:
         with torch.cuda.graph(self.graph):
             self._step()
         self.n_kernels = ops.LAUNCHES - k0
+        self.graph_multi = None
+        if self.n_multi > 1:
+            self.graph_multi = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_multi):
+                for _ in range(self.n_multi):
+                    self._step()
+        ops.LAUNCHES = k0 + self.n_kernels
         self._reset(T_seed)
 
     def _initial_capacity(self) -> int:
@@ -137,7 +149,10 @@ class DenoiseGraph:
             self._capture(T_seed)
         worst = None
         while True:
-            for _ in range(self.n_steps):
+            n_full = self.n_steps // self.n_multi if self.graph_multi is not None else 0
+            for _ in range(n_full):
+                self.graph_multi.replay()
+            for _ in range(self.n_steps - n_full * self.n_multi):
                 self.graph.replay()
             ops.LAUNCHES += self.n_kernels * self.n_steps
             self.traj[self.n_steps + 1].copy_(self.T64)

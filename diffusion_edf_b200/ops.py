@@ -31,6 +31,31 @@ class Csr(NamedTuple):
 GRID_MIN_SOURCES = 1024     # radius searches over at least this many sources use the grid-hash kernels
 LAUNCHES = 0
 PROFILE = None      # set to {} to collect {entry point: [(start_event, end_event), ...]}
+FLOPS = {}          # while PROFILE is on: {entry point: algorithmic fp32 FLOPs (2 x MAC) of the calls made} -- bench.py's roofline_step
+
+
+def _flops(name: str, value: float) -> None:
+    if PROFILE is not None:
+        FLOPS[name] = FLOPS.get(name, 0.0) + float(value)
+
+
+def _irr_mac(a, b) -> int:
+    """MACs per node of a block-diagonal LinearRS a -> b (each l block applied to its 2l+1 components)."""
+    return a[0] * b[0] + 3 * a[1] * b[1] + 5 * a[2] * b[2]
+
+
+def _tp_act_flops(G: int) -> float:
+    """per edge: [sep_alpha | sep_act.lin] on the depthwise tensor-product output (104 448 at G = 32) + the CG contraction."""
+    M0, M1, M2 = 2 * G, G, G // 2
+    D0, D1, D2 = M0 + M1 + M2, M0 + 3 * M1 + 2 * M2, M0 + 2 * M1 + 3 * M2
+    return 2.0 * (D0 * (M0 + D0) + 3 * D1 * M1 + 5 * D2 * M2) + 10_000.0 * G / 32
+
+
+def _value_flops(G: int):
+    """(per edge, per destination): CG contraction + 4 head-weighted folds of the 49 G outputs; sep_value.lin once per destination."""
+    M0, M1, M2 = 2 * G, G, G // 2
+    D0, D1, D2 = M0 + M1 + M2, M0 + 3 * M1 + 2 * M2, M0 + 2 * M1 + 3 * M2
+    return 10_000.0 * G / 32 + 2.0 * 4 * 49 * G, 2.0 * (D0 * M0 + 3 * D1 * M1 + 5 * D2 * M2)
 _KERNELS = {"dedf_grid_build": 4, "dedf_radius_grid_count": 2, "dedf_radius_grid_fill": 1, "dedf_fps": 1, "dedf_radius_count": 2, "dedf_radius_fill": 1, "dedf_edge_geom": 1, "dedf_edge_mlp": 1, "dedf_edge_mlp_tc": 1,
             "dedf_edge_tp_lin": 1, "dedf_segment_softmax_reduce": 1, "dedf_edge_tp_reduce": 1, "dedf_node_linear": 1,
             "dedf_gather_rows": 1, "dedf_weight_post": 1, "dedf_add_scale": 1, "dedf_time_embed": 1, "dedf_query_transform": 1, "dedf_score_tp": 1,
@@ -379,6 +404,7 @@ def edge_mlp(desc: L.MlpDesc, max_edges: int) -> None:
 
 
 def edge_mlp_tc(desc: L.MlpDesc, max_edges: int) -> None:
+    _flops("dedf_edge_mlp_tc", max_edges * 2.0 * sum(desc.dims[i] * desc.dims[i + 1] for i in range(desc.n_layers)))
     _call("dedf_edge_mlp_tc", C.byref(desc), max_edges, stream())
 
 
@@ -396,6 +422,7 @@ def edge_tp_act_tc(mul1: int, x_src: torch.Tensor, x_dst: Optional[torch.Tensor]
                    w_perm: bool = False) -> None:
     """dedf_edge_tp_lin(EPI_ACT) with the linear layer on the tcgen05 tensor cores.  ``w_perm``: the columns of ``w`` are in
     the kernel's chunk-major order (layers.tp_act_w_perm)."""
+    _flops("dedf_edge_tp_act_tc", g.n_edges * _tp_act_flops(mul1))
     _call("dedf_edge_tp_act_tc", mul1, ptr(x_src), ptr(x_dst), ptr(g.edge_src, torch.int32), ptr(g.edge_dst, torch.int32),
           ptr(g.n_edges_dev, torch.int32), g.n_edges, ptr(sh), ptr(w), w_stride, 1 if w_perm else 0, ptr(W_tc), ptr(bias0), ptr(alpha_dot),
           ptr(edge_logit), ptr(logits), ptr(out), stream())
@@ -447,6 +474,7 @@ def node_linear(x: torch.Tensor, irr_in, irr_out, W: Sequence[Optional[torch.Ten
         fy -= irr_out[1] + irr_out[2]
     y = torch.empty(n, fy, dtype=torch.float32, device=x.device)
     ln_w, ln_b = (ln if ln is not None else (None, None))
+    _flops("dedf_node_linear", n * 2.0 * _irr_mac(irr_in, irr_out))
     _call("dedf_node_linear", ptr(x), n, L.int_array(irr_in), L.int_array(irr_out), ptr(W[0]), ptr(W[1]), ptr(W[2]),
                                     ptr(bias0), ptr(ln_w), ptr(ln_b), ln_eps, 1 if gate else 0, ptr(res), res_scale, ptr(y),
                                     stream())
@@ -477,6 +505,8 @@ def node_chain(x: torch.Tensor, irr_emb, irr_pre, P, pb, res1: Optional[torch.Te
     d.A0, d.A1, d.A2, d.ab = ptr(A[0]), ptr(A[1]), ptr(A[2]), ptr(ab)
     d.B0, d.B1, d.B2, d.bb = ptr(B[0]), ptr(B[1]), ptr(B[2]), ptr(bb)
     d.y = ptr(y)
+    mid = (irr_pre[0] - irr_pre[1] - irr_pre[2], irr_pre[1], irr_pre[2])
+    _flops("dedf_node_chain", x.shape[0] * 2.0 * (_irr_mac(irr_emb, irr_emb) + _irr_mac(irr_emb, irr_pre) + _irr_mac(mid, irr_emb)))
     _call("dedf_node_chain", C.byref(d), stream())
     return y
 
@@ -487,6 +517,7 @@ def node_linear_pair(xa: torch.Tensor, irr_in_a, Wa, ba, xb: torch.Tensor, irr_i
     ya = torch.empty(xa.shape[0], fo, dtype=torch.float32, device=xa.device)
     yb = torch.empty(xb.shape[0], fo, dtype=torch.float32, device=xb.device)
     arr = lambda W: (L.c_fp * 3)(ptr(W[0]), ptr(W[1]), ptr(W[2]))
+    _flops("dedf_node_linear_pair", 2.0 * (xa.shape[0] * _irr_mac(irr_in_a, irr_out) + xb.shape[0] * _irr_mac(irr_in_b, irr_out)))
     _call("dedf_node_linear_pair", ptr(xa), xa.shape[0], L.int_array(irr_in_a), arr(Wa), ptr(ba), ptr(ya),
           ptr(xb), xb.shape[0], L.int_array(irr_in_b), arr(Wb), ptr(bb), ptr(yb), L.int_array(irr_out), stream())
     return ya, yb
@@ -533,9 +564,13 @@ def score_tp(Ts, qf_rot, key_f, qx, qw, irr, Wd: List[torch.Tensor], Wl0, Wl1, b
     ang = torch.empty(n_t, 3, dtype=torch.float32, device=Ts.device)
     lin = torch.empty(n_t, 3, dtype=torch.float32, device=Ts.device)
     arr = lambda ts: (L.c_fp * 2)(ptr(ts[0]), ptr(ts[1]))
+    _flops("dedf_score_tp", n_t * qx.shape[0] * SCORE_TP_FLOPS_PER_ROW)
     _call("dedf_score_tp", ptr(Ts), n_t, ptr(qf_rot), ptr(key_f), ptr(qx), ptr(qw), qx.shape[0], L.int_array(irr),
                                  arr(Wd), arr(Wl0), arr(Wl1), arr(bl), n_vec, lin_mult, ptr(ang), ptr(lin), stream())
     return ang, lin
+
+
+SCORE_TP_FLOPS_PER_ROW = 2.0 * (151_296 + 44_256)      # two 'uvu' tensor products (sparse 3j) + their linear layers, per (pose, query point)
 
 
 def score_tp_step(Ts, qf, key_f, qx, qw, irr, Wd: List[torch.Tensor], Wl0, Wl1, bl, n_vec: int, lin_mult: float, state=None):
@@ -557,6 +592,7 @@ def score_tp_step(Ts, qf, key_f, qx, qw, irr, Wd: List[torch.Tensor], Wl0, Wl1, 
         d.seed, d.seed_dev = 0, ptr(state.seed, torch.int64)
         d.ang_mult, d.lin_mult_d = float(state.ang_mult), float(state.lin_mult)
         d.traj, d.T32, d.ticket = ptr(state.traj, torch.float64), ptr(Ts), ptr(state.ticket, torch.int32)
+    _flops("dedf_score_tp_step", n_t * qx.shape[0] * SCORE_TP_FLOPS_PER_ROW)
     _call("dedf_score_tp_step", C.byref(d), stream())
     return ang, lin
 
@@ -603,6 +639,8 @@ def value_reduce(mul1: int, g: Csr, v: torch.Tensor, sh: torch.Tensor, logits: t
                  V0: torch.Tensor, V1: torch.Tensor, V2: torch.Tensor, vb: Optional[torch.Tensor]) -> torch.Tensor:
     """out[d] = lin(sum_e softmax(logits)_e,h (x post_e) * dtp(v_e, sh_e, wv)) + bias * sum_e alpha  -> (n_dst, F)."""
     out = torch.empty(g.n_dst, v.shape[1], dtype=torch.float32, device=v.device)
+    fe, fd = _value_flops(mul1)
+    _flops("dedf_value_reduce", g.n_edges * fe + g.n_dst * fd)
     _call("dedf_value_reduce", mul1, ptr(g.row_ptr, torch.int32), g.n_dst, g.n_seg, ptr(v), ptr(sh), ptr(logits), ptr(post), ptr(wv),
           ptr(V0), ptr(V1), ptr(V2), ptr(vb), ptr(out), stream())
     return out

@@ -33,9 +33,8 @@ grasp = FeaturedPoints(torch.zeros(8, 3, device=dev), torch.zeros(8, 3, device=d
 kw = dict(diffusion_schedules=[[1.0, 0.15], [0.15, 0.09]], N_steps=[n_sub, n_sub], timesteps=[0.04, 0.04], temperatures=[1.0, 1.0],
           log_t_schedule=True, time_exponent_temp=1.0, time_exponent_alpha=0.5)
 with torch.no_grad():
-    # warm-up: a short loop (builds kernels' attributes, allocator pools)
-    parallel.sharded_sample(model, T_seed.to(dev), key if rank == 0 else None, grasp if rank == 0 else None, gather=False,
-                            **{**kw, "N_steps": [3, 3]})
+    # warm-up: the same call once (captures and caches the step graph, denoise.py) -- a server's first request
+    parallel.sharded_sample(model, T_seed.to(dev), key if rank == 0 else None, grasp if rank == 0 else None, gather=False, **kw)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

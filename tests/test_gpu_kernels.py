@@ -555,7 +555,7 @@ def test_pose_update_philox_steps_are_disjoint(cuda):
         for d in (1, 2, 3, 4, 8):
             if s + d < steps:
                 a, b = Z[s], Z[s + d]
-                same = (a[:, :, None] - b[:, None, :]).abs() < 1e-6
+                same = (a[:, :, None] - b[:, None, :]).abs() < 1e-10      # z is recovered to ~1e-13; chance coincidence ~1e-5
                 assert not same.any(), f"steps {s} and {s + d} share a normal draw"
     # standard normal, uncorrelated across steps and components
     flat = Z.permute(1, 0, 2).reshape(n, -1)             # (n, steps*6) samples of a 72-dim vector
