@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
 // tcgen05.commit frees ring stages and publishes the accumulator).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kTcM = 128;
-constexpr int kTcStages = 4;
+constexpr int kTcStages = 4;            // ring capacity in units of the widest stage (stage_bytes): ring bytes = kTcStages * stage_bytes
+constexpr int kTcMaxStages = 16;        // narrower layers cut the same ring into more, smaller stages (see the producer)
 constexpr int kTcEpiWG = 4;            // epilogue warpgroups: the 4 threads with the same (warp % 4, lane) share one edge row
 constexpr int kTcEpiThreads = kTcEpiWG * kTcM;          // 512
 constexpr int kTcProdWarp = kTcEpiThreads / 32;         // warp 16: weight producer (+ TMEM alloc)
@@ -123,6 +124,13 @@ struct MlpTcArgs {
 };
 
 __device__ __forceinline__ int tc_nblocks(int N) { return (N + 255) / 256; }
+// K chunks per ring stage: as many as fit in HALF the ring (two stages in flight at least), a divisor of the layer's chunk count
+__device__ __forceinline__ int tc_chunks_per_stage(uint32_t ring_bytes, uint32_t chunk_bytes, int nkc) {
+    int cps = (int)((ring_bytes / 2) / chunk_bytes);
+    cps = max(1, min(cps, nkc));
+    while (nkc % cps) --cps;
+    return cps;
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
     float* s_freq = s_tab + (size_t)(a.mode == DEDF_MLP_IN_FIELD ? a.n_scales : 1) * a.K[0] * 4;   // [K0/2] sinusoidal frequencies
     float* s_par = s_freq + ((a.K[0] / 2 + 3) & ~3);                               // hidden layer L: [b | ln_g | ln_b] x kTcMaxHidden
     float* s_last = s_par + (DEDF_MLP_MAX_LAYERS - 1) * 3 * kTcMaxHidden;          // last layer: bias + offset, [N_last]
-    __shared__ __align__(8) uint64_t full_bar[kTcStages], empty_bar[kTcStages], a_ready, acc_ready;
+    __shared__ __align__(8) uint64_t full_bar[kTcMaxStages], empty_bar[kTcMaxStages], a_ready, acc_ready, layer_done;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K0 = a.K[0];
@@ -144,7 +152,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
 
     // ---- one-time setup ----
     if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kTcMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&layer_done, 1);
         mbar_init(&a_ready, kTcEpiThreads);
         mbar_init(&acc_ready, 1);
         mbar_init_fence();
@@ -219,20 +228,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
     if (warp == kTcProdWarp) {
         // =========================== weight producer ===========================
         if (lane == 0) {
-            uint32_t st = 0, ph = 0;
+            // The ring (kTcStages * stage_bytes) is cut into stages of ONE K chunk of ONE N block of the CURRENT layer: a 128-wide
+            // layer gets 8 stages of 8 KB, a 64-wide one 16 of 4 KB, the 240-wide blocks of the last layer 4 of 15 KB.  A chunk's
+            // MMAs are bound by the round trip "MMAs done -> commit -> refill (L2, every CTA asks for the same lines at the same
+            // time) -> full": ~2400 cycles measured (profiles/r2_s1_mlp_tc_timeline_128.txt: 600 cycles per chunk at 4 stages, whatever
+            // the chunk's size), so the stage COUNT is what hides it.  Stage geometry changes at a layer boundary: the producer
+            // waits for the previous layer's last MMA (layer_done) before it writes with the new geometry; it still runs ahead of
+            // the issuer by the whole ring during the epilogue between two layers.
+            uint32_t st = 0, pmask = 0, pl = 0;            // pmask bit s: parity the next wait on empty_bar[s] uses
+            bool first_layer = true;
+            const uint32_t ring_bytes = (uint32_t)kTcStages * (uint32_t)a.stage_bytes;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 int e0, e1, scale; tile_range(tile, e0, e1, scale);
                 for (int L = 0; L < a.n_layers; ++L) {
                     const int K = a.K[L], N = a.K[L + 1];
                     const int NB = tc_nblocks(N), Nb = N / NB, nkc = K / 8;
-                    const uint32_t bytes = (uint32_t)Nb * 64u;
+                    const uint32_t cbytes = (uint32_t)Nb * 64u;                       // one K chunk of one N block (hi + lo)
+                    const int cps = tc_chunks_per_stage(ring_bytes, cbytes, nkc);      // K chunks per stage (divides nkc)
+                    const uint32_t bytes = cbytes * (uint32_t)cps;
+                    const uint32_t ns = min((uint32_t)kTcMaxStages, ring_bytes / bytes);
                     const float* Wl = a.Wp[L] + ((field && L == 0) ? (size_t)scale * 2 * K * N : 0);
                     TC_STAMP(kTcProdWarp * 32);
-                    for (int i = 0; i < NB * nkc; ++i) {
-                        tc::mbar_wait_bounded(&empty_bar[st], ph ^ 1u);
+                    if (!first_layer) { tc::mbar_wait_bounded(&layer_done, pl); pl ^= 1u; }
+                    first_layer = false;
+                    st = 0;
+                    for (int i = 0; i < NB * nkc; i += cps) {                          // (the chunks of a stage are contiguous in Wp)
+                        tc::mbar_wait_bounded(&empty_bar[st], ((pmask >> st) & 1u) ^ 1u);
+                        pmask ^= 1u << st;
                         mbar_expect_tx(&full_bar[st], bytes);
-                        bulk_g2s(sB + (size_t)st * a.stage_bytes, Wl + (size_t)i * Nb * 16, bytes, &full_bar[st]);
-                        if (++st == kTcStages) { st = 0; ph ^= 1u; }
+                        bulk_g2s_chunked(sB + (size_t)st * bytes, Wl + (size_t)i * Nb * 16, bytes, &full_bar[st]);
+                        if (++st == ns) st = 0;
                     }
                 }
             }
@@ -241,7 +266,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
     } else if (warp == kTcMmaWarp) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
-            uint32_t st = 0, ph = 0, pa = 0;
+            uint32_t st = 0, cmask = 0, pa = 0;            // cmask bit s: parity the next wait on full_bar[s] uses
+            const uint32_t ring_bytes = (uint32_t)kTcStages * (uint32_t)a.stage_bytes;
             const uint32_t a_hi0 = smem_u32(sA_hi), a_lo0 = smem_u32(sA_lo), b0 = smem_u32(sB);
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int L = 0; L < a.n_layers; ++L) {
@@ -252,24 +278,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                     tc::mbar_wait_bounded(&a_ready, pa); pa ^= 1u;      // A operand written, accumulator drained
                     tc::fence_after();
                     TC_STAMP(kTcMmaWarp * 32);
+                    const uint64_t da_hi_l = tc::smem_desc(a_hi0, kTcM * 16, 128), da_lo_l = tc::smem_desc(a_lo0, kTcM * 16, 128);
+                    constexpr uint64_t kAStep = (2u * kTcM * 16u) >> 4;          // address-field increment per K chunk
+                    const uint32_t cbytes = (uint32_t)Nb * 64u;
+                    const int cps = tc_chunks_per_stage(ring_bytes, cbytes, nkc);
+                    const uint32_t sbytes = cbytes * (uint32_t)cps;
+                    const uint32_t ns = min((uint32_t)kTcMaxStages, ring_bytes / sbytes);     // this layer's stage count (see the producer)
+                    st = 0;
                     for (int nb = 0; nb < NB; ++nb) {
-                        for (int kc = 0; kc < nkc; ++kc) {
-                            tc::mbar_wait_bounded(&full_bar[st], ph);
+                        const uint32_t d = tmem_base + (uint32_t)(nb * Nb);
+                        uint64_t da_hi = da_hi_l, da_lo = da_lo_l;
+                        for (int kc = 0; kc < nkc; kc += cps) {
+                            // one wait, one fence and one commit per STAGE of cps chunks (3 cps MMAs): their fixed cost is what a
+                            // one-chunk stage spent most of its ~600 cycles on
+                            tc::mbar_wait_bounded(&full_bar[st], (cmask >> st) & 1u);
+                            cmask ^= 1u << st;
                             tc::fence_after();
-                            const uint32_t koff = (uint32_t)kc * 2u * kTcM * 16u;
-                            const uint64_t da_hi = tc::smem_desc(a_hi0 + koff, kTcM * 16, 128);
-                            const uint64_t da_lo = tc::smem_desc(a_lo0 + koff, kTcM * 16, 128);
-                            const uint32_t bs = b0 + st * (uint32_t)a.stage_bytes;
-                            const uint64_t db_hi = tc::smem_desc(bs, (uint32_t)Nb * 16, 128);
-                            const uint64_t db_lo = tc::smem_desc(bs + (uint32_t)Nb * 32, (uint32_t)Nb * 16, 128);
-                            const uint32_t d = tmem_base + (uint32_t)(nb * Nb);
-                            tc::mma_tf32(d, da_hi, db_hi, idesc, kc > 0);
-                            tc::mma_tf32(d, da_lo, db_hi, idesc, 1);
-                            tc::mma_tf32(d, da_hi, db_lo, idesc, 1);
+                            uint32_t bs = b0 + st * sbytes;
+                            for (int c = 0; c < cps; ++c) {
+                                const uint64_t db_hi = tc::smem_desc(bs, (uint32_t)Nb * 16, 128);
+                                const uint64_t db_lo = tc::smem_desc(bs + (uint32_t)Nb * 32, (uint32_t)Nb * 16, 128);
+                                tc::mma_tf32(d, da_hi, db_hi, idesc, (kc + c) > 0);
+                                tc::mma_tf32(d, da_lo, db_hi, idesc, 1);
+                                tc::mma_tf32(d, da_hi, db_lo, idesc, 1);
+                                da_hi += kAStep; da_lo += kAStep;
+                                bs += cbytes;
+                            }
                             tc::commit(&empty_bar[st]);                // stage reusable once these MMAs have read it
-                            if (++st == kTcStages) { st = 0; ph ^= 1u; }
+                            if (++st == ns) st = 0;
                         }
                     }
+                    tc::commit(&layer_done);                           // the producer may re-cut the ring for the next layer
                     tc::commit(&acc_ready);
                     TC_STAMP(kTcMmaWarp * 32);
                 }

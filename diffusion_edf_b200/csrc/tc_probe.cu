@@ -1,0 +1,87 @@
+// Micro-benchmark of tcgen05.mma throughput for the operand forms the per-edge kernels use (not part of the public header:
+// a debug hook like dedf_tc_set_debug).  One CTA issues `reps` MMAs of shape M = 128 x N x (K = 8 tf32 | 16 bf16) back to back
+// into one accumulator, with the A operand either in shared memory (descriptor, the no-swizzle chunk-major layout of tc.cuh)
+// or in tensor memory, and reports the cycles from the first issue to the completion of the last one.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace dedf {
+
+__global__ void __launch_bounds__(128, 1) tc_probe_kernel(int kind, int N, int reps, int a_tmem, int n_ksteps, int n_acc, int commit_every, long long* out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar, bar2;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned char* sA = smem_raw;                                   // [n_ksteps][2][128][16 B]
+    unsigned char* sB = sA + (size_t)n_ksteps * 2 * 128 * 16;       // [n_ksteps][2][N][16 B]
+    for (int i = tid; i < (n_ksteps * 2 * (128 + N) * 16) / 4; i += 128) reinterpret_cast<float*>(smem_raw)[i] = 0.f;
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1 << 20); mbar_init_fence(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+    tc::fence_async_smem();
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        // instruction descriptor: D = F32; A/B format 2 = TF32, 1 = BF16; K-major both; N >> 3; M >> 4
+        const uint32_t fmt = kind == 0 ? 2u : 1u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        // descriptors of the 8 K steps precomputed; the issue loop is unrolled and does nothing else (the MLP kernel's loop costs
+        // ~200 cycles of scalar instructions per MMA, which would hide what the tensor pipe itself needs)
+        uint64_t da[8], db[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            da[ks] = tc::smem_desc(a0 + (ks % n_ksteps) * 2 * 128 * 16, 128 * 16, 128);
+            db[ks] = tc::smem_desc(b0 + (ks % n_ksteps) * 2 * N * 16, (uint32_t)N * 16, 128);
+        }
+        const uint32_t step = (n_acc > 1) ? (uint32_t)N : 0u;
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; r += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                // commit_every = c > 0: a tcgen05.commit (to a barrier nobody waits on) after every c MMAs, like the per-chunk
+                // "stage free" commits of the MLP kernel's ring
+                if (commit_every > 0 && u > 0 && (u % commit_every) == 0) tc::commit(&bar2);
+                const uint32_t dacc = tmem_base + (uint32_t)(u % 4 < n_acc ? u % 4 : 0) * step;
+                const uint32_t accf = (uint32_t)(r > 0 || u >= 4);
+                if (a_tmem) {
+                    const uint32_t ta = tmem_base + 448 + u * 8;
+                    if (kind == 0)
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+                                     ::"r"(dacc), "r"(ta), "l"(db[u]), "r"(idesc), "r"(accf) : "memory");
+                    else
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+                                     ::"r"(dacc), "r"(ta), "l"(db[u]), "r"(idesc), "r"(accf) : "memory");
+                } else {
+                    if (kind == 0)
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(dacc), "l"(da[u]), "l"(db[u]), "r"(idesc), "r"(accf) : "memory");
+                    else
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(dacc), "l"(da[u]), "l"(db[u]), "r"(idesc), "r"(accf) : "memory");
+                }
+            }
+        }
+        const long long t1 = clock64();
+        tc::commit(&bar);
+        tc::mbar_wait_bounded(&bar, 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace dedf
+
+/* debug hook: out[0] = cycles to ISSUE `reps` MMAs, out[1] = cycles until the last one has completed */
+extern "C" int dedf_tc_probe(int kind, int N, int reps, int a_tmem, int n_ksteps, int n_acc, int commit_every, long long* out, cudaStream_t stream) {
+    if (!out || N < 16 || N > 256 || (N % 16) || reps < 1 || n_ksteps < 1 || n_acc < 1 || (n_acc > 4 ? 4 : n_acc) * N > 448 || (reps % 8)) return DEDF_ERR_ARG;
+    const size_t smem = (size_t)n_ksteps * 2 * (128 + N) * 16;
+    if (smem > 200 * 1024) return DEDF_ERR_UNSUPPORTED;
+    cudaFuncSetAttribute(dedf::tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    dedf::tc_probe_kernel<<<1, 128, smem, stream>>>(kind, N, reps, a_tmem, n_ksteps, n_acc, commit_every, out);
+    return cudaGetLastError() == cudaSuccess ? DEDF_OK : DEDF_ERR_LAUNCH;
+}
