@@ -35,7 +35,7 @@ from diffusion_edf.gnn_data import FeaturedPoints as RefFP          # noqa: E402
 from diffusion_edf.multiscale_score_model import MultiscaleScoreModel as RefModel    # noqa: E402
 from diffusion_edf.point_attentive_score_model import PointAttentiveScoreModel as RefPointAttentive    # noqa: E402
 
-from tests.golden.model_cases import KINDS, SAMPLE_KW, feature_rows, inputs, seeded_oracle, spec, weight_checksums    # noqa: E402
+from tests.golden.model_cases import KINDS, NO_LOSS, SAMPLE_KW, feature_rows, inputs, seeded_oracle, spec, weight_checksums    # noqa: E402
 
 def run(kind, out):
     kwargs, cls, has_scores, has_sample = spec(kind)
@@ -62,12 +62,14 @@ def run(kind, out):
         if has_scores:
             ang, lin = ref.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=t)
             out[f"{kind}/ang"], out[f"{kind}/lin"] = ang.numpy(), lin.numpy()
-            g = torch.Generator().manual_seed(11)
-            ta, tl = torch.randn(len(Ts), 3, generator=g), torch.randn(len(Ts), 3, generator=g)
-            loss, _, _, stats = ref.get_train_loss(Ts, t, key, grasp, ta, tl)
-            out[f"{kind}/target_ang"], out[f"{kind}/target_lin"] = ta.numpy(), tl.numpy()
-            out[f"{kind}/loss"] = np.array([float(loss)] + [float(stats[k]) for k in sorted(stats)], dtype=np.float64)
-            msg = f"ang {ang.abs().max().item():.4f} loss {float(loss):.4f}"
+            msg = f"ang {ang.abs().max().item():.4f}"
+            if kind not in NO_LOSS:
+                g = torch.Generator().manual_seed(11)
+                ta, tl = torch.randn(len(Ts), 3, generator=g), torch.randn(len(Ts), 3, generator=g)
+                loss, _, _, stats = ref.get_train_loss(Ts, t, key, grasp, ta, tl)
+                out[f"{kind}/target_ang"], out[f"{kind}/target_lin"] = ta.numpy(), tl.numpy()
+                out[f"{kind}/loss"] = np.array([float(loss)] + [float(stats[k]) for k in sorted(stats)], dtype=np.float64)
+                msg += f" loss {float(loss):.4f}"
         else:
             e = ref.score_head.compute_energy(Ts, key_ms, q, t)
             out[f"{kind}/energy"] = e.numpy()

@@ -16,13 +16,16 @@ def weight_checksums(sd):
     return np.array([len(keys), tot] + probe, dtype=np.float64)
 
 
-KINDS = ("pick", "place", "highres", "sapien_highres", "sapien_lowres", "ebm")
+KINDS = ("pick", "place", "highres", "sapien_highres", "sapien_lowres", "ebm", "pick_c2", "pick_1024")
+NO_LOSS = ("pick_1024",)        # cases without the get_train_loss record (1024 poses through the reference's source on the CPU: forward only)
 # kind -> (kwargs function of diffusion_edf_b200.synthetic, model class name, has scores, has sample)
 _SPEC = {"pick": ("model_kwargs", "MultiscaleScoreModel", True, True), "place": ("model_kwargs_place", "MultiscaleScoreModel", True, True),
          "highres": ("model_kwargs_highres", "MultiscaleScoreModel", True, False),
          "sapien_highres": ("model_kwargs_sapien_highres", "MultiscaleScoreModel", True, False),
          "sapien_lowres": ("model_kwargs_sapien_lowres", "PointAttentiveScoreModel", True, False),
-         "ebm": ("model_kwargs_ebm", "MultiscaleScoreModel", False, False)}
+         "ebm": ("model_kwargs_ebm", "MultiscaleScoreModel", False, False),
+         # full-size cases on bench.py's scene: BASELINE config C2 (10k points, 128 poses) and the north-star width (1024 poses)
+         "pick_c2": ("model_kwargs", "MultiscaleScoreModel", True, False), "pick_1024": ("model_kwargs", "MultiscaleScoreModel", True, False)}
 
 
 def spec(kind):
@@ -36,6 +39,10 @@ def inputs(kind):
     if kind == "pick":
         x, rgb = make_scene(1500, seed=3, half_extent=12.0)
         Ts, t = make_poses(6, x, seed=3, spread=6.0)
+        gx, gf = torch.zeros(8, 3), torch.zeros(8, 3)
+    elif kind in ("pick_c2", "pick_1024"):
+        x, rgb = make_scene(10_000, seed=0)
+        Ts, t = make_poses(128 if kind == "pick_c2" else 1024, x, seed=0)
         gx, gf = torch.zeros(8, 3), torch.zeros(8, 3)
     elif kind == "place":
         x, rgb = make_scene(1200, seed=5, half_extent=10.0)

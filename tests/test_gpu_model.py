@@ -85,8 +85,8 @@ def test_score_head_fake_input(cuda):
     with torch.no_grad():
         ang_o, lin_o = oracle.score_head(Ts, keys, query, time)
         ang, lin = model.score_head(Ts.to(cuda), [_fp(FeaturedPoints, k, cuda) for k in keys], _fp(FeaturedPoints, query, cuda), time.to(cuda))
-    assert_close(ang, ang_o, 2e-4, "ang score")
-    assert_close(lin, lin_o, 2e-4, "lin score")
+    assert_close(ang, ang_o, TOL, "ang score")
+    assert_close(lin, lin_o, TOL, "lin score")
 
 
 def test_score_head_zero_edges_and_single_pose(cuda):
@@ -104,8 +104,8 @@ def test_score_head_zero_edges_and_single_pose(cuda):
         ang_o, lin_o = oracle.score_head(Ts, keys, query, time)
         ang, lin = model.score_head(Ts.to(cuda), [_fp(FeaturedPoints, k, cuda) for k in keys],
                                     FeaturedPoints(*[None if v is None else v.detach().to(cuda) for v in query]), time.to(cuda))
-    assert_close(ang, ang_o, 2e-4, "ang")
-    assert_close(lin, lin_o, 2e-4, "lin")
+    assert_close(ang, ang_o, TOL, "ang")
+    assert_close(lin, lin_o, TOL, "lin")
 
 
 def test_full_model_forward(cuda):
@@ -126,7 +126,7 @@ def test_full_model_forward(cuda):
     # the encoder picks the same points (bit-exact fps / radius) and matches feature-wise
     for s, (po, pg) in enumerate(zip(dbg_o[0], dbg[0])):
         assert torch.equal(po.x, pg.x.cpu()), f"scale {s}: pooled coordinates differ"
-        assert_close(pg.f, po.f, 5e-4, f"key features scale {s}")
+        assert_close(pg.f, po.f, TOL, f"key features scale {s}")
     budget = max(TOL, 3 * max(rel_err(ang32, ang64), rel_err(lin32, lin64)))
     assert_close(ang, ang64, budget, "ang vs fp64 oracle")
     assert_close(lin, lin64, budget, "lin vs fp64 oracle")
@@ -154,8 +154,8 @@ def test_sample_matches_oracle(cuda):
             assert got.shape == ref.shape == (14, 6, 7) and got.dtype == torch.float64
             assert torch.equal(got[-1], got[-2])                                    # last pose appended twice (score_model_base.py:199-201)
             assert (got[1:, :, :4].norm(dim=-1) - 1).abs().max() < 1e-9     # row 0 is the (fp32-normalised) seed itself
-            err = (got.cpu() - ref).abs().max().item()
-            assert err < 2e-3, f"trajectory deviates by {err:.3e} (temps {temps})"
+            # poses: unit quaternions and centimetres; relative to the trajectory's largest entry (12 chained steps of an fp32 network)
+            assert_close(got, ref, 2 * TOL, f"trajectory (temps {temps})")
 
 
 def test_train_loss_forward_value(cuda):
@@ -203,7 +203,10 @@ def test_equivariance_full_size(cuda):
     assert [len(p.x) for p in dbg[0]] == [2000, 400, 80, 16]
     assert torch.isfinite(a1).all() and torch.isfinite(l1).all()
     # FPS ties / radius boundaries can flip under the rigid motion's round-off, so allow a looser bound than per-kernel parity
-    assert rel_err(a2, a1) < 5e-3 and rel_err(l2, l1) < 5e-3, (rel_err(a2, a1), rel_err(l2, l1))
+    # (this is a statement about the MODEL's equivariance in fp32, evaluated on two different point sets; it is not a parity bound)
+    from tests.util import _log
+    _log("equivariance ang", rel_err(a2, a1), 0.0, 1e-3); _log("equivariance lin", rel_err(l2, l1), 0.0, 1e-3)
+    assert rel_err(a2, a1) < 1e-3 and rel_err(l2, l1) < 1e-3, (rel_err(a2, a1), rel_err(l2, l1))
 
 
 def test_identity_pose_deviation(cuda):
@@ -343,9 +346,9 @@ def test_full_size_head_vs_unfused_torch_on_gpu(cuda):
             pytest.skip(f"oracle does not run on the GPU: {err}")
     for s, (po, pg) in enumerate(zip(key_o, key_g)):
         assert torch.equal(po.x, pg.x), f"scale {s}: pooled coordinates differ"
-        assert_close(pg.f, po.f, 1e-3, f"key features scale {s}")
-    assert_close(ang, ang_o, 1e-3, "ang, 1024 poses")
-    assert_close(lin, lin_o, 1e-3, "lin, 1024 poses")
+        assert_close(pg.f, po.f, TOL, f"key features scale {s}")
+    assert_close(ang, ang_o, TOL, "ang, 1024 poses")
+    assert_close(lin, lin_o, TOL, "lin, 1024 poses")
     res = {"workload": "score head, 10k-point scene, 1024 poses, 1xB200", "unfused_torch_gpu_ms": ms_ref, "this_repo_ms": ms_ours,
            "speedup": ms_ref / ms_ours, "pose_scores_per_s_unfused": 1024 / ms_ref * 1e3, "pose_scores_per_s_this_repo": 1024 / ms_ours * 1e3,
            "rel_err_ang": rel_err(ang, ang_o), "rel_err_lin": rel_err(lin, lin_o)}
@@ -378,10 +381,10 @@ def test_place_model_with_keypoint_extractor(cuda):
                                 FeaturedPoints(gx.to(cuda), grgb.to(cuda), gb.to(cuda)), debug=True)
         qo, qg = dbg_o[1], dbg[1]
         assert torch.equal(qo.x, qg.x.cpu()) and len(qo.x) > 10
-        assert_close(qg.f, qo.f, 5e-4, "query features")
-        assert_close(qg.w, qo.w, 5e-4, "query weights")
-        assert_close(ang, ang_o, 1e-3, "ang")
-        assert_close(lin, lin_o, 1e-3, "lin")
+        assert_close(qg.f, qo.f, TOL, "query features")
+        assert_close(qg.w, qo.w, TOL, "query weights")
+        assert_close(ang, ang_o, TOL, "ang")
+        assert_close(lin, lin_o, TOL, "lin")
         # the place query model has data-dependent shapes (bbox filter): forward() must stay eager, sample() still graph-replays
         model(Ts.to(cuda), t.to(cuda), FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)), FeaturedPoints(gx.to(cuda), grgb.to(cuda), gb.to(cuda)))
         assert len(model._graphs) == 0
@@ -390,7 +393,7 @@ def test_place_model_with_keypoint_extractor(cuda):
         tr_g = model.sample(Ts.to(cuda), keys, qg, **kw)
         keys_o = oracle.get_key_pcd_multiscale(OM.FeaturedPoints(x, rgb, b))
         tr_o = oracle.sample(Ts, keys_o, qo, noise=torch.zeros(4, 5, 6, dtype=torch.float64), **kw)
-        assert (tr_g.cpu() - tr_o).abs().max() < 2e-3
+        assert_close(tr_g, tr_o, 2 * TOL, "place-config trajectory")
 
 
 def test_ebm_critic_energy(cuda):
@@ -418,7 +421,7 @@ def test_ebm_critic_energy(cuda):
         q = model.get_query_pcd(_fp(FeaturedPoints, grasp, cuda))
         e = model.score_head.compute_energy(Ts.to(cuda), keys, q, t.to(cuda))
     assert e.shape == (12,)
-    assert_close(e, e_o, 2e-4, "energy")
+    assert_close(e, e_o, TOL, "energy")
     # what the agent actually uses is the ranking: in the oracle's order the CUDA energies must be sorted too (up to the
     # tolerance: poses without neighbours have near-identical energies)
     es = e.cpu()[e_o.argsort()]
@@ -446,8 +449,8 @@ def test_highres_config_forward(cuda):
         (ang_o, lin_o), _ = oracle(Ts, t, OM.FeaturedPoints(x, rgb, b), grasp)
         for _ in range(2):          # eager record pass, then the CUDA-graph replay
             (ang, lin), _ = model(Ts.to(cuda), t.to(cuda), FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)), _fp(FeaturedPoints, grasp, cuda))
-            assert_close(ang, ang_o, 5e-4, "ang")
-            assert_close(lin, lin_o, 5e-4, "lin")
+            assert_close(ang, ang_o, TOL, "ang")
+            assert_close(lin, lin_o, TOL, "lin")
 
 
 def test_sapien_highres_forward_only_encoder(cuda):
@@ -470,11 +473,11 @@ def test_sapien_highres_forward_only_encoder(cuda):
         (ang_o, lin_o), dbg_o = oracle(Ts, t, OM.FeaturedPoints(x, rgb, b), grasp, debug=True)
         for _ in range(2):
             (ang, lin), _ = model(Ts.to(cuda), t.to(cuda), FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)), _fp(FeaturedPoints, grasp, cuda))
-            assert_close(ang, ang_o, 5e-4, "ang")
-            assert_close(lin, lin_o, 5e-4, "lin")
+            assert_close(ang, ang_o, TOL, "ang")
+            assert_close(lin, lin_o, TOL, "lin")
         keys = model.get_key_pcd_multiscale(FeaturedPoints(x.to(cuda), rgb.to(cuda), b.to(cuda)))
         assert len(keys) == 1 and torch.equal(keys[0].x.cpu(), dbg_o[0][0].x)
-        assert_close(keys[0].f, dbg_o[0][0].f, 2e-4, "key features")
+        assert_close(keys[0].f, dbg_o[0][0].f, TOL, "key features")
 
 
 def test_point_attentive_score_model(cuda):
@@ -498,9 +501,9 @@ def test_point_attentive_score_model(cuda):
         (ang_o, lin_o), dbg_o = oracle(Ts, t, OM.FeaturedPoints(x, rgb, b), grasp, debug=True)
         (ang, lin), dbg = model(Ts.to(cuda), t.to(cuda), key_d, _fp(FeaturedPoints, grasp, cuda), debug=True)
         assert len(dbg[0]) == 1 and torch.equal(dbg[0][0].x.cpu(), dbg_o[0][0].x) and len(dbg_o[0][0].x) >= 50
-        assert_close(dbg[0][0].w, dbg_o[0][0].w, 5e-4, "key point weights")
-        assert_close(ang, ang_o, 1e-3, "ang")
-        assert_close(lin, lin_o, 1e-3, "lin")
+        assert_close(dbg[0][0].w, dbg_o[0][0].w, TOL, "key point weights")
+        assert_close(ang, ang_o, TOL, "ang")
+        assert_close(lin, lin_o, TOL, "lin")
     # training path
     g = torch.Generator().manual_seed(2)
     ta, tl = torch.randn(5, 3, generator=g), torch.randn(5, 3, generator=g)
