@@ -318,7 +318,7 @@ extern "C" int dedf_node_chain(const dedf_node_chain_desc* d, cudaStream_t strea
     // round of work items instead of two -- the launch is latency, not throughput.  Otherwise 16-node tiles when the three
     // weight sets and the tiles fit, 8-node tiles for the wide irreps.
     int rc = DEDF_ERR_UNSUPPORTED;
-    if (d->n <= 4 * kNumSMs && !getenv("DEDF_CHAIN_NO_TN4")) rc = launch_chain<4>(a, stream);
+    if (d->n <= 2 * kNumSMs && !getenv("DEDF_CHAIN_NO_TN4")) rc = launch_chain<4>(a, stream);
     if (rc == DEDF_ERR_UNSUPPORTED) rc = launch_chain<16>(a, stream);
     if (rc == DEDF_ERR_UNSUPPORTED) rc = launch_chain<8>(a, stream);
     return rc;

@@ -155,7 +155,7 @@ def test_sample_matches_oracle(cuda):
             assert torch.equal(got[-1], got[-2])                                    # last pose appended twice (score_model_base.py:199-201)
             assert (got[1:, :, :4].norm(dim=-1) - 1).abs().max() < 1e-9     # row 0 is the (fp32-normalised) seed itself
             # poses: unit quaternions and centimetres; relative to the trajectory's largest entry (12 chained steps of an fp32 network)
-            assert_close(got, ref, 2 * TOL, f"trajectory (temps {temps})")
+            assert_close(got, ref, TOL, f"trajectory (temps {temps})")
 
 
 def test_train_loss_forward_value(cuda):
@@ -393,7 +393,7 @@ def test_place_model_with_keypoint_extractor(cuda):
         tr_g = model.sample(Ts.to(cuda), keys, qg, **kw)
         keys_o = oracle.get_key_pcd_multiscale(OM.FeaturedPoints(x, rgb, b))
         tr_o = oracle.sample(Ts, keys_o, qo, noise=torch.zeros(4, 5, 6, dtype=torch.float64), **kw)
-        assert_close(tr_g, tr_o, 2 * TOL, "place-config trajectory")
+        assert_close(tr_g, tr_o, TOL, "place-config trajectory")
 
 
 def test_ebm_critic_energy(cuda):
