@@ -74,7 +74,76 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(int kind, int N, int r
     if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
+__device__ __forceinline__ uint32_t probe_elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .pred px;\nelect.sync _|px, 0xffffffff;\nselp.u32 %0, 1, 0, px;\n}" : "=r"(pred));
+    return pred;
+}
+
+// The MLP kernel's issue loop in isolation: 16 K chunks x 3 MMAs (hi.hi, lo.hi, hi.lo) + one commit per `cps` chunks, operands
+// resident in shared memory.  mode 0: one thread runs the loop (if lane == 0, as the round-1 kernels do); mode 1: the whole warp
+// runs the loop and an elected lane issues (addresses stay warp-uniform: no per-MMA R2UR traffic).
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) tc_probe_loop_kernel(int N, int nkc, int cps, int reps, long long* out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar, bar2;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (2 * 128 * 128 * 4 + 2 * 8 * N * 32) / 4; i += 128) reinterpret_cast<float*>(smem_raw)[i] = 0.f;
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1 << 20); mbar_init_fence(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+    tc::fence_async_smem();
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (warp == 1 && (MODE >= 1 || lane == 0)) {
+        const uint32_t idesc = tc::idesc_tf32(128, N);
+        const uint32_t a_hi0 = smem_u32(smem_raw), a_lo0 = a_hi0 + 128 * 128 * 4, b0 = a_lo0 + 128 * 128 * 4;
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            uint64_t da_hi = tc::smem_desc(a_hi0, 128 * 16, 128), da_lo = tc::smem_desc(a_lo0, 128 * 16, 128);
+            for (int kc = 0; kc < nkc; ++kc) {
+                const uint32_t bs = b0 + (uint32_t)(kc & 7) * (uint32_t)N * 64u;
+                const uint64_t db_hi = tc::smem_desc(bs, (uint32_t)N * 16, 128), db_lo = tc::smem_desc(bs + (uint32_t)N * 32, (uint32_t)N * 16, 128);
+                if (MODE == 0 || probe_elect_one()) {
+                    // MODE 2: the three terms of the split go to three accumulators (no MMA depends on the previous one)
+                    const uint32_t d1 = MODE == 2 ? tmem_base + (uint32_t)N : tmem_base, d2 = MODE == 2 ? tmem_base + 2u * (uint32_t)N : tmem_base;
+                    tc::mma_tf32(tmem_base, da_hi, db_hi, idesc, (r | kc) > 0);
+                    tc::mma_tf32(d1, da_lo, db_hi, idesc, MODE == 2 ? (uint32_t)((r | kc) > 0) : 1u);
+                    tc::mma_tf32(d2, da_hi, db_lo, idesc, MODE == 2 ? (uint32_t)((r | kc) > 0) : 1u);
+                    if ((kc + 1) % cps == 0) tc::commit(&bar2);
+                }
+                if (MODE >= 1) __syncwarp();
+                da_hi += (2u * 128 * 16u) >> 4; da_lo += (2u * 128 * 16u) >> 4;
+            }
+        }
+        const long long t1 = clock64();
+        if (MODE == 0 || probe_elect_one()) {
+            tc::commit(&bar);
+            tc::mbar_wait_bounded(&bar, 0);
+            out[0] = t1 - t0; out[1] = clock64() - t0;
+        }
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace dedf
+
+extern "C" int dedf_tc_probe_loop(int mode, int N, int nkc, int cps, int reps, long long* out, cudaStream_t stream) {
+    if (!out || N < 16 || N > 256 || (N % 16) || nkc < 1 || nkc > 16 || cps < 1 || reps < 1) return DEDF_ERR_ARG;
+    const size_t smem = (size_t)2 * 128 * 128 * 4 + (size_t)2 * 8 * N * 32;
+    if (smem > 220 * 1024) return DEDF_ERR_UNSUPPORTED;
+    cudaFuncSetAttribute(dedf::tc_probe_loop_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(dedf::tc_probe_loop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(dedf::tc_probe_loop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (mode == 0) dedf::tc_probe_loop_kernel<0><<<1, 128, smem, stream>>>(N, nkc, cps, reps, out);
+    else if (mode == 1) dedf::tc_probe_loop_kernel<1><<<1, 128, smem, stream>>>(N, nkc, cps, reps, out);
+    else dedf::tc_probe_loop_kernel<2><<<1, 128, smem, stream>>>(N, nkc, cps, reps, out);
+    return cudaGetLastError() == cudaSuccess ? DEDF_OK : DEDF_ERR_LAUNCH;
+}
 
 /* debug hook: out[0] = cycles to ISSUE `reps` MMAs, out[1] = cycles until the last one has completed */
 extern "C" int dedf_tc_probe(int kind, int N, int reps, int a_tmem, int n_ksteps, int n_acc, int commit_every, long long* out, cudaStream_t stream) {
