@@ -151,6 +151,12 @@ _PROTOS = {
     "dedf_edge_gather_scalar": [c_fp, c_fp, c_fp, c_int, c_fp, c_fp],
     "dedf_rowdot": [c_fp, c_fp, c_int, c_int, c_fp, c_fp],
     "dedf_value_reduce": [c_int, c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp],
+    "dedf_dtp_bwd_sh": [c_int, c_fp, c_fp, c_ll, c_fp, c_int, c_fp, c_fp],
+    "dedf_rbf_bwd_len": [c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_f, c_f, c_int, c_fp, c_fp, c_fp],
+    "dedf_sinusoid_bwd": [c_fp, c_int, c_int, c_fp, c_f, c_fp, c_fp, c_fp],
+    "dedf_edge_geom_bwd": [c_fp, c_fp, c_fp, c_fp, c_int, c_int, C.POINTER(c_int), C.POINTER(c_f), c_f, c_f, c_fp, c_fp, c_fp, c_fp, c_fp],
+    "dedf_ebm_energy_bwd": [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_f, c_fp, c_fp, c_fp],
+    "dedf_ebm_pose_grad": [c_fp, c_int, c_int, C.POINTER(c_int), c_fp, c_fp, c_fp, c_fp, c_f, c_f, c_fp, c_fp, c_fp],
     "dedf_build_arch": [],
 }
 

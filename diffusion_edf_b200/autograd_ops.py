@@ -57,6 +57,8 @@ class LinearFn(Function):
         if ctx.needs_input_grad[0]:
             WsT = [w.t().contiguous() if w is not None else None for w in _split(w_flat.detach(), irr_in, irr_out)]
             dx = ops.node_linear(gy, irr_out, irr_in, WsT, None)
+        if not (ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])):
+            return dx, None, None, None, None          # frozen parameters (EbmScoreModelHead.forward in inference mode)
         dW = torch.zeros_like(w_flat)
         db = torch.zeros(irr_out[0], dtype=torch.float32, device=x.device) if ctx.has_bias else None
         dWs = _split(dW, irr_in, irr_out)
@@ -163,7 +165,12 @@ class DtpFn(Function):
         dw = torch.zeros_like(w) if ctx.shared else torch.empty_like(w)
         ops._call("dedf_dtp_bwd", ctx.mul1, ptr(x), ptr(sh), ptr(w.detach()), 0 if ctx.shared else w.shape[1], ptr(g), x.shape[0],
                   ptr(dx), ptr(dw), stream())
-        return dx, None, dw, None
+        dsh = None
+        if ctx.needs_input_grad[1]:        # position gradients (EbmScoreModelHead.forward): the harmonics depend on the query coordinates
+            dsh = torch.empty_like(sh)
+            ops._call("dedf_dtp_bwd_sh", ctx.mul1, ptr(x), ptr(w.detach()), 0 if ctx.shared else w.shape[1], ptr(g), x.shape[0],
+                      ptr(dsh), stream())
+        return dx, dsh, dw, None
 
 
 class GatherFn(Function):
@@ -227,7 +234,13 @@ class AlphaFn(Function):
         dad = torch.zeros(ma, dtype=torch.float32, device=pre.device)
         ops._call("dedf_alpha_bwd", ptr(pre), E, ma, ptr(alpha_dot.detach().reshape(-1).contiguous()), ptr(g.contiguous()),
                   ptr(dpre), ptr(dad), stream())
-        return dpre, dad.view_as(alpha_dot), None
+        dlogit = None
+        if ctx.needs_input_grad[2]:        # logits[e, h] = ... + edge_logit[e]
+            g = g.contiguous()
+            dlogit = torch.empty(E, dtype=torch.float32, device=pre.device)
+            ones = torch.ones_like(g)
+            ops._call("dedf_rowdot", ptr(g), ptr(ones), E, g.shape[1], ptr(dlogit), stream())
+        return dpre, dad.view_as(alpha_dot), dlogit
 
 
 class SoftmaxReduceFn(Function):
@@ -271,7 +284,12 @@ class RbfFn(Function):
         d = [torch.zeros(K, dtype=torch.float32, device=length.device) for _ in range(3)]
         ops._call("dedf_rbf_bwd", ptr(length), length.shape[0], K, ptr(p[0]), ptr(p[1]), ptr(p[2]), *ctx.cfg, ptr(g.contiguous()),
                   ptr(d[0]), ptr(d[1]), ptr(d[2]), stream())
-        return None, d[0].view_as(mean), d[1].view_as(std_logit), d[2].view_as(weight_logit), None, None, None
+        dlen = None
+        if ctx.needs_input_grad[0]:
+            dlen = torch.empty_like(length)
+            ops._call("dedf_rbf_bwd_len", ptr(length), length.shape[0], K, ptr(p[0]), ptr(p[1]), ptr(p[2]), *ctx.cfg, ptr(g.contiguous()),
+                      ptr(dlen), stream())
+        return dlen, d[0].view_as(mean), d[1].view_as(std_logit), d[2].view_as(weight_logit), None, None, None
 
 
 def sinusoid(x: torch.Tensor, freq: torch.Tensor, dim: int, scale: float) -> torch.Tensor:
@@ -280,6 +298,74 @@ def sinusoid(x: torch.Tensor, freq: torch.Tensor, dim: int, scale: float) -> tor
     out = torch.empty(x.shape[0], dim, dtype=torch.float32, device=x.device)
     ops._call("dedf_sinusoid", ptr(x), x.shape[0], dim, ptr(freq), scale, ptr(out), stream())
     return out
+
+
+class SinusoidFn(Function):
+    """SinusoidalPositionEmbeddings of a quantity that carries a gradient (the edge lengths of the all-pairs scale on the
+    EbmScoreModelHead.forward path)."""
+
+    @staticmethod
+    def forward(ctx, x, freq, dim: int, scale: float):
+        x = x.contiguous()
+        out = torch.empty(x.shape[0], dim, dtype=torch.float32, device=x.device)
+        ops._call("dedf_sinusoid", ptr(x), x.shape[0], dim, ptr(freq), scale, ptr(out), stream())
+        ctx.save_for_backward(x, freq)
+        ctx.cfg = (dim, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, freq = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        ops._call("dedf_sinusoid_bwd", ptr(x), x.shape[0], ctx.cfg[0], ptr(freq), ctx.cfg[1], ptr(g.contiguous()), ptr(dx), stream())
+        return dx, None, None, None
+
+
+class EdgeGeomFn(Function):
+    """graph_parser.py:146-224 with a gradient w.r.t. the DESTINATION (query) coordinates: x_dst -> (length (E), harmonics (E, 9),
+    edge logit (E)).  The sources (the encoded scene) are constants on the EbmScoreModelHead.forward path."""
+
+    @staticmethod
+    def forward(ctx, x_dst, x_src, g: ops.Csr, radii, src_off, ns_cut):
+        x_dst, x_src = x_dst.contiguous(), x_src.contiguous()
+        length, sh, logit = ops.edge_geom(x_src, x_dst, g, radii=radii, src_off=src_off, ns_cut=ns_cut, want_logit=True)
+        E = g.n_edges
+        ctx.save_for_backward(x_dst, x_src)
+        ctx.cfg = (g, list(radii), list(src_off), tuple(ns_cut))
+        return length[:E].clone(), sh[:E].clone(), logit[:E].clone()
+
+    @staticmethod
+    def backward(ctx, g_len, g_sh, g_logit):
+        x_dst, x_src = ctx.saved_tensors
+        g, radii, src_off, ns_cut = ctx.cfg
+        E = g.n_edges
+        dx = torch.zeros_like(x_dst)
+        z = lambda t, shape: (t.contiguous() if t is not None else torch.zeros(shape, dtype=torch.float32, device=x_dst.device))   # noqa: E731
+        g_len, g_sh, g_logit = z(g_len, (E,)), z(g_sh, (E, 9)), z(g_logit, (E,))
+        ops._call("dedf_edge_geom_bwd", ptr(x_src), ptr(x_dst), ptr(g.edge_src, torch.int32), ptr(g.edge_dst, torch.int32), E,
+                  len(radii), L.int_array(src_off), L.float_array([-1.0 if r is None else float(r) for r in radii]),
+                  float(ns_cut[0]), float(ns_cut[1]), ptr(g_len), ptr(g_sh), ptr(g_logit), ptr(dx), stream())
+        return dx, None, None, None, None, None
+
+
+class EbmEnergyFn(Function):
+    """energy[t] = scale sum_q w_q |key_f[t, q] - query_f[t, q]|^2 (score_head_ebm.py:171-172) with gradients to both features."""
+
+    @staticmethod
+    def forward(ctx, key_f, query_f, qw, n_t: int, n_q: int, scale: float):
+        key_f, query_f, qw = key_f.contiguous(), query_f.contiguous(), qw.contiguous()
+        ctx.save_for_backward(key_f, query_f, qw)
+        ctx.cfg = (n_t, n_q, scale)
+        return ops.ebm_energy(key_f, query_f, qw, n_t, n_q, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        key_f, query_f, qw = ctx.saved_tensors
+        n_t, n_q, scale = ctx.cfg
+        dk, dq = torch.empty_like(key_f), torch.empty_like(query_f)
+        ops._call("dedf_ebm_energy_bwd", ptr(key_f), ptr(query_f), ptr(qw), ptr(g.contiguous()), n_t, n_q, key_f.shape[1], scale,
+                  ptr(dk), ptr(dq), stream())
+        return dk, dq, None, None, None, None
 
 
 class ScoreTpFn(Function):

@@ -479,6 +479,244 @@ __global__ void sinusoid_kernel(const float* __restrict__ x, int n, int dim, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// position gradients (EbmScoreModelHead.forward, score_head_ebm.py:192-222: score = d(-energy)/d(pose)).  The reference gets
+// them from torch autograd through graph_parser._encode_edges; here every adjoint is its own kernel:
+//   dtp_bwd_sh        adjoint of the depthwise tensor product w.r.t. the harmonics          (one warp per edge)
+//   rbf_bwd_len       adjoint of the Gaussian radial bases w.r.t. the edge length
+//   sinusoid_bwd      adjoint of the sinusoidal length embedding w.r.t. the edge length
+//   edge_geom_bwd     (d length, d harmonics, d edge logit) -> d x_dst                      (graph_parser.py:146-224)
+//   ebm_energy_bwd    adjoint of the energy tail w.r.t. the field and the rotated query features
+//   ebm_pose_grad     (d x', d f') -> body-frame angular / linear score of every pose
+// ---------------------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256) dtp_bwd_sh_kernel(const float* __restrict__ x, const float* __restrict__ w, long long w_stride,
+                                                        const float* __restrict__ g, int E, float* __restrict__ dsh) {
+    using D = Dtp<G>;
+    constexpr int NCH = D::M0 + D::M1 + D::M2, B1 = D::D0, B2 = D::D0 + 3 * D::D1;
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < E; e += n_warps) {
+        const float* xe = x + (size_t)e * D::F;
+        const float* we = w + (size_t)e * w_stride;
+        const float* go = g + (size_t)e * D::FOUT;
+        float d[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) d[j] = 0.f;
+        for (int c = lane; c < NCH; c += 32) {
+            if (c < D::M0) {
+                const int ch = c;
+                const float xv = xe[ch];
+                d[0] = fmaf(xv * we[D::W_K0 + ch], go[D::C0_K0 + ch], d[0]);
+                const float a1 = xv * we[D::W_K1 + ch], a2 = xv * we[D::W_K2 + ch];
+                for (int k = 0; k < 3; ++k) d[1 + k] = fmaf(a1, go[B1 + (D::C1_K1 + ch) * 3 + k], d[1 + k]);
+                for (int k = 0; k < 5; ++k) d[4 + k] = fmaf(a2, go[B2 + (D::C2_K2 + ch) * 5 + k], d[4 + k]);
+            } else if (c < D::M0 + D::M1) {
+                const int ch = c - D::M0;
+                float xv[3], wv[6], a[5];
+                for (int k = 0; k < 3; ++k) xv[k] = xe[D::M0 + 3 * ch + k];
+                for (int k = 0; k < 6; ++k) wv[k] = we[D::W_K3 + ch + k * D::M1];
+                const float* g3 = go + B1 + (D::C1_K3 + ch) * 3; const float g4 = go[D::C0_K4 + ch];
+                const float* g5 = go + B1 + (D::C1_K5 + ch) * 3; const float* g6 = go + B2 + (D::C2_K6 + ch) * 5;
+                const float* g7 = go + B1 + (D::C1_K7 + ch) * 3; const float* g8 = go + B2 + (D::C2_K8 + ch) * 5;
+                d[0] = fmaf(wv[0], xv[0] * g3[0] + xv[1] * g3[1] + xv[2] * g3[2], d[0]);
+                cg_110_dy(xv, &g4, a); for (int k = 0; k < 3; ++k) d[1 + k] = fmaf(wv[1], a[k], d[1 + k]);
+                cg_111_dy(xv, g5, a);  for (int k = 0; k < 3; ++k) d[1 + k] = fmaf(wv[2], a[k], d[1 + k]);
+                cg_112_dy(xv, g6, a);  for (int k = 0; k < 3; ++k) d[1 + k] = fmaf(wv[3], a[k], d[1 + k]);
+                cg_121_dy(xv, g7, a);  for (int k = 0; k < 5; ++k) d[4 + k] = fmaf(wv[4], a[k], d[4 + k]);
+                cg_122_dy(xv, g8, a);  for (int k = 0; k < 5; ++k) d[4 + k] = fmaf(wv[5], a[k], d[4 + k]);
+            } else {
+                const int ch = c - D::M0 - D::M1;
+                float xv[5], wv[6], a[5];
+                for (int k = 0; k < 5; ++k) xv[k] = xe[D::M0 + 3 * D::M1 + 5 * ch + k];
+                for (int k = 0; k < 6; ++k) wv[k] = we[D::W_K9 + ch + k * D::M2];
+                const float* g9 = go + B2 + (D::C2_K9 + ch) * 5; const float* g10 = go + B1 + (D::C1_K10 + ch) * 3;
+                const float* g11 = go + B2 + (D::C2_K11 + ch) * 5; const float g12 = go[D::C0_K12 + ch];
+                const float* g13 = go + B1 + (D::C1_K13 + ch) * 3; const float* g14 = go + B2 + (D::C2_K14 + ch) * 5;
+                float dot = 0.f;
+                for (int k = 0; k < 5; ++k) dot = fmaf(xv[k], g9[k], dot);
+                d[0] = fmaf(wv[0], dot, d[0]);
+                cg_211_dy(xv, g10, a);  for (int k = 0; k < 3; ++k) d[1 + k] = fmaf(wv[1], a[k], d[1 + k]);
+                cg_212_dy(xv, g11, a);  for (int k = 0; k < 3; ++k) d[1 + k] = fmaf(wv[2], a[k], d[1 + k]);
+                cg_220_dy(xv, &g12, a); for (int k = 0; k < 5; ++k) d[4 + k] = fmaf(wv[3], a[k], d[4 + k]);
+                cg_221_dy(xv, g13, a);  for (int k = 0; k < 5; ++k) d[4 + k] = fmaf(wv[4], a[k], d[4 + k]);
+                cg_222_dy(xv, g14, a);  for (int k = 0; k < 5; ++k) d[4 + k] = fmaf(wv[5], a[k], d[4 + k]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j) d[j] = warp_sum(d[j]);
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) dsh[(size_t)e * 9 + j] = d[j];
+        }
+    }
+}
+
+__device__ __forceinline__ float dsoft_step3(float x) { return (x <= 0.0f || x >= 1.0f) ? 0.0f : 12.0f * x * x * (1.0f - x); }
+
+// dlen[e] = sum_k g[e, k] d out[e, k] / d len[e]
+__global__ void rbf_bwd_len_kernel(const float* __restrict__ len, int E, int K, const float* __restrict__ mean, const float* __restrict__ sl,
+                                   const float* __restrict__ wl, float offset, float inv_span, int mode, const float* __restrict__ g,
+                                   float* __restrict__ dlen) {
+    const float amp = 4.0f * sqrtf((float)K);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const float d = (len[e] - offset) * inv_span;
+        const float cut = mode ? rbf_cut(d) : 1.0f;
+        // rbf_cut(d) = 1 - soft_step3((0.2 - d) / 0.2) for d <= 0.5  ->  d cut / d d = soft_step3'((0.2 - d) / 0.2) / 0.2
+        const float dcut = (mode && d <= 0.5f) ? dsoft_step3(((1.0f - d) - 0.8f) / (1.0f - 0.8f)) / (1.0f - 0.8f) : 0.0f;
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float sd = softplus_(sl[k]) + 1e-5f;
+            const float z = (d - mean[k]) / sd;
+            const float base = expf(-0.5f * z * z) * sigmoidf_(wl[k]) * amp;
+            acc = fmaf(g[(size_t)e * K + k], base * (dcut - cut * z / sd), acc);
+        }
+        dlen[e] = acc * inv_span;
+    }
+}
+
+__global__ void sinusoid_bwd_kernel(const float* __restrict__ x, int n, int dim, const float* __restrict__ freq, float scale,
+                                    const float* __restrict__ g, float* __restrict__ dx) {
+    const int half = dim / 2;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int k = 0; k < half; ++k) {
+            const float arg = __fmul_rn(x[r] * scale, freq[k]);
+            float sn, cs; sincosf(arg, &sn, &cs);
+            acc = fmaf(scale * freq[k], g[(size_t)r * dim + k] * cs - g[(size_t)r * dim + half + k] * sn, acc);
+        }
+        dx[r] = acc;
+    }
+}
+
+struct GeomBwdArgs {
+    const float* x_src; const float* x_dst;
+    const int* edge_src; const int* edge_dst;
+    int n_edges;
+    const float* g_len; const float* g_sh; const float* g_logit;     // g_logit may be null
+    float* dx_dst;                                                    // (n_dst, 3), accumulated
+    float ns_lo, ns_hi;
+    int n_scales;
+    int src_off[DEDF_MAX_SCALES + 1];
+    float r[DEDF_MAX_SCALES];
+};
+
+__global__ void __launch_bounds__(256) edge_geom_bwd_kernel(GeomBwdArgs a) {
+    const float s3 = 1.7320508075688772f, s5 = 2.23606797749979f, s15 = 3.872983346207417f;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < a.n_edges; e += gridDim.x * blockDim.x) {
+        const int s = a.edge_src[e], d = a.edge_dst[e];
+        const float vx = a.x_src[3 * s] - a.x_dst[3 * d], vy = a.x_src[3 * s + 1] - a.x_dst[3 * d + 1], vz = a.x_src[3 * s + 2] - a.x_dst[3 * d + 2];
+        const float len = sqrtf(vx * vx + vy * vy + vz * vz);
+        const float inv = 1.0f / fmaxf(len, 1e-12f);
+        const float x = vx * inv, y = vy * inv, z = vz * inv;
+        const float* gs = a.g_sh + (size_t)e * 9;
+        float c = 1.0f, dc = 0.0f;
+        if (a.ns_hi > 0.f) {
+            const float t = (len - a.ns_lo) / (a.ns_hi - a.ns_lo);
+            c = soft_step3(t); dc = dsoft_step3(t) / (a.ns_hi - a.ns_lo);
+        }
+        // un-cut harmonics (for the derivative of the cut) and their gradient w.r.t. the unit vector
+        float Y[9]; sph_harm_l2(x, y, z, Y);
+        float g_len = a.g_len[e];
+        if (dc != 0.0f) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 1; j < 9; ++j) acc = fmaf(gs[j], Y[j], acc);
+            g_len = fmaf(acc, dc, g_len);
+        }
+        if (a.g_logit) {
+            int sc = 0;
+            while (sc + 1 < a.n_scales && s >= a.src_off[sc + 1]) ++sc;
+            const float r = a.r[sc];
+            if (r >= 0.f) {
+                const float r8 = 0.8f * r, t = (len - r8) / (r - r8);
+                const float cut = 1.0f - soft_step3(t);
+                if (cut > 1e-12f) g_len = fmaf(a.g_logit[e], -dsoft_step3(t) / ((r - r8) * cut), g_len);
+            }
+        }
+        float gx = c * (s3 * gs[1] + s15 * (z * gs[4] + y * gs[5]) - s5 * x * gs[6] - s15 * x * gs[8]);
+        float gy = c * (s3 * gs[2] + s15 * (x * gs[5] + z * gs[7]) + 2.0f * s5 * y * gs[6]);
+        float gz = c * (s3 * gs[3] + s15 * (x * gs[4] + y * gs[7]) - s5 * z * gs[6] + s15 * z * gs[8]);
+        const float gu = gx * x + gy * y + gz * z;
+        gx = (gx - gu * x) * inv + g_len * x;      // d/d vec = (I - u u^T) / len . g_u + g_len u
+        gy = (gy - gu * y) * inv + g_len * y;
+        gz = (gz - gu * z) * inv + g_len * z;
+        atomicAdd(a.dx_dst + 3 * d, -gx); atomicAdd(a.dx_dst + 3 * d + 1, -gy); atomicAdd(a.dx_dst + 3 * d + 2, -gz);    // vec = x_src - x_dst
+    }
+}
+
+__global__ void ebm_energy_bwd_kernel(const float* __restrict__ key_f, const float* __restrict__ query_f, const float* __restrict__ qw,
+                                      const float* __restrict__ g_energy, int n_t, int n_q, int F, float scale,
+                                      float* __restrict__ dkey, float* __restrict__ dquery) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n_t * n_q * F; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / F;
+        const int t = (int)(row / n_q), q = (int)(row % n_q);
+        const float v = 2.0f * scale * qw[q] * g_energy[t] * (key_f[i] - query_f[i]);
+        dkey[i] = v; dquery[i] = -v;
+    }
+}
+
+// one CTA per pose:  lin = lin_mult R^T sum_q g_x ;  ang = ang_mult sum_q [ x_q x (R^T g_x) + sum_u f_u x (R^T g_u) (l = 1)
+//                                                                          + sum_u (X_a f_u) . (D2^T g_u) (l = 2) ]
+// g_x (n_t n_q, 3), g_f (n_t n_q, F): gradients of log P w.r.t. the transformed coordinates / rotated features
+__global__ void __launch_bounds__(128) ebm_pose_grad_kernel(const float* __restrict__ Ts, int n_t, int n_q, Irr irr, const float* __restrict__ qx,
+                                                           const float* __restrict__ qf, const float* __restrict__ g_x,
+                                                           const float* __restrict__ g_f, float ang_mult, float lin_mult,
+                                                           float* __restrict__ ang, float* __restrict__ lin) {
+    __shared__ float sR[9], sD2[25], red[4][6];
+    const int t = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        const float* T = Ts + (size_t)t * 7;
+        const float nrm = sqrtf(T[0] * T[0] + T[1] * T[1] + T[2] * T[2] + T[3] * T[3]);
+        float qn[4] = {T[0] / nrm, T[1] / nrm, T[2] / nrm, T[3] / nrm};
+        float R[9]; quat_to_matrix<float>(qn, R);
+        for (int i = 0; i < 9; ++i) sR[i] = R[i];
+        float D[25]; wigner_d2_from_R(R, D);
+        for (int i = 0; i < 25; ++i) sD2[i] = D[i];
+    }
+    __syncthreads();
+    const int F = irr.dim();
+    const int per_q = 1 + irr.m1 + irr.m2;         // items of a query point: its coordinates, every l = 1 / l = 2 channel
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // ang xyz | lin xyz (world frame sums; rotated at the end)
+    for (int i = tid; i < n_q * per_q; i += blockDim.x) {
+        const int q = i / per_q, it = i % per_q;
+        const size_t row = (size_t)t * n_q + q;
+        if (it == 0 || it <= irr.m1) {
+            const float* gv = (it == 0) ? g_x + row * 3 : g_f + row * F + irr.m0 + 3 * (it - 1);
+            const float* v = (it == 0) ? qx + (size_t)q * 3 : qf + (size_t)q * F + irr.m0 + 3 * (it - 1);
+            float b[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) b[m] = sR[0 * 3 + m] * gv[0] + sR[1 * 3 + m] * gv[1] + sR[2 * 3 + m] * gv[2];       // R^T g
+            acc[0] += v[1] * b[2] - v[2] * b[1]; acc[1] += v[2] * b[0] - v[0] * b[2]; acc[2] += v[0] * b[1] - v[1] * b[0];
+            if (it == 0) { acc[3] += b[0]; acc[4] += b[1]; acc[5] += b[2]; }
+        } else {
+            const int u = it - 1 - irr.m1;
+            const float* gv = g_f + row * F + irr.off2() + 5 * u;
+            const float* v = qf + (size_t)q * F + irr.off2() + 5 * u;
+            float b[5];
+#pragma unroll
+            for (int m = 0; m < 5; ++m) { float s = 0.f; for (int j = 0; j < 5; ++j) s = fmaf(sD2[j * 5 + m], gv[j], s); b[m] = s; }   // D2^T g
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float s = 0.f;
+#pragma unroll
+                for (int i2 = 0; i2 < 5; ++i2)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) if (kGenL2[a][i2][j] != 0.0f) s = fmaf(kGenL2[a][i2][j] * v[j], b[i2], s);
+                acc[a] += s;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
+    if ((tid & 31) == 0) for (int k = 0; k < 6; ++k) red[tid >> 5][k] = acc[k];
+    __syncthreads();
+    if (tid < 3) {
+        ang[(size_t)t * 3 + tid] = ang_mult * (red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid]);
+        lin[(size_t)t * 3 + tid] = lin_mult * (red[0][3 + tid] + red[1][3 + tid] + red[2][3 + tid] + red[3][3 + tid]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // score tensor product ('uvu', shared weights, mul2 > 1, l_out <= 1), un-fused
 //   paths:  0: 0x0->0 | 1: 0x1->1 | 2: 1x0->1 | 3: 1x1->0 | 4: 1x1->1 | 5: 1x2->1 | 6: 2x1->1 | 7: 2x2->0 | 8: 2x2->1
 //   out: [lo0: p0 (M0) | p3 (M1) | p7 (M2)] then [lo1: (p1 M0 | p2 M1 | p4 M1 | p5 M1 | p6 M2 | p8 M2) x 3]
@@ -975,6 +1213,73 @@ extern "C" int dedf_rowdot(const float* a, const float* b, int n, int F, float* 
     if (!a || !b || !out || F <= 0) return DEDF_ERR_ARG;
     if (n <= 0) return DEDF_OK;
     rowdot_kernel<<<grid_for(n, 8, kNumSMs * 8), 256, 0, stream>>>(a, b, n, F, out);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_dtp_bwd_sh(int mul1, const float* x, const float* w, long long w_stride, const float* g, int n_edges, float* dsh,
+                               cudaStream_t stream) {
+    if (n_edges <= 0) return DEDF_OK;
+    if (!x || !w || !g || !dsh) return DEDF_ERR_ARG;
+    const int grid = grid_for((long long)n_edges * 32, 256, kNumSMs * 8);
+    if (mul1 == 32) dtp_bwd_sh_kernel<32><<<grid, 256, 0, stream>>>(x, w, w_stride, g, n_edges, dsh);
+    else if (mul1 == 16) dtp_bwd_sh_kernel<16><<<grid, 256, 0, stream>>>(x, w, w_stride, g, n_edges, dsh);
+    else return DEDF_ERR_UNSUPPORTED;
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_rbf_bwd_len(const float* len, int n_edges, int k, const float* mean, const float* std_logit, const float* weight_logit,
+                                float offset, float inv_span, int mode, const float* g, float* dlen, cudaStream_t stream) {
+    if (n_edges <= 0) return DEDF_OK;
+    if (!len || !mean || !std_logit || !weight_logit || !g || !dlen || k <= 0) return DEDF_ERR_ARG;
+    rbf_bwd_len_kernel<<<grid_for(n_edges, 128, kNumSMs * 8), 128, 0, stream>>>(len, n_edges, k, mean, std_logit, weight_logit, offset,
+                                                                                 inv_span, mode, g, dlen);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_sinusoid_bwd(const float* x, int n, int dim, const float* freq, float scale, const float* g, float* dx,
+                                 cudaStream_t stream) {
+    if (n <= 0) return DEDF_OK;
+    if (!x || !freq || !g || !dx || dim < 2 || (dim & 1)) return DEDF_ERR_ARG;
+    sinusoid_bwd_kernel<<<grid_for(n, 128, kNumSMs * 8), 128, 0, stream>>>(x, n, dim, freq, scale, g, dx);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_edge_geom_bwd(const float* x_src, const float* x_dst, const int* edge_src, const int* edge_dst, int n_edges,
+                                  int n_scales, const int* src_off, const float* r, float ns_lo, float ns_hi, const float* g_len,
+                                  const float* g_sh, const float* g_logit, float* dx_dst, cudaStream_t stream) {
+    if (n_edges <= 0) return DEDF_OK;
+    if (!x_src || !x_dst || !edge_src || !edge_dst || !g_len || !g_sh || !dx_dst) return DEDF_ERR_ARG;
+    if (n_scales < 1 || n_scales > DEDF_MAX_SCALES) return DEDF_ERR_ARG;
+    if (g_logit && (!src_off || !r)) return DEDF_ERR_ARG;
+    GeomBwdArgs a{};
+    a.x_src = x_src; a.x_dst = x_dst; a.edge_src = edge_src; a.edge_dst = edge_dst; a.n_edges = n_edges;
+    a.g_len = g_len; a.g_sh = g_sh; a.g_logit = g_logit; a.dx_dst = dx_dst; a.ns_lo = ns_lo; a.ns_hi = ns_hi; a.n_scales = n_scales;
+    for (int s = 0; s < n_scales; ++s) { a.src_off[s] = src_off ? src_off[s] : 0; a.r[s] = r ? r[s] : -1.f; }
+    a.src_off[n_scales] = src_off ? src_off[n_scales] : 0x7fffffff;
+    edge_geom_bwd_kernel<<<grid_for(n_edges, 256, kNumSMs * 8), 256, 0, stream>>>(a);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_ebm_energy_bwd(const float* key_f, const float* query_f, const float* qw, const float* g_energy, int n_t, int n_q,
+                                   int F, float scale, float* dkey, float* dquery, cudaStream_t stream) {
+    if (n_t <= 0 || n_q <= 0) return DEDF_OK;
+    if (!key_f || !query_f || !qw || !g_energy || !dkey || !dquery || F <= 0) return DEDF_ERR_ARG;
+    ebm_energy_bwd_kernel<<<grid_for((long long)n_t * n_q * F, 256, kNumSMs * 8), 256, 0, stream>>>(key_f, query_f, qw, g_energy, n_t, n_q,
+                                                                                                     F, scale, dkey, dquery);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_ebm_pose_grad(const float* Ts, int n_t, int n_q, const int* irr, const float* qx, const float* qf, const float* g_x,
+                                  const float* g_f, float ang_mult, float lin_mult, float* ang, float* lin, cudaStream_t stream) {
+    if (n_t <= 0) return DEDF_OK;
+    if (!Ts || !irr || !qx || !qf || !g_x || !g_f || !ang || !lin) return DEDF_ERR_ARG;
+    ebm_pose_grad_kernel<<<n_t, 128, 0, stream>>>(Ts, n_t, n_q, Irr{irr[0], irr[1], irr[2]}, qx, qf, g_x, g_f, ang_mult, lin_mult, ang, lin);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

@@ -1,8 +1,9 @@
 """EbmScoreModelHead (critic) on the CUDA path.  Mirrors /root/reference/diffusion_edf/score_head_ebm.py:32-222: same
 constructor kwargs and parameter names.  ``compute_energy`` -- what agent.py:163-174 calls under no_grad to re-rank the
 sampled poses -- runs on the kernels of the tensor field plus one energy kernel.  ``forward`` (the score as the gradient
-of the energy w.r.t. the pose, :192-222) needs the derivative of the field w.r.t. the query coordinates and, for training,
-a double backward; neither is built: it raises."""
+of -energy w.r.t. the pose, :192-222) runs the differentiable (un-fused) field kernels of train_path.py with the adjoints
+w.r.t. the query coordinates (csrc/train.cu "position gradients") in inference mode; in train mode (create_graph=True: a
+double backward) it raises."""
 from __future__ import annotations
 
 from typing import Dict, List
@@ -82,5 +83,14 @@ class EbmScoreModelHead(nn.Module):
         return self
 
     def forward(self, Ts, key_pcd_multiscale, query_pcd, time):
-        raise NotImplementedError("EbmScoreModelHead.forward (score = gradient of the energy w.r.t. the pose, score_head_ebm.py:192-222) "
-                                  "is not built on the CUDA path; the critic use (compute_energy, agent.py:163-174) is")
+        """(ang_vel (nT, 3), lin_vel (nT, 3)) = pose gradient of log P = -energy in the body frame (score_head_ebm.py:192-222).
+        Inference mode only (after ``.eval()``: ``create_graph=False`` in the reference); training the energy-based head
+        through its score needs a double backward, which is not built."""
+        assert Ts.ndim == 2 and Ts.shape[-1] == 7, f"{Ts.shape}"
+        assert time.ndim == 1 and len(time) == len(Ts), f"{time.shape}"
+        assert query_pcd.f.ndim == 2 and query_pcd.f.shape[-1] == self.query_edf_dim, f"{query_pcd.f.shape}"
+        if not self.inference_mode:
+            raise NotImplementedError("EbmScoreModelHead.forward in train mode (create_graph=True: a double backward through the "
+                                      "field) is not built; call .eval() first")
+        from . import train_path
+        return train_path.ebm_score(self, Ts, key_pcd_multiscale, query_pcd)

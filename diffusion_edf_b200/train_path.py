@@ -188,8 +188,10 @@ def unet_forward(net, pcd: FeaturedPoints) -> List[FeaturedPoints]:
 
 # ------------------------------------------------------------------------------------------------ tensor field + head
 def tensor_field(field, query_x: torch.Tensor, query_b: torch.Tensor, keys: List[FeaturedPoints],
-                 time_emb: Optional[List[torch.Tensor]], rows_per_time: int) -> torch.Tensor:
-    """MultiscaleTensorField.forward (multiscale_tensor_field.py:192-260) -> (n_query, F)."""
+                 time_emb: Optional[List[torch.Tensor]], rows_per_time: int, pos_grad: bool = False) -> torch.Tensor:
+    """MultiscaleTensorField.forward (multiscale_tensor_field.py:192-260) -> (n_query, F).  ``pos_grad``: the edge geometry
+    carries a gradient back to ``query_x`` (EbmScoreModelHead.forward); the graph itself (which edges exist) is piecewise
+    constant in the coordinates, as in the reference (torch_cluster.radius returns indices)."""
     x_src = torch.cat([p.x for p in keys], dim=0).contiguous()
     f_src = torch.cat([p.f for p in keys], dim=0)
     w_src = torch.cat([p.w for p in keys], dim=0) if field.gnn_block_init.use_src_point_attn else None
@@ -201,8 +203,13 @@ def tensor_field(field, query_x: torch.Tensor, query_b: torch.Tensor, keys: List
     xq = query_x.contiguous()
     g = ops.radius_csr(x_src, xq, radii, src_off=off, b_src=b_src, b_dst=query_b.contiguous(), max_num_neighbors=1000)
     ns = field.r_mincut_nonscalar_sh
-    length, sh, logit = ops.edge_geom(x_src, xq, g, radii=radii, src_off=off, ns_cut=(0.2 * ns, 1.0 * ns), want_logit=True)
     E = g.n_edges
+    if pos_grad:
+        if E == 0:
+            raise NotImplementedError("position gradient with an empty query graph")
+        length, sh, logit = A.EdgeGeomFn.apply(query_x, x_src, g, radii, off, (0.2 * ns, 1.0 * ns))
+    else:
+        length, sh, logit = ops.edge_geom(x_src, xq, g, radii=radii, src_off=off, ns_cut=(0.2 * ns, 1.0 * ns), want_logit=True)
     bounds = g.row_ptr[::g.n_dst][: field.n_scales + 1].tolist()        # edge range of every scale (one host read)
     if field._sin_freq is None or field._sin_freq.device != xq.device:
         half = field.length_emb_dim // 2
@@ -216,6 +223,8 @@ def tensor_field(field, query_x: torch.Tensor, query_b: torch.Tensor, keys: List
         if gp.r is not None:
             pm = gp.length_enc.param_module
             emb = A.RbfFn.apply(ln, pm.mean, pm.std_logit, pm.weight_logit, 0.0, 1.0 / gp.r, 0)
+        elif pos_grad:
+            emb = A.SinusoidFn.apply(ln, field._sin_freq, field.length_emb_dim, 1000.0 / float(field.length_enc_max_r))
         else:
             emb = A.sinusoid(ln, field._sin_freq, field.length_emb_dim, 1000.0 / float(field.length_enc_max_r))
         if time_emb is not None:
@@ -277,3 +286,30 @@ def keypoint_extractor(mod, input_points: FeaturedPoints) -> FeaturedPoints:
     h = A.SiluFn.apply(A.LayerNormFn.apply(wf, ln.weight, ln.bias, (ln.normalized_shape[0], 0, 0), ln.eps))
     w = A.SigmoidFn.apply(nn_linear(lin, h)).reshape(-1)
     return FeaturedPoints(x=q.x, f=f, b=q.b, w=w)
+
+
+# ------------------------------------------------------------------------------------------------ energy-based head
+def ebm_score(head, Ts: torch.Tensor, keys: List[FeaturedPoints], query: FeaturedPoints):
+    """EbmScoreModelHead.forward (score_head_ebm.py:192-222), first order (the reference's inference mode): the gradient of
+    log P = -energy w.r.t. the transformed query coordinates x' = R x + p and the rotated query features f' = D(R) f comes from
+    the adjoint kernels (autograd only orders them); the pull-back to the pose -- what the reference obtains by differentiating
+    through quaternion_to_matrix / the Euler-angle Wigner matrices and contracting with L(q) -- is closed form in
+    dedf_ebm_pose_grad:  ang_a = sum_q [x_q x R^T g_x + sum_u f_u x R^T g_u + sum_u (X_a f_u) . D2^T g_u],  lin = R^T sum_q g_x."""
+    Ts = Ts.detach().to(torch.float32).contiguous()
+    nT, nQ = len(Ts), len(query.x)
+    irr = head.irreps_query_edf.m
+    qx, qf = query.x.detach().contiguous(), query.f.detach().contiguous()
+    with torch.enable_grad():
+        xq, fq = ops.query_transform(Ts, qx, qf, irr)
+        xq, fq = xq.requires_grad_(True), fq.requires_grad_(True)
+        bq = query.b.unsqueeze(0).expand(nT, -1).reshape(-1).contiguous()
+        key_f = tensor_field(head.key_tensor_field, xq, bq, [FeaturedPoints(x=p.x.detach(), f=p.f.detach(), b=p.b, w=None if p.w is None else p.w.detach()) for p in keys],
+                             None, nQ, pos_grad=True)
+        energy = A.EbmEnergyFn.apply(key_f, fq, query.w.detach().contiguous(), nT, nQ, head.energy_rescale_factor)
+        g_x, g_f = torch.autograd.grad(-energy.sum(), (xq, fq))
+    ang = torch.empty(nT, 3, dtype=torch.float32, device=Ts.device)
+    lin = torch.empty(nT, 3, dtype=torch.float32, device=Ts.device)
+    g_x, g_f = g_x.contiguous(), g_f.contiguous()
+    ops._call("dedf_ebm_pose_grad", A.ptr(Ts), nT, nQ, A.L.int_array(irr), A.ptr(qx), A.ptr(qf), A.ptr(g_x), A.ptr(g_f),
+              float(head.ang_mult), float(head.lin_mult), A.ptr(ang), A.ptr(lin), A.stream())
+    return ang, lin

@@ -410,6 +410,29 @@ int dedf_group_scale(const float* x, const float* mask, int n, const int* irr_ho
 int dedf_edge_gather_scalar(const float* w, const int* edge_src, const int* n_edges_dev, int max_edges, float* out, cudaStream_t stream);
 int dedf_rowdot(const float* a, const float* b, int n, int F, float* out, cudaStream_t stream);
 
+/* ---- position gradients: EbmScoreModelHead.forward (score_head_ebm.py:192-222) ----------------------------------------------
+ * The reference's score of the energy-based head is torch.autograd.grad(-energy, T) through the tensor field; the adjoints of
+ * the pieces that depend on the query coordinates (graph_parser.py:146-224 edge geometry, the length embeddings, the harmonics
+ * operand of the depthwise tensor products) and the pull-back to the body frame are kernels of their own:
+ *   dedf_dtp_bwd_sh     dsh (E, 9) of dedf_dtp_fwd
+ *   dedf_rbf_bwd_len    dlen (E) of dedf_rbf_fwd;  dedf_sinusoid_bwd: dx (n) of dedf_sinusoid
+ *   dedf_edge_geom_bwd  (g_len, g_sh, g_logit [may be NULL]) of dedf_edge_geom -> dx_dst (n_dst, 3), ACCUMULATED (zero it first)
+ *   dedf_ebm_energy_bwd dkey / dquery (n_t n_q, F) of dedf_ebm_energy given g_energy (n_t)
+ *   dedf_ebm_pose_grad  g_x (n_t n_q, 3), g_f (n_t n_q, F) = d logP / d(transformed coordinates, rotated features) ->
+ *                       ang (n_t, 3) = ang_mult * right-trivialised rotational derivative, lin (n_t, 3) = lin_mult R^-1 d/dp */
+int dedf_dtp_bwd_sh(int mul1, const float* x, const float* w, long long w_stride, const float* g, int n_edges, float* dsh,
+                    cudaStream_t stream);
+int dedf_rbf_bwd_len(const float* len, int n_edges, int k, const float* mean, const float* std_logit, const float* weight_logit,
+                     float offset, float inv_span, int mode, const float* g, float* dlen, cudaStream_t stream);
+int dedf_sinusoid_bwd(const float* x, int n, int dim, const float* freq, float scale, const float* g, float* dx, cudaStream_t stream);
+int dedf_edge_geom_bwd(const float* x_src, const float* x_dst, const int* edge_src, const int* edge_dst, int n_edges, int n_scales,
+                       const int* src_off_host, const float* r_host, float ns_lo, float ns_hi, const float* g_len, const float* g_sh,
+                       const float* g_logit, float* dx_dst, cudaStream_t stream);
+int dedf_ebm_energy_bwd(const float* key_f, const float* query_f, const float* qw, const float* g_energy, int n_t, int n_q, int F,
+                        float scale, float* dkey, float* dquery, cudaStream_t stream);
+int dedf_ebm_pose_grad(const float* Ts, int n_t, int n_q, const int* irr_host, const float* qx, const float* qf, const float* g_x,
+                       const float* g_f, float ang_mult, float lin_mult, float* ang, float* lin, cudaStream_t stream);
+
 int dedf_build_arch(void);
 
 /* Self-test of the tcgen05 path (tc.cuh): D[128,N] = A[128,K] . B[N,K]^T on the tensor cores with the accumulator in TMEM;

@@ -490,6 +490,19 @@ class EbmScoreModelHead(nn.Module):
         energy = (field.f - qf).square().sum(dim=-1) * self.energy_rescale_factor
         return torch.einsum("q,tq->t", query_pcd.w, energy.view(nT, nQ))
 
+    def forward(self, Ts, key_pcd_multiscale: List[FeaturedPoints], query_pcd: FeaturedPoints, time):
+        """score_head_ebm.py:192-222: the score is the gradient of log P = -energy w.r.t. the pose, pulled back to the body
+        frame: ang = L(q)^T d/dq (right-trivialised quaternion derivative), lin = R(q)^-1 d/dp.  First order only
+        (the reference's inference mode, ``create_graph=False``)."""
+        with torch.enable_grad():
+            T = Ts.detach().clone().requires_grad_(True)
+            logp = -self.compute_energy(T, key_pcd_multiscale, query_pcd, time)
+            grad = torch.autograd.grad(logp.sum(), T)[0]
+        L = T.detach()[..., self.q_indices] * self.q_factor
+        ang_vel = torch.einsum("...ia,...i", L, grad[..., :4]) * self.ang_mult
+        lin_vel = enc.quaternion_apply(enc.quaternion_invert(T[..., :4].detach()), grad[..., 4:]) * self.lin_mult
+        return ang_vel.detach(), lin_vel.detach()
+
 
 class StaticKeypointModel(nn.Module):
     def __init__(self, keypoint_coords, irreps_output):

@@ -74,6 +74,12 @@ def run(kind, out):
             e = ref.score_head.compute_energy(Ts, key_ms, q, t)
             out[f"{kind}/energy"] = e.numpy()
             msg = f"energy {e.min().item():.4f}..{e.max().item():.4f}"
+            # EbmScoreModelHead.forward (score_head_ebm.py:192-222): the score as the pose gradient of -energy (autograd through
+            # the reference's own field code; .eval() put the head in inference mode: first order, detached)
+            with torch.enable_grad():
+                ang, lin = ref.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=t)
+            out[f"{kind}/ang"], out[f"{kind}/lin"] = ang.detach().numpy(), lin.detach().numpy()
+            msg += f" ang {ang.abs().max().item():.4f} lin {lin.abs().max().item():.4f}"
         if has_sample:
             traj = ref.sample(Ts, scene_pcd_multiscale=key_ms, grasp_pcd=q, **SAMPLE_KW)
             out[f"{kind}/traj"] = traj.numpy()
@@ -100,8 +106,12 @@ def run_c1(out):
 
 def main():
     out = {}
-    run_c1(out)
-    for kind in KINDS:
+    only = [a for a in sys.argv[1:] if a in KINDS]                  # `make_golden_model.py ebm`: refresh these kinds only
+    if only:
+        out.update(np.load(os.path.join(HERE, "ref_model_golden.npz")))
+    else:
+        run_c1(out)
+    for kind in only or KINDS:
         run(kind, out)
     np.savez_compressed(os.path.join(HERE, "ref_model_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "ref_model_golden.npz"), os.path.getsize(os.path.join(HERE, "ref_model_golden.npz")) // 1024, "KiB")

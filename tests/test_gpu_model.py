@@ -398,7 +398,7 @@ def test_place_model_with_keypoint_extractor(cuda):
 
 def test_ebm_critic_energy(cuda):
     """SURVEY 8f rank 2 (critic use): EbmScoreModelHead.compute_energy of the *_ebm configs (agent.py:163-174 re-ranks the
-    sampled poses by it) against the oracle; state_dict keys identical; forward() (score from the energy gradient) raises."""
+    sampled poses by it) against the oracle; state_dict keys identical; forward() (score = pose gradient of -energy) against autograd through the oracle."""
     from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel
     from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs_ebm
     torch.manual_seed(21)
@@ -427,8 +427,18 @@ def test_ebm_critic_energy(cuda):
     es = e.cpu()[e_o.argsort()]
     assert bool((es[1:] - es[:-1] >= -2e-4 * float(e_o.abs().max())).all())
     assert float(e_o.max() - e_o.min()) > 1e-3 * float(e_o.abs().max())          # the test poses do differ in energy
+    # EbmScoreModelHead.forward (score_head_ebm.py:192-222): the score as the pose gradient of -energy, against torch autograd
+    # through the oracle (the reference's formulation).  Inference mode only; train mode (double backward) raises.
+    ang_o, lin_o = oracle.score_head(Ts, keys_o, q_o, t)
+    ang, lin = model.score_head(Ts.to(cuda), keys, q, t.to(cuda))
+    assert ang.shape == lin.shape == (12, 3) and not ang.requires_grad
+    assert float(ang_o.abs().max()) > 1e-2 and float(lin_o.abs().max()) > 1e-2
+    assert_close(ang, ang_o, TOL, "ebm ang score")
+    assert_close(lin, lin_o, TOL, "ebm lin score")
+    model.score_head.train()
     with pytest.raises(NotImplementedError):
         model.score_head(Ts.to(cuda), keys, q, t.to(cuda))
+    model.score_head.eval()
 
 
 def test_highres_config_forward(cuda):

@@ -54,6 +54,9 @@ def test_cuda_matches_reference_code_golden(cuda, kind):
                 assert_close(got, g("loss"), TOL, "training loss and statistics")
         else:
             assert_close(model.score_head.compute_energy(Ts, key_ms, q, t), g("energy"), TOL, "critic energy")
+            ang, lin = model.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=t)       # EbmScoreModelHead.forward
+            assert_close(ang, g("ang"), TOL, "ebm ang (pose gradient of -energy)")
+            assert_close(lin, g("lin"), TOL, "ebm lin (pose gradient of -energy)")
         if has_sample:
             traj = model.sample(Ts, key_ms, q, **SAMPLE_KW)
             assert traj.shape == g("traj").shape and traj.dtype == torch.float64

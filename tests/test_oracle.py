@@ -260,6 +260,9 @@ def test_oracle_matches_reference_code_golden(kind):
                 close(torch.tensor([float(out[0])], dtype=torch.float64), g("loss")[:1], 2e-5, "training loss")     # g("loss")[1:]: the statistics dict
         else:
             close(oracle.score_head.compute_energy(Ts, key_ms, q, t), g("energy"), 2e-5, "energy")
+            ang, lin = oracle.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=t)      # EbmScoreModelHead.forward
+            close(ang, g("ang"), 5e-5, "ebm ang")
+            close(lin, g("lin"), 5e-5, "ebm lin")
         if has_sample:
             traj = oracle.sample(Ts, key_ms, q, **SAMPLE_KW)
             assert traj.shape == g("traj").shape and traj.dtype == torch.float64
