@@ -157,6 +157,9 @@ _PROTOS = {
     "dedf_edge_geom_bwd": [c_fp, c_fp, c_fp, c_fp, c_int, c_int, C.POINTER(c_int), C.POINTER(c_f), c_f, c_f, c_fp, c_fp, c_fp, c_fp, c_fp],
     "dedf_ebm_energy_bwd": [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_f, c_fp, c_fp, c_fp],
     "dedf_ebm_pose_grad": [c_fp, c_int, c_int, C.POINTER(c_int), c_fp, c_fp, c_fp, c_fp, c_f, c_f, c_fp, c_fp, c_fp],
+    "dedf_collision_check": [c_fp, c_int, c_fp, c_ll, c_fp, c_int, c_int, c_f, c_fp, c_fp],
+    "dedf_collision_energy": [c_fp, c_int, c_fp, c_ll, c_fp, c_int, c_int, c_f, c_int, c_f, c_int, c_fp, c_fp, c_fp],
+    "dedf_collision_step": [c_fp, c_fp, c_int, c_f, c_f, c_fp, c_fp],
     "dedf_build_arch": [],
 }
 

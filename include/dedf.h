@@ -433,6 +433,23 @@ int dedf_ebm_energy_bwd(const float* key_f, const float* query_f, const float* q
 int dedf_ebm_pose_grad(const float* Ts, int n_t, int n_q, const int* irr_host, const float* qx, const float* qf, const float* g_x,
                        const float* g_f, float ang_mult, float lin_mult, float* ang, float* lin, cudaStream_t stream);
 
+/* ---- post-processing behind the path: collision-aware pre-place trajectory optimisation ---------------------
+ * edf_interface/edf_interface/utils/collision_utils.py.  x (n_x, 3) scene cloud; y grasp cloud, (n_y, 3) shared by all poses
+ * (y_pose_stride = 0) or (n_pose, n_y, 3) (y_pose_stride = 3 n_y); Ts (n_pose, 7) poses applied to y on the fly
+ * (pcd_utils.transform_points, raw quaternion) or NULL when y is already in the scene frame.
+ *   dedf_collision_check   _check_pcd_collision (:18-34): hit[pose] = 1 iff some point of the pose has a scene point with d^2 < r^2
+ *   dedf_collision_energy  _pcd_energy (:40-110): energy[pose] = sum over the neighbours of cutoff_r / (|x - y|_1 + eps cutoff_r);
+ *                          method 0 'knn' (the max_num_neighbors nearest, then |x - y|_1 <= cutoff_r), 1 'radius' (the first
+ *                          max_num_neighbors in index order with d^2 < cutoff_r^2); grad (n_pose, 6) = d energy / d (rot xyz, trans xyz)
+ *                          of an infinitesimal world-frame motion (the reference's autograd result), or NULL
+ *   dedf_collision_step    _se3_adjoint_lie_grad + the update of _optimize_pcd_collision_once (:116-196):
+ *                          Ts_out = Ts * exp(-dt cutoff_r diag(1,1,1,c,c,c) Ad^T grad)  (se3._exp_map / se3._multiply) */
+int dedf_collision_check(const float* x, int n_x, const float* y, long long y_pose_stride, const float* Ts, int n_pose, int n_y, float r,
+                         int* hit, cudaStream_t stream);
+int dedf_collision_energy(const float* x, int n_x, const float* y, long long y_pose_stride, const float* Ts, int n_pose, int n_y,
+                          float cutoff_r, int max_num_neighbors, float eps, int method, float* energy, float* grad, cudaStream_t stream);
+int dedf_collision_step(const float* Ts, const float* grad, int n_pose, float dt, float cutoff_r, float* Ts_out, cudaStream_t stream);
+
 int dedf_build_arch(void);
 
 /* Self-test of the tcgen05 path (tc.cuh): D[128,N] = A[128,K] . B[N,K]^T on the tensor cores with the accumulator in TMEM;

@@ -285,3 +285,44 @@ def test_config_c1_matches_reference_code_golden():
     ref = torch.from_numpy(G["c1/out_f"])
     assert out.f.shape == ref.shape == (64, 40)
     assert float((out.f - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+# ------------------------------------------------------------------ collision-aware trajectory optimisation
+@pytest.mark.parametrize("name", ["knn", "radius", "knn_sparse"])
+def test_collision_oracle_matches_reference_code_golden(name):
+    """collision_golden.npz holds what the REFERENCE'S OWN function sources compute (collision_utils._pcd_energy,
+    _optimize_pcd_collision_trajectory, _check_pcd_collision with se3._exp_map / _multiply and pcd_utils.transform_points, executed by
+    tests/golden/make_golden_collision.py with stand-ins for torch_cluster.knn / radius and torch_scatter.scatter_sum only);
+    oracle/collision.py must reproduce it."""
+    from oracle import collision as OC
+    from tests.golden.collision_cases import CASES, inputs
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "collision_golden.npz"))
+    cfg = CASES[name]
+    x, y, Ts = inputs(name)
+    Ty = OC.transform_points_batched(y.expand(len(Ts), -1, 3), Ts)
+    e, g = OC.pcd_energy(x, Ty, cfg["cutoff_r"], cfg["k"], cfg["eps"], True, cfg["method"])
+    tr = OC.optimize_trajectory(x, y, Ts, cfg["n_steps"], cfg["dt"], cfg["cutoff_r"], cfg["k"], cfg["eps"], cfg["method"], revert_order=True)
+    hit = OC.check_pcd_collision(x, Ty, cfg["check_r"])
+    rel = lambda a, k: float((a - torch.from_numpy(G[f"{name}/{k}"])).abs().max() / max(1e-30, float(np.abs(G[f"{name}/{k}"]).max())))   # noqa: E731
+    assert rel(e, "energy") < 1e-6 and rel(g, "grad") < 1e-6 and rel(tr, "traj") < 1e-6
+    assert np.array_equal(hit.numpy(), G[f"{name}/hit"])
+    assert float(e[-1]) == 0.0 and torch.equal(tr[-1, 0], tr[-1, -1])          # the far-away pose: no energy, never moves
+    assert float(e[:-1].min()) > 0.0
+
+
+def test_collision_energy_gradient_is_the_lie_derivative():
+    """Independent pin of _pcd_energy's gradient convention: a finite difference of the energy under a small world-frame rotation /
+    translation of the transformed cloud (float64, radius method with a neighbour set that does not change)."""
+    from oracle import collision as OC
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(400, 3, generator=g, dtype=torch.float64) * 2 - 1
+    y = (torch.rand(2, 30, 3, generator=g, dtype=torch.float64) * 2 - 1) * 0.5
+    e0, grad = OC.pcd_energy(x, y, 0.5, max_num_neighbor=10_000, eps=0.05, cluster_method="radius")
+    h = 1e-6
+    for a in range(3):
+        d = torch.zeros(3, dtype=torch.float64); d[a] = h
+        e_t, _ = OC.pcd_energy(x, y + d, 0.5, max_num_neighbor=10_000, eps=0.05, compute_grad=False, cluster_method="radius")
+        e_r, _ = OC.pcd_energy(x, y + torch.cross(d.expand_as(y), y, dim=-1), 0.5, max_num_neighbor=10_000, eps=0.05, compute_grad=False,
+                               cluster_method="radius")
+        assert torch.allclose((e_t - e0) / h, grad[:, 3 + a], rtol=2e-3, atol=1e-3 * float(grad.abs().max()))
+        assert torch.allclose((e_r - e0) / h, grad[:, a], rtol=2e-3, atol=1e-3 * float(grad.abs().max()))
