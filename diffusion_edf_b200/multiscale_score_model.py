@@ -49,8 +49,8 @@ class MultiscaleScoreModel(ScoreModelBase):
         self.lin_mult = self.score_head.lin_mult
         self.ang_mult = self.score_head.ang_mult
 
-    def get_key_pcd_multiscale(self, pcd: FeaturedPoints) -> List[FeaturedPoints]:
+    def _key_pcd_multiscale(self, pcd: FeaturedPoints) -> List[FeaturedPoints]:
         return self.key_model(pcd)
 
-    def get_query_pcd(self, pcd: FeaturedPoints) -> FeaturedPoints:
+    def _query_pcd(self, pcd: FeaturedPoints) -> FeaturedPoints:
         return self.query_model(pcd)

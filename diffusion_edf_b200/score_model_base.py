@@ -28,11 +28,54 @@ class ScoreModelBase(nn.Module):
         self._denoise_graphs = {}
         self._prefetch_tab = None
 
-    def get_key_pcd_multiscale(self, pcd: FeaturedPoints) -> List[FeaturedPoints]:
+    # ------------------------------------------------------------------ reduced-precision switch of the reference
+    def half(self):
+        """agent.py:48-51 calls ``model.half()`` when ``half_precision`` is configured.  The kernels compute in fp32 (never
+        below the reference's fp16 arithmetic), so the parameters stay fp32: the switch only changes the interface --
+        fp16 inputs (poses, times, point clouds) are widened on entry and the scores / features come back in fp16, as a
+        caller of the reference's half model sees them."""
+        self._io_half = True
+        return self
+
+    def float(self):
+        self._io_half = False
+        return super().float()
+
+    @staticmethod
+    def _widen(v):
+        """fp16 / bf16 tensor or FeaturedPoints (or a list of them) -> fp32; anything else unchanged."""
+        if isinstance(v, torch.Tensor):
+            return v.float() if v.dtype in (torch.float16, torch.bfloat16) else v
+        if isinstance(v, FeaturedPoints):
+            return FeaturedPoints(x=ScoreModelBase._widen(v.x), f=ScoreModelBase._widen(v.f), b=v.b, w=ScoreModelBase._widen(v.w))
+        if isinstance(v, (list, tuple)):
+            return type(v)(ScoreModelBase._widen(e) for e in v)
+        return v
+
+    def _narrow(self, v):
+        """fp32 result -> fp16 when the model was switched with .half()."""
+        if not getattr(self, "_io_half", False):
+            return v
+        if isinstance(v, torch.Tensor):
+            return v.half() if v.dtype == torch.float32 else v
+        if isinstance(v, FeaturedPoints):
+            return FeaturedPoints(x=self._narrow(v.x), f=self._narrow(v.f), b=v.b, w=self._narrow(v.w))
+        if isinstance(v, (list, tuple)):
+            return type(v)(self._narrow(e) for e in v)
+        return v
+
+    # subclasses implement the fp32 internals; the public methods add the .half() interface conversion
+    def _key_pcd_multiscale(self, pcd: FeaturedPoints) -> List[FeaturedPoints]:
         raise NotImplementedError
 
-    def get_query_pcd(self, pcd: FeaturedPoints) -> FeaturedPoints:
+    def _query_pcd(self, pcd: FeaturedPoints) -> FeaturedPoints:
         raise NotImplementedError
+
+    def get_key_pcd_multiscale(self, pcd: FeaturedPoints) -> List[FeaturedPoints]:
+        return self._narrow(self._key_pcd_multiscale(self._widen(pcd)))
+
+    def get_query_pcd(self, pcd: FeaturedPoints) -> FeaturedPoints:
+        return self._narrow(self._query_pcd(self._widen(pcd)))
 
     # ------------------------------------------------------------------ training loss (forward value)
     def get_train_loss(self, Ts, time, key_pcd, query_pcd, target_ang_score, target_lin_score):
@@ -43,6 +86,8 @@ class ScoreModelBase(nn.Module):
         assert target_ang_score.ndim == 2 and target_ang_score.shape[-1] == 3
         assert target_lin_score.ndim == 2 and target_lin_score.shape[-1] == 3
         assert len(time) == len(target_ang_score) == len(target_lin_score)
+        Ts, time, key_pcd, query_pcd, target_ang_score, target_lin_score = self._widen((Ts, time, key_pcd, query_pcd, target_ang_score,
+                                                                                        target_lin_score))
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
             from . import train_path
@@ -54,11 +99,11 @@ class ScoreModelBase(nn.Module):
             if isinstance(self.query_model, KeypointExtractor):
                 q = train_path.keypoint_extractor(self.query_model, query_pcd)      # place configs
             else:
-                q = self.get_query_pcd(query_pcd)                                    # StaticKeypointModel: torch views of parameters
+                q = self._query_pcd(query_pcd)                                       # StaticKeypointModel: torch views of parameters
             ang, lin = train_path.score_head(self.score_head, Ts, key_ms, q, time)
         else:
-            key_ms = self.get_key_pcd_multiscale(key_pcd)
-            q = self.get_query_pcd(query_pcd)
+            key_ms = self._key_pcd_multiscale(key_pcd)
+            q = self._query_pcd(query_pcd)
             ang, lin = self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)
         t_ang = target_ang_score * torch.sqrt(time[..., None]) * self.ang_mult
         t_lin = target_lin_score * torch.sqrt(time[..., None]) * self.lin_mult
@@ -91,6 +136,7 @@ class ScoreModelBase(nn.Module):
         (seed = ``self.sample_seed``) unless ``noise`` (sum(N_steps), nT, 6) standard normals is given."""
         if isinstance(temperatures, (int, float)):
             temperatures = [float(temperatures)] * len(diffusion_schedules)
+        scene_pcd_multiscale, grasp_pcd = self._widen(list(scene_pcd_multiscale)), self._widen(grasp_pcd)
         dev = T_seed.device
         nT = T_seed.shape[0]
         T = T_seed.detach().to(torch.float64).contiguous().clone()
@@ -184,12 +230,13 @@ class ScoreModelBase(nn.Module):
 
     def _forward_tensors(self, Ts, time, kx, kf, kb, qx, qf, qb):
         self.prefetch_weights()
-        key_ms = self.get_key_pcd_multiscale(FeaturedPoints(kx, kf, kb))
-        q = self.get_query_pcd(FeaturedPoints(qx, qf, qb))
+        key_ms = self._key_pcd_multiscale(FeaturedPoints(kx, kf, kb))
+        q = self._query_pcd(FeaturedPoints(qx, qf, qb))
         return self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)
 
     def forward(self, Ts: torch.Tensor, time: torch.Tensor, key_pcd: FeaturedPoints, query_pcd: FeaturedPoints,
                 debug: bool = False):
+        Ts, time, key_pcd, query_pcd = self._widen((Ts, time, key_pcd, query_pcd))
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         graph_ok = getattr(self.query_model, "graph_safe", False)      # see graphs.py: shapes must not depend on the data
         if self.use_cuda_graph and graph_ok and Ts.is_cuda and not debug and not needs_grad and not self.training:
@@ -202,10 +249,10 @@ class ScoreModelBase(nn.Module):
                     self._graphs.clear()
                 g = GraphedCallable(self._forward_tensors, ins)
                 self._graphs[key] = g
-                return tuple(o.clone() for o in g.eager_out), None
-            return g(*ins), None
-        key_ms = self.get_key_pcd_multiscale(key_pcd)
-        q = self.get_query_pcd(query_pcd)
+                return self._narrow(tuple(o.clone() for o in g.eager_out)), None
+            return self._narrow(tuple(g(*ins))), None
+        key_ms = self._key_pcd_multiscale(key_pcd)
+        q = self._query_pcd(query_pcd)
         score = self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)
         dbg = ([detach_featured_points(k) for k in key_ms], detach_featured_points(q)) if debug else None
-        return score, dbg
+        return self._narrow(tuple(score)), self._narrow(dbg)

@@ -132,6 +132,37 @@ def test_full_model_forward(cuda):
     assert_close(lin, lin64, budget, "lin vs fp64 oracle")
 
 
+def test_half_switch_keeps_fp32_arithmetic(cuda):
+    """agent.py:48-51: ``model.half()``.  The kernels stay fp32 (parameters untouched); fp16 inputs are widened on entry and the
+    scores / features come back in fp16.  The scores must equal the fp32 model's scores of the SAME fp16-rounded inputs up to the
+    final fp16 rounding (2^-11 relative), and ``sample`` must accept the fp16 feature clouds."""
+    from diffusion_edf_b200 import FeaturedPoints
+    from diffusion_edf_b200.synthetic import make_poses, make_scene
+    _, model = _models(cuda, seed=4)
+    x, rgb = make_scene(1500, seed=4, half_extent=12.0)
+    Ts, t = make_poses(8, x, seed=4, spread=6.0)
+    b = torch.zeros(len(x), dtype=torch.long)
+    h = lambda v: v.to(cuda).half()          # noqa: E731
+    grasp32 = FeaturedPoints(torch.zeros(5, 3, device=cuda), torch.zeros(5, 3, device=cuda), torch.zeros(5, dtype=torch.long, device=cuda))
+    with torch.no_grad():
+        (a32, l32), _ = model(h(Ts).float(), h(t).float(), FeaturedPoints(h(x).float(), h(rgb).float(), b.to(cuda)), grasp32)
+        ret = model.half()
+        assert ret is model and all(p.dtype == torch.float32 for p in model.parameters())
+        grasp16 = FeaturedPoints(grasp32.x.half(), grasp32.f.half(), grasp32.b)
+        (a16, l16), _ = model(h(Ts), h(t), FeaturedPoints(h(x), h(rgb), b.to(cuda)), grasp16)
+        assert a16.dtype == l16.dtype == torch.float16
+        assert_close(a16.float(), a32, 1e-3, "half-interface ang")
+        assert_close(l16.float(), l32, 1e-3, "half-interface lin")
+        keys = model.get_key_pcd_multiscale(FeaturedPoints(h(x), h(rgb), b.to(cuda)))
+        q = model.get_query_pcd(grasp16)
+        assert all(k.f.dtype == torch.float16 for k in keys) and q.f.dtype == torch.float16
+        traj = model.sample(h(Ts), keys, q, diffusion_schedules=[[1.0, 0.2]], N_steps=[3], timesteps=[0.04], temperatures=[0.0])
+        assert traj.dtype == torch.float64 and traj.shape == (5, 8, 7) and bool(torch.isfinite(traj).all())
+        model.float()
+        (a, l), _ = model(h(Ts).float(), h(t).float(), FeaturedPoints(h(x).float(), h(rgb).float(), b.to(cuda)), grasp32)
+        assert a.dtype == torch.float32 and torch.equal(a, a32)
+
+
 def test_sample_matches_oracle(cuda):
     """Denoise loop: noise-free (temperature 0) and with injected noise, 12 steps, 6 poses; float64 poses."""
     from diffusion_edf_b200 import FeaturedPoints
