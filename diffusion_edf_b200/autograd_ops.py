@@ -173,6 +173,29 @@ class DtpFn(Function):
         return dx, dsh, dw, None
 
 
+def dtp_generic(x: torch.Tensor, sh: torch.Tensor, w: torch.Tensor, irr_in: Irr, paths, irr_out: Irr) -> torch.Tensor:
+    """Depthwise tensor product for irreps outside the fused kernels' family (table-driven, irreps.dtp_paths).  FORWARD ONLY: the
+    training path (a backward through it) exists for the 2G:G:G/2 family of the shipped configs."""
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or sh.requires_grad):
+        raise NotImplementedError("gradients through the table-driven depthwise tensor product (irreps outside 2G x0e + G x1e + G/2 x2e) "
+                                  "are not built")
+    x, sh, w = x.contiguous(), sh.contiguous(), w.contiguous()
+    E = x.shape[0]
+    shared = w.dim() == 1
+    out = torch.empty(E, _dim(irr_out), dtype=torch.float32, device=x.device)
+    flat = [int(v) for p in paths for v in p]
+    ops._call("dedf_dtp_generic_fwd", ptr(x), L.int_array(irr_in), ptr(sh), ptr(w), 0 if shared else w.shape[1], len(paths),
+              L.int_array(flat), L.int_array(irr_out), E, ptr(out), stream())
+    return out
+
+
+def dtp(sep, x: torch.Tensor, sh: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """The depthwise tensor product of a SeparableFCTP: the family-specialised kernels (with backward) or the table-driven one."""
+    if sep.fused_family:
+        return DtpFn.apply(x, sh, w, sep.irreps_node.m[1])
+    return dtp_generic(x, sh, w, sep.irreps_node.m, sep.paths, sep.irreps_dtp_out.m)
+
+
 class GatherFn(Function):
     """y = x[idx] (idx int32 or int64); backward scatters with atomics."""
 

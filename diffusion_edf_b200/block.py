@@ -110,7 +110,7 @@ class EquiformerBlock(nn.Module):
         self.prenorm_src = EquivariantLayerNormV2(self.irreps_src)
         self.linear_src = LinearRS(self.irreps_src, self.irreps_emb, bias=True)
         self.skip_2 = ProjectIfMismatch(self.irreps_emb, self.irreps_output, bias=True, layernorm=False)
-        self.ga = GraphAttention(self.irreps_emb, self.irreps_emb, fc_neurons, num_heads)
+        self.ga = GraphAttention(self.irreps_emb, self.irreps_emb, fc_neurons, num_heads, sh_lmax=Irreps(irreps_edge_attr).lmax)
         self.post_norm = EquivariantLayerNormV2(self.irreps_emb)
         self.ffn = FeedForwardNetwork(self.irreps_emb, self.irreps_output, mlp_mid(self.irreps_emb, irreps_mlp_mid))
 

@@ -324,6 +324,50 @@ __global__ void __launch_bounds__(256) dtp_bwd_kernel(const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// depthwise tensor product for ANY even-parity l <= 2 irreps and harmonics degree, driven by a path table
+// (irreps.dtp_paths: creation order of tensor_product_rescale.py:352-382).  The un-fused tensor field of irreps outside the
+// fused kernels' family runs on it (BASELINE config C1: 16x0e+8x1e with the l <= 1 harmonics).  One thread per (edge, weight):
+// 'uvu' paths own disjoint output channels, so there are no atomics.  Forward only.
+// ---------------------------------------------------------------------------------------------------------------
+struct DtpPathTable {
+    int n_paths;
+    int l1[DEDF_DTP_MAX_PATHS], l2[DEDF_DTP_MAX_PATHS], lo[DEDF_DTP_MAX_PATHS], mul[DEDF_DTP_MAX_PATHS], w_off[DEDF_DTP_MAX_PATHS],
+        ch_off[DEDF_DTP_MAX_PATHS];
+};
+
+__device__ __forceinline__ void cg_any(int l1, int l2, int lo, const float* x, const float* y, float* o) {
+    switch (l1 * 9 + l2 * 3 + lo) {
+        case 0: cg_000(x, y, o); break;   case 4: cg_011(x, y, o); break;   case 8: cg_022(x, y, o); break;
+        case 10: cg_101(x, y, o); break;  case 12: cg_110(x, y, o); break;  case 13: cg_111(x, y, o); break;
+        case 14: cg_112(x, y, o); break;  case 16: cg_121(x, y, o); break;  case 17: cg_122(x, y, o); break;
+        case 20: cg_202(x, y, o); break;  case 22: cg_211(x, y, o); break;  case 23: cg_212(x, y, o); break;
+        case 24: cg_220(x, y, o); break;  case 25: cg_221(x, y, o); break;  case 26: cg_222(x, y, o); break;
+        default: for (int k = 0; k < 5; ++k) o[k] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) dtp_generic_fwd_kernel(const float* __restrict__ x, Irr in, const float* __restrict__ sh,
+                                                             const float* __restrict__ w, long long w_stride, DtpPathTable t, Irr out,
+                                                             int numel, int E, float* __restrict__ y) {
+    const int Fin = in.dim(), Fout = out.dim();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)E * numel; i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i / numel), wi = (int)(i % numel);
+        int p = 0;
+        while (p + 1 < t.n_paths && wi >= t.w_off[p + 1]) ++p;
+        const int u = wi - t.w_off[p], l1 = t.l1[p], l2 = t.l2[p], lo = t.lo[p];
+        const float* xe = x + (size_t)e * Fin + (l1 == 0 ? 0 : l1 == 1 ? in.off1() : in.off2()) + u * (2 * l1 + 1);
+        const float* se = sh + (size_t)e * 9 + (l2 == 0 ? 0 : l2 == 1 ? 1 : 4);
+        float xv[5], sv[5], o[5];
+        for (int k = 0; k < 2 * l1 + 1; ++k) xv[k] = xe[k];
+        for (int k = 0; k < 2 * l2 + 1; ++k) sv[k] = se[k];
+        cg_any(l1, l2, lo, xv, sv, o);
+        const float wv = w[(size_t)e * w_stride + wi];
+        float* ye = y + (size_t)e * Fout + (lo == 0 ? 0 : lo == 1 ? out.off1() : out.off2()) + (t.ch_off[p] + u) * (2 * lo + 1);
+        for (int k = 0; k < 2 * lo + 1; ++k) ye[k] = wv * o[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // gather / scatter-add
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void gather_rows_i32_kernel(const float* __restrict__ x, const int* __restrict__ idx, int n, int F, float* __restrict__ y) {
@@ -1280,6 +1324,28 @@ extern "C" int dedf_ebm_pose_grad(const float* Ts, int n_t, int n_q, const int* 
     if (n_t <= 0) return DEDF_OK;
     if (!Ts || !irr || !qx || !qf || !g_x || !g_f || !ang || !lin) return DEDF_ERR_ARG;
     ebm_pose_grad_kernel<<<n_t, 128, 0, stream>>>(Ts, n_t, n_q, Irr{irr[0], irr[1], irr[2]}, qx, qf, g_x, g_f, ang_mult, lin_mult, ang, lin);
+    DEDF_CHECK_LAUNCH();
+    return DEDF_OK;
+}
+
+extern "C" int dedf_dtp_generic_fwd(const float* x, const int* irr_in, const float* sh, const float* w, long long w_stride, int n_paths,
+                                    const int* paths, const int* irr_out, int n_edges, float* out, cudaStream_t stream) {
+    if (n_edges <= 0) return DEDF_OK;
+    if (!x || !irr_in || !sh || !w || !paths || !irr_out || !out || n_paths < 1 || n_paths > DEDF_DTP_MAX_PATHS) return DEDF_ERR_ARG;
+    DtpPathTable t{};
+    t.n_paths = n_paths;
+    const Irr in{irr_in[0], irr_in[1], irr_in[2]}, o{irr_out[0], irr_out[1], irr_out[2]};
+    int numel = 0;
+    for (int p = 0; p < n_paths; ++p) {
+        const int* r = paths + 6 * p;
+        t.l1[p] = r[0]; t.l2[p] = r[1]; t.lo[p] = r[2]; t.mul[p] = r[3]; t.w_off[p] = r[4]; t.ch_off[p] = r[5];
+        if (r[0] < 0 || r[0] > 2 || r[1] < 0 || r[1] > 2 || r[2] < abs(r[0] - r[1]) || r[2] > 2 || r[2] > r[0] + r[1]) return DEDF_ERR_ARG;
+        const int m_in = r[0] == 0 ? in.m0 : r[0] == 1 ? in.m1 : in.m2, m_out = r[2] == 0 ? o.m0 : r[2] == 1 ? o.m1 : o.m2;
+        if (r[3] != m_in || r[4] != numel || r[5] < 0 || r[5] + r[3] > m_out) return DEDF_ERR_ARG;
+        numel += r[3];
+    }
+    dtp_generic_fwd_kernel<<<grid_for((long long)n_edges * numel, 256, kNumSMs * 8), 256, 0, stream>>>(x, in, sh, w, w_stride, t, o, numel,
+                                                                                                        n_edges, out);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

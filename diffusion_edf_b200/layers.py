@@ -23,7 +23,7 @@ from torch import nn
 
 from . import _lib as L
 from . import ops
-from .irreps import Irreps, dtp_numel, dtp_out, gate_pre
+from .irreps import Irreps, dtp_numel, dtp_out, dtp_paths, gate_pre, is_fused_family
 
 
 def _versions(mod: nn.Module):
@@ -361,27 +361,32 @@ class _DTP(nn.Module):
 
 
 class SeparableFCTP(nn.Module):
-    """dtp (+ dtp_rad) + lin (+ gate) for node irreps ``m0=2G, m1=G, m2=G/2`` and the l<=2 spherical harmonics."""
+    """dtp (+ dtp_rad) + lin (+ gate).  Node irreps ``m0=2G, m1=G, m2=G/2`` with the l<=2 harmonics (every shipped config) run on
+    the fused edge kernels; any other even-parity l<=2 irreps / harmonics degree keeps the same parameters (same state_dict keys)
+    and runs un-fused on the table-driven depthwise tensor product (``fused_family`` False, ``paths``)."""
 
     def __init__(self, irreps_node: Irreps, irreps_out: Irreps, fc_neurons: Optional[Sequence[int]], use_activation: bool,
-                 internal_weights: bool):
+                 internal_weights: bool, sh_lmax: int = 2):
         super().__init__()
         self.irreps_node, self.irreps_out = Irreps(irreps_node), Irreps(irreps_out)
-        m0, m1, m2 = self.irreps_node.m
-        if not (m0 == 2 * m1 and m1 == 2 * m2 and m1 in (16, 32)):
-            raise NotImplementedError(f"the fused edge kernels are specialised for 2G x0e + G x1e + G/2 x2e with G in (16, 32); got {self.irreps_node}")
-        self.numel = dtp_numel(self.irreps_node)
+        self.sh_lmax = int(sh_lmax)
+        self.fused_family = is_fused_family(self.irreps_node) and self.sh_lmax == 2 and all(self.irreps_out.m)
+        # output filter of DepthwiseTensorProduct = the l's of the node OUTPUT irreps (0e always kept)
+        filt = None if self.fused_family else self.irreps_out
+        self.paths = dtp_paths(self.irreps_node, self.sh_lmax, (0, 1, 2) if filt is None else tuple(l for l in range(3) if filt.m[l]))
+        self.irreps_dtp_out = dtp_out(self.irreps_node, self.sh_lmax, filt)
+        self.numel = dtp_numel(self.irreps_node, self.sh_lmax, filt)
         self.dtp = _DTP(self.numel, internal_weights)
         self.dtp_rad = RadialProfile(list(fc_neurons) + [self.numel]) if fc_neurons is not None else None
         self.use_activation = use_activation
         lin_out = gate_pre(self.irreps_out) if use_activation else self.irreps_out
-        self.lin = LinearRS(dtp_out(self.irreps_node), lin_out)
+        self.lin = LinearRS(self.irreps_dtp_out, lin_out)
 
 
 class GraphAttention(nn.Module):
     """GraphAttentionMLP / GraphAttentionMLP2 (same parameters; the latter adds the edge logits)."""
 
-    def __init__(self, irreps_emb, irreps_out, fc_neurons: Sequence[int], num_heads: int):
+    def __init__(self, irreps_emb, irreps_out, fc_neurons: Sequence[int], num_heads: int, sh_lmax: int = 2):
         super().__init__()
         self.irreps_emb, self.irreps_out = Irreps(irreps_emb), Irreps(irreps_out)
         if num_heads != 4:
@@ -389,9 +394,10 @@ class GraphAttention(nn.Module):
         self.num_heads = num_heads
         self.irreps_head = self.irreps_emb.div(num_heads)
         mul_alpha = self.irreps_emb.m[0]
-        self.sep_act = SeparableFCTP(self.irreps_emb, self.irreps_emb, fc_neurons, use_activation=True, internal_weights=False)
-        self.sep_alpha = LinearRS(Irreps((dtp_out(self.irreps_emb).m[0], 0, 0)), Irreps((mul_alpha, 0, 0)))
-        self.sep_value = SeparableFCTP(self.irreps_emb, self.irreps_emb, None, use_activation=False, internal_weights=True)
+        self.sep_act = SeparableFCTP(self.irreps_emb, self.irreps_emb, fc_neurons, use_activation=True, internal_weights=False, sh_lmax=sh_lmax)
+        self.fused_family = self.sep_act.fused_family
+        self.sep_alpha = LinearRS(Irreps((self.sep_act.irreps_dtp_out.m[0], 0, 0)), Irreps((mul_alpha, 0, 0)))
+        self.sep_value = SeparableFCTP(self.irreps_emb, self.irreps_emb, None, use_activation=False, internal_weights=True, sh_lmax=sh_lmax)
         self.alpha_dot = nn.Parameter(torch.randn(1, num_heads, mul_alpha // num_heads))
         nn.init.xavier_uniform_(self.alpha_dot)
         self.proj = LinearRS(self.irreps_emb, self.irreps_out)
@@ -423,6 +429,8 @@ class GraphAttention(nn.Module):
         attention, alpha_e *= w[src_e] AFTER the softmax (graph_attention.py:258-259) == scaling the value rows.
         ``w``: per-edge tensor-product weights as produced by the kernels from ``self.sep_act.dtp_rad.packed()`` (column order
         ``dtp_rad.permuted()``); pass ``w_perm=False`` for weights in the reference's order."""
+        if not self.fused_family:
+            raise L.DedfError("irreps outside the fused kernels' family run through train_path.graph_attention (un-fused kernels)")
         p = self.packed()
         G = self.irreps_emb.m[1]
         F = self.irreps_emb.dim

@@ -46,8 +46,9 @@ class MultiscaleTensorField(nn.Module):
                  use_src_point_attn: bool = False, use_dst_point_attn: bool = False, cutoff_method: str = "edge_attn"):
         super().__init__()
         self.irreps_input, self.irreps_output = Irreps(irreps_input), Irreps(irreps_output)
-        if Irreps(irreps_sh).m != (1, 1, 1):
-            raise NotImplementedError("irreps_sh must be 1x0e+1x1e+1x2e")
+        self.irreps_sh = Irreps(irreps_sh)
+        if self.irreps_sh.m not in ((1, 1, 1), (1, 1, 0)):
+            raise NotImplementedError("irreps_sh must be the l <= 2 (or l <= 1) spherical harmonics 1x0e+1x1e(+1x2e)")
         if irreps_query is not None:
             raise NotImplementedError("query (dst) features are not used by the shipped configs (query_time_encoding: False)")
         if cutoff_method != "edge_attn" or attn_type != "mlp" or n_layers != 1:
@@ -88,6 +89,8 @@ class MultiscaleTensorField(nn.Module):
                                               bias=True, use_src_point_attn=use_src_point_attn,
                                               use_dst_point_attn=use_dst_point_attn, use_edge_weights=True)
         self.gnn_blocks = nn.ModuleList()
+        # irreps outside the fused kernels' family (BASELINE config C1: 16x0e+8x1e, l <= 1 harmonics): same parameters, un-fused kernels
+        self.fused_family = self.gnn_block_init.ga.fused_family
         self._pre_cache = (None, None)
         self._pre_tc = None
         self._sin_freq = None
@@ -132,6 +135,8 @@ class MultiscaleTensorField(nn.Module):
         edge is ``edge_dst // rows_per_time`` (clamped), i.e. nQ consecutive query nodes share a pose's time."""
         if context_emb is not None:
             raise NotImplementedError("pass the time rows produced by ScoreModelHead (time_rows=...), not context_emb")
+        if not self.fused_family:
+            return self._forward_unfused(query_points, input_points_multiscale, max_neighbors)
         assert (time_rows is not None) == (self.context_emb_dim is not None)
         srcs = sources if sources is not None else self.encode_sources(input_points_multiscale)
         x_src, b_src, src_off, msg_src = srcs[:4]
@@ -144,6 +149,19 @@ class MultiscaleTensorField(nn.Module):
                                           want_logit=True)
         out = self.attend_edges(g, length, sh, logit, srcs, time_rows, rows_per_time)
         return FeaturedPoints(x=query_points.x, f=out, b=query_points.b, w=query_points.w)
+
+    def _forward_unfused(self, query_points: FeaturedPoints, input_points_multiscale: List[FeaturedPoints], max_neighbors: int) -> FeaturedPoints:
+        """Any even-parity l <= 2 irreps: the field composed from the un-fused CUDA primitives of the training path (train_path.py:
+        radius search, edge geometry, length embedding, pre-linear, RadialProfile, table-driven depthwise tensor products, block-
+        diagonal linears, gate, segment softmax-reduce, proj, LN, FFN) -- forward only.  BASELINE config C1 runs here."""
+        if self.context_emb_dim is not None:
+            raise NotImplementedError("edge context embeddings with irreps outside 2G x0e + G x1e + G/2 x2e")
+        if max_neighbors != 1000:
+            raise NotImplementedError("max_neighbors other than the reference's default (1000)")
+        from . import train_path
+        with torch.no_grad():
+            f = train_path.tensor_field(self, query_points.x, query_points.b, list(input_points_multiscale), None, 1)
+        return FeaturedPoints(x=query_points.x, f=f, b=query_points.b, w=query_points.w)
 
     def forward_poses(self, Ts: torch.Tensor, query_pcd: FeaturedPoints, sources, *, time_rows: Optional[torch.Tensor] = None,
                       max_neighbors: int = 1000, edge_capacity: Optional[int] = None, step: Optional[torch.Tensor] = None,

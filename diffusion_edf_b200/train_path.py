@@ -19,7 +19,7 @@ import torch
 from . import autograd_ops as A
 from . import ops
 from .gnn_data import FeaturedPoints
-from .irreps import dtp_out, gate_pre
+from .irreps import gate_pre
 from .layers import EquivariantLayerNormV2, GraphAttention, LinearRS, ProjectIfMismatch, RadialProfile
 
 
@@ -89,12 +89,12 @@ def graph_attention(ga: GraphAttention, msg_src: torch.Tensor, msg_dst: Optional
     message = A.GatherFn.apply(msg_src, es)
     if msg_dst is not None:
         message = A.AddScaleFn.apply(message, A.GatherFn.apply(msg_dst, ed), 1.0)
-    m = A.DtpFn.apply(message, sh, w, G)                                                   # (E, 49 G)
-    d_out = dtp_out(ga.irreps_emb)
+    m = A.dtp(ga.sep_act, message, sh, w)                                                  # (E, 49 G) for the 2G:G:G/2 family
+    d_out = ga.sep_act.irreps_dtp_out
     alpha_pre = linear_rs(ga.sep_alpha, m[:, :d_out.m[0]].contiguous())
     logits = A.AlphaFn.apply(alpha_pre, ga.alpha_dot, edge_logit)
     v = A.GateFn.apply(linear_rs(ga.sep_act.lin, m), ga.sep_act.lin.irreps_out.m)
-    m2 = A.DtpFn.apply(v, sh, ga.sep_value.dtp.tp.weight, G)
+    m2 = A.dtp(ga.sep_value, v, sh, ga.sep_value.dtp.tp.weight)
     val = linear_rs(ga.sep_value.lin, m2)
     if src_weight is not None:      # source-point attention: alpha_e *= w[src_e] after the softmax == scaling the value rows
         val = A.RowScaleFn.apply(val, A.GatherFn.apply(src_weight.reshape(-1, 1), es), ga.irreps_emb.m)

@@ -367,6 +367,12 @@ int dedf_dtp_fwd(int mul1, const float* x, const float* sh, const float* w, long
                  cudaStream_t stream);
 int dedf_dtp_bwd(int mul1, const float* x, const float* sh, const float* w, long long w_stride, const float* g, int n_edges,
                  float* dx, float* dw, cudaStream_t stream);
+/* The same tensor product for ANY even-parity l <= 2 irreps / harmonics degree, driven by a path table (creation order of
+ * tensor_product_rescale.py:352-382): paths_host = n_paths rows of (l1, l2, lo, mul, w_off, ch_off); out (E, dim(irr_out)) in the sorted
+ * simplified layout.  Forward only: the un-fused tensor field of irreps outside the fused kernels' family (BASELINE config C1). */
+#define DEDF_DTP_MAX_PATHS 15
+int dedf_dtp_generic_fwd(const float* x, const int* irr_in_host, const float* sh, const float* w, long long w_stride, int n_paths,
+                         const int* paths_host, const int* irr_out_host, int n_edges, float* out, cudaStream_t stream);
 int dedf_gather_rows_i32(const float* x, const int* idx, int n, int F, float* y, cudaStream_t stream);
 int dedf_scatter_add_rows(const float* g, const void* idx, int idx_is_i64, int n, int F, float* out, cudaStream_t stream);
 /* attention logits sum_k c SLReLU(pre[e,h,k]) alpha_dot[h,k] + edge_logit[e]   (graph_attention.py:241-246) */

@@ -163,6 +163,61 @@ def test_half_switch_keeps_fp32_arithmetic(cuda):
         assert a.dtype == torch.float32 and torch.equal(a, a32)
 
 
+def test_config_c1_tensor_field_on_gpu(cuda):
+    """BASELINE.json configs[0] (C1: MultiscaleTensorField, 16x0e+8x1e, l <= 1 harmonics, 256-point cloud) on the CUDA path: irreps
+    outside the fused kernels' family run un-fused on the table-driven depthwise tensor product.  Held to the numbers the REFERENCE'S
+    OWN MultiscaleTensorField source produced (tests/golden/make_golden_model.py::run_c1) and to the oracle."""
+    import os
+    import numpy as np
+    from diffusion_edf_b200 import FeaturedPoints, MultiscaleTensorField
+    from tests.golden.model_cases import C1_KWARGS, c1_inputs, c1_seeded_oracle, weight_checksums
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_model_golden.npz"))
+    tf = c1_seeded_oracle()
+    field = MultiscaleTensorField(**C1_KWARGS).eval()
+    assert set(field.state_dict()) == set(tf.state_dict()) and not field.fused_family
+    field.load_state_dict(tf.state_dict())
+    field = field.to(cuda)
+    x0, f0, xq = c1_inputs()
+    z = lambda n: torch.zeros(n, dtype=torch.long)                   # noqa: E731
+    with torch.no_grad():
+        ref = tf(OM.FeaturedPoints(xq, torch.empty(64, 0), z(64)), [OM.FeaturedPoints(x0, f0, z(256)), OM.FeaturedPoints(x0[:32], f0[:32], z(32))])
+        keys = [FeaturedPoints(x0.to(cuda), f0.to(cuda), z(256).to(cuda)), FeaturedPoints(x0[:32].to(cuda).contiguous(), f0[:32].to(cuda).contiguous(), z(32).to(cuda))]
+        out = field(FeaturedPoints(xq.to(cuda), torch.empty(64, 0, device=cuda), z(64).to(cuda)), keys)
+    assert out.f.shape == (64, 40)
+    assert_close(out.f, ref.f, TOL, "C1 field vs oracle")
+    if np.allclose(weight_checksums(tf.state_dict()), G["c1/weights"], rtol=1e-9, atol=0):
+        assert_close(out.f, torch.from_numpy(G["c1/out_f"]), TOL, "C1 field vs the reference's own source")
+
+
+@pytest.mark.parametrize("spec,sh_lmax,filt", [("32x0e+16x1e+8x2e", 2, None), ("16x0e+8x1e", 1, "16x0e+8x1e"), ("8x0e+12x1e+4x2e", 2, "1x0e+1x1e"),
+                                               ("12x0e", 2, "4x0e+4x1e+4x2e")])
+def test_dtp_generic_matches_oracle_tensor_product(cuda, spec, sh_lmax, filt):
+    """dedf_dtp_generic_fwd (table-driven depthwise tensor product, any even-parity l <= 2 irreps) against the oracle's restatement of
+    o3.TensorProduct as built by DepthwiseTensorProduct; for the fused family also bit-level agreement in layout with dedf_dtp_fwd."""
+    from diffusion_edf_b200 import autograd_ops as A
+    from diffusion_edf_b200.irreps import Irreps, dtp_numel, dtp_out, dtp_paths
+    from oracle import nn as ONN
+    from oracle.irreps import Irreps as OIrreps
+    gen = torch.Generator().manual_seed(11)
+    irr = Irreps(spec)
+    fo = None if filt is None else Irreps(filt)
+    lo_f = (0, 1, 2) if fo is None else tuple(l for l in range(3) if fo.m[l])
+    paths, d_out, numel = dtp_paths(irr, sh_lmax, lo_f), dtp_out(irr, sh_lmax, fo), dtp_numel(irr, sh_lmax, fo)
+    sh_spec = "1x0e+1x1e+1x2e" if sh_lmax == 2 else "1x0e+1x1e"
+    o_tp = ONN.DepthwiseTensorProduct(OIrreps(spec), OIrreps(sh_spec), OIrreps(filt or "1x0e+1x1e+1x2e"), internal_weights=False, bias=False)
+    assert o_tp.tp.weight_numel == numel and o_tp.irreps_out.simplify().dim == d_out.dim
+    E = 53
+    x = torch.randn(E, irr.dim, generator=gen)
+    sh9 = torch.randn(E, 9, generator=gen)
+    w = torch.randn(E, numel, generator=gen)
+    ref = o_tp(x, sh9[:, :(sh_lmax + 1) ** 2].contiguous(), w)
+    out = A.dtp_generic(x.to(cuda), sh9.to(cuda), w.to(cuda), irr.m, paths, d_out.m)
+    assert_close(out, ref, 1e-5, "generic depthwise tensor product")
+    if filt is None:
+        fam = A.DtpFn.apply(x.to(cuda), sh9.to(cuda), w.to(cuda), irr.m[1])
+        assert_close(out, fam, 1e-6, "generic vs family kernel")
+
+
 def test_sample_matches_oracle(cuda):
     """Denoise loop: noise-free (temperature 0) and with injected noise, 12 steps, 6 poses; float64 poses."""
     from diffusion_edf_b200 import FeaturedPoints
