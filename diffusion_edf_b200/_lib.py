@@ -161,6 +161,7 @@ _PROTOS = {
     "dedf_collision_energy": [c_fp, c_int, c_fp, c_ll, c_fp, c_int, c_int, c_f, c_int, c_f, c_int, c_fp, c_fp, c_fp],
     "dedf_collision_step": [c_fp, c_fp, c_int, c_f, c_f, c_fp, c_fp],
     "dedf_dtp_generic_fwd": [c_fp, C.POINTER(c_int), c_fp, c_fp, c_ll, c_int, C.POINTER(c_int), C.POINTER(c_int), c_int, c_fp, c_fp],
+    "dedf_stamp": [c_fp, c_fp],
     "dedf_build_arch": [],
 }
 

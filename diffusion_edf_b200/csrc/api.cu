@@ -76,3 +76,21 @@ extern "C" int dedf_prefetch_l2(const void* const* ptrs_dev, const long long* by
     if (cudaGetLastError() != cudaSuccess) return DEDF_ERR_LAUNCH;
     return DEDF_OK;
 }
+
+// Profiling aid (profiles/run_timeline.py): one thread writes %globaltimer (ns) to *slot.  Enqueued between the kernels of a forward
+// -- also under CUDA-graph capture -- it gives the in-graph timeline of both streams, which neither the serialised ncu launch list
+// nor eager per-call events show.  Never launched by the product path unless ops.TIMELINE is set.
+namespace dedf {
+__global__ void stamp_kernel(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
+}  // namespace dedf
+
+extern "C" int dedf_stamp(unsigned long long* slot, cudaStream_t stream) {
+    if (!slot) return DEDF_ERR_ARG;
+    dedf::stamp_kernel<<<1, 1, 0, stream>>>(slot);
+    if (cudaGetLastError() != cudaSuccess) return DEDF_ERR_LAUNCH;
+    return DEDF_OK;
+}

@@ -359,16 +359,29 @@ static void launch_radius(const RadiusArgs& a, long long items, int* counts, con
 }
 
 // single-CTA exclusive scan: row_ptr[0..n] from counts[0..n-1]
+// STAGED: the counts are first copied into shared memory with coalesced, independent loads (n <= kScanStageMax); every thread then
+// scans its contiguous chunk there.  The direct variant walked its chunk with one dependent global load per element: 59 us for the
+// 32 768 buckets of the 10k-point hash grid, all of it on the critical path in front of the first UNet block
+// (profiles/r2_s8_timeline_128_before.txt).
+constexpr int kScanStageMax = 48 * 1024;           // ints staged in shared memory (+ 1/32 padding): 198 KB
+__device__ __forceinline__ int scan_pad(int i) { return i + (i >> 5); }     // chunk starts of consecutive threads fall into different banks
+
+template <bool STAGED>
 __global__ void __launch_bounds__(1024, 1)
 exclusive_scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ row_ptr, int capacity,
                       int* __restrict__ n_edges_out, int* __restrict__ overflow) {
     pdl_wait(); pdl_launch();     // PDL: see common.cuh
+    extern __shared__ int s_all[];
     __shared__ int s_part[1024];
     const int tid = threadIdx.x;
     const int chunk = (n + 1023) / 1024;
     const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    if (STAGED) {
+        for (int i = tid; i < n; i += 1024) s_all[scan_pad(i)] = counts[i];
+        __syncthreads();
+    }
     int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += counts[i];
+    for (int i = lo; i < hi; ++i) sum += STAGED ? s_all[scan_pad(i)] : counts[i];
     s_part[tid] = sum;
     __syncthreads();
     // Hillis-Steele inclusive scan over 1024 partials
@@ -382,13 +395,29 @@ exclusive_scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ r
     // index past them and raise the overflow flag -- the host then re-plans with larger buffers.
     const int cap = capacity > 0 ? capacity : 0x7fffffff;
     int run = s_part[tid] - sum;
-    for (int i = lo; i < hi; ++i) { row_ptr[i] = min(run, cap); run += counts[i]; }
+    if (STAGED) {
+        for (int i = lo; i < hi; ++i) { const int c = s_all[scan_pad(i)]; s_all[scan_pad(i)] = min(run, cap); run += c; }
+        __syncthreads();
+        for (int i = tid; i < n; i += 1024) row_ptr[i] = s_all[scan_pad(i)];        // coalesced
+    } else {
+        for (int i = lo; i < hi; ++i) { row_ptr[i] = min(run, cap); run += counts[i]; }
+    }
     if (tid == 1023) {
         const int total = s_part[1023];
         row_ptr[n] = min(total, cap);
         if (n_edges_out) *n_edges_out = min(total, cap);
         if (overflow && total > cap) atomicOr(overflow, 1);
     }
+}
+
+static cudaError_t launch_scan(const int* counts, int n, int* row_ptr, int capacity, int* n_edges_out, int* overflow, cudaStream_t stream) {
+    if (n <= kScanStageMax && !getenv("DEDF_SCAN_DIRECT")) {
+        static bool done = false;
+        if (!done) { cudaFuncSetAttribute(exclusive_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kScanStageMax + kScanStageMax / 32 + 32) * 4); done = true; }
+        return launch_pdl(exclusive_scan_kernel<true>, dim3(1), dim3(1024), (size_t)(n + n / 32 + 32) * sizeof(int), stream, counts, n, row_ptr,
+                          capacity, n_edges_out, overflow);
+    }
+    return launch_pdl(exclusive_scan_kernel<false>, dim3(1), dim3(1024), 0, stream, counts, n, row_ptr, capacity, n_edges_out, overflow);
 }
 
 
@@ -426,12 +455,40 @@ __global__ void grid_fill_kernel(const float* __restrict__ x, int n, float inv_c
 }
 
 // one thread per bucket: order the bucket by source index (the atomics above fill it in arbitrary order) and lay the
-// coordinates out in the same order so that the query kernel streams them
+// coordinates out in the same order so that the query kernel streams them.  Buckets of up to kSortReg points are loaded with
+// independent loads, ordered in registers and written back once (the in-place insertion sort on global memory it replaces was a
+// chain of dependent loads / stores per element: 58 us for the 10k-point grid); larger buckets keep the in-place path.
+constexpr int kSortReg = 16;
 __global__ void grid_sort_kernel(const float* __restrict__ x, int n_buckets, const int* __restrict__ bucket_start,
                                  int* __restrict__ sorted_idx, float* __restrict__ sorted_xyz) {
     pdl_wait(); pdl_launch();     // PDL: see common.cuh
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += gridDim.x * blockDim.x) {
         const int s = bucket_start[b], e = bucket_start[b + 1];
+        const int k = e - s;
+        if (k <= 0) continue;
+        if (k <= kSortReg) {
+            int v[kSortReg];
+#pragma unroll
+            for (int i = 0; i < kSortReg; ++i) v[i] = (i < k) ? sorted_idx[s + i] : 0x7fffffff;
+            // odd-even transposition sort: fixed network, fully unrolled, registers only
+#pragma unroll
+            for (int pass = 0; pass < kSortReg; ++pass) {
+#pragma unroll
+                for (int i = pass & 1; i + 1 < kSortReg; i += 2) {
+                    const int lo = min(v[i], v[i + 1]), hi = max(v[i], v[i + 1]);
+                    v[i] = lo; v[i + 1] = hi;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kSortReg; ++i) {
+                if (i < k) {
+                    const int p = v[i];
+                    sorted_idx[s + i] = p;
+                    sorted_xyz[3 * (s + i)] = x[3 * p]; sorted_xyz[3 * (s + i) + 1] = x[3 * p + 1]; sorted_xyz[3 * (s + i) + 2] = x[3 * p + 2];
+                }
+            }
+            continue;
+        }
         for (int i = s + 1; i < e; ++i) {
             const int v = sorted_idx[i];
             int j = i - 1;
@@ -652,7 +709,7 @@ extern "C" int dedf_radius_count(const float* x_src, const float* x_dst, int n_d
         launch_radius<false>(a, items, counts, nullptr, nullptr, nullptr, stream);
         DEDF_CHECK_LAUNCH();
     }
-    launch_pdl(exclusive_scan_kernel, dim3(1), dim3(1024), 0, stream, counts, (int)items, row_ptr, capacity, n_edges_out, overflow);
+    launch_scan(counts, (int)items, row_ptr, capacity, n_edges_out, overflow, stream);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -696,7 +753,7 @@ extern "C" int dedf_grid_build(const float* x_src, int n_src, float r, int n_buc
     const unsigned mask = (unsigned)(n_buckets - 1);
     cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * n_buckets, stream);
     if (n_src > 0) { launch_pdl(grid_count_kernel, dim3(grid_for(n_src, 256, kNumSMs * 8)), dim3(256), 0, stream, x_src, n_src, inv_cell, mask, bucket_cnt); DEDF_CHECK_LAUNCH(); }
-    launch_pdl(exclusive_scan_kernel, dim3(1), dim3(1024), 0, stream, bucket_cnt, n_buckets, bucket_start, 0, nullptr, nullptr);
+    launch_scan(bucket_cnt, n_buckets, bucket_start, 0, nullptr, nullptr, stream);
     DEDF_CHECK_LAUNCH();
     cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * n_buckets, stream);
     if (n_src > 0) { launch_pdl(grid_fill_kernel, dim3(grid_for(n_src, 256, kNumSMs * 8)), dim3(256), 0, stream, x_src, n_src, inv_cell, mask, bucket_start, bucket_cnt, sorted_idx); DEDF_CHECK_LAUNCH(); }
@@ -715,7 +772,7 @@ extern "C" int dedf_radius_grid_count(const float* x_src, int n_src, const float
     if (rc) return rc;
     if (!counts || !row_ptr) return DEDF_ERR_ARG;
     if (n_dst > 0) { launch_pdl((radius_grid_kernel<false>), dim3(grid_for(n_dst, kGridWarps, kNumSMs * 4)), dim3(kGridWarps * 32), 0, stream, a, counts, nullptr, nullptr, nullptr); DEDF_CHECK_LAUNCH(); }
-    launch_pdl(exclusive_scan_kernel, dim3(1), dim3(1024), 0, stream, counts, n_dst, row_ptr, capacity, n_edges_out, overflow);
+    launch_scan(counts, n_dst, row_ptr, capacity, n_edges_out, overflow, stream);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

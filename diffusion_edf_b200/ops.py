@@ -80,6 +80,22 @@ def _call(name: str, *args) -> None:
 # ----------------------------------------------------------------------------
 # static plans: make a data-dependent forward replayable as a CUDA graph
 # ----------------------------------------------------------------------------
+TIMELINE = None     # profiling only (profiles/run_timeline.py): {"buf": int64 device tensor, "names": []}
+
+
+def stamp(name: str) -> None:
+    """Record %globaltimer at this point of the current stream into the next slot of ``TIMELINE`` (no-op when it is None)."""
+    tl = TIMELINE
+    if tl is None:
+        return
+    i = len(tl["names"])
+    if i >= tl["buf"].numel():
+        return
+    tl["names"].append((name, int(torch.cuda.current_stream().cuda_stream)))
+    rc = L.load().dedf_stamp(tl["buf"].data_ptr() + 8 * i, stream())
+    check(rc, "dedf_stamp")
+
+
 class Plan:
     """Host-side values a forward pass normally has to read back from the device (edge counts, batch layout), recorded
     once in an eager pass and then replayed, so that the same Python code runs without any host synchronisation and with

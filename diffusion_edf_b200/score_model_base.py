@@ -187,8 +187,22 @@ class ScoreModelBase(nn.Module):
         return dg.run(T, sources, grasp_pcd, rows, rows_all, noise, int(self.sample_seed))
 
     # ------------------------------------------------------------------ forward
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__["_param_cache"] = None               # .to() / .cuda() / .float(): storage moves
+        return super()._apply(fn, *args, **kwargs)
+
     def _param_signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Changes whenever a parameter is updated in place (optimizer step, load_state_dict: version counters only grow) or the
+        parameters move (first / last storage pointer).  Cheap on purpose: it is evaluated on EVERY forward to pick the cached CUDA
+        graph -- walking the module tree (733 tensors) cost 1.3 ms per call, a quarter of the C2 step (profiles/r2_s8_timeline_*)."""
+        ps = self.__dict__.get("_param_cache")
+        if ps is None:
+            ps = tuple(self.parameters())
+            self.__dict__["_param_cache"] = ps
+        v = 0
+        for p in ps:
+            v += p._version
+        return (len(ps), ps[0].data_ptr(), ps[-1].data_ptr(), v)
 
     def _weight_tensors(self):
         """Every tensor the kernels read as a weight: parameters plus the cached kernel-layout copies."""
@@ -229,10 +243,14 @@ class ScoreModelBase(nn.Module):
         ops.prefetch_l2(self._prefetch_tab[1])
 
     def _forward_tensors(self, Ts, time, kx, kf, kb, qx, qf, qb):
+        ops.stamp("forward start")
         self.prefetch_weights()
         key_ms = self._key_pcd_multiscale(FeaturedPoints(kx, kf, kb))
+        ops.stamp("key encoder done")
         q = self._query_pcd(FeaturedPoints(qx, qf, qb))
-        return self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)
+        out = self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)
+        ops.stamp("score head done")
+        return out
 
     def forward(self, Ts: torch.Tensor, time: torch.Tensor, key_pcd: FeaturedPoints, query_pcd: FeaturedPoints,
                 debug: bool = False):

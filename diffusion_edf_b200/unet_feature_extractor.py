@@ -13,7 +13,9 @@ Only the order in which a destination's edges are summed differs from the refere
 """
 from __future__ import annotations
 
+import contextlib
 import math
+import os
 from typing import List, Optional, Union
 
 import torch
@@ -105,6 +107,7 @@ class UnetFeatureExtractor(nn.Module):
                                               for n in range(self.n_scales)])
         self.overlap_geometry = True     # graph construction + radial MLPs on a side stream (see _geometry)
         self._side = None
+        self._fps_stream = None
 
     @staticmethod
     def _geom(x_src, x_dst, g) -> _Geom:
@@ -112,7 +115,7 @@ class UnetFeatureExtractor(nn.Module):
         return _Geom(g, length, sh)
 
     # ------------------------------------------------------------------ geometry pass (feature independent)
-    def _geometry(self, x: torch.Tensor, b: torch.Tensor, done):
+    def _geometry(self, x: torch.Tensor, b: torch.Tensor, done, fps_stream=None):
         """FPS pooling, radius graphs, edge geometry and the per-edge radial TP weights of EVERY block, in the order the
         feature pass consumes them.  Nothing here reads a feature, so forward() runs it on a side stream: after the first
         FPS the whole graph-construction / radial-MLP pipeline overlaps the attention blocks of the previous scales.
@@ -130,17 +133,43 @@ class UnetFeatureExtractor(nn.Module):
 
         levels = []          # per scale: (x_src, b_src, idx, x_dst, b_dst, self geom)
         geom = None
+        # The FPS chain of ALL scales first, on its own stream when there is one: level n + 1 only needs the coordinates level n
+        # picked, not its graphs / radial MLPs, and an FPS launch occupies 1-8 SMs.  In the in-graph timeline
+        # (profiles/r2_s8_timeline_128_before.txt) FPS 1-3 sat in the middle of the geometry chain and the main stream idled for them.
+        pooled = []
+        cur = torch.cuda.current_stream() if x.is_cuda else None
+        if fps_stream is not None:
+            fps_stream.wait_stream(cur)
+        xx, bb = x, b
+        for n in range(len(self.down_blocks)):
+            with torch.cuda.stream(fps_stream) if fps_stream is not None else contextlib.nullcontext():
+                idx = ops.fps(xx, bb, self.pool_ratio[n], random_start=not self.deterministic)
+                ops.stamp(f"geo fps{n}")
+                x_dst = ops.gather_rows(xx, idx)
+                b_dst = bb.index_select(0, idx)
+                ev = None
+                if fps_stream is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(fps_stream)
+                    for t in (idx, x_dst, b_dst):
+                        t.record_stream(cur)
+            pooled.append((idx, x_dst, b_dst, ev))
+            xx, bb = x_dst, b_dst
         for n, blk in enumerate(self.down_blocks):
-            idx = ops.fps(x, b, self.pool_ratio[n], random_start=not self.deterministic)
-            x_dst = ops.gather_rows(x, idx)
-            b_dst = b.index_select(0, idx)
+            idx, x_dst, b_dst, ev = pooled[n]
+            if ev is not None:
+                cur.wait_event(ev)
             g = ops.radius_csr(x, x_dst, [self.radius[n]], b_src=b, b_dst=b_dst, excl_mode=1, excl=idx, max_num_neighbors=1000)
             gp = self._geom(x, x_dst, g)
+            ops.stamp(f"geo pool-graph{n}")
             emit("pool", n=n, idx=idx, x_dst=x_dst, b_dst=b_dst, geom=gp, w=block(blk["pool_layer"], gp))
+            ops.stamp(f"geo pool-mlp{n}")
             g = ops.radius_csr(x_dst, x_dst, [self.radius[n]], b_src=b_dst, b_dst=b_dst, excl_mode=2, max_num_neighbors=1001)
             geom = self._geom(x_dst, x_dst, g)
+            ops.stamp(f"geo self-graph{n}")
             for layer in blk["layer_stack"]:
                 emit("self", geom=geom, w=block(layer, geom))
+            ops.stamp(f"geo self-mlps{n}")
             levels.append((x, b, idx, x_dst, b_dst, geom))
             x, b = x_dst, b_dst
         for layer in self.mid_block:
@@ -156,6 +185,7 @@ class UnetFeatureExtractor(nn.Module):
                                    max_num_neighbors=1000)
                 gu = self._geom(x_c, x_fine, g)
                 emit("unpool", geom=gu, w=block(blk["unpool_layer"], gu))
+                ops.stamp(f"geo unpool{scale}")
         return items
 
     def forward(self, pcd: FeaturedPoints) -> List[FeaturedPoints]:
@@ -165,7 +195,9 @@ class UnetFeatureExtractor(nn.Module):
         use_side = self.overlap_geometry and x.is_cuda
         if use_side:
             if self._side is None or self._side.device != x.device:
-                self._side = torch.cuda.Stream(device=x.device)
+                # high priority: the geometry chain is many small kernels the feature pass waits on; without it they queue behind the
+                # feature pass's chip-filling kernels (in-graph timeline: the main stream idled ~0.3 ms per forward for them)
+                self._side = torch.cuda.Stream(device=x.device, priority=-1 if os.environ.get("DEDF_GEOM_PRIO", "1") != "0" else 0)
             side = self._side
             side.wait_stream(main)                       # fork (inputs are ready on the main stream)
 
@@ -173,8 +205,10 @@ class UnetFeatureExtractor(nn.Module):
                 ev = torch.cuda.Event()
                 ev.record(side)
                 it["event"] = ev
+            if self._fps_stream is None or self._fps_stream.device != x.device:
+                self._fps_stream = torch.cuda.Stream(device=x.device, priority=-1 if os.environ.get("DEDF_GEOM_PRIO", "1") != "0" else 0)
             with torch.cuda.stream(side):
-                items = self._geometry(x, b, done)
+                items = self._geometry(x, b, done, self._fps_stream)
         else:
             items = self._geometry(x, b, lambda it: None)
         pos = [0]
@@ -196,7 +230,10 @@ class UnetFeatureExtractor(nn.Module):
 
         def run(layer, f_src, f_dst, it):
             gm = it["geom"]
-            return layer["gnn"](f_src, f_dst, gm.g, gm.sh, gm.length, layer["radial"], w=it["w"])
+            ops.stamp(f"blk start {it['kind']} n_dst={gm.g.n_dst}")
+            out = layer["gnn"](f_src, f_dst, gm.g, gm.sh, gm.length, layer["radial"], w=it["w"])
+            ops.stamp(f"blk end {it['kind']} n_dst={gm.g.n_dst}")
+            return out
 
         f = self.input_emb(pcd.f.contiguous())
         outs = [(f, x, b)]

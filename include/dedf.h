@@ -479,6 +479,10 @@ int dedf_flag_if_differs(const long long* a, const long long* b, long long n, in
  * implicitly); here the few-CTA kernels of the coarse UNet scales would otherwise pay DRAM latency per weight row. */
 int dedf_prefetch_l2(const void* const* ptrs_dev, const long long* bytes_dev, int n, cudaStream_t stream);
 
+/* Profiling aid: *slot = %globaltimer (ns) at this point of `stream` (capturable).  profiles/run_timeline.py enqueues it between the
+ * kernels of a forward to read the in-graph timeline of the main and the geometry stream. */
+int dedf_stamp(unsigned long long* slot, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
