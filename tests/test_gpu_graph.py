@@ -20,6 +20,42 @@ def test_fps_bitexact(cuda, n, ratio):
     assert torch.equal(got, ref), f"first mismatch at {(got != ref).nonzero()[:3].flatten().tolist()}"
 
 
+@pytest.mark.parametrize("kind", ["surface", "duplicates", "flat", "line", "clustered", "all_selected", "scene"])
+def test_fps_hard_clouds_bitexact(cuda, kind):
+    """FPS on clouds that stress the arg-max: surface-like and clustered clouds, exact duplicates (ties -> lowest index), degenerate
+    extents (a plane, a line), every point selected (ratio 1), the bench scene.  (Written for the round-2 bucketed / chunked FPS
+    experiments -- bit-exact but slower than the cluster kernel, DESIGN section 8 -- and kept for the kernels that ship.)"""
+    from diffusion_edf_b200 import ops
+    from diffusion_edf_b200.synthetic import make_scene
+    g = torch.Generator().manual_seed(17)
+    n, ratio = 6000, 0.2
+    if kind == "surface":
+        u = torch.rand(n, 2, generator=g) * 20
+        x = torch.stack([u[:, 0], u[:, 1], torch.sin(u[:, 0]) * torch.cos(u[:, 1])], dim=1)
+    elif kind == "duplicates":
+        x = torch.rand(n, 3, generator=g) * 10
+        x[1000:2000] = x[0:1000]
+        x[5000:5500] = x[2500]
+    elif kind == "flat":
+        x = torch.rand(n, 3, generator=g) * 10
+        x[:, 2] = 3.0
+    elif kind == "line":
+        x = torch.zeros(n, 3)
+        x[:, 0] = torch.rand(n, generator=g) * 100
+    elif kind == "clustered":
+        c = torch.rand(12, 3, generator=g) * 50
+        x = c[torch.randint(0, 12, (n,), generator=g)] + torch.randn(n, 3, generator=g) * 0.3
+    elif kind == "all_selected":
+        n, ratio = 2500, 1.0
+        x = torch.rand(n, 3, generator=g) * 5
+    else:
+        x, _ = make_scene(10_000, seed=0)
+    ref = OG.fps(x, None, ratio)
+    got = ops.fps(x.to(cuda), None, ratio).cpu()
+    assert got.shape == ref.shape
+    assert torch.equal(got, ref), f"{kind}: first mismatch at {(got != ref).nonzero()[:3].flatten().tolist()}"
+
+
 def test_fps_batched_and_duplicates(cuda):
     from diffusion_edf_b200 import ops
     g = torch.Generator().manual_seed(5)
