@@ -51,6 +51,29 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// Warp-uniform issue: the WHOLE warp runs the issue loop on warp-uniform values (so the descriptors live in uniform registers and
+// are advanced with uniform adds: no per-MMA R2UR chain) and the lane elected once up front issues under a predicate.  Measured
+// (profiles/run_tc_probe_swz.py, r2_s9_tc_probe_issue.txt): 40-45 cycles per M = 128, K = 8 MMA at N <= 48 and 64.7 at N = 128 --
+// the tensor pipe's N / 2 floor -- against ~65 (N <= 48) / ~111 (N = 128) for the single-thread loops with per-MMA descriptor math.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .pred px;\nelect.sync _|px, 0xffffffff;\nselp.u32 %0, 1, 0, px;\n}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void mma_tf32_if(uint32_t leader, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void commit_if(uint32_t leader, uint64_t* bar) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}"
+                 ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+
 // arrive on an mbarrier when every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

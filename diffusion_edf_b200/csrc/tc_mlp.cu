@@ -265,7 +265,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
         __syncwarp();
     } else if (warp == kTcMmaWarp) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // warp-uniform issue loop (tc.cuh: mma_tf32_if): all 32 lanes run it on uniform values (descriptors in uniform registers,
+        // no per-MMA R2UR chain), the lane elected here issues
+        {
+            const uint32_t leader = tc::elect_one();
             uint32_t st = 0, cmask = 0, pa = 0;            // cmask bit s: parity the next wait on full_bar[s] uses
             const uint32_t ring_bytes = (uint32_t)kTcStages * (uint32_t)a.stage_bytes;
             const uint32_t a_hi0 = smem_u32(sA_hi), a_lo0 = smem_u32(sA_lo), b0 = smem_u32(sB);
@@ -298,18 +301,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                             for (int c = 0; c < cps; ++c) {
                                 const uint64_t db_hi = tc::smem_desc(bs, (uint32_t)Nb * 16, 128);
                                 const uint64_t db_lo = tc::smem_desc(bs + (uint32_t)Nb * 32, (uint32_t)Nb * 16, 128);
-                                tc::mma_tf32(d, da_hi, db_hi, idesc, (kc + c) > 0);
-                                tc::mma_tf32(d, da_lo, db_hi, idesc, 1);
-                                tc::mma_tf32(d, da_hi, db_lo, idesc, 1);
+                                tc::mma_tf32_if(leader, d, da_hi, db_hi, idesc, (kc + c) > 0);
+                                tc::mma_tf32_if(leader, d, da_lo, db_hi, idesc, 1);
+                                tc::mma_tf32_if(leader, d, da_hi, db_lo, idesc, 1);
                                 da_hi += kAStep; da_lo += kAStep;
                                 bs += cbytes;
                             }
-                            tc::commit(&empty_bar[st]);                // stage reusable once these MMAs have read it
+                            tc::commit_if(leader, &empty_bar[st]);     // stage reusable once these MMAs have read it
                             if (++st == ns) st = 0;
                         }
                     }
-                    tc::commit(&layer_done);                           // the producer may re-cut the ring for the next layer
-                    tc::commit(&acc_ready);
+                    tc::commit_if(leader, &layer_done);                // the producer may re-cut the ring for the next layer
+                    tc::commit_if(leader, &acc_ready);
                     TC_STAMP(kTcMmaWarp * 32);
                 }
             }

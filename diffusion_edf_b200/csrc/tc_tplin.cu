@@ -319,7 +319,9 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
         __syncwarp();
     } else if (warp == kTaMmaWarp) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // warp-uniform issue loop (tc.cuh: mma_tf32_if): all 32 lanes run it, the lane elected here issues
+        {
+            const uint32_t leader = tc::elect_one();
             uint32_t st = 0, ph = 0;
             const uint32_t a_base = smem_u32(sA), w_base = smem_u32(sW);
             const uint32_t id0 = tc::idesc_tf32(128, kTaTE), id1 = tc::idesc_tf32(128, C::N1C), id2 = tc::idesc_tf32(128, C::N2P);
@@ -357,13 +359,13 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                             const uint32_t wo = C::W0Off + ks * 2 * (C::N0P * 16) + g * 128 * 16, ao = kA0Off + ks * 2 * (kR0 * 16);
                             const uint64_t dw = tc::smem_desc((p == 2 ? wl : wh) + wo, C::N0P * 16, 128);
                             const uint64_t da = tc::smem_desc((p == 1 ? al : ah) + ao, kR0 * 16, 128);
-                            tc::mma_tf32(d0 + C::T0 + g * kTaTE, dw, da, id0, acc);
+                            tc::mma_tf32_if(leader, d0 + C::T0 + g * kTaTE, dw, da, id0, acc);
                         } else {
                             const uint32_t a_off = (g == 2) ? kA1Off : kA2Off, lbo_a = (g == 2 ? kR1 : kR2) * 16;
                             const uint32_t w_off = (g == 2) ? C::W1Off : C::W2Off, lbo_w = (g == 2 ? C::N1C : C::N2P) * 16;
                             const uint64_t da = tc::smem_desc((p == 1 ? al : ah) + a_off + ks * 2 * lbo_a, lbo_a, 128);
                             const uint64_t dw = tc::smem_desc((p == 2 ? wl : wh) + w_off + ks * 2 * lbo_w, lbo_w, 128);
-                            tc::mma_tf32(d0 + (g == 2 ? C::T1 : C::T2A), da, dw, g == 2 ? id1 : id2, acc);
+                            tc::mma_tf32_if(leader, d0 + (g == 2 ? C::T1 : C::T2A), da, dw, g == 2 ? id1 : id2, acc);
                         }
                     };
                     constexpr int n0 = 3 * (kKC0 / 8), n12 = 3 * (kKC1 / 8);
@@ -373,14 +375,14 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                         issue(2, i);
                         issue(3, i);
                     }
-                    tc::commit(&emptyA[st]);
-                    tc::commit(&emptyW[st]);
+                    tc::commit_if(leader, &emptyA[st]);
+                    tc::commit_if(leader, &emptyW[st]);
                     tIssue += clock64() - ci;
                     if (++st == kTaStages) { st = 0; ph ^= 1u; }
                 }
-                tc::commit(&accFull[buf]);
+                tc::commit_if(leader, &accFull[buf]);
             }
-            if (a.dbg && blockIdx.x == 0) {      // host debug: where the MMA issuer of CTA 0 spent its cycles
+            if (leader && a.dbg && blockIdx.x == 0) {      // host debug: where the MMA issuer of CTA 0 spent its cycles
                 a.dbg[0] = clock64() - tStart; a.dbg[1] = wA; a.dbg[2] = wW; a.dbg[3] = wE; a.dbg[4] = tIssue; a.dbg[5] = it;
             }
         }
