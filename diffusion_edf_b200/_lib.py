@@ -16,7 +16,8 @@ MLP_MAX_LAYERS = 4
 MLP_IN_ROWS, MLP_IN_RBF, MLP_IN_FIELD = 0, 1, 2
 EPI_ACT, EPI_LIN = 0, 1
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdedf.so")
+# DEDF_LIB: another build of the SAME library (A/B runs of a kernel change under profiles/); never a fallback
+_LIB_PATH = os.environ.get("DEDF_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdedf.so")
 _lib: Optional[C.CDLL] = None
 
 c_fp = C.c_void_p

@@ -55,6 +55,7 @@ if rank == 0:
                       "metric": "pose-scores/sec (nPoses x steps)", "value": n_seeds * steps / float(tt), "unit": "pose-scores/s",
                       "n_gpus": world, "n_seeds": n_seeds, "steps": steps, "wall_s": float(tt), "ms_per_step": 1e3 * float(tt) / steps,
                       "scaling": "strong", "gpu_launches_rank0": ops.LAUNCHES - k0,
+                      "replans": [g.replans for g in model._denoise_graphs.values()], "capacity": [g.capacity for g in model._denoise_graphs.values()],
                       "final_quat_norm_err": float((traj[-1, :, :4].norm(dim=-1) - 1).abs().max())}))
 if world > 1:
     dist.destroy_process_group()
