@@ -162,21 +162,24 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
             const float* xd = a.x_dst ? a.x_dst + (size_t)dst * D::F : nullptr;
             const float* wr = a.w + (size_t)eg * a.w_stride;
             const float okf = ok ? 1.f : 0.f;
-            float4 xa, xb = make_float4(0.f, 0.f, 0.f, 0.f);
+            // the source and destination halves of a message slice stay in separate registers until stx() adds them: the adds (the
+            // first USE of the gathered values) then sit a whole chunk of math behind the loads instead of right after them
+            // (ncu source view: the producers' long-scoreboard samples were on exactly those adds)
+            float4 xa, xb = make_float4(0.f, 0.f, 0.f, 0.f), xad = make_float4(0.f, 0.f, 0.f, 0.f), xbd = make_float4(0.f, 0.f, 0.f, 0.f);
             auto ldx = [&](int j) {
                 const int oa = slice_off(j, sliceA);
                 xa = *reinterpret_cast<const float4*>(xs + oa);
-                if (xd) { const float4 t = *reinterpret_cast<const float4*>(xd + oa); xa.x += t.x; xa.y += t.y; xa.z += t.z; xa.w += t.w; }
+                if (xd) xad = *reinterpret_cast<const float4*>(xd + oa);
                 if (sliceB >= 0) {
                     const int ob = slice_off(j, sliceB);
                     xb = *reinterpret_cast<const float4*>(xs + ob);
-                    if (xd) { const float4 t = *reinterpret_cast<const float4*>(xd + ob); xb.x += t.x; xb.y += t.y; xb.z += t.z; xb.w += t.w; }
+                    if (xd) xbd = *reinterpret_cast<const float4*>(xd + ob);
                 }
             };
             auto stx = [&](int stage) {
                 float* row = s_x + (stage * kTaTE + e) * kTaXLd;
-                *reinterpret_cast<float4*>(row + 4 * sliceA) = make_float4(xa.x * okf, xa.y * okf, xa.z * okf, xa.w * okf);
-                if (sliceB >= 0) *reinterpret_cast<float4*>(row + 4 * sliceB) = make_float4(xb.x * okf, xb.y * okf, xb.z * okf, xb.w * okf);
+                *reinterpret_cast<float4*>(row + 4 * sliceA) = make_float4((xa.x + xad.x) * okf, (xa.y + xad.y) * okf, (xa.z + xad.z) * okf, (xa.w + xad.w) * okf);
+                if (sliceB >= 0) *reinterpret_cast<float4*>(row + 4 * sliceB) = make_float4((xb.x + xbd.x) * okf, (xb.y + xbd.y) * okf, (xb.z + xbd.z) * okf, (xb.w + xbd.w) * okf);
             };
             if (warp < 4) {
                 const int i = warp;
