@@ -27,7 +27,11 @@ inline int num_sms() {
 
 // return codes: DEDF_OK / DEDF_ERR_* of include/dedf.h
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// 1 / (1 + e^-x) with the hardware reciprocal (__fdividef: MUFU.RCP + one multiply, <= 2 ulp).  The IEEE division this replaced
+// compiled to a range check + BRANCH (+ a subroutine call on the slow path) per element: ~35 instructions and a reconvergence point
+// for every SiLU / gate, which made "activate + split + store" the longest phase of the tensor-core MLP's epilogues (5.7-6.2 k cycles
+// for 32 elements per thread; CTA-0 phase stamps, profiles/r2_s9_mlp_tc_timeline_128.txt).
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 // SmoothLeakyReLU(0.2): 0.6 x + 0.4 x (2 sigmoid(x) - 1)   (fast_activation.py:14-23)
 __device__ __forceinline__ float slreluf_(float x) { return 0.6f * x + 0.4f * x * (2.0f * sigmoidf_(x) - 1.0f); }
