@@ -57,20 +57,17 @@ fps_kernel(const float* __restrict__ x, int n, int m, int start, const long long
         float bv = 0.f;
 #pragma unroll
         for (int j = 0; j < PT; ++j) {
-            if (tid + j * kFpsThreads < n) {
-                const float d = sqdist_exact(px[j], py[j], pz[j], cx, cy, cz);
-                dist[j] = fminf(dist[j], d);
-            }
+            const float d = sqdist_exact(px[j], py[j], pz[j], cx, cy, cz);      // padding: dist = 0 stays 0 (see fps_cluster_kernel)
+            dist[j] = fminf(dist[j], d);
             bv = fmaxf(bv, dist[j]);
         }
         // distances are >= 0, so their bit patterns order like unsigned integers
-        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(bv));
-        int cand = 0x7fffffff;
-        if (__float_as_uint(bv) == wm) {
+        int mine = 0x7fffffff;
 #pragma unroll
-            for (int j = PT - 1; j >= 0; --j)
-                if (__float_as_uint(dist[j]) == wm) cand = tid + j * kFpsThreads;   // lowest index among this thread's ties
-        }
+        for (int j = PT - 1; j >= 0; --j)
+            if (dist[j] == bv) mine = tid + j * kFpsThreads;                        // lowest index among this thread's ties
+        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(bv));
+        const int cand = (__float_as_uint(bv) == wm) ? mine : 0x7fffffff;
         const int wi = __reduce_min_sync(0xffffffffu, cand);
         const int buf = it & 1;
         if (lane == 0) { s_val[buf][warp] = wm; s_idx[buf][warp] = wi; }
@@ -138,20 +135,21 @@ fps_cluster_kernel(const float* __restrict__ x, int n, int m, int start, const l
         float bv = 0.f;
 #pragma unroll
         for (int j = 0; j < PT; ++j) {
-            if (gtid + j * STRIDE < n) {
-                const float d = sqdist_exact(px[j], py[j], pz[j], cx, cy, cz);
-                dist[j] = fminf(dist[j], d);
-            }
+            // no bounds test: a padding slot has dist = 0 and fminf(0, d) = 0 for every d >= 0 -- the per-point branch put each of
+            // the PT updates into its own reconvergence region, i.e. serialised five dependent FADD/FMUL chains per iteration
+            const float d = sqdist_exact(px[j], py[j], pz[j], cx, cy, cz);
+            dist[j] = fminf(dist[j], d);
             bv = fmaxf(bv, dist[j]);
         }
-        // distances are >= 0, so their bit patterns order like unsigned integers
-        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(bv));
-        int cand = kFpsClusterMaxN - 1;
-        if (__float_as_uint(bv) == wm) {
+        // distances are >= 0, so their bit patterns order like unsigned integers.  The thread's own candidate (lowest index among
+        // ITS maxima) does not depend on the warp maximum: it is computed in the shadow of the first REDUX, and only one
+        // compare + select sits between the two reductions.
+        int mine = kFpsClusterMaxN - 1;
 #pragma unroll
-            for (int j = PT - 1; j >= 0; --j)
-                if (__float_as_uint(dist[j]) == wm) cand = gtid + j * STRIDE;
-        }
+        for (int j = PT - 1; j >= 0; --j)
+            if (dist[j] == bv) mine = gtid + j * STRIDE;
+        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(bv));
+        const int cand = (__float_as_uint(bv) == wm) ? mine : kFpsClusterMaxN - 1;
         const int wi = __reduce_min_sync(0xffffffffu, cand);
         // key: larger distance first, then LOWER index (stored complemented so that one max picks both), then the tag
         const unsigned long long tag = (unsigned long long)it & TAG_MASK;
