@@ -259,11 +259,13 @@ def radius_csr(x_src: torch.Tensor, x_dst: torch.Tensor, radii: Sequence[Optiona
         r = float(radii[0])
         _call("dedf_grid_build", ptr(x_src), n_src, r, n_buckets, ptr(bucket_cnt, torch.int32), ptr(bucket_start, torch.int32),
               ptr(sorted_idx, torch.int32), ptr(sorted_xyz), stream())
+        stamp(f"  grid built n_src={n_src}")
         gargs = (ptr(x_src), n_src, ptr(x_dst), n_dst, r, n_buckets, ptr(bucket_start, torch.int32), ptr(sorted_idx, torch.int32),
                  ptr(sorted_xyz), pb_s, pb_d, excl_mode, pex, max_num_neighbors)
         cap = max(1, int(capacity)) if capacity is not None else 0
         _call("dedf_radius_grid_count", *gargs, ptr(counts, torch.int32), ptr(row_ptr, torch.int32), cap, None,
               ptr(overflow, torch.int32) if capacity is not None else None, stream())
+        stamp(f"  grid counted n_dst={n_dst}")
         if capacity is None:
             n_edges_dev = row_ptr[-1:]
             n_edges = plan_value(lambda: int(n_edges_dev.item()))
@@ -273,6 +275,7 @@ def radius_csr(x_src: torch.Tensor, x_dst: torch.Tensor, radii: Sequence[Optiona
         edge_src = torch.empty(max(1, n_alloc), dtype=torch.int32, device=dev)
         edge_dst = torch.empty(max(1, n_alloc), dtype=torch.int32, device=dev)
         _call("dedf_radius_grid_fill", *gargs, ptr(row_ptr, torch.int32), ptr(edge_src, torch.int32), ptr(edge_dst, torch.int32), stream())
+        stamp(f"  grid filled n_dst={n_dst}")
         return Csr(row_ptr, edge_src[:n_edges], edge_dst[:n_edges], row_ptr[-1:], n_edges, n_dst, 1)
     if capacity is not None:
         capacity = max(1, int(capacity))
