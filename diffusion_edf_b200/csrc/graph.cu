@@ -452,51 +452,15 @@ __global__ void grid_fill_kernel(const float* __restrict__ x, int n, float inv_c
     }
 }
 
-// one thread per bucket: order the bucket by source index (the atomics above fill it in arbitrary order) and lay the
-// coordinates out in the same order so that the query kernel streams them.  Buckets of up to kSortReg points are loaded with
-// independent loads, ordered in registers and written back once (the in-place insertion sort on global memory it replaces was a
-// chain of dependent loads / stores per element: 58 us for the 10k-point grid); larger buckets keep the in-place path.
-constexpr int kSortReg = 16;
-__global__ void grid_sort_kernel(const float* __restrict__ x, int n_buckets, const int* __restrict__ bucket_start,
-                                 int* __restrict__ sorted_idx, float* __restrict__ sorted_xyz) {
+// Lay the coordinates out in bucket order so that the query kernel streams them.  The order INSIDE a bucket is whatever the fill
+// atomics produced: the query kernel sorts every destination's hit list by source index anyway, so the CSR does not depend on it.
+// (Until the end of round 2 a thread per bucket insertion-sorted its bucket in global memory first: with cell = r a bucket of the
+// coarser scales holds dozens of points, and that sort was 40-76 us per grid -- 124 us per forward -- of purely redundant work.)
+__global__ void grid_gather_kernel(const float* __restrict__ x, int n, const int* __restrict__ sorted_idx, float* __restrict__ sorted_xyz) {
     pdl_wait(); pdl_launch();     // PDL: see common.cuh
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += gridDim.x * blockDim.x) {
-        const int s = bucket_start[b], e = bucket_start[b + 1];
-        const int k = e - s;
-        if (k <= 0) continue;
-        if (k <= kSortReg) {
-            int v[kSortReg];
-#pragma unroll
-            for (int i = 0; i < kSortReg; ++i) v[i] = (i < k) ? sorted_idx[s + i] : 0x7fffffff;
-            // odd-even transposition sort: fixed network, fully unrolled, registers only
-#pragma unroll
-            for (int pass = 0; pass < kSortReg; ++pass) {
-#pragma unroll
-                for (int i = pass & 1; i + 1 < kSortReg; i += 2) {
-                    const int lo = min(v[i], v[i + 1]), hi = max(v[i], v[i + 1]);
-                    v[i] = lo; v[i + 1] = hi;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < kSortReg; ++i) {
-                if (i < k) {
-                    const int p = v[i];
-                    sorted_idx[s + i] = p;
-                    sorted_xyz[3 * (s + i)] = x[3 * p]; sorted_xyz[3 * (s + i) + 1] = x[3 * p + 1]; sorted_xyz[3 * (s + i) + 2] = x[3 * p + 2];
-                }
-            }
-            continue;
-        }
-        for (int i = s + 1; i < e; ++i) {
-            const int v = sorted_idx[i];
-            int j = i - 1;
-            while (j >= s && sorted_idx[j] > v) { sorted_idx[j + 1] = sorted_idx[j]; --j; }
-            sorted_idx[j + 1] = v;
-        }
-        for (int i = s; i < e; ++i) {
-            const int v = sorted_idx[i];
-            sorted_xyz[3 * i] = x[3 * v]; sorted_xyz[3 * i + 1] = x[3 * v + 1]; sorted_xyz[3 * i + 2] = x[3 * v + 2];
-        }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int v = sorted_idx[i];
+        sorted_xyz[3 * i] = x[3 * v]; sorted_xyz[3 * i + 1] = x[3 * v + 1]; sorted_xyz[3 * i + 2] = x[3 * v + 2];
     }
 }
 
@@ -759,7 +723,7 @@ extern "C" int dedf_grid_build(const float* x_src, int n_src, float r, int n_buc
     DEDF_CHECK_LAUNCH();
     cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * n_buckets, stream);
     if (n_src > 0) { launch_pdl(grid_fill_kernel, dim3(grid_for(n_src, 256, kNumSMs * 8)), dim3(256), 0, stream, x_src, n_src, inv_cell, mask, bucket_start, bucket_cnt, sorted_idx); DEDF_CHECK_LAUNCH(); }
-    launch_pdl(grid_sort_kernel, dim3(grid_for(n_buckets, 256, kNumSMs * 8)), dim3(256), 0, stream, x_src, n_buckets, bucket_start, sorted_idx, sorted_xyz);
+    if (n_src > 0) launch_pdl(grid_gather_kernel, dim3(grid_for(n_src, 256, kNumSMs * 8)), dim3(256), 0, stream, x_src, n_src, sorted_idx, sorted_xyz);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
