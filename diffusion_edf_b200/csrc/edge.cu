@@ -676,6 +676,11 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
     w0[0] = a.wv[D::W_K0 + ch0]; w0[1] = a.wv[D::W_K1 + ch0]; w0[2] = a.wv[D::W_K2 + ch0];
 #pragma unroll
     for (int i = 0; i < 6; ++i) { w1[i] = a.wv[D::W_K3 + ch1 + i * D::M1]; w2[i] = a.wv[D::W_K9 + ch2 + i * D::M2]; }
+    // The tensor-product weights of the value path are SHARED (sep_value.dtp.tp.weight, one per path and channel, the same for every
+    // edge), so  sum_e alpha_e w_p cg_p(x_e, sh_e) = w_p sum_e alpha_e cg_p(x_e, sh_e):  the edge loop runs with unit weights and the
+    // path weights are applied ONCE per destination when the reduced outputs are written (one multiply per output instead of one per
+    // output and edge: ~15 % of the loop's FP instructions, and 15 registers that are no longer live across it).
+    const float kOnes[6] = {1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f};
     if (tid == 0) {
         mbar_init(&bar, 1); mbar_init(&vbar, 1);
         mbar_init_fence();
@@ -808,7 +813,7 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
                     const float x = ok ? s_v[e * D::F + ch0] : 0.f;
                     const float al0 = ok ? s_lg[e * 4 + 2 * hp] : 0.f, al1 = ok ? s_lg[e * 4 + 2 * hp + 1] : 0.f;
                     float o[9];
-                    dtp_l0(x, w0[0], w0[1], w0[2], s_sh + (ok ? e : 0) * 12, o);
+                    dtp_l0(x, 1.0f, 1.0f, 1.0f, s_sh + (ok ? e : 0) * 12, o);
 #pragma unroll
                     for (int k = 0; k < 9; ++k) { acc0[0][k] = fmaf(al0, o[k], acc0[0][k]); acc0[1][k] = fmaf(al1, o[k], acc0[1][k]); }
                 }
@@ -820,7 +825,7 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
                     const float xv[3] = {ok ? xs[0] : 0.f, ok ? xs[1] : 0.f, ok ? xs[2] : 0.f};
                     const float al0 = ok ? s_lg[e * 4 + 2 * hp] : 0.f, al1 = ok ? s_lg[e * 4 + 2 * hp + 1] : 0.f;
                     float o[20];
-                    dtp_l1(xv, w1, s_sh + (ok ? e : 0) * 12, o);
+                    dtp_l1(xv, kOnes, s_sh + (ok ? e : 0) * 12, o);
 #pragma unroll
                     for (int k = 0; k < 20; ++k) { acc1[0][k] = fmaf(al0, o[k], acc1[0][k]); acc1[1][k] = fmaf(al1, o[k], acc1[1][k]); }
                 }
@@ -833,7 +838,7 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
                     for (int i = 0; i < 5; ++i) xv[i] = ok ? xs[i] : 0.f;
                     const float al0 = ok ? s_lg[e * 4 + 2 * hp] : 0.f, al1 = ok ? s_lg[e * 4 + 2 * hp + 1] : 0.f;
                     float o[22];
-                    dtp_l2(xv, w2, s_sh + (ok ? e : 0) * 12, o);
+                    dtp_l2(xv, kOnes, s_sh + (ok ? e : 0) * 12, o);
 #pragma unroll
                     for (int k = 0; k < 22; ++k) { acc2[0][k] = fmaf(al0, o[k], acc2[0][k]); acc2[1][k] = fmaf(al1, o[k], acc2[1][k]); }
                 }
@@ -856,31 +861,31 @@ __global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs 
         for (int h = 0; h < 2; ++h) {
             float* Dh = s_D + (size_t)(2 * hp + h) * D::FOUT;
             if (lane < 16) {
-                Dh[D::C0_K0 + ch0] = acc0[h][0];
+                Dh[D::C0_K0 + ch0] = acc0[h][0] * w0[0];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) Dh[B1 + (D::C1_K1 + ch0) * 3 + k] = acc0[h][1 + k];
+                for (int k = 0; k < 3; ++k) Dh[B1 + (D::C1_K1 + ch0) * 3 + k] = acc0[h][1 + k] * w0[1];
 #pragma unroll
-                for (int k = 0; k < 5; ++k) Dh[B2 + (D::C2_K2 + ch0) * 5 + k] = acc0[h][4 + k];
+                for (int k = 0; k < 5; ++k) Dh[B2 + (D::C2_K2 + ch0) * 5 + k] = acc0[h][4 + k] * w0[2];
             }
             if (lane < 8) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    Dh[B1 + (D::C1_K3 + ch1) * 3 + k] = acc1[h][k]; Dh[B1 + (D::C1_K5 + ch1) * 3 + k] = acc1[h][4 + k];
-                    Dh[B1 + (D::C1_K7 + ch1) * 3 + k] = acc1[h][12 + k];
+                    Dh[B1 + (D::C1_K3 + ch1) * 3 + k] = acc1[h][k] * w1[0]; Dh[B1 + (D::C1_K5 + ch1) * 3 + k] = acc1[h][4 + k] * w1[2];
+                    Dh[B1 + (D::C1_K7 + ch1) * 3 + k] = acc1[h][12 + k] * w1[4];
                 }
-                Dh[D::C0_K4 + ch1] = acc1[h][3];
+                Dh[D::C0_K4 + ch1] = acc1[h][3] * w1[1];
 #pragma unroll
-                for (int k = 0; k < 5; ++k) { Dh[B2 + (D::C2_K6 + ch1) * 5 + k] = acc1[h][7 + k]; Dh[B2 + (D::C2_K8 + ch1) * 5 + k] = acc1[h][15 + k]; }
+                for (int k = 0; k < 5; ++k) { Dh[B2 + (D::C2_K6 + ch1) * 5 + k] = acc1[h][7 + k] * w1[3]; Dh[B2 + (D::C2_K8 + ch1) * 5 + k] = acc1[h][15 + k] * w1[5]; }
             }
             if (lane < 4) {
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
-                    Dh[B2 + (D::C2_K9 + ch2) * 5 + k] = acc2[h][k]; Dh[B2 + (D::C2_K11 + ch2) * 5 + k] = acc2[h][8 + k];
-                    Dh[B2 + (D::C2_K14 + ch2) * 5 + k] = acc2[h][17 + k];
+                    Dh[B2 + (D::C2_K9 + ch2) * 5 + k] = acc2[h][k] * w2[0]; Dh[B2 + (D::C2_K11 + ch2) * 5 + k] = acc2[h][8 + k] * w2[2];
+                    Dh[B2 + (D::C2_K14 + ch2) * 5 + k] = acc2[h][17 + k] * w2[5];
                 }
 #pragma unroll
-                for (int k = 0; k < 3; ++k) { Dh[B1 + (D::C1_K10 + ch2) * 3 + k] = acc2[h][5 + k]; Dh[B1 + (D::C1_K13 + ch2) * 3 + k] = acc2[h][14 + k]; }
-                Dh[D::C0_K12 + ch2] = acc2[h][13];
+                for (int k = 0; k < 3; ++k) { Dh[B1 + (D::C1_K10 + ch2) * 3 + k] = acc2[h][5 + k] * w2[1]; Dh[B1 + (D::C1_K13 + ch2) * 3 + k] = acc2[h][14 + k] * w2[4]; }
+                Dh[D::C0_K12 + ch2] = acc2[h][13] * w2[3];
             }
         }
         if (v_pending) { mbar_wait(&vbar, 0); v_pending = false; }
