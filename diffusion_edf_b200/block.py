@@ -77,7 +77,7 @@ class UnetEquiformerBlock(nn.Module):
         return w
 
     def forward(self, f_src: torch.Tensor, f_dst: torch.Tensor, g: ops.Csr, sh: torch.Tensor, length: torch.Tensor,
-                radial: GaussianRadialBasisLayerFiniteCutoff, w: Optional[torch.Tensor] = None) -> torch.Tensor:
+                radial: GaussianRadialBasisLayerFiniteCutoff, w: Optional[torch.Tensor] = None, w_ready=None) -> torch.Tensor:
         ms = list(self.irreps_src.m) + list(self.irreps_dst.m) + list(self.irreps_emb.m)
         if ops.USE_LINEAR_PAIR and all(m > 0 and m % 4 == 0 for m in ms):
             (Ws, bs), (Wd, bd) = self.linear_src.packed(), self.linear_dst.packed()
@@ -88,6 +88,8 @@ class UnetEquiformerBlock(nn.Module):
             msg_dst = self.linear_dst(f_dst)
         if w is None:
             w = self.radial_weights(g, length, radial)
+        elif w_ready is not None:
+            w_ready()        # ``w`` is produced on another stream: the caller's wait, placed after the node linears
         attn = self.ga.attend(msg_src, msg_dst, g, sh, w, None)
         return node_tail(self.ga.proj, self.norm_2, self.ffn, attn, f_dst)
 

@@ -161,6 +161,7 @@ __device__ __forceinline__ void mbar_init_fence() {
 // global -> shared bulk copy of `bytes` (multiple of 16, both sides 16-byte aligned) in chunks the tx-count can hold
 __device__ __forceinline__ void bulk_g2s_chunked(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     constexpr uint32_t kChunk = 32768;
+#pragma unroll 1       // one thread issues a handful of copies: unrolled, these loops were a quarter of node_chain_kernel's code
     for (uint32_t o = 0; o < bytes; o += kChunk)
         bulk_g2s(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, min(kChunk, bytes - o), bar);
 }

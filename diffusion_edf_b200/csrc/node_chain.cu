@@ -13,7 +13,8 @@
 // shared memory by TMA bulk copies issued BEFORE the PDL wait (they are parameters): for `64x0e+32x1e+16x2e` that is
 // 21.5 + 101 + 64.5 KB, so the proj weights share their region with the FFN intermediates and are re-fetched (from L2) per
 // tile; everything else stays resident for the CTA's lifetime.  The arithmetic and its summation order are those of
-// node_linear_tma_kernel (same gemm_item_4x4 micro-kernel, K ascending), so results are bit-identical to the un-fused path.
+// node_linear_tma_kernel (same gemm_item_4x4 micro-kernel, K ascending), so results are bit-identical to the un-fused path
+// for the 8- and 16-node tiles; the 4-node tiles of small launches split K over four lanes (chain_gemm_splitk below).
 #include "common.cuh"
 #include "gemm_tile.cuh"
 #include "../../include/dedf.h"
@@ -21,6 +22,15 @@
 namespace dedf {
 
 constexpr int kChainThreads = 256;
+
+// -DDEDF_CHAIN_TRACE (profiles/run_chain_trace.py builds its own copy of the library with it): thread 0 of CTA 0 stamps clock64()
+// at every phase boundary into a device array that dedf_chain_trace() copies out.  Not compiled into the shipped library.
+#ifdef DEDF_CHAIN_TRACE
+__device__ long long g_chain_trace[32];
+#define CHAIN_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_chain_trace[i] = clock64(); } while (0)
+#else
+#define CHAIN_STAMP(i) do { } while (0)
+#endif
 
 struct ChainArgs {
     const float* x; int n;
@@ -36,9 +46,12 @@ struct ChainArgs {
     int o_wp, o_x, o_res;                 // inside the U region (proj phase)
     int o_o0, o_m;                        // inside the U region (FFN phases)
     int wp_transient;                     // the proj weights are overwritten by the FFN phase: re-fetch them per tile
+    int o_par;                            // biases + layer-norm affine parameters: [pb m0][ab pre.m0][bb m0][ln_w nirr][ln_b m0]
 };
 
-// block-diagonal GEMM over the three l blocks; epi(l, r, k, c, v): node row r, harmonic index k, output channel c
+// block-diagonal GEMM over the three l blocks; epi(l, r, k, c, v): node row r, harmonic index k, output channel c.
+// The l block of an item only selects pointers and sizes: ONE inlined copy of the micro-kernel and of the epilogue per GEMM (three
+// copies, one per l, made the kernel 10.7 k instructions that each CTA runs once -- instruction fetch of straight-line code).
 template <int TN, typename Epi>
 __device__ __forceinline__ void chain_gemm(const float* A0, int lda0, const float* A1, int lda1, const float* A2, int lda2,
                                            const float* W0, const float* W1, const float* W2, Irr in, Irr out, Epi epi) {
@@ -46,29 +59,76 @@ __device__ __forceinline__ void chain_gemm(const float* A0, int lda0, const floa
     const int I0 = (TN / 4) * cg0, I1 = (3 * TN / 4) * cg1, I2 = (5 * TN / 4) * cg2;
     for (int item = threadIdx.x; item < I0 + I1 + I2; item += kChainThreads) {
         float acc[4][4] = {};
-        if (item < I0) {
-            const int cg = item % cg0, rg = item / cg0;
-            gemm_item_4x4<true, true>(A0, lda0, TN / 4, rg, W0, out.m0, 4 * cg, in.m0, acc);
+        int l, cg, rg, lda, nrg, N, K; const float* A; const float* W;
+        if (item < I0) { l = 0; cg = item % cg0; rg = item / cg0; A = A0; lda = lda0; nrg = TN / 4; W = W0; N = out.m0; K = in.m0; }
+        else if (item < I0 + I1) { const int t = item - I0; l = 1; cg = t % cg1; rg = t / cg1; A = A1; lda = lda1; nrg = 3 * TN / 4; W = W1; N = out.m1; K = in.m1; }
+        else { const int t = item - I0 - I1; l = 2; cg = t % cg2; rg = t / cg2; A = A2; lda = lda2; nrg = 5 * TN / 4; W = W2; N = out.m2; K = in.m2; }
+        gemm_item_4x4<true, true>(A, lda, nrg, rg, W, N, 4 * cg, K, acc);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) {
+            const int row = rg + i * nrg, r = row % TN, k = row / TN;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) epi(0, rg + i * (TN / 4), 0, 4 * cg + j, acc[i][j]);
-        } else if (item < I0 + I1) {
-            const int t = item - I0, cg = t % cg1, rg = t / cg1;
-            gemm_item_4x4<true, true>(A1, lda1, 3 * TN / 4, rg, W1, out.m1, 4 * cg, in.m1, acc);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const int row = rg + i * (3 * TN / 4); epi(1, row % TN, row / TN, 4 * cg + j, acc[i][j]); }
-        } else {
-            const int t = item - I0 - I1, cg = t % cg2, rg = t / cg2;
-            gemm_item_4x4<true, true>(A2, lda2, 5 * TN / 4, rg, W2, out.m2, 4 * cg, in.m2, acc);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const int row = rg + i * (5 * TN / 4); epi(2, row % TN, row / TN, 4 * cg + j, acc[i][j]); }
+            for (int j = 0; j < 4; ++j) epi(l, r, k, 4 * cg + j, acc[i][j]);
         }
     }
+}
+
+// Few-node tiles (TN = 4: at most 2 x SMs nodes in the whole launch, e.g. the coarse UNet scales and a 128-pose denoise step): the
+// launch is ONE round of latency, and with one 4 x 4 item per thread only 60 of 256 threads had work in the emb -> emb GEMMs while
+// one warp walked K = 192 alone (warm-cache ncu, profiles/r2_s11_node_chain_*: 30 % of the kernel waiting for that warp).  Here KS
+// adjacent lanes split an item's K range (k4-steps partitioned evenly, each slice K ascending) and add their partial sums with two
+// butterfly shuffles -- (s0 + s1) + (s2 + s3): not the summation order of node_linear_tma_kernel any more (1 ulp-level differences).
+template <int TN, int KS, typename Epi>
+__device__ __forceinline__ void chain_gemm_splitk(const float* A0, int lda0, const float* A1, int lda1, const float* A2, int lda2,
+                                                  const float* W0, const float* W1, const float* W2, Irr in, Irr out, Epi epi) {
+    static_assert(KS == 4, "two butterfly rounds");
+    const int cg0 = out.m0 >> 2, cg1 = out.m1 >> 2, cg2 = out.m2 >> 2;
+    const int I0 = (TN / 4) * cg0, I1 = (3 * TN / 4) * cg1, I2 = (5 * TN / 4) * cg2;
+    const int total = I0 + I1 + I2;
+    const int ks = threadIdx.x & (KS - 1);
+    constexpr int kItemsPerRound = kChainThreads / KS;
+    const int rounds = (total + kItemsPerRound - 1) / kItemsPerRound;
+    for (int rd = 0; rd < rounds; ++rd) {                       // warp-uniform trip count: every lane takes part in the shuffles
+        const int item = rd * kItemsPerRound + (threadIdx.x >> 2);
+        float acc[4][4] = {};
+        int l = -1, cg = 0, rg = 0;
+        if (item < total) {
+            const float* A; const float* W; int lda, nrg, N, K;
+            if (item < I0) { l = 0; cg = item % cg0; rg = item / cg0; A = A0; lda = lda0; nrg = TN / 4; W = W0; N = out.m0; K = in.m0; }
+            else if (item < I0 + I1) { const int t = item - I0; l = 1; cg = t % cg1; rg = t / cg1; A = A1; lda = lda1; nrg = 3 * TN / 4; W = W1; N = out.m1; K = in.m1; }
+            else { const int t = item - I0 - I1; l = 2; cg = t % cg2; rg = t / cg2; A = A2; lda = lda2; nrg = 5 * TN / 4; W = W2; N = out.m2; K = in.m2; }
+            const int k4 = K >> 2, lo = 4 * ((k4 * ks) / KS), hi = 4 * ((k4 * (ks + 1)) / KS);
+            if (hi > lo) gemm_item_4x4<true, true>(A + lo, lda, nrg, rg, W + (size_t)lo * N, N, 4 * cg, hi - lo, acc);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = acc[i][j];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                acc[i][j] = v;
+            }
+        if (l < 0) continue;
+        // every lane of the quad holds the sums: lane ks writes row-group member ks (4 of the 16 outputs each)
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = ks == 0 ? acc[0][j] : ks == 1 ? acc[1][j] : ks == 2 ? acc[2][j] : acc[3][j];
+        const int nrg = l == 0 ? TN / 4 : l == 1 ? 3 * TN / 4 : 5 * TN / 4;
+        const int row = rg + ks * nrg;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) epi(l, row % TN, row / TN, 4 * cg + j, o[j]);
+    }
+}
+
+// SPLIT: the emb -> emb and mid -> emb GEMMs (60 items for the 240-dim irreps, K up to 192).  emb -> pre has 216 items of K <= 64:
+// splitting it costs four rounds of shuffles + epilogues instead of one K loop (clock64 phase trace, profiles/run_chain_trace.py:
+// 12.3 k cycles split against ~6 k whole).
+template <int TN, bool SPLIT, typename Epi>
+__device__ __forceinline__ void chain_gemm_any(const float* A0, int lda0, const float* A1, int lda1, const float* A2, int lda2,
+                                               const float* W0, const float* W1, const float* W2, Irr in, Irr out, Epi epi) {
+    if constexpr (TN == 4 && SPLIT) chain_gemm_splitk<TN, 4>(A0, lda0, A1, lda1, A2, lda2, W0, W1, W2, in, out, epi);
+    else chain_gemm<TN>(A0, lda0, A1, lda1, A2, lda2, W0, W1, W2, in, out, epi);
 }
 
 template <int TN>
@@ -76,6 +136,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) node_chain_kernel(ChainArgs 
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t w1bar, w2bar, wpbar, xbar, rbar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    CHAIN_STAMP(0);
     const Irr emb = a.emb, pre = a.pre, mid = a.mid;
     const int F = emb.dim();
     const int lda0 = pad_lda(emb.m0), lda1 = pad_lda(emb.m1), lda2 = pad_lda(emb.m2);
@@ -114,7 +175,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) node_chain_kernel(ChainArgs 
             bulk_g2s_chunked(sW2 + nB0 + nB1, a.B2, (uint32_t)nB2 * 4u, &w2bar);
         }
     }
+    // biases and layer-norm parameters -> shared memory (parameters: read before the PDL wait; the epilogues and the LN pass then
+    // take them at shared-memory latency instead of one L2 round trip per phase on the critical path of a one-tile CTA)
+    float* s_pb = smem + a.o_par; float* s_ab = s_pb + emb.m0; float* s_bb = s_ab + pre.m0;
+    float* s_lnw = s_bb + emb.m0; float* s_lnb = s_lnw + emb.nirr();
+    if (has_tile && tid >= 32) {          // (warp 0 is busy issuing the bulk copies)
+        constexpr int NT = kChainThreads - 32;
+        for (int c = tid - 32; c < emb.m0; c += NT) { s_pb[c] = a.pb ? a.pb[c] : 0.f; s_bb[c] = a.bb ? a.bb[c] : 0.f; s_lnb[c] = a.ln_b[c]; }
+        for (int c = tid - 32; c < pre.m0; c += NT) s_ab[c] = a.ab ? a.ab[c] : 0.f;
+        for (int c = tid - 32; c < emb.nirr(); c += NT) s_lnw[c] = a.ln_w[c];
+    }
+    CHAIN_STAMP(1);
     pdl_wait(); pdl_launch();     // PDL: barrier init and the weight copies above overlap the previous kernel's tail
+    CHAIN_STAMP(2);
     const int m0s = mid.m0;       // scalars that survive the gate
     uint32_t ph = 0, php = 0;
     bool first = true;
@@ -132,6 +205,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) node_chain_kernel(ChainArgs 
             }
         }
         mbar_wait(&xbar, ph);
+        CHAIN_STAMP(3);
         // ---- A tiles of the attention output (l-split, K contiguous) ----
         for (int r = warp; r < TN; r += kChainThreads / 32) {
             const float* xr = X + r * F;
@@ -141,21 +215,24 @@ __global__ void __launch_bounds__(kChainThreads, 1) node_chain_kernel(ChainArgs 
             for (int c = lane; c < 5 * emb.m2; c += 32) { const int u = c / 5, k = c - 5 * u; A2[(k * TN + r) * lda2 + u] = ok ? xr[emb.off2() + c] : 0.f; }
         }
         __syncthreads();
+        CHAIN_STAMP(4);
         if (first || a.wp_transient) { mbar_wait(&wpbar, php); php ^= 1u; }
         if (a.res1) mbar_wait(&rbar, ph);
+        CHAIN_STAMP(5);
         // ---- y1 = proj(x) + b (+ res1) ----
         {
-            const float* pb = a.pb; const bool has_res = a.res1 != nullptr;
+            const bool has_res = a.res1 != nullptr;
             const int off1 = emb.off1(), off2 = emb.off2();
-            chain_gemm<TN>(A0, lda0, A1, lda1, A2, lda2, sWp, sWp + nP0, sWp + nP0 + nP1, emb, emb,
+            chain_gemm_any<TN, true>(A0, lda0, A1, lda1, A2, lda2, sWp, sWp + nP0, sWp + nP0 + nP1, emb, emb,
                            [&](int l, int r, int k, int c, float v) {
                                const int col = (l == 0) ? c : (l == 1) ? off1 + 3 * c + k : off2 + 5 * c + k;
-                               if (l == 0 && pb) v += pb[c];
+                               if (l == 0) v += s_pb[c];
                                if (has_res) v += R[r * F + col];
                                Y1[r * F + col] = v;
                            });
         }
         __syncthreads();
+        CHAIN_STAMP(6);
         // ---- layer-norm statistics of y1: one warp per node ----
         for (int r = warp; r < TN; r += kChainThreads / 32) {
             float mean = 0.f, sc0 = 0.f, sc1 = 0.f, sc2 = 0.f;
@@ -177,64 +254,71 @@ __global__ void __launch_bounds__(kChainThreads, 1) node_chain_kernel(ChainArgs 
             if (lane == 0) { s_mean[r] = mean; s_scale[r * 3] = sc0; s_scale[r * 3 + 1] = sc1; s_scale[r * 3 + 2] = sc2; }
         }
         __syncthreads();
+        CHAIN_STAMP(7);
         // ---- A tiles of LN(y1) ----
         for (int r = warp; r < TN; r += kChainThreads / 32) {
             const float* xr = Y1 + r * F;
             const bool ok = r < rows;
             const float mean = s_mean[r], sc0 = s_scale[r * 3], sc1 = s_scale[r * 3 + 1], sc2 = s_scale[r * 3 + 2];
-            for (int c = lane; c < emb.m0; c += 32) A0[r * lda0 + c] = ok ? (xr[c] - mean) * sc0 * a.ln_w[c] + a.ln_b[c] : 0.f;
+            for (int c = lane; c < emb.m0; c += 32) A0[r * lda0 + c] = ok ? (xr[c] - mean) * sc0 * s_lnw[c] + s_lnb[c] : 0.f;
             for (int c = lane; c < 3 * emb.m1; c += 32) {
                 const int u = c / 3, k = c - 3 * u;
-                A1[(k * TN + r) * lda1 + u] = ok ? xr[emb.off1() + c] * sc1 * a.ln_w[emb.m0 + u] : 0.f;
+                A1[(k * TN + r) * lda1 + u] = ok ? xr[emb.off1() + c] * sc1 * s_lnw[emb.m0 + u] : 0.f;
             }
             for (int c = lane; c < 5 * emb.m2; c += 32) {
                 const int u = c / 5, k = c - 5 * u;
-                A2[(k * TN + r) * lda2 + u] = ok ? xr[emb.off2() + c] * sc2 * a.ln_w[emb.m0 + emb.m1 + u] : 0.f;
+                A2[(k * TN + r) * lda2 + u] = ok ? xr[emb.off2() + c] * sc2 * s_lnw[emb.m0 + emb.m1 + u] : 0.f;
             }
         }
         __syncthreads();          // (also: the proj GEMM is done with sWp / X / R -- the U region now belongs to the FFN)
+        CHAIN_STAMP(8);
         if (first) mbar_wait(&w1bar, 0);
+        CHAIN_STAMP(9);
         // ---- fctp_1: 0e block raw (+bias) into O0, l > 0 blocks raw into the next GEMM's A tiles ----
         {
-            const float* ab = a.ab;
-            chain_gemm<TN>(A0, lda0, A1, lda1, A2, lda2, sW1, sW1 + nA0, sW1 + nA0 + nA1, emb, pre,
+            chain_gemm_any<TN, false>(A0, lda0, A1, lda1, A2, lda2, sW1, sW1 + nA0, sW1 + nA0 + nA1, emb, pre,
                            [&](int l, int r, int k, int c, float v) {
-                               if (l == 0) O0[r * ldo0 + c] = v + (ab ? ab[c] : 0.f);
+                               if (l == 0) O0[r * ldo0 + c] = v + s_ab[c];
                                else if (l == 1) M1[(k * TN + r) * ldm1 + c] = v;
                                else M2[(k * TN + r) * ldm2 + c] = v;
                            });
         }
         __syncthreads();
+        CHAIN_STAMP(10);
         // ---- Gate: SiLU on the scalars, sigmoid gates multiplied onto the l > 0 channels (in place) ----
-        for (int r = warp; r < TN; r += kChainThreads / 32) {
+        constexpr int NW = kChainThreads / 32, SUB = TN < NW ? NW / TN : 1;       // few-node tiles: SUB warps share a node's columns
+        for (int r = warp % (TN < NW ? TN : NW); r < TN; r += NW) {
             const float* o = O0 + r * ldo0;
-            for (int c = lane; c < m0s; c += 32) M0[r * ldm0 + c] = kCSilu * siluf_(o[c]);
-            for (int c = lane; c < mid.m1; c += 32) {
+            const int c0 = lane + 32 * (TN < NW ? warp / TN : 0);
+            for (int c = c0; c < m0s; c += 32 * SUB) M0[r * ldm0 + c] = kCSilu * siluf_(o[c]);
+            for (int c = c0; c < mid.m1; c += 32 * SUB) {
                 const float g = kCSigmoid * sigmoidf_(o[m0s + c]);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) M1[(k * TN + r) * ldm1 + c] *= g;
             }
-            for (int c = lane; c < mid.m2; c += 32) {
+            for (int c = c0; c < mid.m2; c += 32 * SUB) {
                 const float g = kCSigmoid * sigmoidf_(o[m0s + mid.m1 + c]);
 #pragma unroll
                 for (int k = 0; k < 5; ++k) M2[(k * TN + r) * ldm2 + c] *= g;
             }
         }
         __syncthreads();
+        CHAIN_STAMP(11);
         if (first) mbar_wait(&w2bar, 0);
+        CHAIN_STAMP(12);
         // ---- y = y1 + fctp_2(h) + b ----
         {
-            const float* bb = a.bb;
             const int off1 = emb.off1(), off2 = emb.off2();
-            chain_gemm<TN>(M0, ldm0, M1, ldm1, M2, ldm2, sW2, sW2 + nB0, sW2 + nB0 + nB1, mid, emb,
+            chain_gemm_any<TN, true>(M0, ldm0, M1, ldm1, M2, ldm2, sW2, sW2 + nB0, sW2 + nB0 + nB1, mid, emb,
                            [&](int l, int r, int k, int c, float v) {
                                const int col = (l == 0) ? c : (l == 1) ? off1 + 3 * c + k : off2 + 5 * c + k;
-                               if (l == 0 && bb) v += bb[c];
+                               if (l == 0) v += s_bb[c];
                                Y1[r * F + col] = v + Y1[r * F + col];
                            });
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        CHAIN_STAMP(13);
         if (tid == 0) {
             const uint32_t bytes = (uint32_t)(rows * F) * 4u;
             constexpr uint32_t kChunk = 32768;
@@ -244,6 +328,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) node_chain_kernel(ChainArgs 
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
+        CHAIN_STAMP(14);
         ph ^= 1u;
         first = false;
     }
@@ -269,6 +354,7 @@ static int launch_chain(ChainArgs a, cudaStream_t stream) {
     a.o_y1 = off; off += TN * F;
     a.o_a = off; off += a_tiles;
     a.o_stat = off; off += 4 * TN;
+    a.o_par = off; off += r4(2 * emb.m0 + pre.m0 + emb.nirr() + emb.m0);
     a.o_u = off;
     if (off + proj_u + ffn_u <= kMax) {            // everything resident
         a.wp_transient = 0;
@@ -323,6 +409,12 @@ extern "C" int dedf_node_chain(const dedf_node_chain_desc* d, cudaStream_t strea
     if (rc == DEDF_ERR_UNSUPPORTED) rc = launch_chain<8>(a, stream);
     return rc;
 }
+
+#ifdef DEDF_CHAIN_TRACE
+extern "C" int dedf_chain_trace(long long* host_out32) {
+    return cudaMemcpyFromSymbol(host_out32, dedf::g_chain_trace, sizeof(long long) * 32) == cudaSuccess ? DEDF_OK : DEDF_ERR_LAUNCH;
+}
+#endif
 
 // Two independent dedf_node_linear problems without layer norm / gate / residual in ONE launch (blockIdx.y selects): the
 // linear_src / linear_dst pair at the head of every UNet block (block.py:149-153).

@@ -2,6 +2,8 @@
 signatures (/root/reference/diffusion_edf/score_model_base.py:22-225)."""
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -245,10 +247,33 @@ class ScoreModelBase(nn.Module):
     def _forward_tensors(self, Ts, time, kx, kf, kb, qx, qf, qb):
         ops.stamp("forward start")
         self.prefetch_weights()
+        # The query model and the time embedding depend on neither the scene nor the key encoder: they run on their own stream
+        # under the encoder's farthest-point sampling (the main stream is idle for it) instead of after the encoder (~70 us of
+        # launches on the critical path: in-graph timeline, profiles/r2_s11_*).
+        early = Ts.is_cuda and os.environ.get("DEDF_EARLY_QUERY", "1") != "0" and hasattr(self.score_head, "time_rows_for")
+        q = time_rows = ev = None
+        if early:
+            main = torch.cuda.current_stream()
+            if self.__dict__.get("_aux_stream") is None or self._aux_stream.device != Ts.device:
+                self.__dict__["_aux_stream"] = torch.cuda.Stream(device=Ts.device)
+            aux = self._aux_stream
+            aux.wait_stream(main)
+            with torch.cuda.stream(aux):
+                q = self._query_pcd(FeaturedPoints(qx, qf, qb))
+                time_rows = self.score_head.time_rows_for(time)
+                ev = torch.cuda.Event()
+                ev.record(aux)
         key_ms = self._key_pcd_multiscale(FeaturedPoints(kx, kf, kb))
         ops.stamp("key encoder done")
-        q = self._query_pcd(FeaturedPoints(qx, qf, qb))
-        out = self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)
+        if early:
+            main.wait_event(ev)
+            for t in (q.x, q.f, q.b, q.w, time_rows):
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(main)
+            out = self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time, time_rows=time_rows)
+        else:
+            q = self._query_pcd(FeaturedPoints(qx, qf, qb))
+            out = self.score_head(Ts=Ts, key_pcd_multiscale=key_ms, query_pcd=q, time=time)
         ops.stamp("score head done")
         return out
 

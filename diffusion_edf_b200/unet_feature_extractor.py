@@ -162,7 +162,11 @@ class UnetFeatureExtractor(nn.Module):
             g = ops.radius_csr(x, x_dst, [self.radius[n]], b_src=b, b_dst=b_dst, excl_mode=1, excl=idx, max_num_neighbors=1000)
             gp = self._geom(x, x_dst, g)
             ops.stamp(f"geo pool-graph{n}")
-            emit("pool", n=n, idx=idx, x_dst=x_dst, b_dst=b_dst, geom=gp, w=block(blk["pool_layer"], gp))
+            ev_g = None
+            if fps_stream is not None:       # the block's node linears only need the graph: they start under the radial MLP
+                ev_g = torch.cuda.Event()
+                ev_g.record(cur)
+            emit("pool", n=n, idx=idx, x_dst=x_dst, b_dst=b_dst, geom=gp, w=block(blk["pool_layer"], gp), event_g=ev_g)
             ops.stamp(f"geo pool-mlp{n}")
             g = ops.radius_csr(x_dst, x_dst, [self.radius[n]], b_src=b_dst, b_dst=b_dst, excl_mode=2, max_num_neighbors=1001)
             geom = self._geom(x_dst, x_dst, g)
@@ -218,7 +222,7 @@ class UnetFeatureExtractor(nn.Module):
             pos[0] += 1
             assert it["kind"] == kind, (it["kind"], kind)
             if use_side:
-                main.wait_event(it["event"])
+                main.wait_event(it["event_g"] if it.get("event_g") is not None else it["event"])
                 for v in it.values():                    # tensors allocated on the side stream, consumed on the main one
                     for t in (v if isinstance(v, (tuple, list)) else (v,)):
                         if isinstance(t, torch.Tensor):
@@ -231,7 +235,8 @@ class UnetFeatureExtractor(nn.Module):
         def run(layer, f_src, f_dst, it):
             gm = it["geom"]
             ops.stamp(f"blk start {it['kind']} n_dst={gm.g.n_dst}")
-            out = layer["gnn"](f_src, f_dst, gm.g, gm.sh, gm.length, layer["radial"], w=it["w"])
+            w_ready = (lambda: main.wait_event(it["event"])) if use_side and it.get("event_g") is not None else None
+            out = layer["gnn"](f_src, f_dst, gm.g, gm.sh, gm.length, layer["radial"], w=it["w"], w_ready=w_ready)
             ops.stamp(f"blk end {it['kind']} n_dst={gm.g.n_dst}")
             return out
 

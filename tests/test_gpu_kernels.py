@@ -353,8 +353,8 @@ def test_ln_linear_gate_residual(cuda, G):
 @pytest.mark.parametrize("G,n", [(32, 41), (16, 41), (32, 300), (16, 2000), (32, 8)])
 def test_node_chain_is_bit_identical_to_three_launches(cuda, G, n):
     """dedf_node_chain (proj -> +res -> LN -> fctp_1 -> gate -> fctp_2 -> +res in one launch) against the three dedf_node_linear
-    launches it replaces: same micro-kernel and summation order, so the results must be EQUAL, with and without the first
-    residual; and against the oracle (graph_attention.py:118-121, gnn_block.py:51-57,207-216)."""
+    launches it replaces: same micro-kernel and summation order, so the results must be EQUAL (above 2 x SMs nodes; the 4-node
+    tiles of smaller launches split K: equal to rounding), with and without the first residual; and against the oracle (graph_attention.py:118-121, gnn_block.py:51-57,207-216)."""
     from diffusion_edf_b200 import layers, ops
     from diffusion_edf_b200.block import node_tail
     torch.manual_seed(40 + G)
@@ -385,7 +385,10 @@ def test_node_chain_is_bit_identical_to_three_launches(cuda, G, n):
             unfused = node_tail(p_proj, p_ln, p_ffn, x.to(cuda), rg)
         finally:
             ops.USE_NODE_CHAIN = True
-        assert torch.equal(fused, unfused), f"max diff {(fused - unfused).abs().max().item():.3e}"
+        if n > 2 * 148:      # 8- / 16-node tiles: same micro-kernel and K order as dedf_node_linear
+            assert torch.equal(fused, unfused), f"max diff {(fused - unfused).abs().max().item():.3e}"
+        else:                # 4-node tiles split K over four lanes: same products, another association
+            assert_close(fused, unfused, 2e-6, "node chain (split-K) vs three launches")
         assert_close(fused, ref, TOL, "node chain vs oracle")
 
 
