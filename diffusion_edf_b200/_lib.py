@@ -41,7 +41,7 @@ class MlpDesc(C.Structure):
         ("W", c_fp * MLP_MAX_LAYERS), ("b", c_fp * MLP_MAX_LAYERS),
         ("ln_g", c_fp * MLP_MAX_LAYERS), ("ln_b", c_fp * MLP_MAX_LAYERS),
         ("flags", c_int * MLP_MAX_LAYERS), ("out_offset", c_fp), ("out", c_fp),
-        ("W_tc", c_fp * MLP_MAX_LAYERS), ("pre_w_tc", c_fp),
+        ("W_tc", c_fp * MLP_MAX_LAYERS), ("pre_w_tc", c_fp), ("tc_f16", c_int),
     ]
 
 

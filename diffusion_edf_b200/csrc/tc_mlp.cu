@@ -1,4 +1,5 @@
 // Tensor-core (tcgen05, kind::tf32, 3xTF32 split) kernels: self-test GEMM and the per-edge MLP.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc.cuh"
 #include "../../include/dedf.h"
@@ -132,7 +133,44 @@ __device__ __forceinline__ int tc_chunks_per_stage(uint32_t ring_bytes, uint32_t
     return cps;
 }
 
+// hi / lo operand group of one edge row: KG consecutive K columns = one 16-byte core-matrix row.
+//   tf32 split (F16 = false): 4 floats, hi = 13 low mantissa bits cleared, lo = x - hi, K = 8 per MMA
+//   fp16 split (F16 = true):  8 halves, hi = fp16(x), lo = fp16(x - hi), K = 16 per MMA: half the MMAs, half the weight bytes
+//                             streamed per tile and half the operand bytes written / fetched for the same products (see the
+//                             note on edge_tp_act_tc_kernel; the activations here are O(1) post-LayerNorm values, the inputs radial
+//                             basis values <= 4 sqrt(K0): far inside fp16 range)
+template <bool F16> struct TcGroup;
+template <> struct TcGroup<false> {
+    static constexpr int KG = 4;
+    static __device__ __forceinline__ void store(unsigned char* hi_p, unsigned char* lo_p, const float* v) {
+        float4 hi, lo;
+        hi.x = tc::tf32_hi(v[0]); hi.y = tc::tf32_hi(v[1]); hi.z = tc::tf32_hi(v[2]); hi.w = tc::tf32_hi(v[3]);
+        lo.x = v[0] - hi.x; lo.y = v[1] - hi.y; lo.z = v[2] - hi.z; lo.w = v[3] - hi.w;
+        *reinterpret_cast<float4*>(hi_p) = hi;
+        *reinterpret_cast<float4*>(lo_p) = lo;
+    }
+};
+template <> struct TcGroup<true> {
+    static constexpr int KG = 8;
+    static __device__ __forceinline__ void store(unsigned char* hi_p, unsigned char* lo_p, const float* v) {
+        uint32_t H[4], Lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            const float2 f = __half22float2(h);
+            const __half2 l = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+            H[i] = *reinterpret_cast<const uint32_t*>(&h); Lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        *reinterpret_cast<uint4*>(hi_p) = make_uint4(H[0], H[1], H[2], H[3]);
+        *reinterpret_cast<uint4*>(lo_p) = make_uint4(Lo[0], Lo[1], Lo[2], Lo[3]);
+    }
+};
+
+template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a) {
+    using GR = TcGroup<F16>;
+    constexpr int KG = GR::KG;               // K columns per 16-byte operand group
+    constexpr int KM = 2 * KG;               // K per MMA (two groups)
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* sA_hi = smem;
     unsigned char* sA_lo = sA_hi + a.a_bytes;
@@ -242,12 +280,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                 int e0, e1, scale; tile_range(tile, e0, e1, scale);
                 for (int L = 0; L < a.n_layers; ++L) {
                     const int K = a.K[L], N = a.K[L + 1];
-                    const int NB = tc_nblocks(N), Nb = N / NB, nkc = K / 8;
+                    const int NB = tc_nblocks(N), Nb = N / NB, nkc = K / KM;
                     const uint32_t cbytes = (uint32_t)Nb * 64u;                       // one K chunk of one N block (hi + lo)
                     const int cps = tc_chunks_per_stage(ring_bytes, cbytes, nkc);      // K chunks per stage (divides nkc)
                     const uint32_t bytes = cbytes * (uint32_t)cps;
                     const uint32_t ns = min((uint32_t)kTcMaxStages, ring_bytes / bytes);
-                    const float* Wl = a.Wp[L] + ((field && L == 0) ? (size_t)scale * 2 * K * N : 0);
+                    const float* Wl = a.Wp[L] + ((field && L == 0) ? (size_t)scale * (F16 ? 1 : 2) * K * N : 0);
                     TC_STAMP(kTcProdWarp * 32);
                     if (!first_layer) { tc::mbar_wait_bounded(&layer_done, pl); pl ^= 1u; }
                     first_layer = false;
@@ -275,8 +313,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int L = 0; L < a.n_layers; ++L) {
                     const int K = a.K[L], N = a.K[L + 1];
-                    const int NB = tc_nblocks(N), Nb = N / NB, nkc = K / 8;
-                    const uint32_t idesc = tc::idesc_tf32(kTcM, Nb);
+                    const int NB = tc_nblocks(N), Nb = N / NB, nkc = K / KM;
+                    const uint32_t idesc = F16 ? tc::idesc_f16(kTcM, Nb) : tc::idesc_tf32(kTcM, Nb);
                     TC_STAMP(kTcMmaWarp * 32);
                     tc::mbar_wait_bounded(&a_ready, pa); pa ^= 1u;      // A operand written, accumulator drained
                     tc::fence_after();
@@ -301,9 +339,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                             for (int c = 0; c < cps; ++c) {
                                 const uint64_t db_hi = tc::smem_desc(bs, (uint32_t)Nb * 16, 128);
                                 const uint64_t db_lo = tc::smem_desc(bs + (uint32_t)Nb * 32, (uint32_t)Nb * 16, 128);
-                                tc::mma_tf32_if(leader, d, da_hi, db_hi, idesc, (kc + c) > 0);
-                                tc::mma_tf32_if(leader, d, da_lo, db_hi, idesc, 1);
-                                tc::mma_tf32_if(leader, d, da_hi, db_lo, idesc, 1);
+                                if constexpr (F16) {
+                                    tc::mma_f16_if(leader, d, da_hi, db_hi, idesc, (kc + c) > 0);
+                                    tc::mma_f16_if(leader, d, da_lo, db_hi, idesc, 1);
+                                    tc::mma_f16_if(leader, d, da_hi, db_lo, idesc, 1);
+                                } else {
+                                    tc::mma_tf32_if(leader, d, da_hi, db_hi, idesc, (kc + c) > 0);
+                                    tc::mma_tf32_if(leader, d, da_lo, db_hi, idesc, 1);
+                                    tc::mma_tf32_if(leader, d, da_hi, db_lo, idesc, 1);
+                                }
                                 da_hi += kAStep; da_lo += kAStep;
                                 bs += cbytes;
                             }
@@ -342,10 +386,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                 nrm = sqrtf((float)K0);
             }
             const int half = K0 / 2;
-            for (int k4 = wg * 4; k4 < K0; k4 += 4 * kTcEpiWG) {
-                float v[4];
+            for (int k4 = wg * KG; k4 < K0; k4 += KG * kTcEpiWG) {
+                float v[KG];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < KG; ++j) {
                     const int k = k4 + j;
                     float t;
                     if (sinus) {
@@ -360,12 +404,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                     }
                     v[j] = valid ? t : 0.f;
                 }
-                float4 hi, lo;
-                hi.x = tc::tf32_hi(v[0]); hi.y = tc::tf32_hi(v[1]); hi.z = tc::tf32_hi(v[2]); hi.w = tc::tf32_hi(v[3]);
-                lo.x = v[0] - hi.x; lo.y = v[1] - hi.y; lo.z = v[2] - hi.z; lo.w = v[3] - hi.w;
-                const uint32_t off = (uint32_t)((k4 >> 2) * kTcM + m) * 16u;
-                *reinterpret_cast<float4*>(sA_hi + off) = hi;
-                *reinterpret_cast<float4*>(sA_lo + off) = lo;
+                const uint32_t off = (uint32_t)((k4 / KG) * kTcM + m) * 16u;
+                GR::store(sA_hi + off, sA_lo + off, v);
             }
         };
         int tile = blockIdx.x;
@@ -432,22 +472,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) edge_mlp_tc_kernel(MlpTcArgs a)
                         rstd = rsqrtf(((r2[m] + r2[kTcM + m]) + (r2[2 * kTcM + m] + r2[3 * kTcM + m])) / (float)N + 1e-5f);
                     }
 #pragma unroll
-                    for (int c4 = 0; c4 < 32; c4 += 4) {
-                        if (c4 < 16 * n16 && act_cols) {
-                            const int c = c_lo + c4;
-                            float o[4] = {v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]};
-                            if (ln) {
-                                const float4 g4 = *reinterpret_cast<const float4*>(pg + c), b4 = *reinterpret_cast<const float4*>(pbb + c);
-                                o[0] = (o[0] - mean) * rstd * g4.x + b4.x; o[1] = (o[1] - mean) * rstd * g4.y + b4.y;
-                                o[2] = (o[2] - mean) * rstd * g4.z + b4.z; o[3] = (o[3] - mean) * rstd * g4.w + b4.w;
+                    for (int cg = 0; cg < 32; cg += KG) {
+                        if (cg < 16 * n16 && act_cols) {
+                            float o[KG];
+#pragma unroll
+                            for (int c4 = 0; c4 < KG; c4 += 4) {
+                                const int c = c_lo + cg + c4;
+                                o[c4] = v[cg + c4]; o[c4 + 1] = v[cg + c4 + 1]; o[c4 + 2] = v[cg + c4 + 2]; o[c4 + 3] = v[cg + c4 + 3];
+                                if (ln) {
+                                    const float4 g4 = *reinterpret_cast<const float4*>(pg + c), b4 = *reinterpret_cast<const float4*>(pbb + c);
+                                    o[c4] = (o[c4] - mean) * rstd * g4.x + b4.x; o[c4 + 1] = (o[c4 + 1] - mean) * rstd * g4.y + b4.y;
+                                    o[c4 + 2] = (o[c4 + 2] - mean) * rstd * g4.z + b4.z; o[c4 + 3] = (o[c4 + 3] - mean) * rstd * g4.w + b4.w;
+                                }
+                                if (act) { o[c4] = siluf_(o[c4]); o[c4 + 1] = siluf_(o[c4 + 1]); o[c4 + 2] = siluf_(o[c4 + 2]); o[c4 + 3] = siluf_(o[c4 + 3]); }
                             }
-                            if (act) { o[0] = siluf_(o[0]); o[1] = siluf_(o[1]); o[2] = siluf_(o[2]); o[3] = siluf_(o[3]); }
-                            float4 hi, lo;
-                            hi.x = tc::tf32_hi(o[0]); hi.y = tc::tf32_hi(o[1]); hi.z = tc::tf32_hi(o[2]); hi.w = tc::tf32_hi(o[3]);
-                            lo.x = o[0] - hi.x; lo.y = o[1] - hi.y; lo.z = o[2] - hi.z; lo.w = o[3] - hi.w;
-                            const uint32_t off = (uint32_t)((c >> 2) * kTcM + m) * 16u;
-                            *reinterpret_cast<float4*>(sA_hi + off) = hi;
-                            *reinterpret_cast<float4*>(sA_lo + off) = lo;
+                            const uint32_t off = (uint32_t)(((c_lo + cg) / KG) * kTcM + m) * 16u;
+                            GR::store(sA_hi + off, sA_lo + off, o);
                         }
                     }
                     tc::fence_async_smem();
@@ -559,6 +599,8 @@ extern "C" int dedf_edge_mlp_tc(const dedf_mlp_desc* d, int max_edges, cudaStrea
             if (a.enc_r[s] < 0.f && !a.enc_freq) return DEDF_ERR_ARG;
         }
     }
+    const bool f16 = d->tc_f16 != 0;
+    if (f16) for (int i = 0; i < d->n_layers; ++i) if (a.K[i] % 16) return DEDF_ERR_UNSUPPORTED;      // K = 16 per kind::f16 MMA
     a.out_offset = d->out_offset; a.out = d->out;
     a.dbg = g_tc_dbg;
     a.a_bytes = kTcM * max_k * 4;
@@ -578,9 +620,14 @@ extern "C" int dedf_edge_mlp_tc(const dedf_mlp_desc* d, int max_edges, cudaStrea
                         ((size_t)ns * a.K[0] * 4 + ((a.K[0] / 2 + 3) & ~3) + (DEDF_MLP_MAX_LAYERS - 1) * 3 * kTcMaxHidden + 512 + 2 * kTcEpiWG * kTcM) * sizeof(float);
     if (smem > 220 * 1024) return DEDF_ERR_UNSUPPORTED;
     static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done = true; }
+    if (!attr_done) {
+        cudaFuncSetAttribute(edge_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(edge_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_done = true;
+    }
     const int n_tiles = (max_edges + kTcM - 1) / kTcM + DEDF_MAX_SCALES;
-    launch_pdl(edge_mlp_tc_kernel, dim3(grid_for(n_tiles, 1, kNumSMs)), dim3(kTcThreads), smem, stream, a);
+    if (f16) launch_pdl(edge_mlp_tc_kernel<true>, dim3(grid_for(n_tiles, 1, kNumSMs)), dim3(kTcThreads), smem, stream, a);
+    else launch_pdl(edge_mlp_tc_kernel<false>, dim3(grid_for(n_tiles, 1, kNumSMs)), dim3(kTcThreads), smem, stream, a);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }

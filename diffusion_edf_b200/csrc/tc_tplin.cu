@@ -30,12 +30,23 @@
 //     cycle accounting (dedf_tp_act_tc_set_debug) shows the tensor pipe waiting on shared-memory bandwidth: every
 //     M = 128 x K = 8 tf32 MMA fetches 4 KB for the M side whatever N is, the producers store 53 KB per chunk next to it;
 //     a second producer group (12 warps) made both slower (275 us).
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc.cuh"
 #include "cg_slots.cuh"
 #include "../../include/dedf.h"
 
 namespace dedf {
+
+// -DDEDF_TA_TRACE (profiles/run_tp_act_trace.py builds its own copy of the library): producer warp 0 of CTA 0 accumulates the
+// cycles of each segment of its chunk loop into dbg[8..15].  Not compiled into the shipped library.
+#ifdef DEDF_TA_TRACE
+#define TA_T0() long long ta_c = clock64()
+#define TA_SEG(i) do { const long long ta_n = clock64(); ta_seg[i] += ta_n - ta_c; ta_c = ta_n; } while (0)
+#else
+#define TA_T0() do { } while (0)
+#define TA_SEG(i) do { } while (0)
+#endif
 
 constexpr int kTaTE = 32;
 constexpr int kTaProdWarps = 6;
@@ -95,11 +106,68 @@ struct TpActArgs {
     long long* dbg;
 };
 
-template <int G>
+// fp16 operand split (F16 = true): x = h + l with h = fp16(x), l = fp16(x - h) (22 significand bits between them, like the 21 of
+// the tf32 split; the lo part of a value below ~0.1 is an fp16 subnormal, i.e. an ABSOLUTE error of <= 3e-8 per operand element),
+// products on kind::f16 with K = 16 per MMA: two channel chunks share one operand stage (the 16-byte K-group of a row holds four
+// halves of the even chunk and four of the odd one), so per chunk the producers store, and the tensor core fetches, HALF the
+// shared-memory bytes of the tf32 split -- and shared-memory bandwidth is what bounds this kernel (clock64 trace of the producers
+// and the issuer, profiles/r2_s11_tp_act_trace.txt: 150 KB of operand fetch + ~1000 LSU wavefronts per 2750-cycle chunk).
+// Limit: |operand| must stay below 65504 (fp16); larger values come out as NaN, never silently wrong.  DEDF_TPACT_F16=0 on the
+// host side selects the tf32 split.
+template <bool F16> struct TaStore;
+template <> struct TaStore<false> {
+    static __device__ __forceinline__ void put4(unsigned char* hi, unsigned char* lo, int goff, int, float v0, float v1, float v2, float v3) {
+        const float4 h = make_float4(tc::tf32_hi(v0), tc::tf32_hi(v1), tc::tf32_hi(v2), tc::tf32_hi(v3));
+        *reinterpret_cast<float4*>(hi + goff) = h;
+        *reinterpret_cast<float4*>(lo + goff) = make_float4(v0 - h.x, v1 - h.y, v2 - h.z, v3 - h.w);
+    }
+    static __device__ __forceinline__ void put2(unsigned char* hi, unsigned char* lo, int goff, int, int col, float v0, float v1) {
+        const float2 h = make_float2(tc::tf32_hi(v0), tc::tf32_hi(v1));
+        *reinterpret_cast<float2*>(hi + goff + 4 * col) = h;
+        *reinterpret_cast<float2*>(lo + goff + 4 * col) = make_float2(v0 - h.x, v1 - h.y);
+    }
+    static __device__ __forceinline__ void put1(unsigned char* hi, unsigned char* lo, int goff, int, int col, float v) {
+        const float h = tc::tf32_hi(v);
+        *reinterpret_cast<float*>(hi + goff + 4 * col) = h;
+        *reinterpret_cast<float*>(lo + goff + 4 * col) = v - h;
+    }
+};
+template <> struct TaStore<true> {      // odd: 0 / 1 = which half of the 16-byte K-group this chunk fills
+    static __device__ __forceinline__ void split2(float v0, float v1, __half2& h, __half2& l) {
+        h = __floats2half2_rn(v0, v1);
+        const float2 f = __half22float2(h);
+        l = __floats2half2_rn(v0 - f.x, v1 - f.y);
+    }
+    static __device__ __forceinline__ void put4(unsigned char* hi, unsigned char* lo, int goff, int odd, float v0, float v1, float v2, float v3) {
+        __half2 h0, l0, h1, l1;
+        split2(v0, v1, h0, l0); split2(v2, v3, h1, l1);
+        uint2 H, Lo;
+        H.x = *reinterpret_cast<uint32_t*>(&h0); H.y = *reinterpret_cast<uint32_t*>(&h1);
+        Lo.x = *reinterpret_cast<uint32_t*>(&l0); Lo.y = *reinterpret_cast<uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(hi + goff + 8 * odd) = H;
+        *reinterpret_cast<uint2*>(lo + goff + 8 * odd) = Lo;
+    }
+    static __device__ __forceinline__ void put2(unsigned char* hi, unsigned char* lo, int goff, int odd, int col, float v0, float v1) {
+        __half2 h, l;
+        split2(v0, v1, h, l);
+        *reinterpret_cast<__half2*>(hi + goff + 8 * odd + 2 * col) = h;
+        *reinterpret_cast<__half2*>(lo + goff + 8 * odd + 2 * col) = l;
+    }
+    static __device__ __forceinline__ void put1(unsigned char* hi, unsigned char* lo, int goff, int odd, int col, float v) {
+        const __half h = __float2half_rn(v);
+        *reinterpret_cast<__half*>(hi + goff + 8 * odd + 2 * col) = h;
+        *reinterpret_cast<__half*>(lo + goff + 8 * odd + 2 * col) = __float2half_rn(v - __half2float(h));
+    }
+};
+
+template <int G, bool F16>
 __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs a) {
     using C = TaCfg<G>;
     using D = Dtp<G>;
+    using S = TaStore<F16>;
     constexpr int NCH = C::NCH;
+    constexpr int NST = F16 ? NCH / 2 : NCH;            // operand stages per tile: one per chunk (tf32) / per chunk pair (fp16)
+    static_assert(NCH % 2 == 0, "chunk pairs");
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* sA = smem + C::OffA;
     unsigned char* sW = smem + C::OffW;
@@ -183,6 +251,9 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
             };
             if (warp < 4) {
                 const int i = warp;
+#ifdef DEDF_TA_TRACE
+                long long ta_seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
                 float2 w0, w1, w2; float w6[6];
                 auto ldw = [&](int j) {
                     if (a.w_perm) {
@@ -199,8 +270,10 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                         for (int k = 0; k < 6; ++k) w6[k] = wr[D::W_K3 + p + k * D::M1];
                     }
                 };
+                TA_T0();
                 ldx(0); ldw(0); stx(0);
                 prod_sync();
+                TA_SEG(0);
 #pragma unroll 1
                 for (int j = 0; j < NCH; ++j) {
                     const float* xrow = s_x + ((j & 1) * kTaTE + e) * kTaXLd;
@@ -211,41 +284,44 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                     dtp_l0(xab.x, w0.x, w1.x, w2.x, sh, oa);
                     dtp_l0(xab.y, w0.y, w1.y, w2.y, sh, ob);
                     dtp_l1(x1, w6, sh, o);
+                    TA_SEG(1);
                     if (j + 1 < NCH) ldw(j + 1);
-                    tc::mbar_wait_bounded(&emptyA[st], ph ^ 1u);
+                    const int odd = F16 ? (j & 1) : 0;
+                    if (!F16 || !odd) tc::mbar_wait_bounded(&emptyA[st], ph ^ 1u);
+                    TA_SEG(2);
                     unsigned char* hi = sA + st * kAStage;
                     unsigned char* lo = hi + kAPart;
-                    auto put4 = [&](int off, float v0, float v1, float v2, float v3) {
-                        const float4 h = make_float4(tc::tf32_hi(v0), tc::tf32_hi(v1), tc::tf32_hi(v2), tc::tf32_hi(v3));
-                        *reinterpret_cast<float4*>(hi + off) = h;
-                        *reinterpret_cast<float4*>(lo + off) = make_float4(v0 - h.x, v1 - h.y, v2 - h.z, v3 - h.w);
-                    };
-                    auto put1 = [&](int off, float v) {
-                        const float h = tc::tf32_hi(v);
-                        *reinterpret_cast<float*>(hi + off) = h;
-                        *reinterpret_cast<float*>(lo + off) = v - h;
-                    };
                     // l_out = 0, group i: [k0 a, k0 b, k4 p, (k12: the l=2 warps)]
                     {
                         const int off = kA0Off + (i * kR0 + e) * 16;
-                        put1(off, oa[0]); put1(off + 4, ob[0]); put1(off + 8, o[3]);
+                        S::put2(hi, lo, off, odd, 0, oa[0], ob[0]); S::put1(hi, lo, off, odd, 2, o[3]);
                     }
 #pragma unroll
                     for (int m = 0; m < 3; ++m) {      // l_out = 1, group i: [k3, k5, k7, k1 a]; group 4 column i: k1 b
-                        put4(kA1Off + (i * kR1 + m * kTaTE + e) * 16, o[m], o[4 + m], o[12 + m], oa[1 + m]);
-                        put1(kA1Off + (4 * kR1 + m * kTaTE + e) * 16 + i * 4, ob[1 + m]);
+                        S::put4(hi, lo, kA1Off + (i * kR1 + m * kTaTE + e) * 16, odd, o[m], o[4 + m], o[12 + m], oa[1 + m]);
+                        S::put1(hi, lo, kA1Off + (4 * kR1 + m * kTaTE + e) * 16, odd, i, ob[1 + m]);
                     }
 #pragma unroll
                     for (int m = 0; m < 5; ++m)        // l_out = 2, group i: [k2 a, k2 b, k6, k8]; m = 4 rides in rows 96.. of the 1e operand
-                        put4(m < 4 ? kA2Off + (i * kR2 + m * kTaTE + e) * 16 : kA1Off + (i * kR1 + 3 * kTaTE + e) * 16,
-                             oa[4 + m], ob[4 + m], o[7 + m], o[15 + m]);
-                    tc::fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&fullA[st]);
-                    if (++st == kTaStages) { st = 0; ph ^= 1u; }
+                        S::put4(hi, lo, m < 4 ? kA2Off + (i * kR2 + m * kTaTE + e) * 16 : kA1Off + (i * kR1 + 3 * kTaTE + e) * 16, odd,
+                                oa[4 + m], ob[4 + m], o[7 + m], o[15 + m]);
+                    TA_SEG(3);
+                    if (!F16 || odd) {                 // fp16: the stage is complete after the odd chunk of the pair
+                        tc::fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&fullA[st]);
+                        if (++st == kTaStages) { st = 0; ph ^= 1u; }
+                    }
+                    TA_SEG(4);
                     if (j + 1 < NCH) stx((j + 1) & 1);
+                    TA_SEG(5);
                     prod_sync();
+                    TA_SEG(6);
                 }
+#ifdef DEDF_TA_TRACE
+                if (a.dbg && blockIdx.x == 0 && warp == 0 && lane == 0)
+                    for (int k = 0; k < 8; ++k) a.dbg[8 + k] += ta_seg[k];
+#endif
             } else {
                 const int t = warp - 4;
                 float w6[6];
@@ -270,36 +346,24 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                     float o[22];
                     dtp_l2(x2, w6, sh, o);
                     if (j + 1 < NCH) ldw(j + 1);
-                    tc::mbar_wait_bounded(&emptyA[st], ph ^ 1u);
+                    const int odd = F16 ? (j & 1) : 0;
+                    if (!F16 || !odd) tc::mbar_wait_bounded(&emptyA[st], ph ^ 1u);
                     unsigned char* hi = sA + st * kAStage;
                     unsigned char* lo = hi + kAPart;
-                    auto put4 = [&](int off, float v0, float v1, float v2, float v3) {
-                        const float4 h = make_float4(tc::tf32_hi(v0), tc::tf32_hi(v1), tc::tf32_hi(v2), tc::tf32_hi(v3));
-                        *reinterpret_cast<float4*>(hi + off) = h;
-                        *reinterpret_cast<float4*>(lo + off) = make_float4(v0 - h.x, v1 - h.y, v2 - h.z, v3 - h.w);
-                    };
-                    auto put2 = [&](int off, float v0, float v1) {
-                        const float2 h = make_float2(tc::tf32_hi(v0), tc::tf32_hi(v1));
-                        *reinterpret_cast<float2*>(hi + off) = h;
-                        *reinterpret_cast<float2*>(lo + off) = make_float2(v0 - h.x, v1 - h.y);
-                    };
-                    {   // l_out = 0, group t, column 3: k12
-                        const int off = kA0Off + (t * kR0 + e) * 16 + 12;
-                        const float h = tc::tf32_hi(o[13]);
-                        *reinterpret_cast<float*>(hi + off) = h;
-                        *reinterpret_cast<float*>(lo + off) = o[13] - h;
-                    }
+                    S::put1(hi, lo, kA0Off + (t * kR0 + e) * 16, odd, 3, o[13]);       // l_out = 0, group t, column 3: k12
 #pragma unroll
                     for (int m = 0; m < 3; ++m)        // l_out = 1, group 5, columns 2t, 2t+1: [k10, k13]
-                        put2(kA1Off + (5 * kR1 + m * kTaTE + e) * 16 + t * 8, o[5 + m], o[14 + m]);
+                        S::put2(hi, lo, kA1Off + (5 * kR1 + m * kTaTE + e) * 16, odd, 2 * t, o[5 + m], o[14 + m]);
 #pragma unroll
                     for (int m = 0; m < 5; ++m)        // l_out = 2, group 4 + t: [k9, k11, k14, 0]
-                        put4(m < 4 ? kA2Off + ((4 + t) * kR2 + m * kTaTE + e) * 16 : kA1Off + ((4 + t) * kR1 + 3 * kTaTE + e) * 16,
-                             o[m], o[8 + m], o[17 + m], 0.f);
-                    tc::fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&fullA[st]);
-                    if (++st == kTaStages) { st = 0; ph ^= 1u; }
+                        S::put4(hi, lo, m < 4 ? kA2Off + ((4 + t) * kR2 + m * kTaTE + e) * 16 : kA1Off + ((4 + t) * kR1 + 3 * kTaTE + e) * 16, odd,
+                                o[m], o[8 + m], o[17 + m], 0.f);
+                    if (!F16 || odd) {
+                        tc::fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&fullA[st]);
+                        if (++st == kTaStages) { st = 0; ph ^= 1u; }
+                    }
                     if (j + 1 < NCH) stx((j + 1) & 1);
                     prod_sync();
                 }
@@ -310,7 +374,7 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
         if (lane == 0) {
             uint32_t st = 0, ph = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int j = 0; j < NCH; ++j) {
+                for (int j = 0; j < NST; ++j) {
                     tc::mbar_wait_bounded(&emptyW[st], ph ^ 1u);
                     mbar_expect_tx(&fullW[st], (uint32_t)C::WStage);
                     bulk_g2s_chunked(sW + st * C::WStage, reinterpret_cast<const unsigned char*>(a.Wp) + (size_t)j * C::WStage,
@@ -327,7 +391,13 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
             const uint32_t leader = tc::elect_one();
             uint32_t st = 0, ph = 0;
             const uint32_t a_base = smem_u32(sA), w_base = smem_u32(sW);
-            const uint32_t id0 = tc::idesc_tf32(128, kTaTE), id1 = tc::idesc_tf32(128, C::N1C), id2 = tc::idesc_tf32(128, C::N2P);
+            const uint32_t id0 = F16 ? tc::idesc_f16(128, kTaTE) : tc::idesc_tf32(128, kTaTE);
+            const uint32_t id1 = F16 ? tc::idesc_f16(128, C::N1C) : tc::idesc_tf32(128, C::N1C);
+            const uint32_t id2 = F16 ? tc::idesc_f16(128, C::N2P) : tc::idesc_tf32(128, C::N2P);
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+                if constexpr (F16) tc::mma_f16_if(leader, d, da, db, id, acc);
+                else tc::mma_tf32_if(leader, d, da, db, id, acc);
+            };
             int it = 0;
             long long wA = 0, wW = 0, wE = 0, tIssue = 0;
             const long long tStart = clock64();
@@ -338,7 +408,7 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                 wE += clock64() - c; }
                 tc::fence_after();
                 const uint32_t d0 = tmem_base + buf * (uint32_t)kTaAccCols;
-                for (int j = 0; j < NCH; ++j) {
+                for (int j = 0; j < NST; ++j) {
                     { const long long c = clock64();
                     tc::mbar_wait_bounded(&fullA[st], ph);
                     const long long c2 = clock64();
@@ -362,13 +432,13 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                             const uint32_t wo = C::W0Off + ks * 2 * (C::N0P * 16) + g * 128 * 16, ao = kA0Off + ks * 2 * (kR0 * 16);
                             const uint64_t dw = tc::smem_desc((p == 2 ? wl : wh) + wo, C::N0P * 16, 128);
                             const uint64_t da = tc::smem_desc((p == 1 ? al : ah) + ao, kR0 * 16, 128);
-                            tc::mma_tf32_if(leader, d0 + C::T0 + g * kTaTE, dw, da, id0, acc);
+                            mma(d0 + C::T0 + g * kTaTE, dw, da, id0, acc);
                         } else {
                             const uint32_t a_off = (g == 2) ? kA1Off : kA2Off, lbo_a = (g == 2 ? kR1 : kR2) * 16;
                             const uint32_t w_off = (g == 2) ? C::W1Off : C::W2Off, lbo_w = (g == 2 ? C::N1C : C::N2P) * 16;
                             const uint64_t da = tc::smem_desc((p == 1 ? al : ah) + a_off + ks * 2 * lbo_a, lbo_a, 128);
                             const uint64_t dw = tc::smem_desc((p == 2 ? wl : wh) + w_off + ks * 2 * lbo_w, lbo_w, 128);
-                            tc::mma_tf32_if(leader, d0 + (g == 2 ? C::T1 : C::T2A), da, dw, g == 2 ? id1 : id2, acc);
+                            mma(d0 + (g == 2 ? C::T1 : C::T2A), da, dw, g == 2 ? id1 : id2, acc);
                         }
                     };
                     constexpr int n0 = 3 * (kKC0 / 8), n12 = 3 * (kKC1 / 8);
@@ -485,16 +555,16 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
     if (warp == kTaTmaWarp) tc::tmem_dealloc(tmem_base, 2 * kTaAccCols);
 }
 
-template <int G>
+template <int G, bool F16>
 static int launch_tp_act_tc(const TpActArgs& a, int max_edges, cudaStream_t stream) {
     using C = TaCfg<G>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(edge_tp_act_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::Smem);
+        cudaFuncSetAttribute(edge_tp_act_tc_kernel<G, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::Smem);
         attr_done = true;
     }
     const int n_tiles = (max_edges + kTaTE - 1) / kTaTE;
-    launch_pdl((edge_tp_act_tc_kernel<G>), dim3(grid_for(n_tiles, 1, kNumSMs)), dim3(kTaThreads), (size_t)C::Smem, stream, a);
+    launch_pdl((edge_tp_act_tc_kernel<G, F16>), dim3(grid_for(n_tiles, 1, kNumSMs)), dim3(kTaThreads), (size_t)C::Smem, stream, a);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
 }
@@ -519,9 +589,10 @@ extern "C" int dedf_edge_tp_act_tc(int mul1, const float* x_src, const float* x_
         return DEDF_ERR_ARG;
     TpActArgs a{};
     a.x_src = x_src; a.x_dst = x_dst; a.edge_src = edge_src; a.edge_dst = edge_dst; a.n_edges = n_edges_dev; a.sh = sh;
-    a.w = w; a.w_stride = w_stride; a.w_perm = w_perm ? 1 : 0; a.Wp = W_tc; a.bias0 = bias0; a.alpha_dot = alpha_dot; a.edge_logit = edge_logit;
+    a.w = w; a.w_stride = w_stride; a.w_perm = (w_perm & DEDF_TPACT_W_PERM) ? 1 : 0; a.Wp = W_tc; a.bias0 = bias0; a.alpha_dot = alpha_dot; a.edge_logit = edge_logit;
     a.logits = logits; a.out = out; a.dbg = g_ta_dbg;
-    if (mul1 == 32) return launch_tp_act_tc<32>(a, max_edges, stream);
-    if (mul1 == 16) return launch_tp_act_tc<16>(a, max_edges, stream);
+    const bool f16 = (w_perm & DEDF_TPACT_F16) != 0;
+    if (mul1 == 32) return f16 ? launch_tp_act_tc<32, true>(a, max_edges, stream) : launch_tp_act_tc<32, false>(a, max_edges, stream);
+    if (mul1 == 16) return f16 ? launch_tp_act_tc<16, true>(a, max_edges, stream) : launch_tp_act_tc<16, false>(a, max_edges, stream);
     return DEDF_ERR_UNSUPPORTED;
 }

@@ -46,21 +46,29 @@ class _Packed:
         return self._val
 
 
-def pack_tc(W: torch.Tensor) -> torch.Tensor:
+def pack_tc(W: torch.Tensor, f16: bool = False) -> torch.Tensor:
     """(K, N) "in x out" fp32 weights -> the tensor-core kernel's B-operand stream (include/dedf.h, dedf_mlp_desc.W_tc):
-    tf32 hi / lo split, N blocks of <= 256 columns, 8-wide K chunks, each part chunk-major [2][Nb][4]."""
+    tf32 hi / lo split, N blocks of <= 256 columns, 8-wide K chunks, each part chunk-major [2][Nb][4].
+    ``f16``: fp16 hi / lo split (hi = fp16(w), lo = fp16(w - hi)), 16-wide K chunks, each part [2][Nb][8 halves] -- byte for byte
+    the same chunk shape; returned as a float32 VIEW of the half buffer."""
     K, N = W.shape
     nb = (N + 255) // 256
     assert K % 8 == 0 and N % nb == 0
     nbw = N // nb
     W = W.detach().contiguous().float()
+    if f16:
+        assert K % 16 == 0
+        hi = W.half()
+        parts = torch.stack([hi, (W - hi.float()).half()])           # (2, K, N)
+        v = parts.view(2, K // 16, 2, 8, nb, nbw)                    # [part, kc, j, r, nb, n]
+        return v.permute(4, 1, 0, 2, 5, 3).contiguous().view(-1).view(torch.float32)
     hi = (W.view(torch.int32) & -8192).view(torch.float32)          # clear the 13 low mantissa bits
     parts = torch.stack([hi, W - hi])                                # (2, K, N)
     v = parts.view(2, K // 8, 2, 4, nb, nbw)                         # [part, kc, j, r, nb, n]
     return v.permute(4, 1, 0, 2, 5, 3).contiguous().view(-1)         # [nb, kc, part, j, n, r]
 
 
-def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor) -> torch.Tensor:
+def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor, f16: bool = False) -> torch.Tensor:
     """Block-diagonal weights of the attention block's per-edge linear layer -> the B-operand stream of dedf_edge_tp_act_tc.
 
     W0 (D0, N0) = [sep_alpha | sep_act.lin 0e], W1 (D1, m1), W2 (D2, m2), rows in the depthwise tensor product's i_out order
@@ -72,7 +80,11 @@ def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor)
         l_out=1 (24): group i = [k3 p, k5 p, k7 p, k1 a];  group 4 = [k1 b_0..b_3];  group 5 = [k10 q0, k13 q0, k10 q1, k13 q1]
         l_out=2 (24): group i = [k2 a, k2 b, k6 p, k8 p];  group 4+t = [k9 q_t, k11 q_t, k14 q_t, 0]
     Each block is stored chunk-major [K/4][N padded to 16][4], the chunk as [l0 | l1+l2 | l2] hi then the same for lo; the
-    middle block holds the l_out=1 and l_out=2 weights side by side (the m = 4 rows of the 2e output share the 1e MMA)."""
+    middle block holds the l_out=1 and l_out=2 weights side by side (the m = 4 rows of the 2e output share the 1e MMA).
+
+    ``f16``: the fp16 hi / lo pack of the kind::f16 kernel variant -- chunks 2jj and 2jj+1 share one stage, the 16-byte K-group of a
+    row holding the four values of the even chunk then the four of the odd one as halves ([K/4][N][8] halves: byte-for-byte the
+    shape of a tf32 chunk), hi = fp16(w), lo = fp16(w - hi); returned as a float32 VIEW of the half buffer."""
     M0, M1, M2 = 2 * G, G, G // 2
     C0 = dict(k0=0, k4=M0, k12=M0 + M1)
     C1 = dict(k1=0, k3=M0, k5=M0 + M1, k7=M0 + 2 * M1, k10=M0 + 3 * M1, k13=M0 + 3 * M1 + M2)
@@ -117,8 +129,18 @@ def pack_tp_act_tc(G: int, W0: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor)
         for t in range(2):
             r2 += [C2["k9"] + q[t], C2["k11"] + q[t], C2["k14"] + q[t], None]
         full = torch.cat([block(W0, r0), block2(W1, r1, W2, r2), block(W2, r2)])
+        if f16:
+            chunks.append(full)
+            continue
         hi = (full.view(torch.int32) & -8192).view(torch.float32)
         chunks += [hi, full - hi]
+    if f16:
+        parts = []
+        for jj in range(len(chunks) // 2):
+            pair = torch.cat([chunks[2 * jj].view(-1, 4), chunks[2 * jj + 1].view(-1, 4)], dim=1)        # (K-groups x N, 8)
+            hi = pair.half()
+            parts += [hi.reshape(-1), (pair - hi.float()).half().reshape(-1)]
+        return torch.cat(parts).contiguous().view(torch.float32).to(dev)
     return torch.cat(chunks).contiguous().to(dev)
 
 
@@ -297,12 +319,23 @@ class RadialProfile(nn.Module):
                 b[-1] = b[-1][pm].contiguous() if b[-1] is not None else None
                 off = off[pm].contiguous()
             Wtc = [pack_tc(w) for w in W] if tc_mlp_ok(self.ch_list) else None
-            return W, b, g, bb, off, Wtc
+            Wtc16 = [pack_tc(w, f16=True) for w in W] if Wtc is not None and all(k % 16 == 0 for k in self.ch_list[:-1]) else None
+            return W, b, g, bb, off, Wtc, Wtc16
         return (self._packed_perm if perm is not None else self._packed).get(self, build)
 
-    def fill_desc(self, d: L.MlpDesc, first_layer: int = 0) -> None:
-        """Describe the MLP layers starting at slot ``first_layer`` of ``d`` (dims[first_layer] must be ch_list[0])."""
-        W, b, g, bb, off, Wtc = self.packed()
+    def f16_ok(self) -> bool:
+        """fp16 hi / lo split on the tensor cores (ops.MLP_F16) possible for these layer widths?"""
+        return ops.MLP_F16 and self.packed()[6] is not None
+
+    def fill_desc(self, d: L.MlpDesc, first_layer: int = 0, f16: Optional[bool] = None) -> None:
+        """Describe the MLP layers starting at slot ``first_layer`` of ``d`` (dims[first_layer] must be ch_list[0]).
+        ``f16``: hand over the fp16 packs (None: whenever possible; a caller that adds layers of its own in front decides)."""
+        W, b, g, bb, off, Wtc, Wtc16 = self.packed()
+        if f16 is None:
+            f16 = self.f16_ok()
+        if f16:
+            Wtc = Wtc16
+        d.tc_f16 = 1 if f16 else 0
         n = len(W)
         assert first_layer + n <= L.MLP_MAX_LAYERS
         for i in range(n):
@@ -418,7 +451,8 @@ class GraphAttention(nn.Module):
             G = self.irreps_emb.m[1]
             d1, d2 = dtp_out(self.irreps_emb).m[1], dtp_out(self.irreps_emb).m[2]
             Wtc = pack_tp_act_tc(G, W0, l1.view(d1, -1), l2.view(d2, -1)) if G in (16, 32) else None
-            return dict(W0=W0, W1=l1, W2=l2, Wtc=Wtc, b0=b0, alpha_dot=self.alpha_dot.detach().reshape(-1).contiguous(),
+            Wtc16 = pack_tp_act_tc(G, W0, l1.view(d1, -1), l2.view(d2, -1), f16=True) if G in (16, 32) else None
+            return dict(W0=W0, W1=l1, W2=l2, Wtc=Wtc, Wtc16=Wtc16, b0=b0, alpha_dot=self.alpha_dot.detach().reshape(-1).contiguous(),
                         wv=self.sep_value.dtp.tp.weight.detach().contiguous(), V0=v0, V1=v1, V2=v2, vb=vb)
         return self._packed.get(self, build)
 
@@ -440,8 +474,9 @@ class GraphAttention(nn.Module):
         v = torch.empty(E, F, dtype=torch.float32, device=dev)
         if ops.USE_TC_TPACT and p["Wtc"] is not None:
             # ``w`` comes from self.sep_act.dtp_rad, whose kernel-side output is in the chunk-major column order while the flag is on
-            ops.edge_tp_act_tc(G, msg_src, msg_dst, g, sh, w, self.sep_act.numel, p["Wtc"], p["b0"], p["alpha_dot"], edge_logit, logits, v,
-                               w_perm=self.sep_act.dtp_rad.permuted() if w_perm is None else w_perm)
+            f16 = ops.TPACT_F16 and p.get("Wtc16") is not None
+            ops.edge_tp_act_tc(G, msg_src, msg_dst, g, sh, w, self.sep_act.numel, p["Wtc16"] if f16 else p["Wtc"], p["b0"], p["alpha_dot"],
+                               edge_logit, logits, v, w_perm=self.sep_act.dtp_rad.permuted() if w_perm is None else w_perm, f16=f16)
         else:
             if self.sep_act.dtp_rad.permuted() if w_perm is None else w_perm:
                 raise L.DedfError("tensor-product weights in chunk-major column order need dedf_edge_tp_act_tc")

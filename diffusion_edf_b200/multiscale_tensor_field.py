@@ -93,6 +93,7 @@ class MultiscaleTensorField(nn.Module):
         self.fused_family = self.gnn_block_init.ga.fused_family
         self._pre_cache = (None, None)
         self._pre_tc = None
+        self._pre_tc16 = None
         self._sin_freq = None
 
     # ------------------------------------------------------------------ packed params
@@ -108,6 +109,8 @@ class MultiscaleTensorField(nn.Module):
                 # tensor-core layout of the length halves, all scales back to back (dedf_mlp_desc.pre_w_tc)
                 dims = [ld] + list(self.gnn_block_init.ga.sep_act.dtp_rad.ch_list)
                 self._pre_tc = torch.cat([pack_tc(w) for w in wl]).contiguous() if tc_mlp_ok(dims) else None
+                self._pre_tc16 = (torch.cat([pack_tc(w, f16=True) for w in wl]).contiguous()
+                                  if self._pre_tc is not None and ld % 16 == 0 else None)
             self._pre_cache = (key, (wl, wt, b))
         return self._pre_cache[1]
 
@@ -228,8 +231,9 @@ class MultiscaleTensorField(nn.Module):
         w = torch.empty(E, self.gnn_block_init.ga.sep_act.numel, dtype=torch.float32, device=dev)
         if ops.USE_TC_MLP and self._pre_tc is not None:
             # tensor cores: pre-linear + RadialProfile in ONE launch (the (E, K) pre-linear output stays on chip)
-            rad.fill_desc(d, 1)
-            d.pre_w_tc = L.ptr(self._pre_tc)
+            f16 = self._pre_tc16 is not None and rad.f16_ok()
+            rad.fill_desc(d, 1, f16=f16)
+            d.pre_w_tc = L.ptr(self._pre_tc16 if f16 else self._pre_tc)
             d.out = L.ptr(w)
             ops.edge_mlp_tc(d, g.n_edges)
         else:

@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, NamedTuple, Optional, Sequence, Tuple
 
 import torch
@@ -415,6 +416,10 @@ def edge_geom(x_src: torch.Tensor, x_dst: torch.Tensor, g: Csr, radii: Optional[
 
 USE_VALUE_REDUCE = True     # value path reassociated: linear once per destination (dedf_value_reduce) instead of once per edge
 USE_TC_TPACT = True     # attention logits + gated values: block-diagonal linear on the tensor cores (dedf_edge_tp_act_tc)
+# fp16 hi / lo operand split on kind::f16 instead of the tf32 split (same accuracy for |operands| < 65504, half the shared-memory
+# traffic: include/dedf.h, DEDF_TPACT_F16); DEDF_TPACT_F16=0 selects the tf32 split
+TPACT_F16 = os.environ.get("DEDF_TPACT_F16", "1") != "0"
+MLP_F16 = os.environ.get("DEDF_MLP_F16", "1") != "0"        # the same for dedf_edge_mlp_tc (dedf_mlp_desc.tc_f16)
 USE_TC_MLP = True       # per-edge MLPs on the tcgen05 tensor cores (3xTF32) where the layer widths allow it
 
 
@@ -438,12 +443,12 @@ def edge_tp_lin(mul1: int, epilogue: int, x_src: torch.Tensor, x_dst: Optional[t
 
 def edge_tp_act_tc(mul1: int, x_src: torch.Tensor, x_dst: Optional[torch.Tensor], g: Csr, sh: torch.Tensor, w: torch.Tensor,
                    w_stride: int, W_tc: torch.Tensor, bias0, alpha_dot, edge_logit, logits: torch.Tensor, out: torch.Tensor,
-                   w_perm: bool = False) -> None:
+                   w_perm: bool = False, f16: bool = False) -> None:
     """dedf_edge_tp_lin(EPI_ACT) with the linear layer on the tcgen05 tensor cores.  ``w_perm``: the columns of ``w`` are in
-    the kernel's chunk-major order (layers.tp_act_w_perm)."""
+    the kernel's chunk-major order (layers.tp_act_w_perm); ``f16``: ``W_tc`` is the fp16 hi / lo pack (kind::f16 variant)."""
     _flops("dedf_edge_tp_act_tc", g.n_edges * _tp_act_flops(mul1))
     _call("dedf_edge_tp_act_tc", mul1, ptr(x_src), ptr(x_dst), ptr(g.edge_src, torch.int32), ptr(g.edge_dst, torch.int32),
-          ptr(g.n_edges_dev, torch.int32), g.n_edges, ptr(sh), ptr(w), w_stride, 1 if w_perm else 0, ptr(W_tc), ptr(bias0), ptr(alpha_dot),
+          ptr(g.n_edges_dev, torch.int32), g.n_edges, ptr(sh), ptr(w), w_stride, (1 if w_perm else 0) | (2 if f16 else 0), ptr(W_tc), ptr(bias0), ptr(alpha_dot),
           ptr(edge_logit), ptr(logits), ptr(out), stream())
 
 

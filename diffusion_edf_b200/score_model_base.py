@@ -179,7 +179,7 @@ class ScoreModelBase(nn.Module):
         # is read once after the loop.
         from .denoise import DenoiseGraph
         key = (nT, total, tuple(int(v) for v in sources[2]), tuple(grasp_pcd.x.shape), noise is not None, str(dev), len(sources),
-               self._param_signature(), ops.USE_TC_MLP, ops.USE_TC_TPACT, ops.USE_VALUE_REDUCE, ops.USE_NODE_CHAIN)
+               self._param_signature(), ops.USE_TC_MLP, ops.MLP_F16, ops.USE_TC_TPACT, ops.TPACT_F16, ops.USE_VALUE_REDUCE, ops.USE_NODE_CHAIN)
         dg = self._denoise_graphs.get(key)
         if dg is None:
             if len(self._denoise_graphs) >= 2:
@@ -224,8 +224,9 @@ class ScoreModelBase(nn.Module):
             c = getattr(m, "_packed", None)
             if c is not None and getattr(c, "_val", None) is not None:
                 walk(c._val)
-            if isinstance(getattr(m, "_pre_tc", None), torch.Tensor):
-                out.append(m._pre_tc)
+            for name in ("_pre_tc", "_pre_tc16"):
+                if isinstance(getattr(m, name, None), torch.Tensor):
+                    out.append(getattr(m, name))
             for name in ("_time_cache", "_tp_cache", "_pre_cache"):      # (key, value) caches of the head / field
                 c = getattr(m, name, None)
                 if isinstance(c, tuple) and len(c) == 2 and c[1] is not None:

@@ -125,6 +125,10 @@ typedef struct dedf_mlp_desc {
      * (diffusion_edf_b200/layers.py pack_tc).  pre_w_tc: the n_scales first-layer matrices of FIELD mode, back to back. */
     const float* W_tc[DEDF_MLP_MAX_LAYERS];
     const float* pre_w_tc;
+    /* != 0: W_tc / pre_w_tc are the fp16 hi / lo packs (pack_tc(..., f16=True): 16-wide K chunks of 8-half groups) and the
+     * products run on kind::f16 (three MMAs per K = 16; same accuracy as the tf32 split for |operands| < 65504, half the MMAs and
+     * half the weight bytes streamed per tile).  Needs dims[i] % 16 == 0 for every layer input. */
+    int tc_f16;
 } dedf_mlp_desc;
 
 /* RadialProfile MLP on the edge scalars (equiformer/radial_func.py:56-59) fused with the computation of its
@@ -156,8 +160,13 @@ int dedf_edge_tp_lin(int mul1, int epilogue, const float* x_src, const float* x_
  * inputs, same outputs (graph_attention.py:231-246).  W_tc: the block-diagonal weights [sep_alpha | sep_act.lin] packed
  * per channel chunk as tf32 hi / lo B operands (diffusion_edf_b200/layers.py: pack_tp_act_tc documents the order);
  * bias0 (MA + m0 + m1 + m2) as for dedf_edge_tp_lin.  Gathers only (no per-edge x); x_src, x_dst, w 16-byte aligned,
- * w_stride % 4 == 0.  w_perm != 0: the columns of w are in the kernel's chunk-major order (layers.tp_act_w_perm: the
- * producer of w - the radial MLP - permutes its last layer), which turns 9 / 6 scalar gathers per lane into 3 vector ones. */
+ * w_stride % 4 == 0.  w_perm is a bit set: DEDF_TPACT_W_PERM = the columns of w are in the kernel's chunk-major order
+ * (layers.tp_act_w_perm: the producer of w - the radial MLP - permutes its last layer), which turns 9 / 6 scalar gathers per lane
+ * into 3 vector ones; DEDF_TPACT_F16 = W_tc is the fp16 hi / lo pack (layers.pack_tp_act_tc(..., f16=True)) and the products run
+ * on kind::f16 (x = fp16 hi + fp16 lo, three MMAs per K = 16, fp32 accumulate: the accuracy of the tf32 split at half the
+ * shared-memory traffic; operands must stay below 65504 in magnitude, larger ones come out as NaN). */
+#define DEDF_TPACT_W_PERM 1
+#define DEDF_TPACT_F16 2
 int dedf_edge_tp_act_tc(int mul1, const float* x_src, const float* x_dst, const int* edge_src, const int* edge_dst,
                         const int* n_edges_dev, int max_edges, const float* sh, const float* w, long long w_stride,
                         int w_perm, const float* W_tc, const float* bias0, const float* alpha_dot, const float* edge_logit,

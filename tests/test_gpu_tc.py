@@ -49,7 +49,7 @@ def test_edge_mlp_tc_rbf(cuda, fc, numel, r, E):
     ld = length.to(cuda)
     m, s, w = (p_rbf.mean.detach().reshape(-1), p_rbf.std_logit.detach().reshape(-1), p_rbf.weight_logit.detach().reshape(-1))
     outs = []
-    for tc in (True, False):
+    for tc, f16 in ((True, False), (False, False), (True, True)):
         out = torch.full((E, numel), float("nan"), device=cuda)
         d = L.MlpDesc()
         d.mode = L.MLP_IN_RBF
@@ -57,15 +57,17 @@ def test_edge_mlp_tc_rbf(cuda, fc, numel, r, E):
         d.length = L.ptr(ld)
         d.rbf_mean, d.rbf_std_logit, d.rbf_weight_logit = L.ptr(m), L.ptr(s), L.ptr(w)
         d.rbf_cutoff, d.rbf_offset = p_rbf.cutoff, p_rbf.offset
-        p_rad.fill_desc(d, 0)
+        p_rad.fill_desc(d, 0, f16=f16)
         d.out = L.ptr(out)
-        assert d.W_tc[0]
+        assert d.W_tc[0] and d.tc_f16 == int(f16)
         (ops.edge_mlp_tc if tc else ops.edge_mlp)(d, E)
         outs.append(out)
-    e_tc, e_f32 = rel_err(outs[0], ref), rel_err(outs[1], ref)
-    assert e_tc <= 1e-4, f"tensor-core MLP vs oracle: {e_tc:.3e}"
+    e_tc, e_f32, e_f16 = rel_err(outs[0], ref), rel_err(outs[1], ref), rel_err(outs[2], ref)
+    assert e_tc <= 1e-4, f"tensor-core MLP (tf32 split) vs oracle: {e_tc:.3e}"
+    assert e_f16 <= 1e-4, f"tensor-core MLP (fp16 split) vs oracle: {e_f16:.3e}"
     assert e_f32 <= 1e-4
     assert rel_err(outs[0], outs[1]) <= 2e-5, "tensor-core (3xTF32) vs CUDA-core fp32 kernel"
+    assert rel_err(outs[2], outs[1]) <= 2e-5, f"tensor-core (3xFP16) vs CUDA-core fp32 kernel: {rel_err(outs[2], outs[1]):.3e}"
 
 
 def test_edge_mlp_tc_capacity_exceeds_edges(cuda):
@@ -111,25 +113,28 @@ def test_tensor_field_tc_vs_fp32(cuda, shared_time):
     with torch.no_grad():
         keys = model.get_key_pcd_multiscale(key)
         q = model.get_query_pcd(grasp)
-        for tc in (True, False):
-            ops.USE_TC_MLP = tc
+        for tc, f16 in ((True, True), (False, True), (True, False)):
+            ops.USE_TC_MLP, ops.MLP_F16 = tc, f16
             try:
                 time = t[:1].to(cuda) if shared_time else t.to(cuda)
                 res.append(model.score_head(Ts=Ts.to(cuda), key_pcd_multiscale=keys, query_pcd=q, time=time, shared_time=shared_time))
             finally:
-                ops.USE_TC_MLP = True
-    for a, b in zip(res[0], res[1]):
-        assert rel_err(a, b) <= 2e-5
+                ops.USE_TC_MLP, ops.MLP_F16 = True, True
+    for other in (res[0], res[2]):          # fp16 split, tf32 split   vs   the CUDA-core fp32 MLP
+        for a, b in zip(other, res[1]):
+            assert rel_err(a, b) <= 2e-5
 
 
 # --------------------------------------------------------------------------- attention logits + gated values (dedf_edge_tp_act_tc)
 @pytest.mark.parametrize("G,E,use_dst,use_logit", [(32, 1, True, True), (32, 333, True, True), (32, 64, False, False),
                                                    (16, 777, True, False), (16, 31, False, True), (32, 21_001, True, True),
                                                    (16, 30_000, True, True)])
-def test_edge_tp_act_tc(cuda, G, E, use_dst, use_logit):
+@pytest.mark.parametrize("f16", [False, True], ids=["tf32x3", "f16x3"])
+def test_edge_tp_act_tc(cuda, G, E, use_dst, use_logit, f16):
     """gather -> depthwise TP -> [sep_alpha | sep_act.lin] -> SmoothLeakyReLU.alpha_dot / Gate (graph_attention.py:231-246)
     with the linear layer on the tensor cores, against the oracle arithmetic (small cases) and the fp32 CUDA-core kernel
-    (every case): one edge, ragged last tile, several tiles per CTA (both TMEM accumulator buffers and ring wrap-around)."""
+    (every case): one edge, ragged last tile, several tiles per CTA (both TMEM accumulator buffers and ring wrap-around); with
+    the tf32 hi / lo split and with the fp16 hi / lo split (kind::f16, two chunks per operand stage)."""
     from diffusion_edf_b200 import _lib as L, layers, ops
     from oracle import model as OM
     from oracle import nn as ON
@@ -164,7 +169,8 @@ def test_edge_tp_act_tc(cuda, G, E, use_dst, use_logit):
     dv = lambda t: None if t is None else t.to(cuda)
     logits = torch.full((E, 4), float("nan"), device=cuda)
     v = torch.full((E, F), float("nan"), device=cuda)
-    ops.edge_tp_act_tc(G, dv(msg_src), dv(msg_dst), csr, dv(sh), dv(w), numel, p["Wtc"], p["b0"], p["alpha_dot"], dv(edge_logit), logits, v)
+    Wtc = p["Wtc16"] if f16 else p["Wtc"]
+    ops.edge_tp_act_tc(G, dv(msg_src), dv(msg_dst), csr, dv(sh), dv(w), numel, Wtc, p["b0"], p["alpha_dot"], dv(edge_logit), logits, v, f16=f16)
     logits2 = torch.empty(E, 4, device=cuda)
     v2 = torch.empty(E, F, device=cuda)
     ops.edge_tp_lin(G, L.EPI_ACT, dv(msg_src), dv(msg_dst), False, csr, dv(sh), dv(w), numel, p["W0"], p["W1"], p["W2"], p["b0"],
@@ -185,12 +191,12 @@ def test_edge_tp_act_tc(cuda, G, E, use_dst, use_logit):
     # same launch twice: bit-identical; per-edge weights handed over in the kernel's chunk-major column order: bit-identical too
     logits3 = torch.empty(E, 4, device=cuda)
     v3 = torch.empty(E, F, device=cuda)
-    ops.edge_tp_act_tc(G, dv(msg_src), dv(msg_dst), csr, dv(sh), dv(w), numel, p["Wtc"], p["b0"], p["alpha_dot"], dv(edge_logit), logits3, v3)
+    ops.edge_tp_act_tc(G, dv(msg_src), dv(msg_dst), csr, dv(sh), dv(w), numel, Wtc, p["b0"], p["alpha_dot"], dv(edge_logit), logits3, v3, f16=f16)
     assert torch.equal(logits, logits3) and torch.equal(v, v3)
     w_perm = w[:, layers.tp_act_w_perm(G)].contiguous()
     logits3.fill_(float("nan")); v3.fill_(float("nan"))
-    ops.edge_tp_act_tc(G, dv(msg_src), dv(msg_dst), csr, dv(sh), dv(w_perm), numel, p["Wtc"], p["b0"], p["alpha_dot"], dv(edge_logit), logits3, v3,
-                       w_perm=True)
+    ops.edge_tp_act_tc(G, dv(msg_src), dv(msg_dst), csr, dv(sh), dv(w_perm), numel, Wtc, p["b0"], p["alpha_dot"], dv(edge_logit), logits3, v3,
+                       w_perm=True, f16=f16)
     assert torch.equal(logits, logits3) and torch.equal(v, v3)
 
 
