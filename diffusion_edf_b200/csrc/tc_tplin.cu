@@ -160,6 +160,202 @@ template <> struct TaStore<true> {      // odd: 0 / 1 = which half of the 16-byt
     }
 };
 
+// One tile's worth of a producer warp's work.  pr = 0..5: the warp's role (0-3: two l=0 channels + one l=1 channel of the chunk,
+// 4-5: one l=2 channel); grp / NGRP / MASK: the warp's producer group handles the chunks whose bit is set in MASK.
+//   NGRP = 1: one group of 6 warps takes every chunk, the x-slice staging buffer is double-buffered by chunk parity, one named
+//             barrier per chunk; an fp16 stage is complete after the odd chunk of its pair (6 arrivals).
+//   NGRP = 2 (fp16 split only): group 0 = warps 0-5, group 1 = the epilogue warps 8-13, which produce their share of a tile before
+//             they run its epilogue.  A chunk fills one HALF of an operand stage (even / odd chunk of the pair), whichever group it
+//             belongs to: every half ends with a fence + 6 arrivals, a stage is complete at 12.  The stage and its mbarrier parity
+//             follow from the running pair count (pair_base + j / 2).  Each group owns ONE staging buffer (index grp), so a second
+//             barrier separates the reads of a chunk's slice from staging the next.
+// Every load below has lane = edge, i.e. 32 different rows per instruction: what bounds the producers is the NUMBER of gather
+// instructions.  The chunk's slice of the message row (x_src[src] + x_dst[dst]: 8 + 12 + 10 floats) is therefore fetched as
+// 8 float4 slices spread over the 6 warps, staged in shared memory and read back by the warp that needs it; the per-edge radial
+// weights come as 3 float4 / 3 float2 per lane when the caller permuted their columns chunk-major (w_perm).
+template <int G, bool F16, int NGRP, uint32_t MASK>
+__device__ __forceinline__ void ta_produce_tile(const TpActArgs& a, int E, int tile, int pr, int grp, int lane, unsigned char* sA,
+                                                float* s_x, uint64_t* fullA, uint64_t* emptyA, uint32_t& st, uint32_t& ph, uint32_t pair_base) {
+    using C = TaCfg<G>;
+    using D = Dtp<G>;
+    using S = TaStore<F16>;
+    constexpr int NCH = C::NCH;
+    static_assert(NGRP == 1 || F16, "two producer groups fill the two halves of an fp16 stage");
+    const int e = lane;
+    auto prod_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(kTaProdWarps * 32) : "memory"); };
+    auto xbuf = [&](int j) { return NGRP == 1 ? (j & 1) : grp; };
+    static_assert(MASK != 0 && (MASK >> NCH) == 0, "chunk mask");
+    const int j_first = __ffs((int)MASK) - 1;
+    auto j_next = [&](int j) { const uint32_t rest = MASK >> (j + 1); return rest ? j + __ffs((int)rest) : NCH; };
+    static_assert(kTaStages == 2, "stage = pair count & 1");
+    if (NGRP == 2) { st = 0; ph = 0; }      // (unused: the stage of a chunk follows from the pair count)
+    auto stage_of = [&](int j) { return NGRP == 2 ? ((pair_base + (uint32_t)(j >> 1)) & 1u) : st; };
+    auto wait_par = [&](int j) { return NGRP == 2 ? ((((pair_base + (uint32_t)(j >> 1)) >> 1) & 1u) ^ 1u) : (ph ^ 1u); };
+    const int sliceA = pr, sliceB = (pr < 2) ? 6 + pr : -1;
+    auto slice_off = [&](int j, int sl) {
+        return (sl < 2) ? 8 * j + 4 * sl : (sl < 5) ? D::M0 + 12 * j + 4 * (sl - 2) : D::M0 + 3 * D::M1 + 10 * j - 2 * (j & 1) + 4 * (sl - 5);
+    };
+    const int e0 = tile * kTaTE;
+    const bool ok = e0 + e < E;
+    const int eg = ok ? e0 + e : E - 1;
+    const int src = a.edge_src[eg], dst = a.edge_dst[eg];
+    float sh[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) sh[i] = ok ? a.sh[(size_t)eg * 9 + i] : 0.f;
+    const float* xs = a.x_src + (size_t)src * D::F;
+    const float* xd = a.x_dst ? a.x_dst + (size_t)dst * D::F : nullptr;
+    const float* wr = a.w + (size_t)eg * a.w_stride;
+    const float okf = ok ? 1.f : 0.f;
+    // the source and destination halves of a message slice stay in separate registers until stx() adds them: the adds (the
+    // first USE of the gathered values) then sit a whole chunk of math behind the loads instead of right after them
+    // (ncu source view: the producers' long-scoreboard samples were on exactly those adds)
+    float4 xa, xb = make_float4(0.f, 0.f, 0.f, 0.f), xad = make_float4(0.f, 0.f, 0.f, 0.f), xbd = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ldx = [&](int j) {
+        const int oa = slice_off(j, sliceA);
+        xa = *reinterpret_cast<const float4*>(xs + oa);
+        if (xd) xad = *reinterpret_cast<const float4*>(xd + oa);
+        if (sliceB >= 0) {
+            const int ob = slice_off(j, sliceB);
+            xb = *reinterpret_cast<const float4*>(xs + ob);
+            if (xd) xbd = *reinterpret_cast<const float4*>(xd + ob);
+        }
+    };
+    auto stx = [&](int buf) {
+        float* row = s_x + (buf * kTaTE + e) * kTaXLd;
+        *reinterpret_cast<float4*>(row + 4 * sliceA) = make_float4((xa.x + xad.x) * okf, (xa.y + xad.y) * okf, (xa.z + xad.z) * okf, (xa.w + xad.w) * okf);
+        if (sliceB >= 0) *reinterpret_cast<float4*>(row + 4 * sliceB) = make_float4((xb.x + xbd.x) * okf, (xb.y + xbd.y) * okf, (xb.z + xbd.z) * okf, (xb.w + xbd.w) * okf);
+    };
+    // stage bookkeeping: with one group an fp16 stage is complete after the odd chunk of a pair; with two groups every chunk of a
+    // group is its half of a new stage
+    auto stage_open = [&](int j) { return !F16 || NGRP == 2 || !(j & 1); };
+    auto stage_close = [&](int j) { return !F16 || NGRP == 2 || (j & 1); };
+    if (pr < 4) {
+        const int i = pr;
+#ifdef DEDF_TA_TRACE
+        long long ta_seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+        float2 w0, w1, w2; float w6[6];
+        auto ldw = [&](int j) {
+            if (a.w_perm) {
+                const float4* q = reinterpret_cast<const float4*>(wr + 60 * j + 12 * i);
+                const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+                w0 = make_float2(q0.x, q0.y); w1 = make_float2(q0.z, q0.w); w2 = make_float2(q1.x, q1.y);
+                w6[0] = q1.z; w6[1] = q1.w; w6[2] = q2.x; w6[3] = q2.y; w6[4] = q2.z; w6[5] = q2.w;
+            } else {
+                const int ch = 8 * j + 2 * i, p = 4 * j + i;
+                w0 = *reinterpret_cast<const float2*>(wr + D::W_K0 + ch);
+                w1 = *reinterpret_cast<const float2*>(wr + D::W_K1 + ch);
+                w2 = *reinterpret_cast<const float2*>(wr + D::W_K2 + ch);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) w6[k] = wr[D::W_K3 + p + k * D::M1];
+            }
+        };
+        TA_T0();
+        ldx(j_first); ldw(j_first); stx(xbuf(j_first));
+        prod_sync();
+        TA_SEG(0);
+#pragma unroll 1
+        for (int j = j_first; j < NCH; j = j_next(j)) {
+            const int jn = j_next(j);
+            const float* xrow = s_x + (xbuf(j) * kTaTE + e) * kTaXLd;
+            const float2 xab = *reinterpret_cast<const float2*>(xrow + 2 * i);
+            float x1[3] = {xrow[8 + 3 * i], xrow[9 + 3 * i], xrow[10 + 3 * i]};
+            if (NGRP == 2) prod_sync();                                 // every warp of the group has read the (single) staging buffer
+            if (jn < NCH) ldx(jn);                                      // next chunk's gathers fly during the math and the stores
+            float oa[9], ob[9], o[20];
+            dtp_l0(xab.x, w0.x, w1.x, w2.x, sh, oa);
+            dtp_l0(xab.y, w0.y, w1.y, w2.y, sh, ob);
+            dtp_l1(x1, w6, sh, o);
+            TA_SEG(1);
+            if (jn < NCH) ldw(jn);
+            const int odd = F16 ? (j & 1) : 0;
+            const uint32_t sj = stage_of(j);
+            if (stage_open(j)) tc::mbar_wait_bounded(&emptyA[sj], wait_par(j));
+            TA_SEG(2);
+            unsigned char* hi = sA + sj * kAStage;
+            unsigned char* lo = hi + kAPart;
+            // l_out = 0, group i: [k0 a, k0 b, k4 p, (k12: the l=2 warps)]
+            {
+                const int off = kA0Off + (i * kR0 + e) * 16;
+                S::put2(hi, lo, off, odd, 0, oa[0], ob[0]); S::put1(hi, lo, off, odd, 2, o[3]);
+            }
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {      // l_out = 1, group i: [k3, k5, k7, k1 a]; group 4 column i: k1 b
+                S::put4(hi, lo, kA1Off + (i * kR1 + m * kTaTE + e) * 16, odd, o[m], o[4 + m], o[12 + m], oa[1 + m]);
+                S::put1(hi, lo, kA1Off + (4 * kR1 + m * kTaTE + e) * 16, odd, i, ob[1 + m]);
+            }
+#pragma unroll
+            for (int m = 0; m < 5; ++m)        // l_out = 2, group i: [k2 a, k2 b, k6, k8]; m = 4 rides in rows 96.. of the 1e operand
+                S::put4(hi, lo, m < 4 ? kA2Off + (i * kR2 + m * kTaTE + e) * 16 : kA1Off + (i * kR1 + 3 * kTaTE + e) * 16, odd,
+                        oa[4 + m], ob[4 + m], o[7 + m], o[15 + m]);
+            TA_SEG(3);
+            if (stage_close(j)) {
+                tc::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&fullA[sj]);
+                if (NGRP == 1 && ++st == kTaStages) { st = 0; ph ^= 1u; }
+            }
+            TA_SEG(4);
+            if (jn < NCH) stx(xbuf(jn));
+            TA_SEG(5);
+            prod_sync();
+            TA_SEG(6);
+        }
+#ifdef DEDF_TA_TRACE
+        if (a.dbg && blockIdx.x == 0 && pr == 0 && grp == 0 && lane == 0)
+            for (int k = 0; k < 8; ++k) a.dbg[8 + k] += ta_seg[k];
+#endif
+    } else {
+        const int t = pr - 4;
+        float w6[6];
+        auto ldw = [&](int j) {
+            if (a.w_perm) {
+                const float2* q = reinterpret_cast<const float2*>(wr + 60 * j + 48 + 6 * t);
+                const float2 q0 = q[0], q1 = q[1], q2 = q[2];
+                w6[0] = q0.x; w6[1] = q0.y; w6[2] = q1.x; w6[3] = q1.y; w6[4] = q2.x; w6[5] = q2.y;
+            } else {
+                const int q = 2 * j + t;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) w6[k] = wr[D::W_K9 + q + k * D::M2];
+            }
+        };
+        ldx(j_first); ldw(j_first); stx(xbuf(j_first));
+        prod_sync();
+#pragma unroll 1
+        for (int j = j_first; j < NCH; j = j_next(j)) {
+            const int jn = j_next(j);
+            const float* xrow = s_x + (xbuf(j) * kTaTE + e) * kTaXLd + 20 + 2 * (j & 1) + 5 * t;
+            float x2[5] = {xrow[0], xrow[1], xrow[2], xrow[3], xrow[4]};
+            if (NGRP == 2) prod_sync();
+            if (jn < NCH) ldx(jn);
+            float o[22];
+            dtp_l2(x2, w6, sh, o);
+            if (jn < NCH) ldw(jn);
+            const int odd = F16 ? (j & 1) : 0;
+            const uint32_t sj = stage_of(j);
+            if (stage_open(j)) tc::mbar_wait_bounded(&emptyA[sj], wait_par(j));
+            unsigned char* hi = sA + sj * kAStage;
+            unsigned char* lo = hi + kAPart;
+            S::put1(hi, lo, kA0Off + (t * kR0 + e) * 16, odd, 3, o[13]);       // l_out = 0, group t, column 3: k12
+#pragma unroll
+            for (int m = 0; m < 3; ++m)        // l_out = 1, group 5, columns 2t, 2t+1: [k10, k13]
+                S::put2(hi, lo, kA1Off + (5 * kR1 + m * kTaTE + e) * 16, odd, 2 * t, o[5 + m], o[14 + m]);
+#pragma unroll
+            for (int m = 0; m < 5; ++m)        // l_out = 2, group 4 + t: [k9, k11, k14, 0]
+                S::put4(hi, lo, m < 4 ? kA2Off + ((4 + t) * kR2 + m * kTaTE + e) * 16 : kA1Off + ((4 + t) * kR1 + 3 * kTaTE + e) * 16, odd,
+                        o[m], o[8 + m], o[17 + m], 0.f);
+            if (stage_close(j)) {
+                tc::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&fullA[sj]);
+                if (NGRP == 1 && ++st == kTaStages) { st = 0; ph ^= 1u; }
+            }
+            if (jn < NCH) stx(xbuf(jn));
+            prod_sync();
+        }
+    }
+}
+
 template <int G, bool F16>
 __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs a) {
     using C = TaCfg<G>;
@@ -167,6 +363,19 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
     using S = TaStore<F16>;
     constexpr int NCH = C::NCH;
     constexpr int NST = F16 ? NCH / 2 : NCH;            // operand stages per tile: one per chunk (tf32) / per chunk pair (fp16)
+    // producer groups (ta_produce_tile).  -DDEDF_TA_NGRP=2 (fp16 split only, NOT the default): the epilogue warps 8-13 produce the odd
+    // chunk of every second pair (chunks 1 and 5 of 8; chunk 1 of 4) before they run the tile's epilogue, warps 0-5 the rest.
+    // Measured at 86 k edges, G = 32: one group 230 us; two groups, even split 243 us; two groups, 6 + 2 split 242 us (G = 16,
+    // 60 k edges: 84 -> 98 us).  With both groups running every segment of a producer's chunk gets slower (stores 819 -> 1045
+    // cycles, the second group needs 3.8 k cycles per chunk instead of 2.6 k): the SM's LSU / issue slots are the bound, not the
+    // latency of one warp's chain, so more producer warps buy nothing.
+#ifndef DEDF_TA_NGRP
+#define DEDF_TA_NGRP 1
+#endif
+    constexpr int NGRP = F16 ? DEDF_TA_NGRP : 1;
+    constexpr uint32_t kAll = (1u << NCH) - 1u;
+    constexpr uint32_t MASK1 = NGRP == 2 ? (NCH == 8 ? 0x22u : 0x2u) : 0u;
+    constexpr uint32_t MASK0 = kAll & ~MASK1;
     static_assert(NCH % 2 == 0, "chunk pairs");
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* sA = smem + C::OffA;
@@ -184,7 +393,7 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
     // ---- one-time setup (overlaps the previous kernel under PDL: parameters only) ----
     if (tid == 0) {
         for (int s = 0; s < kTaStages; ++s) {
-            mbar_init(&fullA[s], kTaProdWarps); mbar_init(&emptyA[s], 1);
+            mbar_init(&fullA[s], kTaProdWarps * NGRP); mbar_init(&emptyA[s], 1);      // NGRP = 2: 6 arrivals per HALF stage
             mbar_init(&fullW[s], 1); mbar_init(&emptyW[s], 1);
         }
         for (int b = 0; b < 2; ++b) { mbar_init(&accFull[b], 1); mbar_init(&accEmpty[b], kTaEpiWarps); }
@@ -205,170 +414,10 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
     const int n_tiles = (E + kTaTE - 1) / kTaTE;
 
     if (warp < kTaProdWarps) {
-        // =========================== producers: CG chunk -> hi / lo A operand ===========================
-        // Every load below has lane = edge, i.e. 32 different rows per instruction: what bounds the producers is the
-        // NUMBER of gather instructions.  The chunk's slice of the message row (x_src[src] + x_dst[dst]: 8 + 12 + 10
-        // floats) is therefore fetched as 8 float4 slices spread over the 6 warps, staged in shared memory (two stages,
-        // one named barrier per chunk) and read back by the warp that needs it; the per-edge radial weights come as
-        // 3 float4 / 3 float2 per lane when the caller permuted their columns chunk-major (w_perm).
-        const int e = lane;
-        uint32_t st = 0, ph = 0;
-        auto prod_sync = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(kTaProdWarps * 32) : "memory"); };
-        const int sliceA = warp, sliceB = (warp < 2) ? 6 + warp : -1;
-        auto slice_off = [&](int j, int sl) {
-            return (sl < 2) ? 8 * j + 4 * sl : (sl < 5) ? D::M0 + 12 * j + 4 * (sl - 2) : D::M0 + 3 * D::M1 + 10 * j - 2 * (j & 1) + 4 * (sl - 5);
-        };
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int e0 = tile * kTaTE;
-            const bool ok = e0 + e < E;
-            const int eg = ok ? e0 + e : E - 1;
-            const int src = a.edge_src[eg], dst = a.edge_dst[eg];
-            float sh[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) sh[i] = ok ? a.sh[(size_t)eg * 9 + i] : 0.f;
-            const float* xs = a.x_src + (size_t)src * D::F;
-            const float* xd = a.x_dst ? a.x_dst + (size_t)dst * D::F : nullptr;
-            const float* wr = a.w + (size_t)eg * a.w_stride;
-            const float okf = ok ? 1.f : 0.f;
-            // the source and destination halves of a message slice stay in separate registers until stx() adds them: the adds (the
-            // first USE of the gathered values) then sit a whole chunk of math behind the loads instead of right after them
-            // (ncu source view: the producers' long-scoreboard samples were on exactly those adds)
-            float4 xa, xb = make_float4(0.f, 0.f, 0.f, 0.f), xad = make_float4(0.f, 0.f, 0.f, 0.f), xbd = make_float4(0.f, 0.f, 0.f, 0.f);
-            auto ldx = [&](int j) {
-                const int oa = slice_off(j, sliceA);
-                xa = *reinterpret_cast<const float4*>(xs + oa);
-                if (xd) xad = *reinterpret_cast<const float4*>(xd + oa);
-                if (sliceB >= 0) {
-                    const int ob = slice_off(j, sliceB);
-                    xb = *reinterpret_cast<const float4*>(xs + ob);
-                    if (xd) xbd = *reinterpret_cast<const float4*>(xd + ob);
-                }
-            };
-            auto stx = [&](int stage) {
-                float* row = s_x + (stage * kTaTE + e) * kTaXLd;
-                *reinterpret_cast<float4*>(row + 4 * sliceA) = make_float4((xa.x + xad.x) * okf, (xa.y + xad.y) * okf, (xa.z + xad.z) * okf, (xa.w + xad.w) * okf);
-                if (sliceB >= 0) *reinterpret_cast<float4*>(row + 4 * sliceB) = make_float4((xb.x + xbd.x) * okf, (xb.y + xbd.y) * okf, (xb.z + xbd.z) * okf, (xb.w + xbd.w) * okf);
-            };
-            if (warp < 4) {
-                const int i = warp;
-#ifdef DEDF_TA_TRACE
-                long long ta_seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
-                float2 w0, w1, w2; float w6[6];
-                auto ldw = [&](int j) {
-                    if (a.w_perm) {
-                        const float4* q = reinterpret_cast<const float4*>(wr + 60 * j + 12 * i);
-                        const float4 q0 = q[0], q1 = q[1], q2 = q[2];
-                        w0 = make_float2(q0.x, q0.y); w1 = make_float2(q0.z, q0.w); w2 = make_float2(q1.x, q1.y);
-                        w6[0] = q1.z; w6[1] = q1.w; w6[2] = q2.x; w6[3] = q2.y; w6[4] = q2.z; w6[5] = q2.w;
-                    } else {
-                        const int ch = 8 * j + 2 * i, p = 4 * j + i;
-                        w0 = *reinterpret_cast<const float2*>(wr + D::W_K0 + ch);
-                        w1 = *reinterpret_cast<const float2*>(wr + D::W_K1 + ch);
-                        w2 = *reinterpret_cast<const float2*>(wr + D::W_K2 + ch);
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) w6[k] = wr[D::W_K3 + p + k * D::M1];
-                    }
-                };
-                TA_T0();
-                ldx(0); ldw(0); stx(0);
-                prod_sync();
-                TA_SEG(0);
-#pragma unroll 1
-                for (int j = 0; j < NCH; ++j) {
-                    const float* xrow = s_x + ((j & 1) * kTaTE + e) * kTaXLd;
-                    const float2 xab = *reinterpret_cast<const float2*>(xrow + 2 * i);
-                    float x1[3] = {xrow[8 + 3 * i], xrow[9 + 3 * i], xrow[10 + 3 * i]};
-                    if (j + 1 < NCH) ldx(j + 1);                           // next chunk's gathers fly during the math and the stores
-                    float oa[9], ob[9], o[20];
-                    dtp_l0(xab.x, w0.x, w1.x, w2.x, sh, oa);
-                    dtp_l0(xab.y, w0.y, w1.y, w2.y, sh, ob);
-                    dtp_l1(x1, w6, sh, o);
-                    TA_SEG(1);
-                    if (j + 1 < NCH) ldw(j + 1);
-                    const int odd = F16 ? (j & 1) : 0;
-                    if (!F16 || !odd) tc::mbar_wait_bounded(&emptyA[st], ph ^ 1u);
-                    TA_SEG(2);
-                    unsigned char* hi = sA + st * kAStage;
-                    unsigned char* lo = hi + kAPart;
-                    // l_out = 0, group i: [k0 a, k0 b, k4 p, (k12: the l=2 warps)]
-                    {
-                        const int off = kA0Off + (i * kR0 + e) * 16;
-                        S::put2(hi, lo, off, odd, 0, oa[0], ob[0]); S::put1(hi, lo, off, odd, 2, o[3]);
-                    }
-#pragma unroll
-                    for (int m = 0; m < 3; ++m) {      // l_out = 1, group i: [k3, k5, k7, k1 a]; group 4 column i: k1 b
-                        S::put4(hi, lo, kA1Off + (i * kR1 + m * kTaTE + e) * 16, odd, o[m], o[4 + m], o[12 + m], oa[1 + m]);
-                        S::put1(hi, lo, kA1Off + (4 * kR1 + m * kTaTE + e) * 16, odd, i, ob[1 + m]);
-                    }
-#pragma unroll
-                    for (int m = 0; m < 5; ++m)        // l_out = 2, group i: [k2 a, k2 b, k6, k8]; m = 4 rides in rows 96.. of the 1e operand
-                        S::put4(hi, lo, m < 4 ? kA2Off + (i * kR2 + m * kTaTE + e) * 16 : kA1Off + (i * kR1 + 3 * kTaTE + e) * 16, odd,
-                                oa[4 + m], ob[4 + m], o[7 + m], o[15 + m]);
-                    TA_SEG(3);
-                    if (!F16 || odd) {                 // fp16: the stage is complete after the odd chunk of the pair
-                        tc::fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&fullA[st]);
-                        if (++st == kTaStages) { st = 0; ph ^= 1u; }
-                    }
-                    TA_SEG(4);
-                    if (j + 1 < NCH) stx((j + 1) & 1);
-                    TA_SEG(5);
-                    prod_sync();
-                    TA_SEG(6);
-                }
-#ifdef DEDF_TA_TRACE
-                if (a.dbg && blockIdx.x == 0 && warp == 0 && lane == 0)
-                    for (int k = 0; k < 8; ++k) a.dbg[8 + k] += ta_seg[k];
-#endif
-            } else {
-                const int t = warp - 4;
-                float w6[6];
-                auto ldw = [&](int j) {
-                    if (a.w_perm) {
-                        const float2* q = reinterpret_cast<const float2*>(wr + 60 * j + 48 + 6 * t);
-                        const float2 q0 = q[0], q1 = q[1], q2 = q[2];
-                        w6[0] = q0.x; w6[1] = q0.y; w6[2] = q1.x; w6[3] = q1.y; w6[4] = q2.x; w6[5] = q2.y;
-                    } else {
-                        const int q = 2 * j + t;
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) w6[k] = wr[D::W_K9 + q + k * D::M2];
-                    }
-                };
-                ldx(0); ldw(0); stx(0);
-                prod_sync();
-#pragma unroll 1
-                for (int j = 0; j < NCH; ++j) {
-                    const float* xrow = s_x + ((j & 1) * kTaTE + e) * kTaXLd + 20 + 2 * (j & 1) + 5 * t;
-                    float x2[5] = {xrow[0], xrow[1], xrow[2], xrow[3], xrow[4]};
-                    if (j + 1 < NCH) ldx(j + 1);
-                    float o[22];
-                    dtp_l2(x2, w6, sh, o);
-                    if (j + 1 < NCH) ldw(j + 1);
-                    const int odd = F16 ? (j & 1) : 0;
-                    if (!F16 || !odd) tc::mbar_wait_bounded(&emptyA[st], ph ^ 1u);
-                    unsigned char* hi = sA + st * kAStage;
-                    unsigned char* lo = hi + kAPart;
-                    S::put1(hi, lo, kA0Off + (t * kR0 + e) * 16, odd, 3, o[13]);       // l_out = 0, group t, column 3: k12
-#pragma unroll
-                    for (int m = 0; m < 3; ++m)        // l_out = 1, group 5, columns 2t, 2t+1: [k10, k13]
-                        S::put2(hi, lo, kA1Off + (5 * kR1 + m * kTaTE + e) * 16, odd, 2 * t, o[5 + m], o[14 + m]);
-#pragma unroll
-                    for (int m = 0; m < 5; ++m)        // l_out = 2, group 4 + t: [k9, k11, k14, 0]
-                        S::put4(hi, lo, m < 4 ? kA2Off + ((4 + t) * kR2 + m * kTaTE + e) * 16 : kA1Off + ((4 + t) * kR1 + 3 * kTaTE + e) * 16, odd,
-                                o[m], o[8 + m], o[17 + m], 0.f);
-                    if (!F16 || odd) {
-                        tc::fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&fullA[st]);
-                        if (++st == kTaStages) { st = 0; ph ^= 1u; }
-                    }
-                    if (j + 1 < NCH) stx((j + 1) & 1);
-                    prod_sync();
-                }
-            }
-        }
+        // =========================== producers (group 0): CG chunk -> hi / lo A operand ===========================
+        uint32_t st = 0, ph = 0, pair_base = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, pair_base += NST)
+            ta_produce_tile<G, F16, NGRP, MASK0>(a, E, tile, warp, 0, lane, sA, s_x, fullA, emptyA, st, ph, pair_base);
     } else if (warp == kTaTmaWarp) {
         // =========================== weight ring ===========================
         if (lane == 0) {
@@ -467,11 +516,27 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
         auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kTaEpiWarps * 32) : "memory"); };
         constexpr int HD = C::MA / 4;
         int it = 0;
+        uint32_t pst = 0, pph = 0;                          // producer-side stage / phase (second producer group)
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t buf = (uint32_t)it & 1u;
             const int e0 = tile * kTaTE;
+            if constexpr (NGRP == 2) {
+                if (warp < kTaEpiWarp0 + kTaProdWarps)                  // this tile's share of the production first, then its epilogue
+                    ta_produce_tile<G, F16, NGRP, MASK1>(a, E, tile, warp - kTaEpiWarp0, 1, lane, sA, s_x, fullA, emptyA, pst, pph,
+                                                         (uint32_t)it * NST);
+            }
+#ifdef DEDF_TA_TRACE
+            const long long ep_c0 = clock64();
+#endif
             tc::mbar_wait_bounded(&accFull[buf], ((uint32_t)it >> 1) & 1u);
             tc::fence_after();
+#ifdef DEDF_TA_TRACE
+            const long long ep_c1 = clock64();
+#endif
+            // the previous tile's value rows have left the staging tile (their bulk stores were issued a whole tile ago: the wait is
+            // free here, at the end of that tile's epilogue it cost the drain time of 30 KB)
+            if (warp == kTaEpiWarp0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            epi_sync();
             const uint32_t tq = tmem_base + buf * (uint32_t)kTaAccCols + ((uint32_t)(q * 32) << 16);
             // ---- phase 1: the 0e GEMM (lane = output channel n, column = edge): logit terms | scalars | gates ----
 #pragma unroll
@@ -545,11 +610,15 @@ __global__ void __launch_bounds__(kTaThreads, 1) edge_tp_act_tc_kernel(TpActArgs
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  ::"l"(a.out + (size_t)(e0 + lane) * D::F), "r"(smem_u32(s_out + lane * C::LDO)), "r"((uint32_t)D::F * 4u) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
-            epi_sync();                                    // staging tile, gate and logit tables reusable
+            // (gate and logit tables: every read of them precedes the barrier above; the staging tile is released at the top of the
+            //  next tile's epilogue)
+#ifdef DEDF_TA_TRACE
+            if (a.dbg && blockIdx.x == 0 && warp == kTaEpiWarp0 && lane == 0) { a.dbg[16] += ep_c1 - ep_c0; a.dbg[17] += clock64() - ep_c1; }
+#endif
         }
     }
+    if (warp == kTaEpiWarp0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory stays valid until the last rows left
     tc::fence_before();
     __syncthreads();
     if (warp == kTaTmaWarp) tc::tmem_dealloc(tmem_base, 2 * kTaAccCols);

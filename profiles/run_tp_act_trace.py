@@ -79,3 +79,4 @@ names = ["tile head (index loads, first gathers)", "x slice LDS + CG math", "nex
 for k, nm in enumerate(names):
     per = d[8 + k] / tiles / (1 if k == 0 else nch)
     print(f"   {nm:42s} {d[8 + k]:10d}   {per:8.0f} cycles per {'tile' if k == 0 else 'chunk'}")
+print(f"   epilogue warp 8: wait for the accumulator {d[16] / tiles:8.0f}, epilogue {d[17] / tiles:8.0f} cycles per tile")
