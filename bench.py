@@ -62,22 +62,28 @@ def _peaks():
 
 
 def _tensor_peak():
-    """dense tf32 tensor peak = half the measured cuBLAS bf16 figure (burst: kernels timed alone)."""
+    """dense tensor peak of the MMA kind the kernels issue (burst: kernels timed alone): the measured cuBLAS bf16 figure for the
+    fp16 hi / lo split (kind::f16, the default), half of it for the tf32 split (DEDF_MLP_F16=0 / DEDF_TPACT_F16=0)."""
+    from diffusion_edf_b200 import ops
+    f16 = ops.MLP_F16 and ops.TPACT_F16
+    k = 1.0 if f16 else 0.5
+    kind = "kind::f16, 3 x fp16 split" if f16 else "kind::tf32, 3xTF32"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
             p = json.load(fh)
-        return 0.5 * float(p["bf16_tflops"]), "0.5 x measured bf16 burst (MEASURED_PEAKS.json)"
+        return k * float(p["bf16_tflops"]), f"{k} x measured bf16 burst (MEASURED_PEAKS.json)", kind
     except Exception:
-        return 0.5 * 1590.0, "0.5 x fallback bf16 (B200_PROFILING.md)"
+        return k * 1590.0, f"{k} x fallback bf16 (B200_PROFILING.md)", kind
 
 
 TENSOR_KERNELS = ("dedf_edge_mlp_tc", "dedf_edge_tp_act_tc")
 
 
 def _roofline_rows(times_ms: dict, flops: dict) -> dict:
-    """Per entry point: algorithmic fp32 FLOPs / time against the pipe that executes them.  tcgen05 kernels run 3xTF32 (three
-    tf32 MMAs per fp32 product): `frac` counts the algorithmic FLOPs, `issued_frac` the tf32 FLOPs actually issued."""
-    tpeak, tsrc = _tensor_peak()
+    """Per entry point: algorithmic fp32 FLOPs / time against the pipe that executes them.  tcgen05 kernels issue three MMAs per
+    fp32 product (hi.hi + lo.hi + hi.lo of the fp16 -- or tf32 -- operand split): `frac` counts the algorithmic FLOPs,
+    `issued_frac` the tensor FLOPs actually issued."""
+    tpeak, tsrc, tkind = _tensor_peak()
     rows = {}
     for name, ms in times_ms.items():
         f = flops.get(name)
@@ -85,12 +91,12 @@ def _roofline_rows(times_ms: dict, flops: dict) -> dict:
             continue
         tf = f / (ms * 1e-3) / 1e12
         if name in TENSOR_KERNELS:
-            rows[name] = {"pipe": "tensor (tcgen05 kind::tf32, 3xTF32)", "gflop": f / 1e9, "ms": ms, "achieved_tflops": tf, "peak_tflops": tpeak,
+            rows[name] = {"pipe": f"tensor (tcgen05 {tkind})", "gflop": f / 1e9, "ms": ms, "achieved_tflops": tf, "peak_tflops": tpeak,
                           "frac": tf / tpeak, "issued_frac": 3 * tf / tpeak}
         else:
             rows[name] = {"pipe": "fp32 FMA", "gflop": f / 1e9, "ms": ms, "achieved_tflops": tf, "peak_tflops": FP32_PEAK_TFLOPS,
                           "frac": tf / FP32_PEAK_TFLOPS}
-    return {"peaks": {"tensor_tf32_tflops": tpeak, "tensor_source": tsrc, "fp32_tflops": FP32_PEAK_TFLOPS,
+    return {"peaks": {"tensor_tflops": tpeak, "tensor_kind": tkind, "tensor_source": tsrc, "fp32_tflops": FP32_PEAK_TFLOPS,
                       "fp32_source": "148 SMs x 128 lanes x 2 x 1.965 GHz (nominal boost)"}, "kernels": rows}
 
 
@@ -593,8 +599,10 @@ def run_cuda(args):
         "metric": METRIC, "value": world * N_POSES / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "precision_note": "fp32 arithmetic throughout; the per-edge MLP GEMMs run on the tcgen05 tensor cores as 3xTF32 (hi/lo split, "
-                          "fp32 accumulation in TMEM), which the parity tests hold to the same 1e-4 bound as the CUDA-core kernels",
+        "precision_note": "fp32 arithmetic throughout; the per-edge MLP and attention-linear GEMMs run on the tcgen05 tensor cores with "
+                          "an fp16 hi/lo operand split (x = fp16(x) + fp16(x - fp16(x)), three kind::f16 MMAs per product, fp32 "
+                          "accumulation in TMEM: 22 significand bits, the accuracy of 3xTF32), which the parity tests hold to the same "
+                          "1e-4 bound as the CUDA-core kernels; DEDF_MLP_F16=0 / DEDF_TPACT_F16=0 select the tf32 split",
         "config": dict(CONFIG),
         "run": {   "parallelism": ("single GPU" if world == 1 else
                                    f"pose-sharded x{world}; rank 0 encodes the scene, 1 NCCL broadcast of the packed field per step" if args.share_encoder else
