@@ -655,7 +655,7 @@ struct ValueReduceArgs {
 constexpr int kVrChunk = 64;
 
 template <int G>
-__global__ void __launch_bounds__(G * 8, 1) value_reduce_kernel(ValueReduceArgs a) {
+__global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(ValueReduceArgs a) {
     using D = Dtp<G>;
     constexpr int NCW = G / 8, NW = 2 * NCW, NT = NW * 32, CH = kVrChunk;
     constexpr int B1 = D::D0, B2 = D::D0 + 3 * D::D1;             // block offsets inside one head copy of the reduced TP output
