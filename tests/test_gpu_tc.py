@@ -226,3 +226,72 @@ def test_full_forward_tc_attention_on_off(cuda):
     for a, b in zip(res[0], res[1]):
         assert torch.isfinite(a).all()
         assert rel_err(a, b) <= 5e-5, rel_err(a, b)
+
+
+def test_full_forward_operand_splits_and_early_query_stream(cuda, monkeypatch):
+    """Whole forward through the CUDA-graph path (a) with the fp16 hi / lo operand split of the two tcgen05 kernels (default) against
+    the tf32 split (ops.MLP_F16 / ops.TPACT_F16 off): same scores to fp32 round-off; (b) with the query model + time embedding on
+    their own stream under the key encoder (default) against the plain stream order (DEDF_EARLY_QUERY=0): the SAME kernels on the
+    same data, so the scores must be EQUAL."""
+    from diffusion_edf_b200 import FeaturedPoints, MultiscaleScoreModel, ops
+    from diffusion_edf_b200.synthetic import make_poses, make_scene, model_kwargs
+    torch.manual_seed(0)
+    model = MultiscaleScoreModel(**model_kwargs(), deterministic=True).eval().to(cuda)
+    x, rgb = make_scene(2500, seed=6, half_extent=12.0)
+    Ts, t = make_poses(23, x, seed=6, spread=6.0)
+    key = FeaturedPoints(x.to(cuda), rgb.to(cuda), torch.zeros(len(x), dtype=torch.long, device=cuda))
+    grasp = FeaturedPoints(torch.zeros(8, 3, device=cuda), torch.zeros(8, 3, device=cuda), torch.zeros(8, dtype=torch.long, device=cuda))
+
+    def run():
+        model._graphs.clear()                       # capture again under the current switches
+        with torch.no_grad():
+            model(Ts.to(cuda), t.to(cuda), key, grasp)                       # plan + capture
+            (ang, lin), _ = model(Ts.to(cuda), t.to(cuda), key, grasp)       # replay
+        return ang.clone(), lin.clone()
+
+    base = run()
+    monkeypatch.setenv("DEDF_EARLY_QUERY", "0")
+    late = run()
+    monkeypatch.delenv("DEDF_EARLY_QUERY")
+    assert torch.equal(base[0], late[0]) and torch.equal(base[1], late[1])
+    ops.MLP_F16 = ops.TPACT_F16 = False
+    try:
+        tf32 = run()
+    finally:
+        ops.MLP_F16 = ops.TPACT_F16 = True
+    for a, b in zip(base, tf32):
+        assert torch.isfinite(a).all() and rel_err(a, b) <= 2e-5, rel_err(a, b)
+
+
+def test_edge_tp_act_tc_fp16_range(cuda):
+    """The fp16 operand split has fp16 RANGE: a depthwise-TP output beyond 65504 must come out non-finite (loud), never as a finite
+    wrong number, and the tf32 split (DEDF_TPACT_F16=0 / f16=False) must still agree with the fp32 CUDA-core kernel there."""
+    from diffusion_edf_b200 import _lib as L, layers, ops
+    from oracle import so3
+    G, E, n_src, n_dst = 32, 96, 50, 7
+    irr = "64x0e+32x1e+16x2e"
+    gen = torch.Generator().manual_seed(11)
+    torch.manual_seed(11)
+    pga = layers.GraphAttention(irr, irr, [32, 16, 16], 4).to(cuda)
+    p = pga.packed()
+    F, numel = pga.irreps_emb.dim, 15 * G
+    es = torch.randint(0, n_src, (E,), generator=gen)
+    ed = torch.randint(0, n_dst, (E,), generator=gen).sort().values
+    row_ptr = torch.zeros(n_dst + 1, dtype=torch.long)
+    row_ptr[1:] = torch.bincount(ed, minlength=n_dst).cumsum(0)
+    rp = row_ptr.int().to(cuda)
+    csr = ops.Csr(rp, es.int().to(cuda), ed.int().to(cuda), rp[-1:], E, n_dst, 1)
+    sh = so3.spherical_harmonics(2, torch.randn(E, 3, generator=gen)).to(cuda)
+    msg = (torch.randn(n_src, F, generator=gen) * 3e5).to(cuda)              # message x harmonic x weight ~ 1e5..1e6 > 65504
+    w = (torch.randn(E, numel, generator=gen) / 3.0 ** 0.5).to(cuda)
+    out = {}
+    for name, f16 in (("f16", True), ("tf32", False)):
+        logits = torch.empty(E, 4, device=cuda); v = torch.empty(E, F, device=cuda)
+        ops.edge_tp_act_tc(G, msg, None, csr, sh, w, numel, p["Wtc16"] if f16 else p["Wtc"], p["b0"], p["alpha_dot"], None, logits, v, f16=f16)
+        out[name] = (logits, v)
+    logits2 = torch.empty(E, 4, device=cuda); v2 = torch.empty(E, F, device=cuda)
+    ops.edge_tp_lin(G, L.EPI_ACT, msg, None, False, csr, sh, w, numel, p["W0"], p["W1"], p["W2"], p["b0"],
+                    alpha_dot=p["alpha_dot"], edge_logit=None, logits=logits2, out=v2)
+    assert torch.isfinite(v2).all()
+    assert not torch.isfinite(out["f16"][1]).all(), "operands beyond the fp16 range must not produce finite values silently"
+    assert torch.isfinite(out["tf32"][1]).all() and rel_err(out["tf32"][1], v2) < 2e-5
