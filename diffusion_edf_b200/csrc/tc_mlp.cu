@@ -1,4 +1,5 @@
-// Tensor-core (tcgen05, kind::tf32, 3xTF32 split) kernels: self-test GEMM and the per-edge MLP.
+// Tensor-core (tcgen05) kernels: self-test GEMM (kind::tf32, 3xTF32 split) and the per-edge MLP (kind::f16 with an fp16 hi / lo
+// operand split by default, kind::tf32 3xTF32 as the F16 = false variant: TcGroup below).
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc.cuh"

@@ -6,8 +6,9 @@
 //   (graph_attention.py:231-246, fast_activation.py:210-224)
 //
 // Same arithmetic and outputs as edge_tp_lin_kernel<G, EPI_ACT> (edge.cu); the block-diagonal linear layer (104 kMAC per
-// edge, 90 % of the FLOPs) moves from the fp32 FMA pipe to tcgen05.mma kind::tf32 with the 3xTF32 split (tc.cuh), fp32
-// accumulators in TMEM.  What makes it fit:
+// edge, 90 % of the FLOPs) moves from the fp32 FMA pipe to tcgen05.mma with a hi / lo operand split (tc.cuh: kind::f16 with fp16
+// halves by default, kind::tf32 with the 3xTF32 split as the F16 = false variant -- see TaStore below), fp32 accumulators in TMEM.
+// What makes it fit (sizes below are those of the tf32 variant; the fp16 one packs two chunks into the same bytes):
 //
 //   * K is consumed in CHUNKS of input channels: chunk j = l=0 channels [8j, 8j+8), l=1 channels [4j, 4j+4), l=2 channels
 //     [2j, 2j+2) (8 chunks for 64x0e+32x1e+16x2e, 4 for 32x0e+16x1e+8x2e).  One chunk contributes 14 / 24 / 22 columns

@@ -420,7 +420,7 @@ USE_TC_TPACT = True     # attention logits + gated values: block-diagonal linear
 # traffic: include/dedf.h, DEDF_TPACT_F16); DEDF_TPACT_F16=0 selects the tf32 split
 TPACT_F16 = os.environ.get("DEDF_TPACT_F16", "1") != "0"
 MLP_F16 = os.environ.get("DEDF_MLP_F16", "1") != "0"        # the same for dedf_edge_mlp_tc (dedf_mlp_desc.tc_f16)
-USE_TC_MLP = True       # per-edge MLPs on the tcgen05 tensor cores (3xTF32) where the layer widths allow it
+USE_TC_MLP = True       # per-edge MLPs on the tcgen05 tensor cores (fp16 or tf32 hi / lo split: MLP_F16 below) where the layer widths allow it
 
 
 def edge_mlp(desc: L.MlpDesc, max_edges: int) -> None:
