@@ -160,11 +160,20 @@ struct ScoreArgs {
 // tail of score_tp_kernel.  z: 6 standard normals or null -> Philox (seed, subsequence = pose, window = step).
 constexpr unsigned long long kPhiloxPerStep = 16;   // cuRAND's Philox offset counts 32-bit outputs and one step draws 3 x
                                                     // curand_normal2_double = 12 of them: steps are 16 outputs apart
-__device__ __forceinline__ void langevin_step(double* T, const float* ang, const float* lin, const double* z_in,
-                                              unsigned long long seed, unsigned long long pose, unsigned long long step,
-                                              double t, double ang_mult, double lin_mult, double alpha_ang, double alpha_lin,
-                                              double temperature) {
-    double z[6];
+// The step in three parts so that the fused tail of score_tp_kernel can compute the two that do not depend on the score -- the
+// noise (Philox + Box-Muller in fp64) and the per-step coefficients (square roots) -- BEFORE it waits for its inputs:
+struct LangevinCoef { double den_a, den_l, c_a, c_l, n_a, n_l; };
+__device__ __forceinline__ LangevinCoef langevin_coef(double t, double ang_mult, double lin_mult, double alpha_ang, double alpha_lin,
+                                                      double temperature) {
+    const double sq_t = sqrt(t);
+    LangevinCoef c;
+    c.den_a = ang_mult * sq_t; c.den_l = lin_mult * sq_t;
+    c.c_a = alpha_ang / 2; c.c_l = alpha_lin / 2;
+    c.n_a = sqrt(temperature * alpha_ang); c.n_l = sqrt(temperature * alpha_lin);
+    return c;
+}
+__device__ __forceinline__ void langevin_noise(const double* z_in, unsigned long long seed, unsigned long long pose,
+                                               unsigned long long step, double* z) {
     if (z_in) {
         for (int k = 0; k < 6; ++k) z[k] = z_in[k];
     } else {
@@ -172,13 +181,14 @@ __device__ __forceinline__ void langevin_step(double* T, const float* ang, const
         curand_init(seed, pose, step * kPhiloxPerStep, &st);
         for (int k = 0; k < 6; k += 2) { double2 n = curand_normal2_double(&st); z[k] = n.x; z[k + 1] = n.y; }
     }
-    const double sq_t = sqrt(t);
+}
+__device__ __forceinline__ void langevin_apply(double* T, const float* ang, const float* lin, const double* z, const LangevinCoef& c) {
     double ang_disp[3], lin_disp[3];
     for (int k = 0; k < 3; ++k) {
-        const double as = (double)ang[k] / (ang_mult * sq_t);
-        const double ls = (double)lin[k] / (lin_mult * sq_t);
-        ang_disp[k] = (alpha_ang / 2) * as + sqrt(temperature * alpha_ang) * z[k];
-        lin_disp[k] = (alpha_lin / 2) * ls + sqrt(temperature * alpha_lin) * z[3 + k];
+        const double as = (double)ang[k] / c.den_a;
+        const double ls = (double)lin[k] / c.den_l;
+        ang_disp[k] = c.c_a * as + c.n_a * z[k];
+        lin_disp[k] = c.c_l * ls + c.n_l * z[3 + k];
     }
     const double q[4] = {T[0], T[1], T[2], T[3]};
     // L = T[q_indices] * q_factor   (score_model_base.py:31-32,188)
@@ -187,7 +197,7 @@ __device__ __forceinline__ void langevin_step(double* T, const float* ang, const
     double qn[4], nrm = 0;
     for (int r = 0; r < 4; ++r) {
         double dq = 0;
-        for (int c = 0; c < 3; ++c) dq += q[qi[r][c]] * qf[r][c] * ang_disp[c];
+        for (int c2 = 0; c2 < 3; ++c2) dq += q[qi[r][c2]] * qf[r][c2] * ang_disp[c2];
         qn[r] = q[r] + dq;
         nrm += qn[r] * qn[r];
     }
@@ -197,21 +207,56 @@ __device__ __forceinline__ void langevin_step(double* T, const float* ang, const
     for (int r = 0; r < 4; ++r) T[r] = qn[r] / nrm;
     for (int k = 0; k < 3; ++k) T[4 + k] += dx[k];
 }
+__device__ __forceinline__ void langevin_step(double* T, const float* ang, const float* lin, const double* z_in,
+                                              unsigned long long seed, unsigned long long pose, unsigned long long step,
+                                              double t, double ang_mult, double lin_mult, double alpha_ang, double alpha_lin,
+                                              double temperature) {
+    double z[6];
+    langevin_noise(z_in, seed, pose, step, z);
+    langevin_apply(T, ang, lin, z, langevin_coef(t, ang_mult, lin_mult, alpha_ang, alpha_lin, temperature));
+}
 
 constexpr int kScoreQB = 2;     // (pose, query node) rows processed together: every weight load serves all of them, for both tensor
                                 // products.  Large batches take 2 poses per CTA and 4 rows at a time (the kernel is then bound by the
                                 // L2 stream of the 218 KB of weights per CTA pass).
+
+// -DDEDF_SCORE_TRACE (profiles/run_score_trace.py builds its own copy of the library): thread 0 of CTA 0 stamps clock64() at every
+// phase boundary of its first (pose, query-row) pass into a device array that dedf_score_trace() copies out.
+#ifdef DEDF_SCORE_TRACE
+__device__ long long g_score_trace[16];
+#define SCORE_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_score_trace[i] = clock64(); } while (0)
+#else
+#define SCORE_STAMP(i) do { } while (0)
+#endif
 
 constexpr int kScoreThreads = 384;   // 2 (NU) = 704 tasks in step 1 -> 2 rounds; 2 NY = 258 tasks in step 3 -> 1 round (256 threads: 3 and 2)
 
 // step 1 of score_tp for one (path, u): t[qq][j] += sum_v w[v] b[qq][v][j], KB consecutive v per call.  D2 = 2 l2 + 1 is a
 // compile-time constant (no predicated-off FMAs) and the KB x D2 operand values of a row are contiguous in shared memory: they
 // are fetched as float4s (one LDS per four FMAs instead of one per FMA).  Same summation order as a plain loop over v.
-template <int D2, int QB, int KB>
-__device__ __forceinline__ void score_s1_batch(const float* __restrict__ w, int m1, const float* __restrict__ b, int F, float (&acc)[QB][D2]) {
+// Weight accessor of score_tp_kernel.  The weights live in shared memory (resident variant) or in global memory; a plain pointer
+// that may be either compiles to GENERIC loads with 64-bit address arithmetic (four integer instructions per weight: step 3 spent
+// 560 cycles per batch of 8 weights that way, profiles/run_score_trace.py).  WPtr<true> is a 32-bit shared-memory address read with
+// ld.shared; WPtr<false> a global pointer.
+template <bool SM> struct WPtr;
+template <> struct WPtr<true> {
+    uint32_t a;
+    __device__ __forceinline__ float operator[](int i) const {
+        float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a + 4u * (uint32_t)i)); return v;
+    }
+    __device__ __forceinline__ WPtr operator+(int o) const { return WPtr{a + 4u * (uint32_t)o}; }
+};
+template <> struct WPtr<false> {
+    const float* p;
+    __device__ __forceinline__ float operator[](int i) const { return p[i]; }
+    __device__ __forceinline__ WPtr operator+(int o) const { return WPtr{p + o}; }
+};
+
+template <int D2, int QB, int KB, typename WP>
+__device__ __forceinline__ void score_s1_batch(WP w, int m1, const float* __restrict__ b, int F, float (&acc)[QB][D2]) {
     float wv[KB];
 #pragma unroll
-    for (int k = 0; k < KB; ++k) wv[k] = w[(size_t)k * m1];
+    for (int k = 0; k < KB; ++k) wv[k] = w[k * m1];
 #pragma unroll
     for (int qq = 0; qq < QB; ++qq) {
         float bb[KB * D2];
@@ -227,8 +272,8 @@ __device__ __forceinline__ void score_s1_batch(const float* __restrict__ w, int 
             for (int j = 0; j < D2; ++j) acc[qq][j] = fmaf(wv[k], bb[k * D2 + j], acc[qq][j]);
     }
 }
-template <int D2, int QB>
-__device__ __forceinline__ void score_s1_path(const float* __restrict__ w, int m1, int m2, const float* __restrict__ b, int F,
+template <int D2, int QB, typename WP>
+__device__ __forceinline__ void score_s1_path(WP w, int m1, int m2, const float* __restrict__ b, int F,
                                               float* __restrict__ tout, int TT) {
     float acc[QB][D2];
 #pragma unroll
@@ -237,8 +282,8 @@ __device__ __forceinline__ void score_s1_path(const float* __restrict__ w, int m
         for (int j = 0; j < D2; ++j) acc[qq][j] = 0.f;
     // the chain of dependent weight loads is what a small batch pays for: 8 in flight (4 for a tail; every mul is a multiple of 4)
     int v = 0;
-    for (; v + 8 <= m2; v += 8) score_s1_batch<D2, QB, 8>(w + (size_t)v * m1, m1, b + v * D2, F, acc);
-    for (; v < m2; v += 4) score_s1_batch<D2, QB, 4>(w + (size_t)v * m1, m1, b + v * D2, F, acc);
+    for (; v + 8 <= m2; v += 8) score_s1_batch<D2, QB, 8>(w + v * m1, m1, b + v * D2, F, acc);
+    for (; v < m2; v += 4) score_s1_batch<D2, QB, 4>(w + v * m1, m1, b + v * D2, F, acc);
 #pragma unroll
     for (int qq = 0; qq < QB; ++qq)
 #pragma unroll
@@ -252,6 +297,7 @@ template <int QB>
 __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kernel(ScoreArgs a, int pb, int w_smem) {
     extern __shared__ __align__(16) float sm[];
     __shared__ __align__(8) uint64_t wbar;
+    SCORE_STAMP(0);
     const int M0 = a.irr.m0, M1 = a.irr.m1, M2 = a.irr.m2, F = a.irr.dim();
     const int D0 = M0 + M1 + M2, D1 = M0 + 3 * M1 + 2 * M2;   // 112, 192 channels
     const int NV = a.n_vec, NY = 1 + 4 * NV;
@@ -278,28 +324,62 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
     const int NU = uoff[9];             // (path, u) pairs
     const int boff[3] = {0, M0, M0 + 3 * M1};   // offsets of l blocks in a feature vector
     // resident weights
-    const int nWd = woff[9], nWl1 = D1 * NV;
+    const int nWd = woff[9], nWl1 = D1 * NV, nWl0 = D0 * (1 + NV);
     float* sw = srd + 36 * pb;
     const float* Wd[2] = {a.Wd[0], a.Wd[1]};
     const float* Wl1[2] = {a.Wl1[0], a.Wl1[1]};
+    const float* Wl0[2] = {a.Wl0[0], a.Wl0[1]};
+    // w_smem = 2: the scalar linear layer's weights are resident too (step 3 read them from L2 in dependent batches of 8 rows:
+    // 9.6 k cycles of the 38 k a 128-pose denoise step spends after its PDL wait, profiles/run_score_trace.py)
     if (w_smem) {
         if (tid == 0) {
             mbar_init(&wbar, 1);
             mbar_init_fence();
-            mbar_expect_tx(&wbar, (uint32_t)(2 * (nWd + nWl1)) * 4u);
+            mbar_expect_tx(&wbar, (uint32_t)(2 * (nWd + nWl1 + (w_smem > 1 ? nWl0 : 0))) * 4u);
             for (int i = 0; i < 2; ++i) {
                 bulk_g2s_chunked(sw + i * nWd, a.Wd[i], (uint32_t)nWd * 4u, &wbar);
                 bulk_g2s_chunked(sw + 2 * nWd + i * nWl1, a.Wl1[i], (uint32_t)nWl1 * 4u, &wbar);
+                if (w_smem > 1) bulk_g2s_chunked(sw + 2 * (nWd + nWl1) + i * nWl0, a.Wl0[i], (uint32_t)nWl0 * 4u, &wbar);
             }
         }
-        for (int i = 0; i < 2; ++i) { Wd[i] = sw + i * nWd; Wl1[i] = sw + 2 * nWd + i * nWl1; }
+        for (int i = 0; i < 2; ++i) {
+            Wd[i] = sw + i * nWd; Wl1[i] = sw + 2 * nWd + i * nWl1;
+            if (w_smem > 1) Wl0[i] = sw + 2 * (nWd + nWl1) + i * nWl0;
+        }
     }
+    // Fused Langevin step: the noise of this CTA's first poses and the step's coefficients depend on (seed, pose, step) and the
+    // schedule only, so they are computed HERE, in the shadow of the previous kernels (Philox + Box-Muller + four square roots in
+    // fp64 on one thread were 5 k cycles of the kernel's serial tail).  Reading the step counter before the PDL wait is safe: it was
+    // written by the previous step's launch of this kernel, five launches back -- a kernel starts only after its predecessor
+    // passed ITS wait, i.e. after everything two or more launches back has completed.
+    __shared__ double s_z[8][6];
+    __shared__ LangevinCoef s_coef;
+    auto stage_noise = [&](int t0_, int step_) {      // threads 32 .. 32 + pb - 1: one pose each; thread 64: the coefficients
+        if (tid >= 32 && tid < 32 + pb && pb <= 8) {
+            const int t = t0_ + (tid - 32);
+            if (t < a.n_t && step_ < a.n_steps)
+                langevin_noise(a.noise ? a.noise + ((size_t)step_ * a.n_t + t) * 6 : nullptr, a.seed_dev ? *a.seed_dev : a.seed,
+                               (unsigned long long)t, (unsigned long long)step_, s_z[tid - 32]);
+        }
+        if (tid == 64 && step_ < a.n_steps) {
+            const double* row = a.sched + (size_t)step_ * 4;
+            s_coef = langevin_coef(row[0], a.ang_mult_d, a.lin_mult_d, row[1], row[2], row[3]);
+        }
+    };
+    if (a.T64) stage_noise((int)blockIdx.x * pb, *a.counter);
+    SCORE_STAMP(1);
     pdl_wait(); pdl_launch();     // PDL: see common.cuh
+    SCORE_STAMP(2);
     const int step_now = a.T64 ? *a.counter : 0;
     if (w_smem) { __syncthreads(); mbar_wait(&wbar, 0); }
+    SCORE_STAMP(3);
 
     for (int t0 = blockIdx.x * pb; t0 < a.n_t; t0 += gridDim.x * pb) {
     const int np = min(pb, a.n_t - t0);
+    if (a.T64 && t0 != (int)blockIdx.x * pb) {          // later passes of a persistent CTA: their noise, off the tail as well
+        __syncthreads();                                // (the previous pass's tail has read s_z)
+        stage_noise(t0, step_now);
+    }
     const int rows_total = np * a.n_q;  // (pose, query node) rows of this pass: consecutive nodes of qf_rot / key_f
     if (!a.qf_rot) {
         __syncthreads();                // (the previous pass is done with srd)
@@ -344,21 +424,27 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
             sa[i] = v; sb[i] = a.key_f[node * F + c];
         }
         __syncthreads();
+        SCORE_STAMP(4);
         // step 1: t_p[u][j] = sum_v W_p[u][v] b_{l2}[v][j] for both tensor products and both query nodes: one thread per
         // (which, path, u); consecutive threads take consecutive u (coalesced weight rows, 4 loads in flight), b is broadcast
-        for (int i = tid; i < 2 * NU; i += blockDim.x) {
-            const int which = i / NU, r = i % NU;
-            int p = 0;
-            while (r >= uoff[p + 1]) ++p;
-            const int u = r - uoff[p], l2 = l2s[p];
-            const float* w = Wd[which] + woff[p] + u;
-            const float* b = sb + boff[l2];
-            float* tout = st + (size_t)(which * QB) * TT + toff[p] + u * (2 * l2 + 1);
-            if (l2 == 0) score_s1_path<1, QB>(w, m1s[p], m2s[p], b, F, tout, TT);
-            else if (l2 == 1) score_s1_path<3, QB>(w, m1s[p], m2s[p], b, F, tout, TT);
-            else score_s1_path<5, QB>(w, m1s[p], m2s[p], b, F, tout, TT);
-        }
+        auto step1 = [&](auto wd0, auto wd1) {
+            for (int i = tid; i < 2 * NU; i += blockDim.x) {
+                const int which = i / NU, r = i % NU;
+                int p = 0;
+                while (r >= uoff[p + 1]) ++p;
+                const int u = r - uoff[p], l2 = l2s[p];
+                const auto w = (which ? wd1 : wd0) + (woff[p] + u);
+                const float* b = sb + boff[l2];
+                float* tout = st + (size_t)(which * QB) * TT + toff[p] + u * (2 * l2 + 1);
+                if (l2 == 0) score_s1_path<1, QB>(w, m1s[p], m2s[p], b, F, tout, TT);
+                else if (l2 == 1) score_s1_path<3, QB>(w, m1s[p], m2s[p], b, F, tout, TT);
+                else score_s1_path<5, QB>(w, m1s[p], m2s[p], b, F, tout, TT);
+            }
+        };
+        if (w_smem) step1(WPtr<true>{smem_u32(sw)}, WPtr<true>{smem_u32(sw + nWd)});
+        else step1(WPtr<false>{a.Wd[0]}, WPtr<false>{a.Wd[1]});
         __syncthreads();
+        SCORE_STAMP(5);
         // step 2: d[p][u][:] = cg(a[u], t_p[u])  ->  sd0 [112] , sd1 [192][3] in i_out order
         //   lo=0 block: [p0 (M0) | p3 (M1) | p7 (M2)] ; lo=1 block: [p1 (M0) | p2 (M1) | p4 (M1) | p5 (M1) | p6 (M2) | p8 (M2)]
         const int ntask = 2 * M0 + 4 * M1 + 3 * M2;
@@ -396,51 +482,104 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
             }
         }
         __syncthreads();
-        // step 3: linear  (D0 -> 1+NV scalars with bias ; D1 -> NV vectors), one thread per (which, output) for both query nodes
-        for (int i = tid; i < 2 * NY; i += blockDim.x) {
-            const int which = i / NY, o = i % NY;
-            float acc[QB];
-            const bool scalar = o < 1 + NV;
-            const int k3 = scalar ? 0 : (o - 1 - NV) % 3;
-            const int K = scalar ? D0 : D1;
-            const int ldw = scalar ? (1 + NV) : NV;
-            const float* W = scalar ? (a.Wl0[which] + o) : (Wl1[which] + (o - 1 - NV) / 3);
-            // activations of row qq: sd0[wq][D0] or the k3 plane of sd1[wq][3][D1]; 4 consecutive channels per LDS
-            const float* S = scalar ? (sd0 + (size_t)(which * QB) * D0) : (sd1 + (size_t)(which * QB) * 3 * D1 + k3 * D1);
-            const int lds = scalar ? D0 : 3 * D1;
+        SCORE_STAMP(6);
+        // step 3: linear  (D0 -> 1+NV scalars with bias ; D1 -> NV vectors).  One thread per (which, scalar output) and one per
+        // (which, vector CHANNEL): the three components of a vector output share their weight column, so the thread that owns the
+        // channel loads each weight once and every activation float4 is a warp-wide broadcast -- with one thread per component the
+        // phase was bound by shared-memory wavefronts (20 per warp and batch of 8 rows, three-way bank conflicts between the
+        // component planes: ~10 k cycles at QB = 2).  Scalar tasks sit in threads 0 .. 2 NS - 1, vector tasks start at a warp
+        // boundary (no warp runs both bodies).  Same summation order per output as before (K ascending).
+        auto step3 = [&](auto wl0_0, auto wl0_1, auto wl1_0, auto wl1_1) {
+        const int NS = 1 + NV, v0 = (2 * NS + 31) & ~31;
+        for (int i = tid; i < v0 + 2 * NV; i += blockDim.x) {
+            if (i < 2 * NS) {
+                const int which = i / NS, o = i % NS;
+                float acc[QB];
+                const auto W = (which ? wl0_1 : wl0_0) + o;
+                const float* S = sd0 + (size_t)(which * QB) * D0;
 #pragma unroll
-            for (int qq = 0; qq < QB; ++qq) acc[qq] = scalar ? a.bl[which][o] : 0.f;
-            int r = 0;
-            for (; r + 8 <= K; r += 8) {
-                float wv[8];
+                for (int qq = 0; qq < QB; ++qq) acc[qq] = a.bl[which][o];
+                int r = 0;
+                SCORE_STAMP(11);
+                for (; r + 8 <= D0; r += 8) {
+                    float wv[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) wv[k] = W[(size_t)(r + k) * ldw];
+                    for (int k = 0; k < 8; ++k) wv[k] = W[(r + k) * NS];
 #pragma unroll
-                for (int qq = 0; qq < QB; ++qq) {
-                    const float4 s0 = *reinterpret_cast<const float4*>(S + qq * lds + r);
-                    const float4 s1 = *reinterpret_cast<const float4*>(S + qq * lds + r + 4);
-                    float t = acc[qq];
-                    t = fmaf(s0.x, wv[0], t); t = fmaf(s0.y, wv[1], t); t = fmaf(s0.z, wv[2], t); t = fmaf(s0.w, wv[3], t);
-                    t = fmaf(s1.x, wv[4], t); t = fmaf(s1.y, wv[5], t); t = fmaf(s1.z, wv[6], t); t = fmaf(s1.w, wv[7], t);
-                    acc[qq] = t;
+                    for (int qq = 0; qq < QB; ++qq) {
+                        const float4 s0 = *reinterpret_cast<const float4*>(S + qq * D0 + r);
+                        const float4 s1 = *reinterpret_cast<const float4*>(S + qq * D0 + r + 4);
+                        float t = acc[qq];
+                        t = fmaf(s0.x, wv[0], t); t = fmaf(s0.y, wv[1], t); t = fmaf(s0.z, wv[2], t); t = fmaf(s0.w, wv[3], t);
+                        t = fmaf(s1.x, wv[4], t); t = fmaf(s1.y, wv[5], t); t = fmaf(s1.z, wv[6], t); t = fmaf(s1.w, wv[7], t);
+                        acc[qq] = t;
+                    }
                 }
-            }
-            for (; r < K; r += 4) {
-                float wv[4];
+                for (; r < D0; r += 4) {
+                    float wv[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) wv[k] = W[(size_t)(r + k) * ldw];
+                    for (int k = 0; k < 4; ++k) wv[k] = W[(r + k) * NS];
 #pragma unroll
-                for (int qq = 0; qq < QB; ++qq) {
-                    const float4 s0 = *reinterpret_cast<const float4*>(S + qq * lds + r);
-                    float t = acc[qq];
-                    t = fmaf(s0.x, wv[0], t); t = fmaf(s0.y, wv[1], t); t = fmaf(s0.z, wv[2], t); t = fmaf(s0.w, wv[3], t);
-                    acc[qq] = t;
+                    for (int qq = 0; qq < QB; ++qq) {
+                        const float4 s0 = *reinterpret_cast<const float4*>(S + qq * D0 + r);
+                        float t = acc[qq];
+                        t = fmaf(s0.x, wv[0], t); t = fmaf(s0.y, wv[1], t); t = fmaf(s0.z, wv[2], t); t = fmaf(s0.w, wv[3], t);
+                        acc[qq] = t;
+                    }
                 }
-            }
+                SCORE_STAMP(12);
 #pragma unroll
-            for (int qq = 0; qq < QB; ++qq) sy[(which * QB + qq) * NY + o] = acc[qq];
+                for (int qq = 0; qq < QB; ++qq) sy[(which * QB + qq) * NY + o] = acc[qq];
+            } else if (i >= v0) {
+                const int which = (i - v0) / NV, c = (i - v0) % NV;
+                float acc[QB][3];
+#pragma unroll
+                for (int qq = 0; qq < QB; ++qq) acc[qq][0] = acc[qq][1] = acc[qq][2] = 0.f;
+                const auto W = (which ? wl1_1 : wl1_0) + c;
+                const float* S = sd1 + (size_t)(which * QB) * 3 * D1;          // [qq][k3][D1]
+                int r = 0;
+                for (; r + 8 <= D1; r += 8) {
+                    float wv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) wv[k] = W[(r + k) * NV];
+#pragma unroll
+                    for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+                        for (int k3 = 0; k3 < 3; ++k3) {
+                            const float4 s0 = *reinterpret_cast<const float4*>(S + (qq * 3 + k3) * D1 + r);
+                            const float4 s1 = *reinterpret_cast<const float4*>(S + (qq * 3 + k3) * D1 + r + 4);
+                            float t = acc[qq][k3];
+                            t = fmaf(s0.x, wv[0], t); t = fmaf(s0.y, wv[1], t); t = fmaf(s0.z, wv[2], t); t = fmaf(s0.w, wv[3], t);
+                            t = fmaf(s1.x, wv[4], t); t = fmaf(s1.y, wv[5], t); t = fmaf(s1.z, wv[6], t); t = fmaf(s1.w, wv[7], t);
+                            acc[qq][k3] = t;
+                        }
+                }
+                for (; r < D1; r += 4) {
+                    float wv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) wv[k] = W[(r + k) * NV];
+#pragma unroll
+                    for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+                        for (int k3 = 0; k3 < 3; ++k3) {
+                            const float4 s0 = *reinterpret_cast<const float4*>(S + (qq * 3 + k3) * D1 + r);
+                            float t = acc[qq][k3];
+                            t = fmaf(s0.x, wv[0], t); t = fmaf(s0.y, wv[1], t); t = fmaf(s0.z, wv[2], t); t = fmaf(s0.w, wv[3], t);
+                            acc[qq][k3] = t;
+                        }
+                }
+#pragma unroll
+                for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+                    for (int k3 = 0; k3 < 3; ++k3) sy[(which * QB + qq) * NY + NS + 3 * c + k3] = acc[qq][k3];
+            }
         }
+        };
+        if (w_smem > 1) step3(WPtr<true>{smem_u32(Wl0[0])}, WPtr<true>{smem_u32(Wl0[1])}, WPtr<true>{smem_u32(Wl1[0])}, WPtr<true>{smem_u32(Wl1[1])});
+        else step3(WPtr<false>{Wl0[0]}, WPtr<false>{Wl0[1]}, WPtr<false>{Wl1[0]}, WPtr<false>{Wl1[1]});
+        SCORE_STAMP(10);
         __syncthreads();
+        SCORE_STAMP(7);
         // step 4: gate, mean over the NV vectors (drop the scalar)
         // 8 lanes per (product, row, component), each NV / 8 vectors apart, folded with shuffles (2 QB 3 8 is a multiple of 32:
         // whole warps enter or skip the loop)
@@ -456,6 +595,7 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
         }
     }
     __syncthreads();
+    SCORE_STAMP(8);
     if (tid < np) {
         const int t = t0 + tid;
         const float* T = a.Ts + (size_t)t * 7;
@@ -475,16 +615,21 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
         if (a.T64 && step_now < a.n_steps) {       // (a replay past the end of the schedule is a no-op, not an out-of-bounds row)
             // fused Langevin step of pose t (pose_update_kernel + cast_pose_kernel); every CTA read `step_now` before any
             // CTA can advance the counter (the last ticket holder does, below)
-            const double* row = a.sched + (size_t)step_now * 4;
             double* Td = a.T64 + (size_t)t * 7;
-            langevin_step(Td, ang, lin, a.noise ? a.noise + ((size_t)step_now * a.n_t + t) * 6 : nullptr,
-                          a.seed_dev ? *a.seed_dev : a.seed, (unsigned long long)t,
-                          (unsigned long long)step_now, row[0], a.ang_mult_d, a.lin_mult_d, row[1], row[2], row[3]);
+            if (pb <= 8) {
+                langevin_apply(Td, ang, lin, s_z[tid], s_coef);
+            } else {
+                const double* row = a.sched + (size_t)step_now * 4;
+                langevin_step(Td, ang, lin, a.noise ? a.noise + ((size_t)step_now * a.n_t + t) * 6 : nullptr,
+                              a.seed_dev ? *a.seed_dev : a.seed, (unsigned long long)t,
+                              (unsigned long long)step_now, row[0], a.ang_mult_d, a.lin_mult_d, row[1], row[2], row[3]);
+            }
             if (a.traj) for (int k = 0; k < 7; ++k) a.traj[((size_t)(step_now + 1) * a.n_t + t) * 7 + k] = Td[k];
             for (int k = 0; k < 7; ++k) a.T32[(size_t)t * 7 + k] = (float)Td[k];
         }
     }
     }   // poses of this CTA
+    SCORE_STAMP(9);
     if (a.T64) {
         __syncthreads();
         if (tid == 0) {
@@ -493,6 +638,14 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
         }
     }
 }
+
+#ifdef DEDF_SCORE_TRACE
+}  // namespace dedf
+extern "C" int dedf_score_trace(long long* host_out16) {
+    return cudaMemcpyFromSymbol(host_out16, dedf::g_score_trace, sizeof(long long) * 16) == cudaSuccess ? DEDF_OK : DEDF_ERR_LAUNCH;
+}
+namespace dedf {
+#endif
 
 // ---------------------------------------------------------------------------
 // pose update (float64)
@@ -637,11 +790,13 @@ static int launch_score_tp(ScoreArgs a, cudaStream_t stream) {
             return DEDF_OK;
         }
     }
-    const size_t smem = act + (w_smem ? wbytes : 0);
+    const size_t wl0_bytes = (size_t)2 * D0 * (1 + n_vec) * sizeof(float);
+    const bool wl0_smem = w_smem && act + wbytes + wl0_bytes <= 226 * 1024 && al16(a.Wl0[0]) && al16(a.Wl0[1]) && ((D0 * (1 + n_vec)) % 4 == 0);
+    const size_t smem = act + (w_smem ? wbytes : 0) + (wl0_smem ? wl0_bytes : 0);
     if (smem > 226 * 1024) return DEDF_ERR_UNSUPPORTED;
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(score_tp_kernel<kScoreQB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); done = true; }
-    if (w_smem) launch_pdl(score_tp_kernel<kScoreQB>, dim3(grid_for(n_t, pb, kNumSMs)), dim3(kScoreThreads), smem, stream, a, pb, 1);
+    if (w_smem) launch_pdl(score_tp_kernel<kScoreQB>, dim3(grid_for(n_t, pb, kNumSMs)), dim3(kScoreThreads), smem, stream, a, pb, wl0_smem ? 2 : 1);
     else launch_pdl(score_tp_kernel<kScoreQB>, dim3((n_t + pb - 1) / pb), dim3(256), smem, stream, a, pb, 0);
     DEDF_CHECK_LAUNCH();
     return DEDF_OK;
