@@ -654,6 +654,17 @@ struct ValueReduceArgs {
 
 constexpr int kVrChunk = 64;
 
+// -DDEDF_VR_TRACE (profiles/run_vr_trace.py builds its own copy of the library): thread 0 of CTA 0 stamps clock64() at the phase
+// boundaries of its FIRST destination into a device array that dedf_vr_trace() copies out.
+#ifdef DEDF_VR_TRACE
+__device__ long long g_vr_trace[24];
+#define VR_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && d == (int)blockIdx.x) g_vr_trace[i] = clock64(); } while (0)
+#define VR_STAMP0(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_vr_trace[i] = clock64(); } while (0)
+#else
+#define VR_STAMP(i) do { } while (0)
+#define VR_STAMP0(i) do { } while (0)
+#endif
+
 template <int G>
 __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(ValueReduceArgs a) {
     using D = Dtp<G>;
@@ -670,6 +681,7 @@ __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(Va
     __shared__ int s_cum[DEDF_MAX_SCALES + 1], s_beg[DEDF_MAX_SCALES];
     __shared__ __align__(8) uint64_t bar, vbar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    VR_STAMP0(0);
     const int cw = warp % NCW, hp = warp / NCW;
     const int ch0 = cw * 16 + (lane & 15), ch1 = cw * 8 + (lane & 7), ch2 = cw * 4 + (lane & 3);
     float w0[3], w1[6], w2[6];
@@ -690,7 +702,9 @@ __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(Va
         bulk_g2s_chunked(s_V + NV0, a.V1, NV1 * 4u, &vbar);
         bulk_g2s_chunked(s_V + NV0 + NV1, a.V2, NV2 * 4u, &vbar);
     }
+    VR_STAMP0(1);
     pdl_wait(); pdl_launch();     // PDL: see common.cuh
+    VR_STAMP0(2);
     __syncthreads();
     uint32_t ph = 0;
     bool v_pending = true;
@@ -710,40 +724,55 @@ __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(Va
 
     for (int d = blockIdx.x; d < a.n_dst; d += gridDim.x) {
         __syncthreads();                                           // previous destination done with every shared buffer
-        if (tid == 0) {
-            int c = 0;
-            for (int s = 0; s < a.n_seg; ++s) {
-                const int b = a.row_ptr[(size_t)s * a.n_dst + d], e = a.row_ptr[(size_t)s * a.n_dst + d + 1];
-                s_cum[s] = c; s_beg[s] = b; c += e - b;
+        if (warp == 0) {
+            // the segments' row pointers in parallel (lane = segment; one L2 round trip instead of a serial loop of 2 n_seg loads on
+            // one thread: 2.3 k of the ~20 k cycles a destination costs after the PDL wait, profiles/run_vr_trace.py), then a shuffle scan
+            int b = 0, e = 0;
+            if (lane < a.n_seg) { b = a.row_ptr[(size_t)lane * a.n_dst + d]; e = a.row_ptr[(size_t)lane * a.n_dst + d + 1]; }
+            const int len = e - b;
+            int cum = len;
+#pragma unroll
+            for (int o = 1; o < DEDF_MAX_SCALES; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, cum, o); if (lane >= o) cum += t; }
+            if (lane < a.n_seg) { s_cum[lane] = cum - len; s_beg[lane] = b; }
+            if (lane == a.n_seg - 1) s_cum[a.n_seg] = cum;
+            __syncwarp();
+            if (lane == 0) {
+                const int c = s_cum[a.n_seg];
+                if (c > 0) issue_chunk(0, min(CH, c));             // the first chunk flies while the statistics are computed
             }
-            s_cum[a.n_seg] = c;
-            if (c > 0) issue_chunk(0, min(CH, c));                 // the first chunk flies while the statistics are computed
         }
         if (tid < 4) s_sal[tid] = 0.f;
         __syncthreads();
+        VR_STAMP(3);
         const int deg = s_cum[a.n_seg];
         // ---- softmax statistics over all incoming edges: per-head max, log Z (logits straight from global / L2) ----
+        // thread t owns the flat edges t, t + NT, ... of the destination (all segments back to back); the first one -- the only one
+        // unless the destination has more than NT edges -- stays in registers for the second pass
+        auto flat_edge = [&](int f) { int s = 0; while (f >= s_cum[s + 1]) ++s; return (size_t)s_beg[s] + (f - s_cum[s]); };
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        for (int s = 0; s < a.n_seg; ++s) {
-            const int b = s_beg[s], e = b + (s_cum[s + 1] - s_cum[s]);
-            for (int i = b + tid; i < e; i += NT) {
-                const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
-                mx[0] = fmaxf(mx[0], l.x); mx[1] = fmaxf(mx[1], l.y); mx[2] = fmaxf(mx[2], l.z); mx[3] = fmaxf(mx[3], l.w);
-            }
+        float4 l_first = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < deg) {
+            l_first = *reinterpret_cast<const float4*>(a.logits + flat_edge(tid) * 4);
+            mx[0] = l_first.x; mx[1] = l_first.y; mx[2] = l_first.z; mx[3] = l_first.w;
+        }
+        for (int f = tid + NT; f < deg; f += NT) {
+            const float4 l = *reinterpret_cast<const float4*>(a.logits + flat_edge(f) * 4);
+            mx[0] = fmaxf(mx[0], l.x); mx[1] = fmaxf(mx[1], l.y); mx[2] = fmaxf(mx[2], l.z); mx[3] = fmaxf(mx[3], l.w);
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) mx[h] = warp_max(mx[h]);
         if (lane == 0) { s_red[warp][0] = mx[0]; s_red[warp][1] = mx[1]; s_red[warp][2] = mx[2]; s_red[warp][3] = mx[3]; }
         __syncthreads();
+        VR_STAMP(4);
 #pragma unroll
         for (int h = 0; h < 4; ++h) { float m = s_red[0][h]; for (int w = 1; w < NW; ++w) m = fmaxf(m, s_red[w][h]); mx[h] = m; }
         float sm[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int s = 0; s < a.n_seg; ++s) {
-            const int b = s_beg[s], e = b + (s_cum[s + 1] - s_cum[s]);
-            for (int i = b + tid; i < e; i += NT) {
-                const float4 l = *reinterpret_cast<const float4*>(a.logits + (size_t)i * 4);
-                sm[0] += __expf(l.x - mx[0]); sm[1] += __expf(l.y - mx[1]); sm[2] += __expf(l.z - mx[2]); sm[3] += __expf(l.w - mx[3]);
-            }
+        if (tid < deg) {
+            sm[0] = __expf(l_first.x - mx[0]); sm[1] = __expf(l_first.y - mx[1]); sm[2] = __expf(l_first.z - mx[2]); sm[3] = __expf(l_first.w - mx[3]);
+        }
+        for (int f = tid + NT; f < deg; f += NT) {
+            const float4 l = *reinterpret_cast<const float4*>(a.logits + flat_edge(f) * 4);
+            sm[0] += __expf(l.x - mx[0]); sm[1] += __expf(l.y - mx[1]); sm[2] += __expf(l.z - mx[2]); sm[3] += __expf(l.w - mx[3]);
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) sm[h] = warp_sum(sm[h]);
@@ -757,6 +786,7 @@ __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(Va
             for (int w = 0; w < NW; ++w) t += s_red[w][h];
             logZ[h] = (deg > 0) ? (logf(t + 1e-12f) + mx[h]) : 0.f;
         }
+        VR_STAMP(5);
 
         // ---- edge loop: accumulate alpha_h * dtp(v_e, sh_e, w) for this warp's channels and its two heads ----
         float acc0[2][9], acc1[2][20], acc2[2][22];
@@ -782,8 +812,10 @@ __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(Va
                 while (f >= s_cum[s + 1]) ++s;
                 s_sh[r * 12 + (i % 9)] = a.sh[((size_t)s_beg[s] + (f - s_cum[s])) * 9 + (i % 9)];
             }
+            VR_STAMP(6);
             mbar_wait(&bar, ph); ph ^= 1u;
             __syncthreads();
+            VR_STAMP(7);
             // logits -> alpha (x optional post factor), in place; per-head sums for the bias term (fixed order)
             if (tid < CH) {
                 float4 al = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -804,6 +836,7 @@ __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(Va
             }
             __syncthreads();
             if (tid < 4) s_sal[tid] += s_red[0][tid] + s_red[1][tid];      // CH = 64 = the first two warps
+            VR_STAMP(8);
             // packs of 8 edges
             for (int p0 = 0; p0 < n; p0 += 8) {
 #pragma unroll
@@ -844,6 +877,7 @@ __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(Va
                 }
             }
         }
+        VR_STAMP(9);
         // ---- fold the lanes that share a channel, write the 4 head copies of the reduced TP output to shared memory ----
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -888,8 +922,10 @@ __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(Va
                 Dh[D::C0_K12 + ch2] = acc2[h][13] * w2[3];
             }
         }
+        VR_STAMP(10);
         if (v_pending) { mbar_wait(&vbar, 0); v_pending = false; }
         __syncthreads();
+        VR_STAMP(11);
         // ---- linear layer, once per destination: out[c] = sum_k V_l[k, u] D_{head(u)}[k, m] (+ bias * sum alpha) ----
         for (int c = tid; c < D::F; c += NT) {
             int l, u, m;
@@ -911,8 +947,16 @@ __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(Va
             if (l == 0 && a.vb) acc = fmaf(a.vb[u], s_sal[h], acc);
             a.out[(size_t)d * D::F + c] = acc;
         }
+        VR_STAMP(12);
     }
 }
+#ifdef DEDF_VR_TRACE
+}  // namespace dedf
+extern "C" int dedf_vr_trace(long long* host_out24) {
+    return cudaMemcpyFromSymbol(host_out24, dedf::g_vr_trace, sizeof(long long) * 24) == cudaSuccess ? DEDF_OK : DEDF_ERR_LAUNCH;
+}
+namespace dedf {
+#endif
 
 // ---------------------------------------------------------------------------
 
