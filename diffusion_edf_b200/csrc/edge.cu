@@ -749,12 +749,25 @@ __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(Va
         // thread t owns the flat edges t, t + NT, ... of the destination (all segments back to back); the first one -- the only one
         // unless the destination has more than NT edges -- stays in registers for the second pass
         auto flat_edge = [&](int f) { int s = 0; while (f >= s_cum[s + 1]) ++s; return (size_t)s_beg[s] + (f - s_cum[s]); };
+        // the harmonics of the FIRST chunk are fetched here, together with the logits: their L2 round trip overlaps the statistics
+        // instead of following them (9-float rows are not 16-byte aligned: plain loads)
+        constexpr int SHN = (CH * 9 + NT - 1) / NT;
+        const int n_first = min(CH, deg);
+        float shv[SHN];
+#pragma unroll
+        for (int k = 0; k < SHN; ++k) {
+            const int i = tid + k * NT;
+            shv[k] = (i < n_first * 9) ? a.sh[flat_edge(i / 9) * 9 + (i % 9)] : 0.f;
+        }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         float4 l_first = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tid < deg) {
-            l_first = *reinterpret_cast<const float4*>(a.logits + flat_edge(tid) * 4);
-            mx[0] = l_first.x; mx[1] = l_first.y; mx[2] = l_first.z; mx[3] = l_first.w;
+        if (tid < deg) l_first = *reinterpret_cast<const float4*>(a.logits + flat_edge(tid) * 4);
+#pragma unroll
+        for (int k = 0; k < SHN; ++k) {
+            const int i = tid + k * NT;
+            if (i < n_first * 9) s_sh[(i / 9) * 12 + (i % 9)] = shv[k];
         }
+        if (tid < deg) { mx[0] = l_first.x; mx[1] = l_first.y; mx[2] = l_first.z; mx[3] = l_first.w; }
         for (int f = tid + NT; f < deg; f += NT) {
             const float4 l = *reinterpret_cast<const float4*>(a.logits + flat_edge(f) * 4);
             mx[0] = fmaxf(mx[0], l.x); mx[1] = fmaxf(mx[1], l.y); mx[2] = fmaxf(mx[2], l.z); mx[3] = fmaxf(mx[3], l.w);
@@ -805,8 +818,8 @@ __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(Va
                 __syncthreads();                                   // previous chunk fully consumed
                 if (tid == 0) issue_chunk(f0, n);
             }
-            // harmonics of the chunk (9-float rows are not 16-byte aligned: plain loads), per segment piece
-            for (int i = tid; i < n * 9; i += NT) {
+            // harmonics of the later chunks, per segment piece (the first chunk's were staged with the statistics)
+            for (int i = tid; f0 > 0 && i < n * 9; i += NT) {
                 const int r = i / 9, f = f0 + r;
                 int s = 0;
                 while (f >= s_cum[s + 1]) ++s;
@@ -927,25 +940,35 @@ __global__ void __launch_bounds__(G * 8, G == 16 ? 3 : 1) value_reduce_kernel(Va
         __syncthreads();
         VR_STAMP(11);
         // ---- linear layer, once per destination: out[c] = sum_k V_l[k, u] D_{head(u)}[k, m] (+ bias * sum alpha) ----
-        for (int c = tid; c < D::F; c += NT) {
+        // One thread per (l, m, channel PAIR u, u + 1): the two outputs read the same reduced TP value D[k, m] (same head: the heads'
+        // channel ranges are even) and adjacent weights V[k, u], V[k, u + 1] -- one LDS.64 + one LDS.32 per two FMAs instead of four
+        // LDS.32 (the phase is bound by shared-memory wavefronts).  Same products in the same order per output as before.
+        constexpr int P0 = D::M0 / 2, P1 = 3 * (D::M1 / 2), P2 = 5 * (D::M2 / 2);
+        static_assert((D::M0 / 4) % 2 == 0 && (D::M1 / 4) % 2 == 0 && (D::M2 / 4) % 2 == 0, "channel pairs inside one head");
+        for (int t = tid; t < P0 + P1 + P2; t += NT) {
             int l, u, m;
-            if (c < D::M0) { l = 0; u = c; m = 0; }
-            else if (c < D::M0 + 3 * D::M1) { l = 1; u = (c - D::M0) / 3; m = (c - D::M0) % 3; }
-            else { l = 2; u = (c - D::M0 - 3 * D::M1) / 5; m = (c - D::M0 - 3 * D::M1) % 5; }
+            if (t < P0) { l = 0; u = 2 * t; m = 0; }
+            else if (t < P0 + P1) { l = 1; u = 2 * ((t - P0) / 3); m = (t - P0) % 3; }
+            else { l = 2; u = 2 * ((t - P0 - P1) / 5); m = (t - P0 - P1) % 5; }
             const int ML = (l == 0) ? D::M0 : (l == 1) ? D::M1 : D::M2;
             const int KL = (l == 0) ? D::D0 : (l == 1) ? D::D1 : D::D2;
             const int dd = 2 * l + 1;
             const int h = u / (ML / 4);
             const float* V = s_V + ((l == 0) ? 0 : (l == 1) ? NV0 : NV0 + NV1) + u;
             const float* Dl = s_D + (size_t)h * D::FOUT + ((l == 0) ? 0 : (l == 1) ? B1 : B2) + m;
-            float acc = 0.f, accb = 0.f;
+            float acc0 = 0.f, accb0 = 0.f, acc1 = 0.f, accb1 = 0.f;
             for (int k = 0; k < KL; k += 4) {                      // every D_l is a multiple of 4
-                acc = fmaf(V[k * ML], Dl[k * dd], acc); accb = fmaf(V[(k + 1) * ML], Dl[(k + 1) * dd], accb);
-                acc = fmaf(V[(k + 2) * ML], Dl[(k + 2) * dd], acc); accb = fmaf(V[(k + 3) * ML], Dl[(k + 3) * dd], accb);
+                const float2 v0 = *reinterpret_cast<const float2*>(V + k * ML), v1 = *reinterpret_cast<const float2*>(V + (k + 1) * ML);
+                const float2 v2 = *reinterpret_cast<const float2*>(V + (k + 2) * ML), v3 = *reinterpret_cast<const float2*>(V + (k + 3) * ML);
+                const float d0 = Dl[k * dd], d1 = Dl[(k + 1) * dd], d2 = Dl[(k + 2) * dd], d3 = Dl[(k + 3) * dd];
+                acc0 = fmaf(v0.x, d0, acc0); accb0 = fmaf(v1.x, d1, accb0); acc0 = fmaf(v2.x, d2, acc0); accb0 = fmaf(v3.x, d3, accb0);
+                acc1 = fmaf(v0.y, d0, acc1); accb1 = fmaf(v1.y, d1, accb1); acc1 = fmaf(v2.y, d2, acc1); accb1 = fmaf(v3.y, d3, accb1);
             }
-            acc += accb;
-            if (l == 0 && a.vb) acc = fmaf(a.vb[u], s_sal[h], acc);
-            a.out[(size_t)d * D::F + c] = acc;
+            acc0 += accb0; acc1 += accb1;
+            if (l == 0 && a.vb) { acc0 = fmaf(a.vb[u], s_sal[h], acc0); acc1 = fmaf(a.vb[u + 1], s_sal[h], acc1); }
+            const int c = ((l == 0) ? 0 : (l == 1) ? D::M0 : D::M0 + 3 * D::M1) + u * dd + m;
+            a.out[(size_t)d * D::F + c] = acc0;
+            a.out[(size_t)d * D::F + c + dd] = acc1;
         }
         VR_STAMP(12);
     }
