@@ -319,3 +319,43 @@ def test_ctypes_signatures_have_the_headers_arity():
         assert fn.argtypes is not None and len(fn.argtypes) == arity, f"{name}: header has {arity} parameters, ctypes {None if fn.argtypes is None else len(fn.argtypes)}"
         n += 1
     assert n >= 16
+
+
+def test_tensor_core_weight_packs_round_trip():
+    """Host side of the tcgen05 kernels' B operands (layers.pack_tc / pack_tp_act_tc): un-packing the documented layouts must give
+    back the weights -- exactly hi + lo for the tf32 split, to 2^-21 relative for the fp16 split (hi = fp16(w), lo = fp16(w - hi));
+    the fp16 pack has the byte size of the tf32 one per K chunk PAIR (two 8-wide chunks -> one 16-wide chunk)."""
+    import torch
+    from diffusion_edf_b200 import layers
+    torch.manual_seed(0)
+    for K, N in ((64, 128), (128, 480), (32, 16)):
+        W = torch.randn(K, N) * 0.3
+        nb = (N + 255) // 256
+        nbw = N // nb
+        t32 = layers.pack_tc(W)
+        v = t32.view(nb, K // 8, 2, 2, nbw, 4)                                 # [nb, kc, part, j, n, r]
+        hi = v[:, :, 0].permute(1, 2, 4, 0, 3).reshape(K, N)                   # [kc, j, r, nb, n] -> (K, N)
+        lo = v[:, :, 1].permute(1, 2, 4, 0, 3).reshape(K, N)
+        assert torch.equal(hi + lo, W) and torch.equal(hi.view(torch.int32) & 8191, torch.zeros(K, N, dtype=torch.int32))
+        t16 = layers.pack_tc(W, f16=True)
+        assert t16.dtype == torch.float32 and t16.numel() * 2 == t32.numel()
+        h = t16.view(torch.float16).view(nb, K // 16, 2, 2, nbw, 8)
+        hi16 = h[:, :, 0].permute(1, 2, 4, 0, 3).reshape(K, N).float()
+        lo16 = h[:, :, 1].permute(1, 2, 4, 0, 3).reshape(K, N).float()
+        assert torch.equal(hi16, W.half().float())
+        assert ((hi16 + lo16 - W).abs() <= W.abs() * 2.0 ** -21 + 6e-8).all()
+    # attention block: the fp16 pack interleaves chunk pairs (four halves of the even chunk, four of the odd one per 16-byte group)
+    for G in (16, 32):
+        M0, M1, M2 = 2 * G, G, G // 2
+        d0, d1, d2 = M0 + M1 + M2, M0 + 3 * M1 + 2 * M2, M0 + 2 * M1 + 3 * M2
+        W0, W1, W2 = torch.randn(d0, M0 + d0) * 0.2, torch.randn(d1, M1) * 0.2, torch.randn(d2, M2) * 0.2
+        p32 = layers.pack_tp_act_tc(G, W0, W1, W2)
+        p16 = layers.pack_tp_act_tc(G, W0, W1, W2, f16=True)
+        nch = M0 // 8
+        c32 = p32.view(nch, 2, -1, 4)                                          # [chunk, hi / lo, K-group x N, 4]
+        c16 = p16.view(torch.float16).view(nch // 2, 2, -1, 8).float()         # [chunk pair, hi / lo, K-group x N, 8]
+        assert c16.shape[2] == c32.shape[2]
+        full32 = c32[:, 0] + c32[:, 1]                                         # (chunk, groups, 4): the weights themselves
+        full16 = c16[:, 0] + c16[:, 1]
+        pair = torch.cat([full32[0::2], full32[1::2]], dim=-1)                 # even chunk | odd chunk
+        assert ((full16 - pair).abs() <= pair.abs() * 2.0 ** -21 + 6e-8).all()
