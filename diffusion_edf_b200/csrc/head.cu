@@ -366,25 +366,10 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
             s_coef = langevin_coef(row[0], a.ang_mult_d, a.lin_mult_d, row[1], row[2], row[3]);
         }
     };
-    if (a.T64) stage_noise((int)blockIdx.x * pb, *a.counter);
-    SCORE_STAMP(1);
-    pdl_wait(); pdl_launch();     // PDL: see common.cuh
-    SCORE_STAMP(2);
-    const int step_now = a.T64 ? *a.counter : 0;
-    if (w_smem) { __syncthreads(); mbar_wait(&wbar, 0); }
-    SCORE_STAMP(3);
-
-    for (int t0 = blockIdx.x * pb; t0 < a.n_t; t0 += gridDim.x * pb) {
-    const int np = min(pb, a.n_t - t0);
-    if (a.T64 && t0 != (int)blockIdx.x * pb) {          // later passes of a persistent CTA: their noise, off the tail as well
-        __syncthreads();                                // (the previous pass's tail has read s_z)
-        stage_noise(t0, step_now);
-    }
-    const int rows_total = np * a.n_q;  // (pose, query node) rows of this pass: consecutive nodes of qf_rot / key_f
-    if (!a.qf_rot) {
-        __syncthreads();                // (the previous pass is done with srd)
-        if (tid < np) {                 // R(q / |q|) and D^2 from R, exactly as query_transform_kernel
-            const float* T = a.Ts + (size_t)(t0 + tid) * 7;
+    // R(q / |q|) and D^2 from R of the poses of a pass, exactly as query_transform_kernel
+    auto compute_srd = [&](int t0_, int np_) {
+        if (tid < np_) {
+            const float* T = a.Ts + (size_t)(t0_ + tid) * 7;
             const float nrm = sqrtf(T[0] * T[0] + T[1] * T[1] + T[2] * T[2] + T[3] * T[3]);
             float qn[4] = {T[0] / nrm, T[1] / nrm, T[2] / nrm, T[3] / nrm};
             float R[9]; quat_to_matrix<float>(qn, R);
@@ -393,17 +378,15 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
             for (int i = 0; i < 9; ++i) o[i] = R[i];
             for (int i = 0; i < 25; ++i) o[9 + i] = D[i];
         }
-    }
-    for (int q0 = 0; q0 < rows_total; q0 += QB) {
-        const int nq = min(QB, rows_total - q0);
-        __syncthreads();
+    };
+    // first operand of the rows [q0, q0 + QB) of a pass: D(q) psi (rotated on the fly, or the caller's rotated copy)
+    auto stage_a = [&](int t0_, int q0_, int nq_) {
         for (int i = tid; i < QB * F; i += blockDim.x) {
             const int qq = i / F, c = i % F;
-            const int row = q0 + min(qq, nq - 1);
-            const size_t node = (size_t)t0 * a.n_q + row;
+            const int row = q0_ + min(qq, nq_ - 1);
             float v;
             if (a.qf_rot) {
-                v = a.qf_rot[node * F + c];
+                v = a.qf_rot[((size_t)t0_ * a.n_q + row) * F + c];
             } else {
                 const float* f = a.qf + (size_t)(row % a.n_q) * F;
                 const float* sR = srd + (row / a.n_q) * 36;
@@ -421,7 +404,48 @@ __global__ void __launch_bounds__(kScoreThreads, QB >= 8 ? 2 : 1) score_tp_kerne
                     for (int j = 0; j < 5; ++j) v = fmaf(sD2[m * 5 + j], fu[j], v);
                 }
             }
-            sa[i] = v; sb[i] = a.key_f[node * F + c];
+            sa[i] = v;
+        }
+    };
+    // Denoise step: the poses (written by the previous step's launch of this kernel) and the static query features are final two
+    // or more launches back, so the Wigner matrices and the rotated query features of the CTA's first rows are staged before the
+    // PDL wait as well; after it only the field output (the previous kernel's) has to be fetched.
+    const int t0_first = (int)blockIdx.x * pb;
+    const bool early = a.T64 != nullptr && a.qf_rot == nullptr && t0_first < a.n_t;
+    if (a.T64) stage_noise(t0_first, *a.counter);
+    if (early) {
+        const int np_f = min(pb, a.n_t - t0_first);
+        compute_srd(t0_first, np_f);
+        __syncthreads();
+        stage_a(t0_first, 0, min(QB, np_f * a.n_q));
+    }
+    SCORE_STAMP(1);
+    pdl_wait(); pdl_launch();     // PDL: see common.cuh
+    SCORE_STAMP(2);
+    const int step_now = a.T64 ? *a.counter : 0;
+    if (w_smem) { __syncthreads(); mbar_wait(&wbar, 0); }
+    SCORE_STAMP(3);
+
+    for (int t0 = blockIdx.x * pb; t0 < a.n_t; t0 += gridDim.x * pb) {
+    const int np = min(pb, a.n_t - t0);
+    if (a.T64 && t0 != (int)blockIdx.x * pb) {          // later passes of a persistent CTA: their noise, off the tail as well
+        __syncthreads();                                // (the previous pass's tail has read s_z)
+        stage_noise(t0, step_now);
+    }
+    const int rows_total = np * a.n_q;  // (pose, query node) rows of this pass: consecutive nodes of qf_rot / key_f
+    const bool pre = early && t0 == t0_first;       // this pass's Wigner matrices and first rows were staged before the wait
+    if (!a.qf_rot && !pre) {
+        __syncthreads();                // (the previous pass is done with srd)
+        compute_srd(t0, np);
+    }
+    for (int q0 = 0; q0 < rows_total; q0 += QB) {
+        const int nq = min(QB, rows_total - q0);
+        __syncthreads();
+        if (!(pre && q0 == 0)) stage_a(t0, q0, nq);
+        for (int i = tid; i < QB * F; i += blockDim.x) {
+            const int qq = i / F, c = i % F;
+            const int row = q0 + min(qq, nq - 1);
+            sb[i] = a.key_f[((size_t)t0 * a.n_q + row) * F + c];
         }
         __syncthreads();
         SCORE_STAMP(4);
